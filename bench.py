@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native AIR hot path (contract: see README / DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|st] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `--workload st` is BASELINE.json configs[1] (Spatial
+Transformer fwd/bwd microbench, B = 65536); `--workload train` is configs[2]/[3] (full
+AIR train step, per-GPU batch 4096, weak scaling: global batch = 4096 * N, 32768 at N = 8).
+`--impl reference` times the CPU oracle (the reference restated op for op in torch; TF 1.3
+cannot run here) on the host cores -- a reported baseline, not the target.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0, period_ms=100):
+        self.index, self.period_ms, self.rows, self.proc = index, period_ms, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(self.period_ms / 1000.0 * 1.5)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    return rank, local, world
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------
+# ST microbench (BASELINE.json configs[1]); algorithmic bytes per image from SURVEY.md 8(d)
+# ------------------------------------------------------------------------------------------
+ST_BYTES = {"crop_fwd": 13160, "crop_bwd": 13184, "writeback_canvas_fwd": 23168, "writeback_canvas_bwd": 16332}
+
+
+def st_inputs(B, dev, seed=1):
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    r = lambda *s: torch.rand(*s, device=dev, generator=g)
+    s = r(B) * 0.6 + 0.3
+    xy = r(B, 2) - 0.5
+    th = torch.zeros(B, 6, device=dev)
+    th[:, 0] = s; th[:, 4] = s; th[:, 2] = xy[:, 0]; th[:, 5] = xy[:, 1]
+    thi = torch.zeros(B, 6, device=dev)
+    thi[:, 0] = 1.0 / s; thi[:, 4] = 1.0 / s; thi[:, 2] = -xy[:, 0] / s; thi[:, 5] = -xy[:, 1] / s
+    canv = (r(B, 2500) > 0.9).float() * r(B, 2500)       # sparse "digit" canvases
+    return dict(U=canv.contiguous(), th=th, thi=thi, win=r(B, 784), z=r(B), stop=(r(B) > 0.7).float() * 1.5,
+                canvas=r(B, 2500), dwin=torch.randn(B, 784, device=dev, generator=g),
+                dcanvas=torch.randn(B, 2500, device=dev, generator=g))
+
+
+def st_kernels(d, B):
+    """name -> zero-arg launcher through the C ABI (device-resident inputs)."""
+    import torch
+    import air_b200 as ab
+    c = ab._cabi
+    L = c.lib()
+    dev = d["U"].device
+    out_win = torch.empty(B, 784, device=dev)
+    dth = torch.empty(B, 6, device=dev)
+    canvas_out = torch.empty(B, 2500, device=dev)
+    dwin = torch.empty(B, 784, device=dev)
+    dz = torch.empty(B, device=dev)
+    p = c.ptr
+
+    def crop_fwd():
+        c.check(L.air_st_forward(p(d["U"]), p(d["th"]), p(out_win), B, 50, 50, 1, 28, 28, c.stream()), "crop_fwd")
+
+    def crop_bwd():
+        c.check(L.air_st_backward(p(d["U"]), p(d["th"]), p(d["dwin"]), None, p(dth), B, 50, 50, 1, 28, 28, c.stream()),
+                "crop_bwd")
+
+    def wb_fwd():
+        c.check(L.air_st_writeback_canvas_fwd(p(d["win"]), p(d["thi"]), p(d["z"]), p(d["stop"]), 0.99, p(d["canvas"]),
+                                              p(canvas_out), B, 28, 28, 50, 50, c.stream()), "wb_fwd")
+
+    def wb_bwd():
+        c.check(L.air_st_writeback_canvas_bwd(p(d["win"]), p(d["thi"]), p(d["z"]), p(d["stop"]), 0.99, p(d["dcanvas"]),
+                                              p(dwin), p(dth), p(dz), B, 28, 28, 50, 50, c.stream()), "wb_bwd")
+
+    return {"crop_fwd": crop_fwd, "crop_bwd": crop_bwd, "writeback_canvas_fwd": wb_fwd, "writeback_canvas_bwd": wb_bwd}
+
+
+def time_launches(fn, steps, warmup):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_st(args, rank, world, peaks):
+    import torch
+    import air_b200 as ab
+    B = args.batch or 65536
+    dev = torch.device("cuda")
+    d = st_inputs(B, dev)
+    ks = st_kernels(d, B)
+    res = {}
+    n0 = ab.launch_count()
+    barrier(world)
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        t_all0 = time.time()
+        for name, fn in ks.items():
+            ms = max_over_ranks(time_launches(fn, args.steps, args.warmup), world)
+            gbs = B * ST_BYTES[name] / (ms * 1e-3) / 1e9
+            res[name] = {"ms": round(ms, 5), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+                         "bytes_per_image": ST_BYTES[name]}
+        barrier(world)
+        _ = time.time() - t_all0
+    launches = ab.launch_count() - n0
+    # end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    U_h = d["U"].cpu().pin_memory(); th_h = d["th"].cpu().pin_memory()
+    out_h = torch.empty(B, 28, 28, 1).pin_memory()
+
+    def e2e_step():
+        U = U_h.to(dev, non_blocking=True).reshape(B, 50, 50, 1)
+        th = th_h.to(dev, non_blocking=True)
+        out_h.copy_(ab.transformer(U, th, (28, 28)), non_blocking=True)
+
+    e2e_ms = max_over_ranks(time_launches(e2e_step, max(3, args.steps // 5), 3), world)
+    head = res["crop_fwd"]
+    line = {
+        "metric": "ST bilinear sample GB/s (crop 50x50->28x28 fwd)", "value": head["GBps"] * world, "unit": "GB/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "st_microbench configs[1]: ST fwd/bwd 50x50<->28x28, batch %d per GPU, fp32" % B,
+                   "batch_per_gpu": B, "l2": "working set (>= 860 MB per launch) >> 126 MB L2, no flush needed"},
+        "roofline": {"bound": "hbm", "achieved": head["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": head["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["source"],
+                     "kernel": "st_fwd_staged<50,50,28,28,4,false>"},
+        "kernels": res,
+        "e2e": {"value": round(B * ST_BYTES["crop_fwd"] / (e2e_ms * 1e-3) / 1e9 * world, 2), "unit": "GB/s",
+                "h2d_bytes_per_step": int(U_h.numel() * 4 + th_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
+                "ms_per_step": round(e2e_ms, 4)},
+        "gpu_launches": int(launches),
+        "clocks": cs.summary(),
+    }
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_baseline_st()
+    return line
+
+
+def cpu_baseline_st(B=4096):
+    """The C oracle's ST forward (crop) timed on the host, scalar, 1 thread."""
+    import numpy as np
+    from oracle import c_oracle as C
+    rng = np.random.RandomState(1)
+    U = rng.rand(B, 50, 50, 1).astype(np.float32)
+    th = np.zeros((B, 2, 3), np.float32)
+    th[:, 0, 0] = th[:, 1, 1] = rng.uniform(0.3, 0.9, B)
+    th[:, :, 2] = rng.uniform(-0.5, 0.5, (B, 2))
+    C.st_forward(U[:64], th[:64], (28, 28))
+    t0 = time.time()
+    reps = 0
+    while time.time() - t0 < 5.0:
+        C.st_forward(U, th, (28, 28))
+        reps += 1
+    dt = (time.time() - t0) / reps
+    return {"value": round(B * ST_BYTES["crop_fwd"] / dt / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/st_oracle.c crop fwd, batch {B}, {reps} reps (~5 s)"}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=["train", "st", "infer"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 4096 train, 65536 st)")
+    ap.add_argument("--gemm", default=None, help="GEMM mode for the train workload")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    peaks = measured_peaks()
+
+    try:
+        import bench_train  # noqa: F401  (added with the full model)
+        have_train = True
+    except ImportError:
+        have_train = False
+    if args.workload is None:
+        args.workload = "train" if have_train else "st"
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return 0
+        if have_train and args.workload != "st":
+            line = bench_train.run_reference(args, peaks)
+        else:
+            cb = cpu_baseline_st()
+            line = {"impl": "reference", "metric": "ST bilinear sample GB/s (crop 50x50->28x28 fwd)", "value": cb["value"],
+                    "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                    "higher_is_better": True, "cpu_baseline": cb, "config": {"workload": "st_microbench configs[1]"},
+                    "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    rank, local, world = dist_setup(args.gpus)
+    if args.workload == "st":
+        line = run_st(args, rank, world, peaks)
+    else:
+        line = bench_train.run(args, rank, world, peaks)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,201 @@
+"""CPU tests pinning the oracle (no GPU): golden vectors, cross-restatement agreement,
+known-answer cases, fp64 finite differences.  Parity against TensorFlow itself is
+UNPINNED (TF cannot run here; see oracle/air_oracle.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import air_oracle as O
+from oracle import c_oracle as C
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_golden_st(golden_dir):
+    g = _g(golden_dir, "st.npz")
+    for impl in ("torch", "c"):
+        f = (lambda U, t, s: O.transformer(torch.from_numpy(U), torch.from_numpy(t), s).numpy()) if impl == "torch" \
+            else C.st_forward
+        assert np.array_equal(f(g["U"], g["theta"], (28, 28)), g["crop"])
+        assert np.array_equal(f(g["window"], g["theta_inv"], (50, 50)), g["back"])
+        assert np.array_equal(f(g["Ug"], g["thg"], (7, 9)), g["outg"])
+    out = C.canvas_update(g["canvas"], g["back"].reshape(-1, 2500), g["z"], g["stop"], 0.99)
+    assert np.array_equal(out, g["canvas_out"])
+    # rows with stop >= thr are untouched (0.99 itself is NOT < 0.99)
+    dead = g["stop"] >= np.float32(0.99)
+    assert dead.sum() == 3 and np.array_equal(out[dead], g["canvas"][dead])
+
+
+def test_golden_concrete(golden_dir):
+    g = _g(golden_dir, "concrete.npz")
+    for train in (0, 1):
+        out = C.concrete_step(g["log_odds"], g["u"], g["stop_prev"], g["loss_prev"], g["digits_prev"],
+                              float(g["prior"]), float(g["temperature"]), float(g["thr"]), train)
+        for k, v in out.items():
+            assert np.array_equal(v, g[f"{k}_train{train}"]), k
+    # torch restatement agrees with the C one to float rounding of log/exp
+    lo, u = torch.from_numpy(g["log_odds"]), torch.from_numpy(g["u"])
+    y = O.concrete_binary_pre_sigmoid_sample(lo, 1.0, u)
+    np.testing.assert_allclose(y.numpy(), g["y_train1"], rtol=2e-6, atol=2e-6)
+    kl = O.concrete_binary_kl_mc_sample(y, float(g["prior"]), 1.0, lo, 1.0)
+    np.testing.assert_allclose(kl.numpy(), g["kl_train1"], rtol=1e-5, atol=2e-6)
+
+
+def test_golden_model(golden_dir):
+    g = _g(golden_dir, "model_b8.npz")
+    imgs, cnt = O.synthetic_canvases(8, seed=0)
+    for train in (True, False):
+        m = O.AIROracle(annealing_schedules=O.DEFAULT_ANNEALING, train=train, seed=0)
+        m.global_step = 2000
+        out = m.forward(imgs, cnt, O.make_noise(0, 3, 8))
+        tag = "train" if train else "test"
+        assert np.array_equal(out["rec_num_digits"].numpy(), g[f"{tag}_rec_num_digits"])
+        assert np.array_equal(out["stop_masks"].numpy(), g[f"{tag}_stop_masks"])
+        assert int(out["executed_steps"]) == int(g[f"{tag}_executed_steps"])
+        # same machine + same BLAS gives bit equality; allow last-bit BLAS differences elsewhere
+        np.testing.assert_allclose(out["loss"].numpy(), g[f"{tag}_loss"], rtol=1e-5)
+        np.testing.assert_allclose(out["rec_scales"].numpy(), g[f"{tag}_rec_scales"], rtol=1e-5, atol=1e-6)
+
+
+def test_identity_theta_is_1001_shrink():
+    """Identity theta does NOT reproduce U: (W - 1.001) shrink, SURVEY 8a-2."""
+    torch.manual_seed(0)
+    U = torch.rand(2, 50, 50, 1)
+    th = torch.tensor([[1.0, 0, 0, 0, 1.0, 0]]).repeat(2, 1)
+    out = O.transformer(U, th, (50, 50))
+    err = (out - U).abs().max().item()
+    assert 1e-4 < err < 3e-3
+    assert torch.equal(out[:, 0, 0], U[:, 0, 0])  # the (-1,-1) corner is exact
+
+
+def test_out_of_range_residue_semantics():
+    """Both axes clipped -> exactly 0; one axis clipped -> tiny rounding residue (hard part 1)."""
+    U = torch.ones(1, 28, 28, 1)
+    s = 0.5
+    thi = torch.tensor([[1 / s, 0, 0.0, 0, 1 / s, 0.0]])
+    out = O.transformer(U, thi, (50, 50))[0, :, :, 0]
+    assert out[0, 0].item() == 0.0 and out[49, 49].item() == 0.0
+    assert abs(out[25, 25].item() - 1.0) < 1e-5
+    edge = out[25, 0].abs().item()  # x clipped, y inside
+    assert edge < 1e-5
+
+
+def test_crop_writeback_roundtrip():
+    """writeback(crop(img)) reproduces a smooth image inside the attended window."""
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, 50), torch.linspace(0, 1, 50), indexing="ij")
+    img = (0.5 + 0.5 * torch.sin(3 * xx) * torch.cos(2 * yy)).reshape(1, 50, 50, 1)
+    s, x, y = 0.6, 0.1, -0.2
+    th = torch.tensor([[s, 0, x, 0, s, y]])
+    thi = torch.tensor([[1 / s, 0, -x / s, 0, 1 / s, -y / s]])
+    back = O.transformer(O.transformer(img, th, (28, 28)), thi, (50, 50))
+    c = slice(18, 28)
+    assert (back[0, c, 22:32, 0] - img[0, c, 22:32, 0]).abs().max() < 0.02
+
+
+def test_st_gradcheck_fp64():
+    torch.manual_seed(1)
+    U = torch.rand(2, 9, 8, 2, dtype=torch.float64, requires_grad=True)
+    th = (torch.tensor([[0.7, 0.1, 0.05, -0.1, 0.8, -0.03]], dtype=torch.float64).repeat(2, 1)
+          + 0.01 * torch.randn(2, 6, dtype=torch.float64)).requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda a, b: O.transformer(a, b, (5, 6)), (U, th), eps=1e-7, atol=1e-5)
+
+
+def test_c_backward_matches_autograd():
+    rng = np.random.RandomState(0)
+    U = rng.rand(3, 12, 10, 2).astype(np.float32)
+    th = (np.array([[0.8, 0.1, 0.0, -0.1, 0.7, 0.1]], np.float32) + 0.05 * rng.randn(3, 6)).astype(np.float32)
+    g = rng.randn(3, 6, 7, 2).astype(np.float32)
+    Ut, tt = torch.from_numpy(U).requires_grad_(True), torch.from_numpy(th).requires_grad_(True)
+    O.transformer(Ut, tt, (6, 7)).backward(torch.from_numpy(g))
+    dU, dth = C.st_backward(U, th, g)
+    np.testing.assert_allclose(dU, Ut.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dth.reshape(3, 6), tt.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_concrete_kl_closed_form():
+    """log-density restatement vs an fp64 closed form of the binary Concrete density."""
+    y = torch.linspace(-4, 4, 33, dtype=torch.float64)
+    a_q, a_p, tau = 0.7, -2.0, 1.3
+
+    def logpdf(y, a, t):
+        return np.log(t) - t * y + a - 2 * np.log1p(np.exp(-t * y + a))
+
+    want = logpdf(y.numpy(), a_q, tau) - logpdf(y.numpy(), a_p, tau)
+    got = O.concrete_binary_kl_mc_sample(y, a_p, tau, torch.tensor(a_q, dtype=torch.float64), tau)
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-6, atol=1e-6)
+
+
+def test_stop_semantics_zero_digits():
+    """z ~ 0 at step 1 => stop ~ 1 >= 0.99 => zero digits (README: thr = 0.99 < 1)."""
+    out = C.concrete_step(np.array([-30.0, 30.0], np.float32), np.array([0.5, 0.5], np.float32),
+                          np.zeros(2, np.float32), np.zeros(2, np.float32), np.zeros(2, np.int32), -0.01, 1.0, 0.99, 1)
+    assert out["digits_new"].tolist() == [0, 1]
+    assert out["stop_new"][0] >= 0.99 and out["stop_new"][1] < 0.01
+
+
+def test_round_half_even_at_test_time():
+    out = C.concrete_step(np.array([0.0], np.float32), np.array([0.5], np.float32), np.zeros(1, np.float32),
+                          np.zeros(1, np.float32), np.zeros(1, np.int32), 0.0, 1.0, 0.99, 0)
+    assert out["z"][0] == 0.0  # sigmoid(0) = 0.5 rounds to even (0), tf.round semantics
+
+
+def test_fixed_trip_equals_early_exit():
+    """Items that stopped contribute exact +0.0: digits cannot grow after stopping."""
+    imgs, cnt = O.synthetic_canvases(16, seed=5)
+    m = O.AIROracle(train=False, seed=1, max_steps=5)
+    out = m.forward(imgs, cnt, O.make_noise(1, 5, 16))
+    masks = out["stop_masks"].numpy()
+    assert np.all(np.diff(masks.astype(np.int32), axis=1) <= 0)  # live mask is monotone non-increasing
+    assert np.array_equal(out["rec_num_digits"].numpy(), masks.sum(1))
+
+
+def test_tf_softplus_branches_and_grad():
+    x = torch.tensor([-20.0, -13.0, 0.0, 13.0, 20.0], requires_grad=True)
+    y = O.tf_softplus(x)
+    assert y[0].item() == pytest.approx(np.exp(-20.0), rel=1e-6)
+    assert y[4].item() == 20.0
+    y.sum().backward()
+    np.testing.assert_allclose(x.grad.numpy(), 1 / (1 + np.exp(-x.detach().numpy())), rtol=1e-6)
+
+
+def test_tf_adam_and_clip_semantics():
+    m = O.AIROracle(seed=0)
+    g = {k: torch.full_like(v, 0.5) for k, v in m.params.items()}
+    clipped, norm = O.AIROracle.clip_by_global_norm(g, 1.0)
+    n = sum(v.numel() for v in g.values())
+    assert norm.item() == pytest.approx(0.5 * np.sqrt(n), rel=1e-5)
+    k0 = "rnn/bias"
+    before = m.params[k0].clone()
+    m.adam_apply(clipped)
+    gc = 0.5 / norm.item()
+    mm, vv = 0.1 * gc, 0.001 * gc * gc
+    alpha = 1e-4 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    want = -alpha * mm / (np.sqrt(vv) + 1e-8)   # epsilon OUTSIDE the bias correction
+    np.testing.assert_allclose((m.params[k0] - before).numpy(), want, rtol=1e-4)
+    assert m.global_step == 1
+
+
+def test_annealed_prior():
+    v = O.annealed_value(O.DEFAULT_ANNEALING["z_pres_prior_log_odds"], 3000)
+    assert v.item() == pytest.approx(np.log(1000.0), rel=1e-5)
+    v = O.annealed_value(O.DEFAULT_ANNEALING["z_pres_prior_log_odds"], 60000)
+    assert v.item() == pytest.approx(np.log(2e-9), rel=1e-4)   # min 1e-9, then log(. + 1e-9)
+
+
+def test_param_census_matches_checkpoint_index():
+    """36 trainables, 4,011,643 parameters (model/air-model.index)."""
+    shapes = O.param_shapes()
+    assert len(shapes) == 36
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 4011643
+    assert shapes["rnn/kernel"] == (2756, 1024)
+
+
+def test_gemm_seq_fma_oracle():
+    rng = np.random.RandomState(0)
+    A, Bm = rng.randn(5, 37).astype(np.float32), rng.randn(37, 11).astype(np.float32)
+    out = C.gemm_seq_fma(A, Bm, bias=np.ones(11, np.float32))
+    np.testing.assert_allclose(out, A.astype(np.float64) @ Bm.astype(np.float64) + 1, rtol=1e-5, atol=1e-5)

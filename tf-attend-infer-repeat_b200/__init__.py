@@ -1,0 +1,17 @@
+"""B200-native (sm_100a) AIR hot path: drop-in for the reference's ``air`` package.
+
+    from air_b200 import transformer, batch_transformer, vae, AIRModel, \
+        concrete_binary_pre_sigmoid_sample, concrete_binary_kl_mc_sample
+
+Everything numeric runs in hand-written CUDA (csrc/) behind the C ABI in
+include/air_b200.h; PyTorch only owns device memory, streams and torch.distributed.
+"""
+from . import _cabi
+from ._cabi import AirError, build, launch_count
+from .air.transformer import transformer, batch_transformer, writeback_canvas
+from .air.concrete import (concrete_binary_sample, concrete_binary_pre_sigmoid_sample,
+                           concrete_binary_kl_mc_sample, concrete_step)
+
+__all__ = ["transformer", "batch_transformer", "writeback_canvas", "concrete_binary_sample",
+           "concrete_binary_pre_sigmoid_sample", "concrete_binary_kl_mc_sample", "concrete_step",
+           "AirError", "build", "launch_count"]

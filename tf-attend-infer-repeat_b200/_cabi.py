@@ -1,0 +1,99 @@
+"""ctypes binding of libair_b200.so (the C ABI declared in include/air_b200.h).
+
+There is deliberately no CPU fallback: if the shared library is missing, or a compute
+entry point is called without a CUDA device, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libair_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "air_b200.h")
+
+_c_f = ctypes.c_void_p  # device pointers travel as void*
+_SIGS = {
+    "air_abi_version": (ctypes.c_int, []),
+    "air_last_error": (ctypes.c_char_p, []),
+    "air_launch_count": (ctypes.c_int64, []),
+    "air_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
+    "air_st_forward": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
+    "air_st_backward": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
+    "air_st_writeback_canvas_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_float] + [_c_f] * 2 + [ctypes.c_int64] +
+                                    [ctypes.c_int] * 4 + [_c_f]),
+    "air_st_writeback_canvas_bwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_float] + [_c_f] * 4 + [ctypes.c_int64] +
+                                    [ctypes.c_int] * 4 + [_c_f]),
+    "air_concrete_step_fwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_float, ctypes.c_int] + [_c_f] * 7 +
+                              [ctypes.c_int64, _c_f]),
+    "air_concrete_step_bwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
+}
+
+_lib = None
+
+
+class AirError(RuntimeError):
+    """Raised when a C-ABI entry point returns a negative AIR_ERR_* code."""
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libair_b200.so (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-j8", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libair_b200.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AirError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(this package has no CPU / PyTorch fallback)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def declared_symbols():
+    return list(_SIGS.keys())
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().air_last_error().decode("utf-8", "replace")
+        raise AirError(f"{what} failed with code {code}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise AirError("air_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise AirError("air_b200 ops need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def f32(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def launch_count() -> int:
+    return int(lib().air_launch_count())

@@ -1,0 +1,587 @@
+// Spatial Transformer kernels for sm_100a: affine grid + bilinear sampling, forward and
+// backward, plus the fused write-back + z_pres-scaled canvas accumulation.
+//
+// Replaces air/transformer.py:48-171 (_repeat/_interpolate/_meshgrid/_transform) and
+// air/air_model.py:429-439 (canvas update) of the reference.  The forward kernels keep the
+// reference's rounding sequence (every TF op rounded separately, add_n left to right), so
+// they are bit-exact against oracle/st_oracle.c.
+//
+// Layout: one CTA stages the source tiles of G images in shared memory with one TMA bulk
+// copy (cp.async.bulk + mbarrier); while the copy is in flight the CTA builds per-image
+// row/column tables (clipped corner offsets + the two 1-D weights).  AIR's theta is
+// axis-aligned (air_model.py:324-327, 353-356) so x depends only on the output column and
+// y only on the row; images whose theta has shear/rotation take a per-pixel path in the
+// same kernel.  Output pixels are written coalesced.
+#include <algorithm>
+
+#include "air_common.cuh"
+
+namespace air {
+
+struct __align__(16) Ent {
+  int i0, i1;    // clipped corner offsets (pre-multiplied by the source stride)
+  float w1, w0;  // (i1f - v), (v - i0f) with v the UNCLIPPED coordinate
+};
+
+// pixel coordinate from a normalised source coordinate: (v + 1) * (n - 1.001) / 2   (:75-76)
+__device__ __forceinline__ float to_pixel(float vs, int n_in) {
+  const float span = sub_rn(static_cast<float>(n_in), 1.001f);
+  return mul_rn(mul_rn(add_rn(vs, 1.0f), span), 0.5f);
+}
+
+__device__ __forceinline__ Ent make_ent(float v, int n_in, int stride) {
+  int i0, i1;
+  floor_clip(v, n_in - 1, i0, i1);
+  Ent e;
+  e.i0 = i0 * stride;
+  e.i1 = i1 * stride;
+  e.w1 = sub_rn(static_cast<float>(i1), v);
+  e.w0 = sub_rn(v, static_cast<float>(i0));
+  return e;
+}
+
+// 1-D table entry for an axis-aligned theta: vs = fl(fl(diag*g) + trans); the zero
+// cross term of the k=3 BatchMatMul (:159) adds exactly 0.
+__device__ __forceinline__ Ent sep_ent(float diag, float trans, int k, int n_out, int n_in, int stride) {
+  const float g = linspace_pm1(k, n_out);
+  return make_ent(to_pixel(add_rn(mul_rn(diag, g), trans), n_in), n_in, stride);
+}
+
+// full 2-D sample for a general theta: fl(fl(fl(a0 x)+fl(a1 y))+a2)
+__device__ __forceinline__ void gen_ents(const float *th, int r, int c, int OH, int OW, int H, int W, Ent &ce,
+                                         Ent &re, float &xt, float &yt) {
+  xt = linspace_pm1(c, OW);
+  yt = linspace_pm1(r, OH);
+  const float xs = add_rn(add_rn(mul_rn(th[0], xt), mul_rn(th[1], yt)), th[2]);
+  const float ys = add_rn(add_rn(mul_rn(th[3], xt), mul_rn(th[4], yt)), th[5]);
+  ce = make_ent(to_pixel(xs, W), W, 1);
+  re = make_ent(to_pixel(ys, H), H, W);
+}
+
+__device__ __forceinline__ float bilerp(const float *im, const Ent &ce, const Ent &re) {
+  const float Ia = im[re.i0 + ce.i0], Ib = im[re.i1 + ce.i0];
+  const float Ic = im[re.i0 + ce.i1], Id = im[re.i1 + ce.i1];
+  const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+  const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+  // add_n([wa*Ia, wb*Ib, wc*Ic, wd*Id]) left to right (:116)
+  return add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
+}
+
+// =========================================================================================
+// Forward, staged (C == 1).  CANVAS: out = canvas_in + (live ? z * sample : 0).
+// =========================================================================================
+constexpr int kFwdThreads = 256;
+
+template <int H_, int W_, int OH_, int OW_, int G, bool CANVAS>
+__global__ void __launch_bounds__(kFwdThreads)
+    st_fwd_staged(const float *__restrict__ U, const float *__restrict__ theta, float *out,
+                  const float *__restrict__ zp, const float *__restrict__ stop, float thr, const float *canvas_in,
+                  int64_t B, int rH, int rW, int rOH, int rOW) {
+  const int H = H_ ? H_ : rH, W = W_ ? W_ : rW, OH = OH_ ? OH_ : rOH, OW = OW_ ? OW_ : rOW;
+  const int HW = H * W, OHW = OH * OW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *sU = reinterpret_cast<float *>(smem_raw);          // [G][HW]
+  Ent *sCol = reinterpret_cast<Ent *>(sU + G * HW);          // [G][OW]
+  Ent *sRow = sCol + G * OW;                                 // [G][OH]
+  float *sTh = reinterpret_cast<float *>(sRow + G * OH);     // [G][8]: theta[6], sep flag, z*live flag
+  __shared__ uint64_t bar;
+
+  const int tid = threadIdx.x;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * G;
+  const int n_img = static_cast<int>((B - g0 < G ? B - g0 : G));
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(n_img) * HW * 4u;
+    mbar_expect_tx(&bar, bytes);
+    bulk_g2s(sU, U + g0 * HW, bytes, &bar);
+  }
+
+  // ---- tables, built while the bulk copy is in flight
+  if (tid < n_img * 8) {
+    const int i = tid >> 3, k = tid & 7;
+    const float *th = theta + (g0 + i) * 6;
+    float v;
+    if (k < 6) {
+      v = __ldg(th + k);
+    } else if (k == 6) {
+      v = (__ldg(th + 1) == 0.0f && __ldg(th + 3) == 0.0f) ? 1.0f : 0.0f;
+    } else {
+      v = 1.0f;
+      if (CANVAS) v = (__ldg(stop + g0 + i) < thr) ? 1.0f : 0.0f;
+    }
+    sTh[tid] = v;
+  }
+  const int per_img = OW + OH;
+  for (int e = tid; e < n_img * per_img; e += kFwdThreads) {
+    const int i = e / per_img, k = e - i * per_img;
+    const float *th = theta + (g0 + i) * 6;
+    if (k < OW) {
+      sCol[i * OW + k] = sep_ent(__ldg(th + 0), __ldg(th + 2), k, OW, W, 1);
+    } else {
+      sRow[i * OH + (k - OW)] = sep_ent(__ldg(th + 4), __ldg(th + 5), k - OW, OH, H, W);
+    }
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  const int total = n_img * OHW;
+  for (int p = tid; p < total; p += kFwdThreads) {
+    const int i = p / OHW, q = p - i * OHW;
+    const int r = q / OW, c = q - r * OW;
+    const int64_t o = (g0 + i) * OHW + q;
+    const float *th = sTh + i * 8;
+    float v = 0.0f;
+    const bool live = !CANVAS || th[7] != 0.0f;
+    if (live) {
+      if (th[6] != 0.0f) {
+        v = bilerp(sU + i * HW, sCol[i * OW + c], sRow[i * OH + r]);
+      } else {
+        Ent ce, re;
+        float xt, yt;
+        gen_ents(th, r, c, OH, OW, H, W, ce, re, xt, yt);
+        v = bilerp(sU + i * HW, ce, re);
+      }
+    }
+    if (CANVAS) {
+      const float add = live ? mul_rn(__ldg(zp + g0 + i), v) : 0.0f;
+      out[o] = add_rn(canvas_in[o], add);
+    } else {
+      out[o] = v;
+    }
+  }
+}
+
+// =========================================================================================
+// Forward, generic: any C, any size, unaligned pointers.  One thread per output pixel.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+    st_fwd_generic(const float *__restrict__ U, const float *__restrict__ theta, float *__restrict__ out, int64_t B,
+                   int H, int W, int C, int OH, int OW) {
+  const int64_t n = B * OH * OW;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = p / (OH * OW);
+    const int q = static_cast<int>(p - b * OH * OW);
+    const int r = q / OW, c = q - r * OW;
+    float th[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) th[k] = __ldg(theta + b * 6 + k);
+    Ent ce, re;
+    float xt, yt;
+    gen_ents(th, r, c, OH, OW, H, W, ce, re, xt, yt);
+    const float *im = U + b * static_cast<int64_t>(H) * W * C;
+    const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+    const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+    const float *pa = im + static_cast<int64_t>(re.i0 + ce.i0) * C;
+    const float *pb = im + static_cast<int64_t>(re.i1 + ce.i0) * C;
+    const float *pc = im + static_cast<int64_t>(re.i0 + ce.i1) * C;
+    const float *pd = im + static_cast<int64_t>(re.i1 + ce.i1) * C;
+    float *o = out + p * C;
+    for (int ch = 0; ch < C; ++ch) {
+      o[ch] = add_rn(add_rn(add_rn(mul_rn(wa, __ldg(pa + ch)), mul_rn(wb, __ldg(pb + ch))), mul_rn(wc, __ldg(pc + ch))),
+                     mul_rn(wd, __ldg(pd + ch)));
+    }
+  }
+}
+
+// =========================================================================================
+// Backward, staged (C == 1), one CTA per image.
+//   upstream g[p] = FUSED ? (live ? dcanvas[p] : 0) * z : dout[p]
+//   dtheta[6]   : always
+//   dU [H,W]    : if non-null; separable gather form (deterministic) for axis-aligned theta,
+//                 shared-memory atomics otherwise
+//   dz          : FUSED only, sum_p (live ? dcanvas[p] : 0) * sample[p]
+// Gradient formulas are TF autodiff of transformer.py:108-116 (no gradient through
+// floor / clip / cast); only the summation order differs from the oracle.
+// =========================================================================================
+constexpr int kBwdThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float *red /*[8]*/) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect red from the previous use
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kBwdThreads / 32; ++k) t += red[k];
+  return t;
+}
+
+template <int H_, int W_, int OH_, int OW_, bool FUSED>
+__global__ void __launch_bounds__(kBwdThreads)
+    st_bwd_staged(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dout,
+                  const float *__restrict__ zp, const float *__restrict__ stop, float thr, float *__restrict__ dU,
+                  float *__restrict__ dtheta, float *__restrict__ dz, int64_t B, int rH, int rW, int rOH, int rOW) {
+  const int H = H_ ? H_ : rH, W = W_ ? W_ : rW, OH = OH_ ? OH_ : rOH, OW = OW_ ? OW_ : rOW;
+  const int HW = H * W, OHW = OH * OW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *sU = reinterpret_cast<float *>(smem_raw);  // [HW]
+  float *sG = sU + ((HW + 3) & ~3);                 // [OHW]  upstream gradient tile
+  Ent *sCol = reinterpret_cast<Ent *>(sG + ((OHW + 3) & ~3));  // [OW]
+  Ent *sRow = sCol + OW;                                         // [OH]
+  int2 *sRange = reinterpret_cast<int2 *>(sRow + OH);           // [W + H] contributor ranges
+  float *sT = reinterpret_cast<float *>(sRange + ((W + H + 1) & ~1));  // [OH][W] pass-1 buffer / dU atomics tile
+  __shared__ uint64_t bar;
+  __shared__ float red[kBwdThreads / 32];
+  __shared__ float sTh[8];
+
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const float *th_g = theta + b * 6;
+
+  bool live = true;
+  float zval = 1.0f;
+  if (FUSED) {
+    live = __ldg(stop + b) < thr;
+    zval = __ldg(zp + b);
+  }
+  if (!live) {  // whole image masked out: every gradient is exactly zero (uniform branch)
+    if (dU)
+      for (int k = tid; k < HW; k += kBwdThreads) dU[b * HW + k] = 0.0f;
+    if (tid < 6) dtheta[b * 6 + tid] = 0.0f;
+    if (tid == 0 && dz) dz[b] = 0.0f;
+    return;
+  }
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, static_cast<uint32_t>(HW + OHW) * 4u);
+    bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
+    bulk_g2s(sG, dout + b * OHW, OHW * 4u, &bar);
+  }
+  if (tid < 6) sTh[tid] = __ldg(th_g + tid);
+  if (tid == 6) sTh[6] = (__ldg(th_g + 1) == 0.0f && __ldg(th_g + 3) == 0.0f) ? 1.0f : 0.0f;
+  for (int k = tid; k < OW + OH; k += kBwdThreads) {
+    if (k < OW)
+      sCol[k] = sep_ent(__ldg(th_g + 0), __ldg(th_g + 2), k, OW, W, 1);
+    else
+      sRow[k - OW] = sep_ent(__ldg(th_g + 4), __ldg(th_g + 5), k - OW, OH, H, W);
+  }
+  __syncthreads();
+  const bool sep = sTh[6] != 0.0f;
+  if (dU && !sep)
+    for (int k = tid; k < HW; k += kBwdThreads) sT[k] = 0.0f;  // atomics tile (needs HW <= OH*W, checked on host)
+  mbar_wait(&bar, 0);
+  if (dU && !sep) __syncthreads();
+
+  const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, az = 0.f;
+  for (int q = tid; q < OHW; q += kBwdThreads) {
+    const int r = q / OW, c = q - r * OW;
+    Ent ce, re;
+    float xt, yt;
+    if (sep) {
+      ce = sCol[c];
+      re = sRow[r];
+      xt = linspace_pm1(c, OW);
+      yt = linspace_pm1(r, OH);
+    } else {
+      gen_ents(sTh, r, c, OH, OW, H, W, ce, re, xt, yt);
+    }
+    const float Ia = sU[re.i0 + ce.i0], Ib = sU[re.i1 + ce.i0];
+    const float Ic = sU[re.i0 + ce.i1], Id = sU[re.i1 + ce.i1];
+    float g = sG[q];
+    if (FUSED) {
+      const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+      const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+      const float v = add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
+      az += g * v;  // d(z * v)/dz
+      g *= zval;    // d(z * v)/dv
+    }
+    const float dwa = g * Ia, dwb = g * Ib, dwc = g * Ic, dwd = g * Id;
+    const float dx = ((-(dwa * re.w1) - dwb * re.w0) + dwc * re.w1) + dwd * re.w0;
+    const float dy = ((-(dwa * ce.w1) + dwb * ce.w1) - dwc * ce.w0) + dwd * ce.w0;
+    const float dxs = dx * 0.5f * wf, dys = dy * 0.5f * hf;
+    a0 += dxs * xt;
+    a1 += dxs * yt;
+    a2 += dxs;
+    a3 += dys * xt;
+    a4 += dys * yt;
+    a5 += dys;
+    if (dU && !sep) {
+      atomicAdd(&sT[re.i0 + ce.i0], mul_rn(ce.w1, re.w1) * g);
+      atomicAdd(&sT[re.i1 + ce.i0], mul_rn(ce.w1, re.w0) * g);
+      atomicAdd(&sT[re.i0 + ce.i1], mul_rn(ce.w0, re.w1) * g);
+      atomicAdd(&sT[re.i1 + ce.i1], mul_rn(ce.w0, re.w0) * g);
+    }
+  }
+  a0 = block_sum(a0, red);
+  a1 = block_sum(a1, red);
+  a2 = block_sum(a2, red);
+  a3 = block_sum(a3, red);
+  a4 = block_sum(a4, red);
+  a5 = block_sum(a5, red);
+  if (FUSED) az = block_sum(az, red);
+  if (tid == 0) {
+    float *d = dtheta + b * 6;
+    d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3; d[4] = a4; d[5] = a5;
+    if (FUSED && dz) dz[b] = az;
+  }
+  if (!dU) return;
+
+  if (!sep) {
+    __syncthreads();
+    for (int k = tid; k < HW; k += kBwdThreads) dU[b * HW + k] = sT[k];
+    return;
+  }
+
+  // ---- deterministic separable dU:  dU = z * Wy^T * g * Wx,
+  //      Wx[c][j] = [x0(c)==j]*wx1(c) + [x1(c)==j]*wx0(c)  (clipped columns give exactly 0).
+  //      theta is axis-aligned, so the contributors of source column j (row i) are one
+  //      contiguous range of output columns (rows): gather form, fixed order, no atomics.
+  __syncthreads();
+  for (int j = tid; j < W + H; j += kBwdThreads) {
+    int lo = 1 << 30, hi = -1;
+    if (j < W) {
+      for (int c = 0; c < OW; ++c)
+        if (sCol[c].i0 == j || sCol[c].i1 == j) { lo = min(lo, c); hi = max(hi, c); }
+    } else {
+      const int iw = (j - W) * W;
+      for (int r = 0; r < OH; ++r)
+        if (sRow[r].i0 == iw || sRow[r].i1 == iw) { lo = min(lo, r); hi = max(hi, r); }
+    }
+    sRange[j] = make_int2(lo, hi);
+  }
+  __syncthreads();
+  // pass 1: T[r][j] = sum_c g[r][c] * Wx[c][j]
+  for (int e = tid; e < OH * W; e += kBwdThreads) {
+    const int r = e / W, j = e - r * W;
+    const int2 rg = sRange[j];
+    float acc = 0.0f;
+    for (int c = rg.x; c <= rg.y; ++c) {
+      const Ent ce = sCol[c];
+      const float coef = (ce.i0 == j ? ce.w1 : 0.0f) + (ce.i1 == j ? ce.w0 : 0.0f);
+      acc += coef * sG[r * OW + c];
+    }
+    sT[e] = acc;
+  }
+  __syncthreads();
+  // pass 2: dU[i][j] = z * sum_r Wy[r][i] * T[r][j]
+  for (int e = tid; e < HW; e += kBwdThreads) {
+    const int i = e / W, j = e - i * W;
+    const int iw = i * W;
+    const int2 rg = sRange[W + i];
+    float acc = 0.0f;
+    for (int r = rg.x; r <= rg.y; ++r) {
+      const Ent re = sRow[r];
+      const float coef = (re.i0 == iw ? re.w1 : 0.0f) + (re.i1 == iw ? re.w0 : 0.0f);
+      acc += coef * sT[r * W + j];
+    }
+    dU[b * HW + e] = FUSED ? acc * zval : acc;
+  }
+}
+
+// =========================================================================================
+// Backward, generic (any C, any size): one CTA per image, global atomics for dU.
+// =========================================================================================
+__global__ void __launch_bounds__(kBwdThreads)
+    st_bwd_generic(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dout,
+                   float *dU, float *__restrict__ dtheta, int H, int W, int C, int OH, int OW) {
+  __shared__ float red[kBwdThreads / 32];
+  const int64_t b = blockIdx.x;
+  float th[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) th[k] = __ldg(theta + b * 6 + k);
+  const float *im = U + b * static_cast<int64_t>(H) * W * C;
+  float *dim = dU ? dU + b * static_cast<int64_t>(H) * W * C : nullptr;
+  const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+  for (int q = threadIdx.x; q < OH * OW; q += kBwdThreads) {
+    const int r = q / OW, c = q - r * OW;
+    Ent ce, re;
+    float xt, yt;
+    gen_ents(th, r, c, OH, OW, H, W, ce, re, xt, yt);
+    const int64_t oa = static_cast<int64_t>(re.i0 + ce.i0) * C, ob = static_cast<int64_t>(re.i1 + ce.i0) * C;
+    const int64_t oc = static_cast<int64_t>(re.i0 + ce.i1) * C, od = static_cast<int64_t>(re.i1 + ce.i1) * C;
+    const float *g = dout + (b * OH * OW + q) * C;
+    const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+    const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+    float dwa = 0.f, dwb = 0.f, dwc = 0.f, dwd = 0.f;
+    for (int ch = 0; ch < C; ++ch) {
+      const float gc = __ldg(g + ch);
+      dwa += gc * __ldg(im + oa + ch);
+      dwb += gc * __ldg(im + ob + ch);
+      dwc += gc * __ldg(im + oc + ch);
+      dwd += gc * __ldg(im + od + ch);
+      if (dim) {
+        atomicAdd(dim + oa + ch, wa * gc);
+        atomicAdd(dim + ob + ch, wb * gc);
+        atomicAdd(dim + oc + ch, wc * gc);
+        atomicAdd(dim + od + ch, wd * gc);
+      }
+    }
+    const float dx = ((-(dwa * re.w1) - dwb * re.w0) + dwc * re.w1) + dwd * re.w0;
+    const float dy = ((-(dwa * ce.w1) + dwb * ce.w1) - dwc * ce.w0) + dwd * ce.w0;
+    const float dxs = dx * 0.5f * wf, dys = dy * 0.5f * hf;
+    a0 += dxs * xt; a1 += dxs * yt; a2 += dxs;
+    a3 += dys * xt; a4 += dys * yt; a5 += dys;
+  }
+  a0 = block_sum(a0, red); a1 = block_sum(a1, red); a2 = block_sum(a2, red);
+  a3 = block_sum(a3, red); a4 = block_sum(a4, red); a5 = block_sum(a5, red);
+  if (threadIdx.x == 0) {
+    float *d = dtheta + b * 6;
+    d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3; d[4] = a4; d[5] = a5;
+  }
+}
+
+// =========================================================================================
+// Host side
+// =========================================================================================
+constexpr int kMaxStagedSmem = 200 * 1024;
+
+template <int G>
+static size_t fwd_smem_bytes(int H, int W, int OH, int OW) {
+  return static_cast<size_t>(G) * H * W * 4 + static_cast<size_t>(G) * (OW + OH) * sizeof(Ent) + G * 8 * 4;
+}
+
+template <int H_, int W_, int OH_, int OW_, int G, bool CANVAS>
+static int launch_fwd_staged(const float *U, const float *theta, float *out, const float *z, const float *stop,
+                             float thr, const float *canvas_in, int64_t B, int H, int W, int OH, int OW,
+                             cudaStream_t s) {
+  auto kern = st_fwd_staged<H_, W_, OH_, OW_, G, CANVAS>;
+  const size_t smem = fwd_smem_bytes<G>(H, W, OH, OW);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_fwd_staged): %s", cudaGetErrorString(e));
+  }
+  const int64_t grid = (B + G - 1) / G;
+  kern<<<static_cast<unsigned>(grid), kFwdThreads, smem, s>>>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW);
+  count_launch();
+  return check_launch("st_fwd_staged");
+}
+
+static bool staged_ok(const void *U, int H, int W, int C, int64_t B) {
+  return C == 1 && ((H * W) % 4 == 0) && aligned16(U) && B < (int64_t(1) << 31);
+}
+
+static int st_forward_impl(const float *U, const float *theta, float *out, const float *z, const float *stop,
+                           float thr, const float *canvas_in, bool canvas, int64_t B, int H, int W, int C, int OH,
+                           int OW, cudaStream_t s) {
+  AIR_REQUIRE(U && theta && out, AIR_ERR_NULL, "st_forward: null pointer");
+  AIR_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, AIR_ERR_BAD_SHAPE,
+              "st_forward: bad shape B=%lld H=%d W=%d C=%d oh=%d ow=%d", (long long)B, H, W, C, OH, OW);
+  AIR_REQUIRE(static_cast<int64_t>(H) * W * C < (int64_t(1) << 30) && static_cast<int64_t>(OH) * OW < (int64_t(1) << 30),
+              AIR_ERR_BAD_SHAPE, "st_forward: image too large");
+  if (B == 0) return AIR_OK;
+  if (staged_ok(U, H, W, C, B)) {
+    if (canvas) {
+      if (H == 28 && W == 28 && OH == 50 && OW == 50)
+        return launch_fwd_staged<28, 28, 50, 50, 4, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+      if (fwd_smem_bytes<2>(H, W, OH, OW) <= kMaxStagedSmem)
+        return launch_fwd_staged<0, 0, 0, 0, 2, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+    } else {
+      if (H == 50 && W == 50 && OH == 28 && OW == 28)
+        return launch_fwd_staged<50, 50, 28, 28, 4, false>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+      if (H == 28 && W == 28 && OH == 50 && OW == 50)
+        return launch_fwd_staged<28, 28, 50, 50, 4, false>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+      if (fwd_smem_bytes<2>(H, W, OH, OW) <= kMaxStagedSmem)
+        return launch_fwd_staged<0, 0, 0, 0, 2, false>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+    }
+  }
+  AIR_REQUIRE(!canvas, AIR_ERR_UNSUPPORTED,
+              "st_writeback_canvas_fwd: needs a 16-byte aligned single-channel window that fits shared memory");
+  const int64_t n = B * OH * OW;
+  const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+  st_fwd_generic<<<blocks, 256, 0, s>>>(U, theta, out, B, H, W, C, OH, OW);
+  count_launch();
+  return check_launch("st_fwd_generic");
+}
+
+static size_t bwd_smem_bytes(int H, int W, int OH, int OW) {
+  const size_t hw = (static_cast<size_t>(H) * W + 3) & ~size_t(3), ohw = (static_cast<size_t>(OH) * OW + 3) & ~size_t(3);
+  const size_t t = std::max(static_cast<size_t>(OH) * W, static_cast<size_t>(H) * W);
+  return (hw + ohw) * 4 + static_cast<size_t>(OW + OH) * sizeof(Ent) + static_cast<size_t>((W + H + 1) & ~1) * 8 + t * 4;
+}
+
+template <int H_, int W_, int OH_, int OW_, bool FUSED>
+static int launch_bwd_staged(const float *U, const float *theta, const float *dout, const float *z, const float *stop,
+                             float thr, float *dU, float *dtheta, float *dz, int64_t B, int H, int W, int OH, int OW,
+                             cudaStream_t s) {
+  auto kern = st_bwd_staged<H_, W_, OH_, OW_, FUSED>;
+  const size_t smem = bwd_smem_bytes(H, W, OH, OW);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_bwd_staged): %s", cudaGetErrorString(e));
+  }
+  kern<<<static_cast<unsigned>(B), kBwdThreads, smem, s>>>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW);
+  count_launch();
+  return check_launch("st_bwd_staged");
+}
+
+static int st_backward_impl(const float *U, const float *theta, const float *dout, const float *z, const float *stop,
+                            float thr, bool fused, float *dU, float *dtheta, float *dz, int64_t B, int H, int W, int C,
+                            int OH, int OW, cudaStream_t s) {
+  AIR_REQUIRE(U && theta && dout && dtheta, AIR_ERR_NULL, "st_backward: null pointer");
+  AIR_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, AIR_ERR_BAD_SHAPE,
+              "st_backward: bad shape B=%lld H=%d W=%d C=%d oh=%d ow=%d", (long long)B, H, W, C, OH, OW);
+  AIR_REQUIRE(static_cast<int64_t>(H) * W * C < (int64_t(1) << 30) && static_cast<int64_t>(OH) * OW < (int64_t(1) << 30),
+              AIR_ERR_BAD_SHAPE, "st_backward: image too large");
+  if (B == 0) return AIR_OK;
+  const bool staged = staged_ok(U, H, W, C, B) && ((OH * OW) % 4 == 0) && aligned16(dout) &&
+                      bwd_smem_bytes(H, W, OH, OW) <= static_cast<size_t>(kMaxStagedSmem);
+  if (staged) {
+    if (fused) {
+      if (H == 28 && W == 28 && OH == 50 && OW == 50)
+        return launch_bwd_staged<28, 28, 50, 50, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+      return launch_bwd_staged<0, 0, 0, 0, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+    }
+    if (H == 50 && W == 50 && OH == 28 && OW == 28)
+      return launch_bwd_staged<50, 50, 28, 28, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+    if (H == 28 && W == 28 && OH == 50 && OW == 50)
+      return launch_bwd_staged<28, 28, 50, 50, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+    return launch_bwd_staged<0, 0, 0, 0, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+  }
+  AIR_REQUIRE(!fused, AIR_ERR_UNSUPPORTED,
+              "st_writeback_canvas_bwd: needs 16-byte aligned single-channel tiles that fit shared memory");
+  AIR_REQUIRE(B < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "st_backward: B too large");
+  if (dU) {
+    cudaError_t e = cudaMemsetAsync(dU, 0, sizeof(float) * static_cast<size_t>(B) * H * W * C, s);
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  }
+  st_bwd_generic<<<static_cast<unsigned>(B), kBwdThreads, 0, s>>>(U, theta, dout, dU, dtheta, H, W, C, OH, OW);
+  count_launch();
+  return check_launch("st_bwd_generic");
+}
+
+}  // namespace air
+
+// ---- C ABI ------------------------------------------------------------------------------
+extern "C" int air_st_forward(const float *U, const float *theta, float *out, int64_t B, int H, int W, int C, int oh,
+                              int ow, air_stream_t stream) {
+  return air::st_forward_impl(U, theta, out, nullptr, nullptr, 0.0f, nullptr, false, B, H, W, C, oh, ow,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int air_st_backward(const float *U, const float *theta, const float *dout, float *dU, float *dtheta,
+                               int64_t B, int H, int W, int C, int oh, int ow, air_stream_t stream) {
+  return air::st_backward_impl(U, theta, dout, nullptr, nullptr, 0.0f, false, dU, dtheta, nullptr, B, H, W, C, oh, ow,
+                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int air_st_writeback_canvas_fwd(const float *window, const float *theta_inv, const float *z,
+                                           const float *stop_new, float thr, const float *canvas_in,
+                                           float *canvas_out, int64_t B, int wh, int ww, int ch, int cw,
+                                           air_stream_t stream) {
+  AIR_REQUIRE(z && stop_new && canvas_in && canvas_out, AIR_ERR_NULL, "st_writeback_canvas_fwd: null pointer");
+  return air::st_forward_impl(window, theta_inv, canvas_out, z, stop_new, thr, canvas_in, true, B, wh, ww, 1, ch, cw,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int air_st_writeback_canvas_bwd(const float *window, const float *theta_inv, const float *z,
+                                           const float *stop_new, float thr, const float *dcanvas, float *dwindow,
+                                           float *dtheta_inv, float *dz, int64_t B, int wh, int ww, int ch, int cw,
+                                           air_stream_t stream) {
+  AIR_REQUIRE(z && stop_new && dwindow && dz, AIR_ERR_NULL, "st_writeback_canvas_bwd: null pointer");
+  return air::st_backward_impl(window, theta_inv, dcanvas, z, stop_new, thr, true, dwindow, dtheta_inv, dz, B, wh, ww,
+                               1, ch, cw, static_cast<cudaStream_t>(stream));
+}
