@@ -1,0 +1,163 @@
+"""Train / inference workloads of bench.py (BASELINE.json configs[2], [3], [4])."""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+from bench import ClockSampler, barrier, max_over_ranks, time_launches
+
+METRIC = "AIR train images/sec"
+
+
+def _model(B, gemm_mode, seed, train=True, max_steps=3):
+    import air_b200 as ab
+    from importlib import import_module
+    data = import_module("tf-attend-infer-repeat_b200.data")
+    imgs, cnt = data.synthetic_canvases(B, seed=seed)
+    hyper = dict(data.TRAINING_HYPER)
+    hyper["max_steps"] = max_steps
+    ab.reset_variable_scopes()
+    m = ab.AIRModel(imgs.cuda(), cnt.cuda(), train=train, annealing_schedules=data.TRAINING_ANNEALING,
+                    gemm_mode=gemm_mode, seed=0, **hyper)
+    return m, imgs, cnt, data
+
+
+def gemm_roofline(B, mode, peaks, steps=20):
+    """The dominant kernel of the step: the [B,2500]x[2500,1024] LSTM input projection GEMM
+    (and its twin dK = x^T dgates), timed alone with CUDA events."""
+    import air_b200 as ab
+    from air_b200 import ops
+    x = torch.rand(B, 2500, device="cuda")
+    W = torch.randn(2500, 1024, device="cuda") * 0.02
+    out = torch.empty(B, 1024, device="cuda")
+    ms = time_launches(lambda: ops.gemm(x, W, out, mode=ab._cabi.GEMM_MODES[mode]), steps, 5)
+    flops = 2.0 * B * 2500 * 1024
+    tf = flops / (ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops"] * (0.5 if mode == "tf32" else 1.0)
+    kern = "gemm_simt<128,128,16,8,8> (fp32 FFMA, exact mode)" if mode == "fp32" else "gemm_tf32 (tcgen05)"
+    return {"bound": "tensor", "achieved": round(tf, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
+            "frac": round(tf / peak, 4), "traffic": None, "peak_source": peaks["source"], "kernel": kern,
+            "shape": f"[{B},2500]x[2500,1024]", "ms": round(ms, 4),
+            "note": "peak = measured cuBLAS bf16 burst" + (" / 2 (TF32 dense estimate)" if mode == "tf32" else
+                                                           "; exact-fp32 SIMT mode cannot approach a tensor-core peak")}
+
+
+def run(args, rank, world, peaks):
+    import air_b200 as ab
+    B = args.batch or 4096
+    mode = args.gemm or os.environ.get("AIR_GEMM", "fp32")
+    infer = args.workload == "infer"
+    T = 5 if infer else 3
+    if infer and not args.batch:
+        B = 65536
+    m, imgs, cnt, data = _model(B, mode, seed=rank, train=not infer, max_steps=T)
+    if infer:
+        step = lambda: m.run()
+    else:
+        m.capture()
+        step = m.train_step
+    n0 = ab.launch_count()
+    for _ in range(args.warmup):
+        step()
+    barrier(world)
+    launches_eager = ab.launch_count() - n0
+    with ClockSampler(torch.cuda.current_device()) as cs:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+    value = B * world / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> device, step, loss back to the host, every step
+    imgs_h, cnt_h = imgs.pin_memory(), cnt.pin_memory()
+
+    def e2e_step():
+        m.feed(imgs_h, cnt_h)
+        step()
+        return float(m.loss.item()) if not infer else int(m.rec_num_digits[0].item())
+
+    for _ in range(3):
+        e2e_step()
+    barrier(world)
+    t0 = time.perf_counter()
+    n_e2e = max(5, args.steps // 2)
+    for _ in range(n_e2e):
+        last = e2e_step()
+    barrier(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / n_e2e
+
+    # kernels per step: count one eager step (graph replays do not pass through the launch counter)
+    probe, _, _, _ = (m, None, None, None)
+    c0 = ab.launch_count()
+    if infer:
+        m.run()
+    else:
+        g, m._graphs = m._graphs, None
+        m.train_step()
+        m._graphs = g
+    per_step = ab.launch_count() - c0
+    torch.cuda.synchronize()
+
+    flops_img = data.train_flops_per_image(T) if not infer else 2 * T * data.MAC_FWD_STEP
+    line = {
+        "metric": METRIC if not infer else "AIR inference images/sec", "value": round(value, 1), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if mode == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": ("AIRModel default (training.py:100-122) full train step: forward, backward, "
+                                "global-norm clip, TF-Adam; T=3" if not infer else
+                                "AIRModel default inference (train=False), T=5"),
+                   "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": mode, "parallelism": f"dp{world}",
+                   "noise": "drawn on device inside the timed step", "cuda_graph": not infer,
+                   "l2": f"per-step working set ~{B * 61e3 / 1e6:.0f} MB of activations + 16 MB weights > 126 MB L2"},
+        "step_tflops_canonical": round(value * flops_img / 1e12, 2),
+        "e2e": {"value": round(B * world / (e2e_ms * 1e-3), 1), "unit": "images/s",
+                "h2d_bytes_per_step": int(imgs_h.numel() * 4 + cnt_h.numel() * 4), "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_ms, 4), "last_result": last},
+        "gpu_launches": int(per_step * args.steps),
+        "kernels_per_step": int(per_step),
+        "loss": float(m.loss.item()) if not infer else None,
+        "clocks": cs.summary(),
+    }
+    if rank == 0:
+        line["roofline"] = gemm_roofline(B, mode, peaks)
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(seconds=12.0)
+    return line
+
+
+def cpu_baseline(seconds=12.0, B=64, steps=None):
+    """The reference restated on the CPU (oracle/air_oracle.py, torch, NOT TensorFlow): full
+    train step at BASELINE.json configs[0] (batch 64), all host cores."""
+    from oracle import air_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    imgs, cnt = O.synthetic_canvases(B, seed=0)
+    m = O.AIROracle(annealing_schedules=O.DEFAULT_ANNEALING, train=True, seed=0)
+    noise = O.make_noise(0, 3, B)
+    for _ in range(2):
+        m.train_step(imgs, cnt, noise)
+    t0 = time.perf_counter()
+    n = 0
+    while (steps is None and time.perf_counter() - t0 < seconds) or (steps is not None and n < steps):
+        m.train_step(imgs, cnt, noise)
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": round(B / dt, 1), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle (torch CPU restatement of the TF-1.3 reference) full train step, batch {B}, "
+                      f"{n} steps, {dt * 1e3:.1f} ms/step"}
+
+
+def run_reference(args, peaks):
+    cb = cpu_baseline(steps=max(args.steps, 5))
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "AIRModel default full train step (reference restated on CPU; TF 1.3 cannot run here)",
+                       "batch_per_gpu": 64, "note": "each step is a bounded sample (batch 64) of the batch-4096 workload"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

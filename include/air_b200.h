@@ -87,6 +87,125 @@ int air_concrete_step_bwd(const float *log_odds, const float *y, const float *z,
                           const float *prior_log_odds, float temperature, int train, float *dlog_odds, int64_t B,
                           air_stream_t stream);
 
+/* ---- dense contractions: MatMul + BiasAdd (+ activation) ---------------------------
+ * Replaces the dense layers of the reference -- tf.contrib.layers.fully_connected
+ * (air/vae.py:13-34, air/air_model.py:292-316, 372-376), BasicLSTMCell's linear map
+ * (air/air_model.py:284-286, 539) -- and the MatMul gradients TF autodiff derives from them.
+ *
+ *   C[M,N] = epilogue( (Cinit[M,N] + op(A)[M,K] * op(B)[K,N]) + bias[N] )
+ *
+ * op(A) = A (row-major [M,K], leading dim lda) or A^T (A stored [K,M]) when transA;
+ * op(B) = B (row-major [K,N], ldb)            or B^T (B stored [N,K]) when transB.
+ * Cinit / bias / aux may be NULL; Cinit and aux use ldc; Cinit may alias C.
+ * mode AIR_GEMM_FP32_EXACT: SIMT FFMA, one FMA per k in strictly increasing k order
+ *   (bit-reproducible, equals oracle_gemm_seq_fma);
+ * mode AIR_GEMM_TF32: tcgen05 tensor cores, TF32 inputs, FP32 accumulation in TMEM. */
+#define AIR_EPI_NONE 0
+#define AIR_EPI_RELU 1
+#define AIR_EPI_SOFTPLUS 2      /* tf.nn.softplus: x>13.94->x, x<-13.94->exp(x), else log(exp(x)+1) */
+#define AIR_EPI_MUL_DRELU 3     /* out = v * (aux > 0)            (ReLU backward, aux = ReLU output) */
+#define AIR_EPI_MUL_DSOFTPLUS 4 /* out = v * (1 - exp(-aux))      (softplus backward, aux = softplus output) */
+#define AIR_GEMM_FP32_EXACT 0
+#define AIR_GEMM_TF32 1
+int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
+             int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue, int mode,
+             air_stream_t stream);
+
+/* ---- fused model-specific elementwise kernels (air/air_model.py loop body) ----------
+ * Hyper-parameters that are plain Python floats in the reference constructor
+ * (air_model.py:13-22).  Passed by pointer to a HOST struct. */
+typedef struct air_hyper {
+  float scale_prior_mean, scale_prior_variance;
+  float shift_prior_mean, shift_prior_variance;
+  float vae_prior_mean, vae_prior_variance;
+  float vae_likelihood_std;
+  float z_pres_temperature, stopping_threshold;
+  int32_t train; /* 0: z_pres is rounded (air_model.py:389-390) */
+} air_hyper_t;
+
+/* Per-step table of per-image scalars, laid out [AIR_NF][B] (struct of arrays). */
+enum air_field {
+  AIR_F_SCALE_MEAN = 0, AIR_F_SCALE_LV, AIR_F_SHIFT_MEAN_X, AIR_F_SHIFT_MEAN_Y, AIR_F_SHIFT_LV_X, AIR_F_SHIFT_LV_Y,
+  AIR_F_LOG_ODDS,                       /* the 7 head outputs */
+  AIR_F_S, AIR_F_X, AIR_F_Y,            /* sigmoid / tanh of the Gaussian samples (air_model.py:301, 318) */
+  AIR_F_YPRE, AIR_F_Z, AIR_F_ZPROB,     /* Concrete pre-sigmoid sample, z_pres, sigmoid(log_odds) */
+  AIR_F_KL_Z, AIR_F_KL_SCALE, AIR_F_KL_SHIFT, AIR_F_KL_VAE,
+  AIR_F_STOP_PREV, AIR_F_STOP_NEW,      /* stopping_sum before / after this step */
+  AIR_NF = 20
+};
+
+/* BasicLSTMCell pointwise part (air_model.py:286, 539): gates [B,4H] = [x,h]K + b, order
+ * i,j,f,o, forget bias 1.0.  c_prev NULL = zero state. */
+int air_lstm_fwd(const float *gates, const float *c_prev, float *c_new, float *h_new, int64_t B, int H,
+                 air_stream_t stream);
+/* dgates [B,4H], dc_prev [B,H]; dc_new NULL = 0; dgates_sum (nullable) += dgates. */
+int air_lstm_bwd(const float *gates, const float *c_prev, const float *c_new, const float *dh, const float *dc_new,
+                 float *dgates, float *dc_prev, float *dgates_sum, int64_t B, int H, air_stream_t stream);
+
+/* Everything between the hidden head layers and the VAE for one step
+ * (air_model.py:294-327, 353-356, 376-427, 441-477): the 7 head outputs (k-sequential FMA
+ * dot products over `hidden` [B,5*HU], post-ReLU, heads ordered scale/mean, scale/log_variance,
+ * shift/mean, shift/log_variance, z_pres/log_odds; w_out [7,HU], b_out [7]), Gaussian sampling +
+ * sigmoid/tanh, scale & shift KLs, theta / theta_inv, and the fused Concrete/ACT step.
+ * stop / loss / digits are updated in place; fields [AIR_NF,B]; theta, theta_inv [B,6]. */
+int air_heads_fwd(const float *hidden, const float *w_out, const float *b_out, const float *noise_scale,
+                  const float *noise_shift, const float *u, const float *prior_log_odds, const air_hyper_t *hyper,
+                  float *stop, float *loss, int32_t *digits, float *fields, float *theta, float *theta_inv, int64_t B,
+                  int HU, air_stream_t stream);
+/* Backward of air_heads_fwd.  dtheta / dtheta_inv [B,6], dz [B] come from the ST kernels;
+ * dloss is d(total)/d(running_loss[b]) (1/batch).  Writes dhidden [B,5*HU] (ReLU mask applied)
+ * and accumulates (if accumulate) or writes d(w_out) [7,HU] and d(b_out) [7]; deterministic.
+ * workspace: at least air_heads_bwd_workspace(B, HU) floats. */
+int64_t air_heads_bwd_workspace(int64_t B, int HU);
+int air_heads_bwd(const float *hidden, const float *w_out, const float *noise_scale, const float *noise_shift,
+                  const float *fields, const float *dtheta, const float *dtheta_inv, const float *dz,
+                  const float *prior_log_odds, const air_hyper_t *hyper, float dloss, float *dhidden, float *dw_out,
+                  float *db_out, int accumulate, float *workspace, int64_t B, int HU, air_stream_t stream);
+
+/* VAE latent (vae.py:22-24, air_model.py:479-493): ml [B,2L] = (mean | log_variance);
+ * sample = mean + noise*sqrt(exp(lv)); KL vs N(prior) -> fields[AIR_F_KL_VAE];
+ * loss += (stop_new < thr ? kl : 0). */
+int air_vae_latent_fwd(const float *ml, const float *noise, const air_hyper_t *hyper, float *sample, float *fields,
+                       float *loss, int64_t B, int L, air_stream_t stream);
+int air_vae_latent_bwd(const float *ml, const float *noise, const float *dsample, const float *fields,
+                       const air_hyper_t *hyper, float dloss, float *dml, int64_t B, int L, air_stream_t stream);
+
+/* vae.py:36-41: out = sigmoid(gen + noise*std); backward dgen = dout*out*(1-out) (may be in place). */
+int air_sigmoid_noise_fwd(const float *gen, const float *noise, float std, float *out, int64_t n, air_stream_t stream);
+int air_sigmoid_bwd(const float *out, const float *dout, float *dgen, int64_t n, air_stream_t stream);
+
+/* air_model.py:580-590: r = max(min(canvas,1),0); rec_loss[b] = -sum(x log(r+1e-9) + (1-x) log(1-r+1e-9)).
+ * recon (nullable) receives r; dcanvas (nullable) receives dscale * d rec_loss / d canvas
+ * (gradient passes at r == 0 and r == 1, TF minimum/maximum tie rules). */
+int air_bce_loss(const float *canvas, const float *x, float *recon, float *rec_loss, float *dcanvas, float dscale,
+                 int64_t B, int N, air_stream_t stream);
+
+/* air_model.py:593-611: out[0] = mean(running_loss + rec_loss), out[1] = mean(target == digits);
+ * loss_per_item (nullable) [B]. */
+int air_finalize_loss(const float *running_loss, const float *rec_loss, const int32_t *digits, const int32_t *target,
+                      float *out, float *loss_per_item, int64_t B, air_stream_t stream);
+
+/* out[n] (+)= sum_b X[b, n]  (bias gradients); deterministic.  workspace >= air_colsum_workspace(B, N) floats,
+ * zero-initialised once by the caller (the kernel leaves its counters zeroed). */
+int64_t air_colsum_workspace(int64_t B, int N);
+int air_colsum(const float *X, int ld, float *out, int accumulate, float *workspace, int64_t B, int N,
+               air_stream_t stream);
+
+/* air_model.py:673, 692: tf.clip_by_global_norm + tf.train.AdamOptimizer.apply_gradients on a flat
+ * parameter buffer of n floats.  state (device, 8 floats): [0] beta1^t, [1] beta2^t, [2] global_step,
+ * [3] last global norm, [4] learning rate; updated in place (t -> t+1).  clip_norm <= 0 disables clipping.
+ * grad_scale multiplies the gradients first (1/world_size after an allreduce-sum).
+ * workspace >= air_adam_workspace(n) floats. */
+int64_t air_adam_workspace(int64_t n);
+int air_adam_step(float *params, const float *grads, float *m, float *v, float *state, float clip_norm, float beta1,
+                  float beta2, float epsilon, float grad_scale, float *workspace, int64_t n, air_stream_t stream);
+
+/* air_model.py:94-121: value = init * factor^(step/iters) [floor if staircase], clamped to
+ * [min,max] (NaN = no bound), optional log(value + 1e-9); step read from adam state[2].
+ * Writes the device scalar *out. */
+int air_anneal(const float *state, float init, float factor, float iters, int staircase, float vmin, float vmax,
+               int take_log, float *out, air_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+"""Shared helpers for the parity tests and __graft_entry__.smoke() (test infrastructure)."""
+import numpy as np
+import torch
+
+from oracle import air_oracle as O
+
+
+def relnorm(a, b):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def covered_fixture(B, seed=0, T=3):
+    """Well-conditioned ("covered", SURVEY hard part 2) fixture: digits away from the canvas
+    border, windows that cover nearly the whole canvas (s ~ 0.98, tiny pose noise), all steps
+    live -- every lit pixel has reconstruction > 0, so no 1e9 gradient amplification."""
+    imgs, cnt = O.synthetic_canvases(B, seed=seed)
+    im = imgs.reshape(B, 50, 50).clone()
+    im[:, :7] = 0; im[:, -7:] = 0; im[:, :, :7] = 0; im[:, :, -7:] = 0
+    params = O.init_params(seed=seed)
+    params["scale/mean/output/biases"] += 4.0
+    params["scale/log_variance/output/biases"] -= 8.0
+    params["shift/log_variance/output/biases"] -= 8.0
+    params["shift/mean/output/weights"] *= 0.05
+    params["z_pres/log_odds/output/biases"] += 5.0
+    return im.reshape(B, -1).contiguous(), cnt, params, O.make_noise(seed, T, B)
+
+
+def default_fixture(B, seed=0, T=3):
+    imgs, cnt = O.synthetic_canvases(B, seed=seed)
+    return imgs, cnt, O.init_params(seed=seed), O.make_noise(seed, T, B)
+
+
+def make_pair(imgs, cnt, params, train=True, global_step=2000, gemm_mode="fp32", **hyper):
+    """(oracle, cuda model) with identical parameters / hyper-parameters / global step."""
+    import air_b200 as ab
+    h = dict(O.DEFAULT_HYPER)
+    h.update(hyper)
+    orc = O.AIROracle(params={k: v.clone() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING,
+                      train=train, **hyper)
+    orc.global_step = global_step
+    ab.reset_variable_scopes()
+    m = ab.AIRModel(imgs.cuda(), cnt.cuda(), train=train, annealing_schedules=O.DEFAULT_ANNEALING, gemm_mode=gemm_mode,
+                    **{k: v for k, v in h.items()})
+    m.store.load_named({k: v.cuda() for k, v in params.items()})
+    m.store.global_step = global_step
+    return orc, m
+
+
+def cuda_noise(noise):
+    return {k: v.cuda() for k, v in noise.items()}
+
+
+def smoke_model():
+    """One tiny train step of the full model on cuda:0, checked against the oracle."""
+    imgs, cnt, params, noise = covered_fixture(8, seed=0)
+    orc, m = make_pair(imgs, cnt, params, train=True)
+    out, grads = orc.loss_and_grads(imgs, cnt, noise)
+    m.loss_and_grads(cuda_noise(noise))
+    assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"]), "digit counts differ from the oracle"
+    rel = abs(m.loss.item() - out["loss"].item()) / abs(out["loss"].item())
+    assert rel < 1e-5, f"loss differs from the oracle by {rel:.2e}"
+    worst = max(relnorm(g, grads[k]) for k, g in m.store.named_grads().items())
+    assert worst < 1e-4, f"gradient differs from the oracle by {worst:.2e}"
+    m._apply_gradients()
+    torch.cuda.synchronize()
+    print(f"smoke model OK: loss rel err {rel:.2e}, worst grad rel err {worst:.2e}")

@@ -37,6 +37,7 @@ def test_no_cpu_fallback():
 def test_bad_arguments_are_rejected_before_launch():
     l = ab._cabi.lib()
     assert l.air_st_forward(None, None, None, 1, 4, 4, 1, 2, 2, None) == -5   # AIR_ERR_NULL
+    assert l.air_st_forward(None, None, None, 0, 4, 4, 1, 2, 2, None) == 0    # empty batch: no pointers needed
     one = ctypes.c_void_p(16)
     assert l.air_st_forward(one, one, one, 1, 0, 4, 1, 2, 2, None) == -1       # AIR_ERR_BAD_SHAPE
     assert b"bad shape" in l.air_last_error()

@@ -1,0 +1,193 @@
+"""GPU unit parity tests of the dense / elementwise kernels behind the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import air_b200 as ab
+from air_b200 import ops
+from oracle import air_oracle as O
+from oracle import c_oracle as C
+from tests.parity_util import relnorm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+K = ab._cabi
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(64, 64, 64), (130, 70, 33), (257, 320, 256), (5, 7, 3), (300, 100, 50),
+                                    (1, 1, 1), (128, 1024, 2500), (2500, 1024, 64)])
+@pytest.mark.parametrize("tA,tB", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_exact_is_k_sequential_fma(M, N, Kd, tA, tB):
+    rng = np.random.RandomState(M + N + Kd)
+    A = rng.randn(M, Kd).astype(np.float32)
+    Bm = rng.randn(Kd, N).astype(np.float32)
+    Ci = rng.randn(M, N).astype(np.float32)
+    bias = rng.randn(N).astype(np.float32)
+    want = C.gemm_seq_fma(A, Bm, Ci, bias)
+    At = cu(A.T.copy()) if tA else cu(A)
+    Bt = cu(Bm.T.copy()) if tB else cu(Bm)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(At, Bt, out, Cinit=cu(Ci), bias=cu(bias), tA=tA, tB=tB)
+    assert np.array_equal(out.cpu().numpy(), want)
+    # accumulate in place (Cinit aliases out) and no bias
+    out2 = cu(Ci).clone()
+    ops.gemm(At, Bt, out2, Cinit=out2, tA=tA, tB=tB)
+    assert np.array_equal(out2.cpu().numpy(), C.gemm_seq_fma(A, Bm, Ci, None))
+
+
+def test_gemm_strided_views_and_epilogues():
+    rng = np.random.RandomState(0)
+    big = cu(rng.randn(40, 100).astype(np.float32))
+    A = big[:, 10:60]                       # [40,50] view, lda = 100
+    W = cu(rng.randn(50, 24).astype(np.float32))
+    b = cu(rng.randn(24).astype(np.float32))
+    pre = torch.from_numpy(C.gemm_seq_fma(A.cpu().numpy(), W.cpu().numpy(), None, b.cpu().numpy()))
+    for epi, f in ((K.EPI_RELU, torch.relu), (K.EPI_SOFTPLUS, O.tf_softplus), (K.EPI_NONE, lambda v: v)):
+        out = torch.empty(40, 24, device=DEV)
+        ops.gemm(A, W, out, bias=b, epi=epi)
+        np.testing.assert_allclose(out.cpu().numpy(), f(pre).numpy(), rtol=2e-6, atol=1e-7)
+    # backward epilogues: dX = (dY W^T) * act'(aux)
+    dY = cu(rng.randn(40, 24).astype(np.float32))
+    x_pre = torch.from_numpy(rng.randn(40, 50).astype(np.float32) * 6)
+    for epi, post, dact in ((K.EPI_MUL_DRELU, torch.relu(x_pre), (x_pre > 0).float()),
+                            (K.EPI_MUL_DSOFTPLUS, O.tf_softplus(x_pre), torch.sigmoid(x_pre))):
+        dX = torch.empty(40, 50, device=DEV)
+        ops.gemm(dY, W, dX, tB=True, aux=post.to(DEV), epi=epi)
+        want = (dY.cpu() @ W.cpu().t()) * dact
+        assert relnorm(dX, want) < 2e-6
+
+
+def test_softplus_backward_tiny_activations():
+    """softplus' from the stored OUTPUT must stay accurate for very negative inputs (expm1)."""
+    x = torch.tensor([[-20.0, -14.0, -10.0, -3.0, 0.0, 5.0, 14.5, 30.0]])
+    post = O.tf_softplus(x)
+    dX = torch.empty(1, 8, device=DEV)
+    ops.gemm(torch.ones(1, 1, device=DEV), torch.ones(8, 1, device=DEV), dX, tB=True, aux=post.to(DEV),
+             epi=K.EPI_MUL_DSOFTPLUS)
+    np.testing.assert_allclose(dX.cpu().numpy(), torch.sigmoid(x.double()).numpy(), rtol=3e-6)
+
+
+def test_gemm_errors():
+    a = torch.zeros(4, 4, device=DEV)
+    with pytest.raises(ab.AirError):
+        ops.gemm(a, torch.zeros(5, 4, device=DEV), torch.zeros(4, 4, device=DEV))
+    with pytest.raises(ab.AirError, match="tcgen05|TF32|UNSUPPORTED|not built|code -4|shape"):
+        ops.gemm(a, a, torch.zeros(4, 4, device=DEV), epi=K.EPI_MUL_DRELU)  # needs aux
+
+
+def test_lstm_pointwise_fwd_bwd():
+    torch.manual_seed(0)
+    B, H = 37, 256
+    gates = torch.randn(B, 4 * H, requires_grad=True)
+    c0 = torch.randn(B, H, requires_grad=True)
+    gi, gj, gf, go = torch.split(gates, H, dim=1)
+    c = c0 * torch.sigmoid(gf + 1.0) + torch.sigmoid(gi) * torch.tanh(gj)
+    h = torch.tanh(c) * torch.sigmoid(go)
+    dh, dc = torch.randn(B, H), torch.randn(B, H)
+    (h * dh).sum().add((c * dc).sum()).backward()
+    cg, hg = torch.empty(B, H, device=DEV), torch.empty(B, H, device=DEV)
+    ops.lstm_fwd(gates.detach().to(DEV), c0.detach().to(DEV), cg, hg)
+    np.testing.assert_allclose(cg.cpu().numpy(), c.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(hg.cpu().numpy(), h.detach().numpy(), rtol=1e-5, atol=1e-6)
+    dg, dcp = torch.empty(B, 4 * H, device=DEV), torch.empty(B, H, device=DEV)
+    dsum = torch.ones(B, 4 * H, device=DEV)
+    ops.lstm_bwd(gates.detach().to(DEV), c0.detach().to(DEV), cg, dh.to(DEV), dc.to(DEV), dg, dcp, dsum)
+    assert relnorm(dg, gates.grad) < 1e-5 and relnorm(dcp, c0.grad) < 1e-5
+    assert relnorm(dsum - 1.0, gates.grad) < 1e-5
+    # zero initial state (c_prev = NULL)
+    ops.lstm_fwd(gates.detach().to(DEV), None, cg, hg)
+    c_z = torch.sigmoid(gi) * torch.tanh(gj)
+    np.testing.assert_allclose(cg.cpu().numpy(), c_z.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_bce_loss_and_grad():
+    rng = np.random.RandomState(1)
+    B, N = 9, 2500
+    canvas = (rng.rand(B, N).astype(np.float32) * 1.6 - 0.3)
+    canvas[0, :5] = [0.0, 1.0, -0.0, 1.0000001, -1e-8]           # tie rules at the clip boundaries
+    x = (rng.rand(B, N) > 0.8).astype(np.float32) * rng.rand(B, N).astype(np.float32)
+    ct = torch.from_numpy(canvas).requires_grad_(True)
+    r = torch.clamp(ct, 0.0, 1.0)
+    xt = torch.from_numpy(x)
+    rl = -torch.sum(xt * torch.log(r + O.EPS) + (1.0 - xt) * torch.log(1.0 - r + O.EPS), 1)
+    (rl.sum() * 0.125).backward()
+    recon, loss, dcv = torch.empty(B, N, device=DEV), torch.empty(B, device=DEV), torch.empty(B, N, device=DEV)
+    ops.bce_loss(cu(canvas), cu(x), recon, loss, dcv, 0.125)
+    assert np.array_equal(recon.cpu().numpy(), r.detach().numpy())
+    np.testing.assert_allclose(loss.cpu().numpy(), rl.detach().numpy(), rtol=2e-6)
+    assert relnorm(dcv, ct.grad) < 1e-6
+    assert np.array_equal(dcv.cpu().numpy() != 0, ct.grad.numpy() != 0)   # identical pass/block pattern
+
+
+def test_colsum_deterministic():
+    rng = np.random.RandomState(2)
+    for B, N in ((4096, 1024), (100, 7), (33, 320), (1, 50)):
+        X = rng.randn(B, N).astype(np.float32)
+        ws = torch.zeros(int(K.lib().air_colsum_workspace(B, N)), device=DEV)
+        out = torch.full((N,), 3.0, device=DEV)
+        ops.colsum(cu(X), out, False, ws)
+        np.testing.assert_allclose(out.cpu().numpy(), X.astype(np.float64).sum(0), rtol=1e-5, atol=1e-4)
+        first = out.clone()
+        ops.colsum(cu(X), out, True, ws)
+        np.testing.assert_allclose(out.cpu().numpy(), 2 * first.cpu().numpy(), rtol=1e-6)
+        again = torch.empty(N, device=DEV)
+        ops.colsum(cu(X), again, False, ws)
+        assert torch.equal(again, first)
+
+
+def test_adam_step_matches_tf_semantics():
+    torch.manual_seed(3)
+    orc = O.AIROracle(seed=1)
+    st = ab.ParamStore(DEV, 2500, 784, 256, 64, 50, (512, 256), (256, 512), seed=1)
+    st.state[4] = 1e-4
+    ws = torch.zeros(int(K.lib().air_adam_workspace(st.n)), device=DEV)
+    for step in range(3):
+        grads = {k: torch.randn_like(v) * (10.0 if step == 0 else 1e-3) for k, v in orc.params.items()}
+        for k, gview in st.named_grads().items():
+            gview.copy_(grads[k].to(DEV))
+        clipped, norm = O.AIROracle.clip_by_global_norm(grads, 1.0)
+        orc.adam_apply(clipped)
+        ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, 1.0, 0.9, 0.999, 1e-8, 1.0, ws)
+        assert abs(st.state[3].item() - norm.item()) / norm.item() < 1e-5
+        for k, v in st.named_views().items():
+            np.testing.assert_allclose(v.cpu().numpy(), orc.params[k].numpy(), rtol=2e-5, atol=2e-8, err_msg=k)
+    assert st.global_step == 3
+    np.testing.assert_allclose(st.state[:2].cpu().numpy(), [0.9 ** 4, 0.999 ** 4], rtol=1e-6)
+
+
+def test_anneal_kernel():
+    st = torch.zeros(8, device=DEV)
+    out = torch.zeros(1, device=DEV)
+    sched = O.DEFAULT_ANNEALING["z_pres_prior_log_odds"]
+    for step in (0, 1, 2999, 3000, 10000, 60000):
+        st[2] = float(step)
+        ops.anneal(st, sched, out)
+        assert out.item() == pytest.approx(O.annealed_value(sched, step).item(), rel=2e-5, abs=1e-6)
+
+
+def test_vae_function_reference_signature():
+    torch.manual_seed(4)
+    B = 33
+    x = torch.rand(B, 784)
+    n1, n2 = torch.randn(B, 50), torch.randn(B, 784)
+    xg = x.to(DEV).requires_grad_(True)
+    rec, mean, logvar, latent = ab.vae(xg, 784, (512, 256), 50, (256, 512), 0.3, scope="t_vae", seed=5,
+                                       noise_latent=n1.to(DEV), noise_like=n2.to(DEV))
+    assert latent is mean                                    # vae.py:43 returns the mean twice
+    store = ab.air.vae.variables("t_vae")[0] if hasattr(ab, "air") else None
+    from importlib import import_module
+    store = import_module("tf-attend-infer-repeat_b200.air.vae").variables("t_vae")[0]
+    params = {"vae/" + k[4:]: v.cpu() for k, v in store.named_views().items() if k.startswith("vae/")}
+    xt = x.clone().requires_grad_(True)
+    orec, omean, olv, _ = O.vae(xt, params, "vae/", 2, 2, n1, n2, 0.3)
+    np.testing.assert_allclose(rec.detach().cpu().numpy(), orec.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mean.detach().cpu().numpy(), omean.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(logvar.detach().cpu().numpy(), olv.detach().numpy(), rtol=1e-5, atol=1e-6)
+    g = torch.randn(B, 784)
+    orec.backward(g)
+    rec.backward(g.to(DEV))
+    assert relnorm(xg.grad, xt.grad) < 1e-4

@@ -9,9 +9,13 @@ include/air_b200.h; PyTorch only owns device memory, streams and torch.distribut
 from . import _cabi
 from ._cabi import AirError, build, launch_count
 from .air.transformer import transformer, batch_transformer, writeback_canvas
+from .air.vae import vae
+from .air.air_model import AIRModel, reset_variable_scopes
+from .air.params import ParamStore
+from . import ops
 from .air.concrete import (concrete_binary_sample, concrete_binary_pre_sigmoid_sample,
                            concrete_binary_kl_mc_sample, concrete_step)
 
-__all__ = ["transformer", "batch_transformer", "writeback_canvas", "concrete_binary_sample",
+__all__ = ["AIRModel", "vae", "ParamStore", "ops", "reset_variable_scopes", "transformer", "batch_transformer", "writeback_canvas", "concrete_binary_sample",
            "concrete_binary_pre_sigmoid_sample", "concrete_binary_kl_mc_sample", "concrete_step",
            "AirError", "build", "launch_count"]

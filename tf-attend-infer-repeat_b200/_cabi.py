@@ -30,7 +30,41 @@ _SIGS = {
     "air_concrete_step_fwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_float, ctypes.c_int] + [_c_f] * 7 +
                               [ctypes.c_int64, _c_f]),
     "air_concrete_step_bwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
+    "air_gemm": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 9 + [_c_f]),
+    "air_lstm_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_lstm_bwd": (ctypes.c_int, [_c_f] * 8 + [ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_heads_fwd": (ctypes.c_int, [_c_f] * 14 + [ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_heads_bwd_workspace": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int]),
+    "air_heads_bwd": (ctypes.c_int, [_c_f] * 10 + [ctypes.c_float] + [_c_f] * 3 + [ctypes.c_int, _c_f, ctypes.c_int64,
+                                                                                 ctypes.c_int, _c_f]),
+    "air_vae_latent_fwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_vae_latent_bwd": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float, _c_f, ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_sigmoid_noise_fwd": (ctypes.c_int, [_c_f, _c_f, ctypes.c_float, _c_f, ctypes.c_int64, _c_f]),
+    "air_sigmoid_bwd": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int64, _c_f]),
+    "air_bce_loss": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float, ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_finalize_loss": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64, _c_f]),
+    "air_colsum_workspace": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int]),
+    "air_colsum": (ctypes.c_int, [_c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_adam_workspace": (ctypes.c_int64, [ctypes.c_int64]),
+    "air_adam_step": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float] * 5 + [_c_f, ctypes.c_int64, _c_f]),
+    "air_anneal": (ctypes.c_int, [_c_f] + [ctypes.c_float] * 3 + [ctypes.c_int] + [ctypes.c_float] * 2 +
+                   [ctypes.c_int, _c_f, _c_f]),
 }
+
+
+class Hyper(ctypes.Structure):
+    """air_hyper_t (include/air_b200.h)."""
+    _fields_ = [(n, ctypes.c_float) for n in (
+        "scale_prior_mean", "scale_prior_variance", "shift_prior_mean", "shift_prior_variance", "vae_prior_mean",
+        "vae_prior_variance", "vae_likelihood_std", "z_pres_temperature", "stopping_threshold")] + [("train", ctypes.c_int32)]
+
+
+# enum air_field
+(F_SCALE_MEAN, F_SCALE_LV, F_SHIFT_MEAN_X, F_SHIFT_MEAN_Y, F_SHIFT_LV_X, F_SHIFT_LV_Y, F_LOG_ODDS, F_S, F_X, F_Y,
+ F_YPRE, F_Z, F_ZPROB, F_KL_Z, F_KL_SCALE, F_KL_SHIFT, F_KL_VAE, F_STOP_PREV, F_STOP_NEW) = range(19)
+NF = 20
+EPI_NONE, EPI_RELU, EPI_SOFTPLUS, EPI_MUL_DRELU, EPI_MUL_DSOFTPLUS = range(5)
+GEMM_MODES = {"fp32": 0, "tf32": 1}
 
 _lib = None
 

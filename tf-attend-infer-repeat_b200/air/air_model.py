@@ -1,0 +1,385 @@
+"""AIRModel with the reference constructor (air/air_model.py:13-22), B200-native underneath.
+
+The reference builds a TF graph (tf.while_loop over body(), air_model.py:278-508) and the
+caller fetches result attributes with session.run.  Here the object is eager:
+
+    model = AIRModel(images, targets, max_steps=3, ..., train=True)       # same kwargs
+    model.train_step()            # == sess.run(model.training): forward, backward, clip, Adam
+    model.run()                   # forward only (what fetching .loss / .rec_* evaluates)
+    model.loss, model.accuracy, model.rec_num_digits, model.rec_scales, ...   # CUDA tensors
+
+``input_images`` / ``target_num_digits`` play the role of the reference's input tensors:
+persistent CUDA buffers that the caller refills (``feed``).  All arithmetic is hand-written
+CUDA behind the C ABI (csrc/); the schedule below only orders kernel launches on the current
+stream, so a whole step can be captured in a CUDA graph (``capture()``).
+
+Differences from the reference, by design:
+  * the loop always runs ``max_steps`` iterations (no device->host sync for the batch-global
+    early exit, air_model.py:271-275); stopped items contribute exact +0.0, so loss, canvas,
+    digit counts and gradients are identical.  Per-step outputs therefore have
+    time dimension ``max_steps``; ``executed_steps`` gives the reference's dynamic trip count.
+  * sampling noise can be injected (``noise=`` dict of [T,B,...] tensors) for reproducibility;
+    otherwise it is drawn with torch's CUDA generator into persistent buffers.
+  * the image part of the LSTM input projection (x @ K[:2500]) is step-invariant
+    (air_model.py:535: rnn_input is the raw image every step) and is computed once.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import _cabi as C
+from .. import ops
+from .params import ParamStore
+from .vae import (VAEWeights, alloc_vae_scratch, dense_bwd, vae_backward, vae_forward)
+
+_VARIABLE_SCOPES = {}
+
+_DEVICE_ANNEALABLE = ("z_pres_prior_log_odds", "learning_rate")
+
+
+def reset_variable_scopes():
+    """Forget all shared variable stores (the equivalent of tf.reset_default_graph())."""
+    _VARIABLE_SCOPES.clear()
+
+
+class AIRModel:
+
+    def __init__(self, input_images, target_num_digits,
+                 max_steps=3, max_digits=2, rnn_units=256, canvas_size=50, windows_size=28,
+                 vae_latent_dimensions=50, vae_recognition_units=(512, 256), vae_generative_units=(256, 512),
+                 scale_prior_mean=-1.0, scale_prior_variance=0.1, shift_prior_mean=0.0, shift_prior_variance=1.0,
+                 vae_prior_mean=0.0, vae_prior_variance=1.0, vae_likelihood_std=0.3,
+                 scale_hidden_units=64, shift_hidden_units=64, z_pres_hidden_units=64,
+                 z_pres_prior_log_odds=-2.0, z_pres_temperature=1.0, stopping_threshold=0.99,
+                 learning_rate=1e-3, gradient_clipping_norm=100.0, cnn=True, cnn_filters=8,
+                 num_summary_images=60, train=False, reuse=False, scope="air",
+                 annealing_schedules=None, *, gemm_mode="fp32", seed=0, process_group=None):
+        if cnn:
+            raise NotImplementedError(
+                "cnn=True (air_model.py:510-535) is outside the accelerated hot path (SURVEY.md section 8f); "
+                "training.py, demo.py and the shipped checkpoint all use cnn=False")
+        if not (scale_hidden_units == shift_hidden_units == z_pres_hidden_units):
+            raise NotImplementedError("the fused heads kernel needs equal scale/shift/z_pres hidden sizes")
+        if not input_images.is_cuda:
+            raise C.AirError("AIRModel needs CUDA tensors (no CPU fallback)")
+        C.lib()  # fail loudly if the extension is missing
+
+        self.input_images = C.f32(input_images)
+        self.target_num_digits = target_num_digits.to(torch.int32).contiguous()
+        self.batch_size = int(input_images.shape[0])
+        for k, v in list(locals().items()):
+            if k not in ("self", "input_images", "target_num_digits", "k", "v"):
+                setattr(self, k, v)
+        self.vae_recognition_units = tuple(vae_recognition_units)
+        self.vae_generative_units = tuple(vae_generative_units)
+        self.gemm = C.GEMM_MODES[gemm_mode]
+        self.device = input_images.device
+        self.num_summaries, self.img_summaries, self.var_summaries, self.grad_summaries = [], [], [], []
+        assert self.input_images.shape[1] == canvas_size * canvas_size
+
+        # ---- variables: shared by scope, like tf.variable_scope(scope, reuse=reuse) (air_model.py:68)
+        key = (scope, self.device)
+        if reuse:
+            if key not in _VARIABLE_SCOPES:
+                raise ValueError(f"variable scope {scope!r} does not exist (reuse=True)")
+            self.store = _VARIABLE_SCOPES[key]
+        else:
+            self.store = ParamStore(self.device, canvas_size * canvas_size, windows_size * windows_size, rnn_units,
+                                    scale_hidden_units, vae_latent_dimensions, self.vae_recognition_units,
+                                    self.vae_generative_units, seed=seed)
+            _VARIABLE_SCOPES[key] = self.store
+        if train:
+            self.store.state[4] = float(learning_rate if not self._annealed("learning_rate") else 0.0)
+
+        # ---- annealed hyper-parameters (air_model.py:76-82): evaluated on device from global_step
+        self.annealing_schedules = annealing_schedules or {}
+        for name in self.annealing_schedules:
+            if name not in _DEVICE_ANNEALABLE:
+                raise NotImplementedError(f"annealing of {name!r} is not supported on device "
+                                          f"(supported: {_DEVICE_ANNEALABLE})")
+        self._prior = torch.full((1,), float(z_pres_prior_log_odds), device=self.device, dtype=torch.float32)
+        self.hyper = C.Hyper(scale_prior_mean, scale_prior_variance, shift_prior_mean, shift_prior_variance,
+                             vae_prior_mean, vae_prior_variance, vae_likelihood_std, z_pres_temperature,
+                             stopping_threshold, 1 if train else 0)
+
+        # ---- data parallelism: one process per GPU, gradients all-reduced over NCCL
+        self.world = 1
+        self.pg = process_group
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+
+        self._alloc()
+        self._graphs = None
+        self.noise = None
+        self.rec_num_digits = self.rec_scales = self.reconstruction = None
+        self.loss = self.accuracy = None
+        self.training = self.train_step if train else None
+
+    # ------------------------------------------------------------------------------------------
+    def _annealed(self, name):
+        return bool(getattr(self, "annealing_schedules", None)) and name in self.annealing_schedules
+
+    @property
+    def global_step(self):
+        return self.store.global_step
+
+    def _alloc(self):
+        B, T, dev = self.batch_size, self.max_steps, self.device
+        R, HU, L = self.rnn_units, self.scale_hidden_units, self.vae_latent_dimensions
+        win, cs2 = self.windows_size ** 2, self.canvas_size ** 2
+        z = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        w = self.w = {}
+        w["xk"] = z(B, 4 * R)
+        w["h0"] = torch.zeros(B, R, device=dev)
+        w["gates"], w["c"], w["h"] = z(T, B, 4 * R), z(T, B, R), z(T, B, R)
+        w["hh"] = z(T, B, 5 * HU)
+        w["fields"] = torch.zeros(T, C.NF, B, device=dev)
+        w["theta"], w["theta_inv"] = z(T, B, 6), z(T, B, 6)
+        w["win"] = z(T, B, win)
+        w["enc"] = [z(T, B, u) for u in self.vae_recognition_units]
+        w["ml"], w["zs"] = z(T, B, 2 * L), z(T, B, L)
+        w["dec"] = [z(T, B, u) for u in self.vae_generative_units]
+        w["recon"] = z(T, B, win)
+        w["gen"] = z(B, win)
+        w["stop"], w["loss"], w["rec_loss"], w["loss_item"] = z(B), z(B), z(B), z(B)
+        w["digits"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        w["canvas"], w["reconstruction"] = z(B, cs2), z(B, cs2)
+        w["out2"] = torch.zeros(2, device=dev)
+        w["noise"] = dict(scale=z(T, B, 1), shift=z(T, B, 2), vae_latent=z(T, B, L), vae_like=z(T, B, win),
+                          concrete_u=z(T, B))
+        if self.train:
+            w["dcanvas"] = z(B, cs2)
+            w["d_recon"] = z(B, win)
+            w["dwin"] = z(B, win)
+            w["dtheta"], w["dtheta_inv"], w["dz"] = z(B, 6), z(B, 6), z(B)
+            w["dhh"] = z(B, 5 * HU)
+            w["dh"], w["dh_next"], w["dc"] = z(B, R), z(B, R), z(B, R)
+            w["dgates"], w["dgates_sum"] = z(B, 4 * R), z(B, 4 * R)
+            w["vae_scratch"] = alloc_vae_scratch(B, win, self.vae_recognition_units, L, self.vae_generative_units, dev)
+            nmax = max(4 * R, 5 * HU, win, 2 * L, *self.vae_recognition_units, *self.vae_generative_units)
+            w["colsum_ws"] = torch.zeros(int(C.lib().air_colsum_workspace(B, nmax)), device=dev)
+            w["heads_ws"] = torch.zeros(int(C.lib().air_heads_bwd_workspace(B, HU)), device=dev)
+            w["adam_ws"] = torch.zeros(int(C.lib().air_adam_workspace(self.store.n)), device=dev)
+        p, g = self.store.p, self.store.g
+        in_dim = cs2
+        self.Kx, self.Kh = p["rnn/kernel"][:in_dim], p["rnn/kernel"][in_dim:]
+        self.gKx, self.gKh = g["rnn/kernel"][:in_dim], g["rnn/kernel"][in_dim:]
+        self.vw = VAEWeights(p, g, len(self.vae_recognition_units), len(self.vae_generative_units))
+
+    # ------------------------------------------------------------------------------------------
+    def feed(self, input_images, target_num_digits=None):
+        """Refill the input buffers in place (the feed_dict of the reference)."""
+        self.input_images.copy_(input_images, non_blocking=True)
+        if target_num_digits is not None:
+            self.target_num_digits.copy_(target_num_digits, non_blocking=True)
+
+    def set_noise(self, noise):
+        """Inject the five noise tensors ([T,B,1], [T,B,2], [T,B,L], [T,B,win], [T,B])."""
+        for k, buf in self.w["noise"].items():
+            buf.copy_(noise[k].reshape(buf.shape))
+        self.noise = "injected"
+
+    def _draw_noise(self):
+        n = self.w["noise"]
+        for k in ("scale", "shift", "vae_latent", "vae_like"):
+            n[k].normal_()
+        n["concrete_u"].uniform_()
+
+    def _update_scalars(self):
+        st = self.store.state
+        if self._annealed("z_pres_prior_log_odds"):
+            ops.anneal(st, self.annealing_schedules["z_pres_prior_log_odds"], self._prior)
+        if self.train and self._annealed("learning_rate"):
+            ops.anneal(st, self.annealing_schedules["learning_rate"], st[4:5])
+
+    # ------------------------------------------------------------------------------------------
+    # forward: air_model.py:278-508 (loop body) + :580-611 (loss / accuracy)
+    # ------------------------------------------------------------------------------------------
+    def _forward(self):
+        w, hp, mode = self.w, self.hyper, self.gemm
+        B, T = self.batch_size, self.max_steps
+        x = self.input_images
+        p = self.store.p
+        cs, wsz = self.canvas_size, self.windows_size
+        n = w["noise"]
+        w["stop"].zero_(); w["loss"].zero_(); w["digits"].zero_(); w["canvas"].zero_()
+        self._update_scalars()
+        # step-invariant image projection x @ K[:in_dim] (bias added per step, after the h part)
+        ops.gemm(x, self.Kx, w["xk"], mode=mode)
+        for t in range(T):
+            h_prev = w["h"][t - 1] if t > 0 else w["h0"]
+            c_prev = w["c"][t - 1] if t > 0 else None
+            # LSTM: gates = ([x,h] K) + b, accumulated in concat order (x part first)
+            ops.gemm(h_prev, self.Kh, w["gates"][t], Cinit=w["xk"], bias=p["rnn/bias"], mode=mode)
+            ops.lstm_fwd(w["gates"][t], c_prev, w["c"][t], w["h"][t])
+            # five hidden head layers as one GEMM + ReLU; outputs, sampling, KLs, theta, z_pres fused
+            ops.gemm(w["h"][t], p["heads/hidden_w"], w["hh"][t], bias=p["heads/hidden_b"], epi=C.EPI_RELU, mode=mode)
+            ops.heads_fwd(w["hh"][t], p["heads/out_w"], p["heads/out_b"], n["scale"][t], n["shift"][t],
+                          n["concrete_u"][t], self._prior, hp, w["stop"], w["loss"], w["digits"], w["fields"][t],
+                          w["theta"][t], w["theta_inv"][t])
+            # attention crop, VAE, write-back + canvas
+            ops.st_forward(x, w["theta"][t], w["win"][t], cs, cs, 1, wsz, wsz)
+            buf = self._vae_buf(t)
+            vae_forward(w["win"][t], self.vw, n["vae_latent"][t], n["vae_like"][t], self.vae_likelihood_std, hp, buf,
+                        w["gen"], w["fields"][t], w["loss"], mode)
+            f = w["fields"][t]
+            ops.writeback_canvas_fwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
+                                     self.stopping_threshold, w["canvas"], w["canvas"], wsz, wsz, cs, cs)
+        dscale = 1.0 / (B * self.world)
+        ops.bce_loss(w["canvas"], x, w["reconstruction"], w["rec_loss"], w["dcanvas"] if self.train else None, dscale)
+        ops.finalize_loss(w["loss"], w["rec_loss"], w["digits"], self.target_num_digits, w["out2"], w["loss_item"])
+
+    def _vae_buf(self, t):
+        w = self.w
+        return dict(enc=[e[t] for e in w["enc"]], ml=w["ml"][t], zs=w["zs"][t], dec=[d[t] for d in w["dec"]],
+                    recon=w["recon"][t])
+
+    # ------------------------------------------------------------------------------------------
+    # backward: what TF autodiff derives for air_model.py:655 (gradients of the mean loss)
+    # ------------------------------------------------------------------------------------------
+    def _backward(self):
+        w, hp, mode = self.w, self.hyper, self.gemm
+        B, T = self.batch_size, self.max_steps
+        x = self.input_images
+        p, g = self.store.p, self.store.g
+        cs, wsz = self.canvas_size, self.windows_size
+        n = w["noise"]
+        dscale = 1.0 / (B * self.world)
+        w["dgates_sum"].zero_()
+        if T == 1:
+            self.gKh.zero_()
+        for t in range(T - 1, -1, -1):
+            acc = t != T - 1
+            f = w["fields"][t]
+            ops.writeback_canvas_bwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
+                                     self.stopping_threshold, w["dcanvas"], w["d_recon"], w["dtheta_inv"], w["dz"],
+                                     wsz, wsz, cs, cs)
+            vae_backward(w["win"][t], self.vw, n["vae_latent"][t], hp, self._vae_buf(t), w["d_recon"], dscale, f,
+                         w["vae_scratch"], acc, w["colsum_ws"], mode, dx_out=w["dwin"])
+            ops.st_backward(x, w["theta"][t], w["dwin"], None, w["dtheta"], cs, cs, 1, wsz, wsz)
+            ops.heads_bwd(w["hh"][t], p["heads/out_w"], n["scale"][t], n["shift"][t], f, w["dtheta"], w["dtheta_inv"],
+                          w["dz"], self._prior, hp, dscale, w["dhh"], g["heads/out_w"], g["heads/out_b"], acc,
+                          w["heads_ws"])
+            # hidden head layer (input h_t, a tanh*sigmoid output: no activation mask on dX)
+            ops.gemm(w["h"][t], w["dhh"], g["heads/hidden_w"], Cinit=g["heads/hidden_w"] if acc else None, tA=True,
+                     mode=mode)
+            ops.colsum(w["dhh"], g["heads/hidden_b"], acc, w["colsum_ws"])
+            ops.gemm(w["dhh"], p["heads/hidden_w"], w["dh"], Cinit=w["dh_next"] if acc else None, tB=True, mode=mode)
+            ops.lstm_bwd(w["gates"][t], w["c"][t - 1] if t > 0 else None, w["c"][t], w["dh"],
+                         w["dc"] if acc else None, w["dgates"], w["dc"], w["dgates_sum"])
+            if t > 0:
+                ops.gemm(w["h"][t - 1], w["dgates"], self.gKh, Cinit=self.gKh if acc else None, tA=True, mode=mode)
+                ops.gemm(w["dgates"], self.Kh, w["dh_next"], tB=True, mode=mode)
+        # the image rows of the LSTM kernel see the same x every step: one GEMM on the summed dgates
+        ops.gemm(x, w["dgates_sum"], self.gKx, tA=True, mode=mode)
+        ops.colsum(w["dgates_sum"], g["rnn/bias"], False, w["colsum_ws"])
+
+    def _apply_gradients(self):
+        """air_model.py:673, 692: clip by global norm, Adam, global_step += 1."""
+        st = self.store
+        ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, self.gradient_clipping_norm, 0.9, 0.999, 1e-8,
+                      1.0, self.w["adam_ws"])
+
+    def _allreduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.store.grad, group=self.pg)  # SUM; dscale already has 1/world
+
+    # ------------------------------------------------------------------------------------------
+    # public API
+    # ------------------------------------------------------------------------------------------
+    def run(self, noise=None):
+        """Forward pass only (what session.run of any result attribute evaluates)."""
+        if noise is not None:
+            self.set_noise(noise)
+        elif self.noise != "injected":
+            self._draw_noise()
+        self._forward()
+        self._publish()
+        return self
+
+    infer = run
+
+    def loss_and_grads(self, noise=None):
+        """Forward + backward without the optimizer (gradients in store.named_grads())."""
+        if not self.train:
+            raise C.AirError("model was built with train=False")
+        self.run(noise)
+        self._backward()
+        self._allreduce()
+        return self.loss, self.store.named_grads()
+
+    def train_step(self, noise=None):
+        """One optimisation step == sess.run(model.training) (training.py:212-224)."""
+        if not self.train:
+            raise C.AirError("model was built with train=False")
+        if self._graphs is not None and noise is None:
+            g_fb, g_opt = self._graphs
+            g_fb.replay()
+            self._allreduce()
+            g_opt.replay()
+            return self
+        self.loss_and_grads(noise)
+        self._apply_gradients()
+        return self
+
+    def capture(self, warmup=3):
+        """Capture noise + forward + backward, and clip + Adam, as two CUDA graphs (the NCCL
+        allreduce between them stays eager).  Subsequent train_step() calls replay them."""
+        assert self.train and self.noise != "injected"
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._draw_noise(); self._forward(); self._backward()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fb):
+            self._draw_noise(); self._forward(); self._backward()
+        with torch.cuda.graph(g_opt):
+            self._apply_gradients()
+        self._graphs = (g_fb, g_opt)
+        self._publish()
+        return self
+
+    def _publish(self):
+        """Result attributes of the reference (air_model.py:569-611), as views (no copies)."""
+        w, L = self.w, self.vae_latent_dimensions
+        F = w["fields"]  # [T, NF, B]
+        col = lambda i: F[:, i, :].t()  # [B, T]
+        self.rec_num_digits = w["digits"]
+        self.rec_scales = col(C.F_S).unsqueeze(2)
+        self.rec_st_back = w["theta_inv"].permute(1, 0, 2).reshape(self.batch_size, self.max_steps, 2, 3)
+        self.rec_windows = w["recon"].permute(1, 0, 2)
+        self.rec_latents = w["ml"][:, :, :L].permute(1, 0, 2)
+        self.z_pres_probs, self.z_pres_kls = col(C.F_ZPROB), col(C.F_KL_Z)
+        self.scale_kls, self.shift_kls, self.vae_kls = col(C.F_KL_SCALE), col(C.F_KL_SHIFT), col(C.F_KL_VAE)
+        self.z_pres = col(C.F_Z)
+        self.reconstruction = w["reconstruction"]
+        self.reconstruction_loss = w["rec_loss"]
+        self.loss_per_item = w["loss_item"]
+        self.loss, self.accuracy = w["out2"][0], w["out2"][1]
+
+    @property
+    def rec_shifts(self):
+        """[B, T, 2] (air_model.py:570); a fresh stack of the x / y field rows."""
+        F = self.w["fields"]
+        return torch.stack([F[:, C.F_X, :].t(), F[:, C.F_Y, :].t()], dim=2)
+
+    @property
+    def stop_masks(self):
+        """[B, T] bool: stopping_sum < threshold after each step (the mask of air_model.py:427-496)."""
+        return self.w["fields"][:, C.F_STOP_NEW, :].t() < self.stopping_threshold
+
+    @property
+    def executed_steps(self):
+        """Trip count of the reference's while_loop (air_model.py:271-275); needs a host sync."""
+        live_before = (self.w["fields"][:, C.F_STOP_PREV, :] < self.stopping_threshold).any(dim=1).cpu().tolist()
+        n = 0
+        for t in range(self.max_steps):
+            if not live_before[t]:
+                break
+            n = t + 1
+        return n

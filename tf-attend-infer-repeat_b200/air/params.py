@@ -1,0 +1,177 @@
+"""Flat parameter / gradient / Adam-slot storage with checkpoint-named views.
+
+The reference keeps 36 separate TF variables under ``air/rnn/...`` (model/air-model.index;
+created at air_model.py:284-376, vae.py:11-34).  Here they live in ONE flat fp32 buffer
+(one NCCL allreduce, one fused clip+Adam launch), and tensors that feed the same GEMM are
+stored fused: the five 256->64 hidden head layers as one [256, 320] matrix, the seven
+head outputs as one [7, 64] matrix, rec_mean / rec_log_variance as one [256, 100] matrix.
+``named_views()`` exposes exactly the reference's variable names and shapes as (strided)
+views, so checkpoints and the oracle's parameter dict load/save by name.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+HEADS = (("scale", "mean"), ("scale", "log_variance"), ("shift", "mean"), ("shift", "log_variance"),
+         ("z_pres", "log_odds"))
+# rows of heads/out_w: (head block, first output column, number of outputs)
+HEAD_OUT_ROWS = ((0, 0, 1), (1, 1, 1), (2, 2, 2), (3, 4, 2), (4, 6, 1))
+
+
+def reference_shapes(in_dim, win, R, HU, L, rec_units, gen_units):
+    """name -> shape exactly as in model/air-model.index (minus the 'air/rnn/' prefix),
+    ordered rnn, scale, shift, z_pres, vae (the order only matters for the init RNG stream)."""
+    s = OrderedDict()
+    s["rnn/kernel"] = (in_dim + R, 4 * R)
+    s["rnn/bias"] = (4 * R,)
+    for head, stat in HEADS:
+        out = 2 if head == "shift" else 1
+        s[f"{head}/{stat}/hidden/weights"] = (R, HU)
+        s[f"{head}/{stat}/hidden/biases"] = (HU,)
+        s[f"{head}/{stat}/output/weights"] = (HU, out)
+        s[f"{head}/{stat}/output/biases"] = (out,)
+    prev = win
+    for i, u in enumerate(rec_units):
+        s[f"vae/recognition_{i + 1}/weights"] = (prev, u)
+        s[f"vae/recognition_{i + 1}/biases"] = (u,)
+        prev = u
+    for nm in ("rec_mean", "rec_log_variance"):
+        s[f"vae/{nm}/weights"] = (prev, L)
+        s[f"vae/{nm}/biases"] = (L,)
+    prev = L
+    for i, u in enumerate(gen_units):
+        s[f"vae/generative_{i + 1}/weights"] = (prev, u)
+        s[f"vae/generative_{i + 1}/biases"] = (u,)
+        prev = u
+    s["vae/gen_mean/weights"] = (prev, win)
+    s["vae/gen_mean/biases"] = (win,)
+    return s
+
+
+class ParamStore:
+    def __init__(self, device, in_dim, win, R, HU, L, rec_units, gen_units, seed=0):
+        self.device = torch.device(device)
+        self.dims = dict(in_dim=in_dim, win=win, R=R, HU=HU, L=L, rec_units=tuple(rec_units), gen_units=tuple(gen_units))
+        fused = OrderedDict()
+        fused["rnn/kernel"] = (in_dim + R, 4 * R)
+        fused["rnn/bias"] = (4 * R,)
+        fused["heads/hidden_w"] = (R, 5 * HU)
+        fused["heads/hidden_b"] = (5 * HU,)
+        fused["heads/out_w"] = (7, HU)
+        fused["heads/out_b"] = (7,)
+        prev = win
+        for i, u in enumerate(rec_units):
+            fused[f"vae/recognition_{i + 1}/weights"] = (prev, u)
+            fused[f"vae/recognition_{i + 1}/biases"] = (u,)
+            prev = u
+        fused["vae/rec_ml/weights"] = (prev, 2 * L)
+        fused["vae/rec_ml/biases"] = (2 * L,)
+        prev = L
+        for i, u in enumerate(gen_units):
+            fused[f"vae/generative_{i + 1}/weights"] = (prev, u)
+            fused[f"vae/generative_{i + 1}/biases"] = (u,)
+            prev = u
+        fused["vae/gen_mean/weights"] = (prev, win)
+        fused["vae/gen_mean/biases"] = (win,)
+        self.fused_shapes = fused
+        self.offsets = OrderedDict()
+        off = 0
+        for k, shp in fused.items():
+            self.offsets[k] = off
+            off += (int(math.prod(shp)) + 3) & ~3  # 16-byte aligned tensors
+        self.n = off
+        self.n_params = sum(int(math.prod(s)) for s in fused.values())
+        self.flat = torch.zeros(self.n, device=self.device, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.flat)
+        self.adam_m = torch.zeros_like(self.flat)
+        self.adam_v = torch.zeros_like(self.flat)
+        # [beta1^t, beta2^t, global_step, last global grad norm, learning rate, -, -, -]
+        self.state = torch.zeros(8, device=self.device, dtype=torch.float32)
+        self.reset_optimizer()
+        self.p = self._views(self.flat)
+        self.g = self._views(self.grad)
+        self.init_xavier(seed)
+
+    # ---- views -------------------------------------------------------------------------
+    def _views(self, flat):
+        return OrderedDict((k, flat[o:o + int(math.prod(self.fused_shapes[k]))].view(self.fused_shapes[k]))
+                           for k, o in self.offsets.items())
+
+    def _named(self, v):
+        d, HU, L = OrderedDict(), self.dims["HU"], self.dims["L"]
+        d["rnn/kernel"], d["rnn/bias"] = v["rnn/kernel"], v["rnn/bias"]
+        for (head, stat), (blk, row, nout) in zip(HEADS, HEAD_OUT_ROWS):
+            d[f"{head}/{stat}/hidden/weights"] = v["heads/hidden_w"][:, blk * HU:(blk + 1) * HU]
+            d[f"{head}/{stat}/hidden/biases"] = v["heads/hidden_b"][blk * HU:(blk + 1) * HU]
+            d[f"{head}/{stat}/output/weights"] = v["heads/out_w"][row:row + nout].t()
+            d[f"{head}/{stat}/output/biases"] = v["heads/out_b"][row:row + nout]
+        for k in v:
+            if k.startswith("vae/") and not k.startswith("vae/rec_ml/"):
+                d[k] = v[k]
+        d["vae/rec_mean/weights"] = v["vae/rec_ml/weights"][:, :L]
+        d["vae/rec_log_variance/weights"] = v["vae/rec_ml/weights"][:, L:]
+        d["vae/rec_mean/biases"] = v["vae/rec_ml/biases"][:L]
+        d["vae/rec_log_variance/biases"] = v["vae/rec_ml/biases"][L:]
+        return d
+
+    def named_views(self):
+        """reference variable name -> view of the flat parameter buffer."""
+        return self._named(self.p)
+
+    def named_grads(self):
+        return self._named(self.g)
+
+    def named_adam(self):
+        return self._named(self._views(self.adam_m)), self._named(self._views(self.adam_v))
+
+    # ---- init / load / save ------------------------------------------------------------------
+    def init_xavier(self, seed=0):
+        """glorot-uniform weights (limit sqrt(6/(fan_in+fan_out)) of the REFERENCE-shaped
+        tensor), zero biases: the TF defaults of fully_connected / BasicLSTMCell."""
+        g = torch.Generator().manual_seed(seed)
+        d = self.dims
+        named = self.named_views()
+        for name, shape in reference_shapes(d["in_dim"], d["win"], d["R"], d["HU"], d["L"], d["rec_units"],
+                                            d["gen_units"]).items():
+            if len(shape) == 2:
+                lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+                w = (torch.rand(shape, generator=g, dtype=torch.float64) * 2.0 - 1.0) * lim
+                named[name].copy_(w.to(torch.float32))
+            else:
+                named[name].zero_()
+
+    def load_named(self, tensors, strict=True):
+        named = self.named_views()
+        missing = [k for k in named if k not in tensors]
+        if strict and missing:
+            raise KeyError(f"missing parameters: {missing}")
+        for k, t in tensors.items():
+            if k in named:
+                if tuple(named[k].shape) != tuple(t.shape):
+                    raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(named[k].shape)}")
+                named[k].copy_(torch.as_tensor(t).to(torch.float32))
+
+    def state_dict(self):
+        return OrderedDict((k, v.detach().clone()) for k, v in self.named_views().items())
+
+    def reset_optimizer(self, learning_rate=None):
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+        st = torch.zeros(8, dtype=torch.float32)
+        st[0], st[1] = 0.9, 0.999  # beta powers start at beta (TF creates them initialised to beta)
+        if learning_rate is not None:
+            st[4] = learning_rate
+        else:
+            st[4] = float(self.state[4].item()) if self.state[4].item() != 0 else 0.0
+        self.state.copy_(st)
+
+    @property
+    def global_step(self):
+        return int(self.state[2].item())
+
+    @global_step.setter
+    def global_step(self, v):
+        self.state[2] = float(v)

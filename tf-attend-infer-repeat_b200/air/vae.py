@@ -1,0 +1,185 @@
+"""VAE with the reference signature (air/vae.py:5-43), running on the C-ABI kernels.
+
+``vae(inputs, input_dim, rec_hidden_units, latent_dim, gen_hidden_units, likelihood_std,
+activation)`` returns ``(reconstruction, rec_mean, rec_log_variance, rec_mean)`` exactly
+like the reference (the 4th item is the MEAN: vae.py:43).  The two noise tensors the
+reference draws internally (vae.py:23, :37) are explicit keyword arguments.
+
+``vae_forward`` / ``vae_backward`` are the kernel schedules shared with AIRModel.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _cabi as C
+from .. import ops
+
+
+class VAEWeights:
+    """Views into a ParamStore-like dict, fused mean|log_variance layer included."""
+
+    def __init__(self, p, g, n_rec, n_gen):
+        self.rec = [(p[f"vae/recognition_{i + 1}/weights"], p[f"vae/recognition_{i + 1}/biases"]) for i in range(n_rec)]
+        self.ml = (p["vae/rec_ml/weights"], p["vae/rec_ml/biases"])
+        self.gen = [(p[f"vae/generative_{i + 1}/weights"], p[f"vae/generative_{i + 1}/biases"]) for i in range(n_gen)]
+        self.gm = (p["vae/gen_mean/weights"], p["vae/gen_mean/biases"])
+        if g is not None:
+            self.g_rec = [(g[f"vae/recognition_{i + 1}/weights"], g[f"vae/recognition_{i + 1}/biases"])
+                          for i in range(n_rec)]
+            self.g_ml = (g["vae/rec_ml/weights"], g["vae/rec_ml/biases"])
+            self.g_gen = [(g[f"vae/generative_{i + 1}/weights"], g[f"vae/generative_{i + 1}/biases"])
+                          for i in range(n_gen)]
+            self.g_gm = (g["vae/gen_mean/weights"], g["vae/gen_mean/biases"])
+
+
+def alloc_vae_buffers(B, win, rec_units, L, gen_units, device, lead=()):
+    """Activation buffers of one (or ``lead``-many) VAE evaluations."""
+    z = lambda *s: torch.empty(*lead, *s, device=device, dtype=torch.float32)
+    return dict(enc=[z(B, u) for u in rec_units], ml=z(B, 2 * L), zs=z(B, L), dec=[z(B, u) for u in gen_units],
+                recon=z(B, win))
+
+
+def vae_forward(x, w: VAEWeights, noise_latent, noise_like, likelihood_std, hyper, buf, gen_tmp, fields, loss, mode):
+    """x [B,win] -> buf['recon'].  Softplus MLP 784->512->256 -> (mean|logvar) -> sample
+    -> 256->512->784 -> sigmoid(gen + noise*std)   (vae.py:9-41).  Also accumulates the VAE
+    KL into ``loss`` / ``fields`` (air_model.py:479-493)."""
+    a = x
+    for (W, b), out in zip(w.rec, buf["enc"]):
+        ops.gemm(a, W, out, bias=b, epi=C.EPI_SOFTPLUS, mode=mode)
+        a = out
+    ops.gemm(a, w.ml[0], buf["ml"], bias=w.ml[1], mode=mode)
+    ops.vae_latent_fwd(buf["ml"], noise_latent, hyper, buf["zs"], fields, loss)
+    a = buf["zs"]
+    for (W, b), out in zip(w.gen, buf["dec"]):
+        ops.gemm(a, W, out, bias=b, epi=C.EPI_SOFTPLUS, mode=mode)
+        a = out
+    ops.gemm(a, w.gm[0], gen_tmp, bias=w.gm[1], mode=mode)
+    ops.sigmoid_noise_fwd(gen_tmp, noise_like, likelihood_std, buf["recon"])
+    return buf["recon"]
+
+
+def dense_bwd(x_in, W, dY, gW, gb, accumulate, colsum_ws, mode, dX=None, act_of_x=False):
+    """Gradients of Y = x_in W + b: gW (+)= x_in^T dY, gb (+)= colsum(dY),
+    dX = (dY W^T) * softplus'(pre-activation of x_in) when x_in is a softplus output."""
+    ops.gemm(x_in, dY, gW, Cinit=gW if accumulate else None, tA=True, mode=mode)
+    ops.colsum(dY, gb, accumulate, colsum_ws)
+    if dX is not None:
+        ops.gemm(dY, W, dX, tB=True, aux=x_in if act_of_x else None,
+                 epi=C.EPI_MUL_DSOFTPLUS if act_of_x else C.EPI_NONE, mode=mode)
+    return dX
+
+
+def vae_backward(x, w: VAEWeights, noise_latent, hyper, buf, drecon, dloss, fields, scratch, accumulate, colsum_ws,
+                 mode, dx_out=None):
+    """drecon [B,win] (overwritten) -> parameter gradients (+ dx_out [B,win] if given).
+    scratch: dict of [B,u] gradient buffers keyed like buf (allocated by the caller)."""
+    ops.sigmoid_bwd(buf["recon"], drecon, drecon)  # d gen_mean, in place
+    dY = drecon
+    acts = [buf["zs"]] + list(buf["dec"])
+    layers = list(w.gen) + [w.gm]
+    grads = list(w.g_gen) + [w.g_gm]
+    dbufs = [scratch["dzs"]] + list(scratch["ddec"])
+    for i in range(len(layers) - 1, -1, -1):
+        dY = dense_bwd(acts[i], layers[i][0], dY, grads[i][0], grads[i][1], accumulate, colsum_ws, mode, dX=dbufs[i],
+                       act_of_x=(i > 0))
+    ops.vae_latent_bwd(buf["ml"], noise_latent, dY, fields, hyper, dloss, scratch["dml"])
+    dY = scratch["dml"]
+    acts = [x] + list(buf["enc"])
+    layers = list(w.rec) + [w.ml]
+    grads = list(w.g_rec) + [w.g_ml]
+    dbufs = [dx_out] + list(scratch["denc"])
+    for i in range(len(layers) - 1, -1, -1):
+        dY = dense_bwd(acts[i], layers[i][0], dY, grads[i][0], grads[i][1], accumulate, colsum_ws, mode, dX=dbufs[i],
+                       act_of_x=(i > 0))
+    return dx_out
+
+
+def alloc_vae_scratch(B, win, rec_units, L, gen_units, device):
+    z = lambda *s: torch.empty(*s, device=device, dtype=torch.float32)
+    return dict(denc=[z(B, u) for u in rec_units], dml=z(B, 2 * L), dzs=z(B, L), ddec=[z(B, u) for u in gen_units])
+
+
+# ------------------------------------------------------------------------------------------
+# public function with the reference signature
+# ------------------------------------------------------------------------------------------
+_SCOPES = {}
+
+
+def _softplus_marker(x):  # placeholder so that ``activation=softplus`` can be passed explicitly
+    raise RuntimeError("marker only")
+
+
+softplus = _softplus_marker
+
+
+class _VAEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, flat, store, n_rec, n_gen, noise_latent, noise_like, likelihood_std, mode):
+        B = inputs.shape[0]
+        d = store.dims
+        dev = inputs.device
+        buf = alloc_vae_buffers(B, d["win"], d["rec_units"], d["L"], d["gen_units"], dev)
+        w = VAEWeights(store.p, store.g, n_rec, n_gen)
+        hyper = C.Hyper(0, 1, 0, 1, 0.0, 1.0, likelihood_std, 1.0, 2.0, 1)
+        fields = torch.zeros(C.NF, B, device=dev)
+        loss = torch.zeros(B, device=dev)
+        gen_tmp = torch.empty(B, d["win"], device=dev)
+        x = C.f32(inputs)
+        vae_forward(x, w, C.f32(noise_latent), C.f32(noise_like), likelihood_std, hyper, buf, gen_tmp, fields, loss, mode)
+        ctx.stuff = (x, buf, w, hyper, fields, C.f32(noise_latent), store, mode)
+        L = d["L"]
+        mean, logvar = buf["ml"][:, :L], buf["ml"][:, L:]
+        return buf["recon"], mean, logvar
+
+    @staticmethod
+    def backward(ctx, drecon, dmean, dlogvar):
+        x, buf, w, hyper, fields, noise_latent, store, mode = ctx.stuff
+        B = x.shape[0]
+        d = store.dims
+        dev = x.device
+        scratch = alloc_vae_scratch(B, d["win"], d["rec_units"], d["L"], d["gen_units"], dev)
+        ws = torch.zeros(int(C.lib().air_colsum_workspace(B, max(d["win"], 2 * d["L"], *d["rec_units"], *d["gen_units"]))),
+                         device=dev)
+        dx = torch.empty_like(x)
+        store.grad.zero_()
+        # dloss = 0: the KL term belongs to the caller (air_model.py:479-493), not to vae()
+        if dmean is not None or dlogvar is not None:
+            raise NotImplementedError("vae(): gradients through rec_mean / rec_log_variance outputs are taken by "
+                                      "AIRModel's fused schedule; the standalone function differentiates the "
+                                      "reconstruction only")
+        vae_backward(x, w, noise_latent, hyper, buf, drecon.contiguous().clone(), 0.0, fields, scratch, False, ws, mode,
+                     dx_out=dx)
+        return dx, store.grad.clone(), None, None, None, None, None, None, None
+
+
+def vae(inputs, input_dim, rec_hidden_units, latent_dim, gen_hidden_units, likelihood_std=0.0, activation=softplus,
+        *, scope="vae", reuse=False, noise_latent=None, noise_like=None, seed=0, gemm_mode="fp32"):
+    """Drop-in for air/vae.py:5-43.  Variables are created on first use under ``scope``
+    (Xavier-uniform, zero biases) and re-used with ``reuse=True``; the flat parameter
+    buffer is ``vae.variables(scope).flat`` (requires_grad leaf returned by variables())."""
+    if activation is not softplus:
+        raise NotImplementedError("the CUDA VAE is compiled for the reference's softplus activation")
+    from .params import ParamStore
+    key = (scope, input_dim, tuple(rec_hidden_units), latent_dim, tuple(gen_hidden_units), inputs.device)
+    if key not in _SCOPES:
+        if reuse:
+            raise ValueError(f"vae scope {scope!r} does not exist (reuse=True)")
+        store = ParamStore(inputs.device, in_dim=1, win=input_dim, R=1, HU=1, L=latent_dim,
+                           rec_units=rec_hidden_units, gen_units=gen_hidden_units, seed=seed)
+        store.flat.requires_grad_(True)
+        _SCOPES[key] = store
+    store = _SCOPES[key]
+    B = inputs.shape[0]
+    if noise_latent is None:
+        noise_latent = torch.randn(B, latent_dim, device=inputs.device)
+    if noise_like is None:
+        noise_like = torch.randn(B, input_dim, device=inputs.device)
+    recon, mean, logvar = _VAEFunction.apply(inputs, store.flat, store, len(rec_hidden_units), len(gen_hidden_units),
+                                             noise_latent, noise_like, float(likelihood_std),
+                                             C.GEMM_MODES[gemm_mode])
+    return recon, mean, logvar, mean
+
+
+def variables(scope="vae"):
+    """ParamStores created by vae() under ``scope`` (named_views() gives the TF names)."""
+    return [s for k, s in _SCOPES.items() if k[0] == scope]

@@ -14,20 +14,9 @@
 #include <algorithm>
 
 #include "air_common.cuh"
+#include "concrete.cuh"
 
 namespace air {
-
-constexpr float kEps = 1e-9f;  // the reference's 10e-10
-
-// log(tau+eps) - y*tau + alpha - 2*log(1 + exp(-y*tau + alpha) + eps)      (concrete.py:35-37)
-__device__ __forceinline__ float log_density(float y, float alpha, float tau) {
-  const float yt = mul_rn(y, tau);
-  const float e = expf(add_rn(-yt, alpha));
-  const float l = logf(add_rn(add_rn(1.0f, e), kEps));
-  return sub_rn(add_rn(sub_rn(logf(add_rn(tau, kEps)), yt), alpha), mul_rn(2.0f, l));
-}
-
-__device__ __forceinline__ float sigmoid_tf(float x) { return __fdiv_rn(1.0f, add_rn(1.0f, expf(-x))); }
 
 __global__ void __launch_bounds__(256)
     concrete_step_fwd(const float *__restrict__ log_odds, const float *__restrict__ u, const float *stop_prev,
@@ -38,22 +27,14 @@ __global__ void __launch_bounds__(256)
   const float prior = __ldg(prior_log_odds);
   for (int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; b < B;
        b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float lo = log_odds[b], uu = u[b];
-    const float noise = sub_rn(logf(add_rn(uu, kEps)), logf(add_rn(sub_rn(1.0f, uu), kEps)));
-    const float yy = __fdiv_rn(add_rn(lo, noise), tau);
-    float zz = sigmoid_tf(yy);
-    if (!train) zz = rintf(zz);  // tf.round: half to even
-    const float k = sub_rn(log_density(yy, lo, tau), log_density(yy, prior, tau));
-    const float sp = stop_prev[b];
-    const float sn = add_rn(sp, sub_rn(1.0f, zz));
-    const float ln = add_rn(loss_prev[b], sp < thr ? k : 0.0f);
-    const int32_t dn = digits_prev[b] + (sn < thr ? 1 : 0);
-    y[b] = yy;
-    z[b] = zz;
-    z_prob[b] = sigmoid_tf(lo);
-    kl[b] = k;
-    stop_new[b] = sn;
-    loss_new[b] = ln;
+    const ConcreteOut o = concrete_step_one(log_odds[b], u[b], stop_prev[b], loss_prev[b], prior, tau, thr, train);
+    const int32_t dn = digits_prev[b] + o.digit_inc;
+    y[b] = o.y;
+    z[b] = o.z;
+    z_prob[b] = o.z_prob;
+    kl[b] = o.kl;
+    stop_new[b] = o.stop_new;
+    loss_new[b] = o.loss_new;
     digits_new[b] = dn;
   }
 }
@@ -68,22 +49,8 @@ __global__ void __launch_bounds__(256)
   const float prior = __ldg(prior_log_odds);
   for (int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; b < B;
        b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float lo = log_odds[b], yy = y[b], gk = dkl ? dkl[b] : 0.0f;
-    const float yt = yy * tau;
-    // posterior: alpha = lo ;  f = -yt + alpha - 2 log(1 + exp(-yt+alpha) + eps)
-    const float eq = expf(-yt + lo), sq = eq / (1.0f + eq + kEps);
-    const float ep = expf(-yt + prior), sp = ep / (1.0f + ep + kEps);
-    // d kl / d y      = tau * [(-1 + 2 sq) - (-1 + 2 sp)]
-    // d kl / d lo|y   = 1 - 2 sq
-    const float dkl_dy = tau * (2.0f * sq - 2.0f * sp);
-    const float dkl_dlo = 1.0f - 2.0f * sq;
-    float gy = gk * dkl_dy;
-    if (train && dz) {
-      const float zz = z[b];
-      gy += dz[b] * zz * (1.0f - zz);  // sigmoid'
-    }
-    // y = (lo + noise)/tau
-    dlog_odds[b] = gy / tau + gk * dkl_dlo;
+    dlog_odds[b] = concrete_bwd_one(log_odds[b], y[b], z[b], (train && dz) ? dz[b] : 0.0f, dkl ? dkl[b] : 0.0f, prior,
+                                    tau, train);
   }
 }
 

@@ -1,0 +1,633 @@
+// Fused model-specific kernels of the AIR loop body (air/air_model.py:278-508, 580-611,
+// 651-694): LSTM pointwise, the Gaussian heads (sampling, squashing, KLs, theta, theta^-1)
+// fused with the Concrete/ACT step, the VAE latent, the noisy-sigmoid output, the BCE
+// reconstruction loss, deterministic bias-gradient column sums, and global-norm clipping +
+// TF-flavoured Adam on a flat parameter buffer.  All HBM-bound elementwise / reduction work.
+// Compiled with --fmad=false so that each reference op is rounded separately.
+#include <algorithm>
+#include <math.h>
+
+#include "air_common.cuh"
+#include "concrete.cuh"
+#include "epilogue.cuh"
+
+namespace air {
+
+static inline int grid_for(int64_t n, int threads, int per_sm = 8) {
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads,
+                                                                  static_cast<int64_t>(sm_count()) * per_sm)));
+}
+
+#define AIR_GRID_STRIDE(i, n)                                                                    \
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < (n);         \
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+
+// =========================================================================================
+// LSTM pointwise (BasicLSTMCell: i, j, f, o; forget bias 1.0)
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+    lstm_fwd_k(const float *__restrict__ gates, const float *__restrict__ c_prev, float *__restrict__ c_new,
+               float *__restrict__ h_new, int64_t B, int H) {
+  AIR_GRID_STRIDE(e, B * H) {
+    const int64_t b = e / H;
+    const int k = static_cast<int>(e - b * H);
+    const float *g = gates + b * 4 * H;
+    const float gi = g[k], gj = g[H + k], gf = g[2 * H + k], go = g[3 * H + k];
+    const float cp = c_prev ? c_prev[e] : 0.0f;
+    const float c = cp * sigmoid_f(gf + 1.0f) + sigmoid_f(gi) * tanhf(gj);
+    c_new[e] = c;
+    h_new[e] = tanhf(c) * sigmoid_f(go);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    lstm_bwd_k(const float *__restrict__ gates, const float *__restrict__ c_prev, const float *__restrict__ c_new,
+               const float *__restrict__ dh, const float *dc_new, float *__restrict__ dgates, float *dc_prev,
+               float *dgates_sum, int64_t B, int H) {  // dc_prev may alias dc_new (same index, read before write)
+  AIR_GRID_STRIDE(e, B * H) {
+    const int64_t b = e / H;
+    const int k = static_cast<int>(e - b * H);
+    const float *g = gates + b * 4 * H;
+    const float i = sigmoid_f(g[k]), j = tanhf(g[H + k]), f = sigmoid_f(g[2 * H + k] + 1.0f), o = sigmoid_f(g[3 * H + k]);
+    const float cp = c_prev ? c_prev[e] : 0.0f;
+    const float tc = tanhf(c_new[e]);
+    const float gh = dh[e];
+    const float dc = (dc_new ? dc_new[e] : 0.0f) + gh * o * (1.0f - tc * tc);
+    const float di = dc * j * i * (1.0f - i);
+    const float dj = dc * i * (1.0f - j * j);
+    const float df = dc * cp * f * (1.0f - f);
+    const float dd = gh * tc * o * (1.0f - o);
+    float *dg = dgates + b * 4 * H;
+    dg[k] = di; dg[H + k] = dj; dg[2 * H + k] = df; dg[3 * H + k] = dd;
+    if (dgates_sum) {
+      float *ds = dgates_sum + b * 4 * H;
+      ds[k] += di; ds[H + k] += dj; ds[2 * H + k] += df; ds[3 * H + k] += dd;
+    }
+    dc_prev[e] = dc * f;
+  }
+}
+
+// =========================================================================================
+// Heads: 8 lanes per image.  Lane j < 7 owns head output j:
+//   0 scale/mean  1 scale/log_variance  2,3 shift/mean x,y  4,5 shift/log_variance x,y  6 z_pres/log_odds
+// =========================================================================================
+__device__ __forceinline__ int head_block(int j) { return j < 2 ? j : (j < 4 ? 2 : (j < 6 ? 3 : 4)); }
+
+// 0.5 * (((plv - lv) - 1) + var/pv + (mean-pm)^2/pv) for one dimension (air_model.py:443-447)
+__device__ __forceinline__ float gauss_kl_term(float mean, float lv, float var, float pm, float pv, float plv) {
+  const float d = mean - pm;
+  return (((plv - lv) - 1.0f) + var / pv) + (d * d) / pv;
+}
+
+__global__ void __launch_bounds__(256)
+    heads_fwd_k(const float *__restrict__ hidden, const float *__restrict__ w_out, const float *__restrict__ b_out,
+                const float *__restrict__ n_scale, const float *__restrict__ n_shift, const float *__restrict__ u,
+                const float *__restrict__ prior_p, air_hyper_t hp, float *stop, float *loss, int32_t *digits,
+                float *__restrict__ fields, float *__restrict__ theta, float *__restrict__ theta_inv, int64_t B, int HU) {
+  const int64_t gt = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t b = gt >> 3;
+  const int j = static_cast<int>(gt & 7);
+  const bool valid = b < B;
+  float out = 0.0f;
+  if (valid && j < 7) {
+    const float *h = hidden + b * 5 * HU + head_block(j) * HU;
+    const float *w = w_out + j * HU;
+    float acc = 0.0f;
+    for (int k = 0; k < HU; ++k) acc = __fmaf_rn(h[k], __ldg(w + k), acc);  // k-sequential FMA, like air_gemm exact
+    out = acc + __ldg(b_out + j);
+  }
+  const unsigned full = 0xffffffffu;
+  const int base = (threadIdx.x & 31) & ~7;
+  float o[7];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) o[q] = __shfl_sync(full, out, base + q);
+  if (!valid || j != 0) return;
+
+  const float thr = hp.stopping_threshold;
+  // ---- scale (air_model.py:300-303) and shift (:317-320)
+  const float s_var = expf(o[1]);
+  const float s = sigmoid_f(o[0] + n_scale[b] * sqrtf(s_var));
+  const float vx = expf(o[4]), vy = expf(o[5]);
+  const float x = tanhf(o[2] + n_shift[2 * b] * sqrtf(vx));
+  const float y = tanhf(o[3] + n_shift[2 * b + 1] * sqrtf(vy));
+  // ---- theta (:324-327) and theta^-1 (:353-356, three separate divisions)
+  float *th = theta + b * 6;
+  th[0] = s; th[1] = 0.0f; th[2] = x; th[3] = 0.0f; th[4] = s; th[5] = y;
+  float *ti = theta_inv + b * 6;
+  const float inv = 1.0f / s;
+  ti[0] = inv; ti[1] = 0.0f; ti[2] = -x / s; ti[3] = 0.0f; ti[4] = inv; ti[5] = -y / s;
+  // ---- Concrete / ACT step (:380-427)
+  const float stop_prev = stop[b];
+  const ConcreteOut c = concrete_step_one(o[6], u[b], stop_prev, loss[b], __ldg(prior_p), hp.z_pres_temperature, thr,
+                                          hp.train);
+  const bool live = c.stop_new < thr;
+  // ---- Gaussian KLs masked by the NEW stopping sum (:441-477)
+  const float kl_s = 0.5f * gauss_kl_term(o[0], o[1], s_var, hp.scale_prior_mean, hp.scale_prior_variance,
+                                          logf(hp.scale_prior_variance));
+  const float plv = logf(hp.shift_prior_variance);
+  const float kl_t = 0.5f * (gauss_kl_term(o[2], o[4], vx, hp.shift_prior_mean, hp.shift_prior_variance, plv) +
+                             gauss_kl_term(o[3], o[5], vy, hp.shift_prior_mean, hp.shift_prior_variance, plv));
+  float l = c.loss_new;
+  l = l + (live ? kl_s : 0.0f);
+  l = l + (live ? kl_t : 0.0f);
+  stop[b] = c.stop_new;
+  loss[b] = l;
+  digits[b] += c.digit_inc;
+  float *f = fields + b;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) f[static_cast<int64_t>(q) * B] = o[q];
+  f[AIR_F_S * B] = s; f[AIR_F_X * B] = x; f[AIR_F_Y * B] = y;
+  f[AIR_F_YPRE * B] = c.y; f[AIR_F_Z * B] = c.z; f[AIR_F_ZPROB * B] = c.z_prob;
+  f[AIR_F_KL_Z * B] = c.kl; f[AIR_F_KL_SCALE * B] = kl_s; f[AIR_F_KL_SHIFT * B] = kl_t;
+  f[AIR_F_STOP_PREV * B] = stop_prev; f[AIR_F_STOP_NEW * B] = c.stop_new;
+}
+
+constexpr int kHeadsImgs = 32;  // images per CTA in heads_bwd (256 threads, 8 lanes each)
+
+__global__ void __launch_bounds__(256)
+    heads_bwd_k(const float *__restrict__ hidden, const float *__restrict__ w_out, const float *__restrict__ n_scale,
+                const float *__restrict__ n_shift, const float *__restrict__ fields, const float *__restrict__ dtheta,
+                const float *__restrict__ dtheta_inv, const float *__restrict__ dz, const float *__restrict__ prior_p,
+                air_hyper_t hp, float dloss, float *__restrict__ dhidden, float *__restrict__ partials, int64_t B,
+                int HU) {
+  __shared__ float sOut[kHeadsImgs][8];
+  const int tid = threadIdx.x;
+  const int img = tid >> 3, j = tid & 7;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kHeadsImgs;
+  const int64_t b = b0 + img;
+  const bool valid = b < B;
+  if (j == 0) {
+    float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const float *f = fields + b;
+      const float thr = hp.stopping_threshold;
+      const float m_s = f[AIR_F_SCALE_MEAN * B], lv_s = f[AIR_F_SCALE_LV * B];
+      const float m_x = f[AIR_F_SHIFT_MEAN_X * B], m_y = f[AIR_F_SHIFT_MEAN_Y * B];
+      const float lv_x = f[AIR_F_SHIFT_LV_X * B], lv_y = f[AIR_F_SHIFT_LV_Y * B];
+      const float s = f[AIR_F_S * B], x = f[AIR_F_X * B], y = f[AIR_F_Y * B];
+      const bool live = f[AIR_F_STOP_NEW * B] < thr;
+      const float gl = live ? dloss : 0.0f;                                // weight of the KLs masked by the new sum
+      const float gk = f[AIR_F_STOP_PREV * B] < thr ? dloss : 0.0f;        // weight of the z_pres KL (previous sum)
+      const float *dt = dtheta + b * 6, *di = dtheta_inv + b * 6;
+      // theta = [s,0,x;0,s,y]; theta_inv = [1/s,0,-x/s;0,1/s,-y/s]
+      const float is = 1.0f / s, is2 = is * is;
+      const float ds = (dt[0] + dt[4]) - (di[0] + di[4]) * is2 + (di[2] * x + di[5] * y) * is2;
+      const float dx = dt[2] - di[2] * is;
+      const float dy = dt[5] - di[5] * is;
+      // s = sigmoid(a), a = mean + n*sqrt(var), var = exp(lv)
+      const float var_s = expf(lv_s), var_x = expf(lv_x), var_y = expf(lv_y);
+      const float da_s = ds * s * (1.0f - s);
+      const float da_x = dx * (1.0f - x * x), da_y = dy * (1.0f - y * y);
+      const float pvs = hp.scale_prior_variance, pvt = hp.shift_prior_variance;
+      d[0] = da_s + gl * (m_s - hp.scale_prior_mean) / pvs;
+      d[1] = da_s * n_scale[b] * 0.5f * sqrtf(var_s) + gl * 0.5f * (var_s / pvs - 1.0f);
+      d[2] = da_x + gl * (m_x - hp.shift_prior_mean) / pvt;
+      d[3] = da_y + gl * (m_y - hp.shift_prior_mean) / pvt;
+      d[4] = da_x * n_shift[2 * b] * 0.5f * sqrtf(var_x) + gl * 0.5f * (var_x / pvt - 1.0f);
+      d[5] = da_y * n_shift[2 * b + 1] * 0.5f * sqrtf(var_y) + gl * 0.5f * (var_y / pvt - 1.0f);
+      d[6] = concrete_bwd_one(f[AIR_F_LOG_ODDS * B], f[AIR_F_YPRE * B], f[AIR_F_Z * B], dz[b], gk, __ldg(prior_p),
+                              hp.z_pres_temperature, hp.train);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sOut[img][q] = d[q];
+  }
+  __syncthreads();
+  // ---- dhidden[b, blk*HU + k] = relu'(hidden) * sum_{j in blk} dOut[j] * w_out[j][k]
+  if (valid) {
+    const int n = 5 * HU;
+    for (int e = j; e < n; e += 8) {
+      const int blk = e / HU, k = e - blk * HU;
+      float g;
+      if (blk < 2) g = sOut[img][blk] * __ldg(w_out + blk * HU + k);
+      else if (blk == 2) g = sOut[img][2] * __ldg(w_out + 2 * HU + k) + sOut[img][3] * __ldg(w_out + 3 * HU + k);
+      else if (blk == 3) g = sOut[img][4] * __ldg(w_out + 4 * HU + k) + sOut[img][5] * __ldg(w_out + 5 * HU + k);
+      else g = sOut[img][6] * __ldg(w_out + 6 * HU + k);
+      const int64_t o = b * n + e;
+      dhidden[o] = hidden[o] > 0.0f ? g : 0.0f;
+    }
+  }
+  // ---- per-CTA partial d(w_out) [7,HU] and d(b_out) [7]: fixed order over the CTA's images
+  const int n_img = static_cast<int>((B - b0 < kHeadsImgs ? B - b0 : kHeadsImgs));
+  float *part = partials + static_cast<int64_t>(blockIdx.x) * (7 * HU + 7);
+  for (int e = tid; e < 7 * HU + 7; e += 256) {
+    float acc = 0.0f;
+    if (e < 7 * HU) {
+      const int jj = e / HU, k = e - jj * HU;
+      const float *h = hidden + b0 * 5 * HU + head_block(jj) * HU + k;
+      for (int i = 0; i < n_img; ++i) acc += sOut[i][jj] * h[static_cast<int64_t>(i) * 5 * HU];
+    } else {
+      const int jj = e - 7 * HU;
+      for (int i = 0; i < n_img; ++i) acc += sOut[i][jj];
+    }
+    part[e] = acc;
+  }
+}
+
+// out[e] (+)= sum_r partials[r*stride + e], r in increasing order (deterministic)
+__global__ void __launch_bounds__(256)
+    reduce_rows_k(const float *__restrict__ partials, int R, int stride, int n, float *out, int accumulate) {
+  AIR_GRID_STRIDE(e, n) {
+    float acc = 0.0f;
+    for (int r = 0; r < R; ++r) acc += partials[static_cast<int64_t>(r) * stride + e];
+    out[e] = accumulate ? out[e] + acc : acc;
+  }
+}
+
+// =========================================================================================
+// VAE latent: one warp per image
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+    vae_latent_fwd_k(const float *__restrict__ ml, const float *__restrict__ noise, air_hyper_t hp,
+                     float *__restrict__ sample, float *__restrict__ fields, float *loss, int64_t B, int L) {
+  const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float pm = hp.vae_prior_mean, pv = hp.vae_prior_variance, plv = logf(pv);
+  float acc = 0.0f;
+  for (int d = lane; d < L; d += 32) {
+    const float mean = ml[b * 2 * L + d], lv = ml[b * 2 * L + L + d];
+    const float var = expf(lv);
+    sample[b * L + d] = mean + noise[b * L + d] * sqrtf(var);
+    acc += gauss_kl_term(mean, lv, var, pm, pv, plv);
+  }
+  acc = 0.5f * warp_sum(acc);
+  if (lane == 0) {
+    const bool live = fields[AIR_F_STOP_NEW * B + b] < hp.stopping_threshold;
+    fields[AIR_F_KL_VAE * B + b] = acc;
+    loss[b] = loss[b] + (live ? acc : 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    vae_latent_bwd_k(const float *__restrict__ ml, const float *__restrict__ noise, const float *__restrict__ dsample,
+                     const float *__restrict__ fields, air_hyper_t hp, float dloss, float *__restrict__ dml, int64_t B,
+                     int L) {
+  AIR_GRID_STRIDE(e, B * L) {
+    const int64_t b = e / L;
+    const int d = static_cast<int>(e - b * L);
+    const float gl = fields[AIR_F_STOP_NEW * B + b] < hp.stopping_threshold ? dloss : 0.0f;
+    const float mean = ml[b * 2 * L + d], lv = ml[b * 2 * L + L + d];
+    const float var = expf(lv);
+    const float ds = dsample[e];
+    dml[b * 2 * L + d] = ds + gl * (mean - hp.vae_prior_mean) / hp.vae_prior_variance;
+    dml[b * 2 * L + L + d] = ds * noise[e] * 0.5f * sqrtf(var) + gl * 0.5f * (var / hp.vae_prior_variance - 1.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    sigmoid_noise_fwd_k(const float *__restrict__ gen, const float *__restrict__ noise, float sd, float *__restrict__ out,
+                        int64_t n) {
+  AIR_GRID_STRIDE(e, n) out[e] = sigmoid_f(gen[e] + noise[e] * sd);
+}
+
+__global__ void __launch_bounds__(256)
+    sigmoid_bwd_k(const float *out, const float *dout, float *dgen, int64_t n) {
+  AIR_GRID_STRIDE(e, n) {
+    const float o = out[e];
+    dgen[e] = dout[e] * o * (1.0f - o);
+  }
+}
+
+// =========================================================================================
+// BCE reconstruction loss: one CTA per image
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+    bce_loss_k(const float *__restrict__ canvas, const float *__restrict__ x, float *__restrict__ recon,
+               float *__restrict__ rec_loss, float *__restrict__ dcanvas, float dscale, int N) {
+  __shared__ float red[8];
+  const int64_t b = blockIdx.x;
+  const float *c = canvas + b * N, *xi = x + b * N;
+  float acc = 0.0f;
+  for (int p = threadIdx.x; p < N; p += 256) {
+    const float cv = c[p], xv = xi[p];
+    const float r = fmaxf(fminf(cv, 1.0f), 0.0f);
+    const float a = r + kEps, q = (1.0f - r) + kEps;
+    acc += xv * logf(a) + (1.0f - xv) * logf(q);
+    if (recon) recon[b * N + p] = r;
+    if (dcanvas) {
+      const bool pass = cv <= 1.0f && cv >= 0.0f;  // minimum passes x<=y, maximum passes x>=y
+      dcanvas[b * N + p] = pass ? dscale * ((1.0f - xv) / q - xv / a) : 0.0f;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    rec_loss[b] = -t;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+    finalize_loss_k(const float *__restrict__ running_loss, const float *__restrict__ rec_loss,
+                    const int32_t *__restrict__ digits, const int32_t *__restrict__ target, float *__restrict__ out,
+                    float *__restrict__ loss_per_item, int64_t B) {
+  __shared__ float r0[32], r1[32];
+  float a = 0.0f, c = 0.0f;
+  for (int64_t b = threadIdx.x; b < B; b += 1024) {
+    const float l = running_loss[b] + rec_loss[b];
+    if (loss_per_item) loss_per_item[b] = l;
+    a += l;
+    c += (digits[b] == target[b]) ? 1.0f : 0.0f;
+  }
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = a; r1[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.0f, tc = 0.0f;
+    for (int k = 0; k < 32; ++k) { ta += r0[k]; tc += r1[k]; }
+    out[0] = ta / static_cast<float>(B);
+    out[1] = tc / static_cast<float>(B);
+  }
+}
+
+// =========================================================================================
+// Column sums (bias gradients): stage 1 -> partials[R][N], stage 2 = reduce_rows_k
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+    colsum_partial_k(const float *__restrict__ X, int ld, float *__restrict__ partials, int64_t B, int N,
+                     int rows_per_chunk) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk;
+  const int64_t r1 = (r0 + rows_per_chunk < B) ? r0 + rows_per_chunk : B;
+  float acc = 0.0f;
+  if (col < N)
+    for (int64_t r = r0 + w; r < r1; r += 8) acc += X[r * ld + col];
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && col < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    partials[static_cast<int64_t>(blockIdx.y) * N + col] = t;
+  }
+}
+
+static int colsum_chunks(int64_t B, int N) {
+  const int cb = (N + 31) / 32;
+  int R = (2 * sm_count() + cb - 1) / cb;
+  R = std::max(1, std::min(R, 64));
+  R = static_cast<int>(std::min<int64_t>(R, (B + 7) / 8));
+  return std::max(R, 1);
+}
+
+// =========================================================================================
+// Global-norm clip + TF Adam on the flat parameter buffer
+// =========================================================================================
+constexpr int kAdamPartials = 1024;
+
+__global__ void __launch_bounds__(256)
+    sumsq_partial_k(const float *__restrict__ g, float gs, float *__restrict__ partials, int64_t n) {
+  __shared__ float red[8];
+  float acc = 0.0f;
+  AIR_GRID_STRIDE(e, n) {
+    const float v = g[e] * gs;
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    adam_apply_k(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                 const float *__restrict__ state, const float *__restrict__ partials, int n_partials, float clip,
+                 float beta1, float beta2, float eps, float gs, float *__restrict__ norm_out, int64_t n) {
+  __shared__ float red[8];
+  __shared__ float s_scale;
+  // every CTA reduces the same partials in the same order -> identical clip scale everywhere
+  float acc = 0.0f;
+  for (int k = threadIdx.x; k < n_partials; k += 256) acc += partials[k];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    const float norm = sqrtf((t / 2.0f) * 2.0f);  // sqrt(2 * sum(l2_loss))
+    float sc = 1.0f;
+    if (clip > 0.0f) sc = clip * fminf(1.0f / norm, 1.0f / clip);  // tf.clip_by_global_norm
+    s_scale = sc;
+    if (blockIdx.x == 0) *norm_out = norm;
+  }
+  __syncthreads();
+  const float sc = s_scale * gs;
+  const float b1p = state[0], b2p = state[1], lr = state[4];
+  const float alpha = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  AIR_GRID_STRIDE(e, n) {
+    const float gv = g[e] * sc;
+    float mm = m[e], vv = v[e];
+    mm = mm + (gv - mm) * omb1;
+    vv = vv + (gv * gv - vv) * omb2;
+    m[e] = mm;
+    v[e] = vv;
+    p[e] = p[e] - (mm * alpha) / (sqrtf(vv) + eps);
+  }
+}
+
+__global__ void adam_advance_k(float *state, float beta1, float beta2, const float *norm_in) {
+  state[0] *= beta1;
+  state[1] *= beta2;
+  state[2] += 1.0f;
+  state[3] = *norm_in;
+}
+
+__global__ void anneal_k(const float *state, float init, float factor, float iters, int staircase, float vmin,
+                         float vmax, int take_log, float *out) {
+  float p = state[2] / iters;
+  if (staircase) p = floorf(p);
+  float v = init * powf(factor, p);
+  if (vmin == vmin) v = fmaxf(v, vmin);
+  if (vmax == vmax) v = fminf(v, vmax);
+  if (take_log) v = logf(v + kEps);
+  *out = v;
+}
+
+}  // namespace air
+
+// ---- C ABI --------------------------------------------------------------------------------
+using namespace air;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int air_lstm_fwd(const float *gates, const float *c_prev, float *c_new, float *h_new, int64_t B, int H,
+                            air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && H > 0, AIR_ERR_BAD_SHAPE, "lstm_fwd: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(gates && c_new && h_new, AIR_ERR_NULL, "lstm_fwd: null pointer");
+  lstm_fwd_k<<<grid_for(B * H, 256), 256, 0, ST(stream)>>>(gates, c_prev, c_new, h_new, B, H);
+  count_launch();
+  return check_launch("lstm_fwd");
+}
+
+extern "C" int air_lstm_bwd(const float *gates, const float *c_prev, const float *c_new, const float *dh,
+                            const float *dc_new, float *dgates, float *dc_prev, float *dgates_sum, int64_t B, int H,
+                            air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && H > 0, AIR_ERR_BAD_SHAPE, "lstm_bwd: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(gates && c_new && dh && dgates && dc_prev, AIR_ERR_NULL, "lstm_bwd: null pointer");
+  lstm_bwd_k<<<grid_for(B * H, 256), 256, 0, ST(stream)>>>(gates, c_prev, c_new, dh, dc_new, dgates, dc_prev, dgates_sum,
+                                                          B, H);
+  count_launch();
+  return check_launch("lstm_bwd");
+}
+
+extern "C" int air_heads_fwd(const float *hidden, const float *w_out, const float *b_out, const float *noise_scale,
+                             const float *noise_shift, const float *u, const float *prior_log_odds,
+                             const air_hyper_t *hyper, float *stop, float *loss, int32_t *digits, float *fields,
+                             float *theta, float *theta_inv, int64_t B, int HU, air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && HU > 0, AIR_ERR_BAD_SHAPE, "heads_fwd: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(hidden && w_out && b_out && noise_scale && noise_shift && u && prior_log_odds && hyper && stop && loss &&
+                  digits && fields && theta && theta_inv,
+              AIR_ERR_NULL, "heads_fwd: null pointer");
+  const int64_t threads = B * 8;
+  heads_fwd_k<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ST(stream)>>>(
+      hidden, w_out, b_out, noise_scale, noise_shift, u, prior_log_odds, *hyper, stop, loss, digits, fields, theta,
+      theta_inv, B, HU);
+  count_launch();
+  return check_launch("heads_fwd");
+}
+
+extern "C" int64_t air_heads_bwd_workspace(int64_t B, int HU) {
+  return ((B + kHeadsImgs - 1) / kHeadsImgs) * (7 * static_cast<int64_t>(HU) + 7);
+}
+
+extern "C" int air_heads_bwd(const float *hidden, const float *w_out, const float *noise_scale,
+                             const float *noise_shift, const float *fields, const float *dtheta,
+                             const float *dtheta_inv, const float *dz, const float *prior_log_odds,
+                             const air_hyper_t *hyper, float dloss, float *dhidden, float *dw_out, float *db_out,
+                             int accumulate, float *workspace, int64_t B, int HU, air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && HU > 0, AIR_ERR_BAD_SHAPE, "heads_bwd: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(hidden && w_out && noise_scale && noise_shift && fields && dtheta && dtheta_inv && dz && prior_log_odds &&
+                  hyper && dhidden && dw_out && db_out && workspace,
+              AIR_ERR_NULL, "heads_bwd: null pointer");
+  const int R = static_cast<int>((B + kHeadsImgs - 1) / kHeadsImgs);
+  heads_bwd_k<<<R, 256, 0, ST(stream)>>>(hidden, w_out, noise_scale, noise_shift, fields, dtheta, dtheta_inv, dz,
+                                         prior_log_odds, *hyper, dloss, dhidden, workspace, B, HU);
+  count_launch();
+  int rc = check_launch("heads_bwd");
+  if (rc) return rc;
+  const int n = 7 * HU;
+  reduce_rows_k<<<grid_for(n, 256), 256, 0, ST(stream)>>>(workspace, R, n + 7, n, dw_out, accumulate);
+  reduce_rows_k<<<1, 32, 0, ST(stream)>>>(workspace + n, R, n + 7, 7, db_out, accumulate);
+  count_launch(2);
+  return check_launch("heads_bwd reduce");
+}
+
+extern "C" int air_vae_latent_fwd(const float *ml, const float *noise, const air_hyper_t *hyper, float *sample,
+                                  float *fields, float *loss, int64_t B, int L, air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && L > 0, AIR_ERR_BAD_SHAPE, "vae_latent_fwd: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(ml && noise && hyper && sample && fields && loss, AIR_ERR_NULL, "vae_latent_fwd: null pointer");
+  vae_latent_fwd_k<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, ST(stream)>>>(ml, noise, *hyper, sample, fields,
+                                                                                       loss, B, L);
+  count_launch();
+  return check_launch("vae_latent_fwd");
+}
+
+extern "C" int air_vae_latent_bwd(const float *ml, const float *noise, const float *dsample, const float *fields,
+                                  const air_hyper_t *hyper, float dloss, float *dml, int64_t B, int L,
+                                  air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && L > 0, AIR_ERR_BAD_SHAPE, "vae_latent_bwd: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(ml && noise && dsample && fields && hyper && dml, AIR_ERR_NULL, "vae_latent_bwd: null pointer");
+  vae_latent_bwd_k<<<grid_for(B * L, 256), 256, 0, ST(stream)>>>(ml, noise, dsample, fields, *hyper, dloss, dml, B, L);
+  count_launch();
+  return check_launch("vae_latent_bwd");
+}
+
+extern "C" int air_sigmoid_noise_fwd(const float *gen, const float *noise, float sd, float *out, int64_t n,
+                                     air_stream_t stream) {
+  AIR_REQUIRE(n >= 0, AIR_ERR_BAD_SHAPE, "sigmoid_noise_fwd: n < 0");
+  if (n == 0) return AIR_OK;
+  AIR_REQUIRE(gen && noise && out, AIR_ERR_NULL, "sigmoid_noise_fwd: null pointer");
+  sigmoid_noise_fwd_k<<<grid_for(n, 256, 16), 256, 0, ST(stream)>>>(gen, noise, sd, out, n);
+  count_launch();
+  return check_launch("sigmoid_noise_fwd");
+}
+
+extern "C" int air_sigmoid_bwd(const float *out, const float *dout, float *dgen, int64_t n, air_stream_t stream) {
+  AIR_REQUIRE(n >= 0, AIR_ERR_BAD_SHAPE, "sigmoid_bwd: n < 0");
+  if (n == 0) return AIR_OK;
+  AIR_REQUIRE(out && dout && dgen, AIR_ERR_NULL, "sigmoid_bwd: null pointer");
+  sigmoid_bwd_k<<<grid_for(n, 256, 16), 256, 0, ST(stream)>>>(out, dout, dgen, n);
+  count_launch();
+  return check_launch("sigmoid_bwd");
+}
+
+extern "C" int air_bce_loss(const float *canvas, const float *x, float *recon, float *rec_loss, float *dcanvas,
+                            float dscale, int64_t B, int N, air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && N > 0 && B < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "bce_loss: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(canvas && x && rec_loss, AIR_ERR_NULL, "bce_loss: null pointer");
+  bce_loss_k<<<static_cast<unsigned>(B), 256, 0, ST(stream)>>>(canvas, x, recon, rec_loss, dcanvas, dscale, N);
+  count_launch();
+  return check_launch("bce_loss");
+}
+
+extern "C" int air_finalize_loss(const float *running_loss, const float *rec_loss, const int32_t *digits,
+                                 const int32_t *target, float *out, float *loss_per_item, int64_t B,
+                                 air_stream_t stream) {
+  AIR_REQUIRE(B > 0, AIR_ERR_BAD_SHAPE, "finalize_loss: B <= 0");
+  AIR_REQUIRE(running_loss && rec_loss && digits && target && out, AIR_ERR_NULL, "finalize_loss: null pointer");
+  finalize_loss_k<<<1, 1024, 0, ST(stream)>>>(running_loss, rec_loss, digits, target, out, loss_per_item, B);
+  count_launch();
+  return check_launch("finalize_loss");
+}
+
+extern "C" int64_t air_colsum_workspace(int64_t B, int N) { return static_cast<int64_t>(64) * N + 64 + 0 * B; }
+
+extern "C" int air_colsum(const float *X, int ld, float *out, int accumulate, float *workspace, int64_t B, int N,
+                          air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && N > 0 && ld >= N, AIR_ERR_BAD_SHAPE, "colsum: bad shape");
+  AIR_REQUIRE(X && out && workspace, AIR_ERR_NULL, "colsum: null pointer");
+  if (B == 0) {
+    if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, ST(stream));
+    return AIR_OK;
+  }
+  const int R = colsum_chunks(B, N);
+  const int rows = static_cast<int>((B + R - 1) / R);
+  dim3 grid((N + 31) / 32, R);
+  colsum_partial_k<<<grid, 256, 0, ST(stream)>>>(X, ld, workspace, B, N, rows);
+  count_launch();
+  int rc = check_launch("colsum_partial");
+  if (rc) return rc;
+  reduce_rows_k<<<grid_for(N, 256), 256, 0, ST(stream)>>>(workspace, R, N, N, out, accumulate);
+  count_launch();
+  return check_launch("colsum reduce");
+}
+
+extern "C" int64_t air_adam_workspace(int64_t n) { return kAdamPartials + 8 + 0 * n; }
+
+extern "C" int air_adam_step(float *params, const float *grads, float *m, float *v, float *state, float clip_norm,
+                             float beta1, float beta2, float epsilon, float grad_scale, float *workspace, int64_t n,
+                             air_stream_t stream) {
+  AIR_REQUIRE(n > 0, AIR_ERR_BAD_SHAPE, "adam_step: n <= 0");
+  AIR_REQUIRE(params && grads && m && v && state && workspace, AIR_ERR_NULL, "adam_step: null pointer");
+  const int np = static_cast<int>(std::min<int64_t>(kAdamPartials, (n + 1023) / 1024));
+  sumsq_partial_k<<<np, 256, 0, ST(stream)>>>(grads, grad_scale, workspace, n);
+  adam_apply_k<<<grid_for(n, 256, 4), 256, 0, ST(stream)>>>(params, grads, m, v, state, workspace, np, clip_norm, beta1,
+                                                            beta2, epsilon, grad_scale, workspace + kAdamPartials, n);
+  adam_advance_k<<<1, 1, 0, ST(stream)>>>(state, beta1, beta2, workspace + kAdamPartials);
+  count_launch(3);
+  return check_launch("adam_step");
+}
+
+extern "C" int air_anneal(const float *state, float init, float factor, float iters, int staircase, float vmin,
+                          float vmax, int take_log, float *out, air_stream_t stream) {
+  AIR_REQUIRE(state && out, AIR_ERR_NULL, "anneal: null pointer");
+  anneal_k<<<1, 1, 0, ST(stream)>>>(state, init, factor, iters, staircase, vmin, vmax, take_log, out);
+  count_launch();
+  return check_launch("anneal");
+}

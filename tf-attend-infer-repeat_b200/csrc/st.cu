@@ -467,12 +467,12 @@ static bool staged_ok(const void *U, int H, int W, int C, int64_t B) {
 static int st_forward_impl(const float *U, const float *theta, float *out, const float *z, const float *stop,
                            float thr, const float *canvas_in, bool canvas, int64_t B, int H, int W, int C, int OH,
                            int OW, cudaStream_t s) {
-  AIR_REQUIRE(U && theta && out, AIR_ERR_NULL, "st_forward: null pointer");
   AIR_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, AIR_ERR_BAD_SHAPE,
               "st_forward: bad shape B=%lld H=%d W=%d C=%d oh=%d ow=%d", (long long)B, H, W, C, OH, OW);
   AIR_REQUIRE(static_cast<int64_t>(H) * W * C < (int64_t(1) << 30) && static_cast<int64_t>(OH) * OW < (int64_t(1) << 30),
               AIR_ERR_BAD_SHAPE, "st_forward: image too large");
   if (B == 0) return AIR_OK;
+  AIR_REQUIRE(U && theta && out, AIR_ERR_NULL, "st_forward: null pointer");
   if (staged_ok(U, H, W, C, B)) {
     if (canvas) {
       if (H == 28 && W == 28 && OH == 50 && OW == 50)
@@ -521,12 +521,12 @@ static int launch_bwd_staged(const float *U, const float *theta, const float *do
 static int st_backward_impl(const float *U, const float *theta, const float *dout, const float *z, const float *stop,
                             float thr, bool fused, float *dU, float *dtheta, float *dz, int64_t B, int H, int W, int C,
                             int OH, int OW, cudaStream_t s) {
-  AIR_REQUIRE(U && theta && dout && dtheta, AIR_ERR_NULL, "st_backward: null pointer");
   AIR_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, AIR_ERR_BAD_SHAPE,
               "st_backward: bad shape B=%lld H=%d W=%d C=%d oh=%d ow=%d", (long long)B, H, W, C, OH, OW);
   AIR_REQUIRE(static_cast<int64_t>(H) * W * C < (int64_t(1) << 30) && static_cast<int64_t>(OH) * OW < (int64_t(1) << 30),
               AIR_ERR_BAD_SHAPE, "st_backward: image too large");
   if (B == 0) return AIR_OK;
+  AIR_REQUIRE(U && theta && dout && dtheta, AIR_ERR_NULL, "st_backward: null pointer");
   const bool staged = staged_ok(U, H, W, C, B) && ((OH * OW) % 4 == 0) && aligned16(dout) &&
                       bwd_smem_bytes(H, W, OH, OW) <= static_cast<size_t>(kMaxStagedSmem);
   if (staged) {
@@ -572,7 +572,8 @@ extern "C" int air_st_writeback_canvas_fwd(const float *window, const float *the
                                            const float *stop_new, float thr, const float *canvas_in,
                                            float *canvas_out, int64_t B, int wh, int ww, int ch, int cw,
                                            air_stream_t stream) {
-  AIR_REQUIRE(z && stop_new && canvas_in && canvas_out, AIR_ERR_NULL, "st_writeback_canvas_fwd: null pointer");
+  AIR_REQUIRE(B <= 0 || (z && stop_new && canvas_in && canvas_out), AIR_ERR_NULL,
+              "st_writeback_canvas_fwd: null pointer");
   return air::st_forward_impl(window, theta_inv, canvas_out, z, stop_new, thr, canvas_in, true, B, wh, ww, 1, ch, cw,
                               static_cast<cudaStream_t>(stream));
 }
@@ -581,7 +582,7 @@ extern "C" int air_st_writeback_canvas_bwd(const float *window, const float *the
                                            const float *stop_new, float thr, const float *dcanvas, float *dwindow,
                                            float *dtheta_inv, float *dz, int64_t B, int wh, int ww, int ch, int cw,
                                            air_stream_t stream) {
-  AIR_REQUIRE(z && stop_new && dwindow && dz, AIR_ERR_NULL, "st_writeback_canvas_bwd: null pointer");
+  AIR_REQUIRE(B <= 0 || (z && stop_new && dwindow && dz), AIR_ERR_NULL, "st_writeback_canvas_bwd: null pointer");
   return air::st_backward_impl(window, theta_inv, dcanvas, z, stop_new, thr, true, dwindow, dtheta_inv, dz, B, wh, ww,
                                1, ch, cw, static_cast<cudaStream_t>(stream));
 }

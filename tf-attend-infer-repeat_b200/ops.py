@@ -1,0 +1,141 @@
+"""Tensor-level wrappers over the C ABI (no autograd): each function launches one
+entry point of libair_b200.so on torch's current CUDA stream."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _cabi as C
+from ._cabi import check, lib, ptr, stream
+
+
+def _ld(t):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise C.AirError("GEMM operands must be 2-D with unit inner stride")
+    return t.stride(0)
+
+
+def _p2(t):
+    """pointer of a 2-D row-strided tensor (view allowed)."""
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise C.AirError("air_b200 ops need float32 CUDA tensors (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.EPI_NONE, mode=0):
+    """out[M,N] = epi((Cinit + op(A) op(B)) + bias); see include/air_b200.h (air_gemm)."""
+    M, N = out.shape
+    K = A.shape[0] if tA else A.shape[1]
+    kb = B.shape[1] if tB else B.shape[0]
+    if kb != K or (A.shape[1] if tA else A.shape[0]) != M or (B.shape[0] if tB else B.shape[1]) != N:
+        raise C.AirError(f"gemm shape mismatch: A{tuple(A.shape)} tA={tA} B{tuple(B.shape)} tB={tB} out{tuple(out.shape)}")
+    ldc = _ld(out)
+    for t in (Cinit, aux):
+        if t is not None and (_ld(t) != ldc or t.shape != out.shape):
+            raise C.AirError("Cinit / aux must have the layout of out")
+    check(lib().air_gemm(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), _p2(aux), M, N, K, _ld(A), _ld(B), ldc,
+                         int(tA), int(tB), epi, mode, stream()), "air_gemm")
+    return out
+
+
+def lstm_fwd(gates, c_prev, c_new, h_new):
+    B, H4 = gates.shape
+    check(lib().air_lstm_fwd(ptr(gates), ptr(c_prev), ptr(c_new), ptr(h_new), B, H4 // 4, stream()), "air_lstm_fwd")
+
+
+def lstm_bwd(gates, c_prev, c_new, dh, dc_new, dgates, dc_prev, dgates_sum):
+    B, H4 = gates.shape
+    check(lib().air_lstm_bwd(ptr(gates), ptr(c_prev), ptr(c_new), ptr(dh), ptr(dc_new), ptr(dgates), ptr(dc_prev),
+                             ptr(dgates_sum), B, H4 // 4, stream()), "air_lstm_bwd")
+
+
+def heads_fwd(hidden, w_out, b_out, n_scale, n_shift, u, prior, hyper, stop, loss, digits, fields, theta, theta_inv):
+    B = hidden.shape[0]
+    HU = w_out.shape[1]
+    check(lib().air_heads_fwd(ptr(hidden), ptr(w_out), ptr(b_out), ptr(n_scale), ptr(n_shift), ptr(u), ptr(prior),
+                              ctypes.byref(hyper), ptr(stop), ptr(loss), ptr(digits), ptr(fields), ptr(theta),
+                              ptr(theta_inv), B, HU, stream()), "air_heads_fwd")
+
+
+def heads_bwd(hidden, w_out, n_scale, n_shift, fields, dtheta, dtheta_inv, dz, prior, hyper, dloss, dhidden, dw_out,
+              db_out, accumulate, workspace):
+    B = hidden.shape[0]
+    HU = w_out.shape[1]
+    check(lib().air_heads_bwd(ptr(hidden), ptr(w_out), ptr(n_scale), ptr(n_shift), ptr(fields), ptr(dtheta),
+                              ptr(dtheta_inv), ptr(dz), ptr(prior), ctypes.byref(hyper), float(dloss), ptr(dhidden),
+                              ptr(dw_out), ptr(db_out), int(accumulate), ptr(workspace), B, HU, stream()),
+          "air_heads_bwd")
+
+
+def vae_latent_fwd(ml, noise, hyper, sample, fields, loss):
+    B, L2 = ml.shape
+    check(lib().air_vae_latent_fwd(ptr(ml), ptr(noise), ctypes.byref(hyper), ptr(sample), ptr(fields), ptr(loss), B,
+                                   L2 // 2, stream()), "air_vae_latent_fwd")
+
+
+def vae_latent_bwd(ml, noise, dsample, fields, hyper, dloss, dml):
+    B, L2 = ml.shape
+    check(lib().air_vae_latent_bwd(ptr(ml), ptr(noise), ptr(dsample), ptr(fields), ctypes.byref(hyper), float(dloss),
+                                   ptr(dml), B, L2 // 2, stream()), "air_vae_latent_bwd")
+
+
+def sigmoid_noise_fwd(gen, noise, std, out):
+    check(lib().air_sigmoid_noise_fwd(ptr(gen), ptr(noise), float(std), ptr(out), gen.numel(), stream()),
+          "air_sigmoid_noise_fwd")
+
+
+def sigmoid_bwd(out, dout, dgen):
+    check(lib().air_sigmoid_bwd(ptr(out), ptr(dout), ptr(dgen), out.numel(), stream()), "air_sigmoid_bwd")
+
+
+def bce_loss(canvas, x, recon, rec_loss, dcanvas, dscale):
+    B, N = canvas.shape
+    check(lib().air_bce_loss(ptr(canvas), ptr(x), ptr(recon), ptr(rec_loss), ptr(dcanvas), float(dscale), B, N,
+                             stream()), "air_bce_loss")
+
+
+def finalize_loss(running_loss, rec_loss, digits, target, out, loss_per_item=None):
+    check(lib().air_finalize_loss(ptr(running_loss), ptr(rec_loss), ptr(digits), ptr(target), ptr(out),
+                                  ptr(loss_per_item), running_loss.shape[0], stream()), "air_finalize_loss")
+
+
+def colsum(X, out, accumulate, workspace):
+    B, N = X.shape
+    check(lib().air_colsum(_p2(X), _ld(X), ptr(out), int(accumulate), ptr(workspace), B, N, stream()), "air_colsum")
+
+
+def adam_step(params, grads, m, v, state, clip_norm, beta1, beta2, eps, grad_scale, workspace):
+    check(lib().air_adam_step(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(state), float(clip_norm or 0.0), beta1,
+                              beta2, eps, float(grad_scale), ptr(workspace), params.numel(), stream()), "air_adam_step")
+
+
+def anneal(state, schedule, out):
+    nan = float("nan")
+    check(lib().air_anneal(ptr(state), float(schedule["init"]), float(schedule["factor"]), float(schedule["iters"]),
+                           int(bool(schedule.get("staircase", False))), float(schedule.get("min", nan)),
+                           float(schedule.get("max", nan)), int(bool(schedule.get("log", False))), ptr(out), stream()),
+          "air_anneal")
+
+
+def st_forward(U, theta, out, H, W, Cc, oh, ow):
+    check(lib().air_st_forward(ptr(U), ptr(theta), ptr(out), U.shape[0], H, W, Cc, oh, ow, stream()), "air_st_forward")
+
+
+def st_backward(U, theta, dout, dU, dtheta, H, W, Cc, oh, ow):
+    check(lib().air_st_backward(ptr(U), ptr(theta), ptr(dout), ptr(dU), ptr(dtheta), U.shape[0], H, W, Cc, oh, ow,
+                                stream()), "air_st_backward")
+
+
+def writeback_canvas_fwd(window, theta_inv, z, stop_new, thr, canvas_in, canvas_out, wh, ww, ch, cw):
+    check(lib().air_st_writeback_canvas_fwd(ptr(window), ptr(theta_inv), ptr(z), ptr(stop_new), float(thr),
+                                            ptr(canvas_in), ptr(canvas_out), window.shape[0], wh, ww, ch, cw, stream()),
+          "air_st_writeback_canvas_fwd")
+
+
+def writeback_canvas_bwd(window, theta_inv, z, stop_new, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw):
+    check(lib().air_st_writeback_canvas_bwd(ptr(window), ptr(theta_inv), ptr(z), ptr(stop_new), float(thr),
+                                            ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), window.shape[0], wh,
+                                            ww, ch, cw, stream()), "air_st_writeback_canvas_bwd")
