@@ -107,6 +107,11 @@ int air_concrete_step_bwd(const float *log_odds, const float *y, const float *z,
 #define AIR_EPI_MUL_DSOFTPLUS 4 /* out = v * (1 - exp(-aux))      (softplus backward, aux = softplus output) */
 #define AIR_GEMM_FP32_EXACT 0
 #define AIR_GEMM_TF32 1
+/* AIR_GEMM_TF32 needs 16-byte aligned A / B with lda, ldb multiples of 4 (TMA).  GEMMs with few
+ * output tiles and a long K (weight gradients) run split-K through a per-device workspace: give
+ * the library a caller-owned buffer (floats; NULL detaches it) so nothing is allocated inside;
+ * calls that share it must be stream-ordered.  M*N*32 floats of the largest such GEMM suffice. */
+int air_gemm_set_workspace(float *workspace, int64_t nfloats);
 int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
              int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue, int mode,
              air_stream_t stream);

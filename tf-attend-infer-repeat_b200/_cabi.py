@@ -31,6 +31,7 @@ _SIGS = {
                               [ctypes.c_int64, _c_f]),
     "air_concrete_step_bwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
     "air_gemm": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 9 + [_c_f]),
+    "air_gemm_set_workspace": (ctypes.c_int, [_c_f, ctypes.c_int64]),
     "air_lstm_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_lstm_bwd": (ctypes.c_int, [_c_f] * 8 + [ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_heads_fwd": (ctypes.c_int, [_c_f] * 14 + [ctypes.c_int64, ctypes.c_int, _c_f]),

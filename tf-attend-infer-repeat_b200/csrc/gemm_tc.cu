@@ -1,11 +1,402 @@
-// tcgen05 / TMEM / TMA TF32 GEMM (throughput mode of air_gemm).  Placeholder until the
-// tensor-core kernel lands: reports AIR_ERR_UNSUPPORTED rather than silently falling back.
+// TF32 tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) issued by one thread, FP32
+// accumulators in TMEM, operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a
+// 4-stage mbarrier ring, epilogue warps read the accumulator back with tcgen05.ld and fuse
+// Cinit / bias / activation (or activation-derivative) before the global store.
+//
+// This is the throughput mode of air_gemm() (mode AIR_GEMM_TF32); it replaces the MatMul +
+// BiasAdd (+ activation) ops of tf.contrib.layers.fully_connected / BasicLSTMCell
+// (air/vae.py:13-34, air/air_model.py:286-376) and their MatMul gradients.  Operands stay
+// FP32 in HBM (the tensor core reads the top 19 bits), so no conversion pass is needed.
+//
+// All four operand layouts are native: a K-contiguous operand is a "K-major" UMMA operand
+// (TMA box 32 x rows), an M/N-contiguous one is "MN-major" (TMA box 32 x BLOCK_K per 32-wide
+// chunk).  Weight-gradient GEMMs (reduction over the batch, few output tiles) use split-K
+// with a deterministic second pass.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cuda.h>
+
+#include <algorithm>
+
 #include "air_common.cuh"
+#include "epilogue.cuh"
 
 namespace air {
-int gemm_tf32(const float *, const float *, float *, const float *, const float *, const float *, int, int, int, int,
-              int, int, int, int, int, cudaStream_t) {
-  set_error("air_gemm: AIR_GEMM_TF32 (tcgen05) is not built yet; use AIR_GEMM_FP32_EXACT");
-  return AIR_ERR_UNSUPPORTED;
+
+constexpr int kBM = 128;      // UMMA M (cta_group::1)
+constexpr int kBK = 32;       // 32 tf32 = 128 bytes = one swizzle row
+template <int BN> struct TcCfg { static constexpr int kStages = BN >= 128 ? 3 : 4; };  // 2 CTAs / SM either way
+constexpr int kTcThreads = 192;
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
 }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);       // start address      [0,14)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset  [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                           // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32, FP32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4)                                   // c_format = F32
+         | (2u << 7) | (2u << 10)                    // a_format = b_format = TF32
+         | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16)
+         | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+struct TcParams {
+  float *C;             // output (or split-K workspace [splits][M][N] when splits > 1)
+  const float *Cinit;
+  const float *bias;
+  const float *aux;
+  int M, N, K, ldc, epi;
+  int kb_per_split, num_kb, splits;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads)
+    gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+  constexpr uint32_t kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32
+  constexpr int kStages = TcCfg<BN>::kStages;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte aligned tiles (SWIZZLE_128B atoms)
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char *sa = tiles + s * kStageBytes, *sb = sa + kABytes;
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        const int k0 = (kb_begin + i) * kBK;
+        if (!A_MN) {
+          tma_load_2d(sa, &mapA, &full_bar[s], k0, m0);  // box {32 k, 128 m}
+        } else {
+#pragma unroll
+          for (int c = 0; c < kBM / 32; ++c)  // box {32 m, 32 k} per 32-wide chunk
+            tma_load_2d(sa + c * (kBK * 128), &mapA, &full_bar[s], m0 + c * 32, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &mapB, &full_bar[s], k0, n0);  // box {32 k, BN n}
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (kBK * 128), &mapB, &full_bar[s], n0 + c * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, A_MN, B_MN);
+      // K-major: 8-row groups 1024 B apart, K advance 32 B per MMA (8 tf32).
+      // MN-major: 32-wide chunks kBK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO), K advance 1024 B.
+      constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = 1024, a_adv = A_MN ? 1024 : 32;
+      constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = 1024, b_adv = B_MN ? 1024 : 32;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + s * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo);
+          const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo);
+          umma_tf32(tmem_acc, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    float *Cout = p.C;
+    int ldo = p.ldc;
+    const bool partial = p.splits > 1;
+    if (partial) {
+      Cout = p.C + static_cast<int64_t>(split) * p.M * p.N;
+      ldo = p.N;
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_x16(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+      tmem_ld_wait();
+      if (row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < p.N) {
+            float v = __uint_as_float(r[j]);
+            if (!partial) {
+              const int64_t o = static_cast<int64_t>(row) * p.ldc + n;
+              if (p.Cinit) v += p.Cinit[o];
+              if (p.bias) v += __ldg(p.bias + n);
+              v = apply_epilogue(v, p.epi, p.aux ? p.aux[o] : 0.0f);
+            }
+            Cout[static_cast<int64_t>(row) * ldo + n] = v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, kTmemCols);
+  }
+}
+
+// second pass of split-K: C = epi((Cinit + sum_s partial[s]) + bias), s in increasing order
+__global__ void __launch_bounds__(256)
+    splitk_reduce_kernel(const float *__restrict__ ws, int splits, float *C, const float *Cinit,
+                         const float *__restrict__ bias, const float *aux, int M, int N, int ldc, int epi) {
+  const int64_t total = static_cast<int64_t>(M) * N;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(e / N), n = static_cast<int>(e - static_cast<int64_t>(m) * N);
+    float v = 0.0f;
+    for (int s = 0; s < splits; ++s) v += ws[static_cast<int64_t>(s) * total + e];
+    const int64_t o = static_cast<int64_t>(m) * ldc + n;
+    if (Cinit) v += Cinit[o];
+    if (bias) v += __ldg(bias + n);
+    C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 = contiguous dimension (extent d0), dim1 has stride ld elements (extent d1)
+static int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1, int64_t ld, int box0, int box1) {
+  EncodeTiledFn enc = get_encode();
+  AIR_REQUIRE(enc != nullptr, AIR_ERR_CUDA, "air_gemm(TF32): cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AIR_REQUIRE(r == CUDA_SUCCESS, AIR_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (d0=%lld d1=%lld ld=%lld)", (int)r,
+              (long long)d0, (long long)d1, (long long)ld);
+  return AIR_OK;
+}
+
+// split-K workspace, one per device: either provided by the caller (air_gemm_set_workspace, the
+// normal case: torch owns the memory and nothing is allocated during graph capture) or grown
+// on demand.  GEMMs that use it must be stream-ordered with each other.
+static float *g_ws[16] = {nullptr};
+static size_t g_ws_bytes[16] = {0};
+static bool g_ws_external[16] = {false};
+
+int set_gemm_workspace(float *ws, size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return AIR_ERR_CUDA;
+  dev &= 15;
+  if (g_ws[dev] && !g_ws_external[dev]) cudaFree(g_ws[dev]);
+  g_ws[dev] = ws;
+  g_ws_bytes[dev] = ws ? bytes : 0;
+  g_ws_external[dev] = ws != nullptr;
+  return AIR_OK;
+}
+
+static float *splitk_workspace(size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (g_ws_bytes[dev] < bytes) {
+    if (g_ws_external[dev]) return nullptr;  // caller's buffer is too small: fail loudly
+    if (g_ws[dev]) cudaFree(g_ws[dev]);
+    g_ws[dev] = nullptr;
+    g_ws_bytes[dev] = 0;
+    size_t want = std::max(bytes, static_cast<size_t>(64) << 20);
+    if (cudaMalloc(&g_ws[dev], want) != cudaSuccess) return nullptr;
+    g_ws_bytes[dev] = want;
+  }
+  return g_ws[dev];
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, cudaStream_t s) {
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  const size_t smem = static_cast<size_t>(TcCfg<BN>::kStages) * (kBM + BN) * kBK * 4 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(gemm_tf32): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, p.splits);
+  kern<<<grid, kTcThreads, smem, s>>>(ma, mb, p);
+  count_launch();
+  return check_launch("gemm_tf32");
+}
+
+int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
+                    int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, cudaStream_t s);
+
+int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux, int M,
+              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, cudaStream_t s) {
+  if (K == 0)  // no products at all: C = epi(Cinit + bias); nothing for the tensor cores to do
+    return gemm_fp32_exact(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, s);
+  AIR_REQUIRE(aligned16(A) && aligned16(B) && (lda % 4 == 0) && (ldb % 4 == 0), AIR_ERR_BAD_ALIGN,
+              "air_gemm(TF32): TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4 "
+              "(lda=%d ldb=%d)", lda, ldb);
+  const bool a_mn = tA != 0;   // A stored [K,M]: M contiguous
+  const bool b_mn = tB == 0;   // B stored [K,N]: N contiguous
+  const int BN = (N > 64 && static_cast<int64_t>((M + kBM - 1) / kBM) * ((N + 127) / 128) >= sm_count()) ? 128 : 64;
+
+  TcParams p;
+  p.C = C; p.Cinit = Cinit; p.bias = bias; p.aux = aux;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epi;
+  p.num_kb = (K + kBK - 1) / kBK;
+  const int64_t tiles = static_cast<int64_t>((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  int splits = 1;
+  if (tiles < sm_count() && p.num_kb >= 16) {
+    splits = static_cast<int>(std::min<int64_t>((2 * sm_count() + tiles - 1) / tiles, p.num_kb / 8));
+    splits = std::max(1, std::min(splits, 32));
+  }
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  p.splits = splits;
+  float *ws = nullptr;
+  if (splits > 1) {
+    ws = splitk_workspace(sizeof(float) * static_cast<size_t>(splits) * M * N);
+    AIR_REQUIRE(ws != nullptr, AIR_ERR_CUDA, "air_gemm(TF32): split-K workspace too small / not allocatable (%lld floats needed)",
+                (long long)splits * M * N);
+    p.C = ws;
+  }
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a_mn) rc = make_tmap(&ma, A, K, M, lda, kBK, kBM);   // [M,K] K contiguous: box {32 k, 128 m}
+  else       rc = make_tmap(&ma, A, M, K, lda, 32, kBK);    // [K,M] M contiguous: box {32 m, 32 k}
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap(&mb, B, K, N, ldb, kBK, BN);    // [N,K] K contiguous: box {32 k, BN n}
+  else       rc = make_tmap(&mb, B, N, K, ldb, 32, kBK);    // [K,N] N contiguous: box {32 n, 32 k}
+  if (rc) return rc;
+
+#define AIR_TC_DISPATCH(BNv)                                                         \
+  (a_mn ? (b_mn ? launch_tc<BNv, true, true>(ma, mb, p, s) : launch_tc<BNv, true, false>(ma, mb, p, s)) \
+        : (b_mn ? launch_tc<BNv, false, true>(ma, mb, p, s) : launch_tc<BNv, false, false>(ma, mb, p, s)))
+  rc = (BN == 128) ? AIR_TC_DISPATCH(128) : AIR_TC_DISPATCH(64);
+#undef AIR_TC_DISPATCH
+  if (rc) return rc;
+  if (splits > 1) {
+    const int64_t total = static_cast<int64_t>(M) * N;
+    const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(ws, splits, C, Cinit, bias, aux, M, N, ldc, epi);
+    count_launch();
+    rc = check_launch("splitk_reduce");
+  }
+  return rc;
+}
+
 }  // namespace air
+
+extern "C" int air_gemm_set_workspace(float *workspace, int64_t nfloats) {
+  return air::set_gemm_workspace(workspace, workspace ? sizeof(float) * static_cast<size_t>(nfloats) : 0);
+}
