@@ -15,7 +15,8 @@ from tests.parity_util import covered_fixture, cuda_noise, default_fixture, make
 pytestmark = pytest.mark.gpu
 
 
-def _compare_forward(m, out, rtol):
+def _compare_forward(m, out, rtol, canvas_rtol=None):
+    canvas_rtol = canvas_rtol or rtol
     assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"])
     assert torch.equal(m.stop_masks.cpu(), out["stop_masks"])
     assert m.executed_steps == out["executed_steps"]
@@ -23,8 +24,9 @@ def _compare_forward(m, out, rtol):
                  "scale_kls", "shift_kls", "vae_kls", "reconstruction", "reconstruction_loss"):
         got, want = getattr(m, name).cpu(), out[name]
         assert got.shape == want.shape, name
-        assert relnorm(got, want) < rtol, (name, relnorm(got, want))
-    assert abs(m.loss.item() - out["loss"].item()) <= rtol * abs(out["loss"].item())
+        tol = canvas_rtol if name in ("reconstruction", "reconstruction_loss") else rtol
+        assert relnorm(got, want) < tol, (name, relnorm(got, want))
+    assert abs(m.loss.item() - out["loss"].item()) <= canvas_rtol * abs(out["loss"].item())
     assert m.accuracy.item() == pytest.approx(out["accuracy"].item(), abs=1e-7)
 
 
@@ -36,9 +38,12 @@ def test_forward_parity(train, fixture):
     orc, m = make_pair(imgs, cnt, params, train=train)
     out = orc.forward(imgs, cnt, noise)
     m.run(cuda_noise(noise))
-    # the default-init fixture has uncovered lit pixels: 1-ulp theta differences move the loss
-    # through log(residue + 1e-9) (SURVEY hard part 1) -> the 1e-5 bar applies to the covered fixture
-    _compare_forward(m, out, 1e-5 if fixture == "covered" else 2e-3)
+    # Everything upstream of the canvas meets 1e-5 on both fixtures.  The default-init fixture has
+    # uncovered lit pixels: a 1-ulp theta difference flips a +-1e-6 rounding residue of the write-back
+    # ST to 0, which moves that pixel's -x*log(r + 1e-9) by ~7 nats (SURVEY hard part 1), so the
+    # canvas-derived quantities only agree to ~1e-2 there; test_stagewise_st_and_canvas_bit_exact
+    # shows the ST/canvas kernels themselves are bit-exact given identical inputs.
+    _compare_forward(m, out, 1e-5, canvas_rtol=None if fixture == "covered" else 3e-2)
 
 
 def test_stagewise_st_and_canvas_bit_exact():

@@ -191,3 +191,69 @@ def test_vae_function_reference_signature():
     orec.backward(g)
     rec.backward(g.to(DEV))
     assert relnorm(xg.grad, xt.grad) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 TF32 mode
+# ---------------------------------------------------------------------------------------------
+def _tf32_case(M, N, Kd, tA, tB, seed=0, ints=True, epi=K.EPI_NONE, use_cinit=False, use_bias=False):
+    rng = np.random.RandomState(seed)
+    if ints:   # small integers are exact in TF32 and their dot products are exact in FP32
+        A = rng.randint(-2, 3, (M, Kd)).astype(np.float32)
+        Bm = rng.randint(-2, 3, (Kd, N)).astype(np.float32)
+    else:
+        A = rng.randn(M, Kd).astype(np.float32)
+        Bm = rng.randn(Kd, N).astype(np.float32)
+    lda = ((Kd if not tA else M) + 3) // 4 * 4
+    ldb = ((N if not tB else Kd) + 3) // 4 * 4
+    Abuf = torch.zeros((M if not tA else Kd), lda, device=DEV)
+    Bbuf = torch.zeros((Kd if not tB else N), ldb, device=DEV)
+    Av = Abuf[:, :(Kd if not tA else M)]
+    Bv = Bbuf[:, :(N if not tB else Kd)]
+    Av.copy_(cu(A.T.copy() if tA else A))
+    Bv.copy_(cu(Bm.T.copy() if tB else Bm))
+    Ci = cu(rng.randint(-3, 4, (M, N)).astype(np.float32)) if use_cinit else None
+    bias = cu(rng.randint(-3, 4, N).astype(np.float32)) if use_bias else None
+    out = torch.full((M, N), 7.0, device=DEV)
+    ops.gemm(Av, Bv, out, Cinit=Ci, bias=bias, tA=tA, tB=tB, epi=epi, mode=K.GEMM_MODES["tf32"])
+    want = A.astype(np.float64) @ Bm.astype(np.float64)
+    if use_cinit:
+        want = want + Ci.cpu().numpy()
+    if use_bias:
+        want = want + bias.cpu().numpy()
+    return out.cpu().numpy(), want
+
+
+@pytest.mark.parametrize("tA,tB", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,Kd", [(128, 128, 32), (128, 64, 64), (256, 256, 256), (4096, 1024, 256), (200, 100, 50),
+                                    (130, 70, 36), (784, 512, 4096), (2500, 1024, 512), (64, 8, 24), (4096, 320, 256)])
+def test_gemm_tf32_exact_on_integers(M, N, Kd, tA, tB):
+    got, want = _tf32_case(M, N, Kd, tA, tB, seed=M + N + Kd)
+    assert np.array_equal(got, want.astype(np.float32)), np.abs(got - want).max()
+
+
+def test_gemm_tf32_epilogue_cinit_bias_and_splitk():
+    for (M, N, Kd, tA, tB) in ((784, 512, 4096, True, False), (4096, 512, 784, False, False), (256, 1024, 4096, True, False)):
+        got, want = _tf32_case(M, N, Kd, tA, tB, seed=1, use_cinit=True, use_bias=True, epi=K.EPI_RELU)
+        assert np.array_equal(got, np.maximum(want, 0).astype(np.float32))
+
+
+def test_gemm_tf32_random_accuracy():
+    """TF32 keeps 10 mantissa bits of each input: ~1e-3 relative on a dot product."""
+    got, want = _tf32_case(512, 384, 777 // 4 * 4, False, False, seed=2, ints=False)
+    assert relnorm(got, want) < 2e-3
+    # inputs already rounded to TF32 -> only FP32 accumulation error remains
+    rng = np.random.RandomState(3)
+    A = torch.from_numpy(rng.randn(300, 256).astype(np.float32))
+    Bm = torch.from_numpy(rng.randn(256, 200).astype(np.float32))
+    trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    A, Bm = trunc(A), trunc(Bm)
+    out = torch.empty(300, 200, device=DEV)
+    ops.gemm(A.to(DEV), Bm.to(DEV), out, mode=K.GEMM_MODES["tf32"])
+    assert relnorm(out, A.double() @ Bm.double()) < 1e-6
+
+
+def test_gemm_tf32_rejects_unaligned_leading_dimension():
+    a = torch.zeros(64, 50, device=DEV)       # ld = 50 floats = 200 bytes: not a TMA stride
+    with pytest.raises(ab.AirError, match="TMA|aligned"):
+        ops.gemm(a, torch.zeros(50, 64, device=DEV), torch.zeros(64, 64, device=DEV), mode=K.GEMM_MODES["tf32"])
