@@ -1,6 +1,6 @@
 // TF32 tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) issued by one thread, FP32
-// accumulators in TMEM, operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a
-// 4-stage mbarrier ring, epilogue warps read the accumulator back with tcgen05.ld and fuse
+// accumulators in TMEM, operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a
+// 3/4-stage mbarrier ring, epilogue warps read the accumulator back with tcgen05.ld and fuse
 // Cinit / bias / activation (or activation-derivative) before the global store.
 //
 // This is the throughput mode of air_gemm() (mode AIR_GEMM_TF32); it replaces the MatMul +
@@ -77,14 +77,17 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout).
+// layout_type 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B: the only layout the
+// tensor core accepts for MN-major 32-bit (TF32) operands -- 32-byte swizzle granules, 4-row atoms.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);       // start address      [0,14)
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset [16,30)
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset  [32,46)
   d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                           // LayoutType::SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 
@@ -171,10 +174,12 @@ __global__ void __launch_bounds__(kTcThreads)
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, A_MN, B_MN);
-      // K-major: 8-row groups 1024 B apart, K advance 32 B per MMA (8 tf32).
-      // MN-major: 32-wide chunks kBK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO), K advance 1024 B.
-      constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = 1024, a_adv = A_MN ? 1024 : 32;
-      constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = 1024, b_adv = B_MN ? 1024 : 32;
+      // K-major  (SWIZZLE_128B):         8-row groups 1024 B apart (SBO), K advance 32 B per MMA (8 tf32).
+      // MN-major (SWIZZLE_128B_BASE32B): 32-wide chunks kBK*128 B apart (LBO), 4-k-row atoms 512 B apart
+      //                                  (SBO), K advance 8 rows = 1024 B per MMA.
+      constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_adv = A_MN ? 1024 : 32;
+      constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_adv = B_MN ? 1024 : 32;
+      constexpr uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
       for (int i = 0; i < nkb; ++i) {
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
@@ -183,8 +188,8 @@ __global__ void __launch_bounds__(kTcThreads)
         const uint32_t sa = smem_u32(tiles + s * kStageBytes), sb = sa + kABytes;
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo);
-          const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo);
+          const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lt);
+          const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_acc, da, db, idesc, (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
@@ -270,7 +275,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor map: dim0 = contiguous dimension (extent d0), dim1 has stride ld elements (extent d1)
-static int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1, int64_t ld, int box0, int box1) {
+static int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1, int64_t ld, int box0, int box1,
+                     bool mn_major) {
   EncodeTiledFn enc = get_encode();
   AIR_REQUIRE(enc != nullptr, AIR_ERR_CUDA, "air_gemm(TF32): cuTensorMapEncodeTiled is unavailable");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1)};
@@ -278,7 +284,9 @@ static int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AIR_REQUIRE(r == CUDA_SUCCESS, AIR_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (d0=%lld d1=%lld ld=%lld)", (int)r,
               (long long)d0, (long long)d1, (long long)ld);
@@ -372,11 +380,11 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
 
   CUtensorMap ma, mb;
   int rc;
-  if (!a_mn) rc = make_tmap(&ma, A, K, M, lda, kBK, kBM);   // [M,K] K contiguous: box {32 k, 128 m}
-  else       rc = make_tmap(&ma, A, M, K, lda, 32, kBK);    // [K,M] M contiguous: box {32 m, 32 k}
+  if (!a_mn) rc = make_tmap(&ma, A, K, M, lda, kBK, kBM, false);  // [M,K] K contiguous: box {32 k, 128 m}
+  else       rc = make_tmap(&ma, A, M, K, lda, 32, kBK, true);    // [K,M] M contiguous: box {32 m, 32 k}
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap(&mb, B, K, N, ldb, kBK, BN);    // [N,K] K contiguous: box {32 k, BN n}
-  else       rc = make_tmap(&mb, B, N, K, ldb, 32, kBK);    // [K,N] N contiguous: box {32 n, 32 k}
+  if (!b_mn) rc = make_tmap(&mb, B, K, N, ldb, kBK, BN, false);   // [N,K] K contiguous: box {32 k, BN n}
+  else       rc = make_tmap(&mb, B, N, K, ldb, 32, kBK, true);    // [K,N] N contiguous: box {32 n, 32 k}
   if (rc) return rc;
 
 #define AIR_TC_DISPATCH(BNv)                                                         \
