@@ -168,10 +168,11 @@ int air_heads_bwd(const float *hidden, const float *w_out, const float *noise_sc
                   float *db_out, int accumulate, float *workspace, int64_t B, int HU, air_stream_t stream);
 
 /* VAE latent (vae.py:22-24, air_model.py:479-493): ml [B,2L] = (mean | log_variance);
- * sample = mean + noise*sqrt(exp(lv)); KL vs N(prior) -> fields[AIR_F_KL_VAE];
+ * sample [B,L] with leading dimension ld_sample >= L (padded so it can feed the TMA GEMM)
+ * = mean + noise*sqrt(exp(lv)); KL vs N(prior) -> fields[AIR_F_KL_VAE];
  * loss += (stop_new < thr ? kl : 0). */
-int air_vae_latent_fwd(const float *ml, const float *noise, const air_hyper_t *hyper, float *sample, float *fields,
-                       float *loss, int64_t B, int L, air_stream_t stream);
+int air_vae_latent_fwd(const float *ml, const float *noise, const air_hyper_t *hyper, float *sample, int ld_sample,
+                       float *fields, float *loss, int64_t B, int L, air_stream_t stream);
 int air_vae_latent_bwd(const float *ml, const float *noise, const float *dsample, const float *fields,
                        const air_hyper_t *hyper, float dloss, float *dml, int64_t B, int L, air_stream_t stream);
 

@@ -170,3 +170,24 @@ def test_constructor_rejects_out_of_scope_options():
         ab.AIRModel(x, t)                                   # reference default cnn=True is a "next" row
     with pytest.raises(ab.AirError):
         ab.AIRModel(x.cpu(), t.cpu(), cnn=False)
+
+
+def test_tf32_mode_close_to_oracle_and_trains():
+    """Throughput mode (tcgen05, TF32 inputs, FP32 accumulate): ~1e-3 relative GEMM error, so
+    the 1e-5 parity bar does not apply; counts still agree and gradients stay close."""
+    B = 64
+    imgs, cnt, params, noise = covered_fixture(B, seed=9)
+    orc, m = make_pair(imgs, cnt, params, train=True, gemm_mode="tf32")
+    out, grads = orc.loss_and_grads(imgs, cnt, noise)
+    m.loss_and_grads(cuda_noise(noise))
+    assert (m.rec_num_digits.cpu() == out["rec_num_digits"]).float().mean() > 0.95
+    assert abs(m.loss.item() - out["loss"].item()) <= 5e-3 * abs(out["loss"].item())
+    tot = lambda gd: torch.cat([gd[k].detach().cpu().double().reshape(-1) for k in grads])
+    e = relnorm(tot(m.store.named_grads()), tot(grads))
+    print(f"tf32 mode: loss rel err {abs(m.loss.item() - out['loss'].item()) / abs(out['loss'].item()):.2e}, grad rel err {e:.2e}")
+    assert e < 5e-2
+    first = m.loss.item()
+    m.noise = None
+    for _ in range(40):
+        m.train_step()
+    assert np.isfinite(m.loss.item()) and m.loss.item() < first

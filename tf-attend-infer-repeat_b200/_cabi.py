@@ -38,7 +38,7 @@ _SIGS = {
     "air_heads_bwd_workspace": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int]),
     "air_heads_bwd": (ctypes.c_int, [_c_f] * 10 + [ctypes.c_float] + [_c_f] * 3 + [ctypes.c_int, _c_f, ctypes.c_int64,
                                                                                  ctypes.c_int, _c_f]),
-    "air_vae_latent_fwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_vae_latent_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int] + [_c_f] * 2 + [ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_vae_latent_bwd": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float, _c_f, ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_sigmoid_noise_fwd": (ctypes.c_int, [_c_f, _c_f, ctypes.c_float, _c_f, ctypes.c_int64, _c_f]),
     "air_sigmoid_bwd": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int64, _c_f]),

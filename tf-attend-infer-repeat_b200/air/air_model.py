@@ -111,6 +111,12 @@ class AIRModel:
             self.world = torch.distributed.get_world_size(process_group)
 
         self._alloc()
+        if self.gemm == C.GEMM_MODES["tf32"]:
+            # torch-owned split-K workspace for the weight-gradient GEMMs (nothing is allocated inside the library)
+            AIRModel._gemm_ws = getattr(AIRModel, "_gemm_ws", None)
+            if AIRModel._gemm_ws is None or AIRModel._gemm_ws.device != self.device:
+                AIRModel._gemm_ws = torch.empty(16 << 20, device=self.device, dtype=torch.float32)
+            ops.set_gemm_workspace(AIRModel._gemm_ws)
         self._graphs = None
         self.noise = None
         self.rec_num_digits = self.rec_scales = self.reconstruction = None
@@ -139,7 +145,8 @@ class AIRModel:
         w["theta"], w["theta_inv"] = z(T, B, 6), z(T, B, 6)
         w["win"] = z(T, B, win)
         w["enc"] = [z(T, B, u) for u in self.vae_recognition_units]
-        w["ml"], w["zs"] = z(T, B, 2 * L), z(T, B, L)
+        Lp = (L + 3) // 4 * 4  # TMA operands need a leading dimension that is a multiple of 4 floats
+        w["ml"], w["zs"] = z(T, B, 2 * L), torch.zeros(T, B, Lp, device=dev)[:, :, :L]
         w["dec"] = [z(T, B, u) for u in self.vae_generative_units]
         w["recon"] = z(T, B, win)
         w["gen"] = z(B, win)

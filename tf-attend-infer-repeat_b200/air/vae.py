@@ -35,8 +35,9 @@ class VAEWeights:
 def alloc_vae_buffers(B, win, rec_units, L, gen_units, device, lead=()):
     """Activation buffers of one (or ``lead``-many) VAE evaluations."""
     z = lambda *s: torch.empty(*lead, *s, device=device, dtype=torch.float32)
-    return dict(enc=[z(B, u) for u in rec_units], ml=z(B, 2 * L), zs=z(B, L), dec=[z(B, u) for u in gen_units],
-                recon=z(B, win))
+    Lp = (L + 3) // 4 * 4  # the sample feeds a TMA GEMM: leading dimension must be a multiple of 4
+    return dict(enc=[z(B, u) for u in rec_units], ml=z(B, 2 * L), zs=torch.zeros(*lead, B, Lp, device=device)[..., :L],
+                dec=[z(B, u) for u in gen_units], recon=z(B, win))
 
 
 def vae_forward(x, w: VAEWeights, noise_latent, noise_like, likelihood_std, hyper, buf, gen_tmp, fields, loss, mode):

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256)
 // =========================================================================================
 __global__ void __launch_bounds__(256)
     vae_latent_fwd_k(const float *__restrict__ ml, const float *__restrict__ noise, air_hyper_t hp,
-                     float *__restrict__ sample, float *__restrict__ fields, float *loss, int64_t B, int L) {
+                     float *__restrict__ sample, int lds, float *__restrict__ fields, float *loss, int64_t B, int L) {
   const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256)
   for (int d = lane; d < L; d += 32) {
     const float mean = ml[b * 2 * L + d], lv = ml[b * 2 * L + L + d];
     const float var = expf(lv);
-    sample[b * L + d] = mean + noise[b * L + d] * sqrtf(var);
+    sample[b * lds + d] = mean + noise[b * L + d] * sqrtf(var);
     acc += gauss_kl_term(mean, lv, var, pm, pv, plv);
   }
   acc = 0.5f * warp_sum(acc);
@@ -526,12 +526,12 @@ extern "C" int air_heads_bwd(const float *hidden, const float *w_out, const floa
 }
 
 extern "C" int air_vae_latent_fwd(const float *ml, const float *noise, const air_hyper_t *hyper, float *sample,
-                                  float *fields, float *loss, int64_t B, int L, air_stream_t stream) {
-  AIR_REQUIRE(B >= 0 && L > 0, AIR_ERR_BAD_SHAPE, "vae_latent_fwd: bad shape");
+                                  int ld_sample, float *fields, float *loss, int64_t B, int L, air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && L > 0 && ld_sample >= L, AIR_ERR_BAD_SHAPE, "vae_latent_fwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(ml && noise && hyper && sample && fields && loss, AIR_ERR_NULL, "vae_latent_fwd: null pointer");
-  vae_latent_fwd_k<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, ST(stream)>>>(ml, noise, *hyper, sample, fields,
-                                                                                       loss, B, L);
+  vae_latent_fwd_k<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, ST(stream)>>>(ml, noise, *hyper, sample, ld_sample,
+                                                                                       fields, loss, B, L);
   count_launch();
   return check_launch("vae_latent_fwd");
 }

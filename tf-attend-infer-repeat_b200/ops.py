@@ -72,8 +72,8 @@ def heads_bwd(hidden, w_out, n_scale, n_shift, fields, dtheta, dtheta_inv, dz, p
 
 def vae_latent_fwd(ml, noise, hyper, sample, fields, loss):
     B, L2 = ml.shape
-    check(lib().air_vae_latent_fwd(ptr(ml), ptr(noise), ctypes.byref(hyper), ptr(sample), ptr(fields), ptr(loss), B,
-                                   L2 // 2, stream()), "air_vae_latent_fwd")
+    check(lib().air_vae_latent_fwd(ptr(ml), ptr(noise), ctypes.byref(hyper), _p2(sample), _ld(sample), ptr(fields),
+                                   ptr(loss), B, L2 // 2, stream()), "air_vae_latent_fwd")
 
 
 def vae_latent_bwd(ml, noise, dsample, fields, hyper, dloss, dml):
@@ -118,6 +118,11 @@ def anneal(state, schedule, out):
                            int(bool(schedule.get("staircase", False))), float(schedule.get("min", nan)),
                            float(schedule.get("max", nan)), int(bool(schedule.get("log", False))), ptr(out), stream()),
           "air_anneal")
+
+
+def set_gemm_workspace(ws):
+    """Attach a caller-owned split-K workspace (float32 CUDA tensor) to the TF32 GEMM; None detaches."""
+    check(lib().air_gemm_set_workspace(ptr(ws), 0 if ws is None else ws.numel()), "air_gemm_set_workspace")
 
 
 def st_forward(U, theta, out, H, W, Cc, oh, ow):
