@@ -24,6 +24,9 @@ def covered_fixture(B, seed=0, T=3):
     params["shift/log_variance/output/biases"] -= 8.0
     params["shift/mean/output/weights"] *= 0.05
     params["z_pres/log_odds/output/biases"] += 5.0
+    # keep the 3-step canvas sum well inside (0, 1): sigmoid(-2) ~ 0.12 per step.  (With ~0.5 per step
+    # the sum exceeds 1, the clip blocks almost every gradient and the rest sits at 1/(1 - r), r -> 1.)
+    params["vae/gen_mean/biases"] -= 2.0
     return im.reshape(B, -1).contiguous(), cnt, params, O.make_noise(seed, T, B)
 
 

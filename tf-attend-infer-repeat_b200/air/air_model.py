@@ -32,7 +32,7 @@ import torch
 from .. import _cabi as C
 from .. import ops
 from .params import ParamStore
-from .vae import (VAEWeights, alloc_vae_scratch, dense_bwd, vae_backward, vae_forward)
+from .vae import (VAEWeights, _flat2, alloc_vae_scratch, dense_dw, vae_backward_dx, vae_forward, vae_weight_grads)
 
 _VARIABLE_SCOPES = {}
 
@@ -158,13 +158,15 @@ class AIRModel:
                           concrete_u=z(T, B))
         if self.train:
             w["dcanvas"] = z(B, cs2)
-            w["d_recon"] = z(B, win)
             w["dwin"] = z(B, win)
             w["dtheta"], w["dtheta_inv"], w["dz"] = z(B, 6), z(B, 6), z(B)
-            w["dhh"] = z(B, 5 * HU)
             w["dh"], w["dh_next"], w["dc"] = z(B, R), z(B, R), z(B, R)
-            w["dgates"], w["dgates_sum"] = z(B, 4 * R), z(B, 4 * R)
-            w["vae_scratch"] = alloc_vae_scratch(B, win, self.vae_recognition_units, L, self.vae_generative_units, dev)
+            # pre-activation gradients are kept for all T steps: the weight-gradient GEMMs run once
+            # per train step over the time-batched [T*B, .] buffers (one long-K GEMM per layer)
+            w["dhh"] = z(T, B, 5 * HU)
+            w["dgates"], w["dgates_sum"] = z(T, B, 4 * R), z(B, 4 * R)
+            w["vae_d"] = alloc_vae_scratch(B, win, self.vae_recognition_units, L, self.vae_generative_units, dev,
+                                           lead=(T,))
             nmax = max(4 * R, 5 * HU, win, 2 * L, *self.vae_recognition_units, *self.vae_generative_units)
             w["colsum_ws"] = torch.zeros(int(C.lib().air_colsum_workspace(B, nmax)), device=dev)
             w["heads_ws"] = torch.zeros(int(C.lib().air_heads_bwd_workspace(B, HU)), device=dev)
@@ -255,33 +257,39 @@ class AIRModel:
         n = w["noise"]
         dscale = 1.0 / (B * self.world)
         w["dgates_sum"].zero_()
-        if T == 1:
-            self.gKh.zero_()
+        vd = w["vae_d"]
         for t in range(T - 1, -1, -1):
-            acc = t != T - 1
+            last = t == T - 1
             f = w["fields"][t]
+            dbuf = dict(denc=[d[t] for d in vd["denc"]], dml=vd["dml"][t], dzs=vd["dzs"][t],
+                        ddec=[d[t] for d in vd["ddec"]], dgen=vd["dgen"][t])
             ops.writeback_canvas_bwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
-                                     self.stopping_threshold, w["dcanvas"], w["d_recon"], w["dtheta_inv"], w["dz"],
+                                     self.stopping_threshold, w["dcanvas"], dbuf["dgen"], w["dtheta_inv"], w["dz"],
                                      wsz, wsz, cs, cs)
-            vae_backward(w["win"][t], self.vw, n["vae_latent"][t], hp, self._vae_buf(t), w["d_recon"], dscale, f,
-                         w["vae_scratch"], acc, w["colsum_ws"], mode, dx_out=w["dwin"])
+            vae_backward_dx(w["win"][t], self.vw, n["vae_latent"][t], hp, self._vae_buf(t), dbuf, dscale, f, mode,
+                            dx_out=w["dwin"])
             ops.st_backward(x, w["theta"][t], w["dwin"], None, w["dtheta"], cs, cs, 1, wsz, wsz)
             ops.heads_bwd(w["hh"][t], p["heads/out_w"], n["scale"][t], n["shift"][t], f, w["dtheta"], w["dtheta_inv"],
-                          w["dz"], self._prior, hp, dscale, w["dhh"], g["heads/out_w"], g["heads/out_b"], acc,
+                          w["dz"], self._prior, hp, dscale, w["dhh"][t], g["heads/out_w"], g["heads/out_b"], not last,
                           w["heads_ws"])
-            # hidden head layer (input h_t, a tanh*sigmoid output: no activation mask on dX)
-            ops.gemm(w["h"][t], w["dhh"], g["heads/hidden_w"], Cinit=g["heads/hidden_w"] if acc else None, tA=True,
-                     mode=mode)
-            ops.colsum(w["dhh"], g["heads/hidden_b"], acc, w["colsum_ws"])
-            ops.gemm(w["dhh"], p["heads/hidden_w"], w["dh"], Cinit=w["dh_next"] if acc else None, tB=True, mode=mode)
+            # dh_t = dhh_t W_hid^T (+ the LSTM path from step t+1)
+            ops.gemm(w["dhh"][t], p["heads/hidden_w"], w["dh"], Cinit=None if last else w["dh_next"], tB=True, mode=mode)
             ops.lstm_bwd(w["gates"][t], w["c"][t - 1] if t > 0 else None, w["c"][t], w["dh"],
-                         w["dc"] if acc else None, w["dgates"], w["dc"], w["dgates_sum"])
+                         None if last else w["dc"], w["dgates"][t], w["dc"], w["dgates_sum"])
             if t > 0:
-                ops.gemm(w["h"][t - 1], w["dgates"], self.gKh, Cinit=self.gKh if acc else None, tA=True, mode=mode)
-                ops.gemm(w["dgates"], self.Kh, w["dh_next"], tB=True, mode=mode)
+                ops.gemm(w["dgates"][t], self.Kh, w["dh_next"], tB=True, mode=mode)
+        # ---- weight gradients, once per train step, over the time-batched buffers
+        cws = w["colsum_ws"]
+        allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
+        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, vd, cws, mode)
+        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], cws, mode)
+        if T > 1:   # K_h sees h_{t-1}: rows t = 1..T-1 (h_{-1} = 0 contributes nothing)
+            ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode)
+        else:
+            self.gKh.zero_()
         # the image rows of the LSTM kernel see the same x every step: one GEMM on the summed dgates
         ops.gemm(x, w["dgates_sum"], self.gKx, tA=True, mode=mode)
-        ops.colsum(w["dgates_sum"], g["rnn/bias"], False, w["colsum_ws"])
+        ops.colsum(w["dgates_sum"], g["rnn/bias"], False, cws)
 
     def _apply_gradients(self):
         """air_model.py:673, 692: clip by global norm, Adam, global_step += 1."""

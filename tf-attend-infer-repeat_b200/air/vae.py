@@ -59,45 +59,72 @@ def vae_forward(x, w: VAEWeights, noise_latent, noise_like, likelihood_std, hype
     return buf["recon"]
 
 
-def dense_bwd(x_in, W, dY, gW, gb, accumulate, colsum_ws, mode, dX=None, act_of_x=False):
-    """Gradients of Y = x_in W + b: gW (+)= x_in^T dY, gb (+)= colsum(dY),
-    dX = (dY W^T) * softplus'(pre-activation of x_in) when x_in is a softplus output."""
-    ops.gemm(x_in, dY, gW, Cinit=gW if accumulate else None, tA=True, mode=mode)
-    ops.colsum(dY, gb, accumulate, colsum_ws)
-    if dX is not None:
-        ops.gemm(dY, W, dX, tB=True, aux=x_in if act_of_x else None,
-                 epi=C.EPI_MUL_DSOFTPLUS if act_of_x else C.EPI_NONE, mode=mode)
+def dense_dx(x_in, W, dY, dX, mode, act_of_x=False):
+    """dX = (dY W^T) * softplus'(pre-activation of x_in) when x_in is a softplus output."""
+    ops.gemm(dY, W, dX, tB=True, aux=x_in if act_of_x else None,
+             epi=C.EPI_MUL_DSOFTPLUS if act_of_x else C.EPI_NONE, mode=mode)
     return dX
 
 
-def vae_backward(x, w: VAEWeights, noise_latent, hyper, buf, drecon, dloss, fields, scratch, accumulate, colsum_ws,
-                 mode, dx_out=None):
-    """drecon [B,win] (overwritten) -> parameter gradients (+ dx_out [B,win] if given).
-    scratch: dict of [B,u] gradient buffers keyed like buf (allocated by the caller)."""
-    ops.sigmoid_bwd(buf["recon"], drecon, drecon)  # d gen_mean, in place
-    dY = drecon
+def dense_dw(x_in, dY, gW, gb, colsum_ws, mode, accumulate=False):
+    """gW (+)= x_in^T dY, gb (+)= colsum(dY).  x_in / dY may be time-batched [T*B, .] views."""
+    ops.gemm(x_in, dY, gW, Cinit=gW if accumulate else None, tA=True, mode=mode)
+    ops.colsum(dY, gb, accumulate, colsum_ws)
+
+
+def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fields, mode, dx_out=None):
+    """Backward through one VAE evaluation, activations only (air/vae.py:9-41 reversed).
+    dbuf['dgen'] holds d(loss)/d(reconstruction) on entry; on exit dbuf holds the gradient
+    w.r.t. every layer's pre-activation output (dgen, ddec[i], dml, denc[i]) -- the dY
+    operands of the deferred weight-gradient GEMMs (vae_weight_grads)."""
+    ops.sigmoid_bwd(buf["recon"], dbuf["dgen"], dbuf["dgen"])  # d gen_mean, in place
+    dY = dbuf["dgen"]
     acts = [buf["zs"]] + list(buf["dec"])
     layers = list(w.gen) + [w.gm]
-    grads = list(w.g_gen) + [w.g_gm]
-    dbufs = [scratch["dzs"]] + list(scratch["ddec"])
+    douts = [dbuf["dzs"]] + list(dbuf["ddec"])
     for i in range(len(layers) - 1, -1, -1):
-        dY = dense_bwd(acts[i], layers[i][0], dY, grads[i][0], grads[i][1], accumulate, colsum_ws, mode, dX=dbufs[i],
-                       act_of_x=(i > 0))
-    ops.vae_latent_bwd(buf["ml"], noise_latent, dY, fields, hyper, dloss, scratch["dml"])
-    dY = scratch["dml"]
+        dY = dense_dx(acts[i], layers[i][0], dY, douts[i], mode, act_of_x=(i > 0))
+    ops.vae_latent_bwd(buf["ml"], noise_latent, dY, fields, hyper, dloss, dbuf["dml"])
+    dY = dbuf["dml"]
     acts = [x] + list(buf["enc"])
     layers = list(w.rec) + [w.ml]
-    grads = list(w.g_rec) + [w.g_ml]
-    dbufs = [dx_out] + list(scratch["denc"])
+    douts = [dx_out] + list(dbuf["denc"])
     for i in range(len(layers) - 1, -1, -1):
-        dY = dense_bwd(acts[i], layers[i][0], dY, grads[i][0], grads[i][1], accumulate, colsum_ws, mode, dX=dbufs[i],
-                       act_of_x=(i > 0))
+        if douts[i] is None:
+            break
+        dY = dense_dx(acts[i], layers[i][0], dY, douts[i], mode, act_of_x=(i > 0))
     return dx_out
 
 
-def alloc_vae_scratch(B, win, rec_units, L, gen_units, device):
-    z = lambda *s: torch.empty(*s, device=device, dtype=torch.float32)
-    return dict(denc=[z(B, u) for u in rec_units], dml=z(B, 2 * L), dzs=z(B, L), ddec=[z(B, u) for u in gen_units])
+def vae_weight_grads(x, w: VAEWeights, buf, dbuf, colsum_ws, mode, accumulate=False):
+    """All VAE parameter gradients from (time-batched) activations ``buf`` and the matching
+    pre-activation gradients ``dbuf``: one long-K GEMM + one column sum per layer."""
+    flat = lambda t: t.reshape(-1, t.shape[-1]) if t.is_contiguous() else t.flatten(0, -2)
+    acts = [buf["zs"]] + list(buf["dec"])
+    dys = list(dbuf["ddec"]) + [dbuf["dgen"]]
+    grads = list(w.g_gen) + [w.g_gm]
+    for a, dy, (gW, gb) in zip(acts, dys, grads):
+        dense_dw(_flat2(a), _flat2(dy), gW, gb, colsum_ws, mode, accumulate)
+    acts = [x] + list(buf["enc"])
+    dys = list(dbuf["denc"]) + [dbuf["dml"]]
+    grads = list(w.g_rec) + [w.g_ml]
+    for a, dy, (gW, gb) in zip(acts, dys, grads):
+        dense_dw(_flat2(a), _flat2(dy), gW, gb, colsum_ws, mode, accumulate)
+
+
+def _flat2(t):
+    """[T,B,n] (possibly a padded view with unit inner stride) -> [T*B, n] view."""
+    if t.dim() == 2:
+        return t
+    T, B, n = t.shape
+    assert t.stride(2) == 1 and t.stride(0) == B * t.stride(1)
+    return t.as_strided((T * B, n), (t.stride(1), 1), t.storage_offset())
+
+
+def alloc_vae_scratch(B, win, rec_units, L, gen_units, device, lead=()):
+    z = lambda *s: torch.empty(*lead, *s, device=device, dtype=torch.float32)
+    return dict(denc=[z(B, u) for u in rec_units], dml=z(B, 2 * L), dzs=z(B, L), ddec=[z(B, u) for u in gen_units],
+                dgen=z(B, win))
 
 
 # ------------------------------------------------------------------------------------------
@@ -138,7 +165,7 @@ class _VAEFunction(torch.autograd.Function):
         B = x.shape[0]
         d = store.dims
         dev = x.device
-        scratch = alloc_vae_scratch(B, d["win"], d["rec_units"], d["L"], d["gen_units"], dev)
+        dbuf = alloc_vae_scratch(B, d["win"], d["rec_units"], d["L"], d["gen_units"], dev)
         ws = torch.zeros(int(C.lib().air_colsum_workspace(B, max(d["win"], 2 * d["L"], *d["rec_units"], *d["gen_units"]))),
                          device=dev)
         dx = torch.empty_like(x)
@@ -148,8 +175,9 @@ class _VAEFunction(torch.autograd.Function):
             raise NotImplementedError("vae(): gradients through rec_mean / rec_log_variance outputs are taken by "
                                       "AIRModel's fused schedule; the standalone function differentiates the "
                                       "reconstruction only")
-        vae_backward(x, w, noise_latent, hyper, buf, drecon.contiguous().clone(), 0.0, fields, scratch, False, ws, mode,
-                     dx_out=dx)
+        dbuf["dgen"].copy_(drecon)
+        vae_backward_dx(x, w, noise_latent, hyper, buf, dbuf, 0.0, fields, mode, dx_out=dx)
+        vae_weight_grads(x, w, buf, dbuf, ws, mode)
         return dx, store.grad.clone(), None, None, None, None, None, None, None
 
 

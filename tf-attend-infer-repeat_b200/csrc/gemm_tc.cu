@@ -209,15 +209,40 @@ __global__ void __launch_bounds__(kTcThreads)
       Cout = p.C + static_cast<int64_t>(split) * p.M * p.N;
       ldo = p.N;
     }
+    const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) &&
+                        (partial || ((!p.Cinit || (reinterpret_cast<uintptr_t>(p.Cinit) & 15) == 0) &&
+                                     (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t r[16];
       tmem_ld_x16(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
       tmem_ld_wait();
-      if (row < p.M) {
+      if (row >= p.M || n0 + c0 >= p.N) continue;
+      const int nb = n0 + c0;
+      if (vec_ok && nb + 16 <= p.N) {
+        float4 *dst = reinterpret_cast<float4 *>(Cout + static_cast<int64_t>(row) * ldo + nb);
+        const int64_t o = static_cast<int64_t>(row) * p.ldc + nb;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          float v[4] = {__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                        __uint_as_float(r[4 * j4 + 3])};
+          if (!partial) {
+            float ci[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.Cinit) *reinterpret_cast<float4 *>(ci) = *reinterpret_cast<const float4 *>(p.Cinit + o + 4 * j4);
+            if (p.aux) *reinterpret_cast<float4 *>(ax) = *reinterpret_cast<const float4 *>(p.aux + o + 4 * j4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float t = v[j] + ci[j];
+              if (p.bias) t += __ldg(p.bias + nb + 4 * j4 + j);
+              v[j] = apply_epilogue(t, p.epi, ax[j]);
+            }
+          }
+          dst[j4] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
+          const int n = nb + j;
           if (n < p.N) {
             float v = __uint_as_float(r[j]);
             if (!partial) {
@@ -240,20 +265,41 @@ __global__ void __launch_bounds__(kTcThreads)
   }
 }
 
-// second pass of split-K: C = epi((Cinit + sum_s partial[s]) + bias), s in increasing order
+// second pass of split-K: C = epi((Cinit + sum_s partial[s]) + bias), s in increasing order.
+// float4 per thread, splits loop unrolled 4x so the partial loads are in flight together.
 __global__ void __launch_bounds__(256)
     splitk_reduce_kernel(const float *__restrict__ ws, int splits, float *C, const float *Cinit,
                          const float *__restrict__ bias, const float *aux, int M, int N, int ldc, int epi) {
-  const int64_t total = static_cast<int64_t>(M) * N;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
-       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int64_t total = static_cast<int64_t>(M) * N;  // N % 4 == 0 on this path
+  const int64_t nvec = total >> 2;
+  for (int64_t v4 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v4 < nvec;
+       v4 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = v4 << 2;
+    const float4 *src = reinterpret_cast<const float4 *>(ws + e);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+      const float4 a = __ldg(src + (static_cast<int64_t>(s) * total >> 2));
+      const float4 b = __ldg(src + (static_cast<int64_t>(s + 1) * total >> 2));
+      const float4 c = __ldg(src + (static_cast<int64_t>(s + 2) * total >> 2));
+      const float4 d = __ldg(src + (static_cast<int64_t>(s + 3) * total >> 2));
+      acc.x = (((acc.x + a.x) + b.x) + c.x) + d.x; acc.y = (((acc.y + a.y) + b.y) + c.y) + d.y;
+      acc.z = (((acc.z + a.z) + b.z) + c.z) + d.z; acc.w = (((acc.w + a.w) + b.w) + c.w) + d.w;
+    }
+    for (; s < splits; ++s) {
+      const float4 a = __ldg(src + (static_cast<int64_t>(s) * total >> 2));
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
     const int m = static_cast<int>(e / N), n = static_cast<int>(e - static_cast<int64_t>(m) * N);
-    float v = 0.0f;
-    for (int s = 0; s < splits; ++s) v += ws[static_cast<int64_t>(s) * total + e];
-    const int64_t o = static_cast<int64_t>(m) * ldc + n;
-    if (Cinit) v += Cinit[o];
-    if (bias) v += __ldg(bias + n);
-    C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f);
+    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t o = static_cast<int64_t>(m) * ldc + n + j;
+      float v = vals[j];
+      if (Cinit) v += Cinit[o];
+      if (bias) v += __ldg(bias + n + j);
+      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f);
+    }
   }
 }
 
@@ -355,7 +401,8 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
               "(lda=%d ldb=%d)", lda, ldb);
   const bool a_mn = tA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = tB == 0;   // B stored [K,N]: N contiguous
-  const int BN = (N > 64 && static_cast<int64_t>((M + kBM - 1) / kBM) * ((N + 127) / 128) >= sm_count()) ? 128 : 64;
+  const int64_t tiles128 = static_cast<int64_t>((M + kBM - 1) / kBM) * ((N + 127) / 128);
+  const int BN = (N > 64 && (tiles128 * 5 >= sm_count() * 3 || K >= 2048)) ? 128 : 64;
 
   TcParams p;
   p.C = C; p.Cinit = Cinit; p.bias = bias; p.aux = aux;
@@ -363,7 +410,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   p.num_kb = (K + kBK - 1) / kBK;
   const int64_t tiles = static_cast<int64_t>((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   int splits = 1;
-  if (tiles < sm_count() && p.num_kb >= 16) {
+  if (tiles < sm_count() && p.num_kb >= 16 && N % 4 == 0) {
     splits = static_cast<int>(std::min<int64_t>((2 * sm_count() + tiles - 1) / tiles, p.num_kb / 8));
     splits = std::max(1, std::min(splits, 32));
   }
@@ -394,7 +441,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
 #undef AIR_TC_DISPATCH
   if (rc) return rc;
   if (splits > 1) {
-    const int64_t total = static_cast<int64_t>(M) * N;
+    const int64_t total = static_cast<int64_t>(M) * N / 4;
     const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
     splitk_reduce_kernel<<<blocks, 256, 0, s>>>(ws, splits, C, Cinit, bias, aux, M, N, ldc, epi);
     count_launch();

@@ -228,7 +228,13 @@ __global__ void __launch_bounds__(256)
     reduce_rows_k(const float *__restrict__ partials, int R, int stride, int n, float *out, int accumulate) {
   AIR_GRID_STRIDE(e, n) {
     float acc = 0.0f;
-    for (int r = 0; r < R; ++r) acc += partials[static_cast<int64_t>(r) * stride + e];
+    int r = 0;
+    for (; r + 4 <= R; r += 4) {  // four loads in flight, summed in row order
+      const float a = partials[static_cast<int64_t>(r) * stride + e], b = partials[static_cast<int64_t>(r + 1) * stride + e];
+      const float c = partials[static_cast<int64_t>(r + 2) * stride + e], d = partials[static_cast<int64_t>(r + 3) * stride + e];
+      acc = (((acc + a) + b) + c) + d;
+    }
+    for (; r < R; ++r) acc += partials[static_cast<int64_t>(r) * stride + e];
     out[e] = accumulate ? out[e] + acc : acc;
   }
 }
