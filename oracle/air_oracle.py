@@ -372,13 +372,15 @@ class AIROracle:
                                  p[f"{head}/{stat}/hidden/biases"], torch.relu)
         return fully_connected(hidden, p[f"{head}/{stat}/output/weights"], p[f"{head}/{stat}/output/biases"])
 
-    def forward(self, input_images, target_num_digits, noise, keep=None):
+    def forward(self, input_images, target_num_digits, noise, keep=None, taps=None):
         """Runs exactly ``max_steps`` iterations of body() (air_model.py:278-508); items
         that already stopped contribute exact +0.0 (tf.where), so loss / canvas / digit
         counts equal the reference's early-exit loop.  ``executed_steps``
         is the trip count the reference's cond() (:271-275) would have produced.
 
-        ``keep`` (optional dict) receives intermediates for stage-wise parity checks."""
+        ``keep`` (optional dict) receives intermediates for stage-wise parity checks; ``taps``
+        (optional dict) receives the raw per-step graph tensors with retain_grad() set, so a
+        later backward() exposes d(loss)/d(intermediate) for localising gradient mismatches."""
         h, p, dt = self.h, self.params, self.dtype
         B = input_images.shape[0]
         cs, ws = h["canvas_size"], h["windows_size"]
@@ -500,6 +502,12 @@ class AIROracle:
             running_loss = running_loss + torch.where(live, vae_kl, torch.zeros_like(running_loss))
             ta["vae_kls"].append(vae_kl)
 
+        if taps is not None:
+            for k in ("thetas", "st_backward", "windows", "windows_in", "z_pres", "scales", "shifts"):
+                taps[k] = ta[k]
+                for tns in ta[k]:
+                    if tns.requires_grad:
+                        tns.retain_grad()
         # ---- post-loop (:569-611)
         out = {
             "rec_num_digits": running_digits,

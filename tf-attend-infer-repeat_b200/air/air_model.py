@@ -278,6 +278,8 @@ class AIRModel:
                          None if last else w["dc"], w["dgates"][t], w["dc"], w["dgates_sum"])
             if t > 0:
                 ops.gemm(w["dgates"][t], self.Kh, w["dh_next"], tB=True, mode=mode)
+            if getattr(self, "_debug", None) is not None:  # per-step intermediate gradients for diagnostics
+                self._debug[t] = {k: w[k].clone() for k in ("dwin", "dtheta", "dtheta_inv", "dz", "dh")}
         # ---- weight gradients, once per train step, over the time-batched buffers
         cws = w["colsum_ws"]
         allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
