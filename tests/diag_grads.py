@@ -17,11 +17,24 @@ leaves = {k: v.detach().clone().requires_grad_(True) for k, v in orc.params.item
 orc.params = leaves
 taps = {}
 out = orc.forward(imgs, cnt, noise, taps=taps)
+out["canvas_raw"].retain_grad()
 out["loss"].backward()
 m._debug = {}
 m.loss_and_grads(cuda_noise(noise))
 print("loss", m.loss.item(), out["loss"].item())
 vd = m.w["vae_d"]
+gc, oc = m.w["dcanvas"].cpu(), out["canvas_raw"].grad
+print("dcanvas relnorm", relnorm(gc, oc), "canvas relnorm", relnorm(m.w["canvas"], out["canvas_raw"]))
+per_img = ((gc - oc).norm(dim=1) / oc.norm(dim=1))
+print("dcanvas per-image rel err: max", per_img.max().item(), "argmax", per_img.argmax().item(), "n>1e-4:", int((per_img > 1e-4).sum()))
+bad = per_img.argmax().item()
+diff = (gc[bad] - oc[bad]).abs()
+idx = diff.topk(5).indices
+print(" worst pixels", idx.tolist(), "gpu", gc[bad][idx].tolist(), "oracle", oc[bad][idx].tolist(),
+      "canvas gpu", m.w["canvas"][bad].cpu()[idx].tolist(), "canvas oracle", out["canvas_raw"][bad][idx].tolist(), "x", imgs[bad][idx].tolist())
+rec0 = taps["windows"][0]
+e = ((vd["dgen"][0].cpu() - rec0.grad * rec0.detach() * (1 - rec0.detach())).norm(dim=1) / (rec0.grad * rec0.detach() * (1 - rec0.detach())).norm(dim=1))
+print("dgen[0] per-image rel err: max", e.max().item(), "median", e.median().item(), "n>1e-3:", int((e > 1e-3).sum()))
 for t in range(3):
     d = m._debug[t]
     rec = taps["windows"][t]

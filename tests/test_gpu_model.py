@@ -10,7 +10,7 @@ import torch
 import air_b200 as ab
 from oracle import air_oracle as O
 from oracle import c_oracle as C
-from tests.parity_util import covered_fixture, cuda_noise, default_fixture, make_pair, relnorm
+from tests.parity_util import covered_fixture, cuda_noise, default_fixture, make_pair, realistic_fixture, relnorm
 
 pytestmark = pytest.mark.gpu
 
@@ -77,6 +77,30 @@ def test_gradient_parity_covered_fixture():
     for k, g in m.store.named_grads().items():
         worst[k] = relnorm(g, grads[k])
     bad = {k: v for k, v in worst.items() if v > 1e-4}
+    assert not bad, bad
+
+
+def test_backward_schedule_teacher_forced_dcanvas():
+    """Realistic poses (windows smaller than the canvas).  The sign of the +-1e-9 residues on
+    out-of-range canvas pixels decides whether max(canvas, 0) passes their gradient, so the
+    end-to-end gradient is noise-limited there (see test_gradient_adversarial_...).  Feeding the
+    ORACLE's d(loss)/d(canvas) into the CUDA backward removes that one non-smooth op and checks
+    every other backward kernel and the whole schedule at the 1e-4 bar."""
+    B = 64
+    imgs, cnt, params, noise = realistic_fixture(B, seed=11)
+    orc, m = make_pair(imgs, cnt, params, train=True)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in orc.params.items()}
+    orc.params = leaves
+    out = orc.forward(imgs, cnt, noise)
+    out["canvas_raw"].retain_grad()
+    out["loss"].backward()
+    m.run(cuda_noise(noise))
+    assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"])
+    assert 0.2 < m.stop_masks.float().mean().item() < 1.0 and 0.3 < m.rec_scales.mean().item() < 0.8
+    m.w["dcanvas"].copy_(out["canvas_raw"].grad.cuda())
+    m._backward()
+    bad = {k: relnorm(g, leaves[k].grad) for k, g in m.store.named_grads().items()}
+    bad = {k: v for k, v in bad.items() if v > 1e-4}
     assert not bad, bad
 
 
