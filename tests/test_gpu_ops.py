@@ -62,21 +62,27 @@ def test_gemm_strided_views_and_epilogues():
 
 
 def test_softplus_backward_tiny_activations():
-    """softplus' from the stored OUTPUT must stay accurate for very negative inputs (expm1)."""
+    """softplus' is taken from the stored OUTPUT y: sigmoid(x) = 1 - exp(-y) = -expm1(-y), which
+    stays accurate for very negative inputs.  TF's forward log(exp(x) + 1) itself carries up to
+    ~1e-3 relative rounding for x ~ -10 (1 + 4.5e-5 in fp32), and the derivative inherits exactly
+    that; elsewhere it is accurate to a few ulp."""
     x = torch.tensor([[-20.0, -14.0, -10.0, -3.0, 0.0, 5.0, 14.5, 30.0]])
     post = O.tf_softplus(x)
     dX = torch.empty(1, 8, device=DEV)
     ops.gemm(torch.ones(1, 1, device=DEV), torch.ones(8, 1, device=DEV), dX, tB=True, aux=post.to(DEV),
              epi=K.EPI_MUL_DSOFTPLUS)
-    np.testing.assert_allclose(dX.cpu().numpy(), torch.sigmoid(x.double()).numpy(), rtol=3e-6)
+    got, want = dX.cpu().numpy()[0], torch.sigmoid(x.double()).numpy()[0]
+    np.testing.assert_allclose(got[[0, 1, 4, 5, 6, 7]], want[[0, 1, 4, 5, 6, 7]], rtol=3e-6)
+    np.testing.assert_allclose(got[[2, 3]], want[[2, 3]], rtol=2e-3)
+    np.testing.assert_allclose(got, -np.expm1(-post.double().numpy()[0]), rtol=3e-6)   # exact w.r.t. the stored y
 
 
 def test_gemm_errors():
     a = torch.zeros(4, 4, device=DEV)
     with pytest.raises(ab.AirError):
         ops.gemm(a, torch.zeros(5, 4, device=DEV), torch.zeros(4, 4, device=DEV))
-    with pytest.raises(ab.AirError, match="tcgen05|TF32|UNSUPPORTED|not built|code -4|shape"):
-        ops.gemm(a, a, torch.zeros(4, 4, device=DEV), epi=K.EPI_MUL_DRELU)  # needs aux
+    with pytest.raises(ab.AirError, match="needs aux"):
+        ops.gemm(a, a, torch.zeros(4, 4, device=DEV), epi=K.EPI_MUL_DRELU)
 
 
 def test_lstm_pointwise_fwd_bwd():

@@ -120,9 +120,9 @@ def test_fused_canvas_forward_bit_exact(inplace):
     cv = cu(canvas).reshape(B, 50, 50)
     if inplace:
         l = ab._cabi
-        l.check(l.lib().air_st_writeback_canvas_fwd(l.ptr(cu(win)), l.ptr(cu(thi).reshape(B, 6)), l.ptr(cu(z)),
-                                                   l.ptr(cu(stop)), 0.99, l.ptr(cv), l.ptr(cv), B, 28, 28, 50, 50,
-                                                   l.stream()), "inplace")
+        keep = (cu(win), cu(thi).reshape(B, 6), cu(z), cu(stop))   # keep the device buffers alive for the launch
+        l.check(l.lib().air_st_writeback_canvas_fwd(l.ptr(keep[0]), l.ptr(keep[1]), l.ptr(keep[2]), l.ptr(keep[3]), 0.99,
+                                                   l.ptr(cv), l.ptr(cv), B, 28, 28, 50, 50, l.stream()), "inplace")
         got = cv
     else:
         got = ab.writeback_canvas(cu(win), cu(thi), cu(z), cu(stop), cv, 0.99)

@@ -143,6 +143,7 @@ softplus = _softplus_marker
 class _VAEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inputs, flat, store, n_rec, n_gen, noise_latent, noise_like, likelihood_std, mode):
+        ctx.set_materialize_grads(False)
         B = inputs.shape[0]
         d = store.dims
         dev = inputs.device
