@@ -527,6 +527,7 @@ class AIROracle:
             "windows_in": torch.stack(ta["windows_in"]).permute(1, 0, 2),
             "thetas": torch.stack(ta["thetas"]).permute(1, 0, 2, 3),
             "canvas_raw": running_recon,
+            "running_loss": running_loss,
             "executed_steps": executed_steps,
         }
         reconstruction = torch.clamp(running_recon, 0.0, 1.0)  # max(min(r,1),0), same tie rules (:582)

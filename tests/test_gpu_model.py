@@ -80,27 +80,28 @@ def test_gradient_parity_covered_fixture():
     assert not bad, bad
 
 
-def test_backward_schedule_teacher_forced_dcanvas():
-    """Realistic poses (windows smaller than the canvas).  The sign of the +-1e-9 residues on
-    out-of-range canvas pixels decides whether max(canvas, 0) passes their gradient, so the
-    end-to-end gradient is noise-limited there (see test_gradient_adversarial_...).  Feeding the
-    ORACLE's d(loss)/d(canvas) into the CUDA backward removes that one non-smooth op and checks
-    every other backward kernel and the whole schedule at the 1e-4 bar."""
+def test_backward_schedule_realistic_poses_smooth_canvas_gradient():
+    """Realistic poses (windows smaller than the canvas, some steps stopped).  With the BCE loss the
+    canvas gradient has ~1e7 spikes on uncovered lit pixels (x / (0 + 1e-9)) that multiply the exactly
+    cancelling out-of-range bilinear weights, so the reference's own gradient is rounding noise there
+    (SURVEY hard part 2; see test_gradient_adversarial_fixture_vs_fp64_truth).  To check every backward
+    kernel and the whole schedule at the 1e-4 bar on such poses, replace the BCE by a smooth surrogate:
+    loss' = mean(running_loss) + sum(canvas * G) with a fixed random G, i.e. d(loss')/d(canvas) = G."""
     B = 64
     imgs, cnt, params, noise = realistic_fixture(B, seed=11)
     orc, m = make_pair(imgs, cnt, params, train=True)
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in orc.params.items()}
     orc.params = leaves
     out = orc.forward(imgs, cnt, noise)
-    out["canvas_raw"].retain_grad()
-    out["loss"].backward()
+    G = torch.randn(B, 2500, generator=torch.Generator().manual_seed(5)) / B
+    (out["running_loss"].mean() + (out["canvas_raw"] * G).sum()).backward()
     m.run(cuda_noise(noise))
     assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"])
     assert 0.2 < m.stop_masks.float().mean().item() < 1.0 and 0.3 < m.rec_scales.mean().item() < 0.8
-    m.w["dcanvas"].copy_(out["canvas_raw"].grad.cuda())
+    m.w["dcanvas"].copy_(G.cuda())
     m._backward()
-    bad = {k: relnorm(g, leaves[k].grad) for k, g in m.store.named_grads().items()}
-    bad = {k: v for k, v in bad.items() if v > 1e-4}
+    err = {k: relnorm(g, leaves[k].grad) for k, g in m.store.named_grads().items()}
+    bad = {k: v for k, v in err.items() if v > 1e-4}
     assert not bad, bad
 
 
