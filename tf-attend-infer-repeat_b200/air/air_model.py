@@ -30,7 +30,7 @@ import math
 import torch
 
 from .. import _cabi as C
-from .. import ops
+from .. import dp, ops
 from .params import ParamStore
 from .vae import (VAEWeights, _flat2, alloc_vae_scratch, dense_dw, vae_backward_dx, vae_forward, vae_weight_grads)
 
@@ -105,10 +105,8 @@ class AIRModel:
                              stopping_threshold, 1 if train else 0)
 
         # ---- data parallelism: one process per GPU, gradients all-reduced over NCCL
-        self.world = 1
         self.pg = process_group
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world = torch.distributed.get_world_size(process_group)
+        self.world = dp.world_size(process_group)
 
         self._alloc()
         if self.gemm == C.GEMM_MODES["tf32"]:
@@ -300,8 +298,7 @@ class AIRModel:
                       1.0, self.w["adam_ws"])
 
     def _allreduce(self):
-        if self.world > 1:
-            torch.distributed.all_reduce(self.store.grad, group=self.pg)  # SUM; dscale already has 1/world
+        dp.allreduce_flat(self.store.grad, self.pg)  # SUM; the per-item loss weight already carries 1/world
 
     # ------------------------------------------------------------------------------------------
     # public API
