@@ -72,7 +72,7 @@ __device__ __forceinline__ float bilerp(const float *im, const Ent &ce, const En
 // =========================================================================================
 constexpr int kFwdThreads = 256;
 
-template <int H_, int W_, int OH_, int OW_, int G, bool CANVAS>
+template <int H_, int W_, int OH_, int OW_, int G, bool CANVAS, bool VEC = false>
 __global__ void __launch_bounds__(kFwdThreads)
     st_fwd_staged(const float *__restrict__ U, const float *__restrict__ theta, float *out,
                   const float *__restrict__ zp, const float *__restrict__ stop, float thr, const float *canvas_in,
@@ -129,6 +129,43 @@ __global__ void __launch_bounds__(kFwdThreads)
   __syncthreads();
   mbar_wait(&bar, 0);
 
+  if (CANVAS && VEC) {
+    // 4 consecutive canvas pixels per thread: one 128-bit load and store of the canvas, tables re-read per pixel
+    const int QPI = OHW >> 2;  // OHW % 4 == 0 on this path
+    for (int qd = tid; qd < n_img * QPI; qd += kFwdThreads) {
+      const int i = qd / QPI, q4 = (qd - i * QPI) << 2;
+      int r = q4 / OW, c = q4 - r * OW;
+      const int64_t o = (g0 + i) * OHW + q4;
+      const float *th = sTh + i * 8;
+      const bool live = th[7] != 0.0f, sepi = th[6] != 0.0f;
+      const float4 cin = *reinterpret_cast<const float4 *>(canvas_in + o);
+      const float cv[4] = {cin.x, cin.y, cin.z, cin.w};
+      float res[4];
+      const float zz = live ? __ldg(zp + g0 + i) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float add = 0.0f;
+        if (live) {
+          float v;
+          if (sepi) {
+            const Ent ce = sCol[i * OW + c], re = sRow[i * OH + r];
+            // clipped on both axes: the four products cancel to exactly +0 (same bits as the full formula)
+            v = (ce.i0 == ce.i1 && re.i0 == re.i1) ? 0.0f : bilerp(sU + i * HW, ce, re);
+          } else {
+            Ent ce, re;
+            float xt, yt;
+            gen_ents(th, r, c, OH, OW, H, W, ce, re, xt, yt);
+            v = bilerp(sU + i * HW, ce, re);
+          }
+          add = mul_rn(zz, v);
+        }
+        res[j] = add_rn(cv[j], add);
+        if (++c == OW) { c = 0; ++r; }
+      }
+      *reinterpret_cast<float4 *>(out + o) = make_float4(res[0], res[1], res[2], res[3]);
+    }
+    return;
+  }
   const int total = n_img * OHW;
   for (int p = tid; p < total; p += kFwdThreads) {
     const int i = p / OHW, q = p - i * OHW;
@@ -190,26 +227,52 @@ __global__ void __launch_bounds__(256)
 }
 
 // =========================================================================================
-// Backward, staged (C == 1), one CTA per image.
+// Backward, staged (C == 1), one 128-thread CTA per image (up to 16 CTAs / SM).
 //   upstream g[p] = FUSED ? (live ? dcanvas[p] : 0) * z : dout[p]
 //   dtheta[6]   : always
 //   dU [H,W]    : if non-null; separable gather form (deterministic) for axis-aligned theta,
 //                 shared-memory atomics otherwise
 //   dz          : FUSED only, sum_p (live ? dcanvas[p] : 0) * sample[p]
-// Gradient formulas are TF autodiff of transformer.py:108-116 (no gradient through
-// floor / clip / cast); only the summation order differs from the oracle.
+// Gradient formulas are TF autodiff of transformer.py:108-116 (no gradient through floor / clip /
+// cast).  For axis-aligned theta only the in-range rectangle of output pixels is visited: a pixel
+// whose row or column is clipped has both corners on the same source pixel with weights (v - i) and
+// (i - v), so its contributions to dU, dtheta and dz are exactly zero in exact arithmetic (the
+// reference accumulates their fp32 cancellation noise instead); only the summation order and that
+// noise differ from the oracle.
 // =========================================================================================
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 128;
+constexpr int kBwdWarps = kBwdThreads / 32;
 
-__device__ __forceinline__ float block_sum(float v, float *red /*[8]*/) {
+// sums NV values across the CTA in one pass: warp shuffles, one smem exchange, fixed order
+template <int NV>
+__device__ __forceinline__ void block_sum_many(float (&v)[NV], float (*red)[8] /*[kBwdWarps][8]*/) {
+  static_assert(NV <= 8, "red row holds 8 values");
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[w][k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kBwdWarps; ++i) t += red[i][k];
+    v[k] = t;
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float *red /*[kBwdWarps]*/) {  // generic kernel helper
   v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();  // protect red from the previous use
+  __syncthreads();
   if (l == 0) red[w] = v;
   __syncthreads();
   float t = 0.0f;
 #pragma unroll
-  for (int k = 0; k < kBwdThreads / 32; ++k) t += red[k];
+  for (int k = 0; k < kBwdWarps; ++k) t += red[k];
   return t;
 }
 
@@ -228,8 +291,9 @@ __global__ void __launch_bounds__(kBwdThreads)
   int2 *sRange = reinterpret_cast<int2 *>(sRow + OH);           // [W + H] contributor ranges
   float *sT = reinterpret_cast<float *>(sRange + ((W + H + 1) & ~1));  // [OH][W] pass-1 buffer / dU atomics tile
   __shared__ uint64_t bar;
-  __shared__ float red[kBwdThreads / 32];
+  __shared__ float red[kBwdWarps][8];
   __shared__ float sTh[8];
+  __shared__ int sRect[4];  // c_lo, c_hi, r_lo, r_hi (inclusive) of the in-range rectangle
 
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
@@ -269,15 +333,37 @@ __global__ void __launch_bounds__(kBwdThreads)
   }
   __syncthreads();
   const bool sep = sTh[6] != 0.0f;
+  // ---- in-range rectangle (first / last output column and row whose two corners differ)
+  if (tid < 64) {  // warp 0: columns, warp 1: rows
+    const int w = tid >> 5, l = tid & 31;
+    const int n = w == 0 ? OW : OH;
+    const Ent *tab = w == 0 ? sCol : sRow;
+    int lo = 1 << 30, hi = -1;
+    for (int k = l; k < n; k += 32) {
+      if (!sep || tab[k].i0 != tab[k].i1) { lo = min(lo, k); hi = max(hi, k); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (l == 0) { sRect[2 * w] = lo; sRect[2 * w + 1] = hi; }
+  }
   if (dU && !sep)
-    for (int k = tid; k < HW; k += kBwdThreads) sT[k] = 0.0f;  // atomics tile (needs HW <= OH*W, checked on host)
+    for (int k = tid; k < HW; k += kBwdThreads) sT[k] = 0.0f;  // atomics tile (HW <= max(OH*W, HW) floats)
+  __syncthreads();
+  const int c_lo = sRect[0], r_lo = sRect[2];
+  const int nc = max(sRect[1] - c_lo + 1, 0), nr = max(sRect[3] - r_lo + 1, 0);
   mbar_wait(&bar, 0);
-  if (dU && !sep) __syncthreads();
 
   const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, az = 0.f;
-  for (int q = tid; q < OHW; q += kBwdThreads) {
-    const int r = q / OW, c = q - r * OW;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int npix = nr * nc;
+  const float inv_nc = nc > 0 ? 1.0f / static_cast<float>(nc) : 0.0f;
+  for (int idx = tid; idx < npix; idx += kBwdThreads) {
+    const int ro = static_cast<int>((static_cast<float>(idx) + 0.5f) * inv_nc);  // exact: idx < 2^20, nc small
+    const int r = r_lo + ro, c = c_lo + (idx - ro * nc);
+    const int q = r * OW + c;
     Ent ce, re;
     float xt, yt;
     if (sep) {
@@ -295,19 +381,19 @@ __global__ void __launch_bounds__(kBwdThreads)
       const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
       const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
       const float v = add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
-      az += g * v;  // d(z * v)/dz
-      g *= zval;    // d(z * v)/dv
+      acc[6] += g * v;  // d(z * v)/dz
+      g *= zval;        // d(z * v)/dv
     }
     const float dwa = g * Ia, dwb = g * Ib, dwc = g * Ic, dwd = g * Id;
     const float dx = ((-(dwa * re.w1) - dwb * re.w0) + dwc * re.w1) + dwd * re.w0;
     const float dy = ((-(dwa * ce.w1) + dwb * ce.w1) - dwc * ce.w0) + dwd * ce.w0;
     const float dxs = dx * 0.5f * wf, dys = dy * 0.5f * hf;
-    a0 += dxs * xt;
-    a1 += dxs * yt;
-    a2 += dxs;
-    a3 += dys * xt;
-    a4 += dys * yt;
-    a5 += dys;
+    acc[0] += dxs * xt;
+    acc[1] += dxs * yt;
+    acc[2] += dxs;
+    acc[3] += dys * xt;
+    acc[4] += dys * yt;
+    acc[5] += dys;
     if (dU && !sep) {
       atomicAdd(&sT[re.i0 + ce.i0], mul_rn(ce.w1, re.w1) * g);
       atomicAdd(&sT[re.i1 + ce.i0], mul_rn(ce.w1, re.w0) * g);
@@ -315,17 +401,12 @@ __global__ void __launch_bounds__(kBwdThreads)
       atomicAdd(&sT[re.i1 + ce.i1], mul_rn(ce.w0, re.w0) * g);
     }
   }
-  a0 = block_sum(a0, red);
-  a1 = block_sum(a1, red);
-  a2 = block_sum(a2, red);
-  a3 = block_sum(a3, red);
-  a4 = block_sum(a4, red);
-  a5 = block_sum(a5, red);
-  if (FUSED) az = block_sum(az, red);
+  block_sum_many<7>(acc, red);
   if (tid == 0) {
     float *d = dtheta + b * 6;
-    d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3; d[4] = a4; d[5] = a5;
-    if (FUSED && dz) dz[b] = az;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = acc[k];
+    if (FUSED && dz) dz[b] = acc[6];
   }
   if (!dU) return;
 
@@ -335,35 +416,35 @@ __global__ void __launch_bounds__(kBwdThreads)
     return;
   }
 
-  // ---- deterministic separable dU:  dU = z * Wy^T * g * Wx,
-  //      Wx[c][j] = [x0(c)==j]*wx1(c) + [x1(c)==j]*wx0(c)  (clipped columns give exactly 0).
-  //      theta is axis-aligned, so the contributors of source column j (row i) are one
-  //      contiguous range of output columns (rows): gather form, fixed order, no atomics.
-  __syncthreads();
+  // ---- deterministic separable dU:  dU = z * Wy^T * g * Wx over the in-range rectangle,
+  //      Wx[c][j] = [x0(c)==j]*wx1(c) + [x1(c)==j]*wx0(c).  theta is axis-aligned, so the
+  //      contributors of source column j (row i) are one contiguous range of output columns
+  //      (rows): gather form, fixed order, no atomics.
   for (int j = tid; j < W + H; j += kBwdThreads) {
     int lo = 1 << 30, hi = -1;
     if (j < W) {
-      for (int c = 0; c < OW; ++c)
+      for (int c = c_lo; c < c_lo + nc; ++c)
         if (sCol[c].i0 == j || sCol[c].i1 == j) { lo = min(lo, c); hi = max(hi, c); }
     } else {
       const int iw = (j - W) * W;
-      for (int r = 0; r < OH; ++r)
+      for (int r = r_lo; r < r_lo + nr; ++r)
         if (sRow[r].i0 == iw || sRow[r].i1 == iw) { lo = min(lo, r); hi = max(hi, r); }
     }
     sRange[j] = make_int2(lo, hi);
   }
   __syncthreads();
-  // pass 1: T[r][j] = sum_c g[r][c] * Wx[c][j]
-  for (int e = tid; e < OH * W; e += kBwdThreads) {
-    const int r = e / W, j = e - r * W;
+  // pass 1: T[r][j] = sum_c g[r][c] * Wx[c][j], in-range rows only
+  for (int e = tid; e < nr * W; e += kBwdThreads) {
+    const int ro = e / W, j = e - ro * W;
+    const int r = r_lo + ro;
     const int2 rg = sRange[j];
-    float acc = 0.0f;
+    float a = 0.0f;
     for (int c = rg.x; c <= rg.y; ++c) {
       const Ent ce = sCol[c];
       const float coef = (ce.i0 == j ? ce.w1 : 0.0f) + (ce.i1 == j ? ce.w0 : 0.0f);
-      acc += coef * sG[r * OW + c];
+      a += coef * sG[r * OW + c];
     }
-    sT[e] = acc;
+    sT[r * W + j] = a;
   }
   __syncthreads();
   // pass 2: dU[i][j] = z * sum_r Wy[r][i] * T[r][j]
@@ -371,13 +452,13 @@ __global__ void __launch_bounds__(kBwdThreads)
     const int i = e / W, j = e - i * W;
     const int iw = i * W;
     const int2 rg = sRange[W + i];
-    float acc = 0.0f;
+    float a = 0.0f;
     for (int r = rg.x; r <= rg.y; ++r) {
       const Ent re = sRow[r];
       const float coef = (re.i0 == iw ? re.w1 : 0.0f) + (re.i1 == iw ? re.w0 : 0.0f);
-      acc += coef * sT[r * W + j];
+      a += coef * sT[r * W + j];
     }
-    dU[b * HW + e] = FUSED ? acc * zval : acc;
+    dU[b * HW + e] = FUSED ? a * zval : a;
   }
 }
 
@@ -387,7 +468,7 @@ __global__ void __launch_bounds__(kBwdThreads)
 __global__ void __launch_bounds__(kBwdThreads)
     st_bwd_generic(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dout,
                    float *dU, float *__restrict__ dtheta, int H, int W, int C, int OH, int OW) {
-  __shared__ float red[kBwdThreads / 32];
+  __shared__ float red[kBwdWarps];
   const int64_t b = blockIdx.x;
   float th[6];
 #pragma unroll
@@ -444,11 +525,11 @@ static size_t fwd_smem_bytes(int H, int W, int OH, int OW) {
   return static_cast<size_t>(G) * H * W * 4 + static_cast<size_t>(G) * (OW + OH) * sizeof(Ent) + G * 8 * 4;
 }
 
-template <int H_, int W_, int OH_, int OW_, int G, bool CANVAS>
+template <int H_, int W_, int OH_, int OW_, int G, bool CANVAS, bool VEC = false>
 static int launch_fwd_staged(const float *U, const float *theta, float *out, const float *z, const float *stop,
                              float thr, const float *canvas_in, int64_t B, int H, int W, int OH, int OW,
                              cudaStream_t s) {
-  auto kern = st_fwd_staged<H_, W_, OH_, OW_, G, CANVAS>;
+  auto kern = st_fwd_staged<H_, W_, OH_, OW_, G, CANVAS, VEC>;
   const size_t smem = fwd_smem_bytes<G>(H, W, OH, OW);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -475,8 +556,11 @@ static int st_forward_impl(const float *U, const float *theta, float *out, const
   AIR_REQUIRE(U && theta && out, AIR_ERR_NULL, "st_forward: null pointer");
   if (staged_ok(U, H, W, C, B)) {
     if (canvas) {
-      if (H == 28 && W == 28 && OH == 50 && OW == 50)
+      if (H == 28 && W == 28 && OH == 50 && OW == 50) {
+        if (aligned16(canvas_in) && aligned16(out))
+          return launch_fwd_staged<28, 28, 50, 50, 4, true, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
         return launch_fwd_staged<28, 28, 50, 50, 4, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+      }
       if (fwd_smem_bytes<2>(H, W, OH, OW) <= kMaxStagedSmem)
         return launch_fwd_staged<0, 0, 0, 0, 2, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
     } else {
