@@ -130,39 +130,52 @@ __global__ void __launch_bounds__(kFwdThreads)
   mbar_wait(&bar, 0);
 
   if (CANVAS && VEC) {
-    // 4 consecutive canvas pixels per thread: one 128-bit load and store of the canvas, tables re-read per pixel
-    const int QPI = OHW >> 2;  // OHW % 4 == 0 on this path
-    for (int qd = tid; qd < n_img * QPI; qd += kFwdThreads) {
-      const int i = qd / QPI, q4 = (qd - i * QPI) << 2;
-      int r = q4 / OW, c = q4 - r * OW;
-      const int64_t o = (g0 + i) * OHW + q4;
+    // Each warp owns chunks of 128 consecutive canvas pixels of one image.  Lane L first issues the 128-bit
+    // load of pixels 4L..4L+3, then computes the samples of pixels L, L+32, L+64, L+96 (consecutive lanes ->
+    // consecutive table entries: conflict-free shared-memory reads), stages z*v in a warp-private buffer and
+    // reads its own four back for the fused add and the 128-bit store.
+    __shared__ __align__(16) float sStage[kFwdThreads / 32][128];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int CPI = (OHW + 127) >> 7;  // chunks per image (the last one may be partial; OHW % 4 == 0)
+    for (int ch = warp; ch < n_img * CPI; ch += kFwdThreads / 32) {
+      const int i = ch / CPI, p0 = (ch - i * CPI) << 7;
       const float *th = sTh + i * 8;
       const bool live = th[7] != 0.0f, sepi = th[6] != 0.0f;
-      const float4 cin = *reinterpret_cast<const float4 *>(canvas_in + o);
-      const float cv[4] = {cin.x, cin.y, cin.z, cin.w};
-      float res[4];
-      const float zz = live ? __ldg(zp + g0 + i) : 0.0f;
+      const int64_t o = (g0 + i) * OHW + p0 + 4 * lane;
+      const bool mine = p0 + 4 * lane < OHW;
+      float4 cin = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mine) cin = *reinterpret_cast<const float4 *>(canvas_in + o);
+      if (live) {
+        const float zz = __ldg(zp + g0 + i);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float add = 0.0f;
-        if (live) {
-          float v;
-          if (sepi) {
-            const Ent ce = sCol[i * OW + c], re = sRow[i * OH + r];
-            // clipped on both axes: the four products cancel to exactly +0 (same bits as the full formula)
-            v = (ce.i0 == ce.i1 && re.i0 == re.i1) ? 0.0f : bilerp(sU + i * HW, ce, re);
-          } else {
-            Ent ce, re;
-            float xt, yt;
-            gen_ents(th, r, c, OH, OW, H, W, ce, re, xt, yt);
-            v = bilerp(sU + i * HW, ce, re);
+        for (int j = 0; j < 4; ++j) {
+          const int q = p0 + 32 * j + lane;
+          float v = 0.0f;
+          if (q < OHW) {
+            const int r = q / OW, c = q - r * OW;
+            if (sepi) {
+              const Ent ce = sCol[i * OW + c], re = sRow[i * OH + r];
+              // clipped on both axes: the four products cancel to exactly +0 (same bits as the full formula)
+              v = (ce.i0 == ce.i1 && re.i0 == re.i1) ? 0.0f : bilerp(sU + i * HW, ce, re);
+            } else {
+              Ent ce, re;
+              float xt, yt;
+              gen_ents(th, r, c, OH, OW, H, W, ce, re, xt, yt);
+              v = bilerp(sU + i * HW, ce, re);
+            }
           }
-          add = mul_rn(zz, v);
+          sStage[warp][32 * j + lane] = mul_rn(zz, v);
         }
-        res[j] = add_rn(cv[j], add);
-        if (++c == OW) { c = 0; ++r; }
+        __syncwarp();
+        const float4 add = *reinterpret_cast<const float4 *>(&sStage[warp][4 * lane]);
+        __syncwarp();
+        cin.x = add_rn(cin.x, add.x); cin.y = add_rn(cin.y, add.y);
+        cin.z = add_rn(cin.z, add.z); cin.w = add_rn(cin.w, add.w);
+      } else {
+        cin.x = add_rn(cin.x, 0.0f); cin.y = add_rn(cin.y, 0.0f);
+        cin.z = add_rn(cin.z, 0.0f); cin.w = add_rn(cin.w, 0.0f);
       }
-      *reinterpret_cast<float4 *>(out + o) = make_float4(res[0], res[1], res[2], res[3]);
+      if (mine) *reinterpret_cast<float4 *>(out + o) = cin;
     }
     return;
   }
@@ -288,8 +301,9 @@ __global__ void __launch_bounds__(kBwdThreads)
   float *sG = sU + ((HW + 3) & ~3);                 // [OHW]  upstream gradient tile
   Ent *sCol = reinterpret_cast<Ent *>(sG + ((OHW + 3) & ~3));  // [OW]
   Ent *sRow = sCol + OW;                                         // [OH]
-  int2 *sRange = reinterpret_cast<int2 *>(sRow + OH);           // [W + H] contributor ranges
-  float *sT = reinterpret_cast<float *>(sRange + ((W + H + 1) & ~1));  // [OH][W] pass-1 buffer / dU atomics tile
+  int2 *sRun = reinterpret_cast<int2 *>(sRow + OH);             // [W + H] runs of output cols/rows with i0 == j
+  float *sGrid = reinterpret_cast<float *>(sRun + ((W + H + 1) & ~1));  // [OW + OH] normalised grid x_t | y_t
+  float *sT = sGrid + ((OW + OH + 3) & ~3);                     // [OH][W] pass-1 buffer / dU atomics tile
   __shared__ uint64_t bar;
   __shared__ float red[kBwdWarps][8];
   __shared__ float sTh[8];
@@ -323,14 +337,19 @@ __global__ void __launch_bounds__(kBwdThreads)
     bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
     bulk_g2s(sG, dout + b * OHW, OHW * 4u, &bar);
   }
+  // ---- tables (overlap the bulk copies): clipped corners + 1-D weights, grid coordinates, empty runs
   if (tid < 6) sTh[tid] = __ldg(th_g + tid);
   if (tid == 6) sTh[6] = (__ldg(th_g + 1) == 0.0f && __ldg(th_g + 3) == 0.0f) ? 1.0f : 0.0f;
   for (int k = tid; k < OW + OH; k += kBwdThreads) {
-    if (k < OW)
+    if (k < OW) {
       sCol[k] = sep_ent(__ldg(th_g + 0), __ldg(th_g + 2), k, OW, W, 1);
-    else
+      sGrid[k] = linspace_pm1(k, OW);
+    } else {
       sRow[k - OW] = sep_ent(__ldg(th_g + 4), __ldg(th_g + 5), k - OW, OH, H, W);
+      sGrid[k] = linspace_pm1(k - OW, OH);
+    }
   }
+  for (int k = tid; k < W + H; k += kBwdThreads) sRun[k] = make_int2(1 << 30, -1);
   __syncthreads();
   const bool sep = sTh[6] != 0.0f;
   // ---- in-range rectangle (first / last output column and row whose two corners differ)
@@ -354,25 +373,41 @@ __global__ void __launch_bounds__(kBwdThreads)
   __syncthreads();
   const int c_lo = sRect[0], r_lo = sRect[2];
   const int nc = max(sRect[1] - c_lo + 1, 0), nr = max(sRect[3] - r_lo + 1, 0);
+  // ---- runs: theta is axis-aligned, so the in-range output columns (rows) whose lower corner is source
+  //      column j (row i) are one contiguous run; its ends are where i0 changes -> O(1) per thread
+  if (dU && sep) {
+    for (int k = tid; k < nc + nr; k += kBwdThreads) {
+      const bool col = k < nc;
+      const int p = col ? c_lo + k : r_lo + (k - nc);
+      const int first = col ? c_lo : r_lo, last = col ? c_lo + nc - 1 : r_lo + nr - 1;
+      const Ent *tab = col ? sCol : sRow;
+      const int i0 = tab[p].i0;
+      if (tab[p].i0 != tab[p].i1) {  // (always true inside the rectangle for monotone maps)
+        const int slot = col ? i0 : W + i0 / W;
+        if (p == first || tab[p - 1].i0 != i0) sRun[slot].x = p;
+        if (p == last || tab[p + 1].i0 != i0) sRun[slot].y = p;
+      }
+    }
+  }
   mbar_wait(&bar, 0);
 
   const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
   float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int npix = nr * nc;
-  const float inv_nc = nc > 0 ? 1.0f / static_cast<float>(nc) : 0.0f;
+  // idx / nc by multiply-high: exact while idx * nc < 2^32 (checked on the host: OH*OW*OW < 2^32)
+  const unsigned magic = nc > 1 ? static_cast<unsigned>((0x100000000ull + nc - 1) / nc) : 0u;
   for (int idx = tid; idx < npix; idx += kBwdThreads) {
-    const int ro = static_cast<int>((static_cast<float>(idx) + 0.5f) * inv_nc);  // exact: idx < 2^20, nc small
+    const int ro = nc > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), magic)) : idx;
     const int r = r_lo + ro, c = c_lo + (idx - ro * nc);
     const int q = r * OW + c;
     Ent ce, re;
-    float xt, yt;
+    const float xt = sGrid[c], yt = sGrid[OW + r];
     if (sep) {
       ce = sCol[c];
       re = sRow[r];
-      xt = linspace_pm1(c, OW);
-      yt = linspace_pm1(r, OH);
     } else {
-      gen_ents(sTh, r, c, OH, OW, H, W, ce, re, xt, yt);
+      float xt2, yt2;
+      gen_ents(sTh, r, c, OH, OW, H, W, ce, re, xt2, yt2);
     }
     const float Ia = sU[re.i0 + ce.i0], Ib = sU[re.i1 + ce.i0];
     const float Ic = sU[re.i0 + ce.i1], Id = sU[re.i1 + ce.i1];
@@ -401,7 +436,7 @@ __global__ void __launch_bounds__(kBwdThreads)
       atomicAdd(&sT[re.i1 + ce.i1], mul_rn(ce.w0, re.w0) * g);
     }
   }
-  block_sum_many<7>(acc, red);
+  block_sum_many<7>(acc, red);  // contains a __syncthreads: the runs written above are visible after it
   if (tid == 0) {
     float *d = dtheta + b * 6;
 #pragma unroll
@@ -416,47 +451,32 @@ __global__ void __launch_bounds__(kBwdThreads)
     return;
   }
 
-  // ---- deterministic separable dU:  dU = z * Wy^T * g * Wx over the in-range rectangle,
-  //      Wx[c][j] = [x0(c)==j]*wx1(c) + [x1(c)==j]*wx0(c).  theta is axis-aligned, so the
-  //      contributors of source column j (row i) are one contiguous range of output columns
-  //      (rows): gather form, fixed order, no atomics.
-  for (int j = tid; j < W + H; j += kBwdThreads) {
-    int lo = 1 << 30, hi = -1;
-    if (j < W) {
-      for (int c = c_lo; c < c_lo + nc; ++c)
-        if (sCol[c].i0 == j || sCol[c].i1 == j) { lo = min(lo, c); hi = max(hi, c); }
-    } else {
-      const int iw = (j - W) * W;
-      for (int r = r_lo; r < r_lo + nr; ++r)
-        if (sRow[r].i0 == iw || sRow[r].i1 == iw) { lo = min(lo, r); hi = max(hi, r); }
-    }
-    sRange[j] = make_int2(lo, hi);
-  }
-  __syncthreads();
-  // pass 1: T[r][j] = sum_c g[r][c] * Wx[c][j], in-range rows only
+  // ---- deterministic separable dU = z * Wy^T * G * Wx over the in-range rectangle (gather form, fixed
+  //      order, no atomics).  An in-range output column c touches source columns i0(c) (weight w1) and
+  //      i0(c)+1 (weight w0), so source column j gathers run(j) with w1 and run(j-1) with w0.
+  // pass 1: T[r][j] = sum_{c in run(j)} w1(c) g[r][c] + sum_{c in run(j-1)} w0(c) g[r][c]
   for (int e = tid; e < nr * W; e += kBwdThreads) {
     const int ro = e / W, j = e - ro * W;
-    const int r = r_lo + ro;
-    const int2 rg = sRange[j];
+    const float *grow = sG + (r_lo + ro) * OW;
     float a = 0.0f;
-    for (int c = rg.x; c <= rg.y; ++c) {
-      const Ent ce = sCol[c];
-      const float coef = (ce.i0 == j ? ce.w1 : 0.0f) + (ce.i1 == j ? ce.w0 : 0.0f);
-      a += coef * sG[r * OW + c];
+    const int2 ra = sRun[j];
+    for (int c = ra.x; c <= ra.y; ++c) a += sCol[c].w1 * grow[c];
+    if (j > 0) {
+      const int2 rb = sRun[j - 1];
+      for (int c = rb.x; c <= rb.y; ++c) a += sCol[c].w0 * grow[c];
     }
-    sT[r * W + j] = a;
+    sT[ro * W + j] = a;
   }
   __syncthreads();
-  // pass 2: dU[i][j] = z * sum_r Wy[r][i] * T[r][j]
+  // pass 2: dU[i][j] = z * (sum_{r in run(i)} w1(r) T[r][j] + sum_{r in run(i-1)} w0(r) T[r][j])
   for (int e = tid; e < HW; e += kBwdThreads) {
     const int i = e / W, j = e - i * W;
-    const int iw = i * W;
-    const int2 rg = sRange[W + i];
     float a = 0.0f;
-    for (int r = rg.x; r <= rg.y; ++r) {
-      const Ent re = sRow[r];
-      const float coef = (re.i0 == iw ? re.w1 : 0.0f) + (re.i1 == iw ? re.w0 : 0.0f);
-      a += coef * sT[r * W + j];
+    const int2 ra = sRun[W + i];
+    for (int r = ra.x; r <= ra.y; ++r) a += sRow[r].w1 * sT[(r - r_lo) * W + j];
+    if (i > 0) {
+      const int2 rb = sRun[W + i - 1];
+      for (int r = rb.x; r <= rb.y; ++r) a += sRow[r].w0 * sT[(r - r_lo) * W + j];
     }
     dU[b * HW + e] = FUSED ? a * zval : a;
   }
@@ -584,7 +604,8 @@ static int st_forward_impl(const float *U, const float *theta, float *out, const
 static size_t bwd_smem_bytes(int H, int W, int OH, int OW) {
   const size_t hw = (static_cast<size_t>(H) * W + 3) & ~size_t(3), ohw = (static_cast<size_t>(OH) * OW + 3) & ~size_t(3);
   const size_t t = std::max(static_cast<size_t>(OH) * W, static_cast<size_t>(H) * W);
-  return (hw + ohw) * 4 + static_cast<size_t>(OW + OH) * sizeof(Ent) + static_cast<size_t>((W + H + 1) & ~1) * 8 + t * 4;
+  return (hw + ohw) * 4 + static_cast<size_t>(OW + OH) * sizeof(Ent) + static_cast<size_t>((W + H + 1) & ~1) * 8 +
+         static_cast<size_t>((OW + OH + 3) & ~3) * 4 + t * 4;
 }
 
 template <int H_, int W_, int OH_, int OW_, bool FUSED>
@@ -612,6 +633,7 @@ static int st_backward_impl(const float *U, const float *theta, const float *dou
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(U && theta && dout && dtheta, AIR_ERR_NULL, "st_backward: null pointer");
   const bool staged = staged_ok(U, H, W, C, B) && ((OH * OW) % 4 == 0) && aligned16(dout) &&
+                      static_cast<int64_t>(OH) * OW * OW < (int64_t(1) << 32) &&
                       bwd_smem_bytes(H, W, OH, OW) <= static_cast<size_t>(kMaxStagedSmem);
   if (staged) {
     if (fused) {
