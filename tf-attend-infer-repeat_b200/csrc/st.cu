@@ -256,25 +256,30 @@ __global__ void __launch_bounds__(256)
 constexpr int kBwdThreads = 128;
 constexpr int kBwdWarps = kBwdThreads / 32;
 
-// sums NV values across the CTA in one pass: warp shuffles, one smem exchange, fixed order
+// sums NV per-thread values across the CTA through shared memory (fixed order, deterministic):
+// scratch[k][tid] <- v[k]; thread (k, part) adds 32 of them; 4 parts are combined by two shuffles.
+// (A pure shuffle tree costs NV*5 SHFL per warp and was 20% of the crop-backward's instructions.)
 template <int NV>
-__device__ __forceinline__ void block_sum_many(float (&v)[NV], float (*red)[8] /*[kBwdWarps][8]*/) {
-  static_assert(NV <= 8, "red row holds 8 values");
+__device__ __forceinline__ void block_sum_many(float (&v)[NV], float *scratch /*[NV][kBwdThreads]*/) {
+  static_assert(NV * kBwdWarps <= 32, "one warp finishes the reduction");
+  const int tid = threadIdx.x;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) red[w][k] = v[k];
+  for (int k = 0; k < NV; ++k) scratch[k * kBwdThreads + tid] = v[k];
+  __syncthreads();
+  if (tid < 32) {
+    float t = 0.0f;
+    if (tid < NV * kBwdWarps) {
+      const float *src = scratch + (tid / kBwdWarps) * kBwdThreads + (tid % kBwdWarps) * 32;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) t += src[i];
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    if (tid < NV * kBwdWarps && (tid % kBwdWarps) == 0) scratch[tid / kBwdWarps] = t;  // after all reads of this warp
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float t = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kBwdWarps; ++i) t += red[i][k];
-    v[k] = t;
-  }
+  for (int k = 0; k < NV; ++k) v[k] = scratch[k];
 }
 
 __device__ __forceinline__ float block_sum(float v, float *red /*[kBwdWarps]*/) {  // generic kernel helper
@@ -301,13 +306,12 @@ __global__ void __launch_bounds__(kBwdThreads)
   float *sG = sU + ((HW + 3) & ~3);                 // [OHW]  upstream gradient tile
   Ent *sCol = reinterpret_cast<Ent *>(sG + ((OHW + 3) & ~3));  // [OW]
   Ent *sRow = sCol + OW;                                         // [OH]
-  int2 *sRun = reinterpret_cast<int2 *>(sRow + OH);             // [W + H] runs of output cols/rows with i0 == j
-  float *sGrid = reinterpret_cast<float *>(sRun + ((W + H + 1) & ~1));  // [OW + OH] normalised grid x_t | y_t
-  float *sT = sGrid + ((OW + OH + 3) & ~3);                     // [OH][W] pass-1 buffer / dU atomics tile
+  float *sGrid = reinterpret_cast<float *>(sRow + OH);          // [OW + OH] normalised grid x_t | y_t
+  float *sT = sGrid + ((OW + OH + 3) & ~3);  // [W][OH|1] pass-1 buffer | [HW] dU atomics tile | reduction scratch
+  float *sScr = sT + ((HW + 3) & ~3);          // reduction scratch of the atomics path (behind its tile)
   __shared__ uint64_t bar;
-  __shared__ float red[kBwdWarps][8];
   __shared__ float sTh[8];
-  __shared__ int sRect[4];  // c_lo, c_hi, r_lo, r_hi (inclusive) of the in-range rectangle
+  __shared__ int sRect[6];  // c_lo, c_hi, r_lo, r_hi (inclusive) of the in-range rectangle; [4] = 2^32/nc magic
 
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
@@ -349,7 +353,6 @@ __global__ void __launch_bounds__(kBwdThreads)
       sGrid[k] = linspace_pm1(k - OW, OH);
     }
   }
-  for (int k = tid; k < W + H; k += kBwdThreads) sRun[k] = make_int2(1 << 30, -1);
   __syncthreads();
   const bool sep = sTh[6] != 0.0f;
   // ---- in-range rectangle (first / last output column and row whose two corners differ)
@@ -366,28 +369,21 @@ __global__ void __launch_bounds__(kBwdThreads)
       lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (l == 0) { sRect[2 * w] = lo; sRect[2 * w + 1] = hi; }
+    if (l == 0) {
+      sRect[2 * w] = lo;
+      sRect[2 * w + 1] = hi;
+      if (w == 0) {  // idx / nc by multiply-high (one 64-bit division per CTA instead of one per thread)
+        const int ncols = max(hi - lo + 1, 1);
+        sRect[4] = static_cast<int>(static_cast<unsigned>((0x100000000ull + ncols - 1) / ncols));
+      }
+    }
   }
-  if (dU && !sep)
-    for (int k = tid; k < HW; k += kBwdThreads) sT[k] = 0.0f;  // atomics tile (HW <= max(OH*W, HW) floats)
   __syncthreads();
   const int c_lo = sRect[0], r_lo = sRect[2];
   const int nc = max(sRect[1] - c_lo + 1, 0), nr = max(sRect[3] - r_lo + 1, 0);
-  // ---- runs: theta is axis-aligned, so the in-range output columns (rows) whose lower corner is source
-  //      column j (row i) are one contiguous run; its ends are where i0 changes -> O(1) per thread
-  if (dU && sep) {
-    for (int k = tid; k < nc + nr; k += kBwdThreads) {
-      const bool col = k < nc;
-      const int p = col ? c_lo + k : r_lo + (k - nc);
-      const int first = col ? c_lo : r_lo, last = col ? c_lo + nc - 1 : r_lo + nr - 1;
-      const Ent *tab = col ? sCol : sRow;
-      const int i0 = tab[p].i0;
-      if (tab[p].i0 != tab[p].i1) {  // (always true inside the rectangle for monotone maps)
-        const int slot = col ? i0 : W + i0 / W;
-        if (p == first || tab[p - 1].i0 != i0) sRun[slot].x = p;
-        if (p == last || tab[p + 1].i0 != i0) sRun[slot].y = p;
-      }
-    }
+  if (dU && !sep) {
+    for (int k = tid; k < HW; k += kBwdThreads) sT[k] = 0.0f;  // atomics tile
+    __syncthreads();
   }
   mbar_wait(&bar, 0);
 
@@ -395,7 +391,7 @@ __global__ void __launch_bounds__(kBwdThreads)
   float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int npix = nr * nc;
   // idx / nc by multiply-high: exact while idx * nc < 2^32 (checked on the host: OH*OW*OW < 2^32)
-  const unsigned magic = nc > 1 ? static_cast<unsigned>((0x100000000ull + nc - 1) / nc) : 0u;
+  const unsigned magic = static_cast<unsigned>(sRect[4]);
   for (int idx = tid; idx < npix; idx += kBwdThreads) {
     const int ro = nc > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), magic)) : idx;
     const int r = r_lo + ro, c = c_lo + (idx - ro * nc);
@@ -436,7 +432,8 @@ __global__ void __launch_bounds__(kBwdThreads)
       atomicAdd(&sT[re.i1 + ce.i1], mul_rn(ce.w0, re.w0) * g);
     }
   }
-  block_sum_many<7>(acc, red);  // contains a __syncthreads: the runs written above are visible after it
+  // the reduction scratch is the (not yet used) pass-1 buffer, or a dedicated region for the atomics path
+  block_sum_many<7>(acc, (dU && !sep) ? sScr : sT);
   if (tid == 0) {
     float *d = dtheta + b * 6;
 #pragma unroll
@@ -446,39 +443,80 @@ __global__ void __launch_bounds__(kBwdThreads)
   if (!dU) return;
 
   if (!sep) {
-    __syncthreads();
     for (int k = tid; k < HW; k += kBwdThreads) dU[b * HW + k] = sT[k];
     return;
   }
 
-  // ---- deterministic separable dU = z * Wy^T * G * Wx over the in-range rectangle (gather form, fixed
-  //      order, no atomics).  An in-range output column c touches source columns i0(c) (weight w1) and
-  //      i0(c)+1 (weight w0), so source column j gathers run(j) with w1 and run(j-1) with w0.
-  // pass 1: T[r][j] = sum_{c in run(j)} w1(c) g[r][c] + sum_{c in run(j-1)} w0(c) g[r][c]
-  for (int e = tid; e < nr * W; e += kBwdThreads) {
-    const int ro = e / W, j = e - ro * W;
-    const float *grow = sG + (r_lo + ro) * OW;
-    float a = 0.0f;
-    const int2 ra = sRun[j];
-    for (int c = ra.x; c <= ra.y; ++c) a += sCol[c].w1 * grow[c];
-    if (j > 0) {
-      const int2 rb = sRun[j - 1];
-      for (int c = rb.x; c <= rb.y; ++c) a += sCol[c].w0 * grow[c];
+  // ---- deterministic separable dU = z * Wy^T * G * Wx over the in-range rectangle (no atomics).
+  // An in-range output column c feeds source columns j = i0(c) (weight w1) and j+1 (weight w0), and i0(c)
+  // is monotone in c, so ONE lane per output row scans the columns in order with two running sums and
+  // emits T[j] whenever j advances; the branch pattern depends only on c => warp-uniform control flow.
+  // Pass 2 does the same along rows with one lane per source column.  Tt is stored [j][row] with an odd
+  // row stride (conflict-free both ways); the dU tile aliases sU (the window is dead after phase 1).
+  const int TS = OH | 1;
+  float *sTile = sU;
+  __syncthreads();  // everyone is past the reduction scratch (sT) and past phase 1 (sU)
+  for (int k = tid; k < W * TS; k += kBwdThreads) sT[k] = 0.0f;
+  for (int k = tid; k < HW; k += kBwdThreads) sTile[k] = 0.0f;
+  __syncthreads();
+  if (nr > 0 && nc > 0) {
+    const bool c_up = sCol[c_lo + nc - 1].i0 >= sCol[c_lo].i0;  // scan direction that makes j non-decreasing
+    for (int ro = tid; ro < nr; ro += kBwdThreads) {
+      const float *grow = sG + (r_lo + ro) * OW;
+      int jcur = -1;
+      float s0 = 0.0f, s1 = 0.0f;
+      for (int k = 0; k < nc; ++k) {
+        const int c = c_up ? c_lo + k : c_lo + nc - 1 - k;
+        const Ent ce = sCol[c];
+        if (ce.i0 == ce.i1) continue;
+        if (ce.i0 != jcur) {
+          if (jcur >= 0) {
+            sT[jcur * TS + ro] = s0;
+            if (ce.i0 == jcur + 1) { s0 = s1; } else { sT[(jcur + 1) * TS + ro] = s1; s0 = 0.0f; }
+            s1 = 0.0f;
+          }
+          jcur = ce.i0;
+        }
+        const float g = grow[c];
+        s0 += ce.w1 * g;
+        s1 += ce.w0 * g;
+      }
+      if (jcur >= 0) { sT[jcur * TS + ro] = s0; sT[(jcur + 1) * TS + ro] = s1; }
     }
-    sT[ro * W + j] = a;
   }
   __syncthreads();
-  // pass 2: dU[i][j] = z * (sum_{r in run(i)} w1(r) T[r][j] + sum_{r in run(i-1)} w0(r) T[r][j])
-  for (int e = tid; e < HW; e += kBwdThreads) {
-    const int i = e / W, j = e - i * W;
-    float a = 0.0f;
-    const int2 ra = sRun[W + i];
-    for (int r = ra.x; r <= ra.y; ++r) a += sRow[r].w1 * sT[(r - r_lo) * W + j];
-    if (i > 0) {
-      const int2 rb = sRun[W + i - 1];
-      for (int r = rb.x; r <= rb.y; ++r) a += sRow[r].w0 * sT[(r - r_lo) * W + j];
+  if (nr > 0 && nc > 0) {
+    const bool r_up = sRow[r_lo + nr - 1].i0 >= sRow[r_lo].i0;
+    for (int j = tid; j < W; j += kBwdThreads) {
+      const float *tcol = sT + j * TS;
+      int icur = -1;  // source row offset (pre-multiplied by W)
+      float s0 = 0.0f, s1 = 0.0f;
+      for (int k = 0; k < nr; ++k) {
+        const int ro = r_up ? k : nr - 1 - k;
+        const Ent re = sRow[r_lo + ro];
+        if (re.i0 == re.i1) continue;
+        if (re.i0 != icur) {
+          if (icur >= 0) {
+            sTile[icur + j] = s0;
+            if (re.i0 == icur + W) { s0 = s1; } else { sTile[icur + W + j] = s1; s0 = 0.0f; }
+            s1 = 0.0f;
+          }
+          icur = re.i0;
+        }
+        const float t = tcol[ro];
+        s0 += re.w1 * t;
+        s1 += re.w0 * t;
+      }
+      if (icur >= 0) { sTile[icur + j] = s0; sTile[icur + W + j] = s1; }
     }
-    dU[b * HW + e] = FUSED ? a * zval : a;
+  }
+  __syncthreads();
+  const float zs = FUSED ? zval : 1.0f;
+  float4 *dst = reinterpret_cast<float4 *>(dU + b * HW);  // HW % 4 == 0 and 16-byte aligned on this path
+  for (int k = tid; k < (HW >> 2); k += kBwdThreads) {
+    float4 v = *reinterpret_cast<const float4 *>(sTile + 4 * k);
+    v.x *= zs; v.y *= zs; v.z *= zs; v.w *= zs;
+    dst[k] = v;
   }
 }
 
@@ -601,11 +639,11 @@ static int st_forward_impl(const float *U, const float *theta, float *out, const
   return check_launch("st_fwd_generic");
 }
 
-static size_t bwd_smem_bytes(int H, int W, int OH, int OW) {
+static size_t bwd_smem_bytes(int H, int W, int OH, int OW, bool need_dU) {
   const size_t hw = (static_cast<size_t>(H) * W + 3) & ~size_t(3), ohw = (static_cast<size_t>(OH) * OW + 3) & ~size_t(3);
-  const size_t t = std::max(static_cast<size_t>(OH) * W, static_cast<size_t>(H) * W);
-  return (hw + ohw) * 4 + static_cast<size_t>(OW + OH) * sizeof(Ent) + static_cast<size_t>((W + H + 1) & ~1) * 8 +
-         static_cast<size_t>((OW + OH + 3) & ~3) * 4 + t * 4;
+  const size_t scr = 7 * kBwdThreads;
+  const size_t t = need_dU ? std::max(static_cast<size_t>(OH | 1) * W, hw + scr) : scr;
+  return (hw + ohw) * 4 + static_cast<size_t>(OW + OH) * sizeof(Ent) + static_cast<size_t>((OW + OH + 3) & ~3) * 4 + t * 4;
 }
 
 template <int H_, int W_, int OH_, int OW_, bool FUSED>
@@ -613,7 +651,7 @@ static int launch_bwd_staged(const float *U, const float *theta, const float *do
                              float thr, float *dU, float *dtheta, float *dz, int64_t B, int H, int W, int OH, int OW,
                              cudaStream_t s) {
   auto kern = st_bwd_staged<H_, W_, OH_, OW_, FUSED>;
-  const size_t smem = bwd_smem_bytes(H, W, OH, OW);
+  const size_t smem = bwd_smem_bytes(H, W, OH, OW, dU != nullptr);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_bwd_staged): %s", cudaGetErrorString(e));
@@ -634,7 +672,7 @@ static int st_backward_impl(const float *U, const float *theta, const float *dou
   AIR_REQUIRE(U && theta && dout && dtheta, AIR_ERR_NULL, "st_backward: null pointer");
   const bool staged = staged_ok(U, H, W, C, B) && ((OH * OW) % 4 == 0) && aligned16(dout) &&
                       static_cast<int64_t>(OH) * OW * OW < (int64_t(1) << 32) &&
-                      bwd_smem_bytes(H, W, OH, OW) <= static_cast<size_t>(kMaxStagedSmem);
+                      bwd_smem_bytes(H, W, OH, OW, dU != nullptr) <= static_cast<size_t>(kMaxStagedSmem);
   if (staged) {
     if (fused) {
       if (H == 28 && W == 28 && OH == 50 && OW == 50)
