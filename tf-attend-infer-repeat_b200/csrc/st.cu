@@ -409,11 +409,13 @@ __global__ void __launch_bounds__(kBwdThreads)
     const float Ic = sU[re.i0 + ce.i1], Id = sU[re.i1 + ce.i1];
     float g = sG[q];
     if (FUSED) {
-      const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
-      const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
-      const float v = add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
-      acc[6] += g * v;  // d(z * v)/dz
-      g *= zval;        // d(z * v)/dv
+      if (!sep || !dU) {  // separable path with dU: dz = <dU / z, U> after the dU passes (the sample is linear in U)
+        const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+        const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+        const float v = add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
+        acc[6] += g * v;  // d(z * v)/dz
+      }
+      g *= zval;  // d(z * v)/dv
     }
     const float dwa = g * Ia, dwb = g * Ib, dwc = g * Ic, dwd = g * Id;
     const float dx = ((-(dwa * re.w1) - dwb * re.w0) + dwc * re.w1) + dwd * re.w0;
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(kBwdThreads)
     float *d = dtheta + b * 6;
 #pragma unroll
     for (int k = 0; k < 6; ++k) d[k] = acc[k];
-    if (FUSED && dz) dz[b] = acc[6];
+    if (FUSED && dz && (!sep || !dU)) dz[b] = acc[6];
   }
   if (!dU) return;
 
@@ -452,12 +454,12 @@ __global__ void __launch_bounds__(kBwdThreads)
   // is monotone in c, so ONE lane per output row scans the columns in order with two running sums and
   // emits T[j] whenever j advances; the branch pattern depends only on c => warp-uniform control flow.
   // Pass 2 does the same along rows with one lane per source column.  Tt is stored [j][row] with an odd
-  // row stride (conflict-free both ways); the dU tile aliases sU (the window is dead after phase 1).
+  // row stride (conflict-free both ways); the dU tile aliases sG (the upstream tile is dead after pass 1),
+  // which keeps the window sU intact for dz = <dU / z, U>.
   const int TS = OH | 1;
-  float *sTile = sU;
+  float *sTile = sG;
   __syncthreads();  // everyone is past the reduction scratch (sT) and past phase 1 (sU)
   for (int k = tid; k < W * TS; k += kBwdThreads) sT[k] = 0.0f;
-  for (int k = tid; k < HW; k += kBwdThreads) sTile[k] = 0.0f;
   __syncthreads();
   if (nr > 0 && nc > 0) {
     const bool c_up = sCol[c_lo + nc - 1].i0 >= sCol[c_lo].i0;  // scan direction that makes j non-decreasing
@@ -484,6 +486,8 @@ __global__ void __launch_bounds__(kBwdThreads)
       if (jcur >= 0) { sT[jcur * TS + ro] = s0; sT[(jcur + 1) * TS + ro] = s1; }
     }
   }
+  __syncthreads();
+  for (int k = tid; k < HW; k += kBwdThreads) sTile[k] = 0.0f;  // sG is dead now
   __syncthreads();
   if (nr > 0 && nc > 0) {
     const bool r_up = sRow[r_lo + nr - 1].i0 >= sRow[r_lo].i0;
@@ -513,10 +517,19 @@ __global__ void __launch_bounds__(kBwdThreads)
   __syncthreads();
   const float zs = FUSED ? zval : 1.0f;
   float4 *dst = reinterpret_cast<float4 *>(dU + b * HW);  // HW % 4 == 0 and 16-byte aligned on this path
+  float dot[1] = {0.0f};
   for (int k = tid; k < (HW >> 2); k += kBwdThreads) {
     float4 v = *reinterpret_cast<const float4 *>(sTile + 4 * k);
+    if (FUSED) {
+      const float4 u = *reinterpret_cast<const float4 *>(sU + 4 * k);
+      dot[0] += ((v.x * u.x + v.y * u.y) + v.z * u.z) + v.w * u.w;
+    }
     v.x *= zs; v.y *= zs; v.z *= zs; v.w *= zs;
     dst[k] = v;
+  }
+  if (FUSED && dz) {
+    block_sum_many<1>(dot, sT);  // contains the barrier that orders it after the last reads of sT
+    if (tid == 0) dz[b] = dot[0];
   }
 }
 
