@@ -21,8 +21,41 @@ int check_launch(const char *what);  // cudaGetLastError -> AIR_ERR_CUDA
     }                                 \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Every kernel of this library is launched with programmaticStreamSerialization = 1 (unless
+// AIR_PDL=0): its CTAs may be scheduled while the previous kernel in the stream drains, run their
+// prologue (shared-memory carve-up, mbarrier init, TMEM allocation, tensor-map prefetch) and then
+// block in pdl_wait() until the previous grid has completed and its memory is visible.  The rule
+// that keeps this safe: NO global-memory access (read or write) before pdl_wait().
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define AIR_LAUNCH(kern, grid, block, smem, stream, ...) \
+  (void)::air::launch_pdl(kern, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int sm_count();  // cached per device
+
+// device side of PDL: wait for the previous grid, then let the next grid start its own prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_trigger();
+}
 
 // ---- exact (never FMA-contracted) fp32 arithmetic -------------------------------------
 // The oracle rounds every TF op separately; these intrinsics are immune to -fmad.

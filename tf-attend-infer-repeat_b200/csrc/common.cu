@@ -1,5 +1,6 @@
 // Library plumbing for libair_b200.so: error strings, launch counter, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "air_common.cuh"
 
@@ -24,6 +25,15 @@ int check_launch(const char *what) {
     return AIR_ERR_CUDA;
   }
   return AIR_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("AIR_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int sm_count() {

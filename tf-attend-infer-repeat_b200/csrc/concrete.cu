@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
                       float tau, float thr, int train, float *__restrict__ y, float *__restrict__ z,
                       float *__restrict__ z_prob, float *__restrict__ kl, float *stop_new, float *loss_new,
                       int32_t *digits_new, int64_t B) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   const float prior = __ldg(prior_log_odds);
   for (int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; b < B;
        b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256)
                       const float *__restrict__ dz, const float *__restrict__ dkl,
                       const float *__restrict__ prior_log_odds, float tau, int train, float *__restrict__ dlog_odds,
                       int64_t B) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   const float prior = __ldg(prior_log_odds);
   for (int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; b < B;
        b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -67,7 +69,7 @@ extern "C" int air_concrete_step_fwd(const float *log_odds, const float *u, cons
   AIR_REQUIRE(B >= 0, AIR_ERR_BAD_SHAPE, "concrete_step_fwd: B < 0");
   if (B == 0) return AIR_OK;
   const int blocks = static_cast<int>(std::min<int64_t>((B + 255) / 256, static_cast<int64_t>(air::sm_count()) * 8));
-  air::concrete_step_fwd<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  AIR_LAUNCH(air::concrete_step_fwd, blocks, 256, 0, static_cast<cudaStream_t>(stream), 
       log_odds, u, stop_prev, loss_prev, digits_prev, prior_log_odds, temperature, thr, train, y, z, z_prob, kl,
       stop_new, loss_new, digits_new, B);
   air::count_launch();
@@ -81,7 +83,7 @@ extern "C" int air_concrete_step_bwd(const float *log_odds, const float *y, cons
   AIR_REQUIRE(B >= 0, AIR_ERR_BAD_SHAPE, "concrete_step_bwd: B < 0");
   if (B == 0) return AIR_OK;
   const int blocks = static_cast<int>(std::min<int64_t>((B + 255) / 256, static_cast<int64_t>(air::sm_count()) * 8));
-  air::concrete_step_bwd<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  AIR_LAUNCH(air::concrete_step_bwd, blocks, 256, 0, static_cast<cudaStream_t>(stream), 
       log_odds, y, z, dz, dkl, prior_log_odds, temperature, train, dlog_odds, B);
   air::count_launch();
   return air::check_launch("concrete_step_bwd");

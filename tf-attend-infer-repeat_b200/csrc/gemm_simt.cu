@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256)
     gemm_simt(const float *__restrict__ A, const float *__restrict__ Bm, float *C, const float *Cinit,
               const float *__restrict__ bias, const float *aux, int M, int N, int K, int lda, int ldb, int ldc,
               int epi) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
   static_assert(TM % 2 == 0 && TN % 2 == 0, "split tiles");
   constexpr int HM = TM / 2, HN = TN / 2;
@@ -118,13 +119,13 @@ static int launch_simt(const float *A, const float *B, float *C, const float *Ci
                        cudaStream_t s) {
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   if (!tA && !tB)
-    gemm_simt<BM, BN, BK, TM, TN, false, false><<<grid, 256, 0, s>>>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, false, false>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
   else if (!tA && tB)
-    gemm_simt<BM, BN, BK, TM, TN, false, true><<<grid, 256, 0, s>>>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, false, true>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
   else if (tA && !tB)
-    gemm_simt<BM, BN, BK, TM, TN, true, false><<<grid, 256, 0, s>>>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, true, false>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
   else
-    gemm_simt<BM, BN, BK, TM, TN, true, true><<<grid, 256, 0, s>>>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, true, true>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
   count_launch();
   return check_launch("gemm_simt");
 }

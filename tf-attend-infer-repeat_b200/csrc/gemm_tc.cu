@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kTcThreads)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
+  pdl_sync();  // PDL: barriers, TMEM and descriptors were set up while the previous grid drained
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(kTcThreads)
 __global__ void __launch_bounds__(256)
     splitk_reduce_kernel(const float *__restrict__ ws, int splits, float *C, const float *Cinit,
                          const float *__restrict__ bias, const float *aux, int M, int N, int ldc, int epi) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   const int64_t total = static_cast<int64_t>(M) * N;  // N % 4 == 0 on this path
   const int64_t nvec = total >> 2;
   for (int64_t v4 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v4 < nvec;
@@ -384,7 +386,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParam
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, p.splits);
-  kern<<<grid, kTcThreads, smem, s>>>(ma, mb, p);
+  AIR_LAUNCH(kern, grid, kTcThreads, smem, s, ma, mb, p);
   count_launch();
   return check_launch("gemm_tf32");
 }
@@ -443,7 +445,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   if (splits > 1) {
     const int64_t total = static_cast<int64_t>(M) * N / 4;
     const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
-    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(ws, splits, C, Cinit, bias, aux, M, N, ldc, epi);
+    AIR_LAUNCH(splitk_reduce_kernel, blocks, 256, 0, s, ws, splits, C, Cinit, bias, aux, M, N, ldc, epi);
     count_launch();
     rc = check_launch("splitk_reduce");
   }

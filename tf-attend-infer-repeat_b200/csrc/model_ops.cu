@@ -28,6 +28,7 @@ static inline int grid_for(int64_t n, int threads, int per_sm = 8) {
 __global__ void __launch_bounds__(256)
     lstm_fwd_k(const float *__restrict__ gates, const float *__restrict__ c_prev, float *__restrict__ c_new,
                float *__restrict__ h_new, int64_t B, int H) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   AIR_GRID_STRIDE(e, B * H) {
     const int64_t b = e / H;
     const int k = static_cast<int>(e - b * H);
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     lstm_bwd_k(const float *__restrict__ gates, const float *__restrict__ c_prev, const float *__restrict__ c_new,
                const float *__restrict__ dh, const float *dc_new, float *__restrict__ dgates, float *dc_prev,
-               float *dgates_sum, int64_t B, int H) {  // dc_prev may alias dc_new (same index, read before write)
+               float *dgates_sum, int64_t B, int H) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed  // dc_prev may alias dc_new (same index, read before write)
   AIR_GRID_STRIDE(e, B * H) {
     const int64_t b = e / H;
     const int k = static_cast<int>(e - b * H);
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256)
                 const float *__restrict__ n_scale, const float *__restrict__ n_shift, const float *__restrict__ u,
                 const float *__restrict__ prior_p, air_hyper_t hp, float *stop, float *loss, int32_t *digits,
                 float *__restrict__ fields, float *__restrict__ theta, float *__restrict__ theta_inv, int64_t B, int HU) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   const int64_t gt = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t b = gt >> 3;
   const int j = static_cast<int>(gt & 7);
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256)
                 const float *__restrict__ dtheta_inv, const float *__restrict__ dz, const float *__restrict__ prior_p,
                 air_hyper_t hp, float dloss, float *__restrict__ dhidden, float *__restrict__ partials, int64_t B,
                 int HU) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float sOut[kHeadsImgs][8];
   const int tid = threadIdx.x;
   const int img = tid >> 3, j = tid & 7;
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(256)
 // out[e] (+)= sum_r partials[r*stride + e], r in increasing order (deterministic)
 __global__ void __launch_bounds__(256)
     reduce_rows_k(const float *__restrict__ partials, int R, int stride, int n, float *out, int accumulate) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   AIR_GRID_STRIDE(e, n) {
     float acc = 0.0f;
     int r = 0;
@@ -245,6 +250,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     vae_latent_fwd_k(const float *__restrict__ ml, const float *__restrict__ noise, air_hyper_t hp,
                      float *__restrict__ sample, int lds, float *__restrict__ fields, float *loss, int64_t B, int L) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -268,6 +274,7 @@ __global__ void __launch_bounds__(256)
     vae_latent_bwd_k(const float *__restrict__ ml, const float *__restrict__ noise, const float *__restrict__ dsample,
                      const float *__restrict__ fields, air_hyper_t hp, float dloss, float *__restrict__ dml, int64_t B,
                      int L) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   AIR_GRID_STRIDE(e, B * L) {
     const int64_t b = e / L;
     const int d = static_cast<int>(e - b * L);
@@ -283,11 +290,13 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     sigmoid_noise_fwd_k(const float *__restrict__ gen, const float *__restrict__ noise, float sd, float *__restrict__ out,
                         int64_t n) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   AIR_GRID_STRIDE(e, n) out[e] = sigmoid_f(gen[e] + noise[e] * sd);
 }
 
 __global__ void __launch_bounds__(256)
     sigmoid_bwd_k(const float *out, const float *dout, float *dgen, int64_t n) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   AIR_GRID_STRIDE(e, n) {
     const float o = out[e];
     dgen[e] = dout[e] * o * (1.0f - o);
@@ -300,6 +309,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     bce_loss_k(const float *__restrict__ canvas, const float *__restrict__ x, float *__restrict__ recon,
                float *__restrict__ rec_loss, float *__restrict__ dcanvas, float dscale, int N) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float red[8];
   const int64_t b = blockIdx.x;
   const float *c = canvas + b * N, *xi = x + b * N;
@@ -329,6 +339,7 @@ __global__ void __launch_bounds__(1024)
     finalize_loss_k(const float *__restrict__ running_loss, const float *__restrict__ rec_loss,
                     const int32_t *__restrict__ digits, const int32_t *__restrict__ target, float *__restrict__ out,
                     float *__restrict__ loss_per_item, int64_t B) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float r0[32], r1[32];
   float a = 0.0f, c = 0.0f;
   for (int64_t b = threadIdx.x; b < B; b += 1024) {
@@ -355,6 +366,7 @@ __global__ void __launch_bounds__(1024)
 __global__ void __launch_bounds__(256)
     colsum_partial_k(const float *__restrict__ X, int ld, float *__restrict__ partials, int64_t B, int N,
                      int rows_per_chunk) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
@@ -388,6 +400,7 @@ constexpr int kAdamPartials = 1024;
 
 __global__ void __launch_bounds__(256)
     sumsq_partial_k(const float *__restrict__ g, float gs, float *__restrict__ partials, int64_t n) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float red[8];
   float acc = 0.0f;
   AIR_GRID_STRIDE(e, n) {
@@ -408,6 +421,7 @@ __global__ void __launch_bounds__(256)
     adam_apply_k(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  const float *__restrict__ state, const float *__restrict__ partials, int n_partials, float clip,
                  float beta1, float beta2, float eps, float gs, float *__restrict__ norm_out, int64_t n) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float red[8];
   __shared__ float s_scale;
   // every CTA reduces the same partials in the same order -> identical clip scale everywhere
@@ -442,6 +456,7 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void adam_advance_k(float *state, float beta1, float beta2, const float *norm_in) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   state[0] *= beta1;
   state[1] *= beta2;
   state[2] += 1.0f;
@@ -450,6 +465,7 @@ __global__ void adam_advance_k(float *state, float beta1, float beta2, const flo
 
 __global__ void anneal_k(const float *state, float init, float factor, float iters, int staircase, float vmin,
                          float vmax, int take_log, float *out) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   float p = state[2] / iters;
   if (staircase) p = floorf(p);
   float v = init * powf(factor, p);
@@ -470,7 +486,7 @@ extern "C" int air_lstm_fwd(const float *gates, const float *c_prev, float *c_ne
   AIR_REQUIRE(B >= 0 && H > 0, AIR_ERR_BAD_SHAPE, "lstm_fwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(gates && c_new && h_new, AIR_ERR_NULL, "lstm_fwd: null pointer");
-  lstm_fwd_k<<<grid_for(B * H, 256), 256, 0, ST(stream)>>>(gates, c_prev, c_new, h_new, B, H);
+  AIR_LAUNCH(lstm_fwd_k, grid_for(B * H, 256), 256, 0, ST(stream), gates, c_prev, c_new, h_new, B, H);
   count_launch();
   return check_launch("lstm_fwd");
 }
@@ -481,7 +497,7 @@ extern "C" int air_lstm_bwd(const float *gates, const float *c_prev, const float
   AIR_REQUIRE(B >= 0 && H > 0, AIR_ERR_BAD_SHAPE, "lstm_bwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(gates && c_new && dh && dgates && dc_prev, AIR_ERR_NULL, "lstm_bwd: null pointer");
-  lstm_bwd_k<<<grid_for(B * H, 256), 256, 0, ST(stream)>>>(gates, c_prev, c_new, dh, dc_new, dgates, dc_prev, dgates_sum,
+  AIR_LAUNCH(lstm_bwd_k, grid_for(B * H, 256), 256, 0, ST(stream), gates, c_prev, c_new, dh, dc_new, dgates, dc_prev, dgates_sum,
                                                           B, H);
   count_launch();
   return check_launch("lstm_bwd");
@@ -497,7 +513,7 @@ extern "C" int air_heads_fwd(const float *hidden, const float *w_out, const floa
                   digits && fields && theta && theta_inv,
               AIR_ERR_NULL, "heads_fwd: null pointer");
   const int64_t threads = B * 8;
-  heads_fwd_k<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ST(stream)>>>(
+  AIR_LAUNCH(heads_fwd_k, static_cast<unsigned>((threads + 255) / 256), 256, 0, ST(stream), 
       hidden, w_out, b_out, noise_scale, noise_shift, u, prior_log_odds, *hyper, stop, loss, digits, fields, theta,
       theta_inv, B, HU);
   count_launch();
@@ -519,14 +535,14 @@ extern "C" int air_heads_bwd(const float *hidden, const float *w_out, const floa
                   hyper && dhidden && dw_out && db_out && workspace,
               AIR_ERR_NULL, "heads_bwd: null pointer");
   const int R = static_cast<int>((B + kHeadsImgs - 1) / kHeadsImgs);
-  heads_bwd_k<<<R, 256, 0, ST(stream)>>>(hidden, w_out, noise_scale, noise_shift, fields, dtheta, dtheta_inv, dz,
+  AIR_LAUNCH(heads_bwd_k, R, 256, 0, ST(stream), hidden, w_out, noise_scale, noise_shift, fields, dtheta, dtheta_inv, dz,
                                          prior_log_odds, *hyper, dloss, dhidden, workspace, B, HU);
   count_launch();
   int rc = check_launch("heads_bwd");
   if (rc) return rc;
   const int n = 7 * HU;
-  reduce_rows_k<<<grid_for(n, 256), 256, 0, ST(stream)>>>(workspace, R, n + 7, n, dw_out, accumulate);
-  reduce_rows_k<<<1, 32, 0, ST(stream)>>>(workspace + n, R, n + 7, 7, db_out, accumulate);
+  AIR_LAUNCH(reduce_rows_k, grid_for(n, 256), 256, 0, ST(stream), workspace, R, n + 7, n, dw_out, accumulate);
+  AIR_LAUNCH(reduce_rows_k, 1, 32, 0, ST(stream), workspace + n, R, n + 7, 7, db_out, accumulate);
   count_launch(2);
   return check_launch("heads_bwd reduce");
 }
@@ -536,7 +552,7 @@ extern "C" int air_vae_latent_fwd(const float *ml, const float *noise, const air
   AIR_REQUIRE(B >= 0 && L > 0 && ld_sample >= L, AIR_ERR_BAD_SHAPE, "vae_latent_fwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(ml && noise && hyper && sample && fields && loss, AIR_ERR_NULL, "vae_latent_fwd: null pointer");
-  vae_latent_fwd_k<<<static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, ST(stream)>>>(ml, noise, *hyper, sample, ld_sample,
+  AIR_LAUNCH(vae_latent_fwd_k, static_cast<unsigned>((B * 32 + 255) / 256), 256, 0, ST(stream), ml, noise, *hyper, sample, ld_sample,
                                                                                        fields, loss, B, L);
   count_launch();
   return check_launch("vae_latent_fwd");
@@ -548,7 +564,7 @@ extern "C" int air_vae_latent_bwd(const float *ml, const float *noise, const flo
   AIR_REQUIRE(B >= 0 && L > 0, AIR_ERR_BAD_SHAPE, "vae_latent_bwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(ml && noise && dsample && fields && hyper && dml, AIR_ERR_NULL, "vae_latent_bwd: null pointer");
-  vae_latent_bwd_k<<<grid_for(B * L, 256), 256, 0, ST(stream)>>>(ml, noise, dsample, fields, *hyper, dloss, dml, B, L);
+  AIR_LAUNCH(vae_latent_bwd_k, grid_for(B * L, 256), 256, 0, ST(stream), ml, noise, dsample, fields, *hyper, dloss, dml, B, L);
   count_launch();
   return check_launch("vae_latent_bwd");
 }
@@ -558,7 +574,7 @@ extern "C" int air_sigmoid_noise_fwd(const float *gen, const float *noise, float
   AIR_REQUIRE(n >= 0, AIR_ERR_BAD_SHAPE, "sigmoid_noise_fwd: n < 0");
   if (n == 0) return AIR_OK;
   AIR_REQUIRE(gen && noise && out, AIR_ERR_NULL, "sigmoid_noise_fwd: null pointer");
-  sigmoid_noise_fwd_k<<<grid_for(n, 256, 16), 256, 0, ST(stream)>>>(gen, noise, sd, out, n);
+  AIR_LAUNCH(sigmoid_noise_fwd_k, grid_for(n, 256, 16), 256, 0, ST(stream), gen, noise, sd, out, n);
   count_launch();
   return check_launch("sigmoid_noise_fwd");
 }
@@ -567,7 +583,7 @@ extern "C" int air_sigmoid_bwd(const float *out, const float *dout, float *dgen,
   AIR_REQUIRE(n >= 0, AIR_ERR_BAD_SHAPE, "sigmoid_bwd: n < 0");
   if (n == 0) return AIR_OK;
   AIR_REQUIRE(out && dout && dgen, AIR_ERR_NULL, "sigmoid_bwd: null pointer");
-  sigmoid_bwd_k<<<grid_for(n, 256, 16), 256, 0, ST(stream)>>>(out, dout, dgen, n);
+  AIR_LAUNCH(sigmoid_bwd_k, grid_for(n, 256, 16), 256, 0, ST(stream), out, dout, dgen, n);
   count_launch();
   return check_launch("sigmoid_bwd");
 }
@@ -577,7 +593,7 @@ extern "C" int air_bce_loss(const float *canvas, const float *x, float *recon, f
   AIR_REQUIRE(B >= 0 && N > 0 && B < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "bce_loss: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(canvas && x && rec_loss, AIR_ERR_NULL, "bce_loss: null pointer");
-  bce_loss_k<<<static_cast<unsigned>(B), 256, 0, ST(stream)>>>(canvas, x, recon, rec_loss, dcanvas, dscale, N);
+  AIR_LAUNCH(bce_loss_k, static_cast<unsigned>(B), 256, 0, ST(stream), canvas, x, recon, rec_loss, dcanvas, dscale, N);
   count_launch();
   return check_launch("bce_loss");
 }
@@ -587,7 +603,7 @@ extern "C" int air_finalize_loss(const float *running_loss, const float *rec_los
                                  air_stream_t stream) {
   AIR_REQUIRE(B > 0, AIR_ERR_BAD_SHAPE, "finalize_loss: B <= 0");
   AIR_REQUIRE(running_loss && rec_loss && digits && target && out, AIR_ERR_NULL, "finalize_loss: null pointer");
-  finalize_loss_k<<<1, 1024, 0, ST(stream)>>>(running_loss, rec_loss, digits, target, out, loss_per_item, B);
+  AIR_LAUNCH(finalize_loss_k, 1, 1024, 0, ST(stream), running_loss, rec_loss, digits, target, out, loss_per_item, B);
   count_launch();
   return check_launch("finalize_loss");
 }
@@ -605,11 +621,11 @@ extern "C" int air_colsum(const float *X, int ld, float *out, int accumulate, fl
   const int R = colsum_chunks(B, N);
   const int rows = static_cast<int>((B + R - 1) / R);
   dim3 grid((N + 31) / 32, R);
-  colsum_partial_k<<<grid, 256, 0, ST(stream)>>>(X, ld, workspace, B, N, rows);
+  AIR_LAUNCH(colsum_partial_k, grid, 256, 0, ST(stream), X, ld, workspace, B, N, rows);
   count_launch();
   int rc = check_launch("colsum_partial");
   if (rc) return rc;
-  reduce_rows_k<<<grid_for(N, 256), 256, 0, ST(stream)>>>(workspace, R, N, N, out, accumulate);
+  AIR_LAUNCH(reduce_rows_k, grid_for(N, 256), 256, 0, ST(stream), workspace, R, N, N, out, accumulate);
   count_launch();
   return check_launch("colsum reduce");
 }
@@ -622,10 +638,10 @@ extern "C" int air_adam_step(float *params, const float *grads, float *m, float 
   AIR_REQUIRE(n > 0, AIR_ERR_BAD_SHAPE, "adam_step: n <= 0");
   AIR_REQUIRE(params && grads && m && v && state && workspace, AIR_ERR_NULL, "adam_step: null pointer");
   const int np = static_cast<int>(std::min<int64_t>(kAdamPartials, (n + 1023) / 1024));
-  sumsq_partial_k<<<np, 256, 0, ST(stream)>>>(grads, grad_scale, workspace, n);
-  adam_apply_k<<<grid_for(n, 256, 4), 256, 0, ST(stream)>>>(params, grads, m, v, state, workspace, np, clip_norm, beta1,
+  AIR_LAUNCH(sumsq_partial_k, np, 256, 0, ST(stream), grads, grad_scale, workspace, n);
+  AIR_LAUNCH(adam_apply_k, grid_for(n, 256, 4), 256, 0, ST(stream), params, grads, m, v, state, workspace, np, clip_norm, beta1,
                                                             beta2, epsilon, grad_scale, workspace + kAdamPartials, n);
-  adam_advance_k<<<1, 1, 0, ST(stream)>>>(state, beta1, beta2, workspace + kAdamPartials);
+  AIR_LAUNCH(adam_advance_k, 1, 1, 0, ST(stream), state, beta1, beta2, workspace + kAdamPartials);
   count_launch(3);
   return check_launch("adam_step");
 }
@@ -633,7 +649,7 @@ extern "C" int air_adam_step(float *params, const float *grads, float *m, float 
 extern "C" int air_anneal(const float *state, float init, float factor, float iters, int staircase, float vmin,
                           float vmax, int take_log, float *out, air_stream_t stream) {
   AIR_REQUIRE(state && out, AIR_ERR_NULL, "anneal: null pointer");
-  anneal_k<<<1, 1, 0, ST(stream)>>>(state, init, factor, iters, staircase, vmin, vmax, take_log, out);
+  AIR_LAUNCH(anneal_k, 1, 1, 0, ST(stream), state, init, factor, iters, staircase, vmin, vmax, take_log, out);
   count_launch();
   return check_launch("anneal");
 }

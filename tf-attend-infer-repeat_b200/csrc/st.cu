@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kFwdThreads)
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   if (tid == 0) {
     const uint32_t bytes = static_cast<uint32_t>(n_img) * HW * 4u;
     mbar_expect_tx(&bar, bytes);
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(kFwdThreads)
 __global__ void __launch_bounds__(256)
     st_fwd_generic(const float *__restrict__ U, const float *__restrict__ theta, float *__restrict__ out, int64_t B,
                    int H, int W, int C, int OH, int OW) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   const int64_t n = B * OH * OW;
   for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n;
        p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(kBwdThreads)
     st_bwd_staged(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dout,
                   const float *__restrict__ zp, const float *__restrict__ stop, float thr, float *__restrict__ dU,
                   float *__restrict__ dtheta, float *__restrict__ dz, int64_t B, int rH, int rW, int rOH, int rOW) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   const int H = H_ ? H_ : rH, W = W_ ? W_ : rW, OH = OH_ ? OH_ : rOH, OW = OW_ ? OW_ : rOW;
   const int HW = H * W, OHW = OH * OW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -539,6 +542,7 @@ __global__ void __launch_bounds__(kBwdThreads)
 __global__ void __launch_bounds__(kBwdThreads)
     st_bwd_generic(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dout,
                    float *dU, float *__restrict__ dtheta, int H, int W, int C, int OH, int OW) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float red[kBwdWarps];
   const int64_t b = blockIdx.x;
   float th[6];
@@ -607,7 +611,7 @@ static int launch_fwd_staged(const float *U, const float *theta, float *out, con
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_fwd_staged): %s", cudaGetErrorString(e));
   }
   const int64_t grid = (B + G - 1) / G;
-  kern<<<static_cast<unsigned>(grid), kFwdThreads, smem, s>>>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW);
+  AIR_LAUNCH(kern, static_cast<unsigned>(grid), kFwdThreads, smem, s, U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW);
   count_launch();
   return check_launch("st_fwd_staged");
 }
@@ -647,7 +651,7 @@ static int st_forward_impl(const float *U, const float *theta, float *out, const
               "st_writeback_canvas_fwd: needs a 16-byte aligned single-channel window that fits shared memory");
   const int64_t n = B * OH * OW;
   const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
-  st_fwd_generic<<<blocks, 256, 0, s>>>(U, theta, out, B, H, W, C, OH, OW);
+  AIR_LAUNCH(st_fwd_generic, blocks, 256, 0, s, U, theta, out, B, H, W, C, OH, OW);
   count_launch();
   return check_launch("st_fwd_generic");
 }
@@ -669,7 +673,7 @@ static int launch_bwd_staged(const float *U, const float *theta, const float *do
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_bwd_staged): %s", cudaGetErrorString(e));
   }
-  kern<<<static_cast<unsigned>(B), kBwdThreads, smem, s>>>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW);
+  AIR_LAUNCH(kern, static_cast<unsigned>(B), kBwdThreads, smem, s, U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW);
   count_launch();
   return check_launch("st_bwd_staged");
 }
@@ -705,7 +709,7 @@ static int st_backward_impl(const float *U, const float *theta, const float *dou
     cudaError_t e = cudaMemsetAsync(dU, 0, sizeof(float) * static_cast<size_t>(B) * H * W * C, s);
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
   }
-  st_bwd_generic<<<static_cast<unsigned>(B), kBwdThreads, 0, s>>>(U, theta, dout, dU, dtheta, H, W, C, OH, OW);
+  AIR_LAUNCH(st_bwd_generic, static_cast<unsigned>(B), kBwdThreads, 0, s, U, theta, dout, dU, dtheta, H, W, C, OH, OW);
   count_launch();
   return check_launch("st_bwd_generic");
 }
