@@ -25,4 +25,36 @@ __device__ __forceinline__ float apply_epilogue(float v, int epi, float aux) {
   }
 }
 
+// 16 independent element chains with the activation selected OUTSIDE the loop (ILP for the
+// tensor-core epilogue; branch-free softplus so the compiler can interleave the exp/log chains)
+__device__ __forceinline__ float softplus_tf_branchless(float x) {
+  const float thr = -13.942385f;
+  const float e = expf(x);
+  const float mid = logf(add_rn(e, 1.0f));
+  return x > -thr ? x : (x < thr ? e : mid);
+}
+
+__device__ __forceinline__ void apply_epilogue16(float (&v)[16], const float (&ax)[16], int epi) {
+  switch (epi) {
+    case AIR_EPI_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+      break;
+    case AIR_EPI_SOFTPLUS:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = softplus_tf_branchless(v[j]);
+      break;
+    case AIR_EPI_MUL_DRELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ax[j] > 0.0f ? v[j] : 0.0f;
+      break;
+    case AIR_EPI_MUL_DSOFTPLUS:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] * (-expm1f(-ax[j]));
+      break;
+    default:
+      break;
+  }
+}
+
 }  // namespace air

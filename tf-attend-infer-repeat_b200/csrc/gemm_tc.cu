@@ -13,8 +13,9 @@
 // chunk).  Weight-gradient GEMMs (reduction over the batch, few output tiles) use split-K
 // with a deterministic second pass.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue: TMEM lane quarter = warp_idx % 4, two warps per quarter each taking half
+// of the tile's columns (the epilogue, not the MMA pipe, bounds the small-K GEMMs of this model).
 #include <cuda.h>
 
 #include <algorithm>
@@ -27,7 +28,7 @@ namespace air {
 constexpr int kBM = 128;      // UMMA M (cta_group::1)
 constexpr int kBK = 32;       // 32 tf32 = 128 bytes = one swizzle row
 template <int BN> struct TcCfg { static constexpr int kStages = BN >= 128 ? 3 : 4; };  // 2 CTAs / SM either way
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -198,8 +199,9 @@ __global__ void __launch_bounds__(kTcThreads)
       umma_commit(&tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ================= epilogue: TMEM -> registers -> global =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ================= epilogue: TMEM -> registers -> global (8 warps) =================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns
     const int row = m0 + q * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
@@ -211,35 +213,44 @@ __global__ void __launch_bounds__(kTcThreads)
       ldo = p.N;
     }
     const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) &&
-                        (partial || ((!p.Cinit || (reinterpret_cast<uintptr_t>(p.Cinit) & 15) == 0) &&
-                                     (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
+                        (partial || ((p.ldc % 4 == 0) && (!p.Cinit || (reinterpret_cast<uintptr_t>(p.Cinit) & 15) == 0) &&
+                                     (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) &&
+                                     (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
+    const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
       uint32_t r[16];
-      tmem_ld_x16(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-      tmem_ld_wait();
-      if (row >= p.M || n0 + c0 >= p.N) continue;
+      tmem_ld_x16(tbase + c0, r);
       const int nb = n0 + c0;
-      if (vec_ok && nb + 16 <= p.N) {
-        float4 *dst = reinterpret_cast<float4 *>(Cout + static_cast<int64_t>(row) * ldo + nb);
-        const int64_t o = static_cast<int64_t>(row) * p.ldc + nb;
+      const bool row_ok = row < p.M && nb < p.N;
+      const bool fast = vec_ok && row_ok && nb + 16 <= p.N;
+      float ci[16], ax[16], bi[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { ci[j] = 0.0f; ax[j] = 0.0f; bi[j] = 0.0f; }
+      const int64_t o = static_cast<int64_t>(row) * p.ldc + nb;
+      if (fast && !partial) {  // epilogue inputs are fetched while the TMEM load is in flight
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          float v[4] = {__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
-                        __uint_as_float(r[4 * j4 + 3])};
-          if (!partial) {
-            float ci[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.Cinit) *reinterpret_cast<float4 *>(ci) = *reinterpret_cast<const float4 *>(p.Cinit + o + 4 * j4);
-            if (p.aux) *reinterpret_cast<float4 *>(ax) = *reinterpret_cast<const float4 *>(p.aux + o + 4 * j4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float t = v[j] + ci[j];
-              if (p.bias) t += __ldg(p.bias + nb + 4 * j4 + j);
-              v[j] = apply_epilogue(t, p.epi, ax[j]);
-            }
-          }
-          dst[j4] = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.Cinit) *reinterpret_cast<float4 *>(ci + 4 * j4) = *reinterpret_cast<const float4 *>(p.Cinit + o + 4 * j4);
+          if (p.aux) *reinterpret_cast<float4 *>(ax + 4 * j4) = *reinterpret_cast<const float4 *>(p.aux + o + 4 * j4);
+          if (p.bias) *reinterpret_cast<float4 *>(bi + 4 * j4) = __ldg(reinterpret_cast<const float4 *>(p.bias + nb) + j4);
         }
+      }
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      if (fast) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (!partial) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (v[j] + ci[j]) + bi[j];
+          apply_epilogue16(v, ax, p.epi);
+        }
+        float4 *dst = reinterpret_cast<float4 *>(Cout + static_cast<int64_t>(row) * ldo + nb);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -247,10 +258,10 @@ __global__ void __launch_bounds__(kTcThreads)
           if (n < p.N) {
             float v = __uint_as_float(r[j]);
             if (!partial) {
-              const int64_t o = static_cast<int64_t>(row) * p.ldc + n;
-              if (p.Cinit) v += p.Cinit[o];
+              const int64_t oo = static_cast<int64_t>(row) * p.ldc + n;
+              if (p.Cinit) v += p.Cinit[oo];
               if (p.bias) v += __ldg(p.bias + n);
-              v = apply_epilogue(v, p.epi, p.aux ? p.aux[o] : 0.0f);
+              v = apply_epilogue(v, p.epi, p.aux ? p.aux[oo] : 0.0f);
             }
             Cout[static_cast<int64_t>(row) * ldo + n] = v;
           }
