@@ -27,7 +27,7 @@ namespace air {
 
 constexpr int kBM = 128;      // UMMA M (cta_group::1)
 constexpr int kBK = 32;       // 32 tf32 = 128 bytes = one swizzle row
-template <int BN> struct TcCfg { static constexpr int kStages = BN >= 128 ? 3 : 4; };  // 2 CTAs / SM either way
+constexpr int kMaxStages = 8;  // ring depth is chosen per launch: deep when one CTA owns the SM, shallow when two share it
 constexpr int kTcThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -107,6 +107,7 @@ struct TcParams {
   const float *aux;
   int M, N, K, ldc, epi;
   int kb_per_split, num_kb, splits;
+  int stages;  // TMA->MMA ring depth (<= kMaxStages)
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -115,11 +116,11 @@ __global__ void __launch_bounds__(kTcThreads)
   constexpr uint32_t kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32
-  constexpr int kStages = TcCfg<BN>::kStages;
+  const int kStages = p.stages;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned tiles (SWIZZLE_128B atoms)
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,7 +133,6 @@ __global__ void __launch_bounds__(kTcThreads)
   if (threadIdx.x == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
-#pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(kTcThreads)
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char *sa = tiles + s * kStageBytes, *sb = sa + kABytes;
         mbar_expect_tx(&full_bar[s], kStageBytes);
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kTcThreads)
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (kBK * 128), &mapB, &full_bar[s], n0 + c * 32, k0);
         }
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -182,9 +183,9 @@ __global__ void __launch_bounds__(kTcThreads)
       constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_adv = A_MN ? 1024 : 32;
       constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_adv = B_MN ? 1024 : 32;
       constexpr uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + s * kStageBytes), sb = sa + kABytes;
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(kTcThreads)
           umma_tf32(tmem_acc, da, db, idesc, (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
       umma_commit(&tmem_full_bar);  // accumulator complete
     }
@@ -387,12 +389,24 @@ static float *splitk_workspace(size_t bytes) {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, cudaStream_t s) {
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, cudaStream_t s) {
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
-  const size_t smem = static_cast<size_t>(TcCfg<BN>::kStages) * (kBM + BN) * kBK * 4 + 1024;
+  const size_t stage_bytes = static_cast<size_t>(kBM + BN) * kBK * 4;
+  // The mainloop of one CTA is TMA-latency bound (~0.7 us per k-block with 3 stages), so keep as many
+  // bytes in flight per SM as shared memory allows: a deep ring when the grid gives each SM one CTA,
+  // half of it when two CTAs will share an SM.
+  const int64_t ctas = static_cast<int64_t>((p.N + BN - 1) / BN) * ((p.M + kBM - 1) / kBM) * p.splits;
+  const size_t budget = (ctas <= sm_count() ? 200 : 100) * 1024;
+  int stages = static_cast<int>(budget / stage_bytes);
+  stages = std::max(2, std::min({stages, kMaxStages, std::max(p.kb_per_split, 2)}));
+  p.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
+  const size_t smem_max = static_cast<size_t>(kMaxStages) * stage_bytes + 1024 > 225 * 1024
+                              ? static_cast<size_t>(200 * 1024 / stage_bytes) * stage_bytes + 1024
+                              : static_cast<size_t>(kMaxStages) * stage_bytes + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(gemm_tf32): %s", cudaGetErrorString(e));
     configured = true;
   }
