@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <stdlib.h>
 
 #include "air_common.cuh"
 #include "epilogue.cuh"
@@ -108,6 +109,7 @@ struct TcParams {
   int M, N, K, ldc, epi;
   int kb_per_split, num_kb, splits;
   int stages;  // TMA->MMA ring depth (<= kMaxStages)
+  int mma_repeat;  // diagnostics only (AIR_TC_MMA_REPEAT): re-issue each k-block's MMAs (results are then wrong)
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -147,32 +149,40 @@ __global__ void __launch_bounds__(kTcThreads)
   const uint32_t tmem_acc = tmem_base_slot;
   pdl_sync();  // PDL: barriers, TMEM and descriptors were set up while the previous grid drained
 
-  if (warp == 0) {
-    // ================= TMA producer =================
+  // ================= TMA producers =================
+  // Every stage is loaded as 4 + 4 quarter boxes issued by four threads: lane 0 of warp 0 and of the
+  // (otherwise idle until the accumulator is complete) epilogue warps 2..4.  Measured neutral against a
+  // single issuing thread: the per-CTA operand rate (~37 GB/s when a CTA is alone on its SM) is not an
+  // issue-rate limit, which is why the host picks grids with two CTAs per SM.
+  if (warp == 0 || (warp >= 2 && warp <= 4)) {
     if (lane == 0) {
+      const int pi = warp == 0 ? 0 : warp - 1;  // producer index 0..3
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait_spin(&empty_bar[s], ph ^ 1);
         unsigned char *sa = tiles + s * kStageBytes, *sb = sa + kABytes;
-        mbar_expect_tx(&full_bar[s], kStageBytes);
+        if (pi == 0) mbar_expect_tx(&full_bar[s], kStageBytes);
         const int k0 = (kb_begin + i) * kBK;
-        if (!A_MN) {
-          tma_load_2d(sa, &mapA, &full_bar[s], k0, m0);  // box {32 k, 128 m}
-        } else {
-#pragma unroll
-          for (int c = 0; c < kBM / 32; ++c)  // box {32 m, 32 k} per 32-wide chunk
-            tma_load_2d(sa + c * (kBK * 128), &mapA, &full_bar[s], m0 + c * 32, k0);
+        if (!A_MN) {  // box {32 k, 32 m}: rows [32 pi, 32 pi + 32)
+          tma_load_2d(sa + pi * (32 * 128), &mapA, &full_bar[s], k0, m0 + pi * 32);
+        } else {      // box {32 m, 32 k}: 32-wide chunk pi
+          tma_load_2d(sa + pi * (kBK * 128), &mapA, &full_bar[s], m0 + pi * 32, k0);
         }
-        if (!B_MN) {
-          tma_load_2d(sb, &mapB, &full_bar[s], k0, n0);  // box {32 k, BN n}
-        } else {
-#pragma unroll
-          for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (kBK * 128), &mapB, &full_bar[s], n0 + c * 32, k0);
+        if (!B_MN) {  // box {32 k, BN/4 n}
+          tma_load_2d(sb + pi * (BN / 4 * 128), &mapB, &full_bar[s], k0, n0 + pi * (BN / 4));
+        } else if (BN == 128) {  // box {32 n, 32 k}: chunk pi
+          tma_load_2d(sb + pi * (kBK * 128), &mapB, &full_bar[s], n0 + pi * 32, k0);
+        } else {      // BN == 64: box {32 n, 16 k}: chunk pi/2, k-half pi%2
+          tma_load_2d(sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128), &mapB, &full_bar[s], n0 + (pi >> 1) * 32,
+                      k0 + (pi & 1) * 16);
         }
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
+    __syncwarp();
+  }
+  if (warp == 0) {
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
@@ -186,21 +196,23 @@ __global__ void __launch_bounds__(kTcThreads)
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait_spin(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + s * kStageBytes), sb = sa + kABytes;
+        for (int rep = 0; rep < p.mma_repeat; ++rep) {
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lt);
-          const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_acc, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lt);
+            const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_acc, da, db, idesc, (i | k | rep) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
       umma_commit(&tmem_full_bar);  // accumulator complete
     }
-  } else {
+  } else if (warp >= 2) {
     // ================= epilogue: TMEM -> registers -> global (8 warps) =================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // which half of the tile's columns
@@ -399,7 +411,10 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, c
   const size_t budget = (ctas <= sm_count() ? 200 : 100) * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
   stages = std::max(2, std::min({stages, kMaxStages, std::max(p.kb_per_split, 2)}));
+  if (const char *e = getenv("AIR_TC_STAGES")) stages = std::max(1, std::min(atoi(e), static_cast<int>(200 * 1024 / stage_bytes)));
   p.stages = stages;
+  p.mma_repeat = 1;
+  if (const char *e = getenv("AIR_TC_MMA_REPEAT")) p.mma_repeat = std::max(1, atoi(e));
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
   const size_t smem_max = static_cast<size_t>(kMaxStages) * stage_bytes + 1024 > 225 * 1024
                               ? static_cast<size_t>(200 * 1024 / stage_bytes) * stage_bytes + 1024
@@ -428,19 +443,34 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
               "(lda=%d ldb=%d)", lda, ldb);
   const bool a_mn = tA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = tB == 0;   // B stored [K,N]: N contiguous
-  const int64_t tiles128 = static_cast<int64_t>((M + kBM - 1) / kBM) * ((N + 127) / 128);
-  const int BN = (N > 64 && (tiles128 * 5 >= sm_count() * 3 || K >= 2048)) ? 128 : 64;
-
+  // Tile / split selection.  Measured on B200 (tests/diag_gemm_*.py): a CTA that is alone on its SM
+  // advances ~1 k-block per us whatever the ring depth, while co-resident CTAs each keep that rate, so the
+  // grid should put ~2 CTAs on every SM: 128-wide tiles when they still give >= 1 CTA per SM (half the
+  // L2 re-reads of the A operand), split-K for the very-long-K weight gradients, otherwise 64-wide tiles.
+  // (Splitting K on medium-K shapes was measured slower: the second pass costs more than it saves.)
+  const int sms = sm_count();
+  const int mt = (M + kBM - 1) / kBM;
+  const int64_t tiles128 = static_cast<int64_t>(mt) * ((N + 127) / 128), tiles64 = static_cast<int64_t>(mt) * ((N + 63) / 64);
   TcParams p;
   p.C = C; p.Cinit = Cinit; p.bias = bias; p.aux = aux;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epi;
   p.num_kb = (K + kBK - 1) / kBK;
-  const int64_t tiles = static_cast<int64_t>((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
-  int splits = 1;
-  if (tiles < sm_count() && p.num_kb >= 16 && N % 4 == 0) {
-    splits = static_cast<int>(std::min<int64_t>((2 * sm_count() + tiles - 1) / tiles, p.num_kb / 8));
-    splits = std::max(1, std::min(splits, 32));
+  const bool can_split = (N % 4 == 0);
+  auto want_splits = [&](int64_t tiles) {
+    int sp = static_cast<int>(std::min<int64_t>((2 * sms + tiles - 1) / tiles, p.num_kb / 8));
+    return std::max(1, std::min(sp, 32));
+  };
+  int BN, splits = 1;
+  if (N > 64 && tiles128 >= sms) {
+    BN = 128;  // at least one wide CTA per SM (most SMs get two)
+  } else if (N > 64 && can_split && p.num_kb >= 64) {
+    BN = 128;  // very long K, few tiles (weight gradients): wide tiles + split-K
+    splits = want_splits(tiles128);
+  } else {
+    BN = 64;   // twice the CTAs of the wide tiling
+    if (tiles64 < sms && can_split && p.num_kb >= 64) splits = want_splits(tiles64);
   }
+  if (const char *e = getenv("AIR_TC_BN")) BN = (atoi(e) == 64 || N <= 64) ? 64 : 128;  // tuning / diagnostics override
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   p.splits = splits;
@@ -454,11 +484,11 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
 
   CUtensorMap ma, mb;
   int rc;
-  if (!a_mn) rc = make_tmap(&ma, A, K, M, lda, kBK, kBM, false);  // [M,K] K contiguous: box {32 k, 128 m}
-  else       rc = make_tmap(&ma, A, M, K, lda, 32, kBK, true);    // [K,M] M contiguous: box {32 m, 32 k}
+  if (!a_mn) rc = make_tmap(&ma, A, K, M, lda, kBK, kBM / 4, false);  // [M,K] K contiguous: box {32 k, 32 m}
+  else       rc = make_tmap(&ma, A, M, K, lda, 32, kBK, true);        // [K,M] M contiguous: box {32 m, 32 k}
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap(&mb, B, K, N, ldb, kBK, BN, false);   // [N,K] K contiguous: box {32 k, BN n}
-  else       rc = make_tmap(&mb, B, N, K, ldb, 32, kBK, true);    // [K,N] N contiguous: box {32 n, 32 k}
+  if (!b_mn) rc = make_tmap(&mb, B, K, N, ldb, kBK, BN / 4, false);              // [N,K] K contiguous: box {32 k, BN/4 n}
+  else       rc = make_tmap(&mb, B, N, K, ldb, 32, BN == 128 ? kBK : 16, true);  // [K,N] N contiguous: box {32 n, 32|16 k}
   if (rc) return rc;
 
 #define AIR_TC_DISPATCH(BNv)                                                         \
