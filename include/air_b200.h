@@ -41,6 +41,9 @@ const char *air_last_error(void);     /* thread-local, never NULL */
 int air_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* number of kernels this library has launched on the calling thread (bench evidence) */
 int64_t air_launch_count(void);
+/* host-side CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of
+ * TensorFlow bundle checkpoints (training.py:141, 203-207 tf.train.Saver); used by checkpoint.py */
+uint32_t air_crc32c(const void *data, uint64_t nbytes, uint32_t crc);
 
 /* ---- Spatial Transformer: air/transformer.py:18 transformer(U, theta, out_size) ----
  * U [B,H,W,C] NHWC, theta [B,6] (row-major 2x3), out [B,oh,ow,C].

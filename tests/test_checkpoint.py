@@ -1,0 +1,129 @@
+"""TF-bundle checkpoint reader/writer, pinned against the reference's own
+model/air-model.index (decoded into tests/golden/air_model_index.json by make_index_fixture.py)."""
+import hashlib
+import importlib
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+import air_b200 as ab
+
+ck = importlib.import_module("tf-attend-infer-repeat_b200.checkpoint")
+
+
+@pytest.fixture(scope="module")
+def ref_index(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "air_model_index.json")))
+
+
+def test_writer_reproduces_the_reference_index_byte_for_byte(ref_index):
+    """Re-encoding the decoded entries gives exactly the file TensorFlow's Saver wrote (same SHA-256):
+    pins the table layout, prefix compression, restart points, block CRCs, index keys and footer."""
+    entries = OrderedDict((e["name"], ck.BundleEntry(e["dtype"], tuple(e["shape"]), e["shard_id"], e["offset"], e["size"],
+                                                     e["crc32c"])) for e in ref_index["entries"])
+    blob = ck.encode_index(entries)
+    assert len(blob) == ref_index["bytes"]
+    assert hashlib.sha256(blob).hexdigest() == ref_index["sha256"]
+
+
+def test_param_store_matches_reference_variable_names_and_shapes(ref_index):
+    """The 36 trainables, their 72 Adam slots, global_step and the beta powers: names, shapes and the
+    4,011,643-parameter total equal the shipped checkpoint."""
+    store = ab.ParamStore("cpu", 2500, 784, 256, 64, 50, (512, 256), (256, 512), seed=0)
+    mine = ck.model_tensors(store, scope="air", with_optimizer=True)
+    ref = {e["name"]: e for e in ref_index["entries"]}
+    assert set(mine) == set(ref)
+    for k, a in mine.items():
+        assert list(np.asarray(a).shape) == ref[k]["shape"], k
+        assert (1 if np.asarray(a).dtype.kind == "f" else 3) == ref[k]["dtype"], k
+        assert np.asarray(a).size * 4 == ref[k]["size"], k
+    trainables = [e for e in ref_index["entries"] if e["name"].startswith("air/rnn/")]
+    assert len(trainables) == 36 and sum(e["size"] // 4 for e in trainables) == 4011643
+    # the data shard of the reference copy is missing: offsets say it would be contiguous in key order
+    off = 0
+    for e in ref_index["entries"]:
+        assert e["offset"] == off
+        off += e["size"]
+
+
+def test_roundtrip_and_corruption_detection(tmp_path):
+    store = ab.ParamStore("cpu", 2500, 784, 256, 64, 50, (512, 256), (256, 512), seed=3)
+    store.global_step = 1234
+    store.adam_m.normal_()
+    store.adam_v.uniform_()
+    store.state[0], store.state[1] = 0.5, 0.25
+    prefix = str(tmp_path / "air-model-1234")
+    ck.save_model(store, prefix)
+    idx = ck.read_index(prefix + ".index")
+    assert len(idx) == 111 and idx["air/rnn/rnn/kernel"].shape == (2756, 1024)
+    other = ab.ParamStore("cpu", 2500, 784, 256, 64, 50, (512, 256), (256, 512), seed=4)
+    ck.restore_model(other, prefix)
+    for (k, a), b in zip(other.named_views().items(), store.named_views().values()):
+        assert torch.equal(a, b), k
+    (om, ov), (sm_, sv) = other.named_adam(), store.named_adam()
+    assert all(torch.equal(om[k], sm_[k]) and torch.equal(ov[k], sv[k]) for k in om)
+    assert other.global_step == 1234
+    assert other.state[0].item() == 0.5 and other.state[1].item() == 0.25
+    # flip one byte of a tensor -> CRC mismatch
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[idx["air/rnn/vae/gen_mean/biases"].offset + 5] ^= 0x40
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    with pytest.raises(ValueError, match="checksum"):
+        ck.load_checkpoint(prefix)
+    # flip one byte of the index -> block CRC mismatch
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    raw[100] ^= 1
+    open(prefix + ".index", "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        ck.read_index(prefix + ".index")
+
+
+def test_crc32c_known_answers():
+    assert ck.crc32c(b"123456789") == 0xE3069283          # standard CRC-32C check value
+    assert ck.crc32c(b"") == 0
+    assert ck.crc32c(b"\x00" * 32) == 0x8A9136AA          # RFC 3720 test vector
+    # the C (SSE4.2) and the pure-Python implementations agree, also when chained
+    data = bytes(range(256)) * 37 + b"tail"
+    t = ck._crc_table()
+    c = 0xFFFFFFFF
+    for b in data:
+        c = t[(c ^ b) & 0xFF] ^ (c >> 8)
+    assert ck.crc32c(data) == c ^ 0xFFFFFFFF
+    assert ck.crc32c(data[100:], ck.crc32c(data[:100])) == ck.crc32c(data)
+
+
+def test_multi_block_index(tmp_path):
+    """Small block size forces several data blocks and separator keys in the index block."""
+    tensors = {f"scope/var_{i:03d}/weights": np.full((3, 2), i, np.float32) for i in range(120)}
+    ents = OrderedDict()
+    off = 0
+    for k in sorted(tensors):
+        raw = tensors[k].tobytes()
+        ents[k] = ck.BundleEntry(1, (3, 2), 0, off, len(raw), ck.mask_crc(ck.crc32c(raw)))
+        off += len(raw)
+    blob = ck.encode_index(ents, block_size=512)
+    p = tmp_path / "multi.index"
+    p.write_bytes(blob)
+    back = ck.read_index(str(p))
+    assert list(back) == sorted(tensors) and back == ents
+
+
+def test_evaluation_summaries_host_logic():
+    """air_model.py:160-209 semantics on hand-built values (no GPU)."""
+    mw = importlib.import_module("tf-attend-infer-repeat_b200.demo.model_wrapper")
+    vals = torch.tensor([1.0, 2.0, 3.0, 4.0])
+    dig = torch.tensor([0, 1, 1, 2])
+    s = mw.summarize_by_digit_count(vals, dig, 2, "x")
+    assert s == {"x_0_dig": 1.0, "x_1_dig": 2.5, "x_2_dig": 4.0, "x_all_dig": 2.5}
+    per_step = torch.tensor([[1.0, 10.0], [2.0, 20.0], [3.0, 30.0]])
+    steps = torch.tensor([0, 1, 2])        # executed attention steps per item
+    tgt = torch.tensor([0, 1, 2])
+    st = mw.summarize_by_step(per_step, steps, tgt, max_steps=3, max_digits=2, name="kl")
+    assert st["kl_1_step_all_dig"] == 2.5 and st["kl_2_step_all_dig"] == 30.0     # only items with steps > i
+    assert np.isnan(st["kl_3_step_all_dig"])                                         # padded step, nobody ran it
+    st1 = mw.summarize_by_step(per_step, steps, tgt, 3, 2, "kl", one_more_step=True)
+    assert st1["kl_1_step_all_dig"] == 2.0 and st1["kl_2_step_all_dig"] == 25.0

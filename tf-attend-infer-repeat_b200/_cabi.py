@@ -20,6 +20,7 @@ _SIGS = {
     "air_abi_version": (ctypes.c_int, []),
     "air_last_error": (ctypes.c_char_p, []),
     "air_launch_count": (ctypes.c_int64, []),
+    "air_crc32c": (ctypes.c_uint32, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32]),
     "air_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
     "air_st_forward": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
     "air_st_backward": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),

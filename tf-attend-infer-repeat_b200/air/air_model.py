@@ -376,6 +376,17 @@ class AIRModel:
         self.loss_per_item = w["loss_item"]
         self.loss, self.accuracy = w["out2"][0], w["out2"][1]
 
+    def save(self, prefix, with_optimizer=True):
+        """Write a TensorFlow-bundle checkpoint (``prefix.index`` + ``prefix.data-00000-of-00001``) with the
+        reference's variable names -- what tf.train.Saver.save does in training.py:203-207."""
+        from .. import checkpoint
+        return checkpoint.save_model(self.store, prefix, scope=self.scope, with_optimizer=with_optimizer)
+
+    def restore(self, prefix, verify_crc=True):
+        """Load a checkpoint written by the reference or by save() (demo.py:33, embeddings.py:168)."""
+        from .. import checkpoint
+        return checkpoint.restore_model(self.store, prefix, scope=self.scope, verify_crc=verify_crc)
+
     @property
     def rec_shifts(self):
         """[B, T, 2] (air_model.py:570); a fresh stack of the x / y field rows."""

@@ -1,4 +1,5 @@
 // Library plumbing for libair_b200.so: error strings, launch counter, device info.
+#include <nmmintrin.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -72,4 +73,16 @@ extern "C" int air_device_info(int *sm_count, int *cc_major, int *cc_minor) {
   }
   air::set_error("air_device_info: %s (no CUDA device; this library has no CPU fallback)", cudaGetErrorString(e));
   return AIR_ERR_CUDA;
+}
+
+extern "C" uint32_t air_crc32c(const void *data, uint64_t nbytes, uint32_t crc) {
+  const unsigned char *p = static_cast<const unsigned char *>(data);
+  uint64_t c = crc ^ 0xFFFFFFFFu;
+  while (nbytes && (reinterpret_cast<uintptr_t>(p) & 7)) {
+    c = _mm_crc32_u8(static_cast<uint32_t>(c), *p++);
+    --nbytes;
+  }
+  for (; nbytes >= 8; nbytes -= 8, p += 8) c = _mm_crc32_u64(c, *reinterpret_cast<const uint64_t *>(p));
+  for (; nbytes; --nbytes) c = _mm_crc32_u8(static_cast<uint32_t>(c), *p++);
+  return static_cast<uint32_t>(c) ^ 0xFFFFFFFFu;
 }
