@@ -227,20 +227,19 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// out[e] (+)= sum_r partials[r*stride + e], r in increasing order (deterministic)
+// out[e] (+)= sum_r partials[r*stride + e]: one warp per output element, lane l adds rows l, l+32, ...
+// in increasing order and the 32 lane sums are combined by a fixed shuffle tree (deterministic).
 __global__ void __launch_bounds__(256)
     reduce_rows_k(const float *__restrict__ partials, int R, int stride, int n, float *out, int accumulate) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
-  AIR_GRID_STRIDE(e, n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t e = warp0; e < n; e += nwarps) {
     float acc = 0.0f;
-    int r = 0;
-    for (; r + 4 <= R; r += 4) {  // four loads in flight, summed in row order
-      const float a = partials[static_cast<int64_t>(r) * stride + e], b = partials[static_cast<int64_t>(r + 1) * stride + e];
-      const float c = partials[static_cast<int64_t>(r + 2) * stride + e], d = partials[static_cast<int64_t>(r + 3) * stride + e];
-      acc = (((acc + a) + b) + c) + d;
-    }
-    for (; r < R; ++r) acc += partials[static_cast<int64_t>(r) * stride + e];
-    out[e] = accumulate ? out[e] + acc : acc;
+    for (int r = lane; r < R; r += 32) acc += partials[static_cast<int64_t>(r) * stride + e];
+    acc = warp_sum(acc);
+    if (lane == 0) out[e] = accumulate ? out[e] + acc : acc;
   }
 }
 
@@ -541,8 +540,8 @@ extern "C" int air_heads_bwd(const float *hidden, const float *w_out, const floa
   int rc = check_launch("heads_bwd");
   if (rc) return rc;
   const int n = 7 * HU;
-  AIR_LAUNCH(reduce_rows_k, grid_for(n, 256), 256, 0, ST(stream), workspace, R, n + 7, n, dw_out, accumulate);
-  AIR_LAUNCH(reduce_rows_k, 1, 32, 0, ST(stream), workspace + n, R, n + 7, 7, db_out, accumulate);
+  AIR_LAUNCH(reduce_rows_k, grid_for(static_cast<int64_t>(n) * 32, 256), 256, 0, ST(stream), workspace, R, n + 7, n, dw_out, accumulate);
+  AIR_LAUNCH(reduce_rows_k, 1, 256, 0, ST(stream), workspace + n, R, n + 7, 7, db_out, accumulate);
   count_launch(2);
   return check_launch("heads_bwd reduce");
 }
@@ -625,7 +624,7 @@ extern "C" int air_colsum(const float *X, int ld, float *out, int accumulate, fl
   count_launch();
   int rc = check_launch("colsum_partial");
   if (rc) return rc;
-  AIR_LAUNCH(reduce_rows_k, grid_for(N, 256), 256, 0, ST(stream), workspace, R, N, N, out, accumulate);
+  AIR_LAUNCH(reduce_rows_k, grid_for(static_cast<int64_t>(N) * 32, 256), 256, 0, ST(stream), workspace, R, N, N, out, accumulate);
   count_launch();
   return check_launch("colsum reduce");
 }

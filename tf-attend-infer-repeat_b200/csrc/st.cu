@@ -348,13 +348,12 @@ __global__ void __launch_bounds__(kBwdThreads)
   if (tid < 6) sTh[tid] = __ldg(th_g + tid);
   if (tid == 6) sTh[6] = (__ldg(th_g + 1) == 0.0f && __ldg(th_g + 3) == 0.0f) ? 1.0f : 0.0f;
   for (int k = tid; k < OW + OH; k += kBwdThreads) {
-    if (k < OW) {
-      sCol[k] = sep_ent(__ldg(th_g + 0), __ldg(th_g + 2), k, OW, W, 1);
-      sGrid[k] = linspace_pm1(k, OW);
-    } else {
-      sRow[k - OW] = sep_ent(__ldg(th_g + 4), __ldg(th_g + 5), k - OW, OH, H, W);
-      sGrid[k] = linspace_pm1(k - OW, OH);
-    }
+    const bool col = k < OW;
+    const float gk = col ? linspace_pm1(k, OW) : linspace_pm1(k - OW, OH);
+    const float diag = __ldg(th_g + (col ? 0 : 4)), trans = __ldg(th_g + (col ? 2 : 5));
+    const Ent e = make_ent(to_pixel(add_rn(mul_rn(diag, gk), trans), col ? W : H), col ? W : H, col ? 1 : W);
+    if (col) sCol[k] = e; else sRow[k - OW] = e;
+    sGrid[k] = gk;
   }
   __syncthreads();
   const bool sep = sTh[6] != 0.0f;
@@ -420,16 +419,16 @@ __global__ void __launch_bounds__(kBwdThreads)
       }
       g *= zval;  // d(z * v)/dv
     }
-    const float dwa = g * Ia, dwb = g * Ib, dwc = g * Ic, dwd = g * Id;
-    const float dx = ((-(dwa * re.w1) - dwb * re.w0) + dwc * re.w1) + dwd * re.w0;
-    const float dy = ((-(dwa * ce.w1) + dwb * ce.w1) - dwc * ce.w0) + dwd * ce.w0;
-    const float dxs = dx * 0.5f * wf, dys = dy * 0.5f * hf;
-    acc[0] += dxs * xt;
-    acc[1] += dxs * yt;
-    acc[2] += dxs;
-    acc[3] += dys * xt;
-    acc[4] += dys * yt;
-    acc[5] += dys;
+    // d out / d x = wy1 (Ic - Ia) + wy0 (Id - Ib),  d out / d y = wx1 (Ib - Ia) + wx0 (Id - Ic)
+    // (the factors 0.5 (W - 1.001) and 0.5 (H - 1.001) of :75-76 are applied once, after the reduction)
+    const float dx = g * (re.w1 * (Ic - Ia) + re.w0 * (Id - Ib));
+    const float dy = g * (ce.w1 * (Ib - Ia) + ce.w0 * (Id - Ic));
+    acc[0] += dx * xt;
+    acc[1] += dx * yt;
+    acc[2] += dx;
+    acc[3] += dy * xt;
+    acc[4] += dy * yt;
+    acc[5] += dy;
     if (dU && !sep) {
       atomicAdd(&sT[re.i0 + ce.i0], mul_rn(ce.w1, re.w1) * g);
       atomicAdd(&sT[re.i1 + ce.i0], mul_rn(ce.w1, re.w0) * g);
@@ -441,8 +440,9 @@ __global__ void __launch_bounds__(kBwdThreads)
   block_sum_many<7>(acc, (dU && !sep) ? sScr : sT);
   if (tid == 0) {
     float *d = dtheta + b * 6;
+    const float sx = 0.5f * wf, sy = 0.5f * hf;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) d[k] = acc[k];
+    for (int k = 0; k < 6; ++k) d[k] = acc[k] * (k < 3 ? sx : sy);
     if (FUSED && dz && (!sep || !dU)) dz[b] = acc[6];
   }
   if (!dU) return;
