@@ -117,7 +117,7 @@ class AIRModel:
             ops.set_gemm_workspace(AIRModel._gemm_ws)
         self._graphs = None
         self.noise = None
-        self.rec_num_digits = self.rec_scales = self.reconstruction = None
+        self.rec_num_digits = self.rec_scales = None
         self.loss = self.accuracy = None
         self.training = self.train_step if train else None
 
@@ -235,7 +235,9 @@ class AIRModel:
             ops.writeback_canvas_fwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
                                      self.stopping_threshold, w["canvas"], w["canvas"], wsz, wsz, cs, cs)
         dscale = 1.0 / (B * self.world)
-        ops.bce_loss(w["canvas"], x, w["reconstruction"], w["rec_loss"], w["dcanvas"] if self.train else None, dscale)
+        # the clipped reconstruction is only an output: written in inference, derived lazily in training
+        ops.bce_loss(w["canvas"], x, None if self.train else w["reconstruction"], w["rec_loss"],
+                     w["dcanvas"] if self.train else None, dscale)
         ops.finalize_loss(w["loss"], w["rec_loss"], w["digits"], self.target_num_digits, w["out2"], w["loss_item"])
 
     def _vae_buf(self, t):
@@ -371,7 +373,6 @@ class AIRModel:
         self.z_pres_probs, self.z_pres_kls = col(C.F_ZPROB), col(C.F_KL_Z)
         self.scale_kls, self.shift_kls, self.vae_kls = col(C.F_KL_SCALE), col(C.F_KL_SHIFT), col(C.F_KL_VAE)
         self.z_pres = col(C.F_Z)
-        self.reconstruction = w["reconstruction"]
         self.reconstruction_loss = w["rec_loss"]
         self.loss_per_item = w["loss_item"]
         self.loss, self.accuracy = w["out2"][0], w["out2"][1]
@@ -386,6 +387,14 @@ class AIRModel:
         """Load a checkpoint written by the reference or by save() (demo.py:33, embeddings.py:168)."""
         from .. import checkpoint
         return checkpoint.restore_model(self.store, prefix, scope=self.scope, verify_crc=verify_crc)
+
+    @property
+    def reconstruction(self):
+        """clip(canvas, 0, 1) (air_model.py:582).  Inference writes it in the loss kernel; a training model
+        derives it on access so the train step does not spend 41 MB of HBM writes on an unused output."""
+        if self.train:
+            return torch.clamp(self.w["canvas"], 0.0, 1.0)
+        return self.w["reconstruction"]
 
     @property
     def rec_shifts(self):
