@@ -68,10 +68,12 @@ int air_st_writeback_canvas_fwd(const float *window, const float *theta_inv, con
                                 int ch, int cw, air_stream_t stream);
 
 /* Backward: dcanvas [B,ch,cw] is d(loss)/d(canvas_out) (== d/d(canvas_in), not rewritten).
- * Writes dwindow [B,wh,ww], dtheta_inv [B,6], dz [B]; all zero for rows with stop_new >= thr. */
+ * Writes dwindow [B,wh,ww], dtheta_inv [B,6], dz [B]; all zero for rows with stop_new >= thr.
+ * window_is_sigmoid != 0: the window is a sigmoid output w (vae.py:39-41) and dwindow receives the gradient
+ * w.r.t. its PRE-sigmoid input, dwindow * w * (1 - w) -- the SigmoidGrad op fused into the final store. */
 int air_st_writeback_canvas_bwd(const float *window, const float *theta_inv, const float *z, const float *stop_new,
                                 float thr, const float *dcanvas, float *dwindow, float *dtheta_inv, float *dz,
-                                int64_t B, int wh, int ww, int ch, int cw, air_stream_t stream);
+                                int window_is_sigmoid, int64_t B, int wh, int ww, int ch, int cw, air_stream_t stream);
 
 /* ---- Concrete / ACT step: concrete.py:20-43 + air_model.py:380-427 -----------------
  * y = (log_odds + log(u+eps) - log(1-u+eps)) / temperature ; z = sigmoid(y) (rounded
@@ -108,6 +110,7 @@ int air_concrete_step_bwd(const float *log_odds, const float *y, const float *z,
 #define AIR_EPI_SOFTPLUS 2      /* tf.nn.softplus: x>13.94->x, x<-13.94->exp(x), else log(exp(x)+1) */
 #define AIR_EPI_MUL_DRELU 3     /* out = v * (aux > 0)            (ReLU backward, aux = ReLU output) */
 #define AIR_EPI_MUL_DSOFTPLUS 4 /* out = v * (1 - exp(-aux))      (softplus backward, aux = softplus output) */
+#define AIR_EPI_SIGMOID_NOISE 5 /* out = sigmoid(v + aux * epi_param): vae.py:36-41 (aux = N(0,1) noise, epi_param = likelihood std) */
 #define AIR_GEMM_FP32_EXACT 0
 #define AIR_GEMM_TF32 1
 /* AIR_GEMM_TF32 needs 16-byte aligned A / B with lda, ldb multiples of 4 (TMA).  GEMMs with few
@@ -118,6 +121,10 @@ int air_gemm_set_workspace(float *workspace, int64_t nfloats);
 int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
              int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue, int mode,
              air_stream_t stream);
+/* same, with the scalar parameter some epilogues take (AIR_EPI_SIGMOID_NOISE: the likelihood std) */
+int air_gemm_ex(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
+                int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue,
+                float epi_param, int mode, air_stream_t stream);
 
 /* ---- fused model-specific elementwise kernels (air/air_model.py loop body) ----------
  * Hyper-parameters that are plain Python floats in the reference constructor

@@ -26,12 +26,13 @@ _SIGS = {
     "air_st_backward": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
     "air_st_writeback_canvas_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_float] + [_c_f] * 2 + [ctypes.c_int64] +
                                     [ctypes.c_int] * 4 + [_c_f]),
-    "air_st_writeback_canvas_bwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_float] + [_c_f] * 4 + [ctypes.c_int64] +
+    "air_st_writeback_canvas_bwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_float] + [_c_f] * 4 + [ctypes.c_int, ctypes.c_int64] +
                                     [ctypes.c_int] * 4 + [_c_f]),
     "air_concrete_step_fwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_float, ctypes.c_int] + [_c_f] * 7 +
                               [ctypes.c_int64, _c_f]),
     "air_concrete_step_bwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
     "air_gemm": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 9 + [_c_f]),
+    "air_gemm_ex": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 8 + [ctypes.c_float, ctypes.c_int, _c_f]),
     "air_gemm_set_workspace": (ctypes.c_int, [_c_f, ctypes.c_int64]),
     "air_lstm_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_lstm_bwd": (ctypes.c_int, [_c_f] * 8 + [ctypes.c_int64, ctypes.c_int, _c_f]),
@@ -65,7 +66,7 @@ class Hyper(ctypes.Structure):
 (F_SCALE_MEAN, F_SCALE_LV, F_SHIFT_MEAN_X, F_SHIFT_MEAN_Y, F_SHIFT_LV_X, F_SHIFT_LV_Y, F_LOG_ODDS, F_S, F_X, F_Y,
  F_YPRE, F_Z, F_ZPROB, F_KL_Z, F_KL_SCALE, F_KL_SHIFT, F_KL_VAE, F_STOP_PREV, F_STOP_NEW) = range(19)
 NF = 20
-EPI_NONE, EPI_RELU, EPI_SOFTPLUS, EPI_MUL_DRELU, EPI_MUL_DSOFTPLUS = range(5)
+EPI_NONE, EPI_RELU, EPI_SOFTPLUS, EPI_MUL_DRELU, EPI_MUL_DSOFTPLUS, EPI_SIGMOID_NOISE = range(6)
 GEMM_MODES = {"fp32": 0, "tf32": 1}
 
 _lib = None

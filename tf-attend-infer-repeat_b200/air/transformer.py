@@ -88,7 +88,7 @@ class _WritebackCanvasFunction(torch.autograd.Function):
         dz = torch.empty_like(z)
         _cabi.check(_cabi.lib().air_st_writeback_canvas_bwd(
             _cabi.ptr(window), _cabi.ptr(th6), _cabi.ptr(z), _cabi.ptr(stop_new), ctx.thr, _cabi.ptr(dcanvas),
-            _cabi.ptr(dwindow), _cabi.ptr(dtheta), _cabi.ptr(dz), B, wh, ww, ch, cw, _cabi.stream()),
+            _cabi.ptr(dwindow), _cabi.ptr(dtheta), _cabi.ptr(dz), 0, B, wh, ww, ch, cw, _cabi.stream()),
             "air_st_writeback_canvas_bwd")
         return dwindow, dtheta.reshape(ctx.theta_shape), dz, None, dcanvas, None
 

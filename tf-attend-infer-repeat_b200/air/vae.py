@@ -54,8 +54,9 @@ def vae_forward(x, w: VAEWeights, noise_latent, noise_like, likelihood_std, hype
     for (W, b), out in zip(w.gen, buf["dec"]):
         ops.gemm(a, W, out, bias=b, epi=C.EPI_SOFTPLUS, mode=mode)
         a = out
-    ops.gemm(a, w.gm[0], gen_tmp, bias=w.gm[1], mode=mode)
-    ops.sigmoid_noise_fwd(gen_tmp, noise_like, likelihood_std, buf["recon"])
+    # gen_mean layer with the noisy-sigmoid output fused into the GEMM epilogue (vae.py:33-41)
+    ops.gemm(a, w.gm[0], buf["recon"], bias=w.gm[1], aux=noise_like, epi=C.EPI_SIGMOID_NOISE, epi_param=likelihood_std,
+             mode=mode)
     return buf["recon"]
 
 
@@ -72,12 +73,14 @@ def dense_dw(x_in, dY, gW, gb, colsum_ws, mode, accumulate=False):
     ops.colsum(dY, gb, accumulate, colsum_ws)
 
 
-def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fields, mode, dx_out=None):
+def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fields, mode, dx_out=None,
+                    dgen_is_presigmoid=False):
     """Backward through one VAE evaluation, activations only (air/vae.py:9-41 reversed).
     dbuf['dgen'] holds d(loss)/d(reconstruction) on entry; on exit dbuf holds the gradient
     w.r.t. every layer's pre-activation output (dgen, ddec[i], dml, denc[i]) -- the dY
     operands of the deferred weight-gradient GEMMs (vae_weight_grads)."""
-    ops.sigmoid_bwd(buf["recon"], dbuf["dgen"], dbuf["dgen"])  # d gen_mean, in place
+    if not dgen_is_presigmoid:  # (AIRModel's write-back backward already applied recon * (1 - recon))
+        ops.sigmoid_bwd(buf["recon"], dbuf["dgen"], dbuf["dgen"])  # d gen_mean, in place
     dY = dbuf["dgen"]
     acts = [buf["zs"]] + list(buf["dec"])
     layers = list(w.gen) + [w.gm]

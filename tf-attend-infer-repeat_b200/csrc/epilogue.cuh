@@ -15,8 +15,9 @@ __device__ __forceinline__ float softplus_tf(float x) {
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, add_rn(1.0f, expf(-x))); }
 
-__device__ __forceinline__ float apply_epilogue(float v, int epi, float aux) {
+__device__ __forceinline__ float apply_epilogue(float v, int epi, float aux, float param = 0.0f) {
   switch (epi) {
+    case AIR_EPI_SIGMOID_NOISE: return sigmoid_f(add_rn(v, mul_rn(aux, param)));
     case AIR_EPI_RELU: return fmaxf(v, 0.0f);
     case AIR_EPI_SOFTPLUS: return softplus_tf(v);
     case AIR_EPI_MUL_DRELU: return aux > 0.0f ? v : 0.0f;
@@ -34,8 +35,12 @@ __device__ __forceinline__ float softplus_tf_branchless(float x) {
   return x > -thr ? x : (x < thr ? e : mid);
 }
 
-__device__ __forceinline__ void apply_epilogue16(float (&v)[16], const float (&ax)[16], int epi) {
+__device__ __forceinline__ void apply_epilogue16(float (&v)[16], const float (&ax)[16], int epi, float param) {
   switch (epi) {
+    case AIR_EPI_SIGMOID_NOISE:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = sigmoid_f(add_rn(v[j], mul_rn(ax[j], param)));
+      break;
     case AIR_EPI_RELU:
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);

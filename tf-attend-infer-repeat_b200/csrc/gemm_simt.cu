@@ -19,7 +19,7 @@ template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
 __global__ void __launch_bounds__(256)
     gemm_simt(const float *__restrict__ A, const float *__restrict__ Bm, float *C, const float *Cinit,
               const float *__restrict__ bias, const float *aux, int M, int N, int K, int lda, int ldb, int ldc,
-              int epi) {
+              int epi, float epi_param) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
   static_assert(TM % 2 == 0 && TN % 2 == 0, "split tiles");
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256)
       const int64_t o = static_cast<int64_t>(m) * ldc + n;
       float v = acc[i][j];
       if (bias) v = add_rn(v, __ldg(bias + n));
-      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f);
+      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f, epi_param);
     }
   }
 }
@@ -116,53 +116,60 @@ __global__ void __launch_bounds__(256)
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_simt(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
                        const float *aux, int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi,
-                       cudaStream_t s) {
+                       float epi_param, cudaStream_t s) {
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   if (!tA && !tB)
-    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, false, false>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, false, false>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi, epi_param);
   else if (!tA && tB)
-    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, false, true>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, false, true>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi, epi_param);
   else if (tA && !tB)
-    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, true, false>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, true, false>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi, epi_param);
   else
-    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, true, true>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi);
+    AIR_LAUNCH((gemm_simt<BM, BN, BK, TM, TN, true, true>), grid, 256, 0, s, A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, epi, epi_param);
   count_launch();
   return check_launch("gemm_simt");
 }
 
 int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
-                    int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, cudaStream_t s) {
+                    int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s) {
   // big tiles when they still fill the machine, small tiles otherwise
   const int64_t big_ctas = static_cast<int64_t>((M + 127) / 128) * ((N + 127) / 128);
   if (N > 64 && M > 64 && big_ctas >= sm_count())
-    return launch_simt<128, 128, 16, 8, 8>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, s);
-  return launch_simt<64, 64, 16, 4, 4>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, s);
+    return launch_simt<128, 128, 16, 8, 8>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, epi_param, s);
+  return launch_simt<64, 64, 16, 4, 4>(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, epi_param, s);
 }
 
 int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux, int M,
-              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, cudaStream_t s);
+              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s);
 
 }  // namespace air
 
-extern "C" int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
-                        const float *aux, int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
-                        int epilogue, int mode, air_stream_t stream) {
+extern "C" int air_gemm_ex(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
+                           const float *aux, int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                           int epilogue, float epi_param, int mode, air_stream_t stream) {
   AIR_REQUIRE(M >= 0 && N >= 0 && K >= 0 && M < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "air_gemm: bad shape M=%lld N=%d K=%d",
               (long long)M, N, K);
   if (M == 0 || N == 0) return AIR_OK;
   AIR_REQUIRE(A && B && C, AIR_ERR_NULL, "air_gemm: null pointer");
   AIR_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, AIR_ERR_BAD_SHAPE,
               "air_gemm: leading dimension too small (lda=%d ldb=%d ldc=%d)", lda, ldb, ldc);
-  AIR_REQUIRE(epilogue >= AIR_EPI_NONE && epilogue <= AIR_EPI_MUL_DSOFTPLUS, AIR_ERR_BAD_SHAPE, "air_gemm: bad epilogue %d",
+  AIR_REQUIRE(epilogue >= AIR_EPI_NONE && epilogue <= AIR_EPI_SIGMOID_NOISE, AIR_ERR_BAD_SHAPE, "air_gemm: bad epilogue %d",
               epilogue);
-  AIR_REQUIRE((epilogue != AIR_EPI_MUL_DRELU && epilogue != AIR_EPI_MUL_DSOFTPLUS) || aux, AIR_ERR_NULL,
-              "air_gemm: epilogue %d needs aux", epilogue);
+  AIR_REQUIRE((epilogue != AIR_EPI_MUL_DRELU && epilogue != AIR_EPI_MUL_DSOFTPLUS && epilogue != AIR_EPI_SIGMOID_NOISE) || aux,
+              AIR_ERR_NULL, "air_gemm: epilogue %d needs aux", epilogue);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (mode == AIR_GEMM_FP32_EXACT)
     return air::gemm_fp32_exact(A, B, C, Cinit, bias, aux, static_cast<int>(M), N, K, lda, ldb, ldc, transA, transB,
-                                epilogue, s);
+                                epilogue, epi_param, s);
   if (mode == AIR_GEMM_TF32)
-    return air::gemm_tf32(A, B, C, Cinit, bias, aux, static_cast<int>(M), N, K, lda, ldb, ldc, transA, transB, epilogue, s);
+    return air::gemm_tf32(A, B, C, Cinit, bias, aux, static_cast<int>(M), N, K, lda, ldb, ldc, transA, transB, epilogue,
+                          epi_param, s);
   air::set_error("air_gemm: unknown mode %d", mode);
   return AIR_ERR_UNSUPPORTED;
+}
+
+extern "C" int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
+                        const float *aux, int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                        int epilogue, int mode, air_stream_t stream) {
+  return air_gemm_ex(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, transA, transB, epilogue, 0.0f, mode, stream);
 }

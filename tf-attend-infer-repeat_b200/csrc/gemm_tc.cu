@@ -107,6 +107,7 @@ struct TcParams {
   const float *bias;
   const float *aux;
   int M, N, K, ldc, epi;
+  float epi_param;
   int kb_per_split, num_kb, splits;
   int stages;  // TMA->MMA ring depth (<= kMaxStages)
   int mma_repeat;  // diagnostics only (AIR_TC_MMA_REPEAT): re-issue each k-block's MMAs (results are then wrong)
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads)
         if (!partial) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = (v[j] + ci[j]) + bi[j];
-          apply_epilogue16(v, ax, p.epi);
+          apply_epilogue16(v, ax, p.epi, p.epi_param);
         }
         float4 *dst = reinterpret_cast<float4 *>(Cout + static_cast<int64_t>(row) * ldo + nb);
 #pragma unroll
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads)
               const int64_t oo = static_cast<int64_t>(row) * p.ldc + n;
               if (p.Cinit) v += p.Cinit[oo];
               if (p.bias) v += __ldg(p.bias + n);
-              v = apply_epilogue(v, p.epi, p.aux ? p.aux[oo] : 0.0f);
+              v = apply_epilogue(v, p.epi, p.aux ? p.aux[oo] : 0.0f, p.epi_param);
             }
             Cout[static_cast<int64_t>(row) * ldo + n] = v;
           }
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(kTcThreads)
 // float4 per thread, splits loop unrolled 4x so the partial loads are in flight together.
 __global__ void __launch_bounds__(256)
     splitk_reduce_kernel(const float *__restrict__ ws, int splits, float *C, const float *Cinit,
-                         const float *__restrict__ bias, const float *aux, int M, int N, int ldc, int epi) {
+                         const float *__restrict__ bias, const float *aux, int M, int N, int ldc, int epi, float epi_param) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
   const int64_t total = static_cast<int64_t>(M) * N;  // N % 4 == 0 on this path
   const int64_t nvec = total >> 2;
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(256)
       float v = vals[j];
       if (Cinit) v += Cinit[o];
       if (bias) v += __ldg(bias + n + j);
-      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f);
+      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f, epi_param);
     }
   }
 }
@@ -432,12 +433,12 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, c
 }
 
 int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
-                    int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, cudaStream_t s);
+                    int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s);
 
 int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux, int M,
-              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, cudaStream_t s) {
+              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s) {
   if (K == 0)  // no products at all: C = epi(Cinit + bias); nothing for the tensor cores to do
-    return gemm_fp32_exact(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, s);
+    return gemm_fp32_exact(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, epi_param, s);
   AIR_REQUIRE(aligned16(A) && aligned16(B) && (lda % 4 == 0) && (ldb % 4 == 0), AIR_ERR_BAD_ALIGN,
               "air_gemm(TF32): TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4 "
               "(lda=%d ldb=%d)", lda, ldb);
@@ -453,7 +454,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   const int64_t tiles128 = static_cast<int64_t>(mt) * ((N + 127) / 128), tiles64 = static_cast<int64_t>(mt) * ((N + 63) / 64);
   TcParams p;
   p.C = C; p.Cinit = Cinit; p.bias = bias; p.aux = aux;
-  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epi;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epi; p.epi_param = epi_param;
   p.num_kb = (K + kBK - 1) / kBK;
   const bool can_split = (N % 4 == 0);
   auto want_splits = [&](int64_t tiles) {
@@ -500,7 +501,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   if (splits > 1) {
     const int64_t total = static_cast<int64_t>(M) * N / 4;
     const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
-    AIR_LAUNCH(splitk_reduce_kernel, blocks, 256, 0, s, ws, splits, C, Cinit, bias, aux, M, N, ldc, epi);
+    AIR_LAUNCH(splitk_reduce_kernel, blocks, 256, 0, s, ws, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param);
     count_launch();
     rc = check_launch("splitk_reduce");
   }

@@ -372,8 +372,15 @@ __global__ void __launch_bounds__(256)
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk;
   const int64_t r1 = (r0 + rows_per_chunk < B) ? r0 + rows_per_chunk : B;
   float acc = 0.0f;
-  if (col < N)
-    for (int64_t r = r0 + w; r < r1; r += 8) acc += X[r * ld + col];
+  if (col < N) {
+    int64_t r = r0 + w;
+    for (; r + 56 < r1; r += 64) {  // 8 independent loads in flight per lane, summed in row order
+      const float v0 = X[r * ld + col], v1 = X[(r + 8) * ld + col], v2 = X[(r + 16) * ld + col], v3 = X[(r + 24) * ld + col];
+      const float v4 = X[(r + 32) * ld + col], v5 = X[(r + 40) * ld + col], v6 = X[(r + 48) * ld + col], v7 = X[(r + 56) * ld + col];
+      acc = (((((((acc + v0) + v1) + v2) + v3) + v4) + v5) + v6) + v7;
+    }
+    for (; r < r1; r += 8) acc += X[r * ld + col];
+  }
   red[w][lane] = acc;
   __syncthreads();
   if (w == 0 && col < N) {

@@ -264,6 +264,8 @@ constexpr int kBwdWarps = kBwdThreads / 32;
 template <int NV>
 __device__ __forceinline__ void block_sum_many(float (&v)[NV], float *scratch /*[NV][kBwdThreads]*/) {
   static_assert(NV * kBwdWarps <= 32, "one warp finishes the reduction");
+  __shared__ float totals[8];  // separate from the scratch the same warp is still reading (racecheck-clean)
+  __syncthreads();             // previous users of `totals` (an earlier reduction of this CTA) are done
   const int tid = threadIdx.x;
 #pragma unroll
   for (int k = 0; k < NV; ++k) scratch[k * kBwdThreads + tid] = v[k];
@@ -277,11 +279,11 @@ __device__ __forceinline__ void block_sum_many(float (&v)[NV], float *scratch /*
     }
     t += __shfl_xor_sync(0xffffffffu, t, 1);
     t += __shfl_xor_sync(0xffffffffu, t, 2);
-    if (tid < NV * kBwdWarps && (tid % kBwdWarps) == 0) scratch[tid / kBwdWarps] = t;  // after all reads of this warp
+    if (tid < NV * kBwdWarps && (tid % kBwdWarps) == 0) totals[tid / kBwdWarps] = t;
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = scratch[k];
+  for (int k = 0; k < NV; ++k) v[k] = totals[k];
 }
 
 __device__ __forceinline__ float block_sum(float v, float *red /*[kBwdWarps]*/) {  // generic kernel helper
@@ -300,7 +302,7 @@ template <int H_, int W_, int OH_, int OW_, bool FUSED>
 __global__ void __launch_bounds__(kBwdThreads)
     st_bwd_staged(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dout,
                   const float *__restrict__ zp, const float *__restrict__ stop, float thr, float *__restrict__ dU,
-                  float *__restrict__ dtheta, float *__restrict__ dz, int64_t B, int rH, int rW, int rOH, int rOW) {
+                  float *__restrict__ dtheta, float *__restrict__ dz, int sig, int64_t B, int rH, int rW, int rOH, int rOW) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
   const int H = H_ ? H_ : rH, W = W_ ? W_ : rW, OH = OH_ ? OH_ : rOH, OW = OW_ ? OW_ : rOW;
   const int HW = H * W, OHW = OH * OW;
@@ -448,7 +450,10 @@ __global__ void __launch_bounds__(kBwdThreads)
   if (!dU) return;
 
   if (!sep) {
-    for (int k = tid; k < HW; k += kBwdThreads) dU[b * HW + k] = sT[k];
+    for (int k = tid; k < HW; k += kBwdThreads) {
+      const float u = sU[k];
+      dU[b * HW + k] = sig ? sT[k] * u * (1.0f - u) : sT[k];
+    }
     return;
   }
 
@@ -523,11 +528,12 @@ __global__ void __launch_bounds__(kBwdThreads)
   float dot[1] = {0.0f};
   for (int k = tid; k < (HW >> 2); k += kBwdThreads) {
     float4 v = *reinterpret_cast<const float4 *>(sTile + 4 * k);
-    if (FUSED) {
-      const float4 u = *reinterpret_cast<const float4 *>(sU + 4 * k);
-      dot[0] += ((v.x * u.x + v.y * u.y) + v.z * u.z) + v.w * u.w;
-    }
+    const float4 u = *reinterpret_cast<const float4 *>(sU + 4 * k);
+    if (FUSED) dot[0] += ((v.x * u.x + v.y * u.y) + v.z * u.z) + v.w * u.w;
     v.x *= zs; v.y *= zs; v.z *= zs; v.w *= zs;
+    if (sig) {  // SigmoidGrad of the window fused into the store: d/d(pre-sigmoid) = d/dw * w (1 - w)
+      v.x *= u.x * (1.0f - u.x); v.y *= u.y * (1.0f - u.y); v.z *= u.z * (1.0f - u.z); v.w *= u.w * (1.0f - u.w);
+    }
     dst[k] = v;
   }
   if (FUSED && dz) {
@@ -665,7 +671,7 @@ static size_t bwd_smem_bytes(int H, int W, int OH, int OW, bool need_dU) {
 
 template <int H_, int W_, int OH_, int OW_, bool FUSED>
 static int launch_bwd_staged(const float *U, const float *theta, const float *dout, const float *z, const float *stop,
-                             float thr, float *dU, float *dtheta, float *dz, int64_t B, int H, int W, int OH, int OW,
+                             float thr, float *dU, float *dtheta, float *dz, int sig, int64_t B, int H, int W, int OH, int OW,
                              cudaStream_t s) {
   auto kern = st_bwd_staged<H_, W_, OH_, OW_, FUSED>;
   const size_t smem = bwd_smem_bytes(H, W, OH, OW, dU != nullptr);
@@ -673,13 +679,13 @@ static int launch_bwd_staged(const float *U, const float *theta, const float *do
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_bwd_staged): %s", cudaGetErrorString(e));
   }
-  AIR_LAUNCH(kern, static_cast<unsigned>(B), kBwdThreads, smem, s, U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW);
+  AIR_LAUNCH(kern, static_cast<unsigned>(B), kBwdThreads, smem, s, U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW);
   count_launch();
   return check_launch("st_bwd_staged");
 }
 
 static int st_backward_impl(const float *U, const float *theta, const float *dout, const float *z, const float *stop,
-                            float thr, bool fused, float *dU, float *dtheta, float *dz, int64_t B, int H, int W, int C,
+                            float thr, bool fused, float *dU, float *dtheta, float *dz, int sig, int64_t B, int H, int W, int C,
                             int OH, int OW, cudaStream_t s) {
   AIR_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, AIR_ERR_BAD_SHAPE,
               "st_backward: bad shape B=%lld H=%d W=%d C=%d oh=%d ow=%d", (long long)B, H, W, C, OH, OW);
@@ -693,14 +699,14 @@ static int st_backward_impl(const float *U, const float *theta, const float *dou
   if (staged) {
     if (fused) {
       if (H == 28 && W == 28 && OH == 50 && OW == 50)
-        return launch_bwd_staged<28, 28, 50, 50, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
-      return launch_bwd_staged<0, 0, 0, 0, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+        return launch_bwd_staged<28, 28, 50, 50, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW, s);
+      return launch_bwd_staged<0, 0, 0, 0, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW, s);
     }
     if (H == 50 && W == 50 && OH == 28 && OW == 28)
-      return launch_bwd_staged<50, 50, 28, 28, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+      return launch_bwd_staged<50, 50, 28, 28, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW, s);
     if (H == 28 && W == 28 && OH == 50 && OW == 50)
-      return launch_bwd_staged<28, 28, 50, 50, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
-    return launch_bwd_staged<0, 0, 0, 0, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, B, H, W, OH, OW, s);
+      return launch_bwd_staged<28, 28, 50, 50, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW, s);
+    return launch_bwd_staged<0, 0, 0, 0, false>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW, s);
   }
   AIR_REQUIRE(!fused, AIR_ERR_UNSUPPORTED,
               "st_writeback_canvas_bwd: needs 16-byte aligned single-channel tiles that fit shared memory");
@@ -725,7 +731,7 @@ extern "C" int air_st_forward(const float *U, const float *theta, float *out, in
 
 extern "C" int air_st_backward(const float *U, const float *theta, const float *dout, float *dU, float *dtheta,
                                int64_t B, int H, int W, int C, int oh, int ow, air_stream_t stream) {
-  return air::st_backward_impl(U, theta, dout, nullptr, nullptr, 0.0f, false, dU, dtheta, nullptr, B, H, W, C, oh, ow,
+  return air::st_backward_impl(U, theta, dout, nullptr, nullptr, 0.0f, false, dU, dtheta, nullptr, 0, B, H, W, C, oh, ow,
                                static_cast<cudaStream_t>(stream));
 }
 
@@ -741,9 +747,9 @@ extern "C" int air_st_writeback_canvas_fwd(const float *window, const float *the
 
 extern "C" int air_st_writeback_canvas_bwd(const float *window, const float *theta_inv, const float *z,
                                            const float *stop_new, float thr, const float *dcanvas, float *dwindow,
-                                           float *dtheta_inv, float *dz, int64_t B, int wh, int ww, int ch, int cw,
-                                           air_stream_t stream) {
+                                           float *dtheta_inv, float *dz, int window_is_sigmoid, int64_t B, int wh, int ww,
+                                           int ch, int cw, air_stream_t stream) {
   AIR_REQUIRE(B <= 0 || (z && stop_new && dwindow && dz), AIR_ERR_NULL, "st_writeback_canvas_bwd: null pointer");
-  return air::st_backward_impl(window, theta_inv, dcanvas, z, stop_new, thr, true, dwindow, dtheta_inv, dz, B, wh, ww,
-                               1, ch, cw, static_cast<cudaStream_t>(stream));
+  return air::st_backward_impl(window, theta_inv, dcanvas, z, stop_new, thr, true, dwindow, dtheta_inv, dz,
+                               window_is_sigmoid, B, wh, ww, 1, ch, cw, static_cast<cudaStream_t>(stream));
 }

@@ -25,7 +25,7 @@ def _p2(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.EPI_NONE, mode=0):
+def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.EPI_NONE, mode=0, epi_param=0.0):
     """out[M,N] = epi((Cinit + op(A) op(B)) + bias); see include/air_b200.h (air_gemm)."""
     M, N = out.shape
     K = A.shape[0] if tA else A.shape[1]
@@ -36,8 +36,8 @@ def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.E
     for t in (Cinit, aux):
         if t is not None and (_ld(t) != ldc or t.shape != out.shape):
             raise C.AirError("Cinit / aux must have the layout of out")
-    check(lib().air_gemm(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), _p2(aux), M, N, K, _ld(A), _ld(B), ldc,
-                         int(tA), int(tB), epi, mode, stream()), "air_gemm")
+    check(lib().air_gemm_ex(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), _p2(aux), M, N, K, _ld(A), _ld(B), ldc,
+                            int(tA), int(tB), epi, float(epi_param), mode, stream()), "air_gemm")
     return out
 
 
@@ -140,7 +140,8 @@ def writeback_canvas_fwd(window, theta_inv, z, stop_new, thr, canvas_in, canvas_
           "air_st_writeback_canvas_fwd")
 
 
-def writeback_canvas_bwd(window, theta_inv, z, stop_new, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw):
+def writeback_canvas_bwd(window, theta_inv, z, stop_new, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw,
+                         window_is_sigmoid=False):
     check(lib().air_st_writeback_canvas_bwd(ptr(window), ptr(theta_inv), ptr(z), ptr(stop_new), float(thr),
-                                            ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), window.shape[0], wh,
-                                            ww, ch, cw, stream()), "air_st_writeback_canvas_bwd")
+                                            ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), int(window_is_sigmoid),
+                                            window.shape[0], wh, ww, ch, cw, stream()), "air_st_writeback_canvas_bwd")
