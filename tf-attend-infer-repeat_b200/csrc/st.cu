@@ -393,49 +393,84 @@ __global__ void __launch_bounds__(kBwdThreads)
 
   const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
   float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int npix = nr * nc;
-  // idx / nc by multiply-high: exact while idx * nc < 2^32 (checked on the host: OH*OW*OW < 2^32)
-  const unsigned magic = static_cast<unsigned>(sRect[4]);
-  for (int idx = tid; idx < npix; idx += kBwdThreads) {
-    const int ro = nc > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), magic)) : idx;
-    const int r = r_lo + ro, c = c_lo + (idx - ro * nc);
-    const int q = r * OW + c;
-    Ent ce, re;
-    const float xt = sGrid[c], yt = sGrid[OW + r];
-    if (sep) {
-      ce = sCol[c];
-      re = sRow[r];
-    } else {
-      float xt2, yt2;
-      gen_ents(sTh, r, c, OH, OW, H, W, ce, re, xt2, yt2);
+  if (sep) {
+    // ---- axis-aligned theta: lane = output column (its table entry and grid coordinate stay in registers),
+    //      warps stripe over the rows of the in-range rectangle (row entry = one broadcast load).
+    //      Per pixel: 4 corner loads, 1 gradient load, ~10 flops, 4 accumulations.
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int cb = 0; cb < nc; cb += 32) {
+      const bool cok = cb + lane < nc;
+      const int c = c_lo + (cok ? cb + lane : 0);
+      const Ent ce = sCol[c];
+      const float xt = sGrid[c];
+      const float *u0 = sU + ce.i0, *u1 = sU + ce.i1;
+      float sdx = 0.f, sdxy = 0.f, sdy = 0.f, sdyy = 0.f;
+      for (int ro = warp; ro < nr; ro += kBwdWarps) {
+        const int r = r_lo + ro;
+        const Ent re = sRow[r];
+        const float yt = sGrid[OW + r];
+        if (cok) {
+          const float Ia = u0[re.i0], Ib = u0[re.i1], Ic = u1[re.i0], Id = u1[re.i1];
+          float g = sG[r * OW + c];
+          if (FUSED) {
+            if (!dU) {  // (dz without dU: not used by the model; dz normally comes from <dU / z, U>)
+              const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+              const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+              acc[6] += g * add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
+            }
+            g *= zval;
+          }
+          // d out / d x = wy1 (Ic - Ia) + wy0 (Id - Ib),  d out / d y = wx1 (Ib - Ia) + wx0 (Id - Ic)
+          const float dx = g * (re.w1 * (Ic - Ia) + re.w0 * (Id - Ib));
+          const float dy = g * (ce.w1 * (Ib - Ia) + ce.w0 * (Id - Ic));
+          sdx += dx;
+          sdxy += dx * yt;
+          sdy += dy;
+          sdyy += dy * yt;
+        }
+      }
+      acc[0] += sdx * xt;
+      acc[1] += sdxy;
+      acc[2] += sdx;
+      acc[3] += sdy * xt;
+      acc[4] += sdyy;
+      acc[5] += sdy;
     }
-    const float Ia = sU[re.i0 + ce.i0], Ib = sU[re.i1 + ce.i0];
-    const float Ic = sU[re.i0 + ce.i1], Id = sU[re.i1 + ce.i1];
-    float g = sG[q];
-    if (FUSED) {
-      if (!sep || !dU) {  // separable path with dU: dz = <dU / z, U> after the dU passes (the sample is linear in U)
+  } else {
+    // ---- general theta (rotation / shear): flat loop over all output pixels, per-pixel coordinates
+    const int npix = nr * nc;
+    // idx / nc by multiply-high: exact while idx * nc < 2^32 (checked on the host: OH*OW*OW < 2^32)
+    const unsigned magic = static_cast<unsigned>(sRect[4]);
+    for (int idx = tid; idx < npix; idx += kBwdThreads) {
+      const int ro = nc > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), magic)) : idx;
+      const int r = r_lo + ro, c = c_lo + (idx - ro * nc);
+      const int q = r * OW + c;
+      Ent ce, re;
+      float xt, yt;
+      gen_ents(sTh, r, c, OH, OW, H, W, ce, re, xt, yt);
+      const float Ia = sU[re.i0 + ce.i0], Ib = sU[re.i1 + ce.i0];
+      const float Ic = sU[re.i0 + ce.i1], Id = sU[re.i1 + ce.i1];
+      float g = sG[q];
+      if (FUSED) {
         const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
         const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
-        const float v = add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
-        acc[6] += g * v;  // d(z * v)/dz
+        acc[6] += g * add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
+        g *= zval;
       }
-      g *= zval;  // d(z * v)/dv
-    }
-    // d out / d x = wy1 (Ic - Ia) + wy0 (Id - Ib),  d out / d y = wx1 (Ib - Ia) + wx0 (Id - Ic)
-    // (the factors 0.5 (W - 1.001) and 0.5 (H - 1.001) of :75-76 are applied once, after the reduction)
-    const float dx = g * (re.w1 * (Ic - Ia) + re.w0 * (Id - Ib));
-    const float dy = g * (ce.w1 * (Ib - Ia) + ce.w0 * (Id - Ic));
-    acc[0] += dx * xt;
-    acc[1] += dx * yt;
-    acc[2] += dx;
-    acc[3] += dy * xt;
-    acc[4] += dy * yt;
-    acc[5] += dy;
-    if (dU && !sep) {
-      atomicAdd(&sT[re.i0 + ce.i0], mul_rn(ce.w1, re.w1) * g);
-      atomicAdd(&sT[re.i1 + ce.i0], mul_rn(ce.w1, re.w0) * g);
-      atomicAdd(&sT[re.i0 + ce.i1], mul_rn(ce.w0, re.w1) * g);
-      atomicAdd(&sT[re.i1 + ce.i1], mul_rn(ce.w0, re.w0) * g);
+      const float dx = g * (re.w1 * (Ic - Ia) + re.w0 * (Id - Ib));
+      const float dy = g * (ce.w1 * (Ib - Ia) + ce.w0 * (Id - Ic));
+      acc[0] += dx * xt;
+      acc[1] += dx * yt;
+      acc[2] += dx;
+      acc[3] += dy * xt;
+      acc[4] += dy * yt;
+      acc[5] += dy;
+      if (dU) {
+        atomicAdd(&sT[re.i0 + ce.i0], mul_rn(ce.w1, re.w1) * g);
+        atomicAdd(&sT[re.i1 + ce.i0], mul_rn(ce.w1, re.w0) * g);
+        atomicAdd(&sT[re.i0 + ce.i1], mul_rn(ce.w0, re.w1) * g);
+        atomicAdd(&sT[re.i1 + ce.i1], mul_rn(ce.w0, re.w0) * g);
+      }
     }
   }
   // the reduction scratch is the (not yet used) pass-1 buffer, or a dedicated region for the atomics path
