@@ -158,7 +158,7 @@ def st_kernels(d, B):
 
     def wb_bwd():
         c.check(L.air_st_writeback_canvas_bwd(p(d["win"]), p(d["thi"]), p(d["z"]), p(d["stop"]), 0.99, p(d["dcanvas"]),
-                                              p(dwin), p(dth), p(dz), B, 28, 28, 50, 50, c.stream()), "wb_bwd")
+                                              p(dwin), p(dth), p(dz), 0, B, 28, 28, 50, 50, c.stream()), "wb_bwd")
 
     return {"crop_fwd": crop_fwd, "crop_bwd": crop_bwd, "writeback_canvas_fwd": wb_fwd, "writeback_canvas_bwd": wb_bwd}
 
