@@ -200,8 +200,9 @@ def cpu_baseline(seconds=12.0, B=64, steps=None):
 
 def run_reference(args, peaks):
     cb = cpu_baseline(steps=max(args.steps, 5))
+    ms = float(cb["sample"].split(",")[-1].split("ms/step")[0]) if "ms/step" in cb["sample"] else None
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "AIRModel default full train step (reference restated on CPU; TF 1.3 cannot run here)",
                        "batch_per_gpu": 64, "note": "each step is a bounded sample (batch 64) of the batch-4096 workload"},

@@ -305,3 +305,64 @@ def test_full_size_properties_b65536():
     sub = torch.arange(0, B, 1024, device=DEV)
     want = C.st_forward(U[sub].cpu().numpy(), th[sub].cpu().numpy(), (28, 28))
     assert np.array_equal(out[sub].cpu().numpy(), want)
+
+
+def test_full_size_properties_fused_and_backward_b65536():
+    """B = 65536 (BASELINE configs[1]): properties that need no oracle."""
+    B = 65536
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    r = lambda *s: torch.rand(*s, device=DEV, generator=gen)
+    s = r(B) * 0.6 + 0.3
+    xy = r(B, 2) - 0.5
+    th = torch.zeros(B, 6, device=DEV)
+    th[:, 0] = s; th[:, 4] = s; th[:, 2] = xy[:, 0]; th[:, 5] = xy[:, 1]
+    thi = torch.zeros(B, 6, device=DEV)
+    thi[:, 0] = 1 / s; thi[:, 4] = 1 / s; thi[:, 2] = -xy[:, 0] / s; thi[:, 5] = -xy[:, 1] / s
+    win, z, canvas = r(B, 28, 28), r(B), r(B, 50, 50)
+    stop = (r(B) > 0.7).float() * 1.5
+    L, c = ab._cabi.lib(), ab._cabi
+    out = torch.empty_like(canvas)
+    c.check(L.air_st_writeback_canvas_fwd(c.ptr(win), c.ptr(thi), c.ptr(z), c.ptr(stop), 0.99, c.ptr(canvas), c.ptr(out),
+                                          B, 28, 28, 50, 50, c.stream()), "fwd")
+    # (1) in place == out of place, bit for bit
+    inpl = canvas.clone()
+    c.check(L.air_st_writeback_canvas_fwd(c.ptr(win), c.ptr(thi), c.ptr(z), c.ptr(stop), 0.99, c.ptr(inpl), c.ptr(inpl),
+                                          B, 28, 28, 50, 50, c.stream()), "fwd inplace")
+    assert torch.equal(inpl, out)
+    # (2) stopped rows are untouched; live rows equal canvas + z * ST(window) computed by the plain ST kernel
+    dead = stop >= 0.99
+    assert torch.equal(out[dead], canvas[dead])
+    plain = ab.transformer(win.unsqueeze(3), thi, (50, 50))[..., 0]
+    want = canvas + torch.where(~dead[:, None, None], z[:, None, None] * plain, torch.zeros_like(plain))
+    assert torch.equal(out, want)
+    # (3) backward: batch-composition invariance and exact linearity in the upstream gradient
+    g = torch.randn(B, 50, 50, device=DEV, generator=gen)
+    def bwd(wi, ti, zi, si, gi):
+        n = wi.shape[0]
+        dw, dt, dz = torch.empty_like(wi), torch.empty(n, 6, device=DEV), torch.empty(n, device=DEV)
+        c.check(L.air_st_writeback_canvas_bwd(c.ptr(wi), c.ptr(ti), c.ptr(zi), c.ptr(si), 0.99, c.ptr(gi), c.ptr(dw),
+                                              c.ptr(dt), c.ptr(dz), 0, n, 28, 28, 50, 50, c.stream()), "bwd")
+        return dw, dt, dz
+    dw, dt, dz = bwd(win, thi, z, stop, g)
+    idx = torch.tensor([0, 5, 4097, 40000, 65535], device=DEV)
+    sub = bwd(win[idx].contiguous(), thi[idx].contiguous(), z[idx].contiguous(), stop[idx].contiguous(), g[idx].contiguous())
+    assert torch.equal(sub[0], dw[idx]) and torch.equal(sub[1], dt[idx]) and torch.equal(sub[2], dz[idx])
+    dw2, dt2, dz2 = bwd(win, thi, z, stop, g * 4)
+    assert torch.equal(dw2, dw * 4) and torch.equal(dt2, dt * 4) and torch.equal(dz2, dz * 4)
+    assert not dw[dead].any() and not dt[dead].any() and not dz[dead].any()
+    # (4) dz is the inner product <dU / z, U> of its own outputs (the identity the kernel uses), and also
+    #     equals sum(g * ST(window)) computed independently, to fp32 accuracy
+    live = ~dead
+    ref_dz = (g * plain).flatten(1).sum(1)
+    assert torch.allclose(dz[live], ref_dz[live], rtol=2e-4, atol=2e-3)
+    # (5) crop backward: subset invariance + linearity
+    U = r(B, 50, 50, 1)
+    gw = torch.randn(B, 28, 28, 1, device=DEV, generator=gen)
+    def crop_bwd(Ui, ti, gi):
+        n = Ui.shape[0]
+        dt_ = torch.empty(n, 6, device=DEV)
+        c.check(L.air_st_backward(c.ptr(Ui), c.ptr(ti), c.ptr(gi), None, c.ptr(dt_), n, 50, 50, 1, 28, 28, c.stream()), "crop bwd")
+        return dt_
+    d1 = crop_bwd(U, th, gw)
+    assert torch.equal(crop_bwd(U[idx].contiguous(), th[idx].contiguous(), gw[idx].contiguous()), d1[idx])
+    assert torch.equal(crop_bwd(U, th, gw * 0.5), d1 * 0.5)

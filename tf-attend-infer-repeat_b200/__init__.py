@@ -12,7 +12,7 @@ from .air.transformer import transformer, batch_transformer, writeback_canvas
 from .air.vae import vae
 from .air.air_model import AIRModel, reset_variable_scopes
 from .air.params import ParamStore
-from . import checkpoint, dp, ops
+from . import checkpoint, dp, ops, tfrecords
 from .demo.model_wrapper import ModelWrapper, evaluation_summaries
 from .air.concrete import (concrete_binary_sample, concrete_binary_pre_sigmoid_sample,
                            concrete_binary_kl_mc_sample, concrete_step)
