@@ -193,9 +193,10 @@ def test_vae_function_reference_signature():
     np.testing.assert_allclose(rec.detach().cpu().numpy(), orec.detach().numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(mean.detach().cpu().numpy(), omean.detach().numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(logvar.detach().cpu().numpy(), olv.detach().numpy(), rtol=1e-5, atol=1e-6)
+    # a caller-side loss that uses all outputs, like air_model.py:479-493 does with its own KL
     g = torch.randn(B, 784)
-    orec.backward(g)
-    rec.backward(g.to(DEV))
+    (orec * g).sum().add(0.5 * torch.sum(torch.exp(olv) + omean ** 2 - olv)).backward()
+    ((rec * g.to(DEV)).sum() + 0.5 * torch.sum(torch.exp(logvar) + mean ** 2 - logvar)).backward()
     assert relnorm(xg.grad, xt.grad) < 1e-4
 
 

@@ -199,3 +199,41 @@ def test_gemm_seq_fma_oracle():
     A, Bm = rng.randn(5, 37).astype(np.float32), rng.randn(37, 11).astype(np.float32)
     out = C.gemm_seq_fma(A, Bm, bias=np.ones(11, np.float32))
     np.testing.assert_allclose(out, A.astype(np.float64) @ Bm.astype(np.float64) + 1, rtol=1e-5, atol=1e-5)
+
+
+# ---- hypothesis: the two independent restatements agree bit for bit on arbitrary shapes / thetas ----------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(B=st.integers(1, 4), H=st.integers(2, 17), W=st.integers(2, 19), Cc=st.integers(1, 3), oh=st.integers(1, 12),
+       ow=st.integers(1, 13), seed=st.integers(0, 10 ** 6), scale=st.floats(0.05, 3.0), axis_aligned=st.booleans())
+def test_c_and_torch_oracles_agree_bitwise(B, H, W, Cc, oh, ow, seed, scale, axis_aligned):
+    rng = np.random.RandomState(seed)
+    U = rng.rand(B, H, W, Cc).astype(np.float32)
+    th = (rng.uniform(-1, 1, (B, 2, 3)) * scale).astype(np.float32)
+    if axis_aligned:
+        th[:, 0, 1] = 0.0
+        th[:, 1, 0] = 0.0
+    a = C.st_forward(U, th, (oh, ow))
+    b = O.transformer(torch.from_numpy(U), torch.from_numpy(th), (oh, ow)).numpy()
+    assert np.array_equal(a, b)
+    assert np.isfinite(a).all()
+    # out-of-range samples never exceed rounding-residue magnitude times the image scale
+    assert np.abs(a).max() <= U.max() * (1 + 1e-5) + 1e-5
+
+
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(1, 40), seed=st.integers(0, 10 ** 6), train=st.booleans(), tau=st.floats(0.3, 2.0))
+def test_concrete_step_invariants(n, seed, train, tau):
+    rng = np.random.RandomState(seed)
+    lo = (rng.randn(n) * 3).astype(np.float32)
+    u = rng.rand(n).astype(np.float32)
+    sp = rng.choice(np.array([0.0, 0.4, 0.98, 0.99, 2.0], np.float32), n)
+    out = C.concrete_step(lo, u, sp, np.zeros(n, np.float32), np.zeros(n, np.int32), -0.5, tau, 0.99, int(train))
+    assert np.all((out["z"] >= 0) & (out["z"] <= 1))
+    if not train:
+        assert np.all((out["z"] == 0) | (out["z"] == 1))
+    assert np.all(out["stop_new"] >= sp)                                       # the stopping sum never decreases
+    assert np.array_equal(out["digits_new"], (out["stop_new"] < np.float32(0.99)).astype(np.int32))
+    assert np.array_equal(out["loss_new"] != 0, (sp < np.float32(0.99)) & (out["kl"] != 0))   # KL masked by the OLD sum

@@ -74,7 +74,7 @@ def dense_dw(x_in, dY, gW, gb, colsum_ws, mode, accumulate=False):
 
 
 def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fields, mode, dx_out=None,
-                    dgen_is_presigmoid=False):
+                    dgen_is_presigmoid=False, dml_extra=None):
     """Backward through one VAE evaluation, activations only (air/vae.py:9-41 reversed).
     dbuf['dgen'] holds d(loss)/d(reconstruction) on entry; on exit dbuf holds the gradient
     w.r.t. every layer's pre-activation output (dgen, ddec[i], dml, denc[i]) -- the dY
@@ -88,6 +88,8 @@ def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fie
     for i in range(len(layers) - 1, -1, -1):
         dY = dense_dx(acts[i], layers[i][0], dY, douts[i], mode, act_of_x=(i > 0))
     ops.vae_latent_bwd(buf["ml"], noise_latent, dY, fields, hyper, dloss, dbuf["dml"])
+    if dml_extra is not None:  # gradients arriving directly at the (mean | log_variance) outputs of vae()
+        dbuf["dml"].add_(dml_extra)
     dY = dbuf["dml"]
     acts = [x] + list(buf["enc"])
     layers = list(w.rec) + [w.ml]
@@ -174,13 +176,21 @@ class _VAEFunction(torch.autograd.Function):
                          device=dev)
         dx = torch.empty_like(x)
         store.grad.zero_()
-        # dloss = 0: the KL term belongs to the caller (air_model.py:479-493), not to vae()
+        # dloss = 0: the KL term belongs to the caller (air_model.py:479-493), who differentiates through the
+        # rec_mean / rec_log_variance outputs; those gradients are added to d(mean | log_variance) here
+        L = d["L"]
+        extra = None
         if dmean is not None or dlogvar is not None:
-            raise NotImplementedError("vae(): gradients through rec_mean / rec_log_variance outputs are taken by "
-                                      "AIRModel's fused schedule; the standalone function differentiates the "
-                                      "reconstruction only")
-        dbuf["dgen"].copy_(drecon)
-        vae_backward_dx(x, w, noise_latent, hyper, buf, dbuf, 0.0, fields, mode, dx_out=dx)
+            extra = torch.zeros(B, 2 * L, device=dev)
+            if dmean is not None:
+                extra[:, :L] = dmean
+            if dlogvar is not None:
+                extra[:, L:] = dlogvar
+        if drecon is None:
+            dbuf["dgen"].zero_()
+        else:
+            dbuf["dgen"].copy_(drecon)
+        vae_backward_dx(x, w, noise_latent, hyper, buf, dbuf, 0.0, fields, mode, dx_out=dx, dml_extra=extra)
         vae_weight_grads(x, w, buf, dbuf, ws, mode)
         return dx, store.grad.clone(), None, None, None, None, None, None, None
 
