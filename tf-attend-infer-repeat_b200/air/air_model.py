@@ -216,10 +216,14 @@ class AIRModel:
         # step-invariant image projection x @ K[:in_dim] (bias added per step, after the h part)
         ops.gemm(x, self.Kx, w["xk"], mode=mode)
         for t in range(T):
-            h_prev = w["h"][t - 1] if t > 0 else w["h0"]
             c_prev = w["c"][t - 1] if t > 0 else None
-            # LSTM: gates = ([x,h] K) + b, accumulated in concat order (x part first)
-            ops.gemm(h_prev, self.Kh, w["gates"][t], Cinit=w["xk"], bias=p["rnn/bias"], mode=mode)
+            # LSTM: gates = ([x,h] K) + b, accumulated in concat order (x part first).  The initial state is
+            # zero (air_model.py:540-542), so at t = 0 the h rows contribute fma(0, k, acc) == acc exactly:
+            # a K = 0 GEMM (accumulator init + bias only) gives the same bits without the MACs.
+            if t > 0:
+                ops.gemm(w["h"][t - 1], self.Kh, w["gates"][t], Cinit=w["xk"], bias=p["rnn/bias"], mode=mode)
+            else:
+                ops.gemm(w["h0"][:, :0], self.Kh[:0], w["gates"][t], Cinit=w["xk"], bias=p["rnn/bias"], mode=mode)
             ops.lstm_fwd(w["gates"][t], c_prev, w["c"][t], w["h"][t])
             # five hidden head layers as one GEMM + ReLU; outputs, sampling, KLs, theta, z_pres fused
             ops.gemm(w["h"][t], p["heads/hidden_w"], w["hh"][t], bias=p["heads/hidden_b"], epi=C.EPI_RELU, mode=mode)
