@@ -163,6 +163,14 @@ def st_kernels(d, B):
     return {"crop_fwd": crop_fwd, "crop_bwd": crop_bwd, "writeback_canvas_fwd": wb_fwd, "writeback_canvas_bwd": wb_bwd}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 65536, from the `ncu --set full` captures
+# summarised under profiles/ (r1_crop_fwd_ncu_full.md was taken at B = 16384 x4 images per CTA: 840.7 MB per
+# 65536 images; r1_st_bwd_k1/k2_ncu_full.md).  The fused backward reads LESS than the algorithmic figure because
+# stopped images (30 % of the synthetic batch) never fetch their dCanvas rows.
+ST_NCU_TRAFFIC_B65536 = {"crop_fwd": 4 * (656.946e6 + 183.790e6), "crop_bwd": 862.487e6 + 5.773e6,
+                         "writeback_canvas_bwd": 606.910e6 + 186.340e6}
+
+
 def time_launches(fn, steps, warmup):
     import torch
     for _ in range(warmup):
@@ -193,7 +201,9 @@ def run_st(args, rank, world, peaks):
             ms = max_over_ranks(time_launches(fn, args.steps, args.warmup), world)
             gbs = B * ST_BYTES[name] / (ms * 1e-3) / 1e9
             res[name] = {"ms": round(ms, 5), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
-                         "bytes_per_image": ST_BYTES[name]}
+                         "bytes_per_image": ST_BYTES[name],
+                         "ncu_dram_bytes": (round(ST_NCU_TRAFFIC_B65536[name] * B / 65536)
+                                            if name in ST_NCU_TRAFFIC_B65536 else None)}
         barrier(world)
         _ = time.time() - t_all0
     launches = ab.launch_count() - n0
@@ -215,7 +225,10 @@ def run_st(args, rank, world, peaks):
         "config": {"workload": "st_microbench configs[1]: ST fwd/bwd 50x50<->28x28, batch %d per GPU, fp32" % B,
                    "batch_per_gpu": B, "l2": "working set (>= 860 MB per launch) >> 126 MB L2, no flush needed"},
         "roofline": {"bound": "hbm", "achieved": head["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": head["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["source"],
+                     "frac": head["frac_of_hbm_peak"],
+                     "traffic": round(ST_NCU_TRAFFIC_B65536["crop_fwd"] * B / 65536),
+                     "traffic_source": "ncu --set full capture (profiles/r1_crop_fwd_ncu_full.md), scaled to this B",
+                     "algorithmic_bytes": B * ST_BYTES["crop_fwd"], "peak_source": peaks["source"],
                      "kernel": "st_fwd_staged<50,50,28,28,4,false>"},
         "kernels": res,
         "e2e": {"value": round(B * ST_BYTES["crop_fwd"] / (e2e_ms * 1e-3) / 1e9 * world, 2), "unit": "GB/s",

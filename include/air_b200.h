@@ -69,11 +69,18 @@ int air_st_writeback_canvas_fwd(const float *window, const float *theta_inv, con
 
 /* Backward: dcanvas [B,ch,cw] is d(loss)/d(canvas_out) (== d/d(canvas_in), not rewritten).
  * Writes dwindow [B,wh,ww], dtheta_inv [B,6], dz [B]; all zero for rows with stop_new >= thr.
- * window_is_sigmoid != 0: the window is a sigmoid output w (vae.py:39-41) and dwindow receives the gradient
- * w.r.t. its PRE-sigmoid input, dwindow * w * (1 - w) -- the SigmoidGrad op fused into the final store. */
+ * flags (bit mask):
+ *   AIR_WB_SIGMOID_WINDOW      the window is a sigmoid output w (vae.py:39-41) and dwindow receives the gradient
+ *                              w.r.t. its PRE-sigmoid input, dwindow * w * (1 - w): SigmoidGrad fused into the store.
+ *   AIR_WB_AXIS_ALIGNED_THETA  the caller builds theta_inv = [[1/s,0,-x/s],[0,1/s,-y/s]] (air_model.py:351-360) and
+ *                              consumes only dtheta_inv[0], [2], [4], [5]; the gradients w.r.t. the structural zeros
+ *                              ([1], [3]) are written as 0 for axis-aligned rows.  Enables the warp-specialised
+ *                              kernel (28x28 window, 50x50 canvas); rows with shear/rotation still get all six. */
+#define AIR_WB_SIGMOID_WINDOW 1
+#define AIR_WB_AXIS_ALIGNED_THETA 2
 int air_st_writeback_canvas_bwd(const float *window, const float *theta_inv, const float *z, const float *stop_new,
                                 float thr, const float *dcanvas, float *dwindow, float *dtheta_inv, float *dz,
-                                int window_is_sigmoid, int64_t B, int wh, int ww, int ch, int cw, air_stream_t stream);
+                                int flags, int64_t B, int wh, int ww, int ch, int cw, air_stream_t stream);
 
 /* ---- Concrete / ACT step: concrete.py:20-43 + air_model.py:380-427 -----------------
  * y = (log_odds + log(u+eps) - log(1-u+eps)) / temperature ; z = sigmoid(y) (rounded

@@ -233,6 +233,92 @@ def test_fused_canvas_backward():
     assert not wg.grad.cpu().numpy()[dead].any() and not zg.grad.cpu().numpy()[dead].any()
 
 
+def _axis_cases(rng):
+    """theta_inv rows [a, 0, tx, 0, e, ty] exercising every branch of the warp-specialised kernel."""
+    rows = []
+    for _ in range(40):                                   # the model's regime: window 30-90 % of the canvas
+        s = rng.uniform(0.3, 0.9); x, y = rng.uniform(-0.5, 0.5, 2)
+        rows.append([1 / s, 0, -x / s, 0, 1 / s, -y / s])
+    for s in (1.0, 1.3, 2.0, 3.0):                       # window covers the canvas: 50 in-range rows / columns (2 blocks)
+        rows.append([1 / s, 0, 0.02, 0, 1 / s, -0.03])
+    for s in (0.04, 0.08, 0.15):                         # tiny windows: a few columns, source index jumps by > 1
+        rows.append([1 / s, 0, 0.3 / s, 0, 1 / s, -0.2 / s])
+    for x, y in ((0.9, 0.0), (-0.95, 0.4), (0.0, 0.97), (0.8, -0.85)):   # partially outside the canvas
+        rows.append([2.0, 0, -2.0 * x, 0, 2.0, -2.0 * y])
+    rows.append([2.0, 0, 7.0, 0, 2.0, 0.0])               # entirely outside: every gradient is zero
+    rows.append([-1.6, 0, 0.1, 0, 1.7, 0.05])             # mirrored columns
+    rows.append([1.4, 0, -0.2, 0, -2.1, 0.1])             # mirrored rows
+    rows.append([1.5, 0, 0.1, 0, 0.7, -0.1])              # anisotropic
+    rows.append([1.5173, 0.2291, 0.1037, -0.1113, 1.4219, 0.0071])   # shear (no sample lands exactly on the hard edge): falls back to the atomics path (all six entries)
+    return np.asarray(rows, np.float32)
+
+
+@pytest.mark.parametrize("sig", [0, 1])
+def test_fused_canvas_backward_axis_aligned_kernel(sig):
+    """AIR_WB_AXIS_ALIGNED_THETA: the P/Q run-scan kernel (dU, dz, dtheta[0,2,4,5]) against the oracle's autograd
+    evaluated in float64 -- the fp32 oracle itself carries the reference's cancellation noise from clipped pixels
+    (weights of +-300 on the tiny-window rows), which is not what this test is about -- and, on the model-regime
+    rows, against the fp32 oracle at the parity tolerance."""
+    rng = np.random.RandomState(43)
+    thi = _axis_cases(rng)
+    B = thi.shape[0]
+    win = rng.rand(B, 28, 28).astype(np.float32) * 0.9 + 0.05
+    z = (rng.rand(B).astype(np.float32) * 0.9 + 0.1)
+    stop = rng.choice(np.array([0.0, 0.5, 1.7], np.float32), B, p=[0.45, 0.45, 0.1])
+    g = (rng.rand(B, 50, 50).astype(np.float32) - 0.3)
+    pre = np.log(win / (1 - win)).astype(np.float32)       # pre-sigmoid input of the window (sig = 1)
+    wwin = torch.sigmoid(torch.from_numpy(pre)).numpy() if sig else win
+
+    def oracle_grads(dtype):
+        if sig:
+            pt = torch.from_numpy(pre).to(dtype).requires_grad_(True)
+            # the kernel multiplies by w (1 - w) of the fp32 window it is given
+            wt = torch.from_numpy(wwin).to(dtype) + (torch.sigmoid(pt) - torch.sigmoid(pt).detach())
+        else:
+            pt = torch.from_numpy(win).to(dtype).requires_grad_(True)
+            wt = pt
+        tt, zt = torch.from_numpy(thi).to(dtype).requires_grad_(True), torch.from_numpy(z).to(dtype).requires_grad_(True)
+        wr = O.transformer(wt.unsqueeze(3), tt, (50, 50))[..., 0]
+        live = torch.from_numpy(stop) < 0.99
+        (torch.where(live[:, None, None], zt[:, None, None] * wr, torch.zeros_like(wr)) * torch.from_numpy(g).to(dtype)).sum().backward()
+        return pt.grad.numpy(), tt.grad.numpy(), zt.grad.numpy()
+
+    want_w, want_t, want_z = oracle_grads(torch.float64)
+    f32_w, f32_t, f32_z = oracle_grads(torch.float32)
+    L, c = ab._cabi.lib(), ab._cabi
+    wi, ti, zi, si, gi = cu(wwin), cu(thi), cu(z), cu(stop), cu(g)
+    res = []
+    for flags in (sig, sig | 2):
+        dw = torch.full((B, 28, 28), 7.0, device=DEV); dt = torch.full((B, 6), 7.0, device=DEV); dz = torch.full((B,), 7.0, device=DEV)
+        c.check(L.air_st_writeback_canvas_bwd(c.ptr(wi), c.ptr(ti), c.ptr(zi), c.ptr(si), 0.99, c.ptr(gi), c.ptr(dw),
+                                              c.ptr(dt), c.ptr(dz), flags, B, 28, 28, 50, 50, c.stream()), "bwd")
+        res.append((dw.cpu().numpy().astype(np.float64), dt.cpu().numpy().astype(np.float64), dz.cpu().numpy().astype(np.float64)))
+    shear = thi[:, 1] != 0
+    diag = [0, 2, 4, 5]
+    model_rows = np.arange(B) < 40
+    for name, (dw, dt, dz) in zip(("staged", "axis"), res):
+        # per image, so that one bad branch cannot hide in a batch norm
+        ew = np.abs(dw - want_w).reshape(B, -1).max(1) / (np.abs(want_w).reshape(B, -1).max(1) + 1e-3)
+        et = np.abs(dt[:, diag] - want_t[:, diag]).max(1) / (np.abs(want_t[:, diag]).max(1) + 1e-2)
+        ez = np.abs(dz - want_z) / (np.abs(want_z) + 1e-1)
+        ew = ew / np.where(shear, 5.0, 1.0)   # the atomics path carries the clipped pixels' cancellation noise
+        bad = []
+        if ew.max() >= 5e-5: bad.append((name, "dU", int(ew.argmax()), float(ew.max()), thi[ew.argmax()]))
+        if et.max() >= 2e-4: bad.append((name, "dtheta", int(et.argmax()), float(et.max()), thi[et.argmax()], dt[et.argmax()], want_t[et.argmax()]))
+        if ez.max() >= 5e-5: bad.append((name, "dz", int(ez.argmax()), float(ez.max()), thi[ez.argmax()]))
+        assert not bad, bad
+        # fp32 oracle, parity tolerance, model regime
+        assert relnorm(dw[model_rows], f32_w[model_rows]) < 1e-4 and relnorm(dz[model_rows], f32_z[model_rows]) < 1e-4, name
+        assert relnorm(dt[model_rows][:, diag], f32_t[model_rows][:, diag]) < 1e-4, name
+    # off-diagonal entries: exact zeros from the axis kernel, the real gradient on the shear row and in the staged kernel
+    dt_axis, dt_staged = res[1][1], res[0][1]
+    assert not dt_axis[~shear][:, [1, 3]].any()
+    assert relnorm(dt_axis[shear], want_t[shear]) < 1e-4
+    assert relnorm(dt_staged[:, [1, 3]], want_t[:, [1, 3]]) < 1e-4
+    dead = stop >= 0.99
+    assert not res[1][0][dead].any() and not res[1][1][dead].any() and not res[1][2][dead].any()
+
+
 def test_concrete_step_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "concrete.npz"))
     for train in (0, 1):
@@ -350,6 +436,22 @@ def test_full_size_properties_fused_and_backward_b65536():
     dw2, dt2, dz2 = bwd(win, thi, z, stop, g * 4)
     assert torch.equal(dw2, dw * 4) and torch.equal(dt2, dt * 4) and torch.equal(dz2, dz * 4)
     assert not dw[dead].any() and not dt[dead].any() and not dz[dead].any()
+    # (3b) the warp-specialised axis-aligned kernel: same invariances, and agreement with the staged kernel
+    def bwd_axis(wi, ti, zi, si, gi):
+        n = wi.shape[0]
+        dw_, dt_, dz_ = torch.empty_like(wi), torch.empty(n, 6, device=DEV), torch.empty(n, device=DEV)
+        c.check(L.air_st_writeback_canvas_bwd(c.ptr(wi), c.ptr(ti), c.ptr(zi), c.ptr(si), 0.99, c.ptr(gi), c.ptr(dw_),
+                                              c.ptr(dt_), c.ptr(dz_), 2, n, 28, 28, 50, 50, c.stream()), "bwd axis")
+        return dw_, dt_, dz_
+    adw, adt, adz = bwd_axis(win, thi, z, stop, g)
+    asub = bwd_axis(win[idx].contiguous(), thi[idx].contiguous(), z[idx].contiguous(), stop[idx].contiguous(), g[idx].contiguous())
+    assert torch.equal(asub[0], adw[idx]) and torch.equal(asub[1], adt[idx]) and torch.equal(asub[2], adz[idx])
+    adw2, adt2, adz2 = bwd_axis(win, thi, z, stop, g * 4)
+    assert torch.equal(adw2, adw * 4) and torch.equal(adt2, adt * 4) and torch.equal(adz2, adz * 4)
+    assert not adw[dead].any() and not adt[dead].any() and not adz[dead].any()
+    rel = lambda a, b_: float((a - b_).norm() / b_.norm())
+    assert rel(adw, dw) < 2e-6 and rel(adz, dz) < 2e-6 and rel(adt[:, [0, 2, 4, 5]], dt[:, [0, 2, 4, 5]]) < 2e-5
+    assert not adt[:, [1, 3]].any()
     # (4) dz is the inner product <dU / z, U> of its own outputs (the identity the kernel uses), and also
     #     equals sum(g * ST(window)) computed independently, to fp32 accuracy
     live = ~dead

@@ -269,7 +269,8 @@ class AIRModel:
                         ddec=[d[t] for d in vd["ddec"]], dgen=vd["dgen"][t])
             ops.writeback_canvas_bwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
                                      self.stopping_threshold, w["dcanvas"], dbuf["dgen"], w["dtheta_inv"], w["dz"],
-                                     wsz, wsz, cs, cs, window_is_sigmoid=True)  # SigmoidGrad fused into the store
+                                     wsz, wsz, cs, cs, window_is_sigmoid=True,  # SigmoidGrad fused into the store
+                                     axis_aligned_theta=True)  # heads_bwd reads dtheta_inv[0,2,4,5] only
             vae_backward_dx(w["win"][t], self.vw, n["vae_latent"][t], hp, self._vae_buf(t), dbuf, dscale, f, mode,
                             dx_out=w["dwin"], dgen_is_presigmoid=True)
             ops.st_backward(x, w["theta"][t], w["dwin"], None, w["dtheta"], cs, cs, 1, wsz, wsz)

@@ -578,6 +578,306 @@ __global__ void __launch_bounds__(kBwdThreads)
 }
 
 // =========================================================================================
+// Fused write-back backward for the model's axis-aligned theta_inv (air_model.py:351-360), fixed
+// W <= 32 window: warp-specialised, no atomics, ONE block barrier after the tables.
+//
+// With Wx [nc x W] / Wy [nr x H] the banded 1-D interpolation matrices of the in-range rectangle
+// (two non-zeros per row: w1 at i0, w0 at i0 + 1) and G the upstream tile:
+//     dU     = z * Wy^T G Wx
+//     d/dy   : sum_j Q[r][j] * (U[i0(r)+1][j] - U[i0(r)][j])        with Q = G Wx     (per output row r)
+//     d/dx   : sum_i P[i][c] * (U[i][j0(c)+1] - U[i][j0(c)])        with P = Wy^T G   (per output column c)
+//     dz     = <dU / z, U>
+// i.e. the same terms TF autodiff sums per output pixel (transformer.py:108-116), contracted in a
+// different order: the per-pixel pass with its four corner loads disappears.
+//   warp 0    : Q by run-scan (lane = output row, 32 rows at a time), then Wy^T Q by a second run-scan
+//               (lane = source column) that stores dU rows straight to global memory as they complete
+//               and accumulates d/dy and dz on the way.  Q lives in a warp-private buffer: __syncwarp only.
+//   warp 1, 2 : P by run-scan (lane = output column, 32 columns each); a finished P row is consumed
+//               immediately into d/dx and never stored.
+// Only dtheta[0], [2], [4], [5] are produced; the off-diagonal entries [1], [3] multiply the structural
+// zeros of theta_inv and are written as 0 (the caller opts in with AIR_WB_AXIS_ALIGNED_THETA).
+// Images whose theta is not axis-aligned take a shared-memory-atomics path (all six entries).
+// =========================================================================================
+__device__ __forceinline__ void rect_1d(const Ent *tab, int n, int lane, int &lo, int &cnt) {
+  const int k1 = lane + 32;
+  const int2 a = *reinterpret_cast<const int2 *>(tab + min(lane, n - 1));
+  const int2 c = *reinterpret_cast<const int2 *>(tab + min(k1, n - 1));
+  const unsigned ma = __ballot_sync(0xffffffffu, lane < n && a.x != a.y);
+  const unsigned mb = __ballot_sync(0xffffffffu, k1 < n && c.x != c.y);
+  const unsigned long long m = (static_cast<unsigned long long>(mb) << 32) | ma;
+  lo = 0;
+  cnt = 0;
+  if (m) {
+    lo = __ffsll(static_cast<long long>(m)) - 1;
+    cnt = 64 - __clzll(static_cast<long long>(m)) - lo;
+  }
+}
+
+constexpr int kAxisQS = 33;  // row stride of the transposed Q buffer [W][33]: conflict-free for both scans
+
+template <int H, int W, int OH, int OW>
+__global__ void __launch_bounds__(kBwdThreads, 11)
+    st_wb_bwd_axis(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dcanvas,
+                   const float *__restrict__ zp, const float *__restrict__ stop, float thr, float *__restrict__ dU,
+                   float *__restrict__ dtheta, float *__restrict__ dz, int sig, int64_t B) {
+  static_assert(W <= 32 && OW <= 64 && OH <= 64 && (H * W) % 4 == 0 && (OH * OW) % 4 == 0, "unsupported tile");
+  static_assert(W * kAxisQS >= H * W && OH * OW >= 7 * kBwdThreads, "fallback path aliases these buffers");
+  pdl_sync();  // PDL: no global access before the previous grid has completed
+  constexpr int HW = H * W, OHW = OH * OW, QS = kAxisQS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *sU = reinterpret_cast<float *>(smem_raw);           // [HW]   window
+  float *sG = sU + HW;                                        // [OHW]  upstream gradient tile (dcanvas)
+  float *sQ = sG + OHW;                                       // [W][QS] Q^T of the current 32-row block (warp 0)
+  Ent *sCol = reinterpret_cast<Ent *>(sQ + W * QS);           // [OW]
+  Ent *sRow = sCol + OW;                                      // [OH]
+  float *sGy = reinterpret_cast<float *>(sRow + OH);          // [OH] normalised grid y_t
+  __shared__ uint64_t bar;
+  __shared__ float sTh[8];
+  __shared__ float sPart[8];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t b = blockIdx.x;
+  const float *th_g = theta + b * 6;
+  float *dUb = dU + b * HW;
+
+  const bool live = __ldg(stop + b) < thr;
+  const float zval = __ldg(zp + b);
+  if (!live) {  // whole image masked out: every gradient is exactly zero (uniform branch)
+    for (int k = tid; k < (HW >> 2); k += kBwdThreads) reinterpret_cast<float4 *>(dUb)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 6) dtheta[b * 6 + tid] = 0.0f;
+    if (tid == 0) dz[b] = 0.0f;
+    return;
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 8) sPart[tid] = 0.0f;
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, static_cast<uint32_t>(HW + OHW) * 4u);
+    bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
+    bulk_g2s(sG, dcanvas + b * OHW, OHW * 4u, &bar);
+  }
+  // ---- tables (overlap the bulk copies)
+  if (tid < 6) sTh[tid] = __ldg(th_g + tid);
+  if (tid == 6) sTh[6] = (__ldg(th_g + 1) == 0.0f && __ldg(th_g + 3) == 0.0f) ? 1.0f : 0.0f;
+  for (int k = tid; k < OW + OH; k += kBwdThreads) {
+    const bool col = k < OW;
+    const float gk = col ? linspace_pm1(k, OW) : linspace_pm1(k - OW, OH);
+    const float diag = __ldg(th_g + (col ? 0 : 4)), trans = __ldg(th_g + (col ? 2 : 5));
+    const Ent e = make_ent(to_pixel(add_rn(mul_rn(diag, gk), trans), col ? W : H), col ? W : H, col ? 1 : W);
+    if (col) {
+      sCol[k] = e;
+    } else {
+      sRow[k - OW] = e;
+      sGy[k - OW] = gk;
+    }
+  }
+  __syncthreads();
+  const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
+
+  if (sTh[6] == 0.0f) {
+    // ---- general theta (rotation / shear): per-pixel coordinates, shared-memory atomics for dU
+    float *sTile = sQ;
+    for (int k = tid; k < HW; k += kBwdThreads) sTile[k] = 0.0f;
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = tid; q < OHW; q += kBwdThreads) {
+      const int r = q / OW, c = q - r * OW;
+      Ent ce, re;
+      float xt, yt;
+      gen_ents(sTh, r, c, OH, OW, H, W, ce, re, xt, yt);
+      const float Ia = sU[re.i0 + ce.i0], Ib = sU[re.i1 + ce.i0];
+      const float Ic = sU[re.i0 + ce.i1], Id = sU[re.i1 + ce.i1];
+      float g = sG[q];
+      const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+      const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+      acc[6] += g * add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
+      g *= zval;
+      const float dx = g * (re.w1 * (Ic - Ia) + re.w0 * (Id - Ib));
+      const float dy = g * (ce.w1 * (Ib - Ia) + ce.w0 * (Id - Ic));
+      acc[0] += dx * xt; acc[1] += dx * yt; acc[2] += dx;
+      acc[3] += dy * xt; acc[4] += dy * yt; acc[5] += dy;
+      atomicAdd(&sTile[re.i0 + ce.i0], wa * g);
+      atomicAdd(&sTile[re.i1 + ce.i0], wb * g);
+      atomicAdd(&sTile[re.i0 + ce.i1], wc * g);
+      atomicAdd(&sTile[re.i1 + ce.i1], wd * g);
+    }
+    block_sum_many<7>(acc, sG);  // its leading barrier orders the scratch writes after the last reads of sG
+    if (tid == 0) {
+      const float sx = 0.5f * wf, sy = 0.5f * hf;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dtheta[b * 6 + k] = acc[k] * (k < 3 ? sx : sy);
+      dz[b] = acc[6];
+    }
+    for (int k = tid; k < HW; k += kBwdThreads) {
+      const float u = sU[k];
+      dUb[k] = sig ? sTile[k] * u * (1.0f - u) : sTile[k];
+    }
+    return;
+  }
+
+  // ---- in-range rectangle, recomputed by every warp from the tables (two ballots each; saves a barrier)
+  int c_lo, nc, r_lo, nr;
+  rect_1d(sCol, OW, lane, c_lo, nc);
+  rect_1d(sRow, OH, lane, r_lo, nr);
+  if (nr == 0 || nc == 0) {  // window entirely outside the canvas (uniform)
+    for (int k = tid; k < (HW >> 2); k += kBwdThreads) reinterpret_cast<float4 *>(dUb)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 6) dtheta[b * 6 + tid] = 0.0f;
+    if (tid == 0) dz[b] = 0.0f;
+    return;
+  }
+  // scan directions that make the source index non-decreasing (negative scale = mirrored window)
+  const bool c_up = sCol[c_lo + nc - 1].i0 >= sCol[c_lo].i0, r_up = sRow[r_lo + nr - 1].i0 >= sRow[r_lo].i0;
+  const int cfirst = c_up ? c_lo : c_lo + nc - 1, cstep = c_up ? 1 : -1;
+  const int rfirst = r_up ? r_lo : r_lo + nr - 1, rstep = r_up ? 1 : -1;
+  mbar_wait(&bar, 0);
+
+  if (warp == 0) {
+    const bool jok = lane < W;
+    const int jj = jok ? lane : W - 1;
+    const float *uj = sU + jj;
+    const float *qj = sQ + jj * QS;
+    float *dUj = dUb + jj;
+    float t0 = 0.0f, t1 = 0.0f, sdy = 0.0f, sdyy = 0.0f, dot = 0.0f;
+    int icur = sRow[rfirst].i0, next = 0;
+    auto emit = [&](int iw, float v) {  // source row iw / W of dU is complete (rows arrive in increasing order)
+      for (; next < iw; next += W)
+        if (jok) dUj[next] = 0.0f;
+      const float u = uj[iw];
+      dot = fmaf(v, u, dot);
+      float o = v * zval;
+      if (sig) o *= u * (1.0f - u);  // SigmoidGrad of the window fused into the store
+      if (jok) dUj[iw] = o;
+      next = iw + W;
+    };
+    for (int m0 = 0; m0 < nr; m0 += 32) {
+      const int mcount = min(32, nr - m0);
+      {  // pass 1: Q[m][j] = sum_c g[r(m)][c] Wx[c][j]; lane = row m0 + lane, columns in scan order
+        const int m = m0 + min(lane, mcount - 1);  // surplus lanes redo the last row into unused Q columns
+        const float *gp = sG + (rfirst + m * rstep) * OW + cfirst;
+        const Ent *ep = sCol + cfirst;
+        float *q = sQ + lane;
+        int jcur = ep->i0;
+        for (int x = 0; x < jcur; ++x) q[x * QS] = 0.0f;
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int n = nc; n > 0; --n, gp += cstep, ep += cstep) {
+          const Ent ce = *ep;
+          const float g = *gp;
+          if (ce.i0 != jcur) {  // warp-uniform: depends on the column only
+            q[jcur * QS] = s0;
+            if (ce.i0 == jcur + 1) {
+              s0 = s1;
+            } else {
+              q[(jcur + 1) * QS] = s1;
+              for (int x = jcur + 2; x < ce.i0; ++x) q[x * QS] = 0.0f;
+              s0 = 0.0f;
+            }
+            s1 = 0.0f;
+            jcur = ce.i0;
+          }
+          s0 = fmaf(ce.w1, g, s0);
+          s1 = fmaf(ce.w0, g, s1);
+        }
+        q[jcur * QS] = s0;
+        q[(jcur + 1) * QS] = s1;
+        for (int x = jcur + 2; x < W; ++x) q[x * QS] = 0.0f;
+      }
+      __syncwarp();
+      {  // pass 2: dU = Wy^T Q, lane = source column; d/dy and dz on the way
+        const Ent *rp = sRow + rfirst + m0 * rstep;
+        const float *yp = sGy + rfirst + m0 * rstep;
+        for (int mm = 0; mm < mcount; ++mm, rp += rstep, yp += rstep) {
+          const Ent re = *rp;
+          const float t = qj[mm];
+          if (re.i0 != icur) {
+            emit(icur, t0);
+            if (re.i0 == icur + W) {
+              t0 = t1;
+            } else {
+              emit(icur + W, t1);
+              t0 = 0.0f;
+            }
+            t1 = 0.0f;
+            icur = re.i0;
+          }
+          t0 = fmaf(re.w1, t, t0);
+          t1 = fmaf(re.w0, t, t1);
+          const float *up = uj + re.i0;
+          const float dyl = t * (up[W] - up[0]);
+          sdy += dyl;
+          sdyy = fmaf(dyl, *yp, sdyy);
+        }
+      }
+      __syncwarp();
+    }
+    emit(icur, t0);
+    emit(icur + W, t1);
+    for (; next < HW; next += W)
+      if (jok) dUj[next] = 0.0f;
+    if (!jok) sdy = sdyy = dot = 0.0f;
+    sdy = warp_sum(sdy);
+    sdyy = warp_sum(sdyy);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      sPart[0] = sdy;
+      sPart[1] = sdyy;
+      sPart[2] = dot;
+    }
+  } else if (warp <= 2 && 32 * (warp - 1) < nc) {
+    // P-scan: lane = output column of the rectangle, rows in scan order
+    const int k = 32 * (warp - 1) + lane;
+    const bool cok = k < nc;
+    const int c = c_lo + (cok ? k : nc - 1);
+    const float *uc = sU + sCol[c].i0;
+    const float *gp = sG + rfirst * OW + c;
+    const int gstep = rstep * OW;
+    const Ent *rp = sRow + rfirst;
+    int icur = rp->i0;
+    float p0 = 0.0f, p1 = 0.0f, dx = 0.0f;
+    for (int n = nr; n > 0; --n, gp += gstep, rp += rstep) {
+      const Ent re = *rp;
+      const float g = *gp;
+      if (re.i0 != icur) {  // warp-uniform: depends on the row only
+        dx = fmaf(p0, uc[icur + 1] - uc[icur], dx);
+        if (re.i0 == icur + W) {
+          p0 = p1;
+        } else {
+          dx = fmaf(p1, uc[icur + W + 1] - uc[icur + W], dx);
+          p0 = 0.0f;
+        }
+        p1 = 0.0f;
+        icur = re.i0;
+      }
+      p0 = fmaf(re.w1, g, p0);
+      p1 = fmaf(re.w0, g, p1);
+    }
+    dx = fmaf(p0, uc[icur + 1] - uc[icur], dx);
+    dx = fmaf(p1, uc[icur + W + 1] - uc[icur + W], dx);
+    if (!cok) dx = 0.0f;
+    const float a0 = warp_sum(dx * linspace_pm1(c, OW)), a2 = warp_sum(dx);
+    if (lane == 0) {
+      sPart[2 + 2 * warp] = a0;
+      sPart[3 + 2 * warp] = a2;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float sx = 0.5f * wf * zval, sy = 0.5f * hf * zval;
+    float *d = dtheta + b * 6;
+    d[0] = (sPart[4] + sPart[6]) * sx;
+    d[1] = 0.0f;
+    d[2] = (sPart[5] + sPart[7]) * sx;
+    d[3] = 0.0f;
+    d[4] = sPart[1] * sy;
+    d[5] = sPart[0] * sy;
+    dz[b] = sPart[2];
+  }
+}
+
+// =========================================================================================
 // Backward, generic (any C, any size): one CTA per image, global atomics for dU.
 // =========================================================================================
 __global__ void __launch_bounds__(kBwdThreads)
@@ -719,9 +1019,27 @@ static int launch_bwd_staged(const float *U, const float *theta, const float *do
   return check_launch("st_bwd_staged");
 }
 
+template <int H_, int W_, int OH_, int OW_>
+static int launch_wb_bwd_axis(const float *U, const float *theta, const float *dcanvas, const float *z, const float *stop,
+                              float thr, float *dU, float *dtheta, float *dz, int sig, int64_t B, cudaStream_t s) {
+  auto kern = st_wb_bwd_axis<H_, W_, OH_, OW_>;
+  constexpr size_t smem = (static_cast<size_t>(H_) * W_ + OH_ * OW_ + W_ * kAxisQS + OH_) * 4 + (OW_ + OH_) * sizeof(Ent);
+  static_assert(smem <= 48 * 1024, "no opt-in needed");
+  static bool once = false;
+  if (!once) {  // ask for the largest shared-memory carve-out so that 11 CTAs fit on an SM
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_wb_bwd_axis): %s", cudaGetErrorString(e));
+    once = true;
+  }
+  AIR_LAUNCH(kern, static_cast<unsigned>(B), kBwdThreads, smem, s, U, theta, dcanvas, z, stop, thr, dU, dtheta, dz, sig, B);
+  count_launch();
+  return check_launch("st_wb_bwd_axis");
+}
+
 static int st_backward_impl(const float *U, const float *theta, const float *dout, const float *z, const float *stop,
-                            float thr, bool fused, float *dU, float *dtheta, float *dz, int sig, int64_t B, int H, int W, int C,
+                            float thr, bool fused, float *dU, float *dtheta, float *dz, int flags, int64_t B, int H, int W, int C,
                             int OH, int OW, cudaStream_t s) {
+  const int sig = flags & AIR_WB_SIGMOID_WINDOW;
   AIR_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, AIR_ERR_BAD_SHAPE,
               "st_backward: bad shape B=%lld H=%d W=%d C=%d oh=%d ow=%d", (long long)B, H, W, C, OH, OW);
   AIR_REQUIRE(static_cast<int64_t>(H) * W * C < (int64_t(1) << 30) && static_cast<int64_t>(OH) * OW < (int64_t(1) << 30),
@@ -733,6 +1051,8 @@ static int st_backward_impl(const float *U, const float *theta, const float *dou
                       bwd_smem_bytes(H, W, OH, OW, dU != nullptr) <= static_cast<size_t>(kMaxStagedSmem);
   if (staged) {
     if (fused) {
+      if (H == 28 && W == 28 && OH == 50 && OW == 50 && (flags & AIR_WB_AXIS_ALIGNED_THETA) && dU && dz && aligned16(dU))
+        return launch_wb_bwd_axis<28, 28, 50, 50>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, s);
       if (H == 28 && W == 28 && OH == 50 && OW == 50)
         return launch_bwd_staged<28, 28, 50, 50, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW, s);
       return launch_bwd_staged<0, 0, 0, 0, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW, s);
@@ -782,9 +1102,9 @@ extern "C" int air_st_writeback_canvas_fwd(const float *window, const float *the
 
 extern "C" int air_st_writeback_canvas_bwd(const float *window, const float *theta_inv, const float *z,
                                            const float *stop_new, float thr, const float *dcanvas, float *dwindow,
-                                           float *dtheta_inv, float *dz, int window_is_sigmoid, int64_t B, int wh, int ww,
+                                           float *dtheta_inv, float *dz, int flags, int64_t B, int wh, int ww,
                                            int ch, int cw, air_stream_t stream) {
   AIR_REQUIRE(B <= 0 || (z && stop_new && dwindow && dz), AIR_ERR_NULL, "st_writeback_canvas_bwd: null pointer");
   return air::st_backward_impl(window, theta_inv, dcanvas, z, stop_new, thr, true, dwindow, dtheta_inv, dz,
-                               window_is_sigmoid, B, wh, ww, 1, ch, cw, static_cast<cudaStream_t>(stream));
+                               flags, B, wh, ww, 1, ch, cw, static_cast<cudaStream_t>(stream));
 }

@@ -141,7 +141,9 @@ def writeback_canvas_fwd(window, theta_inv, z, stop_new, thr, canvas_in, canvas_
 
 
 def writeback_canvas_bwd(window, theta_inv, z, stop_new, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw,
-                         window_is_sigmoid=False):
+                         window_is_sigmoid=False, axis_aligned_theta=False):
+    """flags of include/air_b200.h: AIR_WB_SIGMOID_WINDOW = 1, AIR_WB_AXIS_ALIGNED_THETA = 2 (dtheta_inv[1], [3] := 0)."""
+    flags = (1 if window_is_sigmoid else 0) | (2 if axis_aligned_theta else 0)
     check(lib().air_st_writeback_canvas_bwd(ptr(window), ptr(theta_inv), ptr(z), ptr(stop_new), float(thr),
-                                            ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), int(window_is_sigmoid),
+                                            ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), flags,
                                             window.shape[0], wh, ww, ch, cw, stream()), "air_st_writeback_canvas_bwd")
