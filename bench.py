@@ -112,7 +112,8 @@ def barrier(world):
 # ------------------------------------------------------------------------------------------
 # ST microbench (BASELINE.json configs[1]); algorithmic bytes per image from SURVEY.md 8(d)
 # ------------------------------------------------------------------------------------------
-ST_BYTES = {"crop_fwd": 13160, "crop_bwd": 13184, "writeback_canvas_fwd": 23168, "writeback_canvas_bwd": 16332}
+ST_BYTES = {"crop_fwd": 13160, "crop_bwd": 13184, "writeback_canvas_fwd": 23168, "writeback_canvas_bwd": 16332,
+            "writeback_canvas_bwd_full_dtheta": 16332}
 
 
 def st_inputs(B, dev, seed=1):
@@ -156,11 +157,16 @@ def st_kernels(d, B):
         c.check(L.air_st_writeback_canvas_fwd(p(d["win"]), p(d["thi"]), p(d["z"]), p(d["stop"]), 0.99, p(d["canvas"]),
                                               p(canvas_out), B, 28, 28, 50, 50, c.stream()), "wb_fwd")
 
-    def wb_bwd():
-        c.check(L.air_st_writeback_canvas_bwd(p(d["win"]), p(d["thi"]), p(d["z"]), p(d["stop"]), 0.99, p(d["dcanvas"]),
-                                              p(dwin), p(dth), p(dz), 0, B, 28, 28, 50, 50, c.stream()), "wb_bwd")
+    def wb_bwd(flags):
+        def f():
+            c.check(L.air_st_writeback_canvas_bwd(p(d["win"]), p(d["thi"]), p(d["z"]), p(d["stop"]), 0.99, p(d["dcanvas"]),
+                                                  p(dwin), p(dth), p(dz), flags, B, 28, 28, 50, 50, c.stream()), "wb_bwd")
+        return f
 
-    return {"crop_fwd": crop_fwd, "crop_bwd": crop_bwd, "writeback_canvas_fwd": wb_fwd, "writeback_canvas_bwd": wb_bwd}
+    # writeback_canvas_bwd is the call the model makes (AIR_WB_SIGMOID_WINDOW | AIR_WB_AXIS_ALIGNED_THETA: SigmoidGrad
+    # fused, only the four dtheta_inv entries the model consumes); *_full_dtheta is the general fused kernel (flags 0)
+    return {"crop_fwd": crop_fwd, "crop_bwd": crop_bwd, "writeback_canvas_fwd": wb_fwd, "writeback_canvas_bwd": wb_bwd(3),
+            "writeback_canvas_bwd_full_dtheta": wb_bwd(0)}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 65536, from the `ncu --set full` captures
@@ -168,7 +174,7 @@ def st_kernels(d, B):
 # 65536 images; r1_st_bwd_k1/k2_ncu_full.md).  The fused backward reads LESS than the algorithmic figure because
 # stopped images (30 % of the synthetic batch) never fetch their dCanvas rows.
 ST_NCU_TRAFFIC_B65536 = {"crop_fwd": 4 * (656.946e6 + 183.790e6), "crop_bwd": 862.487e6 + 5.773e6,
-                         "writeback_canvas_bwd": 606.910e6 + 186.340e6}
+                         "writeback_canvas_bwd_full_dtheta": 606.910e6 + 186.340e6}
 
 
 def time_launches(fn, steps, warmup):

@@ -598,22 +598,199 @@ __global__ void __launch_bounds__(kBwdThreads)
 // zeros of theta_inv and are written as 0 (the caller opts in with AIR_WB_AXIS_ALIGNED_THETA).
 // Images whose theta is not axis-aligned take a shared-memory-atomics path (all six entries).
 // =========================================================================================
-__device__ __forceinline__ void rect_1d(const Ent *tab, int n, int lane, int &lo, int &cnt) {
+// Shared-memory accessors on 32-bit shared-window addresses held in registers.  (Through C++ pointers nvcc
+// re-materialises the address of the extern shared array -- S2R CgaCtaId + 3 ALU ops -- inside every cold branch
+// of the scans; ncu r22 showed 14 instructions per run emission instead of 6.)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_i32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ Ent lds_ent(uint32_t a) {
+  Ent e;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.i0), "=r"(e.i1), "=f"(e.w1), "=f"(e.w0) : "r"(a));
+  return e;
+}
+
+// Table entries of the axis kernel: an in-range entry (two distinct corners, i1 == i0 + stride) keeps its
+// normalised grid coordinate in the i1 slot; a clipped entry is marked with a NaN pattern.
+constexpr int kEntClipped = 0x7fc00000;
+
+// first index and count of the in-range entries of a table with n <= 64 entries (they are contiguous: the
+// pixel coordinate is monotone in the output index); two ballots per warp
+__device__ __forceinline__ void rect_1d(uint32_t tab, int n, int lane, int &lo, int &cnt) {
   const int k1 = lane + 32;
-  const int2 a = *reinterpret_cast<const int2 *>(tab + min(lane, n - 1));
-  const int2 c = *reinterpret_cast<const int2 *>(tab + min(k1, n - 1));
-  const unsigned ma = __ballot_sync(0xffffffffu, lane < n && a.x != a.y);
-  const unsigned mb = __ballot_sync(0xffffffffu, k1 < n && c.x != c.y);
-  const unsigned long long m = (static_cast<unsigned long long>(mb) << 32) | ma;
+  const int a = lds_i32(tab + min(lane, n - 1) * 16 + 4), c = lds_i32(tab + min(k1, n - 1) * 16 + 4);
+  const unsigned ma = __ballot_sync(0xffffffffu, lane < n && a != kEntClipped);
+  const unsigned mb = __ballot_sync(0xffffffffu, k1 < n && c != kEntClipped);
   lo = 0;
   cnt = 0;
-  if (m) {
-    lo = __ffsll(static_cast<long long>(m)) - 1;
-    cnt = 64 - __clzll(static_cast<long long>(m)) - lo;
+  if (ma | mb) {
+    lo = ma ? __ffs(ma) - 1 : 31 + __ffs(mb);
+    const int hi = mb ? 63 - __clz(mb) : 31 - __clz(ma);
+    cnt = hi - lo + 1;
   }
 }
 
 constexpr int kAxisQS = 33;  // row stride of the transposed Q buffer [W][33]: conflict-free for both scans
+
+// The three scans.  CS / RS = +1 or -1: direction in which output columns / rows are visited so that the source
+// index is non-decreasing (-1 for a mirrored window, i.e. a negative scale).
+template <int H, int W, int OH, int OW, int CS, int RS>
+__device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ, uint32_t aCol, uint32_t aRow,
+                                           float *sPart, float *dUb, float zval, int sig, int c_lo, int nc, int r_lo,
+                                           int nr, int lane, int warp) {
+  constexpr int HW = H * W, QB = kAxisQS * 4;
+  const int cfirst = CS > 0 ? c_lo : c_lo + nc - 1, rfirst = RS > 0 ? r_lo : r_lo + nr - 1;
+  if (warp == 0) {
+    const bool jok = lane < W;
+    const int jj = jok ? lane : W - 1;
+    const uint32_t aUj = aU + jj * 4, aQj = aQ + jj * QB, q0 = aQ + lane * 4;
+    float *out = dUb + jj;
+    float t0 = 0.0f, t1 = 0.0f, sdy = 0.0f, sdyy = 0.0f, dot = 0.0f;
+    int icur = lds_i32(aRow + rfirst * 16);
+    for (int x = 0; x < icur; x += W)  // source rows above the first touched one
+      if (jok) out[x] = 0.0f;
+    auto emit = [&](int iw, float v) {  // source row iw / W of dU is complete
+      const float u = lds_f32(aUj + iw * 4);
+      dot = fmaf(v, u, dot);
+      float o = v * zval;
+      if (sig) o *= u * (1.0f - u);  // SigmoidGrad of the window fused into the store
+      if (jok) out[iw] = o;
+    };
+    for (int m0 = 0; m0 < nr; m0 += 32) {
+      const int mcount = min(32, nr - m0);
+      {  // pass 1: Q[m][j] = sum_c g[r(m)][c] Wx[c][j]; lane = row m0 + lane, columns in scan order
+        const int m = m0 + min(lane, mcount - 1);  // surplus lanes redo the last row into unused Q columns
+        uint32_t ga = aG + (((rfirst + m * RS) * OW + cfirst) << 2);
+        uint32_t ea = aCol + cfirst * 16;
+        int jcur = lds_i32(ea);
+        for (int x = 0; x < jcur; ++x) sts_f32(q0 + x * QB, 0.0f);
+        uint32_t qa = q0 + jcur * QB;
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int n = nc; n > 0; --n) {
+          const Ent ce = lds_ent(ea);
+          const float g = lds_f32(ga);
+          ea += CS * 16;
+          ga += CS * 4;
+          if (ce.i0 != jcur) {  // warp-uniform: depends on the column only
+            sts_f32(qa, s0);
+            if (ce.i0 == jcur + 1) {
+              s0 = s1;
+              qa += QB;
+            } else {
+              sts_f32(qa + QB, s1);
+              for (int x = jcur + 2; x < ce.i0; ++x) sts_f32(q0 + x * QB, 0.0f);
+              s0 = 0.0f;
+              qa = q0 + ce.i0 * QB;
+            }
+            s1 = 0.0f;
+            jcur = ce.i0;
+          }
+          s0 = fmaf(ce.w1, g, s0);
+          s1 = fmaf(ce.w0, g, s1);
+        }
+        sts_f32(qa, s0);
+        sts_f32(qa + QB, s1);
+        for (int x = jcur + 2; x < W; ++x) sts_f32(q0 + x * QB, 0.0f);
+      }
+      __syncwarp();
+      {  // pass 2: dU = Wy^T Q, lane = source column; d/dy and dz on the way
+        uint32_t ra = aRow + (rfirst + m0 * RS) * 16;
+        uint32_t qa = aQj;
+        for (int mm = mcount; mm > 0; --mm) {
+          const Ent re = lds_ent(ra);
+          const float t = lds_f32(qa);
+          ra += RS * 16;
+          qa += 4;
+          if (re.i0 != icur) {  // warp-uniform: depends on the row only
+            emit(icur, t0);
+            if (re.i0 == icur + W) {
+              t0 = t1;
+            } else {
+              emit(icur + W, t1);
+              for (int x = icur + 2 * W; x < re.i0; x += W)
+                if (jok) out[x] = 0.0f;
+              t0 = 0.0f;
+            }
+            t1 = 0.0f;
+            icur = re.i0;
+          }
+          t0 = fmaf(re.w1, t, t0);
+          t1 = fmaf(re.w0, t, t1);
+          const uint32_t ua = aUj + re.i0 * 4;
+          const float dyl = t * (lds_f32(ua + W * 4) - lds_f32(ua));
+          sdy += dyl;
+          sdyy = fmaf(dyl, __int_as_float(re.i1), sdyy);
+        }
+      }
+      __syncwarp();
+    }
+    emit(icur, t0);
+    emit(icur + W, t1);
+    for (int x = icur + 2 * W; x < HW; x += W)
+      if (jok) out[x] = 0.0f;
+    if (!jok) sdy = sdyy = dot = 0.0f;
+    sdy = warp_sum(sdy);
+    sdyy = warp_sum(sdyy);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      sPart[0] = sdy;
+      sPart[1] = sdyy;
+      sPart[2] = dot;
+    }
+  } else if (warp <= 2 && 32 * (warp - 1) < nc) {
+    // P-scan: lane = output column of the rectangle, rows in scan order; a finished row of P = Wy^T G is
+    // consumed at once: dx += P[i][c] * (U[i][j0(c)+1] - U[i][j0(c)])
+    const int k = 32 * (warp - 1) + lane;
+    const bool cok = k < nc;
+    const int c = c_lo + (cok ? k : nc - 1);
+    const Ent ce = lds_ent(aCol + c * 16);
+    const uint32_t aUc = aU + ce.i0 * 4;
+    uint32_t ga = aG + ((rfirst * OW + c) << 2);
+    uint32_t ra = aRow + rfirst * 16;
+    int icur = lds_i32(ra);
+    uint32_t ua = aUc + icur * 4;
+    float p0 = 0.0f, p1 = 0.0f, dx = 0.0f;
+    for (int n = nr; n > 0; --n) {
+      const Ent re = lds_ent(ra);
+      const float g = lds_f32(ga);
+      ra += RS * 16;
+      ga += RS * OW * 4;
+      if (re.i0 != icur) {  // warp-uniform: depends on the row only
+        dx = fmaf(p0, lds_f32(ua + 4) - lds_f32(ua), dx);
+        if (re.i0 == icur + W) {
+          p0 = p1;
+          ua += W * 4;
+        } else {
+          dx = fmaf(p1, lds_f32(ua + W * 4 + 4) - lds_f32(ua + W * 4), dx);
+          p0 = 0.0f;
+          ua = aUc + re.i0 * 4;
+        }
+        p1 = 0.0f;
+        icur = re.i0;
+      }
+      p0 = fmaf(re.w1, g, p0);
+      p1 = fmaf(re.w0, g, p1);
+    }
+    dx = fmaf(p0, lds_f32(ua + 4) - lds_f32(ua), dx);
+    dx = fmaf(p1, lds_f32(ua + W * 4 + 4) - lds_f32(ua + W * 4), dx);
+    if (!cok) dx = 0.0f;
+    const float a0 = warp_sum(dx * __int_as_float(ce.i1)), a2 = warp_sum(dx);
+    if (lane == 0) {
+      sPart[2 + 2 * warp] = a0;
+      sPart[3 + 2 * warp] = a2;
+    }
+  }
+}
 
 template <int H, int W, int OH, int OW>
 __global__ void __launch_bounds__(kBwdThreads, 11)
@@ -630,7 +807,6 @@ __global__ void __launch_bounds__(kBwdThreads, 11)
   float *sQ = sG + OHW;                                       // [W][QS] Q^T of the current 32-row block (warp 0)
   Ent *sCol = reinterpret_cast<Ent *>(sQ + W * QS);           // [OW]
   Ent *sRow = sCol + OW;                                      // [OH]
-  float *sGy = reinterpret_cast<float *>(sRow + OH);          // [OH] normalised grid y_t
   __shared__ uint64_t bar;
   __shared__ float sTh[8];
   __shared__ float sPart[8];
@@ -666,13 +842,9 @@ __global__ void __launch_bounds__(kBwdThreads, 11)
     const bool col = k < OW;
     const float gk = col ? linspace_pm1(k, OW) : linspace_pm1(k - OW, OH);
     const float diag = __ldg(th_g + (col ? 0 : 4)), trans = __ldg(th_g + (col ? 2 : 5));
-    const Ent e = make_ent(to_pixel(add_rn(mul_rn(diag, gk), trans), col ? W : H), col ? W : H, col ? 1 : W);
-    if (col) {
-      sCol[k] = e;
-    } else {
-      sRow[k - OW] = e;
-      sGy[k - OW] = gk;
-    }
+    Ent e = make_ent(to_pixel(add_rn(mul_rn(diag, gk), trans), col ? W : H), col ? W : H, col ? 1 : W);
+    e.i1 = e.i0 != e.i1 ? __float_as_int(gk) : kEntClipped;
+    sCol[k] = e;  // sRow follows sCol
   }
   __syncthreads();
   const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
@@ -719,148 +891,29 @@ __global__ void __launch_bounds__(kBwdThreads, 11)
     return;
   }
 
-  // ---- in-range rectangle, recomputed by every warp from the tables (two ballots each; saves a barrier)
-  int c_lo, nc, r_lo, nr;
-  rect_1d(sCol, OW, lane, c_lo, nc);
-  rect_1d(sRow, OH, lane, r_lo, nr);
-  if (nr == 0 || nc == 0) {  // window entirely outside the canvas (uniform)
-    for (int k = tid; k < (HW >> 2); k += kBwdThreads) reinterpret_cast<float4 *>(dUb)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < 6) dtheta[b * 6 + tid] = 0.0f;
-    if (tid == 0) dz[b] = 0.0f;
-    return;
-  }
-  // scan directions that make the source index non-decreasing (negative scale = mirrored window)
-  const bool c_up = sCol[c_lo + nc - 1].i0 >= sCol[c_lo].i0, r_up = sRow[r_lo + nr - 1].i0 >= sRow[r_lo].i0;
-  const int cfirst = c_up ? c_lo : c_lo + nc - 1, cstep = c_up ? 1 : -1;
-  const int rfirst = r_up ? r_lo : r_lo + nr - 1, rstep = r_up ? 1 : -1;
-  mbar_wait(&bar, 0);
-
-  if (warp == 0) {
-    const bool jok = lane < W;
-    const int jj = jok ? lane : W - 1;
-    const float *uj = sU + jj;
-    const float *qj = sQ + jj * QS;
-    float *dUj = dUb + jj;
-    float t0 = 0.0f, t1 = 0.0f, sdy = 0.0f, sdyy = 0.0f, dot = 0.0f;
-    int icur = sRow[rfirst].i0, next = 0;
-    auto emit = [&](int iw, float v) {  // source row iw / W of dU is complete (rows arrive in increasing order)
-      for (; next < iw; next += W)
-        if (jok) dUj[next] = 0.0f;
-      const float u = uj[iw];
-      dot = fmaf(v, u, dot);
-      float o = v * zval;
-      if (sig) o *= u * (1.0f - u);  // SigmoidGrad of the window fused into the store
-      if (jok) dUj[iw] = o;
-      next = iw + W;
-    };
-    for (int m0 = 0; m0 < nr; m0 += 32) {
-      const int mcount = min(32, nr - m0);
-      {  // pass 1: Q[m][j] = sum_c g[r(m)][c] Wx[c][j]; lane = row m0 + lane, columns in scan order
-        const int m = m0 + min(lane, mcount - 1);  // surplus lanes redo the last row into unused Q columns
-        const float *gp = sG + (rfirst + m * rstep) * OW + cfirst;
-        const Ent *ep = sCol + cfirst;
-        float *q = sQ + lane;
-        int jcur = ep->i0;
-        for (int x = 0; x < jcur; ++x) q[x * QS] = 0.0f;
-        float s0 = 0.0f, s1 = 0.0f;
-        for (int n = nc; n > 0; --n, gp += cstep, ep += cstep) {
-          const Ent ce = *ep;
-          const float g = *gp;
-          if (ce.i0 != jcur) {  // warp-uniform: depends on the column only
-            q[jcur * QS] = s0;
-            if (ce.i0 == jcur + 1) {
-              s0 = s1;
-            } else {
-              q[(jcur + 1) * QS] = s1;
-              for (int x = jcur + 2; x < ce.i0; ++x) q[x * QS] = 0.0f;
-              s0 = 0.0f;
-            }
-            s1 = 0.0f;
-            jcur = ce.i0;
-          }
-          s0 = fmaf(ce.w1, g, s0);
-          s1 = fmaf(ce.w0, g, s1);
-        }
-        q[jcur * QS] = s0;
-        q[(jcur + 1) * QS] = s1;
-        for (int x = jcur + 2; x < W; ++x) q[x * QS] = 0.0f;
-      }
-      __syncwarp();
-      {  // pass 2: dU = Wy^T Q, lane = source column; d/dy and dz on the way
-        const Ent *rp = sRow + rfirst + m0 * rstep;
-        const float *yp = sGy + rfirst + m0 * rstep;
-        for (int mm = 0; mm < mcount; ++mm, rp += rstep, yp += rstep) {
-          const Ent re = *rp;
-          const float t = qj[mm];
-          if (re.i0 != icur) {
-            emit(icur, t0);
-            if (re.i0 == icur + W) {
-              t0 = t1;
-            } else {
-              emit(icur + W, t1);
-              t0 = 0.0f;
-            }
-            t1 = 0.0f;
-            icur = re.i0;
-          }
-          t0 = fmaf(re.w1, t, t0);
-          t1 = fmaf(re.w0, t, t1);
-          const float *up = uj + re.i0;
-          const float dyl = t * (up[W] - up[0]);
-          sdy += dyl;
-          sdyy = fmaf(dyl, *yp, sdyy);
-        }
-      }
-      __syncwarp();
-    }
-    emit(icur, t0);
-    emit(icur + W, t1);
-    for (; next < HW; next += W)
-      if (jok) dUj[next] = 0.0f;
-    if (!jok) sdy = sdyy = dot = 0.0f;
-    sdy = warp_sum(sdy);
-    sdyy = warp_sum(sdyy);
-    dot = warp_sum(dot);
-    if (lane == 0) {
-      sPart[0] = sdy;
-      sPart[1] = sdyy;
-      sPart[2] = dot;
-    }
-  } else if (warp <= 2 && 32 * (warp - 1) < nc) {
-    // P-scan: lane = output column of the rectangle, rows in scan order
-    const int k = 32 * (warp - 1) + lane;
-    const bool cok = k < nc;
-    const int c = c_lo + (cok ? k : nc - 1);
-    const float *uc = sU + sCol[c].i0;
-    const float *gp = sG + rfirst * OW + c;
-    const int gstep = rstep * OW;
-    const Ent *rp = sRow + rfirst;
-    int icur = rp->i0;
-    float p0 = 0.0f, p1 = 0.0f, dx = 0.0f;
-    for (int n = nr; n > 0; --n, gp += gstep, rp += rstep) {
-      const Ent re = *rp;
-      const float g = *gp;
-      if (re.i0 != icur) {  // warp-uniform: depends on the row only
-        dx = fmaf(p0, uc[icur + 1] - uc[icur], dx);
-        if (re.i0 == icur + W) {
-          p0 = p1;
-        } else {
-          dx = fmaf(p1, uc[icur + W + 1] - uc[icur + W], dx);
-          p0 = 0.0f;
-        }
-        p1 = 0.0f;
-        icur = re.i0;
-      }
-      p0 = fmaf(re.w1, g, p0);
-      p1 = fmaf(re.w0, g, p1);
-    }
-    dx = fmaf(p0, uc[icur + 1] - uc[icur], dx);
-    dx = fmaf(p1, uc[icur + W + 1] - uc[icur + W], dx);
-    if (!cok) dx = 0.0f;
-    const float a0 = warp_sum(dx * linspace_pm1(c, OW)), a2 = warp_sum(dx);
-    if (lane == 0) {
-      sPart[2 + 2 * warp] = a0;
-      sPart[3 + 2 * warp] = a2;
+  if (warp < 3) {
+    const uint32_t aU = smem_u32(sU), aG = smem_u32(sG), aQ = smem_u32(sQ), aCol = smem_u32(sCol), aRow = smem_u32(sRow);
+    // in-range rectangle, recomputed by each working warp from the tables (two ballots per axis; saves a barrier)
+    int c_lo, nc, r_lo, nr;
+    rect_1d(aCol, OW, lane, c_lo, nc);
+    rect_1d(aRow, OH, lane, r_lo, nr);
+    if (nr == 0 || nc == 0) {  // window entirely outside the canvas: every gradient is zero (sPart stays 0)
+      mbar_wait(&bar, 0);      // the bulk copies must have landed before the CTA may exit
+      if (warp == 0)
+        for (int k = lane; k < (HW >> 2); k += 32) reinterpret_cast<float4 *>(dUb)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      // scan directions that make the source index non-decreasing (negative scale = mirrored window)
+      const bool c_up = lds_i32(aCol + (c_lo + nc - 1) * 16) >= lds_i32(aCol + c_lo * 16);
+      const bool r_up = lds_i32(aRow + (r_lo + nr - 1) * 16) >= lds_i32(aRow + r_lo * 16);
+      mbar_wait(&bar, 0);
+      if (c_up && r_up)
+        axis_scans<H, W, OH, OW, 1, 1>(aU, aG, aQ, aCol, aRow, sPart, dUb, zval, sig, c_lo, nc, r_lo, nr, lane, warp);
+      else if (c_up)
+        axis_scans<H, W, OH, OW, 1, -1>(aU, aG, aQ, aCol, aRow, sPart, dUb, zval, sig, c_lo, nc, r_lo, nr, lane, warp);
+      else if (r_up)
+        axis_scans<H, W, OH, OW, -1, 1>(aU, aG, aQ, aCol, aRow, sPart, dUb, zval, sig, c_lo, nc, r_lo, nr, lane, warp);
+      else
+        axis_scans<H, W, OH, OW, -1, -1>(aU, aG, aQ, aCol, aRow, sPart, dUb, zval, sig, c_lo, nc, r_lo, nr, lane, warp);
     }
   }
   __syncthreads();
@@ -1023,7 +1076,7 @@ template <int H_, int W_, int OH_, int OW_>
 static int launch_wb_bwd_axis(const float *U, const float *theta, const float *dcanvas, const float *z, const float *stop,
                               float thr, float *dU, float *dtheta, float *dz, int sig, int64_t B, cudaStream_t s) {
   auto kern = st_wb_bwd_axis<H_, W_, OH_, OW_>;
-  constexpr size_t smem = (static_cast<size_t>(H_) * W_ + OH_ * OW_ + W_ * kAxisQS + OH_) * 4 + (OW_ + OH_) * sizeof(Ent);
+  constexpr size_t smem = (static_cast<size_t>(H_) * W_ + OH_ * OW_ + W_ * kAxisQS) * 4 + (OW_ + OH_) * sizeof(Ent);
   static_assert(smem <= 48 * 1024, "no opt-in needed");
   static bool once = false;
   if (!once) {  // ask for the largest shared-memory carve-out so that 11 CTAs fit on an SM
