@@ -676,11 +676,16 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
         for (int x = 0; x < jcur; ++x) sts_f32(q0 + x * QB, 0.0f);
         uint32_t qa = q0 + jcur * QB;
         float s0 = 0.0f, s1 = 0.0f;
+        // software pipeline: the next column's entry and gradient are fetched before this column's (branchy)
+        // run logic, so a lone warp does not expose the shared-memory latency every iteration.  The read one
+        // past the last column stays inside the CTA's shared memory and is never used.
+        Ent ce = lds_ent(ea);
+        float g = lds_f32(ga);
         for (int n = nc; n > 0; --n) {
-          const Ent ce = lds_ent(ea);
-          const float g = lds_f32(ga);
-          ea += CS * 16;
-          ga += CS * 4;
+          ea += static_cast<uint32_t>(CS * 16);
+          ga += static_cast<uint32_t>(CS * 4);
+          const Ent ce_n = lds_ent(ea);
+          const float g_n = lds_f32(ga);
           if (ce.i0 != jcur) {  // warp-uniform: depends on the column only
             sts_f32(qa, s0);
             if (ce.i0 == jcur + 1) {
@@ -697,6 +702,8 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
           }
           s0 = fmaf(ce.w1, g, s0);
           s1 = fmaf(ce.w0, g, s1);
+          ce = ce_n;
+          g = g_n;
         }
         sts_f32(qa, s0);
         sts_f32(qa + QB, s1);
@@ -706,11 +713,15 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
       {  // pass 2: dU = Wy^T Q, lane = source column; d/dy and dz on the way
         uint32_t ra = aRow + (rfirst + m0 * RS) * 16;
         uint32_t qa = aQj;
+        Ent re = lds_ent(ra);
+        float t = lds_f32(qa);
         for (int mm = mcount; mm > 0; --mm) {
-          const Ent re = lds_ent(ra);
-          const float t = lds_f32(qa);
-          ra += RS * 16;
+          ra += static_cast<uint32_t>(RS * 16);
           qa += 4;
+          const Ent re_n = lds_ent(ra);  // software pipeline, as in pass 1
+          const float t_n = lds_f32(qa);
+          const uint32_t ua = aUj + re.i0 * 4;
+          const float du = lds_f32(ua + W * 4) - lds_f32(ua);
           if (re.i0 != icur) {  // warp-uniform: depends on the row only
             emit(icur, t0);
             if (re.i0 == icur + W) {
@@ -726,10 +737,11 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
           }
           t0 = fmaf(re.w1, t, t0);
           t1 = fmaf(re.w0, t, t1);
-          const uint32_t ua = aUj + re.i0 * 4;
-          const float dyl = t * (lds_f32(ua + W * 4) - lds_f32(ua));
+          const float dyl = t * du;
           sdy += dyl;
           sdyy = fmaf(dyl, __int_as_float(re.i1), sdyy);
+          re = re_n;
+          t = t_n;
         }
       }
       __syncwarp();
@@ -760,11 +772,13 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
     int icur = lds_i32(ra);
     uint32_t ua = aUc + icur * 4;
     float p0 = 0.0f, p1 = 0.0f, dx = 0.0f;
+    Ent re = lds_ent(ra);
+    float g = lds_f32(ga);
     for (int n = nr; n > 0; --n) {
-      const Ent re = lds_ent(ra);
-      const float g = lds_f32(ga);
-      ra += RS * 16;
-      ga += RS * OW * 4;
+      ra += static_cast<uint32_t>(RS * 16);
+      ga += static_cast<uint32_t>(RS * OW * 4);
+      const Ent re_n = lds_ent(ra);  // software pipeline, as in pass 1
+      const float g_n = lds_f32(ga);
       if (re.i0 != icur) {  // warp-uniform: depends on the row only
         dx = fmaf(p0, lds_f32(ua + 4) - lds_f32(ua), dx);
         if (re.i0 == icur + W) {
@@ -780,6 +794,8 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
       }
       p0 = fmaf(re.w1, g, p0);
       p1 = fmaf(re.w0, g, p1);
+      re = re_n;
+      g = g_n;
     }
     dx = fmaf(p0, lds_f32(ua + 4) - lds_f32(ua), dx);
     dx = fmaf(p1, lds_f32(ua + W * 4 + 4) - lds_f32(ua + W * 4), dx);
@@ -792,13 +808,16 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
   }
 }
 
+constexpr int kAxisThreads = 96;  // three working warps (the fourth of a 128-thread CTA only idled at the barrier)
+
 template <int H, int W, int OH, int OW>
-__global__ void __launch_bounds__(kBwdThreads, 11)
+__global__ void __launch_bounds__(kAxisThreads, 11)
     st_wb_bwd_axis(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dcanvas,
                    const float *__restrict__ zp, const float *__restrict__ stop, float thr, float *__restrict__ dU,
                    float *__restrict__ dtheta, float *__restrict__ dz, int sig, int64_t B) {
   static_assert(W <= 32 && OW <= 64 && OH <= 64 && (H * W) % 4 == 0 && (OH * OW) % 4 == 0, "unsupported tile");
-  static_assert(W * kAxisQS >= H * W && OH * OW >= 7 * kBwdThreads, "fallback path aliases these buffers");
+  static_assert(W * kAxisQS >= H * W, "the fallback path keeps its dU tile in the Q buffer");
+  static_assert(OW + OH <= kAxisThreads + 32, "table construction: one entry per thread + a tail on warp 2");
   pdl_sync();  // PDL: no global access before the previous grid has completed
   constexpr int HW = H * W, OHW = OH * OW, QS = kAxisQS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -806,10 +825,11 @@ __global__ void __launch_bounds__(kBwdThreads, 11)
   float *sG = sU + HW;                                        // [OHW]  upstream gradient tile (dcanvas)
   float *sQ = sG + OHW;                                       // [W][QS] Q^T of the current 32-row block (warp 0)
   Ent *sCol = reinterpret_cast<Ent *>(sQ + W * QS);           // [OW]
-  Ent *sRow = sCol + OW;                                      // [OH]
+  Ent *sRow = sCol + OW;                                      // [OH] (+1 pad entry for the prefetch past the end)
   __shared__ uint64_t bar;
   __shared__ float sTh[8];
   __shared__ float sPart[8];
+  __shared__ float sRed[kAxisThreads / 32][8];  // fallback path only
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.x;
@@ -819,7 +839,7 @@ __global__ void __launch_bounds__(kBwdThreads, 11)
   const bool live = __ldg(stop + b) < thr;
   const float zval = __ldg(zp + b);
   if (!live) {  // whole image masked out: every gradient is exactly zero (uniform branch)
-    for (int k = tid; k < (HW >> 2); k += kBwdThreads) reinterpret_cast<float4 *>(dUb)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = tid; k < (HW >> 2); k += kAxisThreads) reinterpret_cast<float4 *>(dUb)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < 6) dtheta[b * 6 + tid] = 0.0f;
     if (tid == 0) dz[b] = 0.0f;
     return;
@@ -835,28 +855,31 @@ __global__ void __launch_bounds__(kBwdThreads, 11)
     bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
     bulk_g2s(sG, dcanvas + b * OHW, OHW * 4u, &bar);
   }
-  // ---- tables (overlap the bulk copies)
+  // ---- tables (overlap the bulk copies): one entry per thread; the tail goes to warp 2, which has the
+  //      least scan work (warp 0 is the critical path)
   if (tid < 6) sTh[tid] = __ldg(th_g + tid);
   if (tid == 6) sTh[6] = (__ldg(th_g + 1) == 0.0f && __ldg(th_g + 3) == 0.0f) ? 1.0f : 0.0f;
-  for (int k = tid; k < OW + OH; k += kBwdThreads) {
+  auto build = [&](int k) {
     const bool col = k < OW;
     const float gk = col ? linspace_pm1(k, OW) : linspace_pm1(k - OW, OH);
     const float diag = __ldg(th_g + (col ? 0 : 4)), trans = __ldg(th_g + (col ? 2 : 5));
     Ent e = make_ent(to_pixel(add_rn(mul_rn(diag, gk), trans), col ? W : H), col ? W : H, col ? 1 : W);
     e.i1 = e.i0 != e.i1 ? __float_as_int(gk) : kEntClipped;
     sCol[k] = e;  // sRow follows sCol
-  }
+  };
+  if (tid < OW + OH) build(tid);
+  if (warp == 2 && tid + 32 < OW + OH) build(tid + 32);
   __syncthreads();
   const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
 
   if (sTh[6] == 0.0f) {
     // ---- general theta (rotation / shear): per-pixel coordinates, shared-memory atomics for dU
     float *sTile = sQ;
-    for (int k = tid; k < HW; k += kBwdThreads) sTile[k] = 0.0f;
+    for (int k = tid; k < HW; k += kAxisThreads) sTile[k] = 0.0f;
     __syncthreads();
     mbar_wait(&bar, 0);
     float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int q = tid; q < OHW; q += kBwdThreads) {
+    for (int q = tid; q < OHW; q += kAxisThreads) {
       const int r = q / OW, c = q - r * OW;
       Ent ce, re;
       float xt, yt;
@@ -877,21 +900,27 @@ __global__ void __launch_bounds__(kBwdThreads, 11)
       atomicAdd(&sTile[re.i0 + ce.i1], wc * g);
       atomicAdd(&sTile[re.i1 + ce.i1], wd * g);
     }
-    block_sum_many<7>(acc, sG);  // its leading barrier orders the scratch writes after the last reads of sG
-    if (tid == 0) {
-      const float sx = 0.5f * wf, sy = 0.5f * hf;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) dtheta[b * 6 + k] = acc[k] * (k < 3 ? sx : sy);
-      dz[b] = acc[6];
+    for (int k = 0; k < 7; ++k) {
+      const float v = warp_sum(acc[k]);
+      if (lane == 0) sRed[warp][k] = v;
     }
-    for (int k = tid; k < HW; k += kBwdThreads) {
+    __syncthreads();  // also: every atomic of the tile has landed
+    if (tid < 7) {
+      float v = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kAxisThreads / 32; ++w) v += sRed[w][tid];
+      if (tid < 6) dtheta[b * 6 + tid] = v * 0.5f * (tid < 3 ? wf : hf);
+      else dz[b] = v;
+    }
+    for (int k = tid; k < HW; k += kAxisThreads) {
       const float u = sU[k];
       dUb[k] = sig ? sTile[k] * u * (1.0f - u) : sTile[k];
     }
     return;
   }
 
-  if (warp < 3) {
+  {
     const uint32_t aU = smem_u32(sU), aG = smem_u32(sG), aQ = smem_u32(sQ), aCol = smem_u32(sCol), aRow = smem_u32(sRow);
     // in-range rectangle, recomputed by each working warp from the tables (two ballots per axis; saves a barrier)
     int c_lo, nc, r_lo, nr;
@@ -1076,7 +1105,8 @@ template <int H_, int W_, int OH_, int OW_>
 static int launch_wb_bwd_axis(const float *U, const float *theta, const float *dcanvas, const float *z, const float *stop,
                               float thr, float *dU, float *dtheta, float *dz, int sig, int64_t B, cudaStream_t s) {
   auto kern = st_wb_bwd_axis<H_, W_, OH_, OW_>;
-  constexpr size_t smem = (static_cast<size_t>(H_) * W_ + OH_ * OW_ + W_ * kAxisQS) * 4 + (OW_ + OH_) * sizeof(Ent);
+  // + one entry: the software-pipelined scans prefetch one element past the last table row
+  constexpr size_t smem = (static_cast<size_t>(H_) * W_ + OH_ * OW_ + W_ * kAxisQS) * 4 + (OW_ + OH_ + 1) * sizeof(Ent);
   static_assert(smem <= 48 * 1024, "no opt-in needed");
   static bool once = false;
   if (!once) {  // ask for the largest shared-memory carve-out so that 11 CTAs fit on an SM
@@ -1084,7 +1114,7 @@ static int launch_wb_bwd_axis(const float *U, const float *theta, const float *d
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_wb_bwd_axis): %s", cudaGetErrorString(e));
     once = true;
   }
-  AIR_LAUNCH(kern, static_cast<unsigned>(B), kBwdThreads, smem, s, U, theta, dcanvas, z, stop, thr, dU, dtheta, dz, sig, B);
+  AIR_LAUNCH(kern, static_cast<unsigned>(B), kAxisThreads, smem, s, U, theta, dcanvas, z, stop, thr, dU, dtheta, dz, sig, B);
   count_launch();
   return check_launch("st_wb_bwd_axis");
 }
