@@ -836,39 +836,40 @@ __global__ void __launch_bounds__(kAxisThreads, 11)
   const float *th_g = theta + b * 6;
   float *dUb = dU + b * HW;
 
-  const bool live = __ldg(stop + b) < thr;
+  // every global scalar this thread needs is requested before the first use, so that the CTA pays ONE DRAM
+  // round trip (not stop -> theta in sequence) before its bulk copies are issued and its tables are built
+  const int k0 = tid, k1 = tid + 32;  // table entries of this thread (k1 only for warp 2, if < OW + OH)
+  const float stop_b = __ldg(stop + b);
   const float zval = __ldg(zp + b);
-  if (!live) {  // whole image masked out: every gradient is exactly zero (uniform branch)
+  const float diag0 = __ldg(th_g + (k0 < OW ? 0 : 4)), trans0 = __ldg(th_g + (k0 < OW ? 2 : 5));
+  const float off1 = __ldg(th_g + 1), off3 = __ldg(th_g + 3);
+  if (!(stop_b < thr)) {  // whole image masked out: every gradient is exactly zero (uniform branch)
     for (int k = tid; k < (HW >> 2); k += kAxisThreads) reinterpret_cast<float4 *>(dUb)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < 6) dtheta[b * 6 + tid] = 0.0f;
     if (tid == 0) dz[b] = 0.0f;
     return;
   }
-  if (tid == 0) {
+  if (tid == 0) {  // only this thread touches the barrier before the __syncthreads below
     mbar_init(&bar, 1);
     fence_mbar_init();
-  }
-  if (tid < 8) sPart[tid] = 0.0f;
-  __syncthreads();
-  if (tid == 0) {
     mbar_expect_tx(&bar, static_cast<uint32_t>(HW + OHW) * 4u);
     bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
     bulk_g2s(sG, dcanvas + b * OHW, OHW * 4u, &bar);
   }
+  if (tid < 8) sPart[tid] = 0.0f;
   // ---- tables (overlap the bulk copies): one entry per thread; the tail goes to warp 2, which has the
   //      least scan work (warp 0 is the critical path)
   if (tid < 6) sTh[tid] = __ldg(th_g + tid);
-  if (tid == 6) sTh[6] = (__ldg(th_g + 1) == 0.0f && __ldg(th_g + 3) == 0.0f) ? 1.0f : 0.0f;
-  auto build = [&](int k) {
+  if (tid == 6) sTh[6] = (off1 == 0.0f && off3 == 0.0f) ? 1.0f : 0.0f;
+  auto build = [&](int k, float diag, float trans) {
     const bool col = k < OW;
     const float gk = col ? linspace_pm1(k, OW) : linspace_pm1(k - OW, OH);
-    const float diag = __ldg(th_g + (col ? 0 : 4)), trans = __ldg(th_g + (col ? 2 : 5));
     Ent e = make_ent(to_pixel(add_rn(mul_rn(diag, gk), trans), col ? W : H), col ? W : H, col ? 1 : W);
     e.i1 = e.i0 != e.i1 ? __float_as_int(gk) : kEntClipped;
     sCol[k] = e;  // sRow follows sCol
   };
-  if (tid < OW + OH) build(tid);
-  if (warp == 2 && tid + 32 < OW + OH) build(tid + 32);
+  if (k0 < OW + OH) build(k0, diag0, trans0);
+  if (warp == 2 && k1 < OW + OH) build(k1, __ldg(th_g + (k1 < OW ? 0 : 4)), __ldg(th_g + (k1 < OW ? 2 : 5)));
   __syncthreads();
   const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
 
