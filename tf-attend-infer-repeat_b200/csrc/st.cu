@@ -644,11 +644,36 @@ constexpr int kAxisQS = 33;  // row stride of the transposed Q buffer [W][33]: c
 
 // The three scans.  CS / RS = +1 or -1: direction in which output columns / rows are visited so that the source
 // index is non-decreasing (-1 for a mirrored window, i.e. a negative scale).
+//
+// Every scan has the same shape: walk the rectangle along one axis with two running sums (weights w1 -> source
+// index i0, w0 -> i0 + 1); when the source index of the next element has advanced, flush the first sum to its
+// finished source index and shift (a `while`, so a jump over several source indices flushes zeros for the gap).
+// The control flow depends on the table entry only => warp-uniform.  The loops are unrolled by two with the
+// operands of the next element fetched before the current element's (branchy) flush logic runs: a lone warp
+// would otherwise expose the shared-memory latency on every iteration.  The fetch one element past the end
+// stays inside the CTA's shared memory (one pad entry behind the tables) and is never used.
+#define AIR_SCAN2(n_total, LOAD_A, LOAD_B, ADVANCE2, STEP_A, STEP_B) \
+  {                                                                  \
+    int n_left = (n_total);                                          \
+    LOAD_A;                                                          \
+    while (true) {                                                   \
+      LOAD_B;                                                        \
+      STEP_A;                                                        \
+      if (--n_left == 0) break;                                      \
+      ADVANCE2;                                                      \
+      LOAD_A;                                                        \
+      STEP_B;                                                        \
+      if (--n_left == 0) break;                                      \
+    }                                                                \
+  }
+
 template <int H, int W, int OH, int OW, int CS, int RS>
 __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ, uint32_t aCol, uint32_t aRow,
                                            float *sPart, float *dUb, float zval, int sig, int c_lo, int nc, int r_lo,
                                            int nr, int lane, int warp) {
   constexpr int HW = H * W, QB = kAxisQS * 4;
+  constexpr uint32_t E1 = static_cast<uint32_t>(CS * 16), G1 = static_cast<uint32_t>(CS * 4);      // pass 1 strides
+  constexpr uint32_t R1 = static_cast<uint32_t>(RS * 16), GR = static_cast<uint32_t>(RS * OW * 4);  // row strides
   const int cfirst = CS > 0 ? c_lo : c_lo + nc - 1, rfirst = RS > 0 ? r_lo : r_lo + nr - 1;
   if (warp == 0) {
     const bool jok = lane < W;
@@ -676,35 +701,22 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
         for (int x = 0; x < jcur; ++x) sts_f32(q0 + x * QB, 0.0f);
         uint32_t qa = q0 + jcur * QB;
         float s0 = 0.0f, s1 = 0.0f;
-        // software pipeline: the next column's entry and gradient are fetched before this column's (branchy)
-        // run logic, so a lone warp does not expose the shared-memory latency every iteration.  The read one
-        // past the last column stays inside the CTA's shared memory and is never used.
-        Ent ce = lds_ent(ea);
-        float g = lds_f32(ga);
-        for (int n = nc; n > 0; --n) {
-          ea += static_cast<uint32_t>(CS * 16);
-          ga += static_cast<uint32_t>(CS * 4);
-          const Ent ce_n = lds_ent(ea);
-          const float g_n = lds_f32(ga);
-          if (ce.i0 != jcur) {  // warp-uniform: depends on the column only
+        auto step = [&](const Ent &ce, float g) {
+#pragma unroll 1
+          while (jcur < ce.i0) {  // warp-uniform: depends on the column only
             sts_f32(qa, s0);
-            if (ce.i0 == jcur + 1) {
-              s0 = s1;
-              qa += QB;
-            } else {
-              sts_f32(qa + QB, s1);
-              for (int x = jcur + 2; x < ce.i0; ++x) sts_f32(q0 + x * QB, 0.0f);
-              s0 = 0.0f;
-              qa = q0 + ce.i0 * QB;
-            }
+            s0 = s1;
             s1 = 0.0f;
-            jcur = ce.i0;
+            qa += QB;
+            ++jcur;
           }
           s0 = fmaf(ce.w1, g, s0);
           s1 = fmaf(ce.w0, g, s1);
-          ce = ce_n;
-          g = g_n;
-        }
+        };
+        Ent ca, cb;
+        float va, vb;
+        AIR_SCAN2(nc, (ca = lds_ent(ea), va = lds_f32(ga)), (cb = lds_ent(ea + E1), vb = lds_f32(ga + G1)),
+                  (ea += 2 * E1, ga += 2 * G1), step(ca, va), step(cb, vb));
         sts_f32(qa, s0);
         sts_f32(qa + QB, s1);
         for (int x = jcur + 2; x < W; ++x) sts_f32(q0 + x * QB, 0.0f);
@@ -713,36 +725,27 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
       {  // pass 2: dU = Wy^T Q, lane = source column; d/dy and dz on the way
         uint32_t ra = aRow + (rfirst + m0 * RS) * 16;
         uint32_t qa = aQj;
-        Ent re = lds_ent(ra);
-        float t = lds_f32(qa);
-        for (int mm = mcount; mm > 0; --mm) {
-          ra += static_cast<uint32_t>(RS * 16);
-          qa += 4;
-          const Ent re_n = lds_ent(ra);  // software pipeline, as in pass 1
-          const float t_n = lds_f32(qa);
+        auto step = [&](const Ent &re, float t) {
           const uint32_t ua = aUj + re.i0 * 4;
           const float du = lds_f32(ua + W * 4) - lds_f32(ua);
-          if (re.i0 != icur) {  // warp-uniform: depends on the row only
+#pragma unroll 1
+    #pragma unroll 1
+      while (icur < re.i0) {  // warp-uniform: depends on the row only
             emit(icur, t0);
-            if (re.i0 == icur + W) {
-              t0 = t1;
-            } else {
-              emit(icur + W, t1);
-              for (int x = icur + 2 * W; x < re.i0; x += W)
-                if (jok) out[x] = 0.0f;
-              t0 = 0.0f;
-            }
+            t0 = t1;
             t1 = 0.0f;
-            icur = re.i0;
+            icur += W;
           }
           t0 = fmaf(re.w1, t, t0);
           t1 = fmaf(re.w0, t, t1);
           const float dyl = t * du;
           sdy += dyl;
           sdyy = fmaf(dyl, __int_as_float(re.i1), sdyy);
-          re = re_n;
-          t = t_n;
-        }
+        };
+        Ent ra_e, rb_e;
+        float va, vb;
+        AIR_SCAN2(mcount, (ra_e = lds_ent(ra), va = lds_f32(qa)), (rb_e = lds_ent(ra + R1), vb = lds_f32(qa + 4)),
+                  (ra += 2 * R1, qa += 8), step(ra_e, va), step(rb_e, vb));
       }
       __syncwarp();
     }
@@ -766,37 +769,26 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
     const bool cok = k < nc;
     const int c = c_lo + (cok ? k : nc - 1);
     const Ent ce = lds_ent(aCol + c * 16);
-    const uint32_t aUc = aU + ce.i0 * 4;
     uint32_t ga = aG + ((rfirst * OW + c) << 2);
     uint32_t ra = aRow + rfirst * 16;
     int icur = lds_i32(ra);
-    uint32_t ua = aUc + icur * 4;
+    uint32_t ua = aU + (ce.i0 + icur) * 4;
     float p0 = 0.0f, p1 = 0.0f, dx = 0.0f;
-    Ent re = lds_ent(ra);
-    float g = lds_f32(ga);
-    for (int n = nr; n > 0; --n) {
-      ra += static_cast<uint32_t>(RS * 16);
-      ga += static_cast<uint32_t>(RS * OW * 4);
-      const Ent re_n = lds_ent(ra);  // software pipeline, as in pass 1
-      const float g_n = lds_f32(ga);
-      if (re.i0 != icur) {  // warp-uniform: depends on the row only
+    auto step = [&](const Ent &re, float g) {
+      while (icur < re.i0) {  // warp-uniform: depends on the row only
         dx = fmaf(p0, lds_f32(ua + 4) - lds_f32(ua), dx);
-        if (re.i0 == icur + W) {
-          p0 = p1;
-          ua += W * 4;
-        } else {
-          dx = fmaf(p1, lds_f32(ua + W * 4 + 4) - lds_f32(ua + W * 4), dx);
-          p0 = 0.0f;
-          ua = aUc + re.i0 * 4;
-        }
+        p0 = p1;
         p1 = 0.0f;
-        icur = re.i0;
+        ua += W * 4;
+        icur += W;
       }
       p0 = fmaf(re.w1, g, p0);
       p1 = fmaf(re.w0, g, p1);
-      re = re_n;
-      g = g_n;
-    }
+    };
+    Ent ra_e, rb_e;
+    float va, vb;
+    AIR_SCAN2(nr, (ra_e = lds_ent(ra), va = lds_f32(ga)), (rb_e = lds_ent(ra + R1), vb = lds_f32(ga + GR)),
+              (ra += 2 * R1, ga += 2 * GR), step(ra_e, va), step(rb_e, vb));
     dx = fmaf(p0, lds_f32(ua + 4) - lds_f32(ua), dx);
     dx = fmaf(p1, lds_f32(ua + W * 4 + 4) - lds_f32(ua + W * 4), dx);
     if (!cok) dx = 0.0f;
@@ -807,6 +799,7 @@ __device__ __forceinline__ void axis_scans(uint32_t aU, uint32_t aG, uint32_t aQ
     }
   }
 }
+#undef AIR_SCAN2
 
 constexpr int kAxisThreads = 96;  // three working warps (the fourth of a 128-thread CTA only idled at the barrier)
 
