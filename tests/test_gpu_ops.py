@@ -85,6 +85,20 @@ def test_gemm_errors():
         ops.gemm(a, a, torch.zeros(4, 4, device=DEV), epi=K.EPI_MUL_DRELU)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gemm_k0_is_cinit_plus_bias(mode):
+    """K == 0 (the first LSTM step: zero initial state, air_model.py:540-542): out = epi(Cinit + bias), no operands read."""
+    torch.manual_seed(3)
+    h0, Kh = torch.zeros(128, 256, device=DEV), torch.randn(256, 1024, device=DEV)
+    cinit, bias = torch.randn(128, 1024, device=DEV), torch.randn(1024, device=DEV)
+    out = torch.full((128, 1024), 7.0, device=DEV)
+    ops.gemm(h0[:, :0], Kh[:0], out, Cinit=cinit, bias=bias, mode=mode)
+    assert torch.equal(out, cinit + bias)
+    full = torch.empty_like(out)
+    ops.gemm(h0, Kh, full, Cinit=cinit, bias=bias, mode=0)     # fma(0, k, acc) == acc: same bits as the full GEMM
+    assert torch.equal(out, full)
+
+
 def test_lstm_pointwise_fwd_bwd():
     torch.manual_seed(0)
     B, H = 37, 256

@@ -150,7 +150,7 @@ extern "C" int air_gemm_ex(const float *A, const float *B, float *C, const float
   AIR_REQUIRE(M >= 0 && N >= 0 && K >= 0 && M < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "air_gemm: bad shape M=%lld N=%d K=%d",
               (long long)M, N, K);
   if (M == 0 || N == 0) return AIR_OK;
-  AIR_REQUIRE(A && B && C, AIR_ERR_NULL, "air_gemm: null pointer");
+  AIR_REQUIRE(((A && B) || K == 0) && C, AIR_ERR_NULL, "air_gemm: null pointer");  // K == 0: C = epi(Cinit + bias)
   AIR_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, AIR_ERR_BAD_SHAPE,
               "air_gemm: leading dimension too small (lda=%d ldb=%d ldc=%d)", lda, ldb, ldc);
   AIR_REQUIRE(epilogue >= AIR_EPI_NONE && epilogue <= AIR_EPI_SIGMOID_NOISE, AIR_ERR_BAD_SHAPE, "air_gemm: bad epilogue %d",

@@ -336,12 +336,9 @@ __global__ void __launch_bounds__(kBwdThreads)
     return;
   }
 
-  if (tid == 0) {
+  if (tid == 0) {  // only this thread touches the barrier before the __syncthreads that follows the tables
     mbar_init(&bar, 1);
     fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
     mbar_expect_tx(&bar, static_cast<uint32_t>(HW + OHW) * 4u);
     bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
     bulk_g2s(sG, dout + b * OHW, OHW * 4u, &bar);
@@ -403,14 +400,17 @@ __global__ void __launch_bounds__(kBwdThreads)
       const int c = c_lo + (cok ? cb + lane : 0);
       const Ent ce = sCol[c];
       const float xt = sGrid[c];
-      const float *u0 = sU + ce.i0, *u1 = sU + ce.i1;
+      // every pixel of the rectangle is in range: its corners are i0, i0 + 1 (columns) and i0, i0 + W (rows),
+      // so one address per pixel serves the four corner loads
+      const float *u0 = sU + ce.i0;
       float sdx = 0.f, sdxy = 0.f, sdy = 0.f, sdyy = 0.f;
       for (int ro = warp; ro < nr; ro += kBwdWarps) {
         const int r = r_lo + ro;
         const Ent re = sRow[r];
         const float yt = sGrid[OW + r];
         if (cok) {
-          const float Ia = u0[re.i0], Ib = u0[re.i1], Ic = u1[re.i0], Id = u1[re.i1];
+          const float *pu = u0 + re.i0;
+          const float Ia = pu[0], Ib = pu[W], Ic = pu[1], Id = pu[W + 1];
           float g = sG[r * OW + c];
           if (FUSED) {
             if (!dU) {  // (dz without dU: not used by the model; dz normally comes from <dU / z, U>)
