@@ -130,6 +130,52 @@ static int launch_simt(const float *A, const float *B, float *C, const float *Ci
   return check_launch("gemm_simt");
 }
 
+// K == 0: no products; C = epi((Cinit + bias)) elementwise (the first LSTM step, whose initial state is zero:
+// air_model.py:540-542).  Same rounding as the GEMM kernels' epilogue: acc = Cinit, then + bias, then the activation.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    gemm_k0_kernel(float *C, const float *Cinit, const float *__restrict__ bias, const float *aux, int M, int N, int ldc,
+                   int epi, float epi_param) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
+  const int NV = N / VEC;
+  const int64_t total = static_cast<int64_t>(M) * NV;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = e / NV;
+    const int n = static_cast<int>(e - m * NV) * VEC;
+    const int64_t o = m * ldc + n;
+    if (VEC == 4) {
+      float4 v = Cinit ? *reinterpret_cast<const float4 *>(Cinit + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n));
+        v.x = add_rn(v.x, bv.x); v.y = add_rn(v.y, bv.y); v.z = add_rn(v.z, bv.z); v.w = add_rn(v.w, bv.w);
+      }
+      const float4 ax = aux ? *reinterpret_cast<const float4 *>(aux + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = apply_epilogue(v.x, epi, ax.x, epi_param); v.y = apply_epilogue(v.y, epi, ax.y, epi_param);
+      v.z = apply_epilogue(v.z, epi, ax.z, epi_param); v.w = apply_epilogue(v.w, epi, ax.w, epi_param);
+      *reinterpret_cast<float4 *>(C + o) = v;
+    } else {
+      float v = Cinit ? Cinit[o] : 0.0f;
+      if (bias) v = add_rn(v, __ldg(bias + n));
+      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f, epi_param);
+    }
+  }
+}
+
+int gemm_k0(float *C, const float *Cinit, const float *bias, const float *aux, int M, int N, int ldc, int epi,
+            float epi_param, cudaStream_t s) {
+  const bool vec = N % 4 == 0 && ldc % 4 == 0 && aligned16(C) && (!Cinit || aligned16(Cinit)) && (!bias || aligned16(bias)) &&
+                   (!aux || aligned16(aux));
+  const int64_t work = static_cast<int64_t>(M) * (vec ? N / 4 : N);
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, static_cast<int64_t>(sm_count()) * 8)));
+  if (vec)
+    AIR_LAUNCH(gemm_k0_kernel<4>, grid, 256, 0, s, C, Cinit, bias, aux, M, N, ldc, epi, epi_param);
+  else
+    AIR_LAUNCH(gemm_k0_kernel<1>, grid, 256, 0, s, C, Cinit, bias, aux, M, N, ldc, epi, epi_param);
+  count_launch();
+  return check_launch("gemm_k0");
+}
+
 int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
                     int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s) {
   // big tiles when they still fill the machine, small tiles otherwise
@@ -158,6 +204,8 @@ extern "C" int air_gemm_ex(const float *A, const float *B, float *C, const float
   AIR_REQUIRE((epilogue != AIR_EPI_MUL_DRELU && epilogue != AIR_EPI_MUL_DSOFTPLUS && epilogue != AIR_EPI_SIGMOID_NOISE) || aux,
               AIR_ERR_NULL, "air_gemm: epilogue %d needs aux", epilogue);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AIR_REQUIRE(mode == AIR_GEMM_FP32_EXACT || mode == AIR_GEMM_TF32, AIR_ERR_UNSUPPORTED, "air_gemm: unknown mode %d", mode);
+  if (K == 0) return air::gemm_k0(C, Cinit, bias, aux, static_cast<int>(M), N, ldc, epilogue, epi_param, s);
   if (mode == AIR_GEMM_FP32_EXACT)
     return air::gemm_fp32_exact(A, B, C, Cinit, bias, aux, static_cast<int>(M), N, K, lda, ldb, ldc, transA, transB,
                                 epilogue, epi_param, s);

@@ -25,47 +25,105 @@ static inline int grid_for(int64_t n, int threads, int per_sm = 8) {
 // =========================================================================================
 // LSTM pointwise (BasicLSTMCell: i, j, f, o; forget bias 1.0)
 // =========================================================================================
+__device__ __forceinline__ void lstm_cell_fwd(float gi, float gj, float gf, float go, float cp, float &c, float &h) {
+  c = cp * sigmoid_f(gf + 1.0f) + sigmoid_f(gi) * tanhf(gj);
+  h = tanhf(c) * sigmoid_f(go);
+}
+
+// VEC = 4: four consecutive cells per thread, 16-byte loads/stores (H % 4 == 0, 16-byte aligned rows)
+template <int VEC>
 __global__ void __launch_bounds__(256)
     lstm_fwd_k(const float *__restrict__ gates, const float *__restrict__ c_prev, float *__restrict__ c_new,
                float *__restrict__ h_new, int64_t B, int H) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
-  AIR_GRID_STRIDE(e, B * H) {
-    const int64_t b = e / H;
-    const int k = static_cast<int>(e - b * H);
-    const float *g = gates + b * 4 * H;
-    const float gi = g[k], gj = g[H + k], gf = g[2 * H + k], go = g[3 * H + k];
-    const float cp = c_prev ? c_prev[e] : 0.0f;
-    const float c = cp * sigmoid_f(gf + 1.0f) + sigmoid_f(gi) * tanhf(gj);
-    c_new[e] = c;
-    h_new[e] = tanhf(c) * sigmoid_f(go);
+  const int HV = H / VEC;
+  AIR_GRID_STRIDE(ev, B * HV) {
+    const int64_t b = ev / HV;
+    const int k = static_cast<int>(ev - b * HV) * VEC;
+    const float *g = gates + b * 4 * H + k;
+    const int64_t e = b * H + k;
+    if (VEC == 4) {
+      const float4 gi = *reinterpret_cast<const float4 *>(g), gj = *reinterpret_cast<const float4 *>(g + H);
+      const float4 gf = *reinterpret_cast<const float4 *>(g + 2 * H), go = *reinterpret_cast<const float4 *>(g + 3 * H);
+      const float4 cp = c_prev ? *reinterpret_cast<const float4 *>(c_prev + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 c, h;
+      lstm_cell_fwd(gi.x, gj.x, gf.x, go.x, cp.x, c.x, h.x);
+      lstm_cell_fwd(gi.y, gj.y, gf.y, go.y, cp.y, c.y, h.y);
+      lstm_cell_fwd(gi.z, gj.z, gf.z, go.z, cp.z, c.z, h.z);
+      lstm_cell_fwd(gi.w, gj.w, gf.w, go.w, cp.w, c.w, h.w);
+      *reinterpret_cast<float4 *>(c_new + e) = c;
+      *reinterpret_cast<float4 *>(h_new + e) = h;
+    } else {
+      float c, h;
+      lstm_cell_fwd(g[0], g[H], g[2 * H], g[3 * H], c_prev ? c_prev[e] : 0.0f, c, h);
+      c_new[e] = c;
+      h_new[e] = h;
+    }
   }
 }
 
+struct LstmGrad { float di, dj, df, dd, dcp; };
+__device__ __forceinline__ LstmGrad lstm_cell_bwd(float gi, float gj, float gf, float go, float cp, float cn, float gh,
+                                                  float dcn) {
+  const float i = sigmoid_f(gi), j = tanhf(gj), f = sigmoid_f(gf + 1.0f), o = sigmoid_f(go);
+  const float tc = tanhf(cn);
+  const float dc = dcn + gh * o * (1.0f - tc * tc);
+  LstmGrad r;
+  r.di = dc * j * i * (1.0f - i);
+  r.dj = dc * i * (1.0f - j * j);
+  r.df = dc * cp * f * (1.0f - f);
+  r.dd = gh * tc * o * (1.0f - o);
+  r.dcp = dc * f;
+  return r;
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256)
     lstm_bwd_k(const float *__restrict__ gates, const float *__restrict__ c_prev, const float *__restrict__ c_new,
                const float *__restrict__ dh, const float *dc_new, float *__restrict__ dgates, float *dc_prev,
                float *dgates_sum, int64_t B, int H) {
   pdl_sync();  // PDL: no global access before the previous grid has completed  // dc_prev may alias dc_new (same index, read before write)
-  AIR_GRID_STRIDE(e, B * H) {
-    const int64_t b = e / H;
-    const int k = static_cast<int>(e - b * H);
-    const float *g = gates + b * 4 * H;
-    const float i = sigmoid_f(g[k]), j = tanhf(g[H + k]), f = sigmoid_f(g[2 * H + k] + 1.0f), o = sigmoid_f(g[3 * H + k]);
-    const float cp = c_prev ? c_prev[e] : 0.0f;
-    const float tc = tanhf(c_new[e]);
-    const float gh = dh[e];
-    const float dc = (dc_new ? dc_new[e] : 0.0f) + gh * o * (1.0f - tc * tc);
-    const float di = dc * j * i * (1.0f - i);
-    const float dj = dc * i * (1.0f - j * j);
-    const float df = dc * cp * f * (1.0f - f);
-    const float dd = gh * tc * o * (1.0f - o);
-    float *dg = dgates + b * 4 * H;
-    dg[k] = di; dg[H + k] = dj; dg[2 * H + k] = df; dg[3 * H + k] = dd;
-    if (dgates_sum) {
-      float *ds = dgates_sum + b * 4 * H;
-      ds[k] += di; ds[H + k] += dj; ds[2 * H + k] += df; ds[3 * H + k] += dd;
+  const int HV = H / VEC;
+  AIR_GRID_STRIDE(ev, B * HV) {
+    const int64_t b = ev / HV;
+    const int k = static_cast<int>(ev - b * HV) * VEC;
+    const float *g = gates + b * 4 * H + k;
+    float *dg = dgates + b * 4 * H + k;
+    const int64_t e = b * H + k;
+    if (VEC == 4) {
+      typedef const float4 *cf4;
+      typedef float4 *f4;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 gi = *cf4(g), gj = *cf4(g + H), gf = *cf4(g + 2 * H), go = *cf4(g + 3 * H);
+      const float4 cp = c_prev ? *cf4(c_prev + e) : z4, cn = *cf4(c_new + e), gh = *cf4(dh + e);
+      const float4 dcn = dc_new ? *cf4(dc_new + e) : z4;
+      const LstmGrad r0 = lstm_cell_bwd(gi.x, gj.x, gf.x, go.x, cp.x, cn.x, gh.x, dcn.x);
+      const LstmGrad r1 = lstm_cell_bwd(gi.y, gj.y, gf.y, go.y, cp.y, cn.y, gh.y, dcn.y);
+      const LstmGrad r2 = lstm_cell_bwd(gi.z, gj.z, gf.z, go.z, cp.z, cn.z, gh.z, dcn.z);
+      const LstmGrad r3 = lstm_cell_bwd(gi.w, gj.w, gf.w, go.w, cp.w, cn.w, gh.w, dcn.w);
+      const float4 di = make_float4(r0.di, r1.di, r2.di, r3.di), dj = make_float4(r0.dj, r1.dj, r2.dj, r3.dj);
+      const float4 df = make_float4(r0.df, r1.df, r2.df, r3.df), dd = make_float4(r0.dd, r1.dd, r2.dd, r3.dd);
+      *f4(dg) = di; *f4(dg + H) = dj; *f4(dg + 2 * H) = df; *f4(dg + 3 * H) = dd;
+      if (dgates_sum) {
+        float *ds = dgates_sum + b * 4 * H + k;
+        float4 a = *cf4(ds), bq = *cf4(ds + H), c = *cf4(ds + 2 * H), d = *cf4(ds + 3 * H);
+        a.x += di.x; a.y += di.y; a.z += di.z; a.w += di.w;
+        bq.x += dj.x; bq.y += dj.y; bq.z += dj.z; bq.w += dj.w;
+        c.x += df.x; c.y += df.y; c.z += df.z; c.w += df.w;
+        d.x += dd.x; d.y += dd.y; d.z += dd.z; d.w += dd.w;
+        *f4(ds) = a; *f4(ds + H) = bq; *f4(ds + 2 * H) = c; *f4(ds + 3 * H) = d;
+      }
+      *f4(dc_prev + e) = make_float4(r0.dcp, r1.dcp, r2.dcp, r3.dcp);
+    } else {
+      const LstmGrad r = lstm_cell_bwd(g[0], g[H], g[2 * H], g[3 * H], c_prev ? c_prev[e] : 0.0f, c_new[e], dh[e],
+                                       dc_new ? dc_new[e] : 0.0f);
+      dg[0] = r.di; dg[H] = r.dj; dg[2 * H] = r.df; dg[3 * H] = r.dd;
+      if (dgates_sum) {
+        float *ds = dgates_sum + b * 4 * H + k;
+        ds[0] += r.di; ds[H] += r.dj; ds[2 * H] += r.df; ds[3 * H] += r.dd;
+      }
+      dc_prev[e] = r.dcp;
     }
-    dc_prev[e] = dc * f;
   }
 }
 
@@ -85,7 +143,8 @@ __global__ void __launch_bounds__(256)
     heads_fwd_k(const float *__restrict__ hidden, const float *__restrict__ w_out, const float *__restrict__ b_out,
                 const float *__restrict__ n_scale, const float *__restrict__ n_shift, const float *__restrict__ u,
                 const float *__restrict__ prior_p, air_hyper_t hp, float *stop, float *loss, int32_t *digits,
-                float *__restrict__ fields, float *__restrict__ theta, float *__restrict__ theta_inv, int64_t B, int HU) {
+                float *__restrict__ fields, float *__restrict__ theta, float *__restrict__ theta_inv, int64_t B, int HU,
+                int vec4) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
   const int64_t gt = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t b = gt >> 3;
@@ -95,8 +154,18 @@ __global__ void __launch_bounds__(256)
   if (valid && j < 7) {
     const float *h = hidden + b * 5 * HU + head_block(j) * HU;
     const float *w = w_out + j * HU;
-    float acc = 0.0f;
-    for (int k = 0; k < HU; ++k) acc = __fmaf_rn(h[k], __ldg(w + k), acc);  // k-sequential FMA, like air_gemm exact
+    float acc = 0.0f;  // k-sequential FMA, like air_gemm's exact mode
+    if (vec4) {        // 16-byte loads, same order of the 64 FMAs
+      for (int k = 0; k < HU; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4 *>(h + k), wv = __ldg(reinterpret_cast<const float4 *>(w + k));
+        acc = __fmaf_rn(hv.x, wv.x, acc);
+        acc = __fmaf_rn(hv.y, wv.y, acc);
+        acc = __fmaf_rn(hv.z, wv.z, acc);
+        acc = __fmaf_rn(hv.w, wv.w, acc);
+      }
+    } else {
+      for (int k = 0; k < HU; ++k) acc = __fmaf_rn(h[k], __ldg(w + k), acc);
+    }
     out = acc + __ldg(b_out + j);
   }
   const unsigned full = 0xffffffffu;
@@ -145,7 +214,8 @@ __global__ void __launch_bounds__(256)
   f[AIR_F_STOP_PREV * B] = stop_prev; f[AIR_F_STOP_NEW * B] = c.stop_new;
 }
 
-constexpr int kHeadsImgs = 32;  // images per CTA in heads_bwd (256 threads, 8 lanes each)
+constexpr int kHeadsImgs = 8;  // images per 256-thread CTA in heads_bwd (4x the CTAs of the first version:
+                               // the kernel is latency-bound, ~5 MB of traffic)
 
 __global__ void __launch_bounds__(256)
     heads_bwd_k(const float *__restrict__ hidden, const float *__restrict__ w_out, const float *__restrict__ n_scale,
@@ -156,13 +226,12 @@ __global__ void __launch_bounds__(256)
   pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float sOut[kHeadsImgs][8];
   const int tid = threadIdx.x;
-  const int img = tid >> 3, j = tid & 7;
   const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kHeadsImgs;
-  const int64_t b = b0 + img;
-  const bool valid = b < B;
-  if (j == 0) {
+  const int n_img = static_cast<int>((B - b0 < kHeadsImgs ? B - b0 : kHeadsImgs));
+  if (tid < kHeadsImgs) {  // one thread per image: gradients w.r.t. the 7 head outputs
+    const int64_t b = b0 + tid;
     float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (valid) {
+    if (b < B) {
       const float *f = fields + b;
       const float thr = hp.stopping_threshold;
       const float m_s = f[AIR_F_SCALE_MEAN * B], lv_s = f[AIR_F_SCALE_LV * B];
@@ -193,35 +262,40 @@ __global__ void __launch_bounds__(256)
                               hp.z_pres_temperature, hp.train);
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) sOut[img][q] = d[q];
+    for (int q = 0; q < 8; ++q) sOut[tid][q] = d[q];
   }
   __syncthreads();
-  // ---- dhidden[b, blk*HU + k] = relu'(hidden) * sum_{j in blk} dOut[j] * w_out[j][k]
-  if (valid) {
-    const int n = 5 * HU;
-    for (int e = j; e < n; e += 8) {
-      const int blk = e / HU, k = e - blk * HU;
-      float g;
-      if (blk < 2) g = sOut[img][blk] * __ldg(w_out + blk * HU + k);
-      else if (blk == 2) g = sOut[img][2] * __ldg(w_out + 2 * HU + k) + sOut[img][3] * __ldg(w_out + 3 * HU + k);
-      else if (blk == 3) g = sOut[img][4] * __ldg(w_out + 4 * HU + k) + sOut[img][5] * __ldg(w_out + 5 * HU + k);
-      else g = sOut[img][6] * __ldg(w_out + 6 * HU + k);
-      const int64_t o = b * n + e;
-      dhidden[o] = hidden[o] > 0.0f ? g : 0.0f;
-    }
+  // ---- dhidden[b, blk*HU + k] = relu'(hidden) * sum_{j in blk} dOut[j] * w_out[j][k]; the CTA's images are
+  //      contiguous rows of [B, 5*HU], so consecutive threads touch consecutive floats
+  const int n = 5 * HU;
+  for (int e = tid; e < n_img * n; e += 256) {
+    const int img = e / n, q = e - img * n;
+    const int blk = q / HU, k = q - blk * HU;
+    const float *so = sOut[img];
+    float g;
+    if (blk < 2) g = so[blk] * __ldg(w_out + blk * HU + k);
+    else if (blk == 2) g = so[2] * __ldg(w_out + 2 * HU + k) + so[3] * __ldg(w_out + 3 * HU + k);
+    else if (blk == 3) g = so[4] * __ldg(w_out + 4 * HU + k) + so[5] * __ldg(w_out + 5 * HU + k);
+    else g = so[6] * __ldg(w_out + 6 * HU + k);
+    const int64_t o = b0 * n + e;
+    dhidden[o] = hidden[o] > 0.0f ? g : 0.0f;
   }
   // ---- per-CTA partial d(w_out) [7,HU] and d(b_out) [7]: fixed order over the CTA's images
-  const int n_img = static_cast<int>((B - b0 < kHeadsImgs ? B - b0 : kHeadsImgs));
   float *part = partials + static_cast<int64_t>(blockIdx.x) * (7 * HU + 7);
   for (int e = tid; e < 7 * HU + 7; e += 256) {
     float acc = 0.0f;
     if (e < 7 * HU) {
       const int jj = e / HU, k = e - jj * HU;
       const float *h = hidden + b0 * 5 * HU + head_block(jj) * HU + k;
-      for (int i = 0; i < n_img; ++i) acc += sOut[i][jj] * h[static_cast<int64_t>(i) * 5 * HU];
+      float hv[kHeadsImgs];
+#pragma unroll
+      for (int i = 0; i < kHeadsImgs; ++i) hv[i] = i < n_img ? h[static_cast<int64_t>(i) * 5 * HU] : 0.0f;  // loads in flight together
+#pragma unroll
+      for (int i = 0; i < kHeadsImgs; ++i) acc += sOut[i][jj] * hv[i];   // sOut rows beyond n_img are zero
     } else {
       const int jj = e - 7 * HU;
-      for (int i = 0; i < n_img; ++i) acc += sOut[i][jj];
+#pragma unroll
+      for (int i = 0; i < kHeadsImgs; ++i) acc += sOut[i][jj];
     }
     part[e] = acc;
   }
@@ -305,6 +379,19 @@ __global__ void __launch_bounds__(256)
 // =========================================================================================
 // BCE reconstruction loss: one CTA per image
 // =========================================================================================
+__device__ __forceinline__ float bce_one(float cv, float xv, float dscale, bool want_grad, float &r, float &dc) {
+  r = fmaxf(fminf(cv, 1.0f), 0.0f);
+  const float a = r + kEps, q = (1.0f - r) + kEps;
+  if (want_grad) {
+    const bool pass = cv <= 1.0f && cv >= 0.0f;  // minimum passes x<=y, maximum passes x>=y
+    // a, q in [1e-9, 1 + 1e-9]: the 2-ulp fast division is far inside the 1e-4 gradient tolerance
+    dc = pass ? dscale * (__fdividef(1.0f - xv, q) - __fdividef(xv, a)) : 0.0f;
+  }
+  return xv * logf(a) + (1.0f - xv) * logf(q);
+}
+
+// VEC = 4: N % 4 == 0 and 16-byte aligned rows
+template <int VEC>
 __global__ void __launch_bounds__(256)
     bce_loss_k(const float *__restrict__ canvas, const float *__restrict__ x, float *__restrict__ recon,
                float *__restrict__ rec_loss, float *__restrict__ dcanvas, float dscale, int N) {
@@ -312,16 +399,26 @@ __global__ void __launch_bounds__(256)
   __shared__ float red[8];
   const int64_t b = blockIdx.x;
   const float *c = canvas + b * N, *xi = x + b * N;
+  const bool wg = dcanvas != nullptr;
   float acc = 0.0f;
-  for (int p = threadIdx.x; p < N; p += 256) {
-    const float cv = c[p], xv = xi[p];
-    const float r = fmaxf(fminf(cv, 1.0f), 0.0f);
-    const float a = r + kEps, q = (1.0f - r) + kEps;
-    acc += xv * logf(a) + (1.0f - xv) * logf(q);
-    if (recon) recon[b * N + p] = r;
-    if (dcanvas) {
-      const bool pass = cv <= 1.0f && cv >= 0.0f;  // minimum passes x<=y, maximum passes x>=y
-      dcanvas[b * N + p] = pass ? dscale * ((1.0f - xv) / q - xv / a) : 0.0f;
+  if (VEC == 4) {
+    for (int p = threadIdx.x * 4; p < N; p += 1024) {
+      const float4 cv = *reinterpret_cast<const float4 *>(c + p), xv = *reinterpret_cast<const float4 *>(xi + p);
+      float4 r, d;
+      // summed in pixel order within the thread, like the scalar path sums its own pixels
+      acc += bce_one(cv.x, xv.x, dscale, wg, r.x, d.x);
+      acc += bce_one(cv.y, xv.y, dscale, wg, r.y, d.y);
+      acc += bce_one(cv.z, xv.z, dscale, wg, r.z, d.z);
+      acc += bce_one(cv.w, xv.w, dscale, wg, r.w, d.w);
+      if (recon) *reinterpret_cast<float4 *>(recon + b * N + p) = r;
+      if (wg) *reinterpret_cast<float4 *>(dcanvas + b * N + p) = d;
+    }
+  } else {
+    for (int p = threadIdx.x; p < N; p += 256) {
+      float r, d;
+      acc += bce_one(c[p], xi[p], dscale, wg, r, d);
+      if (recon) recon[b * N + p] = r;
+      if (wg) dcanvas[b * N + p] = d;
     }
   }
   acc = warp_sum(acc);
@@ -426,7 +523,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     adam_apply_k(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  const float *__restrict__ state, const float *__restrict__ partials, int n_partials, float clip,
-                 float beta1, float beta2, float eps, float gs, float *__restrict__ norm_out, int64_t n) {
+                 float beta1, float beta2, float eps, float gs, float *__restrict__ norm_out, int64_t n, int vec4) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float red[8];
   __shared__ float s_scale;
@@ -450,14 +547,29 @@ __global__ void __launch_bounds__(256)
   const float b1p = state[0], b2p = state[1], lr = state[4];
   const float alpha = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
   const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
-  AIR_GRID_STRIDE(e, n) {
-    const float gv = g[e] * sc;
-    float mm = m[e], vv = v[e];
+  auto one = [&](float gq, float &mm, float &vv, float &pp) {
+    const float gv = gq * sc;
     mm = mm + (gv - mm) * omb1;
     vv = vv + (gv * gv - vv) * omb2;
-    m[e] = mm;
-    v[e] = vv;
-    p[e] = p[e] - (mm * alpha) / (sqrtf(vv) + eps);
+    pp = pp - (mm * alpha) / (sqrtf(vv) + eps);
+  };
+  if (vec4) {  // 16-byte accesses: 7 streams of 16 MB each, HBM-bound
+    AIR_GRID_STRIDE(q, n >> 2) {
+      const float4 gq = reinterpret_cast<const float4 *>(g)[q];
+      float4 mm = reinterpret_cast<float4 *>(m)[q], vv = reinterpret_cast<float4 *>(v)[q], pp = reinterpret_cast<float4 *>(p)[q];
+      one(gq.x, mm.x, vv.x, pp.x);
+      one(gq.y, mm.y, vv.y, pp.y);
+      one(gq.z, mm.z, vv.z, pp.z);
+      one(gq.w, mm.w, vv.w, pp.w);
+      reinterpret_cast<float4 *>(m)[q] = mm;
+      reinterpret_cast<float4 *>(v)[q] = vv;
+      reinterpret_cast<float4 *>(p)[q] = pp;
+    }
+    for (int64_t e = (n & ~int64_t(3)) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < n;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      one(g[e], m[e], v[e], p[e]);
+  } else {
+    AIR_GRID_STRIDE(e, n) one(g[e], m[e], v[e], p[e]);
   }
 }
 
@@ -492,7 +604,10 @@ extern "C" int air_lstm_fwd(const float *gates, const float *c_prev, float *c_ne
   AIR_REQUIRE(B >= 0 && H > 0, AIR_ERR_BAD_SHAPE, "lstm_fwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(gates && c_new && h_new, AIR_ERR_NULL, "lstm_fwd: null pointer");
-  AIR_LAUNCH(lstm_fwd_k, grid_for(B * H, 256), 256, 0, ST(stream), gates, c_prev, c_new, h_new, B, H);
+  if (H % 4 == 0 && aligned16(gates) && aligned16(c_new) && aligned16(h_new) && (!c_prev || aligned16(c_prev)))
+    AIR_LAUNCH(lstm_fwd_k<4>, grid_for(B * H / 4, 256), 256, 0, ST(stream), gates, c_prev, c_new, h_new, B, H);
+  else
+    AIR_LAUNCH(lstm_fwd_k<1>, grid_for(B * H, 256), 256, 0, ST(stream), gates, c_prev, c_new, h_new, B, H);
   count_launch();
   return check_launch("lstm_fwd");
 }
@@ -503,8 +618,15 @@ extern "C" int air_lstm_bwd(const float *gates, const float *c_prev, const float
   AIR_REQUIRE(B >= 0 && H > 0, AIR_ERR_BAD_SHAPE, "lstm_bwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(gates && c_new && dh && dgates && dc_prev, AIR_ERR_NULL, "lstm_bwd: null pointer");
-  AIR_LAUNCH(lstm_bwd_k, grid_for(B * H, 256), 256, 0, ST(stream), gates, c_prev, c_new, dh, dc_new, dgates, dc_prev, dgates_sum,
-                                                          B, H);
+  const bool vec = H % 4 == 0 && aligned16(gates) && aligned16(c_new) && aligned16(dh) && aligned16(dgates) &&
+                   aligned16(dc_prev) && (!c_prev || aligned16(c_prev)) && (!dc_new || aligned16(dc_new)) &&
+                   (!dgates_sum || aligned16(dgates_sum));
+  if (vec)
+    AIR_LAUNCH(lstm_bwd_k<4>, grid_for(B * H / 4, 256), 256, 0, ST(stream), gates, c_prev, c_new, dh, dc_new, dgates, dc_prev,
+               dgates_sum, B, H);
+  else
+    AIR_LAUNCH(lstm_bwd_k<1>, grid_for(B * H, 256), 256, 0, ST(stream), gates, c_prev, c_new, dh, dc_new, dgates, dc_prev,
+               dgates_sum, B, H);
   count_launch();
   return check_launch("lstm_bwd");
 }
@@ -521,7 +643,7 @@ extern "C" int air_heads_fwd(const float *hidden, const float *w_out, const floa
   const int64_t threads = B * 8;
   AIR_LAUNCH(heads_fwd_k, static_cast<unsigned>((threads + 255) / 256), 256, 0, ST(stream), 
       hidden, w_out, b_out, noise_scale, noise_shift, u, prior_log_odds, *hyper, stop, loss, digits, fields, theta,
-      theta_inv, B, HU);
+      theta_inv, B, HU, (HU % 4 == 0 && aligned16(hidden) && aligned16(w_out)) ? 1 : 0);
   count_launch();
   return check_launch("heads_fwd");
 }
@@ -599,7 +721,10 @@ extern "C" int air_bce_loss(const float *canvas, const float *x, float *recon, f
   AIR_REQUIRE(B >= 0 && N > 0 && B < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "bce_loss: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(canvas && x && rec_loss, AIR_ERR_NULL, "bce_loss: null pointer");
-  AIR_LAUNCH(bce_loss_k, static_cast<unsigned>(B), 256, 0, ST(stream), canvas, x, recon, rec_loss, dcanvas, dscale, N);
+  if (N % 4 == 0 && aligned16(canvas) && aligned16(x) && (!recon || aligned16(recon)) && (!dcanvas || aligned16(dcanvas)))
+    AIR_LAUNCH(bce_loss_k<4>, static_cast<unsigned>(B), 256, 0, ST(stream), canvas, x, recon, rec_loss, dcanvas, dscale, N);
+  else
+    AIR_LAUNCH(bce_loss_k<1>, static_cast<unsigned>(B), 256, 0, ST(stream), canvas, x, recon, rec_loss, dcanvas, dscale, N);
   count_launch();
   return check_launch("bce_loss");
 }
@@ -646,7 +771,8 @@ extern "C" int air_adam_step(float *params, const float *grads, float *m, float 
   const int np = static_cast<int>(std::min<int64_t>(kAdamPartials, (n + 1023) / 1024));
   AIR_LAUNCH(sumsq_partial_k, np, 256, 0, ST(stream), grads, grad_scale, workspace, n);
   AIR_LAUNCH(adam_apply_k, grid_for(n, 256, 4), 256, 0, ST(stream), params, grads, m, v, state, workspace, np, clip_norm, beta1,
-                                                            beta2, epsilon, grad_scale, workspace + kAdamPartials, n);
+                                                            beta2, epsilon, grad_scale, workspace + kAdamPartials, n,
+             (aligned16(params) && aligned16(grads) && aligned16(m) && aligned16(v)) ? 1 : 0);
   AIR_LAUNCH(adam_advance_k, 1, 1, 0, ST(stream), state, beta1, beta2, workspace + kAdamPartials);
   count_launch(3);
   return check_launch("adam_step");

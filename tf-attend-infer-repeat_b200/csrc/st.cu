@@ -13,6 +13,7 @@
 // y only on the row; images whose theta has shear/rotation take a per-pixel path in the
 // same kernel.  Output pixels are written coalesced.
 #include <algorithm>
+#include <cstdlib>
 
 #include "air_common.cuh"
 
@@ -1047,17 +1048,25 @@ static int st_forward_impl(const float *U, const float *theta, float *out, const
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(U && theta && out, AIR_ERR_NULL, "st_forward: null pointer");
   if (staged_ok(U, H, W, C, B)) {
+    // images per CTA: 4 amortises the prologue at large B; 2 keeps every SM busy when B / 4 CTAs would leave
+    // the machine under-filled (B = 4096: 1024 CTAs on 148 SMs).  AIR_ST_FWD_G overrides (experiments).
+    static const int g_env = [] { const char *e = getenv("AIR_ST_FWD_G"); return e ? atoi(e) : 0; }();
+    const bool g2 = g_env ? g_env == 2 : B < static_cast<int64_t>(sm_count()) * 64;
     if (canvas) {
       if (H == 28 && W == 28 && OH == 50 && OW == 50) {
-        if (aligned16(canvas_in) && aligned16(out))
+        if (aligned16(canvas_in) && aligned16(out)) {
+          if (g2) return launch_fwd_staged<28, 28, 50, 50, 2, true, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
           return launch_fwd_staged<28, 28, 50, 50, 4, true, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+        }
         return launch_fwd_staged<28, 28, 50, 50, 4, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
       }
       if (fwd_smem_bytes<2>(H, W, OH, OW) <= kMaxStagedSmem)
         return launch_fwd_staged<0, 0, 0, 0, 2, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
     } else {
-      if (H == 50 && W == 50 && OH == 28 && OW == 28)
+      if (H == 50 && W == 50 && OH == 28 && OW == 28) {
+        if (g2) return launch_fwd_staged<50, 50, 28, 28, 2, false>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
         return launch_fwd_staged<50, 50, 28, 28, 4, false>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
+      }
       if (H == 28 && W == 28 && OH == 50 && OW == 50)
         return launch_fwd_staged<28, 28, 50, 50, 4, false>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
       if (fwd_smem_bytes<2>(H, W, OH, OW) <= kMaxStagedSmem)
