@@ -815,11 +815,14 @@ __global__ void __launch_bounds__(kAxisThreads, 11)
   pdl_sync();  // PDL: no global access before the previous grid has completed
   constexpr int HW = H * W, OHW = OH * OW, QS = kAxisQS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float *sU = reinterpret_cast<float *>(smem_raw);           // [HW]   window
+  // Q (the only buffer written during the scans) comes first: the scans' one-element-past prefetches of sU / sG /
+  // the tables then land in buffers that are read-only by that time (or in the pad entry), never in Q.
+  float *sQ = reinterpret_cast<float *>(smem_raw);           // [W][QS] Q^T of the current 32-row block (warp 0)
+  float *sU = sQ + W * QS;                                    // [HW]   window
   float *sG = sU + HW;                                        // [OHW]  upstream gradient tile (dcanvas)
-  float *sQ = sG + OHW;                                       // [W][QS] Q^T of the current 32-row block (warp 0)
-  Ent *sCol = reinterpret_cast<Ent *>(sQ + W * QS);           // [OW]
+  Ent *sCol = reinterpret_cast<Ent *>(sG + OHW);              // [OW]
   Ent *sRow = sCol + OW;                                      // [OH] (+1 pad entry for the prefetch past the end)
+  static_assert((W * QS * 4) % 16 == 0 && (HW * 4) % 16 == 0 && (OHW * 4) % 16 == 0, "16-byte aligned bulk-copy targets");
   __shared__ uint64_t bar;
   __shared__ float sTh[8];
   __shared__ float sPart[8];
