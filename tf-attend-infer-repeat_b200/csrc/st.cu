@@ -317,7 +317,6 @@ __global__ void __launch_bounds__(kBwdThreads)
   float *sScr = sT + ((HW + 3) & ~3);          // reduction scratch of the atomics path (behind its tile)
   __shared__ uint64_t bar;
   __shared__ float sTh[8];
-  __shared__ int sRect[6];  // c_lo, c_hi, r_lo, r_hi (inclusive) of the in-range rectangle; [4] = 2^32/nc magic
 
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
@@ -357,32 +356,30 @@ __global__ void __launch_bounds__(kBwdThreads)
   }
   __syncthreads();
   const bool sep = sTh[6] != 0.0f;
-  // ---- in-range rectangle (first / last output column and row whose two corners differ)
-  if (tid < 64) {  // warp 0: columns, warp 1: rows
-    const int w = tid >> 5, l = tid & 31;
-    const int n = w == 0 ? OW : OH;
-    const Ent *tab = w == 0 ? sCol : sRow;
+  // ---- in-range rectangle (first / last output column and row whose two corners differ), recomputed by every
+  //      warp from the tables with two warp-wide integer reductions per axis (cheaper than a block barrier)
+  int c_lo = 0, nc = OW, r_lo = 0, nr = OH;
+  if (sep) {
+    const int lane = tid & 31;
     int lo = 1 << 30, hi = -1;
-    for (int k = l; k < n; k += 32) {
-      if (!sep || tab[k].i0 != tab[k].i1) { lo = min(lo, k); hi = max(hi, k); }
+    for (int k = lane; k < OW; k += 32) {
+      const int2 e = *reinterpret_cast<const int2 *>(sCol + k);
+      if (e.x != e.y) { lo = min(lo, k); hi = max(hi, k); }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    c_lo = hi >= 0 ? lo : 0;
+    nc = hi >= 0 ? hi - lo + 1 : 0;
+    lo = 1 << 30, hi = -1;
+    for (int k = lane; k < OH; k += 32) {
+      const int2 e = *reinterpret_cast<const int2 *>(sRow + k);
+      if (e.x != e.y) { lo = min(lo, k); hi = max(hi, k); }
     }
-    if (l == 0) {
-      sRect[2 * w] = lo;
-      sRect[2 * w + 1] = hi;
-      if (w == 0) {  // idx / nc by multiply-high (one 64-bit division per CTA instead of one per thread)
-        const int ncols = max(hi - lo + 1, 1);
-        sRect[4] = static_cast<int>(static_cast<unsigned>((0x100000000ull + ncols - 1) / ncols));
-      }
-    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    r_lo = hi >= 0 ? lo : 0;
+    nr = hi >= 0 ? hi - lo + 1 : 0;
   }
-  __syncthreads();
-  const int c_lo = sRect[0], r_lo = sRect[2];
-  const int nc = max(sRect[1] - c_lo + 1, 0), nr = max(sRect[3] - r_lo + 1, 0);
   if (dU && !sep) {
     for (int k = tid; k < HW; k += kBwdThreads) sT[k] = 0.0f;  // atomics tile
     __syncthreads();
@@ -398,38 +395,43 @@ __global__ void __launch_bounds__(kBwdThreads)
     const int lane = tid & 31, warp = tid >> 5;
     for (int cb = 0; cb < nc; cb += 32) {
       const bool cok = cb + lane < nc;
-      const int c = c_lo + (cok ? cb + lane : 0);
+      const int c = c_lo + (cok ? cb + lane : nc - 1);  // surplus lanes redo the last column with a zero weight
       const Ent ce = sCol[c];
       const float xt = sGrid[c];
       // every pixel of the rectangle is in range: its corners are i0, i0 + 1 (columns) and i0, i0 + W (rows),
       // so one address per pixel serves the four corner loads
       const float *u0 = sU + ce.i0;
+      const float *gcol = sG + c;
+      const float gmask = cok ? (FUSED ? zval : 1.0f) : 0.0f;  // lane mask and the z scaling in one multiplier
       float sdx = 0.f, sdxy = 0.f, sdy = 0.f, sdyy = 0.f;
-      for (int ro = warp; ro < nr; ro += kBwdWarps) {
-        const int r = r_lo + ro;
+      auto pixel = [&](int r) {
         const Ent re = sRow[r];
         const float yt = sGrid[OW + r];
-        if (cok) {
-          const float *pu = u0 + re.i0;
-          const float Ia = pu[0], Ib = pu[W], Ic = pu[1], Id = pu[W + 1];
-          float g = sG[r * OW + c];
-          if (FUSED) {
-            if (!dU) {  // (dz without dU: not used by the model; dz normally comes from <dU / z, U>)
-              const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
-              const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
-              acc[6] += g * add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
-            }
-            g *= zval;
+        const float *pu = u0 + re.i0;
+        const float Ia = pu[0], Ib = pu[W], Ic = pu[1], Id = pu[W + 1];
+        float g = gcol[r * OW];
+        if (FUSED) {
+          if (!dU) {  // (dz without dU: not used by the model; dz normally comes from <dU / z, U>)
+            const float wa = mul_rn(ce.w1, re.w1), wb = mul_rn(ce.w1, re.w0);
+            const float wc = mul_rn(ce.w0, re.w1), wd = mul_rn(ce.w0, re.w0);
+            acc[6] += (cok ? g : 0.0f) * add_rn(add_rn(add_rn(mul_rn(wa, Ia), mul_rn(wb, Ib)), mul_rn(wc, Ic)), mul_rn(wd, Id));
           }
-          // d out / d x = wy1 (Ic - Ia) + wy0 (Id - Ib),  d out / d y = wx1 (Ib - Ia) + wx0 (Id - Ic)
-          const float dx = g * (re.w1 * (Ic - Ia) + re.w0 * (Id - Ib));
-          const float dy = g * (ce.w1 * (Ib - Ia) + ce.w0 * (Id - Ic));
-          sdx += dx;
-          sdxy += dx * yt;
-          sdy += dy;
-          sdyy += dy * yt;
         }
+        g *= gmask;
+        // d out / d x = wy1 (Ic - Ia) + wy0 (Id - Ib),  d out / d y = wx1 (Ib - Ia) + wx0 (Id - Ic)
+        const float dx = g * (re.w1 * (Ic - Ia) + re.w0 * (Id - Ib));
+        const float dy = g * (ce.w1 * (Ib - Ia) + ce.w0 * (Id - Ic));
+        sdx += dx;
+        sdxy += dx * yt;
+        sdy += dy;
+        sdyy += dy * yt;
+      };
+      int ro = warp;
+      for (; ro + kBwdWarps < nr; ro += 2 * kBwdWarps) {  // two rows per trip: independent load chains in flight
+        pixel(r_lo + ro);
+        pixel(r_lo + ro + kBwdWarps);
       }
+      if (ro < nr) pixel(r_lo + ro);
       acc[0] += sdx * xt;
       acc[1] += sdxy;
       acc[2] += sdx;
@@ -439,11 +441,9 @@ __global__ void __launch_bounds__(kBwdThreads)
     }
   } else {
     // ---- general theta (rotation / shear): flat loop over all output pixels, per-pixel coordinates
-    const int npix = nr * nc;
-    // idx / nc by multiply-high: exact while idx * nc < 2^32 (checked on the host: OH*OW*OW < 2^32)
-    const unsigned magic = static_cast<unsigned>(sRect[4]);
+    const int npix = nr * nc;  // (= OH * OW: the rectangle is only narrowed for axis-aligned theta)
     for (int idx = tid; idx < npix; idx += kBwdThreads) {
-      const int ro = nc > 1 ? static_cast<int>(__umulhi(static_cast<unsigned>(idx), magic)) : idx;
+      const int ro = idx / nc;
       const int r = r_lo + ro, c = c_lo + (idx - ro * nc);
       const int q = r * OW + c;
       Ent ce, re;
