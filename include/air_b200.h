@@ -229,6 +229,24 @@ int air_adam_step(float *params, const float *grads, float *m, float *v, float *
 int air_anneal(const float *state, float init, float factor, float iters, int staircase, float vmin, float vmax,
                int take_log, float *out, air_stream_t stream);
 
+/* ---- CNN front-end of AIRModel(cnn=True): air_model.py:510-535 -------------------------
+ * tf.layers.conv2d(filters=8, kernel_size=5, padding="same", activation=relu) optionally followed by
+ * tf.layers.max_pooling2d(pool_size=2, strides=2) ("valid": 25 -> 12), NHWC.
+ * in [B,H,W,cin], w [5,5,cin,cout] (TF HWIO), bias [cout], out [B,H',W',cout] with H' = pool ? H/2 : H;
+ * argmax [B,H',W',cout] uint8 (pool only): position 0..3 of the window maximum, first maximum wins.
+ * Built for the reference's three layers: (cin,H,W,pool) = (1,50,50,1), (8,25,25,1), (8,12,12,0), cout = 8;
+ * anything else returns AIR_ERR_UNSUPPORTED. */
+int air_conv5x5_fwd(const float *in, const float *w, const float *bias, float *out, uint8_t *argmax, int64_t B, int H,
+                    int W, int cin, int cout, int pool, air_stream_t stream);
+/* Backward (ReluGrad, MaxPoolGrad and Conv2DBackpropFilter/Input of TF autodiff): dout [B,H',W',cout];
+ * dw [5,5,cin,cout] and db [cout] are written (accumulate == 0) or added to; din [B,H,W,cin] is written if
+ * non-NULL (NULL for the first layer, whose input is data).  Deterministic (fixed-order reductions).
+ * workspace >= air_conv5x5_bwd_workspace(B, cin, cout) floats. */
+int64_t air_conv5x5_bwd_workspace(int64_t B, int cin, int cout);
+int air_conv5x5_bwd(const float *in, const float *w, const float *out, const uint8_t *argmax, const float *dout,
+                    float *din, float *dw, float *db, int accumulate, float *workspace, int64_t B, int H, int W, int cin,
+                    int cout, int pool, air_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,15 +234,43 @@ def vae(inputs, params, prefix, n_rec, n_gen, noise_latent, noise_like,
 # --------------------------------------------------------------------------------------
 # Parameters
 # --------------------------------------------------------------------------------------
+CNN_OUT = 12 * 12  # spatial size after the two valid 2x2/2 max-pools of a 50x50 canvas (air_model.py:533)
+
+
+def cnn_frontend(x_img, p, filters=8):
+    """air_model.py:510-535: tf.layers.conv2d(5x5, 'same', relu) x3 with max_pooling2d(2, 2) ('valid') after the
+    first two, on the canvas reshaped to [-1, 50, 50, 1] (hard-coded in the reference), flattened in NHWC order.
+    Kernels are stored as TF stores them (HWIO); TF's conv2d is a cross-correlation, like torch's."""
+    import torch.nn.functional as F
+    x = x_img.reshape(-1, 1, 50, 50)  # one channel: NCHW and NHWC coincide
+
+    def conv(t, name):
+        w = p[f"cnn/{name}/kernel"].permute(3, 2, 0, 1)  # HWIO -> OIHW
+        return torch.relu(F.conv2d(t, w, p[f"cnn/{name}/bias"], padding=2))
+
+    t = F.max_pool2d(conv(x, "conv1"), 2, 2)    # 50 -> 25
+    t = F.max_pool2d(conv(t, "conv2"), 2, 2)    # 25 -> 12 (valid)
+    t = conv(t, "conv3")
+    return t.permute(0, 2, 3, 1).reshape(-1, CNN_OUT * filters)  # NHWC flatten (:533)
+
+
 def param_shapes(canvas_size=50, windows_size=28, rnn_units=256, vae_latent_dimensions=50,
                  vae_recognition_units=(512, 256), vae_generative_units=(256, 512),
                  scale_hidden_units=64, shift_hidden_units=64, z_pres_hidden_units=64,
-                 rnn_input_dim=None):
+                 rnn_input_dim=None, cnn=False, cnn_filters=8):
     """Trainable tensors in checkpoint order-independent form: name -> shape.  Names are
-    the checkpoint names (model/air-model.index) minus the ``air/rnn/`` prefix."""
+    the checkpoint names (model/air-model.index) minus the ``air/rnn/`` prefix; the CNN front-end's
+    variables live under ``air/cnn/`` in the reference graph and are keyed ``cnn/...`` here."""
     in_dim = canvas_size * canvas_size if rnn_input_dim is None else rnn_input_dim
     win = windows_size * windows_size
     s = OrderedDict()
+    if cnn:
+        in_dim = CNN_OUT * cnn_filters
+        prev = 1
+        for name in ("conv1", "conv2", "conv3"):
+            s[f"cnn/{name}/kernel"] = (5, 5, prev, cnn_filters)
+            s[f"cnn/{name}/bias"] = (cnn_filters,)
+            prev = cnn_filters
     s["rnn/kernel"] = (in_dim + rnn_units, 4 * rnn_units)
     s["rnn/bias"] = (4 * rnn_units,)
     for head, hid, out in (("scale", scale_hidden_units, 1), ("shift", shift_hidden_units, 2)):
@@ -279,8 +307,9 @@ def init_params(seed=0, dtype=torch.float32, **shape_kwargs):
     g = torch.Generator().manual_seed(seed)
     p = OrderedDict()
     for name, shape in param_shapes(**shape_kwargs).items():
-        if len(shape) == 2:
-            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+        if len(shape) >= 2:  # glorot-uniform; conv kernels [kh,kw,in,out]: fan = kh*kw*in / kh*kw*out (TF)
+            rf = math.prod(shape[:-2])
+            lim = math.sqrt(6.0 / (rf * shape[-2] + rf * shape[-1]))
             w = (torch.rand(shape, generator=g, dtype=torch.float64) * 2.0 - 1.0) * lim
             p[name] = w.to(dtype)
         else:
@@ -343,7 +372,9 @@ class AIROracle:
                  dtype=torch.float32, **hyper):
         self.h = dict(DEFAULT_HYPER)
         self.h.update(hyper)
-        assert not self.h["cnn"], "cnn=True front-end (air_model.py:510-535) is a 'next' row"
+        self.h.setdefault("cnn_filters", 8)
+        if self.h["cnn"]:
+            assert self.h["canvas_size"] == 50, "the reference's CNN front-end hard-codes 50x50 canvases (:512, :533)"
         self.train = train
         self.dtype = dtype
         self.annealing = annealing_schedules
@@ -353,7 +384,7 @@ class AIROracle:
             rnn_units=h["rnn_units"], vae_latent_dimensions=h["vae_latent_dimensions"],
             vae_recognition_units=h["vae_recognition_units"], vae_generative_units=h["vae_generative_units"],
             scale_hidden_units=h["scale_hidden_units"], shift_hidden_units=h["shift_hidden_units"],
-            z_pres_hidden_units=h["z_pres_hidden_units"])
+            z_pres_hidden_units=h["z_pres_hidden_units"], cnn=h["cnn"], cnn_filters=h["cnn_filters"])
         self.global_step = 0
         self.adam_m = {k: torch.zeros_like(v) for k, v in self.params.items()}
         self.adam_v = {k: torch.zeros_like(v) for k, v in self.params.items()}
@@ -387,6 +418,7 @@ class AIROracle:
         thr = h["stopping_threshold"]
         x_img = input_images.to(dt)
         U_canvas = x_img.reshape(-1, cs, cs).unsqueeze(3)  # :331
+        rnn_input = cnn_frontend(x_img, p, h["cnn_filters"]) if h["cnn"] else x_img  # :510-535
 
         stopping_sum = torch.zeros(B, dtype=dt)
         c_state = torch.zeros(B, h["rnn_units"], dtype=dt)
@@ -413,7 +445,7 @@ class AIROracle:
                 executed_steps = step + 1  # cond() true on entry to this iteration
 
             # ---- LSTM step, BasicLSTMCell: gates i, j, f, o; forget bias 1.0 (:284-286)
-            concat = torch.matmul(torch.cat([x_img, h_state], dim=1), p["rnn/kernel"]) + p["rnn/bias"]
+            concat = torch.matmul(torch.cat([rnn_input, h_state], dim=1), p["rnn/kernel"]) + p["rnn/bias"]
             gi, gj, gf, go = torch.split(concat, h["rnn_units"], dim=1)
             c_state = c_state * torch.sigmoid(gf + 1.0) + torch.sigmoid(gi) * torch.tanh(gj)
             h_state = torch.tanh(c_state) * torch.sigmoid(go)

@@ -11,7 +11,7 @@ def relnorm(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def covered_fixture(B, seed=0, T=3):
+def covered_fixture(B, seed=0, T=3, cnn=False):
     """Well-conditioned ("covered", SURVEY hard part 2) fixture.  Every canvas pixel must sample
     INSIDE the window, otherwise the write-back leaves +-1e-9 rounding residues on it and
     max(canvas, 0) passes or blocks that pixel's gradient depending on the residue's sign (which
@@ -23,7 +23,7 @@ def covered_fixture(B, seed=0, T=3):
     imgs, cnt = O.synthetic_canvases(B, seed=seed)
     im = imgs.reshape(B, 50, 50).clone()
     im[:, :7] = 0; im[:, -7:] = 0; im[:, :, :7] = 0; im[:, :, -7:] = 0
-    params = O.init_params(seed=seed)
+    params = O.init_params(seed=seed, cnn=cnn)
     params["scale/mean/output/biases"] += 12.0
     params["scale/mean/output/weights"] *= 0.2
     params["scale/log_variance/output/biases"] -= 8.0

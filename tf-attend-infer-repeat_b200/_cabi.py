@@ -52,6 +52,9 @@ _SIGS = {
     "air_adam_step": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float] * 5 + [_c_f, ctypes.c_int64, _c_f]),
     "air_anneal": (ctypes.c_int, [_c_f] + [ctypes.c_float] * 3 + [ctypes.c_int] + [ctypes.c_float] * 2 +
                    [ctypes.c_int, _c_f, _c_f]),
+    "air_conv5x5_fwd": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
+    "air_conv5x5_bwd_workspace": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "air_conv5x5_bwd": (ctypes.c_int, [_c_f] * 8 + [ctypes.c_int, _c_f, ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
 }
 
 

@@ -56,10 +56,10 @@ class AIRModel:
                  learning_rate=1e-3, gradient_clipping_norm=100.0, cnn=True, cnn_filters=8,
                  num_summary_images=60, train=False, reuse=False, scope="air",
                  annealing_schedules=None, *, gemm_mode="fp32", seed=0, process_group=None):
-        if cnn:
-            raise NotImplementedError(
-                "cnn=True (air_model.py:510-535) is outside the accelerated hot path (SURVEY.md section 8f); "
-                "training.py, demo.py and the shipped checkpoint all use cnn=False")
+        if cnn and canvas_size != 50:
+            raise ValueError("the reference's CNN front-end hard-codes 50x50 canvases (air_model.py:512, 533)")
+        if cnn and cnn_filters != 8:
+            raise NotImplementedError("the conv kernels are built for the reference's cnn_filters=8")
         if not (scale_hidden_units == shift_hidden_units == z_pres_hidden_units):
             raise NotImplementedError("the fused heads kernel needs equal scale/shift/z_pres hidden sizes")
         if not input_images.is_cuda:
@@ -78,6 +78,8 @@ class AIRModel:
         self.device = input_images.device
         self.num_summaries, self.img_summaries, self.var_summaries, self.grad_summaries = [], [], [], []
         assert self.input_images.shape[1] == canvas_size * canvas_size
+        # LSTM input: the canvas itself, or the CNN front-end's 12x12xF feature map (air_model.py:533-535)
+        self.rnn_input_dim = 12 * 12 * cnn_filters if cnn else canvas_size * canvas_size
 
         # ---- variables: shared by scope, like tf.variable_scope(scope, reuse=reuse) (air_model.py:68)
         key = (scope, self.device)
@@ -86,9 +88,9 @@ class AIRModel:
                 raise ValueError(f"variable scope {scope!r} does not exist (reuse=True)")
             self.store = _VARIABLE_SCOPES[key]
         else:
-            self.store = ParamStore(self.device, canvas_size * canvas_size, windows_size * windows_size, rnn_units,
+            self.store = ParamStore(self.device, self.rnn_input_dim, windows_size * windows_size, rnn_units,
                                     scale_hidden_units, vae_latent_dimensions, self.vae_recognition_units,
-                                    self.vae_generative_units, seed=seed)
+                                    self.vae_generative_units, seed=seed, cnn_filters=cnn_filters if cnn else None)
             _VARIABLE_SCOPES[key] = self.store
         if train:
             self.store.state[4] = float(learning_rate if not self._annealed("learning_rate") else 0.0)
@@ -169,8 +171,18 @@ class AIRModel:
             w["colsum_ws"] = torch.zeros(int(C.lib().air_colsum_workspace(B, nmax)), device=dev)
             w["heads_ws"] = torch.zeros(int(C.lib().air_heads_bwd_workspace(B, HU)), device=dev)
             w["adam_ws"] = torch.zeros(int(C.lib().air_adam_workspace(self.store.n)), device=dev)
+        if self.cnn:
+            F = self.cnn_filters
+            u8 = lambda *s: torch.empty(*s, device=dev, dtype=torch.uint8)
+            # (input H, W, cin, pool) of the three layers; pooled outputs + one-byte argmax are all the backward needs
+            self._cnn_layers = (("conv1", 50, 50, 1, True), ("conv2", 25, 25, F, True), ("conv3", 12, 12, F, False))
+            w["cnn_out"] = [z(B, 25 * 25 * F), z(B, 12 * 12 * F), z(B, 12 * 12 * F)]
+            w["cnn_arg"] = [u8(B, 25 * 25 * F), u8(B, 12 * 12 * F), None]
+            if self.train:
+                w["cnn_d"] = [z(B, 25 * 25 * F), z(B, 12 * 12 * F), z(B, 12 * 12 * F)]  # d(loss)/d(layer output)
+                w["cnn_ws"] = torch.zeros(ops.conv5x5_bwd_workspace(B, F, F), device=dev)
         p, g = self.store.p, self.store.g
-        in_dim = cs2
+        in_dim = self.rnn_input_dim
         self.Kx, self.Kh = p["rnn/kernel"][:in_dim], p["rnn/kernel"][in_dim:]
         self.gKx, self.gKh = g["rnn/kernel"][:in_dim], g["rnn/kernel"][in_dim:]
         self.vw = VAEWeights(p, g, len(self.vae_recognition_units), len(self.vae_generative_units))
@@ -214,7 +226,7 @@ class AIRModel:
         w["stop"].zero_(); w["loss"].zero_(); w["digits"].zero_(); w["canvas"].zero_()
         self._update_scalars()
         # step-invariant image projection x @ K[:in_dim] (bias added per step, after the h part)
-        ops.gemm(x, self.Kx, w["xk"], mode=mode)
+        ops.gemm(self._rnn_input(), self.Kx, w["xk"], mode=mode)
         for t in range(T):
             c_prev = w["c"][t - 1] if t > 0 else None
             # LSTM: gates = ([x,h] K) + b, accumulated in concat order (x part first).  The initial state is
@@ -243,6 +255,29 @@ class AIRModel:
         ops.bce_loss(w["canvas"], x, None if self.train else w["reconstruction"], w["rec_loss"],
                      w["dcanvas"] if self.train else None, dscale)
         ops.finalize_loss(w["loss"], w["rec_loss"], w["digits"], self.target_num_digits, w["out2"], w["loss_item"])
+
+    def _rnn_input(self):
+        """air_model.py:510-535: the canvas, or conv-relu-pool, conv-relu-pool, conv-relu of it (NHWC flatten)."""
+        if not self.cnn:
+            return self.input_images
+        w, p, F = self.w, self.store.p, self.cnn_filters
+        src = self.input_images
+        for i, (name, H, W, cin, pool) in enumerate(self._cnn_layers):
+            ops.conv5x5_fwd(src, p[f"cnn/{name}/kernel"], p[f"cnn/{name}/bias"], w["cnn_out"][i], w["cnn_arg"][i], H, W, cin,
+                            F, pool)
+            src = w["cnn_out"][i]
+        return src
+
+    def _cnn_backward(self):
+        """d(loss)/d(rnn_input) = dgates_sum K_x^T, then back through the three conv layers (no d(images))."""
+        w, p, g, F = self.w, self.store.p, self.store.g, self.cnn_filters
+        ops.gemm(w["dgates_sum"], self.Kx, w["cnn_d"][2], tB=True, mode=self.gemm)
+        for i in (2, 1, 0):
+            name, H, W, cin, pool = self._cnn_layers[i]
+            src = w["cnn_out"][i - 1] if i > 0 else self.input_images
+            ops.conv5x5_bwd(src, p[f"cnn/{name}/kernel"], w["cnn_out"][i], w["cnn_arg"][i], w["cnn_d"][i],
+                            w["cnn_d"][i - 1] if i > 0 else None, g[f"cnn/{name}/kernel"], g[f"cnn/{name}/bias"], False,
+                            w["cnn_ws"], H, W, cin, F, pool)
 
     def _vae_buf(self, t):
         w = self.w
@@ -294,9 +329,12 @@ class AIRModel:
             ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode)
         else:
             self.gKh.zero_()
-        # the image rows of the LSTM kernel see the same x every step: one GEMM on the summed dgates
-        ops.gemm(x, w["dgates_sum"], self.gKx, tA=True, mode=mode)
+        # the image rows of the LSTM kernel see the same input every step: one GEMM on the summed dgates
+        rnn_in = w["cnn_out"][2] if self.cnn else x
+        ops.gemm(rnn_in, w["dgates_sum"], self.gKx, tA=True, mode=mode)
         ops.colsum(w["dgates_sum"], g["rnn/bias"], False, cws)
+        if self.cnn:
+            self._cnn_backward()
 
     def _apply_gradients(self):
         """air_model.py:673, 692: clip by global norm, Adam, global_step += 1."""

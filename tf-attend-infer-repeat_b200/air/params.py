@@ -21,10 +21,18 @@ HEADS = (("scale", "mean"), ("scale", "log_variance"), ("shift", "mean"), ("shif
 HEAD_OUT_ROWS = ((0, 0, 1), (1, 1, 1), (2, 2, 2), (3, 4, 2), (4, 6, 1))
 
 
-def reference_shapes(in_dim, win, R, HU, L, rec_units, gen_units):
+def reference_shapes(in_dim, win, R, HU, L, rec_units, gen_units, cnn_filters=None):
     """name -> shape exactly as in model/air-model.index (minus the 'air/rnn/' prefix),
-    ordered rnn, scale, shift, z_pres, vae (the order only matters for the init RNG stream)."""
+    ordered [cnn,] rnn, scale, shift, z_pres, vae (the order only matters for the init RNG stream).
+    The CNN front-end's variables (air_model.py:510-535, graph names air/cnn/convN/{kernel,bias}) are keyed
+    ``cnn/...``; ``in_dim`` is then its flattened output size."""
     s = OrderedDict()
+    if cnn_filters:
+        prev = 1
+        for name in ("conv1", "conv2", "conv3"):
+            s[f"cnn/{name}/kernel"] = (5, 5, prev, cnn_filters)
+            s[f"cnn/{name}/bias"] = (cnn_filters,)
+            prev = cnn_filters
     s["rnn/kernel"] = (in_dim + R, 4 * R)
     s["rnn/bias"] = (4 * R,)
     for head, stat in HEADS:
@@ -52,10 +60,17 @@ def reference_shapes(in_dim, win, R, HU, L, rec_units, gen_units):
 
 
 class ParamStore:
-    def __init__(self, device, in_dim, win, R, HU, L, rec_units, gen_units, seed=0):
+    def __init__(self, device, in_dim, win, R, HU, L, rec_units, gen_units, seed=0, cnn_filters=None):
         self.device = torch.device(device)
-        self.dims = dict(in_dim=in_dim, win=win, R=R, HU=HU, L=L, rec_units=tuple(rec_units), gen_units=tuple(gen_units))
+        self.dims = dict(in_dim=in_dim, win=win, R=R, HU=HU, L=L, rec_units=tuple(rec_units), gen_units=tuple(gen_units),
+                         cnn_filters=cnn_filters)
         fused = OrderedDict()
+        if cnn_filters:
+            prev = 1
+            for name in ("conv1", "conv2", "conv3"):
+                fused[f"cnn/{name}/kernel"] = (5, 5, prev, cnn_filters)
+                fused[f"cnn/{name}/bias"] = (cnn_filters,)
+                prev = cnn_filters
         fused["rnn/kernel"] = (in_dim + R, 4 * R)
         fused["rnn/bias"] = (4 * R,)
         fused["heads/hidden_w"] = (R, 5 * HU)
@@ -102,6 +117,9 @@ class ParamStore:
 
     def _named(self, v):
         d, HU, L = OrderedDict(), self.dims["HU"], self.dims["L"]
+        for k in v:
+            if k.startswith("cnn/"):
+                d[k] = v[k]
         d["rnn/kernel"], d["rnn/bias"] = v["rnn/kernel"], v["rnn/bias"]
         for (head, stat), (blk, row, nout) in zip(HEADS, HEAD_OUT_ROWS):
             d[f"{head}/{stat}/hidden/weights"] = v["heads/hidden_w"][:, blk * HU:(blk + 1) * HU]
@@ -135,9 +153,10 @@ class ParamStore:
         d = self.dims
         named = self.named_views()
         for name, shape in reference_shapes(d["in_dim"], d["win"], d["R"], d["HU"], d["L"], d["rec_units"],
-                                            d["gen_units"]).items():
-            if len(shape) == 2:
-                lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+                                            d["gen_units"], d["cnn_filters"]).items():
+            if len(shape) >= 2:  # conv kernels [kh,kw,in,out]: fan_in = kh*kw*in, fan_out = kh*kw*out (TF glorot)
+                rf = math.prod(shape[:-2])
+                lim = math.sqrt(6.0 / (rf * shape[-2] + rf * shape[-1]))
                 w = (torch.rand(shape, generator=g, dtype=torch.float64) * 2.0 - 1.0) * lim
                 named[name].copy_(w.to(torch.float32))
             else:

@@ -305,6 +305,12 @@ def save_checkpoint(prefix: str, tensors) -> "OrderedDict[str, BundleEntry]":
 
 
 # ---- AIRModel <-> reference variable names ----------------------------------------------------------------
+def _graph_name(scope, key):
+    """ParamStore key -> TF variable name: everything lives under <scope>/rnn/ (variable_scope("rnn"),
+    air_model.py:537) except the CNN front-end, created under <scope>/cnn/ (:511)."""
+    return f"{scope}/{key}" if key.startswith("cnn/") else f"{scope}/rnn/{key}"
+
+
 def model_tensors(store, scope="air", with_optimizer=True):
     """The reference's checkpoint contents (model/air-model.index) for a ParamStore: variables under
     ``<scope>/rnn/``, ``<scope>/global_step`` and, optionally, the Adam slots / beta powers under
@@ -312,12 +318,12 @@ def model_tensors(store, scope="air", with_optimizer=True):
     out = OrderedDict()
     out[f"{scope}/global_step"] = np.asarray(store.global_step, dtype=np.int32)
     for k, v in store.named_views().items():
-        out[f"{scope}/rnn/{k}"] = v.detach().cpu().numpy()
+        out[_graph_name(scope, k)] = v.detach().cpu().numpy()
     if with_optimizer:
         m, vv = store.named_adam()
         for k in m:
-            out[f"{scope}/training/{scope}/rnn/{k}/Adam"] = m[k].detach().cpu().numpy()
-            out[f"{scope}/training/{scope}/rnn/{k}/Adam_1"] = vv[k].detach().cpu().numpy()
+            out[f"{scope}/training/{_graph_name(scope, k)}/Adam"] = m[k].detach().cpu().numpy()
+            out[f"{scope}/training/{_graph_name(scope, k)}/Adam_1"] = vv[k].detach().cpu().numpy()
         st = store.state.detach().cpu().numpy()
         out[f"{scope}/training/beta1_power"] = np.float32(st[0])
         out[f"{scope}/training/beta2_power"] = np.float32(st[1])
@@ -332,16 +338,18 @@ def restore_model(store, prefix, scope="air", verify_crc=True):
     """Load a reference (or own) checkpoint into a ParamStore; Adam slots are optional."""
     import torch
     t = load_checkpoint(prefix, verify_crc)
-    pre = f"{scope}/rnn/"
-    store.load_named({k[len(pre):]: torch.from_numpy(v) for k, v in t.items() if k.startswith(pre)})
+    pre, cpre = f"{scope}/rnn/", f"{scope}/cnn/"
+    named = {k[len(pre):]: torch.from_numpy(v) for k, v in t.items() if k.startswith(pre)}
+    named.update({k[len(scope) + 1:]: torch.from_numpy(v) for k, v in t.items() if k.startswith(cpre)})
+    store.load_named(named)
     if f"{scope}/global_step" in t:
         store.global_step = int(t[f"{scope}/global_step"])
     m, vv = store.named_adam()
-    tp = f"{scope}/training/{scope}/rnn/"
     for k in m:
-        if tp + k + "/Adam" in t:
-            m[k].copy_(torch.from_numpy(t[tp + k + "/Adam"]))
-            vv[k].copy_(torch.from_numpy(t[tp + k + "/Adam_1"]))
+        tk = f"{scope}/training/{_graph_name(scope, k)}"
+        if tk + "/Adam" in t:
+            m[k].copy_(torch.from_numpy(t[tk + "/Adam"]))
+            vv[k].copy_(torch.from_numpy(t[tk + "/Adam_1"]))
     if f"{scope}/training/beta1_power" in t:
         store.state[0] = float(t[f"{scope}/training/beta1_power"])
         store.state[1] = float(t[f"{scope}/training/beta2_power"])

@@ -317,6 +317,12 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+int reduce_rows_launch(const float *partials, int R, int stride, int n, float *out, int accumulate, cudaStream_t s) {
+  AIR_LAUNCH(reduce_rows_k, grid_for(static_cast<int64_t>(n) * 32, 256), 256, 0, s, partials, R, stride, n, out, accumulate);
+  count_launch();
+  return check_launch("reduce_rows");
+}
+
 // =========================================================================================
 // VAE latent: one warp per image
 // =========================================================================================

@@ -147,3 +147,20 @@ def writeback_canvas_bwd(window, theta_inv, z, stop_new, thr, dcanvas, dwindow, 
     check(lib().air_st_writeback_canvas_bwd(ptr(window), ptr(theta_inv), ptr(z), ptr(stop_new), float(thr),
                                             ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), flags,
                                             window.shape[0], wh, ww, ch, cw, stream()), "air_st_writeback_canvas_bwd")
+
+
+def conv5x5_fwd(x, w, b, out, argmax, H, W, cin, cout, pool):
+    """NHWC 5x5 'same' conv + ReLU (+ 2x2/2 max-pool): air_model.py:510-535.  x [B,H,W,cin] (any [B, H*W*cin] view)."""
+    check(lib().air_conv5x5_fwd(ptr(x), ptr(w), ptr(b), ptr(out), ptr(argmax), x.shape[0], H, W, cin, cout, int(pool),
+                                stream()), "air_conv5x5_fwd")
+
+
+def conv5x5_bwd_workspace(B, cin, cout):
+    return int(lib().air_conv5x5_bwd_workspace(B, cin, cout))
+
+
+def conv5x5_bwd(x, w, out, argmax, dout, din, dw, db, accumulate, workspace, H, W, cin, cout, pool):
+    check(lib().air_conv5x5_bwd(ptr(x), ptr(w), ptr(out), ptr(argmax), ptr(dout), ptr(din), ptr(dw), ptr(db),
+                                int(accumulate), ptr(workspace), x.shape[0], H, W, cin, cout, int(pool), stream()),
+          "air_conv5x5_bwd")
+
