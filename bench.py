@@ -278,6 +278,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["train", "st", "infer"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 4096 train, 65536 st)")
     ap.add_argument("--gemm", default=None, help="GEMM mode for the train workload")
+    ap.add_argument("--cnn", action="store_true", help="train/infer with the CNN front-end (AIRModel(cnn=True)); not the headline config")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     peaks = measured_peaks()

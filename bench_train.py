@@ -11,13 +11,14 @@ from bench import ClockSampler, barrier, max_over_ranks, time_launches
 METRIC = "AIR train images/sec"
 
 
-def _model(B, gemm_mode, seed, train=True, max_steps=3):
+def _model(B, gemm_mode, seed, train=True, max_steps=3, cnn=False):
     import air_b200 as ab
     from importlib import import_module
     data = import_module("tf-attend-infer-repeat_b200.data")
     imgs, cnt = data.synthetic_canvases(B, seed=seed)
     hyper = dict(data.TRAINING_HYPER)
     hyper["max_steps"] = max_steps
+    hyper["cnn"] = bool(cnn)   # air_model.py:510-535 front-end (the reference's own scripts all run cnn=False)
     ab.reset_variable_scopes()
     m = ab.AIRModel(imgs.cuda(), cnt.cuda(), train=train, annealing_schedules=data.TRAINING_ANNEALING,
                     gemm_mode=gemm_mode, seed=0, **hyper)
@@ -52,7 +53,7 @@ def run(args, rank, world, peaks):
     T = 5 if infer else 3
     if infer and not args.batch:
         B = 65536
-    m, imgs, cnt, data = _model(B, mode, seed=rank, train=not infer, max_steps=T)
+    m, imgs, cnt, data = _model(B, mode, seed=rank, train=not infer, max_steps=T, cnn=getattr(args, "cnn", False))
     if infer:
         step = lambda: m.run()
     else:
@@ -148,6 +149,7 @@ def run(args, rank, world, peaks):
         "config": {"workload": ("AIRModel default (training.py:100-122) full train step: forward, backward, "
                                 "global-norm clip, TF-Adam; T=3" if not infer else
                                 "AIRModel default inference (train=False), T=5"),
+                   "cnn_frontend": bool(getattr(args, "cnn", False)),
                    "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": mode, "parallelism": f"dp{world}",
                    "noise": "drawn on device inside the timed step", "cuda_graph": not infer,
                    "l2": f"per-step working set ~{B * 61e3 / 1e6:.0f} MB of activations + 16 MB weights > 126 MB L2"},

@@ -191,8 +191,13 @@ def test_inference_config_five_steps():
 
 def test_constructor_rejects_out_of_scope_options():
     x, t = torch.zeros(2, 2500, device="cuda"), torch.zeros(2, dtype=torch.int32, device="cuda")
+    ab.reset_variable_scopes()
+    m = ab.AIRModel(x, t)                                   # the reference's literal defaults: cnn=True, 8 filters
+    assert m.cnn and m.Kx.shape == (12 * 12 * 8, 1024)
     with pytest.raises(NotImplementedError):
-        ab.AIRModel(x, t)                                   # reference default cnn=True is a "next" row
+        ab.AIRModel(x, t, cnn_filters=16)                   # conv kernels are built for the reference's 8 filters
+    with pytest.raises(NotImplementedError):
+        ab.AIRModel(x, t, cnn=False, scale_hidden_units=32)  # the fused heads kernel needs equal hidden sizes
     with pytest.raises(ab.AirError):
         ab.AIRModel(x.cpu(), t.cpu(), cnn=False)
 

@@ -237,3 +237,35 @@ def test_concrete_step_invariants(n, seed, train, tau):
     assert np.all(out["stop_new"] >= sp)                                       # the stopping sum never decreases
     assert np.array_equal(out["digits_new"], (out["stop_new"] < np.float32(0.99)).astype(np.int32))
     assert np.array_equal(out["loss_new"] != 0, (sp < np.float32(0.99)) & (out["kl"] != 0))   # KL masked by the OLD sum
+
+
+def test_cnn_frontend_shapes_and_store_init_match_oracle():
+    """cnn=True (air_model.py:510-535): 50x50x1 -> conv/pool 25x25x8 -> conv/pool 12x12x8 -> conv 12x12x8 -> [B,1152];
+    the host ParamStore initialises the same tensors, in the same RNG order, as the oracle."""
+    import air_b200 as ab
+    from air_b200 import checkpoint
+    p = O.init_params(seed=4, cnn=True)
+    assert tuple(p["cnn/conv1/kernel"].shape) == (5, 5, 1, 8) and tuple(p["rnn/kernel"].shape) == (1152 + 256, 1024)
+    x = torch.rand(3, 2500)
+    f = O.cnn_frontend(x, p)
+    assert tuple(f.shape) == (3, 1152) and float(f.min()) >= 0.0
+    # NHWC flatten: feature (y, x, c) of image b sits at index (y*12 + x)*8 + c
+    import torch.nn.functional as F
+    t = torch.relu(F.conv2d(x.reshape(3, 1, 50, 50), p["cnn/conv1/kernel"].permute(3, 2, 0, 1), p["cnn/conv1/bias"], padding=2))
+    t = F.max_pool2d(t, 2, 2)
+    t = F.max_pool2d(torch.relu(F.conv2d(t, p["cnn/conv2/kernel"].permute(3, 2, 0, 1), p["cnn/conv2/bias"], padding=2)), 2, 2)
+    t = torch.relu(F.conv2d(t, p["cnn/conv3/kernel"].permute(3, 2, 0, 1), p["cnn/conv3/bias"], padding=2))
+    assert torch.equal(f.reshape(3, 12, 12, 8)[1, 5, 7, 3], t[1, 3, 5, 7])
+    store = ab.ParamStore("cpu", 1152, 784, 256, 64, 50, (512, 256), (256, 512), seed=4, cnn_filters=8)
+    named = store.named_views()
+    assert list(named)[:6] == [f"cnn/conv{i}/{n}" for i in (1, 2, 3) for n in ("kernel", "bias")]
+    for k, v in p.items():
+        assert torch.equal(named[k], v), k
+    names = checkpoint.model_tensors(store)
+    assert "air/cnn/conv1/kernel" in names and "air/rnn/rnn/kernel" in names and "air/training/air/cnn/conv2/bias/Adam" in names
+    # an oracle forward pass with the front-end runs end to end and differs from the plain model
+    imgs, cnt = O.synthetic_canvases(4, seed=0)
+    noise = O.make_noise(1, 3, 4)
+    out = O.AIROracle(params=p, cnn=True).forward(imgs, cnt, noise)
+    assert torch.isfinite(out["loss"])
+

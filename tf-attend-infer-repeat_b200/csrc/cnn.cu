@@ -247,7 +247,15 @@ static int launch_conv_bwd(const float *in, const float *w, const float *out, co
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(conv5x5_bwd): %s", cudaGetErrorString(e));
   }
-  const int ctas = conv_bwd_ctas(B), R = ctas * (THREADS / GS);
+  // one wave of CTAs: as many as are co-resident (shared memory limits the 25x25x8 layer to 3 per SM), each looping
+  // over its share of the images -- more CTAs than that would run as a second, partial wave
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    AIR_REQUIRE(e == cudaSuccess && per_sm > 0, AIR_ERR_CUDA, "conv5x5_bwd occupancy query: %s", cudaGetErrorString(e));
+    per_sm = std::min(per_sm, 4);  // the workspace is sized for 4 CTAs per SM
+  }
+  const int ctas = static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(sm_count()) * per_sm)), R = ctas * (THREADS / GS);
   AIR_LAUNCH(kern, ctas, THREADS, smem, s, in, w, out, arg, dout, din, workspace, B);
   count_launch();
   int rc = check_launch("conv5x5_bwd");
