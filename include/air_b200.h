@@ -177,7 +177,9 @@ int air_heads_fwd(const float *hidden, const float *w_out, const float *b_out, c
 /* Backward of air_heads_fwd.  dtheta / dtheta_inv [B,6], dz [B] come from the ST kernels;
  * dloss is d(total)/d(running_loss[b]) (1/batch).  Writes dhidden [B,5*HU] (ReLU mask applied)
  * and accumulates (if accumulate) or writes d(w_out) [7,HU] and d(b_out) [7]; deterministic.
- * workspace: at least air_heads_bwd_workspace(B, HU) floats. */
+ * workspace: at least air_heads_bwd_workspace(B, HU) floats = R rows of (7*HU + 7) per-CTA partial sums.
+ * dw_out == db_out == NULL: only the partials are written; the caller sums the rows of all its steps once with
+ * air_reduce_rows (stride 7*HU + 7: d(w_out) at column 0, d(b_out) at column 7*HU). */
 int64_t air_heads_bwd_workspace(int64_t B, int HU);
 int air_heads_bwd(const float *hidden, const float *w_out, const float *noise_scale, const float *noise_shift,
                   const float *fields, const float *dtheta, const float *dtheta_inv, const float *dz,
@@ -213,6 +215,22 @@ int air_finalize_loss(const float *running_loss, const float *rec_loss, const in
 int64_t air_colsum_workspace(int64_t B, int N);
 int air_colsum(const float *X, int ld, float *out, int accumulate, float *workspace, int64_t B, int N,
                air_stream_t stream);
+
+/* Several column sums in one launch pair (all bias gradients of a train step).  items[i]: out[N] (+)= column sums
+ * of X [rows, N] (leading dimension ld).  At most 16 items; workspace >= air_colsum_multi_workspace(items, n). */
+typedef struct air_colsum_item {
+  const float *X;
+  float *out;
+  int64_t rows;
+  int ld, N, accumulate;
+} air_colsum_item_t;
+int64_t air_colsum_multi_workspace(const air_colsum_item_t *items, int n_items);
+int air_colsum_multi(const air_colsum_item_t *items, int n_items, float *workspace, air_stream_t stream);
+
+/* out[e] (+)= sum_{r < R} partials[r * stride + e] for e < n, fixed summation order (deterministic).  The second
+ * stage of air_heads_bwd when that is called with dw_out == db_out == NULL (per-step partials reduced once per
+ * train step instead of once per loop step). */
+int air_reduce_rows(const float *partials, int R, int stride, int n, float *out, int accumulate, air_stream_t stream);
 
 /* air_model.py:673, 692: tf.clip_by_global_norm + tf.train.AdamOptimizer.apply_gradients on a flat
  * parameter buffer of n floats.  state (device, 8 floats): [0] beta1^t, [1] beta2^t, [2] global_step,

@@ -159,6 +159,36 @@ def test_colsum_deterministic():
         assert torch.equal(again, first)
 
 
+def test_colsum_multi_and_reduce_rows():
+    torch.manual_seed(5)
+    shapes = [(12288, 512), (12288, 100), (4096, 1024), (37, 7), (12288, 784)]
+    Xs = [torch.randn(r, n + 3, device=DEV)[:, :n] for r, n in shapes]          # row-strided views
+    outs = [torch.full((n,), 3.0, device=DEV) for _, n in shapes]
+    accs = [False, True, False, False, True]
+    items = ops.colsum_items(list(zip(Xs, outs, accs)))
+    ws = torch.zeros(ops.colsum_multi_workspace(items), device=DEV)
+    ops.colsum_multi(items, ws)
+    for X, o, a in zip(Xs, outs, accs):
+        want = X.double().sum(0) + (3.0 if a else 0.0)
+        assert relnorm(o, want) < 2e-6
+    first = [o.clone() for o in outs]
+    for o in outs:
+        o.fill_(3.0)
+    ops.colsum_multi(items, ws)
+    assert all(torch.equal(a, b) for a, b in zip(first, outs))                       # deterministic
+    # the single-tensor entry point gives the same bits
+    single = torch.empty(512, device=DEV)
+    ops.colsum(Xs[0], single, False, torch.zeros(int(K.lib().air_colsum_workspace(12288, 512)), device=DEV))
+    assert torch.equal(single, outs[0])
+    part = torch.randn(300, 455, device=DEV)
+    out = torch.empty(448, device=DEV)
+    ops.reduce_rows(part, 300, 455, 448, out)
+    assert relnorm(out, part[:, :448].double().sum(0)) < 2e-6
+    out7 = torch.ones(7, device=DEV)
+    ops.reduce_rows(part.view(-1)[448:], 300, 455, 7, out7, accumulate=True)
+    assert relnorm(out7, part[:, 448:].double().sum(0) + 1.0) < 2e-6
+
+
 def test_adam_step_matches_tf_semantics():
     torch.manual_seed(3)
     orc = O.AIROracle(seed=1)

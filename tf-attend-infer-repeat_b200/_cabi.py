@@ -52,6 +52,9 @@ _SIGS = {
     "air_adam_step": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float] * 5 + [_c_f, ctypes.c_int64, _c_f]),
     "air_anneal": (ctypes.c_int, [_c_f] + [ctypes.c_float] * 3 + [ctypes.c_int] + [ctypes.c_float] * 2 +
                    [ctypes.c_int, _c_f, _c_f]),
+    "air_colsum_multi_workspace": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
+    "air_colsum_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_f, _c_f]),
+    "air_reduce_rows": (ctypes.c_int, [_c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_f, ctypes.c_int, _c_f]),
     "air_conv5x5_fwd": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
     "air_conv5x5_bwd_workspace": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "air_conv5x5_bwd": (ctypes.c_int, [_c_f] * 8 + [ctypes.c_int, _c_f, ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
@@ -73,6 +76,12 @@ EPI_NONE, EPI_RELU, EPI_SOFTPLUS, EPI_MUL_DRELU, EPI_MUL_DSOFTPLUS, EPI_SIGMOID_
 GEMM_MODES = {"fp32": 0, "tf32": 1}
 
 _lib = None
+
+
+class ColsumItem(ctypes.Structure):
+    """air_colsum_item_t of include/air_b200.h."""
+    _fields_ = [("X", ctypes.c_void_p), ("out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("ld", ctypes.c_int),
+                ("N", ctypes.c_int), ("accumulate", ctypes.c_int)]
 
 
 class AirError(RuntimeError):

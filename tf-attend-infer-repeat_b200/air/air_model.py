@@ -32,7 +32,8 @@ import torch
 from .. import _cabi as C
 from .. import dp, ops
 from .params import ParamStore
-from .vae import (VAEWeights, _flat2, alloc_vae_scratch, dense_dw, vae_backward_dx, vae_forward, vae_weight_grads)
+from .vae import (VAEWeights, _flat2, alloc_vae_scratch, dense_dw, vae_backward_dx, vae_bias_items, vae_forward,
+                  vae_weight_grads)
 
 _VARIABLE_SCOPES = {}
 
@@ -167,9 +168,9 @@ class AIRModel:
             w["dgates"], w["dgates_sum"] = z(T, B, 4 * R), z(B, 4 * R)
             w["vae_d"] = alloc_vae_scratch(B, win, self.vae_recognition_units, L, self.vae_generative_units, dev,
                                            lead=(T,))
-            nmax = max(4 * R, 5 * HU, win, 2 * L, *self.vae_recognition_units, *self.vae_generative_units)
-            w["colsum_ws"] = torch.zeros(int(C.lib().air_colsum_workspace(B, nmax)), device=dev)
-            w["heads_ws"] = torch.zeros(int(C.lib().air_heads_bwd_workspace(B, HU)), device=dev)
+            # per-CTA partial sums of d(heads/out_w|b) for every step; summed once per train step
+            self._heads_rows = int(C.lib().air_heads_bwd_workspace(B, HU)) // (7 * HU + 7)
+            w["heads_ws"] = torch.zeros(T, self._heads_rows * (7 * HU + 7), device=dev)
             w["adam_ws"] = torch.zeros(int(C.lib().air_adam_workspace(self.store.n)), device=dev)
         if self.cnn:
             F = self.cnn_filters
@@ -186,6 +187,13 @@ class AIRModel:
         self.Kx, self.Kh = p["rnn/kernel"][:in_dim], p["rnn/kernel"][in_dim:]
         self.gKx, self.gKh = g["rnn/kernel"][:in_dim], g["rnn/kernel"][in_dim:]
         self.vw = VAEWeights(p, g, len(self.vae_recognition_units), len(self.vae_generative_units))
+        if self.train:
+            # every bias gradient of the step = column sums of a time-batched dY buffer: one launch pair for all
+            pairs = vae_bias_items(self.vw, w["vae_d"]) + [(_flat2(w["dhh"]), g["heads/hidden_b"], False),
+                                                            (w["dgates_sum"], g["rnn/bias"], False)]
+            self._colsum_items = ops.colsum_items(pairs)
+            self._colsum_keep = pairs  # the ctypes array holds raw pointers: keep the views alive
+            w["colsum_ws"] = torch.zeros(ops.colsum_multi_workspace(self._colsum_items), device=dev)
 
     # ------------------------------------------------------------------------------------------
     def feed(self, input_images, target_num_digits=None):
@@ -310,8 +318,7 @@ class AIRModel:
                             dx_out=w["dwin"], dgen_is_presigmoid=True)
             ops.st_backward(x, w["theta"][t], w["dwin"], None, w["dtheta"], cs, cs, 1, wsz, wsz)
             ops.heads_bwd(w["hh"][t], p["heads/out_w"], n["scale"][t], n["shift"][t], f, w["dtheta"], w["dtheta_inv"],
-                          w["dz"], self._prior, hp, dscale, w["dhh"][t], g["heads/out_w"], g["heads/out_b"], not last,
-                          w["heads_ws"])
+                          w["dz"], self._prior, hp, dscale, w["dhh"][t], None, None, False, w["heads_ws"][t])
             # dh_t = dhh_t W_hid^T (+ the LSTM path from step t+1)
             ops.gemm(w["dhh"][t], p["heads/hidden_w"], w["dh"], Cinit=None if last else w["dh_next"], tB=True, mode=mode)
             ops.lstm_bwd(w["gates"][t], w["c"][t - 1] if t > 0 else None, w["c"][t], w["dh"],
@@ -321,10 +328,13 @@ class AIRModel:
             if getattr(self, "_debug", None) is not None:  # per-step intermediate gradients for diagnostics
                 self._debug[t] = {k: w[k].clone() for k in ("dwin", "dtheta", "dtheta_inv", "dz", "dh")}
         # ---- weight gradients, once per train step, over the time-batched buffers
-        cws = w["colsum_ws"]
+        HU = self.scale_hidden_units
+        nw = 7 * HU
+        ops.reduce_rows(w["heads_ws"], T * self._heads_rows, nw + 7, nw, g["heads/out_w"])
+        ops.reduce_rows(w["heads_ws"].view(-1)[nw:], T * self._heads_rows, nw + 7, 7, g["heads/out_b"])
         allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
-        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, vd, cws, mode)
-        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], cws, mode)
+        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, vd, None, mode)
+        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], None, mode)
         if T > 1:   # K_h sees h_{t-1}: rows t = 1..T-1 (h_{-1} = 0 contributes nothing)
             ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode)
         else:
@@ -332,7 +342,7 @@ class AIRModel:
         # the image rows of the LSTM kernel see the same input every step: one GEMM on the summed dgates
         rnn_in = w["cnn_out"][2] if self.cnn else x
         ops.gemm(rnn_in, w["dgates_sum"], self.gKx, tA=True, mode=mode)
-        ops.colsum(w["dgates_sum"], g["rnn/bias"], False, cws)
+        ops.colsum_multi(self._colsum_items, w["colsum_ws"])
         if self.cnn:
             self._cnn_backward()
 

@@ -70,7 +70,8 @@ def dense_dx(x_in, W, dY, dX, mode, act_of_x=False):
 def dense_dw(x_in, dY, gW, gb, colsum_ws, mode, accumulate=False):
     """gW (+)= x_in^T dY, gb (+)= colsum(dY).  x_in / dY may be time-batched [T*B, .] views."""
     ops.gemm(x_in, dY, gW, Cinit=gW if accumulate else None, tA=True, mode=mode)
-    ops.colsum(dY, gb, accumulate, colsum_ws)
+    if colsum_ws is not None:  # None: the caller sums all its bias gradients in one launch (vae_bias_items)
+        ops.colsum(dY, gb, accumulate, colsum_ws)
 
 
 def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fields, mode, dx_out=None,
@@ -115,6 +116,13 @@ def vae_weight_grads(x, w: VAEWeights, buf, dbuf, colsum_ws, mode, accumulate=Fa
     grads = list(w.g_rec) + [w.g_ml]
     for a, dy, (gW, gb) in zip(acts, dys, grads):
         dense_dw(_flat2(a), _flat2(dy), gW, gb, colsum_ws, mode, accumulate)
+
+
+def vae_bias_items(w: VAEWeights, dbuf, accumulate=False):
+    """(dY, d(bias), accumulate) of every VAE layer, for ops.colsum_multi (same pairing as vae_weight_grads)."""
+    dys = list(dbuf["ddec"]) + [dbuf["dgen"]] + list(dbuf["denc"]) + [dbuf["dml"]]
+    gbs = [gb for _, gb in list(w.g_gen) + [w.g_gm] + list(w.g_rec) + [w.g_ml]]
+    return [(_flat2(dy), gb, accumulate) for dy, gb in zip(dys, gbs)]
 
 
 def _flat2(t):

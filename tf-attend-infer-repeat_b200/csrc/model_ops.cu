@@ -494,6 +494,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Several column sums in ONE launch (the bias gradients of a train step: ~10 tensors of very different widths).
+struct ColsumItem { const float *X; float *out; int64_t rows; int ld, N, accumulate, R, rows_per_chunk, cta0, ws0, out0; };
+constexpr int kMaxColsumItems = 16;
+struct ColsumBatch { ColsumItem it[kMaxColsumItems]; int n; };
+
+__global__ void __launch_bounds__(256) colsum_multi_partial_k(ColsumBatch batch, float *__restrict__ workspace) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
+  __shared__ float red[8][33];
+  int i = 0;
+  while (i + 1 < batch.n && static_cast<int>(blockIdx.x) >= batch.it[i + 1].cta0) ++i;
+  const ColsumItem &q = batch.it[i];
+  const int local = blockIdx.x - q.cta0, cb = (q.N + 31) / 32;
+  const int chunk = local / cb, col = (local - chunk * cb) * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r0 = static_cast<int64_t>(chunk) * q.rows_per_chunk;
+  const int64_t r1 = (r0 + q.rows_per_chunk < q.rows) ? r0 + q.rows_per_chunk : q.rows;
+  const float *X = q.X;
+  const int64_t ld = q.ld;
+  float acc = 0.0f;
+  if (col < q.N) {
+    int64_t r = r0 + w;
+    for (; r + 56 < r1; r += 64) {  // 8 independent loads in flight per lane, summed in row order
+      const float v0 = X[r * ld + col], v1 = X[(r + 8) * ld + col], v2 = X[(r + 16) * ld + col], v3 = X[(r + 24) * ld + col];
+      const float v4 = X[(r + 32) * ld + col], v5 = X[(r + 40) * ld + col], v6 = X[(r + 48) * ld + col], v7 = X[(r + 56) * ld + col];
+      acc = (((((((acc + v0) + v1) + v2) + v3) + v4) + v5) + v6) + v7;
+    }
+    for (; r < r1; r += 8) acc += X[r * ld + col];
+  }
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && col < q.N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    workspace[q.ws0 + static_cast<int64_t>(chunk) * q.N + col] = t;
+  }
+}
+
+// second stage for all items: one warp per output element (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) colsum_multi_reduce_k(ColsumBatch batch, const float *__restrict__ workspace, int total) {
+  pdl_sync();  // PDL: no global access before the previous grid has completed
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t e = warp0; e < total; e += nwarps) {
+    int i = 0;
+    while (i + 1 < batch.n && e >= batch.it[i + 1].out0) ++i;
+    const ColsumItem &q = batch.it[i];
+    const int col = static_cast<int>(e - q.out0);
+    float acc = 0.0f;
+    for (int r = lane; r < q.R; r += 32) acc += workspace[q.ws0 + static_cast<int64_t>(r) * q.N + col];
+    acc = warp_sum(acc);
+    if (lane == 0) q.out[col] = q.accumulate ? q.out[col] + acc : acc;
+  }
+}
+
 static int colsum_chunks(int64_t B, int N) {
   const int cb = (N + 31) / 32;
   int R = (2 * sm_count() + cb - 1) / cb;
@@ -666,14 +722,14 @@ extern "C" int air_heads_bwd(const float *hidden, const float *w_out, const floa
   AIR_REQUIRE(B >= 0 && HU > 0, AIR_ERR_BAD_SHAPE, "heads_bwd: bad shape");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(hidden && w_out && noise_scale && noise_shift && fields && dtheta && dtheta_inv && dz && prior_log_odds &&
-                  hyper && dhidden && dw_out && db_out && workspace,
+                  hyper && dhidden && workspace && ((dw_out != nullptr) == (db_out != nullptr)),
               AIR_ERR_NULL, "heads_bwd: null pointer");
   const int R = static_cast<int>((B + kHeadsImgs - 1) / kHeadsImgs);
   AIR_LAUNCH(heads_bwd_k, R, 256, 0, ST(stream), hidden, w_out, noise_scale, noise_shift, fields, dtheta, dtheta_inv, dz,
                                          prior_log_odds, *hyper, dloss, dhidden, workspace, B, HU);
   count_launch();
   int rc = check_launch("heads_bwd");
-  if (rc) return rc;
+  if (rc || !dw_out) return rc;  // dw_out == NULL: the caller reduces the per-CTA partials itself (air_reduce_rows)
   const int n = 7 * HU;
   AIR_LAUNCH(reduce_rows_k, grid_for(static_cast<int64_t>(n) * 32, 256), 256, 0, ST(stream), workspace, R, n + 7, n, dw_out, accumulate);
   AIR_LAUNCH(reduce_rows_k, 1, 256, 0, ST(stream), workspace + n, R, n + 7, 7, db_out, accumulate);
@@ -765,6 +821,42 @@ extern "C" int air_colsum(const float *X, int ld, float *out, int accumulate, fl
   AIR_LAUNCH(reduce_rows_k, grid_for(static_cast<int64_t>(N) * 32, 256), 256, 0, ST(stream), workspace, R, N, N, out, accumulate);
   count_launch();
   return check_launch("colsum reduce");
+}
+
+extern "C" int64_t air_colsum_multi_workspace(const air_colsum_item_t *items, int n_items) {
+  int64_t tot = 0;
+  for (int i = 0; items && i < n_items; ++i) tot += static_cast<int64_t>(64) * items[i].N;
+  return tot + 64;
+}
+
+extern "C" int air_colsum_multi(const air_colsum_item_t *items, int n_items, float *workspace, air_stream_t stream) {
+  AIR_REQUIRE(items && n_items > 0 && n_items <= kMaxColsumItems, AIR_ERR_BAD_SHAPE, "colsum_multi: 1..%d items", kMaxColsumItems);
+  AIR_REQUIRE(workspace, AIR_ERR_NULL, "colsum_multi: null workspace");
+  ColsumBatch batch;
+  int ctas = 0, ws = 0, outs = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const air_colsum_item_t &a = items[i];
+    AIR_REQUIRE(a.X && a.out && a.rows > 0 && a.N > 0 && a.ld >= a.N, AIR_ERR_BAD_SHAPE, "colsum_multi: bad item %d", i);
+    ColsumItem &q = batch.it[i];
+    q.X = a.X; q.out = a.out; q.rows = a.rows; q.ld = a.ld; q.N = a.N; q.accumulate = a.accumulate;
+    q.R = colsum_chunks(a.rows, a.N);
+    q.rows_per_chunk = static_cast<int>((a.rows + q.R - 1) / q.R);
+    q.cta0 = ctas; q.ws0 = ws; q.out0 = outs;
+    ctas += q.R * ((a.N + 31) / 32);
+    ws += q.R * a.N;
+    outs += a.N;
+  }
+  batch.n = n_items;
+  AIR_LAUNCH(colsum_multi_partial_k, ctas, 256, 0, ST(stream), batch, workspace);
+  AIR_LAUNCH(colsum_multi_reduce_k, grid_for(static_cast<int64_t>(outs) * 32, 256), 256, 0, ST(stream), batch,
+             static_cast<const float *>(workspace), outs);
+  count_launch(2);
+  return check_launch("colsum_multi");
+}
+
+extern "C" int air_reduce_rows(const float *partials, int R, int stride, int n, float *out, int accumulate, air_stream_t stream) {
+  AIR_REQUIRE(partials && out && R > 0 && n > 0 && stride >= n, AIR_ERR_BAD_SHAPE, "reduce_rows: bad arguments");
+  return reduce_rows_launch(partials, R, stride, n, out, accumulate, ST(stream));
 }
 
 extern "C" int64_t air_adam_workspace(int64_t n) { return kAdamPartials + 8 + 0 * n; }

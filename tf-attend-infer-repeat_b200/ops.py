@@ -64,6 +64,7 @@ def heads_bwd(hidden, w_out, n_scale, n_shift, fields, dtheta, dtheta_inv, dz, p
               db_out, accumulate, workspace):
     B = hidden.shape[0]
     HU = w_out.shape[1]
+    # dw_out = db_out = None: per-CTA partials only (summed later over all steps with reduce_rows)
     check(lib().air_heads_bwd(ptr(hidden), ptr(w_out), ptr(n_scale), ptr(n_shift), ptr(fields), ptr(dtheta),
                               ptr(dtheta_inv), ptr(dz), ptr(prior), ctypes.byref(hyper), float(dloss), ptr(dhidden),
                               ptr(dw_out), ptr(db_out), int(accumulate), ptr(workspace), B, HU, stream()),
@@ -105,6 +106,30 @@ def finalize_loss(running_loss, rec_loss, digits, target, out, loss_per_item=Non
 def colsum(X, out, accumulate, workspace):
     B, N = X.shape
     check(lib().air_colsum(_p2(X), _ld(X), ptr(out), int(accumulate), ptr(workspace), B, N, stream()), "air_colsum")
+
+
+def colsum_items(pairs):
+    """[(X [rows,N] (row-strided view allowed), out [N], accumulate), ...] -> ctypes array for colsum_multi."""
+    arr = (C.ColsumItem * len(pairs))()
+    for a, (X, out, acc) in zip(arr, pairs):
+        a.X, a.out = X.data_ptr(), out.data_ptr()
+        a.rows, a.ld, a.N, a.accumulate = X.shape[0], _ld(X), X.shape[1], int(acc)
+        if not (X.is_cuda and out.is_cuda and X.dtype == out.dtype == torch.float32 and out.is_contiguous()):
+            raise C.AirError("colsum_multi needs float32 CUDA tensors (no CPU fallback)")
+    return arr
+
+
+def colsum_multi_workspace(items):
+    return int(lib().air_colsum_multi_workspace(items, len(items)))
+
+
+def colsum_multi(items, workspace):
+    """All column sums of ``items`` (from colsum_items) in one launch pair."""
+    check(lib().air_colsum_multi(items, len(items), ptr(workspace), stream()), "air_colsum_multi")
+
+
+def reduce_rows(partials, R, stride, n, out, accumulate=False):
+    check(lib().air_reduce_rows(ptr(partials), R, stride, n, ptr(out), int(accumulate), stream()), "air_reduce_rows")
 
 
 def adam_step(params, grads, m, v, state, clip_norm, beta1, beta2, eps, grad_scale, workspace):
