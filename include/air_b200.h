@@ -247,6 +247,15 @@ int air_adam_step(float *params, const float *grads, float *m, float *v, float *
 int air_anneal(const float *state, float init, float factor, float iters, int staircase, float vmin, float vmax,
                int take_log, float *out, air_stream_t stream);
 
+/* ---- synthetic input canvases, generated on the device -------------------------------
+ * Stand-in for multi_mnist.py:82-183 (needs the MNIST download): 0..max_digits stroke-like blobs (14-24 x 10-24
+ * pixels) per canvas, uniform placement with pixel-overlap rejection (generate_multi_image, :141-160, 20 attempts),
+ * background exactly 0.0, values in (0, 1]; counts[b] = number of digits drawn for that image's target label.
+ * Counter-based RNG: image first_index + b depends only on (seed, first_index + b), so ranks generate their own
+ * shards of one global data set.  images [B, canvas_size^2], counts [B].  Bit-exact vs oracle/synth_oracle.py. */
+int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int64_t B, int canvas_size,
+                       int max_digits, air_stream_t stream);
+
 /* ---- CNN front-end of AIRModel(cnn=True): air_model.py:510-535 -------------------------
  * tf.layers.conv2d(filters=8, kernel_size=5, padding="same", activation=relu) optionally followed by
  * tf.layers.max_pooling2d(pool_size=2, strides=2) ("valid": 25 -> 12), NHWC.

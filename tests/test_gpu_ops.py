@@ -189,6 +189,28 @@ def test_colsum_multi_and_reduce_rows():
     assert relnorm(out7, part[:, 448:].double().sum(0) + 1.0) < 2e-6
 
 
+def test_device_canvas_generator_bit_exact_and_shardable():
+    from air_b200 import data
+    from oracle import synth_oracle as S
+    im, cnt = data.device_canvases(193, seed=11, first_index=5)
+    want_im, want_cnt = S.synth_canvases(193, seed=11, first_index=5)
+    assert np.array_equal(cnt.cpu().numpy(), want_cnt) and np.array_equal(im.cpu().numpy(), want_im)   # bit-exact
+    # image i of a seed does not depend on the batch it is generated in (data-parallel shards)
+    a, ca = data.device_canvases(64, seed=11, first_index=5)
+    b, cb = data.device_canvases(129, seed=11, first_index=69)
+    assert torch.equal(torch.cat([a, b]), im) and torch.equal(torch.cat([ca, cb]), cnt)
+    # statistics of the stand-in data set (multi_mnist.py strata: 0 / 1 / 2 digits equally likely)
+    big, cbig = data.device_canvases(30000, seed=1)
+    frac = torch.bincount(cbig, minlength=3).float() / 30000
+    assert (frac - 1 / 3).abs().max() < 0.02 and big.min() == 0 and 0.9 < big.max() <= 1.0
+    empty = cbig == 0
+    assert not big[empty].any() and (big[~empty] > 0).any(1).all()
+    # in place refill of a model's input buffers
+    buf = (torch.empty(8, 2500, device=DEV), torch.empty(8, device=DEV, dtype=torch.int32))
+    data.device_canvases(8, seed=11, first_index=5, out=buf)
+    assert torch.equal(buf[0], im[:8])
+
+
 def test_adam_step_matches_tf_semantics():
     torch.manual_seed(3)
     orc = O.AIROracle(seed=1)

@@ -269,3 +269,19 @@ def test_cnn_frontend_shapes_and_store_init_match_oracle():
     out = O.AIROracle(params=p, cnn=True).forward(imgs, cnt, noise)
     assert torch.isfinite(out["loss"])
 
+
+def test_synth_oracle_properties():
+    """The restated device canvas generator: digit counts uniform over {0,1,2}, exact-zero background, no overlap
+    clash (a canvas with k digits has k connected blobs' worth of pixels), image i independent of the batch."""
+    from oracle import synth_oracle as S
+    im, cnt = S.synth_canvases(600, seed=2)
+    assert im.shape == (600, 2500) and im.dtype == np.float32 and cnt.dtype == np.int32
+    frac = np.bincount(cnt, minlength=3) / 600.0
+    assert np.abs(frac - 1 / 3).max() < 0.07
+    assert im.min() == 0.0 and 0.9 < im.max() <= 1.0
+    assert not im[cnt == 0].any() and (im[cnt > 0] > 0).any(1).all()
+    a, ca = S.synth_canvases(10, seed=2, first_index=100)
+    assert np.array_equal(a, im[100:110]) and np.array_equal(ca, cnt[100:110])
+    more = (im[cnt == 2] > 0).sum(1).mean() > 1.5 * (im[cnt == 1] > 0).sum(1).mean()
+    assert more                                                         # two digits -> about twice the ink
+

@@ -655,6 +655,79 @@ __global__ void anneal_k(const float *state, float init, float factor, float ite
   *out = v;
 }
 
+// =========================================================================================
+// Synthetic multi-digit canvases on the device (stand-in for multi_mnist.py:82-183, whose MNIST source is not
+// available offline): 0..max_digits stroke-like blobs per canvas, uniform placement with pixel-overlap rejection
+// (generate_multi_image, :141-160), background exactly 0.  Counter-based RNG: image i of a seed is the same
+// whatever the batch or the sharding.  Restated bit for bit in oracle/synth_oracle.py.
+// =========================================================================================
+__device__ __forceinline__ uint64_t synth_rnd(uint64_t seed, uint64_t image, uint32_t draw) {
+  uint64_t z = seed + (image + 1) * 0x9E3779B97F4A7C15ull + static_cast<uint64_t>(draw) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+    synth_canvases_k(uint64_t seed, int64_t first, float *__restrict__ images, int32_t *__restrict__ counts, int cs,
+                     int max_digits) {
+  extern __shared__ float sC[];  // [cs*cs]
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const uint64_t img = static_cast<uint64_t>(first + b);
+  for (int p = tid; p < cs * cs; p += 256) sC[p] = 0.0f;
+  const int count = static_cast<int>((synth_rnd(seed, img, 0) >> 33) % static_cast<uint64_t>(max_digits + 1));
+  uint32_t draw = 1;
+  __syncthreads();
+  for (int k = 0; k < count; ++k) {
+    for (int attempt = 0; attempt < 20; ++attempt) {
+      const int hh = 14 + static_cast<int>((synth_rnd(seed, img, draw + 0) >> 33) % 11u);
+      const int ww = 10 + static_cast<int>((synth_rnd(seed, img, draw + 1) >> 33) % 15u);
+      const float bar_on = static_cast<float>((synth_rnd(seed, img, draw + 2) >> 33) & 1u);
+      const float u = static_cast<float>(synth_rnd(seed, img, draw + 3) >> 40) * 5.9604644775390625e-08f;  // 2^-24
+      const float bar_off = -2.0f + 4.0f * u;
+      const int top = static_cast<int>((synth_rnd(seed, img, draw + 4) >> 33) % static_cast<uint64_t>(cs - hh + 1));
+      const int left = static_cast<int>((synth_rnd(seed, img, draw + 5) >> 33) % static_cast<uint64_t>(cs - ww + 1));
+      draw += 6;
+      const float cy = static_cast<float>(hh - 1) / 2.0f, cx = static_cast<float>(ww - 1) / 2.0f;
+      const float ry = fmaxf(static_cast<float>(hh) / 2.0f - 1.5f, 2.0f), rx = fmaxf(static_cast<float>(ww) / 2.0f - 1.5f, 2.0f);
+      float v[3];  // hh * ww <= 24 * 24 = 576 <= 3 * 256
+      int clash = 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int p = tid + 256 * q;
+        v[q] = 0.0f;
+        if (p < hh * ww) {
+          const int y = p / ww, x = p - y * ww;
+          const float dy = (static_cast<float>(y) - cy) / ry, dx = (static_cast<float>(x) - cx) / rx;
+          const float r = sqrtf(dy * dy + dx * dx);
+          const float ring = fminf(fmaxf(1.0f - fabsf(r - 0.8f) * 3.0f, 0.0f), 1.0f);
+          const float bar = fminf(fmaxf(1.0f - fabsf((static_cast<float>(x) - cx) - bar_off) / 1.6f, 0.0f), 1.0f) * bar_on;
+          float val = fmaxf(ring, bar);
+          if (val < 0.15f) val = 0.0f;
+          v[q] = val;
+          if (val > 0.0f && sC[(top + y) * cs + left + x] > 0.0f) clash = 1;
+        }
+      }
+      if (__syncthreads_or(clash)) continue;  // overlap rejection (uniform decision)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int p = tid + 256 * q;
+        if (p < hh * ww) {
+          const int y = p / ww, x = p - y * ww;
+          float *c = &sC[(top + y) * cs + left + x];
+          *c = fmaxf(*c, v[q]);
+        }
+      }
+      __syncthreads();
+      break;
+    }
+  }
+  __syncthreads();
+  for (int p = tid; p < cs * cs; p += 256) images[b * cs * cs + p] = sC[p];
+  if (tid == 0) counts[b] = count;
+}
+
 }  // namespace air
 
 // ---- C ABI --------------------------------------------------------------------------------
@@ -852,6 +925,18 @@ extern "C" int air_colsum_multi(const air_colsum_item_t *items, int n_items, flo
              static_cast<const float *>(workspace), outs);
   count_launch(2);
   return check_launch("colsum_multi");
+}
+
+extern "C" int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int64_t B,
+                                  int canvas_size, int max_digits, air_stream_t stream) {
+  AIR_REQUIRE(B >= 0 && canvas_size >= 24 && canvas_size <= 104 && max_digits >= 0 && first_index >= 0, AIR_ERR_BAD_SHAPE,
+              "synth_canvases: bad arguments (24 <= canvas_size <= 104)");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(images && counts, AIR_ERR_NULL, "synth_canvases: null pointer");
+  AIR_LAUNCH(synth_canvases_k, static_cast<unsigned>(B), 256, static_cast<size_t>(canvas_size) * canvas_size * 4, ST(stream), seed,
+             first_index, images, counts, canvas_size, max_digits);
+  count_launch();
+  return check_launch("synth_canvases");
 }
 
 extern "C" int air_reduce_rows(const float *partials, int R, int stride, int n, float *out, int accumulate, air_stream_t stream) {

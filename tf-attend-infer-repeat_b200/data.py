@@ -37,6 +37,17 @@ def synthetic_canvases(B, canvas_size=50, max_digits=2, seed=0, n_templates=256)
     return torch.from_numpy(imgs.reshape(B, -1)), torch.from_numpy(counts)
 
 
+def device_canvases(B, seed=0, first_index=0, canvas_size=50, max_digits=2, device="cuda", out=None):
+    """Multi-digit canvases generated ON the GPU (air_synth_canvases): -> (images [B, cs*cs] fp32, counts [B] int32).
+    Image ``first_index + b`` depends only on (seed, first_index + b): data-parallel ranks call this with their own
+    ``first_index`` and together hold one global, reproducible data set.  ``out=(images, counts)`` refills buffers
+    in place (e.g. AIRModel.input_images / target_num_digits) with no host round trip."""
+    from . import ops
+    if out is None:
+        out = (torch.empty(B, canvas_size * canvas_size, device=device), torch.empty(B, device=device, dtype=torch.int32))
+    return ops.synth_canvases(out[0], out[1], seed, first_index, canvas_size, max_digits)
+
+
 # training.py:100-122 -- the configuration the README / checkpoint call "default"
 TRAINING_HYPER = dict(
     max_steps=3, max_digits=2, rnn_units=256, canvas_size=50, windows_size=28,

@@ -189,3 +189,12 @@ def conv5x5_bwd(x, w, out, argmax, dout, din, dw, db, accumulate, workspace, H, 
                                 int(accumulate), ptr(workspace), x.shape[0], H, W, cin, cout, int(pool), stream()),
           "air_conv5x5_bwd")
 
+
+def synth_canvases(images, counts, seed=0, first_index=0, canvas_size=50, max_digits=2):
+    """Fill images [B, canvas_size**2] / counts [B] int32 with device-generated multi-digit canvases."""
+    if counts.dtype != torch.int32:
+        raise C.AirError("counts must be int32")
+    check(lib().air_synth_canvases(int(seed), int(first_index), ptr(images), ptr(counts), images.shape[0], canvas_size,
+                                   max_digits, stream()), "air_synth_canvases")
+    return images, counts
+
