@@ -53,9 +53,20 @@ flat = m.store.flat.clone()
 gathered = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 same = all(torch.equal(gathered[0], g) for g in gathered)
+# the CUDA-graph path (three graphs: the first gradient bucket's all-reduce overlaps the second graph)
+m.noise = None
+m.capture()
+for _ in range(3):
+    m.train_step()
+torch.cuda.synchronize()
+flat2 = m.store.flat.clone()
+gathered2 = [torch.empty_like(flat2) for _ in range(world)]
+dist.all_gather(gathered2, flat2)
+same_graph = all(torch.equal(gathered2[0], g) for g in gathered2) and bool(torch.isfinite(flat2).all()) and not torch.equal(flat2, flat)
 if rank == 0:
     print(f"[dp] replicas bit-identical after 3 steps: {same}; global_step={m.global_step}")
-    ok &= same
+    print(f"[dp] replicas bit-identical after 3 more CUDA-graph steps with the overlapped all-reduce: {same_graph}")
+    ok &= same and same_graph
     print("DP CHECK", "OK" if ok else "FAILED")
 dist.barrier()
 dist.destroy_process_group()

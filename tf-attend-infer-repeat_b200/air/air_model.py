@@ -189,11 +189,15 @@ class AIRModel:
         self.vw = VAEWeights(p, g, len(self.vae_recognition_units), len(self.vae_generative_units))
         if self.train:
             # every bias gradient of the step = column sums of a time-batched dY buffer: one launch pair for all
-            pairs = vae_bias_items(self.vw, w["vae_d"]) + [(_flat2(w["dhh"]), g["heads/hidden_b"], False),
-                                                            (w["dgates_sum"], g["rnn/bias"], False)]
-            self._colsum_items = ops.colsum_items(pairs)
-            self._colsum_keep = pairs  # the ctypes array holds raw pointers: keep the views alive
+            pairs = vae_bias_items(self.vw, w["vae_d"]) + [(_flat2(w["dhh"]), g["heads/hidden_b"], False)]
+            pairs_rnn = [(w["dgates_sum"], g["rnn/bias"], False)]
+            self._colsum_items, self._colsum_items_rnn = ops.colsum_items(pairs), ops.colsum_items(pairs_rnn)
+            self._colsum_keep = (pairs, pairs_rnn)  # the ctypes arrays hold raw pointers: keep the views alive
             w["colsum_ws"] = torch.zeros(ops.colsum_multi_workspace(self._colsum_items), device=dev)
+            w["colsum_ws_rnn"] = torch.zeros(ops.colsum_multi_workspace(self._colsum_items_rnn), device=dev)
+            # gradient buckets for the data-parallel all-reduce: A = [cnn,] rnn (70 % of the bytes, produced first),
+            # B = heads + vae.  The flat buffer is laid out in that order.
+            self._bucket_split = self.store.offsets["heads/hidden_w"]
 
     # ------------------------------------------------------------------------------------------
     def feed(self, input_images, target_num_digits=None):
@@ -296,6 +300,11 @@ class AIRModel:
     # backward: what TF autodiff derives for air_model.py:655 (gradients of the mean loss)
     # ------------------------------------------------------------------------------------------
     def _backward(self):
+        self._backward_loop()
+        self._weight_grads_rnn()
+        self._weight_grads_rest()
+
+    def _backward_loop(self):
         w, hp, mode = self.w, self.hyper, self.gemm
         B, T = self.batch_size, self.max_steps
         x = self.input_images
@@ -327,24 +336,32 @@ class AIRModel:
                 ops.gemm(w["dgates"][t], self.Kh, w["dh_next"], tB=True, mode=mode)
             if getattr(self, "_debug", None) is not None:  # per-step intermediate gradients for diagnostics
                 self._debug[t] = {k: w[k].clone() for k in ("dwin", "dtheta", "dtheta_inv", "dz", "dh")}
-        # ---- weight gradients, once per train step, over the time-batched buffers
-        HU = self.scale_hidden_units
-        nw = 7 * HU
-        ops.reduce_rows(w["heads_ws"], T * self._heads_rows, nw + 7, nw, g["heads/out_w"])
-        ops.reduce_rows(w["heads_ws"].view(-1)[nw:], T * self._heads_rows, nw + 7, 7, g["heads/out_b"])
-        allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
-        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, vd, None, mode)
-        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], None, mode)
+
+    # ---- weight gradients, once per train step, over the time-batched buffers.  The LSTM kernel (and the CNN
+    #      front-end) come first: they are 70 % of the gradient bytes and the first bucket of the data-parallel
+    #      all-reduce, which then overlaps the remaining weight-gradient GEMMs (train_step).
+    def _weight_grads_rnn(self):
+        w, mode, T = self.w, self.gemm, self.max_steps
         if T > 1:   # K_h sees h_{t-1}: rows t = 1..T-1 (h_{-1} = 0 contributes nothing)
             ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode)
         else:
             self.gKh.zero_()
         # the image rows of the LSTM kernel see the same input every step: one GEMM on the summed dgates
-        rnn_in = w["cnn_out"][2] if self.cnn else x
+        rnn_in = w["cnn_out"][2] if self.cnn else self.input_images
         ops.gemm(rnn_in, w["dgates_sum"], self.gKx, tA=True, mode=mode)
-        ops.colsum_multi(self._colsum_items, w["colsum_ws"])
+        ops.colsum_multi(self._colsum_items_rnn, w["colsum_ws_rnn"])
         if self.cnn:
             self._cnn_backward()
+
+    def _weight_grads_rest(self):
+        w, g, mode, T = self.w, self.store.g, self.gemm, self.max_steps
+        nw = 7 * self.scale_hidden_units
+        ops.reduce_rows(w["heads_ws"], T * self._heads_rows, nw + 7, nw, g["heads/out_w"])
+        ops.reduce_rows(w["heads_ws"].view(-1)[nw:], T * self._heads_rows, nw + 7, 7, g["heads/out_b"])
+        allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
+        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, w["vae_d"], None, mode)
+        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], None, mode)
+        ops.colsum_multi(self._colsum_items, w["colsum_ws"])
 
     def _apply_gradients(self):
         """air_model.py:673, 692: clip by global norm, Adam, global_step += 1."""
@@ -354,6 +371,20 @@ class AIRModel:
 
     def _allreduce(self):
         dp.allreduce_flat(self.store.grad, self.pg)  # SUM; the per-item loss weight already carries 1/world
+
+    def _reduce_overlapped(self, first, second):
+        """first(); all-reduce(bucket A) on the communicator's stream while second() runs; all-reduce(bucket B);
+        the current stream then waits for both.  With one rank: just first(); second()."""
+        first()
+        if self.world == 1:
+            second()
+            return
+        grad, k = self.store.grad, self._bucket_split
+        wa = dp.allreduce_async(grad[:k], self.pg)
+        second()
+        wb = dp.allreduce_async(grad[k:], self.pg)
+        wa.wait()
+        wb.wait()
 
     # ------------------------------------------------------------------------------------------
     # public API
@@ -375,8 +406,7 @@ class AIRModel:
         if not self.train:
             raise C.AirError("model was built with train=False")
         self.run(noise)
-        self._backward()
-        self._allreduce()
+        self._reduce_overlapped(lambda: (self._backward_loop(), self._weight_grads_rnn()), self._weight_grads_rest)
         return self.loss, self.store.named_grads()
 
     def train_step(self, noise=None):
@@ -384,9 +414,8 @@ class AIRModel:
         if not self.train:
             raise C.AirError("model was built with train=False")
         if self._graphs is not None and noise is None:
-            g_fb, g_opt = self._graphs
-            g_fb.replay()
-            self._allreduce()
+            g_a, g_b, g_opt = self._graphs
+            self._reduce_overlapped(g_a.replay, g_b.replay if g_b is not None else (lambda: None))
             g_opt.replay()
             return self
         self.loss_and_grads(noise)
@@ -394,8 +423,9 @@ class AIRModel:
         return self
 
     def capture(self, warmup=3):
-        """Capture noise + forward + backward, and clip + Adam, as two CUDA graphs (the NCCL
-        allreduce between them stays eager).  Subsequent train_step() calls replay them."""
+        """Capture noise + forward + backward, and clip + Adam, as CUDA graphs; subsequent train_step() calls replay
+        them.  With more than one rank the backward is split after the LSTM-kernel gradients so that the (eager)
+        NCCL all-reduce of that first bucket overlaps the remaining weight-gradient GEMMs."""
         assert self.train and self.noise != "injected"
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -404,12 +434,18 @@ class AIRModel:
                 self._draw_noise(); self._forward(); self._backward()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_fb):
-            self._draw_noise(); self._forward(); self._backward()
-        with torch.cuda.graph(g_opt):
+        g_a, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        g_b = torch.cuda.CUDAGraph() if self.world > 1 else None
+        with torch.cuda.graph(g_a):
+            self._draw_noise(); self._forward(); self._backward_loop(); self._weight_grads_rnn()
+            if g_b is None:
+                self._weight_grads_rest()
+        if g_b is not None:  # data parallel: the first gradient bucket is all-reduced while this graph runs
+            with torch.cuda.graph(g_b, pool=g_a.pool()):
+                self._weight_grads_rest()
+        with torch.cuda.graph(g_opt, pool=g_a.pool()):
             self._apply_gradients()
-        self._graphs = (g_fb, g_opt)
+        self._graphs = (g_a, g_b, g_opt)
         self._publish()
         return self
 

@@ -39,6 +39,13 @@ def allreduce_flat(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
     return flat_grad
 
 
+def allreduce_async(t: torch.Tensor, group=None):
+    """SUM all-reduce of a (contiguous slice of the) flat gradient buffer, asynchronous: the collective is ordered
+    after the work already queued on the current stream and runs on the communicator's own stream; ``.wait()`` makes
+    the current stream (not the host) wait for it."""
+    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
 def allreduce_scalars(values: torch.Tensor, group=None) -> torch.Tensor:
     """Mean of per-rank scalars (logged loss / accuracy)."""
     w = world_size(group)
