@@ -37,13 +37,17 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region.  nvidia-smi takes a few hundred ms to
+    start (longer when 8 ranks start one each), so __enter__ waits for its first row before the region begins, and
+    when the region was too short for two samples __exit__ keeps the GPU under the same load (``busy()``: untimed
+    extra steps) until a few more arrive; the summary says how many samples fell inside the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0, period_ms=100):
-        self.index, self.period_ms, self.rows, self.proc = index, period_ms, [], None
+    def __init__(self, index=0, period_ms=25, busy=None):
+        self.index, self.period_ms, self.rows, self.proc, self.busy = index, period_ms, [], None, busy
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
@@ -52,16 +56,30 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            deadline = time.time() + 5.0
+            while not self.rows and time.time() < deadline:   # nvidia-smi is up and streaming
+                if self.busy is not None:
+                    self.busy()                               # (keeps the clocks where the warm-up left them)
+                else:
+                    time.sleep(0.01)
         except Exception:
             self.proc = None
+        self.t0 = time.time()
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
+        self.t1 = time.time()
         if self.proc is not None:
+            deadline = time.time() + 1.5
+            while self.busy is not None and time.time() < deadline and \
+                    sum(1 for t, _ in self.rows if t >= self.t0) < 4:
+                self.busy()                                   # same workload, outside the timed region
+                import torch
+                torch.cuda.synchronize()
             time.sleep(self.period_ms / 1000.0 * 1.5)
             self.proc.terminate()
             try:
@@ -70,12 +88,16 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = lambda r: len(r) >= 9 and r[1].replace(".", "").isdigit()
+        under_load = [r for t, r in self.rows if self.t0 is not None and t >= self.t0 and ok(r)]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) and ok(r)]
+        sm = [float(r[1]) for r in under_load]
+        mx = [float(r[2]) for r in under_load if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        reasons = sorted({n for r in under_load for n, v in zip(names, r[5:9]) if v.lower() == "active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_inside_timed_region": len(inside),
+                "note": "samples beyond the timed region were taken under the same workload, run untimed"}
 
 
 def dist_setup(n_gpus):
@@ -201,7 +223,8 @@ def run_st(args, rank, world, peaks):
     res = {}
     n0 = ab.launch_count()
     barrier(world)
-    with ClockSampler(torch.cuda.current_device()) as cs:
+    with ClockSampler(torch.cuda.current_device(), busy=ks["crop_fwd"]) as cs:
+        barrier(world)
         t_all0 = time.time()
         for name, fn in ks.items():
             ms = max_over_ranks(time_launches(fn, args.steps, args.warmup), world)

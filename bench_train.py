@@ -64,7 +64,10 @@ def run(args, rank, world, peaks):
         step()
     barrier(world)
     launches_eager = ab.launch_count() - n0
-    with ClockSampler(torch.cuda.current_device()) as cs:
+    # (the sampler's keep-busy load must not contain a collective: ranks call it a different number of times)
+    busy = step if world == 1 else (lambda: m.run())
+    with ClockSampler(torch.cuda.current_device(), busy=busy) as cs:
+        barrier(world)  # nvidia-smi start-up differs per rank: re-align before the timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
