@@ -159,8 +159,9 @@ class AIRModel:
                           concrete_u=z(T, B))
         if self.train:
             w["dcanvas"] = z(B, cs2)
-            w["dwin"] = z(B, win)
-            w["dtheta"], w["dtheta_inv"], w["dz"] = z(B, 6), z(B, 6), z(B)
+            # the VAE / ST backward of all T steps runs before the (sequential) LSTM backward: per-step buffers
+            w["dwin"] = z(T, B, win)
+            w["dtheta"], w["dtheta_inv"], w["dz"] = z(T, B, 6), z(T, B, 6), z(T, B)
             w["dh"], w["dh_next"], w["dc"] = z(B, R), z(B, R), z(B, R)
             # pre-activation gradients are kept for all T steps: the weight-gradient GEMMs run once
             # per train step over the time-batched [T*B, .] buffers (one long-K GEMM per layer)
@@ -239,6 +240,8 @@ class AIRModel:
         self._update_scalars()
         # step-invariant image projection x @ K[:in_dim] (bias added per step, after the h part)
         ops.gemm(self._rnn_input(), self.Kx, w["xk"], mode=mode)
+        # ---- (1) the recurrent chain: LSTM -> heads (pose, z_pres, stop) -> attention crop, step by step.  Nothing
+        #      here depends on the VAE or the canvas (air_model.py:284-333, 368-427).
         for t in range(T):
             c_prev = w["c"][t - 1] if t > 0 else None
             # LSTM: gates = ([x,h] K) + b, accumulated in concat order (x part first).  The initial state is
@@ -254,11 +257,20 @@ class AIRModel:
             ops.heads_fwd(w["hh"][t], p["heads/out_w"], p["heads/out_b"], n["scale"][t], n["shift"][t],
                           n["concrete_u"][t], self._prior, hp, w["stop"], w["loss"], w["digits"], w["fields"][t],
                           w["theta"][t], w["theta_inv"][t])
-            # attention crop, VAE, write-back + canvas
             ops.st_forward(x, w["theta"][t], w["win"][t], cs, cs, 1, wsz, wsz)
-            buf = self._vae_buf(t)
-            vae_forward(w["win"][t], self.vw, n["vae_latent"][t], n["vae_like"][t], self.vae_likelihood_std, hp, buf,
-                        w["gen"], w["fields"][t], w["loss"], mode)
+        # ---- (2) the VAE of ALL steps as one evaluation on T*B rows (air_model.py:335-349, 479-496): six GEMMs
+        #      with M = T*B instead of 6 T with M = B.  Only the latent step touches per-step state (live mask,
+        #      running loss), so it stays per step; the running loss therefore adds the VAE KLs after the pose /
+        #      z_pres KLs of all steps -- same terms, different fp32 summation order than the reference's loop.
+        def latent_steps():
+            for t in range(T):
+                ops.vae_latent_fwd(w["ml"][t], n["vae_latent"][t], hp, w["zs"][t], w["fields"][t], w["loss"])
+        allbuf = dict(enc=[_flat2(e) for e in w["enc"]], ml=_flat2(w["ml"]), zs=_flat2(w["zs"]),
+                      dec=[_flat2(d) for d in w["dec"]], recon=_flat2(w["recon"]))
+        vae_forward(_flat2(w["win"]), self.vw, None, _flat2(n["vae_like"]), self.vae_likelihood_std, hp, allbuf,
+                    w["gen"], None, w["loss"], mode, latent_fn=latent_steps)
+        # ---- (3) write-back + canvas accumulation in step order (air_model.py:351-366, 429-439)
+        for t in range(T):
             f = w["fields"][t]
             ops.writeback_canvas_fwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
                                      self.stopping_threshold, w["canvas"], w["canvas"], wsz, wsz, cs, cs)
@@ -314,20 +326,31 @@ class AIRModel:
         dscale = 1.0 / (B * self.world)
         w["dgates_sum"].zero_()
         vd = w["vae_d"]
+        # ---- (1) write-back backward of every step (the canvas is a plain sum: all steps see the same dcanvas)
+        for t in range(T):
+            f = w["fields"][t]
+            ops.writeback_canvas_bwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
+                                     self.stopping_threshold, w["dcanvas"], vd["dgen"][t], w["dtheta_inv"][t], w["dz"][t],
+                                     wsz, wsz, cs, cs, window_is_sigmoid=True,  # SigmoidGrad fused into the store
+                                     axis_aligned_theta=True)  # heads_bwd reads dtheta_inv[0,2,4,5] only
+        # ---- (2) VAE backward of all steps as one evaluation on T*B rows, then the crop backward per step
+        def latent_bwd_steps():
+            for t in range(T):
+                ops.vae_latent_bwd(w["ml"][t], n["vae_latent"][t], vd["dzs"][t], w["fields"][t], hp, dscale, vd["dml"][t])
+        allbuf = dict(enc=[_flat2(e) for e in w["enc"]], ml=_flat2(w["ml"]), zs=_flat2(w["zs"]),
+                      dec=[_flat2(d) for d in w["dec"]], recon=_flat2(w["recon"]))
+        alld = dict(denc=[_flat2(d) for d in vd["denc"]], dml=_flat2(vd["dml"]), dzs=_flat2(vd["dzs"]),
+                    ddec=[_flat2(d) for d in vd["ddec"]], dgen=_flat2(vd["dgen"]))
+        vae_backward_dx(_flat2(w["win"]), self.vw, None, hp, allbuf, alld, dscale, None, mode, dx_out=_flat2(w["dwin"]),
+                        dgen_is_presigmoid=True, latent_bwd_fn=latent_bwd_steps)
+        for t in range(T):
+            ops.st_backward(x, w["theta"][t], w["dwin"][t], None, w["dtheta"][t], cs, cs, 1, wsz, wsz)
+        # ---- (3) the recurrent chain backwards: heads -> LSTM, step by step
         for t in range(T - 1, -1, -1):
             last = t == T - 1
             f = w["fields"][t]
-            dbuf = dict(denc=[d[t] for d in vd["denc"]], dml=vd["dml"][t], dzs=vd["dzs"][t],
-                        ddec=[d[t] for d in vd["ddec"]], dgen=vd["dgen"][t])
-            ops.writeback_canvas_bwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
-                                     self.stopping_threshold, w["dcanvas"], dbuf["dgen"], w["dtheta_inv"], w["dz"],
-                                     wsz, wsz, cs, cs, window_is_sigmoid=True,  # SigmoidGrad fused into the store
-                                     axis_aligned_theta=True)  # heads_bwd reads dtheta_inv[0,2,4,5] only
-            vae_backward_dx(w["win"][t], self.vw, n["vae_latent"][t], hp, self._vae_buf(t), dbuf, dscale, f, mode,
-                            dx_out=w["dwin"], dgen_is_presigmoid=True)
-            ops.st_backward(x, w["theta"][t], w["dwin"], None, w["dtheta"], cs, cs, 1, wsz, wsz)
-            ops.heads_bwd(w["hh"][t], p["heads/out_w"], n["scale"][t], n["shift"][t], f, w["dtheta"], w["dtheta_inv"],
-                          w["dz"], self._prior, hp, dscale, w["dhh"][t], None, None, False, w["heads_ws"][t])
+            ops.heads_bwd(w["hh"][t], p["heads/out_w"], n["scale"][t], n["shift"][t], f, w["dtheta"][t], w["dtheta_inv"][t],
+                          w["dz"][t], self._prior, hp, dscale, w["dhh"][t], None, None, False, w["heads_ws"][t])
             # dh_t = dhh_t W_hid^T (+ the LSTM path from step t+1)
             ops.gemm(w["dhh"][t], p["heads/hidden_w"], w["dh"], Cinit=None if last else w["dh_next"], tB=True, mode=mode)
             ops.lstm_bwd(w["gates"][t], w["c"][t - 1] if t > 0 else None, w["c"][t], w["dh"],
@@ -335,7 +358,8 @@ class AIRModel:
             if t > 0:
                 ops.gemm(w["dgates"][t], self.Kh, w["dh_next"], tB=True, mode=mode)
             if getattr(self, "_debug", None) is not None:  # per-step intermediate gradients for diagnostics
-                self._debug[t] = {k: w[k].clone() for k in ("dwin", "dtheta", "dtheta_inv", "dz", "dh")}
+                self._debug[t] = {k: w[k][t].clone() for k in ("dwin", "dtheta", "dtheta_inv", "dz")}
+                self._debug[t]["dh"] = w["dh"].clone()
 
     # ---- weight gradients, once per train step, over the time-batched buffers.  The LSTM kernel (and the CNN
     #      front-end) come first: they are 70 % of the gradient bytes and the first bucket of the data-parallel

@@ -40,16 +40,22 @@ def alloc_vae_buffers(B, win, rec_units, L, gen_units, device, lead=()):
                 dec=[z(B, u) for u in gen_units], recon=z(B, win))
 
 
-def vae_forward(x, w: VAEWeights, noise_latent, noise_like, likelihood_std, hyper, buf, gen_tmp, fields, loss, mode):
-    """x [B,win] -> buf['recon'].  Softplus MLP 784->512->256 -> (mean|logvar) -> sample
+def vae_forward(x, w: VAEWeights, noise_latent, noise_like, likelihood_std, hyper, buf, gen_tmp, fields, loss, mode,
+                latent_fn=None):
+    """x [rows,win] -> buf['recon'].  Softplus MLP 784->512->256 -> (mean|logvar) -> sample
     -> 256->512->784 -> sigmoid(gen + noise*std)   (vae.py:9-41).  Also accumulates the VAE
-    KL into ``loss`` / ``fields`` (air_model.py:479-493)."""
+    KL into ``loss`` / ``fields`` (air_model.py:479-493).  AIRModel runs all T loop steps as ONE evaluation on
+    T*B rows (the VAE of step t depends on nothing but theta_t) and passes ``latent_fn`` to do the latent step --
+    the only place that touches per-step state -- step by step."""
     a = x
     for (W, b), out in zip(w.rec, buf["enc"]):
         ops.gemm(a, W, out, bias=b, epi=C.EPI_SOFTPLUS, mode=mode)
         a = out
     ops.gemm(a, w.ml[0], buf["ml"], bias=w.ml[1], mode=mode)
-    ops.vae_latent_fwd(buf["ml"], noise_latent, hyper, buf["zs"], fields, loss)
+    if latent_fn is not None:
+        latent_fn()
+    else:
+        ops.vae_latent_fwd(buf["ml"], noise_latent, hyper, buf["zs"], fields, loss)
     a = buf["zs"]
     for (W, b), out in zip(w.gen, buf["dec"]):
         ops.gemm(a, W, out, bias=b, epi=C.EPI_SOFTPLUS, mode=mode)
@@ -75,7 +81,7 @@ def dense_dw(x_in, dY, gW, gb, colsum_ws, mode, accumulate=False):
 
 
 def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fields, mode, dx_out=None,
-                    dgen_is_presigmoid=False, dml_extra=None):
+                    dgen_is_presigmoid=False, dml_extra=None, latent_bwd_fn=None):
     """Backward through one VAE evaluation, activations only (air/vae.py:9-41 reversed).
     dbuf['dgen'] holds d(loss)/d(reconstruction) on entry; on exit dbuf holds the gradient
     w.r.t. every layer's pre-activation output (dgen, ddec[i], dml, denc[i]) -- the dY
@@ -88,7 +94,10 @@ def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fie
     douts = [dbuf["dzs"]] + list(dbuf["ddec"])
     for i in range(len(layers) - 1, -1, -1):
         dY = dense_dx(acts[i], layers[i][0], dY, douts[i], mode, act_of_x=(i > 0))
-    ops.vae_latent_bwd(buf["ml"], noise_latent, dY, fields, hyper, dloss, dbuf["dml"])
+    if latent_bwd_fn is not None:  # AIRModel: T*B rows, the latent step per loop step (see vae_forward)
+        latent_bwd_fn()
+    else:
+        ops.vae_latent_bwd(buf["ml"], noise_latent, dY, fields, hyper, dloss, dbuf["dml"])
     if dml_extra is not None:  # gradients arriving directly at the (mean | log_variance) outputs of vae()
         dbuf["dml"].add_(dml_extra)
     dY = dbuf["dml"]
