@@ -62,7 +62,8 @@ int air_st_backward(const float *U, const float *theta, const float *dout, float
 /* ---- fused write-back + canvas: air_model.py:363-366 and :429-439 ------------------
  * canvas_out[b] = canvas_in[b] + (stop_new[b] < thr ? z[b] * ST(window[b], theta_inv[b]) : 0)
  * window [B,wh,ww] (C == 1), theta_inv [B,6], z [B], stop_new [B], canvas [B,ch,cw].
- * canvas_out may alias canvas_in (in place).  Bit-exact vs the oracle. */
+ * canvas_out may alias canvas_in (in place).  canvas_in == NULL stands for an all-zero canvas (the first loop
+ * step, air_model.py:552: no memset, no read).  Bit-exact vs the oracle. */
 int air_st_writeback_canvas_fwd(const float *window, const float *theta_inv, const float *z, const float *stop_new,
                                 float thr, const float *canvas_in, float *canvas_out, int64_t B, int wh, int ww,
                                 int ch, int cw, air_stream_t stream);

@@ -415,6 +415,14 @@ def test_full_size_properties_fused_and_backward_b65536():
     c.check(L.air_st_writeback_canvas_fwd(c.ptr(win), c.ptr(thi), c.ptr(z), c.ptr(stop), 0.99, c.ptr(inpl), c.ptr(inpl),
                                           B, 28, 28, 50, 50, c.stream()), "fwd inplace")
     assert torch.equal(inpl, out)
+    # (1b) canvas_in == NULL stands for an all-zero canvas (first loop step), bit for bit
+    zero_out, null_out = torch.empty_like(canvas), torch.empty_like(canvas)
+    zc = torch.zeros_like(canvas)
+    c.check(L.air_st_writeback_canvas_fwd(c.ptr(win), c.ptr(thi), c.ptr(z), c.ptr(stop), 0.99, c.ptr(zc), c.ptr(zero_out),
+                                          B, 28, 28, 50, 50, c.stream()), "fwd zero canvas")
+    c.check(L.air_st_writeback_canvas_fwd(c.ptr(win), c.ptr(thi), c.ptr(z), c.ptr(stop), 0.99, None, c.ptr(null_out),
+                                          B, 28, 28, 50, 50, c.stream()), "fwd null canvas")
+    assert torch.equal(zero_out, null_out)
     # (2) stopped rows are untouched; live rows equal canvas + z * ST(window) computed by the plain ST kernel
     dead = stop >= 0.99
     assert torch.equal(out[dead], canvas[dead])

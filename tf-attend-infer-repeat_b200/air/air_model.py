@@ -155,8 +155,17 @@ class AIRModel:
         w["digits"] = torch.zeros(B, device=dev, dtype=torch.int32)
         w["canvas"], w["reconstruction"] = z(B, cs2), z(B, cs2)
         w["out2"] = torch.zeros(2, device=dev)
-        w["noise"] = dict(scale=z(T, B, 1), shift=z(T, B, 2), vae_latent=z(T, B, L), vae_like=z(T, B, win),
-                          concrete_u=z(T, B))
+        # the four Gaussian noise tensors are views of one buffer: one normal_ launch per step (sizes padded to
+        # 16 bytes so that every view stays aligned for the vectorised consumers)
+        sizes = dict(scale=T * B, shift=T * B * 2, vae_latent=T * B * L, vae_like=T * B * win)
+        offs, tot = {}, 0
+        for k, nelem in sizes.items():
+            offs[k] = tot
+            tot += (nelem + 3) & ~3
+        w["noise_flat"] = z(tot)
+        nv = lambda k, *shape: w["noise_flat"][offs[k]:offs[k] + sizes[k]].view(*shape)
+        w["noise"] = dict(scale=nv("scale", T, B, 1), shift=nv("shift", T, B, 2), vae_latent=nv("vae_latent", T, B, L),
+                          vae_like=nv("vae_like", T, B, win), concrete_u=z(T, B))
         if self.train:
             w["dcanvas"] = z(B, cs2)
             # the VAE / ST backward of all T steps runs before the (sequential) LSTM backward: per-step buffers
@@ -214,10 +223,8 @@ class AIRModel:
         self.noise = "injected"
 
     def _draw_noise(self):
-        n = self.w["noise"]
-        for k in ("scale", "shift", "vae_latent", "vae_like"):
-            n[k].normal_()
-        n["concrete_u"].uniform_()
+        self.w["noise_flat"].normal_()
+        self.w["noise"]["concrete_u"].uniform_()
 
     def _update_scalars(self):
         st = self.store.state
@@ -236,7 +243,7 @@ class AIRModel:
         p = self.store.p
         cs, wsz = self.canvas_size, self.windows_size
         n = w["noise"]
-        w["stop"].zero_(); w["loss"].zero_(); w["digits"].zero_(); w["canvas"].zero_()
+        w["stop"].zero_(); w["loss"].zero_(); w["digits"].zero_()  # (the canvas starts at zero: first write-back)
         self._update_scalars()
         # step-invariant image projection x @ K[:in_dim] (bias added per step, after the h part)
         ops.gemm(self._rnn_input(), self.Kx, w["xk"], mode=mode)
@@ -273,7 +280,7 @@ class AIRModel:
         for t in range(T):
             f = w["fields"][t]
             ops.writeback_canvas_fwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
-                                     self.stopping_threshold, w["canvas"], w["canvas"], wsz, wsz, cs, cs)
+                                     self.stopping_threshold, w["canvas"] if t > 0 else None, w["canvas"], wsz, wsz, cs, cs)
         dscale = 1.0 / (B * self.world)
         # the clipped reconstruction is only an output: written in inference, derived lazily in training
         ops.bce_loss(w["canvas"], x, None if self.train else w["reconstruction"], w["rec_loss"],

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kFwdThreads)
       const int64_t o = (g0 + i) * OHW + p0 + 4 * lane;
       const bool mine = p0 + 4 * lane < OHW;
       float4 cin = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mine) cin = *reinterpret_cast<const float4 *>(canvas_in + o);
+      if (mine && canvas_in) cin = *reinterpret_cast<const float4 *>(canvas_in + o);  // NULL: an all-zero canvas
       if (live) {
         const float zz = __ldg(zp + g0 + i);
 #pragma unroll
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kFwdThreads)
     }
     if (CANVAS) {
       const float add = live ? mul_rn(__ldg(zp + g0 + i), v) : 0.0f;
-      out[o] = add_rn(canvas_in[o], add);
+      out[o] = add_rn(canvas_in ? canvas_in[o] : 0.0f, add);
     } else {
       out[o] = v;
     }
@@ -1057,7 +1057,7 @@ static int st_forward_impl(const float *U, const float *theta, float *out, const
     const bool g2 = g_env ? g_env == 2 : B < static_cast<int64_t>(sm_count()) * 64;
     if (canvas) {
       if (H == 28 && W == 28 && OH == 50 && OW == 50) {
-        if (aligned16(canvas_in) && aligned16(out)) {
+        if ((!canvas_in || aligned16(canvas_in)) && aligned16(out)) {
           if (g2) return launch_fwd_staged<28, 28, 50, 50, 2, true, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
           return launch_fwd_staged<28, 28, 50, 50, 4, true, true>(U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW, s);
         }
@@ -1183,7 +1183,7 @@ extern "C" int air_st_writeback_canvas_fwd(const float *window, const float *the
                                            const float *stop_new, float thr, const float *canvas_in,
                                            float *canvas_out, int64_t B, int wh, int ww, int ch, int cw,
                                            air_stream_t stream) {
-  AIR_REQUIRE(B <= 0 || (z && stop_new && canvas_in && canvas_out), AIR_ERR_NULL,
+  AIR_REQUIRE(B <= 0 || (z && stop_new && canvas_out), AIR_ERR_NULL,
               "st_writeback_canvas_fwd: null pointer");
   return air::st_forward_impl(window, theta_inv, canvas_out, z, stop_new, thr, canvas_in, true, B, wh, ww, 1, ch, cw,
                               static_cast<cudaStream_t>(stream));
