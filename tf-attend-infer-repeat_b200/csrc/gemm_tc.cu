@@ -39,6 +39,24 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// same load, delivered to the same shared-memory offsets (tile and mbarrier) of every CTA of the cluster in cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -66,6 +84,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 // arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// the same arrival, on the mbarrier at this offset in every CTA of cta_mask (frees a stage that both CTAs fill)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t *r) {
@@ -113,7 +138,11 @@ struct TcParams {
   int mma_repeat;  // diagnostics only (AIR_TC_MMA_REPEAT): re-issue each k-block's MMAs (results are then wrong)
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// CL: launched as clusters of two CTAs that are neighbours along M (same N tile).  They need the same B tile:
+// each loads half of it and multicasts it to both, which halves the L2 -> SM traffic of that operand (the kernel
+// is L2 -> SM bandwidth bound with fp32 operands, profiles/r1_gemm_tf32_big_ncu_full.md).  A stage is refilled only
+// after BOTH CTAs' MMAs have read it: the empty barriers count two arrivals, one multicast commit from each CTA.
+template <int BN, bool A_MN, bool B_MN, bool CL>
 __global__ void __launch_bounds__(kTcThreads)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
   constexpr uint32_t kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
@@ -138,7 +167,7 @@ __global__ void __launch_bounds__(kTcThreads)
     prefetch_tmap(&mapB);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL ? 2 : 1);
     }
     mbar_init(&tmem_full_bar, 1);
     fence_mbar_init();
@@ -148,6 +177,8 @@ __global__ void __launch_bounds__(kTcThreads)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t crank = CL ? cluster_ctarank() : 0;
+  if (CL) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   pdl_sync();  // PDL: barriers, TMEM and descriptors were set up while the previous grid drained
 
   // ================= TMA producers =================
@@ -170,13 +201,19 @@ __global__ void __launch_bounds__(kTcThreads)
         } else {      // box {32 m, 32 k}: 32-wide chunk pi
           tma_load_2d(sa + pi * (kBK * 128), &mapA, &full_bar[s], m0 + pi * 32, k0);
         }
+        unsigned char *bdst;
+        int bc0, bc1;
         if (!B_MN) {  // box {32 k, BN/4 n}
-          tma_load_2d(sb + pi * (BN / 4 * 128), &mapB, &full_bar[s], k0, n0 + pi * (BN / 4));
+          bdst = sb + pi * (BN / 4 * 128); bc0 = k0; bc1 = n0 + pi * (BN / 4);
         } else if (BN == 128) {  // box {32 n, 32 k}: chunk pi
-          tma_load_2d(sb + pi * (kBK * 128), &mapB, &full_bar[s], n0 + pi * 32, k0);
+          bdst = sb + pi * (kBK * 128); bc0 = n0 + pi * 32; bc1 = k0;
         } else {      // BN == 64: box {32 n, 16 k}: chunk pi/2, k-half pi%2
-          tma_load_2d(sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128), &mapB, &full_bar[s], n0 + (pi >> 1) * 32,
-                      k0 + (pi & 1) * 16);
+          bdst = sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128); bc0 = n0 + (pi >> 1) * 32; bc1 = k0 + (pi & 1) * 16;
+        }
+        if (!CL) {
+          tma_load_2d(bdst, &mapB, &full_bar[s], bc0, bc1);
+        } else if (static_cast<uint32_t>(pi >> 1) == crank) {  // this CTA's half of the shared B tile, to both CTAs
+          tma_load_2d_mc(bdst, &mapB, &full_bar[s], bc0, bc1, static_cast<uint16_t>(3));
         }
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
@@ -208,7 +245,8 @@ __global__ void __launch_bounds__(kTcThreads)
             umma_tf32(tmem_acc, da, db, idesc, (i | k | rep) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        if (CL) umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(3));
+        else umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
       umma_commit(&tmem_full_bar);  // accumulator complete
@@ -290,6 +328,7 @@ __global__ void __launch_bounds__(kTcThreads)
     tc_fence_after();
     tmem_dealloc(tmem_acc, kTmemCols);
   }
+  if (CL) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
 }
 
 // second pass of split-K: C = epi((Cinit + sum_s partial[s]) + bias), s in increasing order.
@@ -401,9 +440,29 @@ static float *splitk_workspace(size_t bytes) {
   return g_ws[dev];
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, dim3 cluster,
+                                      Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster.x;
+  attr[0].val.clusterDim.y = cluster.y;
+  attr[0].val.clusterDim.z = cluster.z;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+template <int BN, bool A_MN, bool B_MN, bool CL>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, cudaStream_t s) {
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL>;
   const size_t stage_bytes = static_cast<size_t>(kBM + BN) * kBK * 4;
   // The mainloop of one CTA is TMA-latency bound (~0.7 us per k-block with 3 stages), so keep as many
   // bytes in flight per SM as shared memory allows: a deep ring when the grid gives each SM one CTA,
@@ -427,7 +486,12 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, c
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, p.splits);
-  AIR_LAUNCH(kern, grid, kTcThreads, smem, s, ma, mb, p);
+  if (CL) {
+    cudaError_t e = launch_cluster_pdl(kern, grid, dim3(kTcThreads), smem, s, dim3(1, 2, 1), ma, mb, p);
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "gemm_tf32 cluster launch: %s", cudaGetErrorString(e));
+  } else {
+    AIR_LAUNCH(kern, grid, kTcThreads, smem, s, ma, mb, p);
+  }
   count_launch();
   return check_launch("gemm_tf32");
 }
@@ -492,10 +556,17 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   else       rc = make_tmap(&mb, B, N, K, ldb, 32, BN == 128 ? kBK : 16, true);  // [K,N] N contiguous: box {32 n, 32|16 k}
   if (rc) return rc;
 
-#define AIR_TC_DISPATCH(BNv)                                                         \
-  (a_mn ? (b_mn ? launch_tc<BNv, true, true>(ma, mb, p, s) : launch_tc<BNv, true, false>(ma, mb, p, s)) \
-        : (b_mn ? launch_tc<BNv, false, true>(ma, mb, p, s) : launch_tc<BNv, false, false>(ma, mb, p, s)))
-  rc = (BN == 128) ? AIR_TC_DISPATCH(128) : AIR_TC_DISPATCH(64);
+  // Pairs of M-neighbour CTAs share their B tile through TMA multicast when the M-tile count is even and the
+  // mainloop is long: measured (profiles/r1_gemm_cluster_multicast.md) +6.5 % / +9 % on the two biggest GEMMs
+  // (K = 2500, 4096), neutral at ~77 k-blocks per CTA, and 3-5 % slower on the short-K GEMMs, where the two
+  // cluster barriers and the gang launch cost more than the operand traffic saves.  AIR_TC_CLUSTER=0/2 forces off/on.
+  static const int cl_env = [] { const char *e = getenv("AIR_TC_CLUSTER"); return e ? atoi(e) : 1; }();
+  const bool cl = cl_env != 0 && (mt % 2 == 0) && (cl_env == 2 || p.kb_per_split >= 64);
+#define AIR_TC_DISPATCH(BNv, CLv)                                                                                \
+  (a_mn ? (b_mn ? launch_tc<BNv, true, true, CLv>(ma, mb, p, s) : launch_tc<BNv, true, false, CLv>(ma, mb, p, s)) \
+        : (b_mn ? launch_tc<BNv, false, true, CLv>(ma, mb, p, s) : launch_tc<BNv, false, false, CLv>(ma, mb, p, s)))
+  if (cl) rc = (BN == 128) ? AIR_TC_DISPATCH(128, true) : AIR_TC_DISPATCH(64, true);
+  else rc = (BN == 128) ? AIR_TC_DISPATCH(128, false) : AIR_TC_DISPATCH(64, false);
 #undef AIR_TC_DISPATCH
   if (rc) return rc;
   if (splits > 1) {
