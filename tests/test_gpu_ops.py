@@ -305,6 +305,15 @@ def test_gemm_tf32_exact_on_integers(M, N, Kd, tA, tB):
     assert np.array_equal(got, want.astype(np.float32)), np.abs(got - want).max()
 
 
+@pytest.mark.parametrize("tA,tB", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,Kd", [(4096, 640, 2112), (2500, 1024, 2500)])
+def test_gemm_tf32_cluster_multicast_exact_on_integers(M, N, Kd, tA, tB):
+    """>= 64 k-blocks per CTA, even M-tile count, >= 148 tiles (no split-K): the 2-CTA cluster path, in which each CTA
+    loads half of the shared B tile and TMA-multicasts it to both.  Ragged M (2500 = 19.5 tiles) and ragged K included."""
+    got, want = _tf32_case(M, N, Kd, tA, tB, seed=M + N + Kd, use_cinit=True, use_bias=True)
+    assert np.array_equal(got, want.astype(np.float32)), np.abs(got - want).max()
+
+
 def test_gemm_tf32_epilogue_cinit_bias_and_splitk():
     for (M, N, Kd, tA, tB) in ((784, 512, 4096, True, False), (4096, 512, 784, False, False), (256, 1024, 4096, True, False)):
         got, want = _tf32_case(M, N, Kd, tA, tB, seed=1, use_cinit=True, use_bias=True, epi=K.EPI_RELU)
