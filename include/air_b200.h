@@ -68,6 +68,15 @@ int air_st_writeback_canvas_fwd(const float *window, const float *theta_inv, con
                                 float thr, const float *canvas_in, float *canvas_out, int64_t B, int wh, int ww,
                                 int ch, int cw, air_stream_t stream);
 
+/* All T write-backs of the loop in one pass over the canvas:
+ *   canvas_out = (((canvas_in + a_0) + a_1) + ...) + a_{T-1},  a_t = stop_new_t < thr ? z_t * ST(window_t, theta_inv_t) : +0
+ * windows [T,B,wh,ww], theta_inv [T,B,6]; z / stop_new point at step 0 and consecutive steps are step_stride floats
+ * apart (rows of the per-step field table).  Bit-identical to T consecutive air_st_writeback_canvas_fwd calls (which is
+ * also the fallback for other sizes); canvas_in may be NULL (zeros) or alias canvas_out. */
+int air_st_writeback_canvas_fwd_steps(const float *windows, const float *theta_inv, const float *z, const float *stop_new,
+                                      int64_t step_stride, float thr, const float *canvas_in, float *canvas_out, int64_t B,
+                                      int T, int wh, int ww, int ch, int cw, air_stream_t stream);
+
 /* Backward: dcanvas [B,ch,cw] is d(loss)/d(canvas_out) (== d/d(canvas_in), not rewritten).
  * Writes dwindow [B,wh,ww], dtheta_inv [B,6], dz [B]; all zero for rows with stop_new >= thr.
  * flags (bit mask):

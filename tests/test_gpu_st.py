@@ -10,6 +10,7 @@ import pytest
 import torch
 
 import air_b200 as ab
+from air_b200 import ops
 from oracle import air_oracle as O
 from oracle import c_oracle as C
 
@@ -317,6 +318,35 @@ def test_fused_canvas_backward_axis_aligned_kernel(sig):
     assert relnorm(dt_staged[:, [1, 3]], want_t[:, [1, 3]]) < 1e-4
     dead = stop >= 0.99
     assert not res[1][0][dead].any() and not res[1][1][dead].any() and not res[1][2][dead].any()
+
+
+@pytest.mark.parametrize("T,B,with_canvas", [(1, 7, True), (3, 33, False), (3, 64, True), (5, 10, False), (30, 3, True)])
+def test_writeback_steps_bit_identical_to_sequential(T, B, with_canvas):
+    """air_st_writeback_canvas_fwd_steps == T consecutive single-step write-backs, bit for bit (T = 30 exceeds the
+    shared-memory budget of the fused kernel and takes the documented fallback)."""
+    rng = np.random.RandomState(70 + T + B)
+    NF = 20
+    win = cu(rng.rand(T, B, 784).astype(np.float32))
+    thi = np.zeros((T, B, 6), np.float32)
+    for t in range(T):
+        thi[t] = air_thetas(rng, B)[1].reshape(B, 6)
+    thi[0, 0] = [1.2, 0.3, 0.1, -0.2, 1.1, 0.0]                       # one sheared row: per-pixel path
+    thi = cu(thi)
+    fields = torch.zeros(T, NF, B, device=DEV)
+    fields[:, 9] = cu(rng.rand(T, B).astype(np.float32))              # z
+    fields[:, 15] = cu(rng.choice(np.array([0.0, 0.5, 1.3], np.float32), (T, B)))   # stop_new
+    canvas0 = cu(rng.rand(B, 2500).astype(np.float32)) if with_canvas else None
+    seq = canvas0.clone() if with_canvas else torch.empty(B, 2500, device=DEV)
+    for t in range(T):
+        ops.writeback_canvas_fwd(win[t], thi[t], fields[t, 9], fields[t, 15], 0.99,
+                                 seq if (t > 0 or with_canvas) else None, seq, 28, 28, 50, 50)
+    fused = torch.full((B, 2500), 7.0, device=DEV)
+    ops.writeback_canvas_fwd_steps(win, thi, fields[0, 9], fields[0, 15], NF * B, 0.99, canvas0, fused, 28, 28, 50, 50)
+    assert torch.equal(fused, seq)
+    if with_canvas:                                                   # in place
+        inpl = canvas0.clone()
+        ops.writeback_canvas_fwd_steps(win, thi, fields[0, 9], fields[0, 15], NF * B, 0.99, inpl, inpl, 28, 28, 50, 50)
+        assert torch.equal(inpl, seq)
 
 
 def test_concrete_step_golden(golden_dir):

@@ -277,10 +277,10 @@ class AIRModel:
         vae_forward(_flat2(w["win"]), self.vw, None, _flat2(n["vae_like"]), self.vae_likelihood_std, hp, allbuf,
                     w["gen"], None, w["loss"], mode, latent_fn=latent_steps)
         # ---- (3) write-back + canvas accumulation in step order (air_model.py:351-366, 429-439)
-        for t in range(T):
-            f = w["fields"][t]
-            ops.writeback_canvas_fwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
-                                     self.stopping_threshold, w["canvas"] if t > 0 else None, w["canvas"], wsz, wsz, cs, cs)
+        #      -- all T of them in one pass over the canvas (the running canvas stays in registers; starts from zero)
+        f0 = w["fields"][0]
+        ops.writeback_canvas_fwd_steps(w["recon"], w["theta_inv"], f0[C.F_Z], f0[C.F_STOP_NEW], C.NF * B,
+                                       self.stopping_threshold, None, w["canvas"], wsz, wsz, cs, cs)
         dscale = 1.0 / (B * self.world)
         # the clipped reconstruction is only an output: written in inference, derived lazily in training
         ops.bce_loss(w["canvas"], x, None if self.train else w["reconstruction"], w["rec_loss"],

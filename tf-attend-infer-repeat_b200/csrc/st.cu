@@ -209,6 +209,114 @@ __global__ void __launch_bounds__(kFwdThreads)
 }
 
 // =========================================================================================
+// All T write-backs of the AIR loop in ONE pass over the canvas (air_model.py:363-366 + 429-439 for every step):
+//     canvas_out = (((canvas_in + a_0) + a_1) + ...) + a_{T-1},   a_t = live_t ? z_t * ST(window_t, theta_inv_t) : +0
+// with exactly the per-step roundings of T consecutive air_st_writeback_canvas_fwd calls (the running canvas is
+// kept in registers instead of making T round trips through HBM: 19 KB instead of 59 KB per image at T = 3).
+// Structure of st_fwd_staged<.., CANVAS, VEC>: G images per CTA, "slot" = (image, step); all G*T windows are staged
+// by bulk copies while the per-slot row / column tables are built.
+// =========================================================================================
+template <int H, int W, int OH, int OW, int G>
+__global__ void __launch_bounds__(kFwdThreads)
+    st_compose_steps(const float *__restrict__ windows, const float *__restrict__ theta_inv, const float *__restrict__ zp,
+                     const float *__restrict__ stop, int64_t step_stride, float thr, const float *canvas_in, float *out,
+                     int64_t B, int T) {
+  constexpr int HW = H * W, OHW = OH * OW, CPI = (OHW + 127) >> 7;
+  static_assert(HW % 4 == 0 && OHW % 4 == 0, "16-byte tiles");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int GT = G * T;
+  float *sU = reinterpret_cast<float *>(smem_raw);          // [G*T][HW]
+  Ent *sCol = reinterpret_cast<Ent *>(sU + GT * HW);         // [G*T][OW]
+  Ent *sRow = sCol + GT * OW;                                // [G*T][OH]
+  float *sTh = reinterpret_cast<float *>(sRow + GT * OH);    // [G*T][8]: theta[6], sep flag, live flag
+  float *sZ = sTh + GT * 8;                                  // [G*T]
+  __shared__ uint64_t bar;
+  __shared__ __align__(16) float sStage[kFwdThreads / 32][128];
+
+  const int tid = threadIdx.x;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * G;
+  const int n_img = static_cast<int>((B - g0 < G ? B - g0 : G));
+  const int slots = n_img * T;  // slot = i * T + t
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_sync();  // PDL: no global access before the previous grid has completed
+  if (tid == 0) {
+    mbar_expect_tx(&bar, static_cast<uint32_t>(slots) * HW * 4u);
+    for (int slot = 0; slot < slots; ++slot) {
+      const int i = slot / T, t = slot - i * T;
+      bulk_g2s(sU + slot * HW, windows + (static_cast<int64_t>(t) * B + g0 + i) * HW, HW * 4u, &bar);
+    }
+  }
+  // ---- per-slot theta / flags / z and tables, built while the bulk copies are in flight
+  for (int e = tid; e < slots * 8; e += kFwdThreads) {
+    const int slot = e >> 3, k = e & 7, i = slot / T, t = slot - i * T;
+    const float *th = theta_inv + (static_cast<int64_t>(t) * B + g0 + i) * 6;
+    float v;
+    if (k < 6) v = __ldg(th + k);
+    else if (k == 6) v = (__ldg(th + 1) == 0.0f && __ldg(th + 3) == 0.0f) ? 1.0f : 0.0f;
+    else v = (__ldg(stop + t * step_stride + g0 + i) < thr) ? 1.0f : 0.0f;
+    sTh[e] = v;
+    if (k == 0) sZ[slot] = __ldg(zp + t * step_stride + g0 + i);
+  }
+  constexpr int per_slot = OW + OH;
+  for (int e = tid; e < slots * per_slot; e += kFwdThreads) {
+    const int slot = e / per_slot, k = e - slot * per_slot, i = slot / T, t = slot - i * T;
+    const float *th = theta_inv + (static_cast<int64_t>(t) * B + g0 + i) * 6;
+    if (k < OW) sCol[slot * OW + k] = sep_ent(__ldg(th + 0), __ldg(th + 2), k, OW, W, 1);
+    else sRow[slot * OH + (k - OW)] = sep_ent(__ldg(th + 4), __ldg(th + 5), k - OW, OH, H, W);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int ch = warp; ch < n_img * CPI; ch += kFwdThreads / 32) {
+    const int i = ch / CPI, p0 = (ch - i * CPI) << 7;
+    const int64_t o = (g0 + i) * OHW + p0 + 4 * lane;
+    const bool mine = p0 + 4 * lane < OHW;
+    float4 cin = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mine && canvas_in) cin = *reinterpret_cast<const float4 *>(canvas_in + o);  // NULL: an all-zero canvas
+    for (int t = 0; t < T; ++t) {
+      const int slot = i * T + t;
+      const float *th = sTh + slot * 8;
+      float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (th[7] != 0.0f) {  // live (warp-uniform)
+        const bool sepi = th[6] != 0.0f;
+        const float zz = sZ[slot];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = p0 + 32 * j + lane;
+          float v = 0.0f;
+          if (q < OHW) {
+            const int r = q / OW, c = q - r * OW;
+            if (sepi) {
+              const Ent ce = sCol[slot * OW + c], re = sRow[slot * OH + r];
+              // clipped on both axes: the four products cancel to exactly +0 (same bits as the full formula)
+              v = (ce.i0 == ce.i1 && re.i0 == re.i1) ? 0.0f : bilerp(sU + slot * HW, ce, re);
+            } else {
+              Ent ce, re;
+              float xt, yt;
+              gen_ents(th, r, c, OH, OW, H, W, ce, re, xt, yt);
+              v = bilerp(sU + slot * HW, ce, re);
+            }
+          }
+          sStage[warp][32 * j + lane] = mul_rn(zz, v);
+        }
+        __syncwarp();
+        add = *reinterpret_cast<const float4 *>(&sStage[warp][4 * lane]);
+        __syncwarp();
+      }
+      cin.x = add_rn(cin.x, add.x); cin.y = add_rn(cin.y, add.y);
+      cin.z = add_rn(cin.z, add.z); cin.w = add_rn(cin.w, add.w);
+    }
+    if (mine) *reinterpret_cast<float4 *>(out + o) = cin;
+  }
+}
+
+// =========================================================================================
 // Forward, generic: any C, any size, unaligned pointers.  One thread per output pixel.
 // =========================================================================================
 __global__ void __launch_bounds__(256)
@@ -1187,6 +1295,40 @@ extern "C" int air_st_writeback_canvas_fwd(const float *window, const float *the
               "st_writeback_canvas_fwd: null pointer");
   return air::st_forward_impl(window, theta_inv, canvas_out, z, stop_new, thr, canvas_in, true, B, wh, ww, 1, ch, cw,
                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int air_st_writeback_canvas_fwd_steps(const float *windows, const float *theta_inv, const float *z,
+                                                 const float *stop_new, int64_t step_stride, float thr,
+                                                 const float *canvas_in, float *canvas_out, int64_t B, int T, int wh,
+                                                 int ww, int ch, int cw, air_stream_t stream) {
+  using namespace air;
+  AIR_REQUIRE(B >= 0 && T >= 1 && wh > 0 && ww > 0 && ch > 0 && cw > 0 && step_stride >= 0, AIR_ERR_BAD_SHAPE,
+              "st_writeback_canvas_fwd_steps: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(windows && theta_inv && z && stop_new && canvas_out, AIR_ERR_NULL, "st_writeback_canvas_fwd_steps: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  constexpr int G = 2;
+  const size_t smem = static_cast<size_t>(G) * T * (28 * 28 * 4 + (50 + 50) * sizeof(Ent) + 8 * 4 + 4);
+  if (wh == 28 && ww == 28 && ch == 50 && cw == 50 && aligned16(windows) && aligned16(canvas_out) &&
+      (!canvas_in || aligned16(canvas_in)) && smem <= static_cast<size_t>(kMaxStagedSmem) && B < (int64_t(1) << 31)) {
+    auto kern = st_compose_steps<28, 28, 50, 50, G>;
+    if (smem > 40 * 1024) {  // (+ 4 KB of static staging buffers: opt in before the 48 KB default limit is reached)
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_compose_steps): %s", cudaGetErrorString(e));
+    }
+    AIR_LAUNCH(kern, static_cast<unsigned>((B + G - 1) / G), kFwdThreads, smem, s, windows, theta_inv, z, stop_new, step_stride,
+               thr, canvas_in, canvas_out, B, T);
+    count_launch();
+    return check_launch("st_compose_steps");
+  }
+  // other sizes / many steps: the same result from T single-step launches
+  for (int t = 0; t < T; ++t) {
+    int rc = st_forward_impl(windows + static_cast<int64_t>(t) * B * wh * ww, theta_inv + static_cast<int64_t>(t) * B * 6,
+                             canvas_out, z + t * step_stride, stop_new + t * step_stride, thr, t == 0 ? canvas_in : canvas_out,
+                             true, B, wh, ww, 1, ch, cw, s);
+    if (rc) return rc;
+  }
+  return AIR_OK;
 }
 
 extern "C" int air_st_writeback_canvas_bwd(const float *window, const float *theta_inv, const float *z,

@@ -165,6 +165,15 @@ def writeback_canvas_fwd(window, theta_inv, z, stop_new, thr, canvas_in, canvas_
           "air_st_writeback_canvas_fwd")
 
 
+def writeback_canvas_fwd_steps(windows, theta_inv, z0, stop0, step_stride, thr, canvas_in, canvas_out, wh, ww, ch, cw):
+    """All T write-backs in one pass: windows [T,B,wh*ww], theta_inv [T,B,6]; z0 / stop0 = the step-0 rows, consecutive
+    steps ``step_stride`` floats apart."""
+    T, B = windows.shape[0], windows.shape[1]
+    check(lib().air_st_writeback_canvas_fwd_steps(ptr(windows), ptr(theta_inv), ptr(z0), ptr(stop0), int(step_stride),
+                                                  float(thr), ptr(canvas_in), ptr(canvas_out), B, T, wh, ww, ch, cw, stream()),
+          "air_st_writeback_canvas_fwd_steps")
+
+
 def writeback_canvas_bwd(window, theta_inv, z, stop_new, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw,
                          window_is_sigmoid=False, axis_aligned_theta=False):
     """flags of include/air_b200.h: AIR_WB_SIGMOID_WINDOW = 1, AIR_WB_AXIS_ALIGNED_THETA = 2 (dtheta_inv[1], [3] := 0)."""
