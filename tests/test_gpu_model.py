@@ -276,3 +276,59 @@ def test_train_step_is_bit_reproducible():
 def test_graft_entry_smoke():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def _covered_params(**shape_kw):
+    """covered_fixture's parameter tweaks (see tests/parity_util.py) for arbitrary model sizes."""
+    params = O.init_params(seed=3, **shape_kw)
+    params["scale/mean/output/biases"] += 12.0
+    params["scale/mean/output/weights"] *= 0.2
+    params["scale/log_variance/output/biases"] -= 8.0
+    params["shift/mean/output/weights"] *= 0.0
+    params["shift/mean/output/biases"] -= 3e-5
+    params["shift/log_variance/output/weights"] *= 0.1
+    params["shift/log_variance/output/biases"] -= 30.0
+    params["z_pres/log_odds/output/biases"] += 5.0
+    params["vae/gen_mean/weights"] *= 0.5
+    params["vae/gen_mean/biases"] -= 3.5
+    return params
+
+
+@pytest.mark.parametrize("T", [1, 2])
+def test_train_parity_other_step_counts(T):
+    """max_steps = 1 / 2: the time-batched schedule (T*B-row VAE, fused write-backs, K_h gradient over T-1 steps)."""
+    imgs, cnt, params, _ = covered_fixture(8, seed=4)
+    noise = O.make_noise(4, T, 8)
+    orc, m = make_pair(imgs, cnt, params, train=True, max_steps=T)
+    out, grads = orc.loss_and_grads(imgs, cnt, noise)
+    m.loss_and_grads(cuda_noise(noise))
+    assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"])
+    assert abs(m.loss.item() - out["loss"].item()) / abs(out["loss"].item()) < 1e-5
+    for k, g in m.store.named_grads().items():
+        assert relnorm(g, grads[k]) < 1e-4, (k, relnorm(g, grads[k]))
+
+
+def test_train_parity_non_default_sizes():
+    """canvas 40x40, window 20x20, 128 LSTM units, other VAE widths: the size-generic kernel paths (staged ST with
+    run-time sizes, the sequential fallback of the fused write-back, generic fused backward) against the oracle."""
+    B, cs, ws = 6, 40, 20
+    shape_kw = dict(canvas_size=cs, windows_size=ws, rnn_units=128, vae_latent_dimensions=24,
+                    vae_recognition_units=(96, 64), vae_generative_units=(64, 96), scale_hidden_units=32,
+                    shift_hidden_units=32, z_pres_hidden_units=32)
+    imgs, cnt = O.synthetic_canvases(B, canvas_size=cs, seed=5, digit_size=(10, 16))
+    im = imgs.reshape(B, cs, cs).clone()
+    im[:, :5] = 0; im[:, -5:] = 0; im[:, :, :5] = 0; im[:, :, -5:] = 0
+    imgs = im.reshape(B, -1).contiguous()
+    params = _covered_params(**shape_kw)
+    noise = O.make_noise(5, 3, B, latent=24, win=ws * ws)
+    orc, m = make_pair(imgs, cnt, params, train=True, **shape_kw)
+    out, grads = orc.loss_and_grads(imgs, cnt, noise)
+    m.loss_and_grads(cuda_noise(noise))
+    assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"])
+    assert abs(m.loss.item() - out["loss"].item()) / abs(out["loss"].item()) < 1e-5
+    assert relnorm(m.rec_windows, out["rec_windows"]) < 1e-5
+    for k, g in m.store.named_grads().items():
+        assert relnorm(g, grads[k]) < 1e-4, (k, relnorm(g, grads[k]))
+    m._apply_gradients()
+    torch.cuda.synchronize()
+
