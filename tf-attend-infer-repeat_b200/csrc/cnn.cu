@@ -163,7 +163,19 @@ __global__ void __launch_bounds__(THREADS)
       }
       __syncthreads();
     }
-    if (tap) {  // dW[ky][kx][ci][:] += sum over output pixels of in[y+ky-2][x+kx-2][ci] * d(conv)[y][x][:]
+    if (tap && NEED_DX) {
+      // dW[ky][kx][ci][:] += sum over conv pixels of in[y+ky-2][x+kx-2][ci] * d(conv)[y][x][:], from the dense
+      // (un-pooled) tile that the dX pass needs anyway: one input load + two broadcast 128-bit loads per 8 FMAs
+      constexpr int CH = POOL ? 2 * PH : H, CW = POOL ? 2 * PW : W;  // conv pixels that can carry a gradient
+      for (int q = group; q < CH * CW; q += NG) {
+        const int y = q / CW, x = q - y * CW;
+        const float *dp = sD + ((y + 2) * IW + (x + 2)) * kCout;
+        const float4 ga = *reinterpret_cast<const float4 *>(dp), gq = *reinterpret_cast<const float4 *>(dp + 4);
+        const float v = sIn[((y + ky) * IW + (x + kx)) * CIN + ci];
+        gw[0] = fmaf(v, ga.x, gw[0]); gw[1] = fmaf(v, ga.y, gw[1]); gw[2] = fmaf(v, ga.z, gw[2]); gw[3] = fmaf(v, ga.w, gw[3]);
+        gw[4] = fmaf(v, gq.x, gw[4]); gw[5] = fmaf(v, gq.y, gw[5]); gw[6] = fmaf(v, gq.z, gw[6]); gw[7] = fmaf(v, gq.w, gw[7]);
+      }
+    } else if (tap) {  // (first layer: no dense tile) the same sum over the pooled elements and their argmax positions
       for (int pp = group; pp < NPIX; pp += NG) {
         const int py = pp / PW, px = pp - py * PW;
         const float4 ga = *reinterpret_cast<const float4 *>(sG + pp * kCout), gq = *reinterpret_cast<const float4 *>(sG + pp * kCout + 4);
