@@ -26,7 +26,15 @@ def _worker(rank, world, init_file, out_dir):
     m = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=True)
     out, grads = m.loss_and_grads(my_imgs, my_cnt, my_noise)      # gradient of the LOCAL mean
     flat = torch.cat([g.reshape(-1) for g in grads.values()]) / world   # per-item weight 1/(B_local*world)
+    # the bucketed, asynchronous form AIRModel uses (first bucket reduced while the rest is still being produced)
+    # must give exactly what one flat all-reduce gives
+    bucketed = flat.clone()
+    k = bucketed.numel() * 7 // 10
+    wa = ab.dp.allreduce_async(bucketed[:k])
+    wb = ab.dp.allreduce_async(bucketed[k:])
+    wa.wait(); wb.wait()
     ab.dp.allreduce_flat(flat)
+    assert torch.equal(bucketed, flat)
     scal = ab.dp.allreduce_scalars(torch.stack([out["loss"], out["accuracy"]]).clone())
     torch.save({"flat": flat, "scal": scal, "digits": out["rec_num_digits"]}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
