@@ -196,6 +196,8 @@ def st_kernels(d, B):
 # 65536 images; r1_st_bwd_k1/k2_ncu_full.md).  The fused backward reads LESS than the algorithmic figure because
 # stopped images (30 % of the synthetic batch) never fetch their dCanvas rows.
 ST_NCU_TRAFFIC_B65536 = {"crop_fwd": 4 * (656.946e6 + 183.790e6), "crop_bwd": 862.487e6 + 5.773e6,
+                         "writeback_canvas_fwd": 863.045e6 + 615.292e6,          # profiles/r1_wb_fwd_ncu_full.md
+                         "writeback_canvas_bwd": 606.693e6 + 187.272e6,          # profiles/r1_st_wb_bwd_axis_ncu_full.md
                          "writeback_canvas_bwd_full_dtheta": 606.910e6 + 186.340e6}
 
 
