@@ -273,6 +273,23 @@ def run_st(args, rank, world, peaks):
     return line
 
 
+def st_summary(peaks, B=65536, steps=20, warmup=5):
+    """Compact ST microbench (the second half of BASELINE.json's metric) for the default train line: per kernel
+    ms / GB/s / fraction of the measured HBM peak at B = 65536, same inputs and timing as --workload st."""
+    import torch
+    d = st_inputs(B, torch.device("cuda"))
+    ks = st_kernels(d, B)
+    out = {}
+    for name, fn in ks.items():
+        ms = time_launches(fn, steps, warmup)
+        gbs = B * ST_BYTES[name] / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 5), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)}
+    del d, ks
+    torch.cuda.empty_cache()
+    return {"batch": B, "steps": steps, "unit": "GB/s of algorithmic bytes (SURVEY 8d)", "hbm_peak_GBps": peaks["hbm_gbs"],
+            "kernels": out}
+
+
 def cpu_baseline_st(B=4096):
     """The C oracle's ST forward (crop) timed on the host, scalar, 1 thread."""
     import numpy as np
@@ -336,6 +353,11 @@ def main():
         line = run_st(args, rank, world, peaks)
     else:
         line = bench_train.run(args, rank, world, peaks)
+        if world == 1 and args.workload == "train":
+            try:  # the other half of the headline metric rides along on the single-GPU line (full detail: --workload st)
+                line["st_microbench"] = st_summary(peaks)
+            except Exception as e:  # never lose the train line over the side measurement
+                line["st_microbench"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
