@@ -68,6 +68,22 @@ int air_st_writeback_canvas_fwd(const float *window, const float *theta_inv, con
                                 float thr, const float *canvas_in, float *canvas_out, int64_t B, int wh, int ww,
                                 int ch, int cw, air_stream_t stream);
 
+/* ---- all T loop steps of an op in one launch --------------------------------------------------------------
+ * The per-step operands are stacked [T, B, ...]; the operand every step shares is passed once:
+ *   air_st_forward_steps   out[t,b] = ST(U[b], theta[t,b])                 (the T attention crops of one canvas)
+ *   air_st_backward_steps  dtheta[t,b] from dout[t,b]                      (U is data: no dU)
+ *   air_st_writeback_canvas_bwd_steps  the fused backward of every step against the one dcanvas [B,ch,cw]; z / stop_new
+ *                          point at step 0, consecutive steps are step_stride floats apart
+ * Each is bit-identical to T calls of the single-step entry point, which is also the fallback when the batched
+ * kernel does not apply (other sizes, B % 4 != 0, flags without AIR_WB_AXIS_ALIGNED_THETA). */
+int air_st_forward_steps(const float *U, const float *theta, float *out, int64_t B, int T, int H, int W, int C, int oh, int ow,
+                         air_stream_t stream);
+int air_st_backward_steps(const float *U, const float *theta, const float *dout, float *dtheta, int64_t B, int T, int H, int W,
+                          int C, int oh, int ow, air_stream_t stream);
+int air_st_writeback_canvas_bwd_steps(const float *windows, const float *theta_inv, const float *z, const float *stop_new,
+                                      int64_t step_stride, float thr, const float *dcanvas, float *dwindow, float *dtheta_inv,
+                                      float *dz, int flags, int64_t B, int T, int wh, int ww, int ch, int cw, air_stream_t stream);
+
 /* All T write-backs of the loop in one pass over the canvas:
  *   canvas_out = (((canvas_in + a_0) + a_1) + ...) + a_{T-1},  a_t = stop_new_t < thr ? z_t * ST(window_t, theta_inv_t) : +0
  * windows [T,B,wh,ww], theta_inv [T,B,6]; z / stop_new point at step 0 and consecutive steps are step_stride floats

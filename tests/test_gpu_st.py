@@ -349,6 +349,58 @@ def test_writeback_steps_bit_identical_to_sequential(T, B, with_canvas):
         assert torch.equal(inpl, seq)
 
 
+@pytest.mark.parametrize("T,B", [(3, 64), (5, 12), (2, 7), (1, 8)])
+def test_steps_launches_bit_identical_to_per_step_calls(T, B):
+    """air_st_forward_steps / air_st_backward_steps / air_st_writeback_canvas_bwd_steps == T single-step calls, bit for
+    bit (B = 7 is not a multiple of 4: the crop forward takes the documented per-step fallback)."""
+    rng = np.random.RandomState(90 + T + B)
+    NF = 20
+    U = cu(rng.rand(B, 2500).astype(np.float32))
+    th = np.zeros((T, B, 6), np.float32); thi = np.zeros((T, B, 6), np.float32)
+    for t in range(T):
+        a, b_ = air_thetas(rng, B)
+        th[t], thi[t] = a.reshape(B, 6), b_.reshape(B, 6)
+    thi[0, 1] = [1.3, 0.2, 0.1, -0.1, 1.2, 0.0]                               # a sheared row (atomics fallback inside)
+    th, thi = cu(th), cu(thi)
+    # crop forward
+    win_b, win_s = torch.empty(T, B, 784, device=DEV), torch.empty(T, B, 784, device=DEV)
+    ops.st_forward_steps(U, th, win_b, 50, 50, 1, 28, 28)
+    for t in range(T):
+        ops.st_forward(U, th[t], win_s[t], 50, 50, 1, 28, 28)
+    assert torch.equal(win_b, win_s)
+    # crop backward
+    dwin = cu(rng.randn(T, B, 784).astype(np.float32))
+    dth_b, dth_s = torch.empty(T, B, 6, device=DEV), torch.empty(T, B, 6, device=DEV)
+    ops.st_backward_steps(U, th, dwin, dth_b, 50, 50, 1, 28, 28)
+    for t in range(T):
+        ops.st_backward(U, th[t], dwin[t], None, dth_s[t], 50, 50, 1, 28, 28)
+    assert torch.equal(dth_b, dth_s)
+    # fused write-back backward against one dcanvas
+    fields = torch.zeros(T, NF, B, device=DEV)
+    fields[:, 9] = cu(rng.rand(T, B).astype(np.float32) * 0.9 + 0.05)
+    fields[:, 15] = cu(rng.choice(np.array([0.0, 0.5, 1.3], np.float32), (T, B)))
+    dcanvas = cu(rng.randn(B, 2500).astype(np.float32))
+    recon = cu(rng.rand(T, B, 784).astype(np.float32))
+    for sig, axis in ((True, True), (False, True), (False, False)):
+        outs = []
+        for batched in (True, False):
+            dw, dt, dz = torch.full((T, B, 784), 7.0, device=DEV), torch.full((T, B, 6), 7.0, device=DEV), torch.full((T, B), 7.0, device=DEV)
+            if batched:
+                ops.writeback_canvas_bwd_steps(recon, thi, fields[0, 9], fields[0, 15], NF * B, 0.99, dcanvas, dw, dt, dz,
+                                               28, 28, 50, 50, window_is_sigmoid=sig, axis_aligned_theta=axis)
+            else:
+                for t in range(T):
+                    ops.writeback_canvas_bwd(recon[t], thi[t], fields[t, 9], fields[t, 15], 0.99, dcanvas, dw[t], dt[t], dz[t],
+                                             28, 28, 50, 50, window_is_sigmoid=sig, axis_aligned_theta=axis)
+            outs.append((dw, dt, dz))
+        for a, b_ in zip(*outs):
+            # the sheared row's dU goes through shared-memory float atomics (order not fixed): close, not identical
+            assert torch.allclose(a[0, 1], b_[0, 1], rtol=1e-4, atol=1e-5), (sig, axis)
+            a, b_ = a.clone(), b_.clone()
+            a[0, 1] = 0; b_[0, 1] = 0
+            assert torch.equal(a, b_), (sig, axis)
+
+
 def test_concrete_step_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "concrete.npz"))
     for train in (0, 1):

@@ -26,6 +26,10 @@ _SIGS = {
     "air_st_backward": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
     "air_st_writeback_canvas_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_float] + [_c_f] * 2 + [ctypes.c_int64] +
                                     [ctypes.c_int] * 4 + [_c_f]),
+    "air_st_forward_steps": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int64] + [ctypes.c_int] * 6 + [_c_f]),
+    "air_st_backward_steps": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int64] + [ctypes.c_int] * 6 + [_c_f]),
+    "air_st_writeback_canvas_bwd_steps": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int64, ctypes.c_float] + [_c_f] * 4 +
+                                          [ctypes.c_int, ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
     "air_st_writeback_canvas_fwd_steps": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int64, ctypes.c_float, _c_f, _c_f, ctypes.c_int64] +
                                           [ctypes.c_int] * 5 + [_c_f]),
     "air_st_writeback_canvas_bwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_float] + [_c_f] * 4 + [ctypes.c_int, ctypes.c_int64] +

@@ -264,7 +264,7 @@ class AIRModel:
             ops.heads_fwd(w["hh"][t], p["heads/out_w"], p["heads/out_b"], n["scale"][t], n["shift"][t],
                           n["concrete_u"][t], self._prior, hp, w["stop"], w["loss"], w["digits"], w["fields"][t],
                           w["theta"][t], w["theta_inv"][t])
-            ops.st_forward(x, w["theta"][t], w["win"][t], cs, cs, 1, wsz, wsz)
+        ops.st_forward_steps(x, w["theta"], w["win"], cs, cs, 1, wsz, wsz)  # the T attention crops: one launch
         # ---- (2) the VAE of ALL steps as one evaluation on T*B rows (air_model.py:335-349, 479-496): six GEMMs
         #      with M = T*B instead of 6 T with M = B.  Only the latent step touches per-step state (live mask,
         #      running loss), so it stays per step; the running loss therefore adds the VAE KLs after the pose /
@@ -334,12 +334,12 @@ class AIRModel:
         w["dgates_sum"].zero_()
         vd = w["vae_d"]
         # ---- (1) write-back backward of every step (the canvas is a plain sum: all steps see the same dcanvas)
-        for t in range(T):
-            f = w["fields"][t]
-            ops.writeback_canvas_bwd(w["recon"][t], w["theta_inv"][t], f[C.F_Z], f[C.F_STOP_NEW],
-                                     self.stopping_threshold, w["dcanvas"], vd["dgen"][t], w["dtheta_inv"][t], w["dz"][t],
-                                     wsz, wsz, cs, cs, window_is_sigmoid=True,  # SigmoidGrad fused into the store
-                                     axis_aligned_theta=True)  # heads_bwd reads dtheta_inv[0,2,4,5] only
+        #      -- one launch for all T steps
+        f0 = w["fields"][0]
+        ops.writeback_canvas_bwd_steps(w["recon"], w["theta_inv"], f0[C.F_Z], f0[C.F_STOP_NEW], C.NF * B,
+                                       self.stopping_threshold, w["dcanvas"], vd["dgen"], w["dtheta_inv"], w["dz"],
+                                       wsz, wsz, cs, cs, window_is_sigmoid=True,  # SigmoidGrad fused into the store
+                                       axis_aligned_theta=True)  # heads_bwd reads dtheta_inv[0,2,4,5] only
         # ---- (2) VAE backward of all steps as one evaluation on T*B rows, then the crop backward per step
         def latent_bwd_steps():
             for t in range(T):
@@ -350,8 +350,7 @@ class AIRModel:
                     ddec=[_flat2(d) for d in vd["ddec"]], dgen=_flat2(vd["dgen"]))
         vae_backward_dx(_flat2(w["win"]), self.vw, None, hp, allbuf, alld, dscale, None, mode, dx_out=_flat2(w["dwin"]),
                         dgen_is_presigmoid=True, latent_bwd_fn=latent_bwd_steps)
-        for t in range(T):
-            ops.st_backward(x, w["theta"][t], w["dwin"][t], None, w["dtheta"][t], cs, cs, 1, wsz, wsz)
+        ops.st_backward_steps(x, w["theta"], w["dwin"], w["dtheta"], cs, cs, 1, wsz, wsz)
         # ---- (3) the recurrent chain backwards: heads -> LSTM, step by step
         for t in range(T - 1, -1, -1):
             last = t == T - 1

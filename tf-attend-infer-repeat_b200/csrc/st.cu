@@ -19,6 +19,13 @@
 
 namespace air {
 
+// "All T loop steps in one launch": rows r = t * B + b of the per-step operands, while the operand that is the same
+// for every step (the canvas for the crop, dCanvas for the write-back backward) is indexed b = r % step_mod and the
+// per-step scalars (z, stop) live step_stride floats apart.  step_mod == 0: plain batch.  Set by the *_steps entry
+// points around their call into the shared dispatch code.
+struct StepsCtx { int64_t mod = 0, stride = 0; };
+static thread_local StepsCtx g_steps;
+
 struct __align__(16) Ent {
   int i0, i1;    // clipped corner offsets (pre-multiplied by the source stride)
   float w1, w0;  // (i1f - v), (v - i0f) with v the UNCLIPPED coordinate
@@ -77,7 +84,7 @@ template <int H_, int W_, int OH_, int OW_, int G, bool CANVAS, bool VEC = false
 __global__ void __launch_bounds__(kFwdThreads)
     st_fwd_staged(const float *__restrict__ U, const float *__restrict__ theta, float *out,
                   const float *__restrict__ zp, const float *__restrict__ stop, float thr, const float *canvas_in,
-                  int64_t B, int rH, int rW, int rOH, int rOW) {
+                  int64_t B, int rH, int rW, int rOH, int rOW, int64_t u_mod) {
   const int H = H_ ? H_ : rH, W = W_ ? W_ : rW, OH = OH_ ? OH_ : rOH, OW = OW_ ? OW_ : rOW;
   const int HW = H * W, OHW = OH * OW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(kFwdThreads)
   if (tid == 0) {
     const uint32_t bytes = static_cast<uint32_t>(n_img) * HW * 4u;
     mbar_expect_tx(&bar, bytes);
-    bulk_g2s(sU, U + g0 * HW, bytes, &bar);
+    bulk_g2s(sU, U + (u_mod ? g0 % u_mod : g0) * HW, bytes, &bar);  // u_mod: the same U for every loop step
   }
 
   // ---- tables, built while the bulk copy is in flight
@@ -411,7 +418,8 @@ template <int H_, int W_, int OH_, int OW_, bool FUSED>
 __global__ void __launch_bounds__(kBwdThreads)
     st_bwd_staged(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dout,
                   const float *__restrict__ zp, const float *__restrict__ stop, float thr, float *__restrict__ dU,
-                  float *__restrict__ dtheta, float *__restrict__ dz, int sig, int64_t B, int rH, int rW, int rOH, int rOW) {
+                  float *__restrict__ dtheta, float *__restrict__ dz, int sig, int64_t B, int rH, int rW, int rOH, int rOW,
+                  int64_t u_mod) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
   const int H = H_ ? H_ : rH, W = W_ ? W_ : rW, OH = OH_ ? OH_ : rOH, OW = OW_ ? OW_ : rOW;
   const int HW = H * W, OHW = OH * OW;
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__(kBwdThreads)
     mbar_init(&bar, 1);
     fence_mbar_init();
     mbar_expect_tx(&bar, static_cast<uint32_t>(HW + OHW) * 4u);
-    bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
+    bulk_g2s(sU, U + (u_mod ? b % u_mod : b) * HW, HW * 4u, &bar);  // u_mod: the same U for every loop step
     bulk_g2s(sG, dout + b * OHW, OHW * 4u, &bar);
   }
   // ---- tables (overlap the bulk copies): clipped corners + 1-D weights, grid coordinates, empty runs
@@ -916,7 +924,8 @@ template <int H, int W, int OH, int OW>
 __global__ void __launch_bounds__(kAxisThreads, 11)
     st_wb_bwd_axis(const float *__restrict__ U, const float *__restrict__ theta, const float *__restrict__ dcanvas,
                    const float *__restrict__ zp, const float *__restrict__ stop, float thr, float *__restrict__ dU,
-                   float *__restrict__ dtheta, float *__restrict__ dz, int sig, int64_t B) {
+                   float *__restrict__ dtheta, float *__restrict__ dz, int sig, int64_t B, int64_t step_mod,
+                   int64_t step_stride) {
   static_assert(W <= 32 && OW <= 64 && OH <= 64 && (H * W) % 4 == 0 && (OH * OW) % 4 == 0, "unsupported tile");
   static_assert(W * kAxisQS >= H * W, "the fallback path keeps its dU tile in the Q buffer");
   static_assert(OW + OH <= kAxisThreads + 32, "table construction: one entry per thread + a tail on warp 2");
@@ -944,8 +953,11 @@ __global__ void __launch_bounds__(kAxisThreads, 11)
   // every global scalar this thread needs is requested before the first use, so that the CTA pays ONE DRAM
   // round trip (not stop -> theta in sequence) before its bulk copies are issued and its tables are built
   const int k0 = tid, k1 = tid + 32;  // table entries of this thread (k1 only for warp 2, if < OW + OH)
-  const float stop_b = __ldg(stop + b);
-  const float zval = __ldg(zp + b);
+  // step_mod != 0: row b = t * step_mod + image; dcanvas is per image, z / stop live step_stride apart per step
+  const int64_t img = step_mod ? b % step_mod : b;
+  const int64_t zi = step_mod ? (b / step_mod) * step_stride + img : b;
+  const float stop_b = __ldg(stop + zi);
+  const float zval = __ldg(zp + zi);
   const float diag0 = __ldg(th_g + (k0 < OW ? 0 : 4)), trans0 = __ldg(th_g + (k0 < OW ? 2 : 5));
   const float off1 = __ldg(th_g + 1), off3 = __ldg(th_g + 3);
   if (!(stop_b < thr)) {  // whole image masked out: every gradient is exactly zero (uniform branch)
@@ -959,7 +971,7 @@ __global__ void __launch_bounds__(kAxisThreads, 11)
     fence_mbar_init();
     mbar_expect_tx(&bar, static_cast<uint32_t>(HW + OHW) * 4u);
     bulk_g2s(sU, U + b * HW, HW * 4u, &bar);
-    bulk_g2s(sG, dcanvas + b * OHW, OHW * 4u, &bar);
+    bulk_g2s(sG, dcanvas + img * OHW, OHW * 4u, &bar);
   }
   if (tid < 8) sPart[tid] = 0.0f;
   // ---- tables (overlap the bulk copies): one entry per thread; the tail goes to warp 2, which has the
@@ -1140,7 +1152,10 @@ static int launch_fwd_staged(const float *U, const float *theta, float *out, con
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_fwd_staged): %s", cudaGetErrorString(e));
   }
   const int64_t grid = (B + G - 1) / G;
-  AIR_LAUNCH(kern, static_cast<unsigned>(grid), kFwdThreads, smem, s, U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW);
+  AIR_REQUIRE(g_steps.mod == 0 || (!CANVAS && g_steps.mod % G == 0), AIR_ERR_UNSUPPORTED,
+              "st_forward_steps: the batch must be a multiple of %d", G);
+  AIR_LAUNCH(kern, static_cast<unsigned>(grid), kFwdThreads, smem, s, U, theta, out, z, stop, thr, canvas_in, B, H, W, OH, OW,
+             g_steps.mod);
   count_launch();
   return check_launch("st_fwd_staged");
 }
@@ -1186,6 +1201,7 @@ static int st_forward_impl(const float *U, const float *theta, float *out, const
   }
   AIR_REQUIRE(!canvas, AIR_ERR_UNSUPPORTED,
               "st_writeback_canvas_fwd: needs a 16-byte aligned single-channel window that fits shared memory");
+  if (g_steps.mod != 0) return AIR_ERR_UNSUPPORTED;  // the *_steps caller falls back to one launch per step
   const int64_t n = B * OH * OW;
   const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
   AIR_LAUNCH(st_fwd_generic, blocks, 256, 0, s, U, theta, out, B, H, W, C, OH, OW);
@@ -1210,7 +1226,10 @@ static int launch_bwd_staged(const float *U, const float *theta, const float *do
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_bwd_staged): %s", cudaGetErrorString(e));
   }
-  AIR_LAUNCH(kern, static_cast<unsigned>(B), kBwdThreads, smem, s, U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW);
+  AIR_REQUIRE(g_steps.mod == 0 || (!FUSED && dU == nullptr), AIR_ERR_UNSUPPORTED,
+              "st_backward_steps: a U shared by all steps cannot receive a per-step dU");
+  AIR_LAUNCH(kern, static_cast<unsigned>(B), kBwdThreads, smem, s, U, theta, dout, z, stop, thr, dU, dtheta, dz, sig, B, H, W, OH, OW,
+             g_steps.mod);
   count_launch();
   return check_launch("st_bwd_staged");
 }
@@ -1228,7 +1247,8 @@ static int launch_wb_bwd_axis(const float *U, const float *theta, const float *d
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(st_wb_bwd_axis): %s", cudaGetErrorString(e));
     once = true;
   }
-  AIR_LAUNCH(kern, static_cast<unsigned>(B), kAxisThreads, smem, s, U, theta, dcanvas, z, stop, thr, dU, dtheta, dz, sig, B);
+  AIR_LAUNCH(kern, static_cast<unsigned>(B), kAxisThreads, smem, s, U, theta, dcanvas, z, stop, thr, dU, dtheta, dz, sig, B,
+             g_steps.mod, g_steps.stride);
   count_launch();
   return check_launch("st_wb_bwd_axis");
 }
@@ -1262,6 +1282,7 @@ static int st_backward_impl(const float *U, const float *theta, const float *dou
   }
   AIR_REQUIRE(!fused, AIR_ERR_UNSUPPORTED,
               "st_writeback_canvas_bwd: needs 16-byte aligned single-channel tiles that fit shared memory");
+  if (g_steps.mod != 0) return AIR_ERR_UNSUPPORTED;  // the *_steps caller falls back to one launch per step
   AIR_REQUIRE(B < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "st_backward: B too large");
   if (dU) {
     cudaError_t e = cudaMemsetAsync(dU, 0, sizeof(float) * static_cast<size_t>(B) * H * W * C, s);
@@ -1295,6 +1316,79 @@ extern "C" int air_st_writeback_canvas_fwd(const float *window, const float *the
               "st_writeback_canvas_fwd: null pointer");
   return air::st_forward_impl(window, theta_inv, canvas_out, z, stop_new, thr, canvas_in, true, B, wh, ww, 1, ch, cw,
                               static_cast<cudaStream_t>(stream));
+}
+
+// ---- all T loop steps in one launch (the per-step operand rows are [T, B, ...]; see StepsCtx) ---------------
+extern "C" int air_st_forward_steps(const float *U, const float *theta, float *out, int64_t B, int T, int H, int W, int C,
+                                    int oh, int ow, air_stream_t stream) {
+  using namespace air;
+  AIR_REQUIRE(B >= 0 && T >= 1, AIR_ERR_BAD_SHAPE, "st_forward_steps: bad shape");
+  if (B == 0) return AIR_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (T > 1 && B % 4 == 0 && C == 1) {
+    g_steps.mod = B;
+    g_steps.stride = 0;
+    const int rc = st_forward_impl(U, theta, out, nullptr, nullptr, 0.0f, nullptr, false, B * T, H, W, C, oh, ow, s);
+    g_steps = StepsCtx();
+    if (rc != AIR_ERR_UNSUPPORTED) return rc;
+  }
+  for (int t = 0; t < T; ++t) {
+    const int rc = st_forward_impl(U, theta + static_cast<int64_t>(t) * B * 6, out + static_cast<int64_t>(t) * B * oh * ow * C,
+                                   nullptr, nullptr, 0.0f, nullptr, false, B, H, W, C, oh, ow, s);
+    if (rc) return rc;
+  }
+  return AIR_OK;
+}
+
+extern "C" int air_st_backward_steps(const float *U, const float *theta, const float *dout, float *dtheta, int64_t B, int T,
+                                     int H, int W, int C, int oh, int ow, air_stream_t stream) {
+  using namespace air;
+  AIR_REQUIRE(B >= 0 && T >= 1, AIR_ERR_BAD_SHAPE, "st_backward_steps: bad shape");
+  if (B == 0) return AIR_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (T > 1 && C == 1) {
+    g_steps.mod = B;
+    g_steps.stride = 0;
+    const int rc = st_backward_impl(U, theta, dout, nullptr, nullptr, 0.0f, false, nullptr, dtheta, nullptr, 0, B * T, H, W, C, oh,
+                                    ow, s);
+    g_steps = StepsCtx();
+    if (rc != AIR_ERR_UNSUPPORTED) return rc;
+  }
+  for (int t = 0; t < T; ++t) {
+    const int rc = st_backward_impl(U, theta + static_cast<int64_t>(t) * B * 6, dout + static_cast<int64_t>(t) * B * oh * ow * C,
+                                    nullptr, nullptr, 0.0f, false, nullptr, dtheta + static_cast<int64_t>(t) * B * 6, nullptr, 0, B,
+                                    H, W, C, oh, ow, s);
+    if (rc) return rc;
+  }
+  return AIR_OK;
+}
+
+extern "C" int air_st_writeback_canvas_bwd_steps(const float *windows, const float *theta_inv, const float *z,
+                                                 const float *stop_new, int64_t step_stride, float thr, const float *dcanvas,
+                                                 float *dwindow, float *dtheta_inv, float *dz, int flags, int64_t B, int T,
+                                                 int wh, int ww, int ch, int cw, air_stream_t stream) {
+  using namespace air;
+  AIR_REQUIRE(B >= 0 && T >= 1 && step_stride >= 0, AIR_ERR_BAD_SHAPE, "st_writeback_canvas_bwd_steps: bad shape");
+  if (B == 0) return AIR_OK;
+  AIR_REQUIRE(windows && theta_inv && z && stop_new && dcanvas && dwindow && dtheta_inv && dz, AIR_ERR_NULL,
+              "st_writeback_canvas_bwd_steps: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (T > 1 && (flags & AIR_WB_AXIS_ALIGNED_THETA) && wh == 28 && ww == 28 && ch == 50 && cw == 50) {
+    g_steps.mod = B;
+    g_steps.stride = step_stride;
+    const int rc = st_backward_impl(windows, theta_inv, dcanvas, z, stop_new, thr, true, dwindow, dtheta_inv, dz, flags, B * T, wh,
+                                    ww, 1, ch, cw, s);
+    g_steps = StepsCtx();
+    if (rc != AIR_ERR_UNSUPPORTED) return rc;
+  }
+  for (int t = 0; t < T; ++t) {
+    const int64_t o = static_cast<int64_t>(t) * B;
+    const int rc = st_backward_impl(windows + o * wh * ww, theta_inv + o * 6, dcanvas, z + t * step_stride,
+                                    stop_new + t * step_stride, thr, true, dwindow + o * wh * ww, dtheta_inv + o * 6, dz + o, flags,
+                                    B, wh, ww, 1, ch, cw, s);
+    if (rc) return rc;
+  }
+  return AIR_OK;
 }
 
 extern "C" int air_st_writeback_canvas_fwd_steps(const float *windows, const float *theta_inv, const float *z,

@@ -165,6 +165,27 @@ def writeback_canvas_fwd(window, theta_inv, z, stop_new, thr, canvas_in, canvas_
           "air_st_writeback_canvas_fwd")
 
 
+def st_forward_steps(U, theta, out, H, W, C_, oh, ow):
+    """out[t,b] = ST(U[b], theta[t,b]) for all T steps in one launch (theta [T,B,6], out [T,B,oh*ow*C])."""
+    T, B = theta.shape[0], theta.shape[1]
+    check(lib().air_st_forward_steps(ptr(U), ptr(theta), ptr(out), B, T, H, W, C_, oh, ow, stream()), "air_st_forward_steps")
+
+
+def st_backward_steps(U, theta, dout, dtheta, H, W, C_, oh, ow):
+    T, B = theta.shape[0], theta.shape[1]
+    check(lib().air_st_backward_steps(ptr(U), ptr(theta), ptr(dout), ptr(dtheta), B, T, H, W, C_, oh, ow, stream()),
+          "air_st_backward_steps")
+
+
+def writeback_canvas_bwd_steps(windows, theta_inv, z0, stop0, step_stride, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw,
+                               window_is_sigmoid=False, axis_aligned_theta=False):
+    T, B = windows.shape[0], windows.shape[1]
+    flags = (1 if window_is_sigmoid else 0) | (2 if axis_aligned_theta else 0)
+    check(lib().air_st_writeback_canvas_bwd_steps(ptr(windows), ptr(theta_inv), ptr(z0), ptr(stop0), int(step_stride), float(thr),
+                                                  ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), flags, B, T, wh, ww, ch, cw,
+                                                  stream()), "air_st_writeback_canvas_bwd_steps")
+
+
 def writeback_canvas_fwd_steps(windows, theta_inv, z0, stop0, step_stride, thr, canvas_in, canvas_out, wh, ww, ch, cw):
     """All T write-backs in one pass: windows [T,B,wh*ww], theta_inv [T,B,6]; z0 / stop0 = the step-0 rows, consecutive
     steps ``step_stride`` floats apart."""
