@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(kTcThreads)
   // ================= TMA producers =================
   // Every stage is loaded as 4 + 4 quarter boxes issued by four threads: lane 0 of warp 0 and of the
   // (otherwise idle until the accumulator is complete) epilogue warps 2..4.  Measured neutral against a
-  // single issuing thread: the per-CTA operand rate (~37 GB/s when a CTA is alone on its SM) is not an
-  // issue-rate limit, which is why the host picks grids with two CTAs per SM.
+  // single issuing thread: TMA issue is not the limit -- machine-wide the kernel is bound by L2 -> SM operand
+  // bandwidth (profiles/r1_gemm_tf32_big_ncu_full.md).
   if (warp == 0 || (warp >= 2 && warp <= 4)) {
     if (lane == 0) {
       const int pi = warp == 0 ? 0 : warp - 1;  // producer index 0..3
@@ -464,9 +464,9 @@ template <int BN, bool A_MN, bool B_MN, bool CL>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, cudaStream_t s) {
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL>;
   const size_t stage_bytes = static_cast<size_t>(kBM + BN) * kBK * 4;
-  // The mainloop of one CTA is TMA-latency bound (~0.7 us per k-block with 3 stages), so keep as many
-  // bytes in flight per SM as shared memory allows: a deep ring when the grid gives each SM one CTA,
-  // half of it when two CTAs will share an SM.
+  // Keep as many operand bytes in flight per SM as shared memory allows: a deep ring when the grid gives each SM
+  // one CTA, half of it when two CTAs will share an SM.  (tests/diag_gemm_single_cta.py: one CTA per SM with
+  // operands streaming from HBM runs 1.5 / 2.3 / 2.35 k-blocks per us with 2 / 4 / 6 stages.)
   const int64_t ctas = static_cast<int64_t>((p.N + BN - 1) / BN) * ((p.M + kBM - 1) / kBM) * p.splits;
   const size_t budget = (ctas <= sm_count() ? 200 : 100) * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
@@ -508,10 +508,10 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
               "(lda=%d ldb=%d)", lda, ldb);
   const bool a_mn = tA != 0;   // A stored [K,M]: M contiguous
   const bool b_mn = tB == 0;   // B stored [K,N]: N contiguous
-  // Tile / split selection.  Measured on B200 (tests/diag_gemm_*.py): a CTA that is alone on its SM
-  // advances ~1 k-block per us whatever the ring depth, while co-resident CTAs each keep that rate, so the
-  // grid should put ~2 CTAs on every SM: 128-wide tiles when they still give >= 1 CTA per SM (half the
-  // L2 re-reads of the A operand), split-K for the very-long-K weight gradients, otherwise 64-wide tiles.
+  // Tile / split selection.  With fp32 operands a 128x128 tile moves 32 KB per k-block for 1 MFLOP (32 FLOP/B) and
+  // the L2 -> SM fabric delivers ~12.5 TB/s, so the wide tile is worth it whenever it still gives every SM a CTA
+  // (most get two: the short-K GEMMs of this model are fill / epilogue bound and want co-resident CTAs);
+  // split-K for the very-long-K weight gradients with few output tiles, otherwise 64-wide tiles.
   // (Splitting K on medium-K shapes was measured slower: the second pass costs more than it saves.)
   const int sms = sm_count();
   const int mt = (M + kBM - 1) / kBM;
