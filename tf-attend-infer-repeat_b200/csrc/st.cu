@@ -12,6 +12,17 @@
 // axis-aligned (air_model.py:324-327, 353-356) so x depends only on the output column and
 // y only on the row; images whose theta has shear/rotation take a per-pixel path in the
 // same kernel.  Output pixels are written coalesced.
+//
+// Kernels in this file:
+//   st_fwd_staged      forward: crop / plain write-back / fused write-back + canvas (one step)
+//   st_compose_steps   fused write-back + canvas for ALL T loop steps in one pass over the canvas
+//   st_bwd_staged      backward: dtheta (+ deterministic dU for axis-aligned theta, smem atomics otherwise),
+//                      also the fused write-back backward with all six dtheta entries
+//   st_wb_bwd_axis     fused write-back backward for the model's axis-aligned theta_inv: warp-specialised
+//                      P / Q run-scans, no atomics, one block barrier
+//   st_fwd_generic / st_bwd_generic   any channel count / size / alignment
+// The *_steps entry points run the T loop steps of an op as one launch (rows [T,B,...] against the one canvas /
+// dCanvas they share), bit-identically to T single-step launches.
 #include <algorithm>
 #include <cstdlib>
 
