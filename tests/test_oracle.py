@@ -285,3 +285,16 @@ def test_synth_oracle_properties():
     more = (im[cnt == 2] > 0).sum(1).mean() > 1.5 * (im[cnt == 1] > 0).sum(1).mean()
     assert more                                                         # two digits -> about twice the ink
 
+
+def test_cnn_frontend_golden(golden_dir):
+    """oracle.cnn_frontend against the committed vector (tests/golden/make_golden_cnn.py): features and the
+    gradients of all six conv tensors."""
+    g = np.load(os.path.join(golden_dir, "cnn.npz"))
+    leaf = {k[2:]: torch.from_numpy(g[k]).requires_grad_(True) for k in g.files if k.startswith("p:")}
+    feat = O.cnn_frontend(torch.from_numpy(g["x"]), leaf)
+    assert tuple(feat.shape) == (3, 1152) and float((feat > 0).float().mean()) > 0.1
+    np.testing.assert_allclose(feat.detach().numpy(), g["features"], rtol=1e-5, atol=1e-6)
+    (feat * torch.from_numpy(g["G"])).sum().backward()
+    for k, v in leaf.items():
+        np.testing.assert_allclose(v.grad.numpy(), g["g:" + k], rtol=1e-4, atol=1e-5, err_msg=k)
+
