@@ -99,3 +99,31 @@ def gemm_seq_fma(A, Bm, Cinit=None, bias=None):
         bias, pb = _f(bias)
     lib().oracle_gemm_seq_fma(pA, pB, pC, pb, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(M), N, K, K, N, N)
     return out
+
+
+def conv5x5_relu_pool(x, w, b, pool):
+    """oracle_conv5x5_relu_pool: x [B,H,W,cin], w [5,5,cin,cout] (HWIO), b [cout] -> [B,H',W',cout]."""
+    x, px = _f(x)
+    w, pw = _f(w)
+    b, pb = _f(b)
+    B, H, W, cin = x.shape
+    cout = w.shape[3]
+    PH, PW = (H // 2, W // 2) if pool else (H, W)
+    out = np.empty((B, PH, PW, cout), np.float32)
+    lib().oracle_conv5x5_relu_pool(px, pw, pb, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(B), H, W, cin, cout, int(pool))
+    return out
+
+
+def conv5x5_relu_pool_bwd(x, w, b, dout, pool, need_dx=True):
+    x, px = _f(x)
+    w, pw = _f(w)
+    b, pb = _f(b)
+    dout, pd = _f(dout)
+    B, H, W, cin = x.shape
+    cout = w.shape[3]
+    dw, db = np.empty_like(w), np.empty_like(b)
+    dx = np.empty_like(x) if need_dx else None
+    lib().oracle_conv5x5_relu_pool_bwd(px, pw, pb, pd, dx.ctypes.data_as(ctypes.c_void_p) if need_dx else None,
+                                       dw.ctypes.data_as(ctypes.c_void_p), db.ctypes.data_as(ctypes.c_void_p),
+                                       ctypes.c_int64(B), H, W, cin, cout, int(pool))
+    return dx, dw, db

@@ -216,3 +216,96 @@ void oracle_gemm_seq_fma(const float *A, const float *Bm, const float *Cinit, co
   }
   free(acc);
 }
+
+/* ---- CNN front-end of AIRModel(cnn=True): air_model.py:510-535 -----------------------------------------------
+ * tf.layers.conv2d(kernel 5x5, strides 1, padding "same", activation relu) optionally followed by
+ * tf.layers.max_pooling2d(pool 2, strides 2, "valid"); NHWC activations, HWIO kernels, 'same' = two zero pixels on
+ * every side for a 5x5 kernel.  Plain loops in (ky, kx, ci) order, multiply and add rounded separately.
+ * Second, independent restatement next to oracle/air_oracle.py::cnn_frontend (which goes through torch's conv2d). */
+static float conv_at(const float *in, const float *w, const float *bias, int H, int W, int cin, int cout, int y, int x,
+                     int co) {
+  float acc = bias[co];
+  for (int ky = 0; ky < 5; ++ky)
+    for (int kx = 0; kx < 5; ++kx) {
+      const int yy = y + ky - 2, xx = x + kx - 2;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      for (int ci = 0; ci < cin; ++ci) {
+        const float prod = in[(yy * W + xx) * cin + ci] * w[((ky * 5 + kx) * cin + ci) * cout + co];
+        acc = acc + prod;
+      }
+    }
+  return acc > 0.0f ? acc : 0.0f; /* relu */
+}
+
+void oracle_conv5x5_relu_pool(const float *in, const float *w, const float *bias, float *out, int64_t B, int H, int W,
+                              int cin, int cout, int pool) {
+  const int PH = pool ? H / 2 : H, PW = pool ? W / 2 : W;
+  for (int64_t b = 0; b < B; ++b) {
+    const float *ib = in + b * H * W * cin;
+    float *ob = out + b * PH * PW * cout;
+    for (int py = 0; py < PH; ++py)
+      for (int px = 0; px < PW; ++px)
+        for (int co = 0; co < cout; ++co) {
+          float m;
+          if (!pool) {
+            m = conv_at(ib, w, bias, H, W, cin, cout, py, px, co);
+          } else {
+            m = conv_at(ib, w, bias, H, W, cin, cout, 2 * py, 2 * px, co);
+            for (int p = 1; p < 4; ++p) {
+              const float v = conv_at(ib, w, bias, H, W, cin, cout, 2 * py + (p >> 1), 2 * px + (p & 1), co);
+              if (v > m) m = v;
+            }
+          }
+          ob[(py * PW + px) * cout + co] = m;
+        }
+  }
+}
+
+/* Backward: ReluGrad (passes where the layer output is > 0), MaxPoolGrad (first maximum of the window in row-major
+ * order), Conv2DBackpropFilter / Conv2DBackpropInput.  dw [5,5,cin,cout], db [cout] and din (if non-NULL) are
+ * overwritten.  Sums are accumulated in double and rounded once (this is a checker, not a bit-level statement). */
+void oracle_conv5x5_relu_pool_bwd(const float *in, const float *w, const float *bias, const float *dout, float *din,
+                                  float *dw, float *db, int64_t B, int H, int W, int cin, int cout, int pool) {
+  const int PH = pool ? H / 2 : H, PW = pool ? W / 2 : W;
+  const int nw = 25 * cin * cout;
+  double *aw = (double *)calloc((size_t)nw + cout, sizeof(double));
+  double *ai = din ? (double *)calloc((size_t)(B * H * W * cin), sizeof(double)) : NULL;
+  for (int64_t b = 0; b < B; ++b) {
+    const float *ib = in + b * H * W * cin;
+    for (int py = 0; py < PH; ++py)
+      for (int px = 0; px < PW; ++px)
+        for (int co = 0; co < cout; ++co) {
+          int y = py, x = px;
+          float m = 0.0f;
+          if (!pool) {
+            m = conv_at(ib, w, bias, H, W, cin, cout, py, px, co);
+          } else {
+            m = conv_at(ib, w, bias, H, W, cin, cout, 2 * py, 2 * px, co);
+            y = 2 * py; x = 2 * px;
+            for (int p = 1; p < 4; ++p) {
+              const float v = conv_at(ib, w, bias, H, W, cin, cout, 2 * py + (p >> 1), 2 * px + (p & 1), co);
+              if (v > m) { m = v; y = 2 * py + (p >> 1); x = 2 * px + (p & 1); }
+            }
+          }
+          if (!(m > 0.0f)) continue;
+          const double g = dout[((b * PH + py) * PW + px) * cout + co];
+          aw[nw + co] += g;
+          for (int ky = 0; ky < 5; ++ky)
+            for (int kx = 0; kx < 5; ++kx) {
+              const int yy = y + ky - 2, xx = x + kx - 2;
+              if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+              for (int ci = 0; ci < cin; ++ci) {
+                aw[((ky * 5 + kx) * cin + ci) * cout + co] += g * ib[(yy * W + xx) * cin + ci];
+                if (ai) ai[((b * H + yy) * W + xx) * cin + ci] += g * w[((ky * 5 + kx) * cin + ci) * cout + co];
+              }
+            }
+        }
+  }
+  for (int e = 0; e < nw; ++e) dw[e] = (float)aw[e];
+  for (int co = 0; co < cout; ++co) db[co] = (float)aw[nw + co];
+  if (ai) {
+    for (int64_t e = 0; e < B * H * W * cin; ++e) din[e] = (float)ai[e];
+    free(ai);
+  }
+  free(aw);
+}

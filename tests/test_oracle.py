@@ -298,3 +298,27 @@ def test_cnn_frontend_golden(golden_dir):
     for k, v in leaf.items():
         np.testing.assert_allclose(v.grad.numpy(), g["g:" + k], rtol=1e-4, atol=1e-5, err_msg=k)
 
+
+
+def test_cnn_c_restatement_agrees_with_torch_restatement(golden_dir):
+    """Second, independent restatement of the cnn=True front-end (oracle/st_oracle.c::oracle_conv5x5_relu_pool*,
+    plain loops) against oracle.cnn_frontend (torch conv2d / autograd) on the committed vector: the three layers
+    chained forward, and the chained backward down to every kernel / bias gradient."""
+    g = np.load(os.path.join(golden_dir, "cnn.npz"))
+    P = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
+    layers = [("cnn/conv1", True), ("cnn/conv2", True), ("cnn/conv3", False)]
+    acts = [g["x"].reshape(3, 50, 50, 1)]
+    for name, pool in layers:
+        acts.append(C.conv5x5_relu_pool(acts[-1], P[name + "/kernel"], P[name + "/bias"], pool))
+    assert acts[1].shape == (3, 25, 25, 8) and acts[2].shape == (3, 12, 12, 8) and acts[3].shape == (3, 12, 12, 8)
+    np.testing.assert_allclose(acts[3].reshape(3, 1152), g["features"], rtol=1e-5, atol=1e-6)
+    d = g["G"].reshape(3, 12, 12, 8)
+    for li in (2, 1, 0):
+        name, pool = layers[li]
+        d, dw, db = C.conv5x5_relu_pool_bwd(acts[li], P[name + "/kernel"], P[name + "/bias"], d, pool, need_dx=li > 0)
+        np.testing.assert_allclose(dw, g["g:" + name + "/kernel"], rtol=1e-4, atol=1e-5, err_msg=name)
+        np.testing.assert_allclose(db, g["g:" + name + "/bias"], rtol=1e-4, atol=1e-5, err_msg=name)
+    # 'same' padding known answer: an all-ones 5x5x1x1 kernel on an all-ones 4x4 image counts the in-range taps
+    ones = C.conv5x5_relu_pool(np.ones((1, 4, 4, 1), np.float32), np.ones((5, 5, 1, 1), np.float32),
+                               np.zeros(1, np.float32), False)[0, :, :, 0]
+    assert np.array_equal(ones, np.outer([3, 4, 4, 3], [3, 4, 4, 3]).astype(np.float32))
