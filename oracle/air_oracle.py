@@ -556,6 +556,7 @@ class AIROracle:
             # extras (not reference attributes) for stage-wise parity
             "z_pres": torch.stack(ta["z_pres"]).t(),
             "stop_masks": torch.stack(ta["stop_masks"]).t(),
+            "stopping_sum": stopping_sum,
             "windows_in": torch.stack(ta["windows_in"]).permute(1, 0, 2),
             "thetas": torch.stack(ta["thetas"]).permute(1, 0, 2, 3),
             "canvas_raw": running_recon,

@@ -1,0 +1,94 @@
+"""Golden vectors produced by EXECUTING THE REFERENCE'S OWN GRAPH (/root/reference/model/air-model.meta, the
+MetaGraphDef training.py:141 saved: train model ``air``, its autodiff gradient graph, clip + ApplyAdam, and the
+test model ``air_1``) with the numpy graph interpreter oracle/tfgraph.  Run in the build container, where
+/root/reference exists:   python tests/golden/make_golden_ref_graph.py
+The fixtures are tests/parity_util.py's (seeded, regenerated at test time), so only outputs are stored."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.tfgraph import air_graph as G, pb            # noqa: E402
+from oracle.tfgraph.interp import Interpreter, run_in_big_stack   # noqa: E402
+from tests import parity_util as PU                      # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SMALL = ("rec_scales", "rec_shifts", "rec_st_back", "rec_latents", "z_pres_probs", "z_pres_kls", "scale_kls", "shift_kls",
+         "vae_kls", "rec_num_digits", "running_loss", "stopping_sum", "reconstruction_loss", "loss_per_item")
+
+
+def st_inputs(B=64, seed=1):
+    """SURVEY 8d microbench poses: s~U(0.3,0.9), x,y~U(-0.5,0.5) -> most canvas pixels fall outside the window."""
+    from oracle import air_oracle as O
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(0.3, 0.9, B).astype(np.float32)
+    x = rng.uniform(-0.5, 0.5, B).astype(np.float32)
+    y = rng.uniform(-0.5, 0.5, B).astype(np.float32)
+    imgs = O.synthetic_canvases(B, seed=0)[0].numpy()
+    rec = rng.uniform(0, 1, (B, 784)).astype(np.float32)
+    return s, x, y, imgs, rec
+
+
+def graph_st(nodes, s, x, y, imgs, rec):
+    """The two transformer() instances of the loop body (air_model.py:322-333, 351-366) evaluated in isolation."""
+    def body():
+        I = Interpreter(nodes, {}, {"pipeline/shuffle_batch:0": imgs, "air/rnn/while/scale/strided_slice:0": s,
+                                    "air/rnn/while/shift/strided_slice:0": x,
+                                    "air/rnn/while/shift/strided_slice_1:0": y,
+                                    "air/rnn/while/vae/gen_sample/Sigmoid:0": rec})
+        return (I.eval("air/rnn/while/st_forward/strided_slice", 0, 0),
+                I.eval("air/rnn/while/st_backward/strided_slice", 0, 0),
+                I.eval("air/rnn/while/st_forward/stack_2", 0, 0), I.eval("air/rnn/while/st_backward/stack_2", 0, 0))
+    return run_in_big_stack(body)
+
+
+def pack_train(out, n=1024):
+    d = {k: out[k] for k in SMALL if k in out}
+    d.update(loss=out["loss"], accuracy=out["accuracy"], executed_steps=np.int32(out["executed_steps"]),
+             global_norm=out["global_norm"], rec_windows_sub=out["rec_windows"][:, :, ::8],
+             reconstruction_sub=out["reconstruction"][:, ::8])
+    for k, g in out["raw_grads"].items():
+        d["g:" + k], d["gn:" + k] = G.digest(g, n)
+    d["clip_scale"] = np.float64(np.linalg.norm(out["clipped_grads"]["rnn/bias"].astype(np.float64)) /
+                                 np.linalg.norm(out["raw_grads"]["rnn/bias"].astype(np.float64)))
+    for k, v in out["new_variables"].items():              # updated variables; Adam slots are implied by them
+        if "/Adam" in k:
+            continue
+        if np.ndim(v):
+            d["v:" + k], d["vn:" + k] = G.digest(v, n)
+        else:
+            d["v:" + k] = np.asarray(v)
+    return d
+
+
+def main():
+    nodes = pb.load_metagraph(G.META)
+    assert nodes[1] == "1.3.0"
+    s, x, y, imgs, rec = st_inputs()
+    win, back, th, thinv = graph_st(nodes, s, x, y, imgs, rec)
+    np.savez_compressed(os.path.join(HERE, "ref_graph_st.npz"), crop=win, back=back, theta=th, theta_inv=thinv)
+
+    imgs, cnt, params, noise = PU.covered_fixture(64, seed=3)
+    out = G.run_train_step(nodes, params, imgs, cnt, noise, global_step=2000)
+    np.savez_compressed(os.path.join(HERE, "ref_graph_train_covered.npz"), **pack_train(out))
+
+    imgs, cnt, params, noise = PU.realistic_fixture(64, seed=1)
+    out = G.run_train_step(nodes, params, imgs, cnt, noise, global_step=2000, float_dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_graph_train_realistic_fp64.npz"), **pack_train(out))
+
+    for name, fx in (("default", PU.default_fixture(64, seed=1)), ("realistic", PU.realistic_fixture(64, seed=2))):
+        imgs, cnt, params, noise = fx
+        out = G.run_test_model(nodes, params, imgs, cnt, noise)
+        d = {k: out[k] for k in SMALL if k in out and k not in ("reconstruction_loss", "loss_per_item")}
+        d.update(accuracy=out["accuracy"], executed_steps=np.int32(out["executed_steps"]),
+                 rec_windows_sub=out["rec_windows"][:, :, ::8])
+        np.savez_compressed(os.path.join(HERE, f"ref_graph_test_{name}.npz"), **d)
+    for f in sorted(os.listdir(HERE)):
+        if f.startswith("ref_graph"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

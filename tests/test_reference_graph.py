@@ -1,0 +1,192 @@
+"""The oracle against the REFERENCE'S OWN GRAPH (no GPU).
+
+tests/golden/ref_graph_*.npz were produced by executing /root/reference/model/air-model.meta -- the MetaGraphDef the
+reference's training.py:141 saved: forward loop, TF's autodiff gradient graph, global-norm clip, ApplyAdam, and the
+test-mode model -- with the numpy graph interpreter in oracle/tfgraph (make_golden_ref_graph.py).  These tests pin
+oracle/air_oracle.py and oracle/st_oracle.c to those outputs; where /root/reference is present (the build container)
+the interpreter is also re-run live against the committed files."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import air_oracle as O
+from oracle import c_oracle as C
+from oracle.tfgraph import air_graph as G
+from oracle.tfgraph import pb
+from oracle.tfgraph.interp import Interpreter, _strided_index
+from tests import parity_util as PU
+from tests.golden import make_golden_ref_graph as MG
+
+HAVE_REF = os.path.exists(G.META)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_st_subgraph_is_bit_exact_with_both_restatements(golden_dir):
+    """transformer() as the reference graph wires it (crop 50x50->28x28 and write-back 28x28->50x50, microbench
+    poses, ~11 % of the write-back pixels are non-zero out-of-range rounding residues): the C and the torch
+    restatements reproduce it BIT FOR BIT, theta and theta^-1 (three separate divisions) included."""
+    g = _g(golden_dir, "ref_graph_st.npz")
+    s, x, y, imgs, rec = MG.st_inputs()
+    B, z = len(s), np.zeros_like(s)
+    th = np.stack([s, z, x, z, s, y], 1)
+    ti = np.stack([1 / s, z, -x / s, z, 1 / s, -y / s], 1).astype(np.float32)
+    assert np.array_equal(g["theta"].reshape(B, 6), th) and np.array_equal(g["theta_inv"].reshape(B, 6), ti)
+    assert np.array_equal(C.st_forward(imgs.reshape(B, 50, 50, 1), th, (28, 28))[..., 0], g["crop"])
+    assert np.array_equal(C.st_forward(rec.reshape(B, 28, 28, 1), ti, (50, 50))[..., 0], g["back"])
+    t = O.transformer(torch.from_numpy(imgs.reshape(B, 50, 50, 1)), torch.from_numpy(th), (28, 28)).numpy()[..., 0]
+    assert np.array_equal(t, g["crop"])
+    t = O.transformer(torch.from_numpy(rec.reshape(B, 28, 28, 1)), torch.from_numpy(ti), (50, 50)).numpy()[..., 0]
+    assert np.array_equal(t, g["back"])
+    residues = (np.abs(g["back"]) < 1e-5) & (g["back"] != 0)
+    assert residues.mean() > 0.05                         # the fixture does exercise the residue arithmetic
+
+
+def _check_per_step(out, g, tol):
+    for k in ("rec_scales", "rec_shifts", "rec_st_back", "z_pres_probs", "z_pres_kls", "scale_kls", "shift_kls",
+              "vae_kls", "running_loss"):
+        assert _rel(out[k].numpy().reshape(g[k].shape), g[k]) < tol, (k, _rel(out[k].numpy().reshape(g[k].shape), g[k]))
+    assert _rel(out["rec_windows"].numpy()[:, :, ::8], g["rec_windows_sub"]) < tol
+    assert np.array_equal(out["rec_num_digits"].numpy(), g["rec_num_digits"])
+    assert out["executed_steps"] == int(g["executed_steps"])
+    assert float(out["accuracy"]) == pytest.approx(float(g["accuracy"]), abs=1e-7)
+
+
+def test_train_step_fp32_covered_fixture(golden_dir):
+    """One sess.run(model.training) of the reference graph on the covered fixture (the one the GPU gradient-parity
+    test uses): loss, per-step outputs, all 36 raw gradients, the global norm, the clip factor and the Adam-updated
+    variables of the oracle agree with the graph's."""
+    g = _g(golden_dir, "ref_graph_train_covered.npz")
+    imgs, cnt, params, noise = PU.covered_fixture(64, seed=3)
+    orc = O.AIROracle(params={k: v.clone() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING)
+    orc.global_step = 2000
+    out, clipped = orc.train_step(imgs, cnt, noise)
+    assert abs(float(out["loss"]) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    _check_per_step(out, g, 1e-6)
+    assert _rel(out["reconstruction_loss"].numpy(), g["reconstruction_loss"]) < 1e-6
+    assert _rel(out["reconstruction"].numpy()[:, ::8], g["reconstruction_sub"]) < 1e-6
+    assert float(out["grad_global_norm"]) == pytest.approx(float(g["global_norm"]), rel=1e-5)
+    scale = float(g["clip_scale"])
+    for k, c in clipped.items():                           # train_step returns the clipped gradients
+        sample, norm = G.digest(c.numpy(), 1024)
+        assert _rel(sample, g["g:" + k] * scale) < 1e-5, k
+        assert norm == pytest.approx(float(g["gn:" + k]) * scale, rel=1e-5), k
+    for k, v in orc.params.items():                        # ApplyAdam: compare the parameter UPDATE, not the value
+        sample, _ = G.digest(v.numpy(), 1024)
+        before, _ = G.digest(params[k].numpy(), 1024)
+        want = g["v:air/rnn/" + k] - before
+        assert _rel(sample - before, want) < 2e-3, (k, _rel(sample - before, want))   # fp32 difference of near-equal numbers
+    assert int(g["v:air/global_step"]) == orc.global_step == 2001
+    assert float(orc.beta1_power) == float(g["v:air/training/beta1_power"])
+    assert float(orc.beta2_power) == float(g["v:air/training/beta2_power"])
+
+
+def test_train_step_fp64_realistic_poses(golden_dir):
+    """Same graph evaluated in fp64 (constants widened to the decimal literals) on realistic poses -- dead steps,
+    windows smaller than the canvas, clipping active.  In fp64 the out-of-range residues (~1e-17) are far below the
+    1e-9 epsilon of the loss, so structure is compared without the fp32 residue noise."""
+    g = _g(golden_dir, "ref_graph_train_realistic_fp64.npz")
+    imgs, cnt, params, noise = PU.realistic_fixture(64, seed=1)
+    orc = O.AIROracle(params={k: v.double() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING,
+                      dtype=torch.float64)
+    orc.global_step = 2000
+    out, grads = orc.loss_and_grads(imgs.double(), cnt, {k: v.double() for k, v in noise.items()})
+    assert abs(float(out["loss"]) - float(g["loss"])) <= 1e-8 * abs(float(g["loss"]))
+    _check_per_step(out, g, 1e-6)
+    assert len(np.unique(g["rec_num_digits"])) >= 3       # some items stop after 1 or 2 steps
+    for k, v in grads.items():
+        sample, norm = G.digest(v.numpy(), 1024)
+        assert _rel(sample, g["g:" + k]) < 1e-4, (k, _rel(sample, g["g:" + k]))
+        assert norm == pytest.approx(float(g["gn:" + k]), rel=1e-4), k
+
+
+@pytest.mark.parametrize("name,fixture,seed", [("default", PU.default_fixture, 1), ("realistic", PU.realistic_fixture, 2)])
+def test_test_mode_graph(golden_dir, name, fixture, seed):
+    """The ``air_1`` model (train=False: tf.round on z_pres): digit counts and stopping sums bit-exact, every
+    per-step output within 1e-5 (summation order of the GEMMs is the only difference)."""
+    g = _g(golden_dir, f"ref_graph_test_{name}.npz")
+    imgs, cnt, params, noise = fixture(64, seed=seed)
+    orc = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False)
+    out = orc.forward(imgs, cnt, noise)
+    _check_per_step(out, g, 1e-5)
+    if "stopping_sum" in out:
+        assert np.array_equal(out["stopping_sum"].numpy(), g["stopping_sum"])
+    assert len(np.unique(g["rec_num_digits"])) >= 3
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
+def test_interpreter_reproduces_committed_goldens_live(golden_dir):
+    nodes = pb.load_metagraph(G.META)
+    assert nodes[1] == "1.3.0" and len(nodes[0]) == 15022
+    s, x, y, imgs, rec = MG.st_inputs()
+    win, back, _, _ = MG.graph_st(nodes, s, x, y, imgs, rec)
+    g = _g(golden_dir, "ref_graph_st.npz")
+    assert np.array_equal(win, g["crop"]) and np.array_equal(back, g["back"])
+    imgs, cnt, params, noise = PU.covered_fixture(64, seed=3)
+    out = G.run_train_step(nodes, params, imgs, cnt, noise, global_step=2000)
+    g = _g(golden_dir, "ref_graph_train_covered.npz")
+    assert float(out["loss"]) == float(g["loss"]) and out["executed_steps"] == 3
+    assert np.array_equal(G.digest(out["raw_grads"]["rnn/kernel"], 1024)[0], g["g:rnn/kernel"])
+    assert out["noise_used"] == {(k, t) for k in ("scale", "shift", "vae_latent", "vae_like", "concrete_u")
+                                 for t in range(3)}
+
+
+def test_interpreter_pieces():
+    """Unit checks of the interpreter's own machinery on hand-built graphs: a while loop with a stack-based
+    'gradient' loop, StridedSlice masks, BroadcastGradientArgs."""
+    class N:
+        def __init__(self, name, op, inputs=(), ctrl=(), **attr):
+            self.name, self.op, self.ctrl, self.attr = name, op, list(ctrl), attr
+            self.inputs = [(i.partition(":")[0], int(i.partition(":")[2] or 0)) for i in inputs]
+    c = lambda name, v: N(name, "Const", value=np.asarray(v))                       # noqa: E731
+    fr = dict(frame_name=b"f")
+    nodes = [c("zero", np.int32(0)), c("one", np.int32(1)), c("n", np.int32(4)), c("x0", np.float32(1.5)),
+             N("stk", "Stack"),
+             N("e_i", "Enter", ["zero"], **fr), N("e_x", "Enter", ["x0"], **fr), N("e_n", "Enter", ["n"], **fr),
+             N("e_one", "Enter", ["one"], **fr), N("e_s", "RefEnter", ["stk"], **fr),
+             N("m_i", "Merge", ["e_i", "nx_i"]), N("m_x", "Merge", ["e_x", "nx_x"]),
+             N("lt", "Less", ["m_i", "e_n"]), N("lc", "LoopCond", ["lt"]),
+             N("s_i", "Switch", ["m_i", "lc"]), N("s_x", "Switch", ["m_x", "lc"]),
+             N("id_i", "Identity", ["s_i:1"]), N("id_x", "Identity", ["s_x:1"]),
+             N("push", "StackPush", ["e_s", "id_x"]),
+             N("add", "Add", ["id_i", "e_one"], ctrl=["push"]), N("sq", "Mul", ["id_x", "id_x"]),
+             N("nx_i", "NextIteration", ["add"]), N("nx_x", "NextIteration", ["sq"]),
+             N("x_i", "Exit", ["s_i"]), N("x_x", "Exit", ["s_x"])]
+    # second loop: pops the stashed x values in reverse and multiplies 2*x into an accumulator (d/dx0 of x^(2^n))
+    fb = dict(frame_name=b"b")
+    nodes += [c("onef", np.float32(1.0)), c("two", np.float32(2.0)),
+              N("b_c", "Enter", ["x_i"], **fb), N("b_g", "Enter", ["onef"], **fb), N("b_s", "RefEnter", ["stk"], **fb),
+              N("b_two", "Enter", ["two"], **fb), N("b_one", "Enter", ["one"], **fb),
+              N("bm_c", "Merge", ["b_c", "bn_c"]), N("bm_g", "Merge", ["b_g", "bn_g"]),
+              N("ge", "GreaterEqual", ["bm_c", "b_one"]), N("blc", "LoopCond", ["ge"]),
+              N("bs_c", "Switch", ["bm_c", "blc"]), N("bs_g", "Switch", ["bm_g", "blc"]),
+              N("bi_c", "Identity", ["bs_c:1"]), N("bi_g", "Identity", ["bs_g:1"]),
+              N("pop", "StackPop", ["b_s"], ctrl=["bi_c"]), N("tx", "Mul", ["b_two", "pop"]),
+              N("g2", "Mul", ["bi_g", "tx"]), N("dec", "Sub", ["bi_c", "b_one"]),
+              N("bn_c", "NextIteration", ["dec"]), N("bn_g", "NextIteration", ["g2"]),
+              N("bx_g", "Exit", ["bs_g"])]
+    I = Interpreter(({n.name: n for n in nodes}, "unit"))
+    assert int(I.fetch("x_i")) == 4 and float(I.fetch("x_x")) == pytest.approx(1.5 ** 16)
+    assert float(I.fetch("bx_g")) == pytest.approx(16 * 1.5 ** 15)      # d/dx x^16
+    assert I.trip_count("f") == 4 and I.trip_count("b") == 4
+
+    a = np.arange(24).reshape(2, 3, 4)
+    at = dict(begin_mask=0, end_mask=0, ellipsis_mask=0, new_axis_mask=0, shrink_axis_mask=0)
+    assert np.array_equal(a[_strided_index(a.shape, [0, 1, 0], [2, 3, 4], [1, 1, 2], at)], a[0:2, 1:3, 0:4:2])
+    assert np.array_equal(a[_strided_index(a.shape, [0, 2], [0, 3], [1, 1], dict(at, begin_mask=1, end_mask=1, shrink_axis_mask=2))],
+                          a[:, 2])
+    assert np.array_equal(a[_strided_index(a.shape, [0, 1], [0, 2], [1, 1], dict(at, ellipsis_mask=1, shrink_axis_mask=2))],
+                          a[..., 1])
+    r0, r1 = I.op_BroadcastGradientArgs(None, None, np.array([64, 1]), np.array([64, 784]))
+    assert list(r0) == [1] and list(r1) == []
+    r0, r1 = I.op_BroadcastGradientArgs(None, None, np.array([], np.int32), np.array([64]))
+    assert list(r0) == [0] and list(r1) == []
