@@ -66,6 +66,20 @@ def _common_fetches(I, scope, nodes):
     return out
 
 
+def scalar_summaries(I, scope):
+    """Every tf.summary.scalar of the model (air_model.py:160-209, 613-625): tag (scope prefix stripped) -> value."""
+    out = {}
+    with np.errstate(all="ignore"):                        # means over empty selections are NaN, as in TF
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for nd in I.nodes.values():
+                if nd.op == "ScalarSummary" and nd.name.startswith(scope + "/"):
+                    tag = I.nodes[nd.inputs[0][0]].attr["value"].ravel()[0].decode()
+                    out[tag[len(scope) + len("/summaries/"):]] = float(I.eval(*nd.inputs[1], None))
+    return out
+
+
 def run_train_step(nodes, params, images, num_digits, noise, float_dtype=np.float32, **var_kwargs):
     """One ``sess.run([model.training, loss, accuracy, ...])`` of the reference's train graph.  Returns a dict with
     loss, accuracy, per-step outputs, raw gradients (inputs of the L2Loss ops of clip_by_global_norm), clipped
@@ -116,6 +130,7 @@ def run_test_model(nodes, params, images, num_digits, noise, float_dtype=np.floa
         out["loss"] = I.fetch("air_1/summaries/loss")
         out["accuracy"] = I.fetch("air_1/summaries/accuracy")
         out["executed_steps"] = I.trip_count("air_1/rnn/while/air_1/rnn/while/")
+        out["summaries"] = scalar_summaries(I, "air_1")
         return out
     return run_in_big_stack(body)
 

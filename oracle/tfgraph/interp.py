@@ -505,6 +505,9 @@ class Interpreter:
     def op_Gather(self, nd, it, params, indices):
         return np.take(params, indices, axis=0)
 
+    def op_Where(self, nd, it, c):
+        return np.argwhere(c).astype(np.int64)
+
     def op_UnsortedSegmentSum(self, nd, it, data, ids, num):
         out = np.zeros((int(num),) + data.shape[ids.ndim:], data.dtype)
         np.add.at(out, ids, data)                       # unbuffered, sequential in index order

@@ -3,6 +3,7 @@ MetaGraphDef training.py:141 saved: train model ``air``, its autodiff gradient g
 test model ``air_1``) with the numpy graph interpreter oracle/tfgraph.  Run in the build container, where
 /root/reference exists:   python tests/golden/make_golden_ref_graph.py
 The fixtures are tests/parity_util.py's (seeded, regenerated at test time), so only outputs are stored."""
+import json
 import os
 import sys
 
@@ -81,8 +82,8 @@ def main():
     for name, fx in (("default", PU.default_fixture(64, seed=1)), ("realistic", PU.realistic_fixture(64, seed=2))):
         imgs, cnt, params, noise = fx
         out = G.run_test_model(nodes, params, imgs, cnt, noise)
-        d = {k: out[k] for k in SMALL if k in out and k not in ("reconstruction_loss", "loss_per_item")}
-        d.update(accuracy=out["accuracy"], executed_steps=np.int32(out["executed_steps"]),
+        d = {k: out[k] for k in SMALL if k in out}
+        d.update(summaries=np.array(json.dumps(out["summaries"])), accuracy=out["accuracy"], executed_steps=np.int32(out["executed_steps"]),
                  rec_windows_sub=out["rec_windows"][:, :, ::8])
         np.savez_compressed(os.path.join(HERE, f"ref_graph_test_{name}.npz"), **d)
     for f in sorted(os.listdir(HERE)):
