@@ -4,12 +4,17 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this module.  The product path
 (``tf-attend-infer-repeat_b200``) never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference (aakhundov/tf-attend-infer-repeat) is TensorFlow-1.3
-graph code; TensorFlow is not installable here and the reference ships no tests, golden
-vectors or fixtures.  This file therefore *defines* "the
-reference's result" as an op-for-op restatement: one torch CPU op per TF op, fp32, so
-every intermediate is rounded exactly where TF's op-at-a-time executor rounds it (no
-FMA contraction).  TF-library semantics that cannot be read from the reference tree
+PARITY PIN: the reference (aakhundov/tf-attend-infer-repeat) is TensorFlow-1.3 graph code;
+TensorFlow is not installable here and the reference ships no tests, golden vectors or
+fixtures.  This file is an op-for-op restatement: one torch CPU
+op per TF op, fp32, so every intermediate is rounded exactly where TF's op-at-a-time
+executor rounds it (no FMA contraction).  It is pinned against the reference's OWN
+serialized graph (model/air-model.meta: forward loop, autodiff gradient graph, clip,
+ApplyAdam, test model) executed by the numpy graph interpreter in oracle/tfgraph --
+tests/test_reference_graph.py: ST bit-exact, loss identical, 36 gradients <= 7e-7 on the
+covered fixture, fp64 agreement on realistic poses.  TensorFlow's own kernels never ran:
+the per-op arithmetic of that interpreter is itself restated.  The
+cnn=True front-end is not part of the saved graph and stays restated-only.  TF-library semantics that cannot be read from the reference tree
 (LSTM gate order, softplus thresholds, Adam epsilon placement ...) are restated from the
 published TF 1.3 behaviour and are listed in SURVEY.md section 8(c).
 

@@ -2,9 +2,12 @@
  * AIR hot path.  TEST INFRASTRUCTURE, NOT PRODUCT CODE: only tests/, smoke() and
  * bench.py's cpu_baseline leg may load this library.
  *
- * PARITY UNPINNED (see oracle/air_oracle.py header): TensorFlow cannot run here and the
- * reference has no golden vectors; this file is a second, independent restatement of
- * the same reference lines, used to cross-check the torch oracle bit-for-bit.
+ * PARITY PIN (see oracle/air_oracle.py header): TensorFlow cannot run here and the reference
+ * has no golden vectors; this file is a second, independent restatement of the same
+ * reference lines, used to cross-check the torch oracle bit-for-bit.  The ST forward of
+ * this file reproduces the reference's own graph (model/air-model.meta run by
+ * oracle/tfgraph) bit for bit: tests/test_reference_graph.py.  The cnn front-end at the
+ * end of the file is not in that graph and is restated-only.
  *
  * Build with -ffp-contract=off: TF 1.3 executes one op at a time, so every product and
  * sum below is rounded separately (no FMA), except oracle_gemm_seq_fma which *defines*

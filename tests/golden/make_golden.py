@@ -1,7 +1,7 @@
 """Generates the committed golden vectors under tests/golden/ from the CPU oracle.
 
-PARITY UNPINNED: the reference (TensorFlow 1.3) cannot run here and ships no vectors, so
-these fixtures are outputs of oracle/air_oracle.py, cross-checked bit-for-bit against the
+The reference (TensorFlow 1.3) cannot run here and ships no vectors; these fixtures are outputs of
+oracle/air_oracle.py (itself pinned to the reference's graph by make_golden_ref_graph.py), cross-checked bit-for-bit against the
 independent C restatement oracle/st_oracle.c at generation time.  They pin the oracle
 (regression) and give the GPU tests inputs/outputs that do not depend on /root/reference
 or on re-running the oracle.

@@ -1,6 +1,7 @@
 """Golden vector of the CNN front-end restatement (oracle.cnn_frontend, air_model.py:510-535): inputs, the six
 conv tensors, the [B,1152] feature map and the parameter gradients of a fixed linear functional of it.
-PARITY UNPINNED (see make_golden.py): an oracle regression pin, not a TensorFlow output.
+PARITY UNPINNED for this part: the cnn=True front-end is not in the reference's saved graph, so this is an oracle
+regression pin (torch conv2d, cross-checked against plain-C loops), not a reference output.
 
     python tests/golden/make_golden_cnn.py
 """

@@ -1,6 +1,6 @@
 """CPU tests pinning the oracle (no GPU): golden vectors, cross-restatement agreement,
-known-answer cases, fp64 finite differences.  Parity against TensorFlow itself is
-UNPINNED (TF cannot run here; see oracle/air_oracle.py)."""
+known-answer cases, fp64 finite differences.  TensorFlow cannot run here; the pin against
+the reference's own graph is tests/test_reference_graph.py."""
 import os
 
 import numpy as np
