@@ -131,6 +131,8 @@ def run_test_model(nodes, params, images, num_digits, noise, float_dtype=np.floa
         out["accuracy"] = I.fetch("air_1/summaries/accuracy")
         out["executed_steps"] = I.trip_count("air_1/rnn/while/air_1/rnn/while/")
         out["summaries"] = scalar_summaries(I, "air_1")
+        # input of tf.summary.image("reconstruction", ...) (air_model.py:211-267, 627-640): [60, 100, 204, 3]
+        out["reconstruction_image"] = I.fetch("air_1/summaries/concat_2")
         return out
     return run_in_big_stack(body)
 

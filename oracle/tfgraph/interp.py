@@ -505,6 +505,56 @@ class Interpreter:
     def op_Gather(self, nd, it, params, indices):
         return np.take(params, indices, axis=0)
 
+    def op_ResizeBilinear(self, nd, it, x, size):
+        """resize_bilinear_op.cc (TF 1.3): in = out_index * (in_size / out_size) (align_corners false), lower =
+        floor(in), upper = min(lower + 1, in_size - 1), lerp = in - lower; rows are interpolated along x first
+        (top, bottom), then along y, each as a + (b - a) * lerp."""
+        assert not nd.attr.get("align_corners")
+        oh, ow = int(size[0]), int(size[1])
+        B, H, W, C = x.shape
+
+        def axis(n_in, n_out):
+            scale = f32(n_in) / f32(n_out)
+            src = np.arange(n_out, dtype=f32) * scale
+            lo = np.floor(src).astype(np.int64)
+            return lo, np.minimum(lo + 1, n_in - 1), (src - lo.astype(f32)).astype(x.dtype)
+        y0, y1, ly = axis(H, oh)
+        x0, x1, lx = axis(W, ow)
+        lx = lx[None, None, :, None]
+        ly = ly[None, :, None, None]
+        tl, tr = x[:, y0][:, :, x0], x[:, y0][:, :, x1]
+        bl, br = x[:, y1][:, :, x0], x[:, y1][:, :, x1]
+        top = tl + (tr - tl) * lx
+        bottom = bl + (br - bl) * lx
+        return top + (bottom - top) * ly
+
+    def op_DrawBoundingBoxes(self, nd, it, images, boxes):
+        """draw_bounding_box_op.cc (TF 1.3): box (ymin, xmin, ymax, xmax) in [0,1] -> rows/cols * (size - 1); the
+        four border lines are painted with colour table entry (box index % 10); the first entry is yellow
+        (1, 1, 0, 1), of which a 1-channel image takes the first component."""
+        table = [(1, 1, 0, 1), (0, 0, 1, 1), (1, 0, 0, 1), (0, 1, 0, 1), (0.5, 0, 0.5, 1), (0.5, 0.5, 0, 1),
+                 (0.5, 0, 0, 1), (0, 0, 0.5, 1), (0, 1, 1, 1), (1, 0, 1, 1)]
+        out = images.copy()
+        B, H, W, C = out.shape
+        for b in range(B):
+            for bb in range(boxes.shape[1]):
+                col = np.array(table[bb % 10][:C], out.dtype)
+                ymin, xmin, ymax, xmax = (float(v) for v in boxes[b, bb])
+                r0, r1 = int(ymin * (H - 1)), int(ymax * (H - 1))
+                c0, c1 = int(xmin * (W - 1)), int(xmax * (W - 1))
+                if r0 > r1 or c0 > c1 or r0 >= H or r1 < 0 or c0 >= W or c1 < 0:
+                    continue
+                rr0, rr1, cc0, cc1 = max(r0, 0), min(r1, H - 1), max(c0, 0), min(c1, W - 1)
+                if r0 >= 0:
+                    out[b, r0, cc0:cc1 + 1] = col
+                if r1 < H:
+                    out[b, r1, cc0:cc1 + 1] = col
+                if c0 >= 0:
+                    out[b, rr0:rr1 + 1, c0] = col
+                if c1 < W:
+                    out[b, rr0:rr1 + 1, c1] = col
+        return out
+
     def op_Where(self, nd, it, c):
         return np.argwhere(c).astype(np.int64)
 

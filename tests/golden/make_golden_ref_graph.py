@@ -3,6 +3,7 @@ MetaGraphDef training.py:141 saved: train model ``air``, its autodiff gradient g
 test model ``air_1``) with the numpy graph interpreter oracle/tfgraph.  Run in the build container, where
 /root/reference exists:   python tests/golden/make_golden_ref_graph.py
 The fixtures are tests/parity_util.py's (seeded, regenerated at test time), so only outputs are stored."""
+import hashlib
 import json
 import os
 import sys
@@ -86,6 +87,14 @@ def main():
         d.update(summaries=np.array(json.dumps(out["summaries"])), accuracy=out["accuracy"], executed_steps=np.int32(out["executed_steps"]),
                  rec_windows_sub=out["rec_windows"][:, :, ::8])
         np.savez_compressed(os.path.join(HERE, f"ref_graph_test_{name}.npz"), **d)
+        if name == "realistic":
+            # the tensor behind tf.summary.image("reconstruction") (air_model.py:211-267) with its inputs, first 12
+            # images: 4 stored in full, all 12 as SHA-256 of the float32 bytes (the computation is bit-reproducible)
+            im = out["reconstruction_image"][:12]
+            np.savez_compressed(os.path.join(HERE, "ref_graph_vis.npz"), reconstruction=out["reconstruction"][:12],
+                                rec_st_back=out["rec_st_back"][:12], rec_num_digits=out["rec_num_digits"][:12],
+                                image_full=im[:4],
+                                sha256=np.array([hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in im]))
     for f in sorted(os.listdir(HERE)):
         if f.startswith("ref_graph"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -74,3 +74,14 @@ def test_test_mode_against_reference_graph(golden_dir, name, fixture, seed):
     _, m = make_pair(imgs, cnt, params, train=False)
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
+
+
+def test_reconstruction_image_summary_bit_exact_on_device(golden_dir):
+    """air_model.py:211-267 through the CUDA write-back ST (28x28 frames -> 100x100, the generic-size kernel path)."""
+    import hashlib
+    g = _g(golden_dir, "ref_graph_vis.npz")
+    imgs = realistic_fixture(64, seed=2)[0][:12].cuda()
+    got = ab.visualize_reconstructions(imgs, _cu(g["reconstruction"]), _cu(g["rec_st_back"]), _cu(g["rec_num_digits"]))
+    got = got.cpu().numpy()
+    assert np.array_equal(got[:4], g["image_full"])
+    assert [hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in got] == list(g["sha256"])

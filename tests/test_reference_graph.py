@@ -220,3 +220,25 @@ def test_annealing_schedule_bit_exact_with_graph():
         if nodes is not None:
             live = Interpreter(nodes, {"air/global_step": np.int32(gs)}).fetch("air/z_pres_prior_log_odds_log")
             assert np.float32(live) == want, gs
+
+
+def test_reconstruction_image_summary_bit_exact(golden_dir):
+    """demo/visualize.py (resize x2, window frames through the write-back ST with rec_st_back, R/G/B per step) equals
+    the tensor the reference graph feeds to tf.summary.image("reconstruction") bit for bit; the ST is the oracle's
+    here and the CUDA kernel's in tests/test_gpu_zz_reference_graph.py."""
+    import hashlib
+    import air_b200 as ab
+    g = _g(golden_dir, "ref_graph_vis.npz")
+    imgs = PU.realistic_fixture(64, seed=2)[0][:12]
+    got = ab.visualize_reconstructions(imgs, torch.from_numpy(g["reconstruction"]), torch.from_numpy(g["rec_st_back"]),
+                                       torch.from_numpy(g["rec_num_digits"]), transformer=O.transformer).numpy()
+    assert got.shape == (12, 100, 204, 3) and got.min() == 0.0 and got.max() == 1.0
+    assert np.array_equal(got[:4], g["image_full"])
+    assert [hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in got] == list(g["sha256"])
+    assert len(set(g["rec_num_digits"].tolist())) >= 3       # frames of 0, 1, 2 and 3 executed steps are all drawn
+    # fewer executed steps than max_steps: the missing matrices are zero-padded (air_model.py:227-231)
+    short = ab.visualize_reconstructions(imgs, torch.from_numpy(g["reconstruction"]),
+                                         torch.from_numpy(g["rec_st_back"][:, :1]),
+                                         torch.clamp(torch.from_numpy(g["rec_num_digits"]), max=1),
+                                         transformer=O.transformer)
+    assert short.shape == (12, 100, 204, 3) and not torch.equal(short, torch.from_numpy(got))

@@ -14,9 +14,10 @@ from .air.air_model import AIRModel, reset_variable_scopes
 from .air.params import ParamStore
 from . import checkpoint, dp, ops, tfrecords
 from .demo.model_wrapper import ModelWrapper, evaluation_summaries
+from .demo.visualize import visualize_reconstructions, draw_colored_bounding_boxes
 from .air.concrete import (concrete_binary_sample, concrete_binary_pre_sigmoid_sample,
                            concrete_binary_kl_mc_sample, concrete_step)
 
-__all__ = ["AIRModel", "ModelWrapper", "evaluation_summaries", "checkpoint", "vae", "ParamStore", "ops", "reset_variable_scopes", "transformer", "batch_transformer", "writeback_canvas", "concrete_binary_sample",
+__all__ = ["AIRModel", "ModelWrapper", "evaluation_summaries", "visualize_reconstructions", "draw_colored_bounding_boxes", "checkpoint", "vae", "ParamStore", "ops", "reset_variable_scopes", "transformer", "batch_transformer", "writeback_canvas", "concrete_binary_sample",
            "concrete_binary_pre_sigmoid_sample", "concrete_binary_kl_mc_sample", "concrete_step",
            "AirError", "build", "launch_count"]
