@@ -71,7 +71,7 @@ def test_test_mode_against_reference_graph(golden_dir, name, fixture, seed):
     <= 1e-5 (the canvas-derived loss is excluded on these uncovered fixtures)."""
     g = _g(golden_dir, f"ref_graph_test_{name}.npz")
     imgs, cnt, params, noise = fixture(64, seed=seed)
-    _, m = make_pair(imgs, cnt, params, train=False)
+    _, m = make_pair(imgs, cnt, params, train=False, global_step=0)      # the golden run used global_step 0
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
 

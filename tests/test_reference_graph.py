@@ -242,3 +242,46 @@ def test_reconstruction_image_summary_bit_exact(golden_dir):
                                          torch.clamp(torch.from_numpy(g["rec_num_digits"]), max=1),
                                          transformer=O.transformer)
     assert short.shape == (12, 100, 204, 3) and not torch.equal(short, torch.from_numpy(got))
+
+
+def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypatch):
+    """The GPU tests of tests/test_gpu_zz_reference_graph.py, run here with the CUDA model replaced by an
+    oracle-backed stand-in: proves that their fixtures, global steps, attribute names and tolerances are consistent
+    with the committed vectors before they ever reach a GPU box."""
+    import types
+    import tests.test_gpu_zz_reference_graph as T
+
+    class Stand:
+        def __init__(self, orc, imgs, cnt):
+            self.orc, self.imgs, self.cnt = orc, imgs, cnt
+            self.store = types.SimpleNamespace(named_grads=lambda: self.grads)
+
+        def _take(self, out):
+            for k, v in out.items():
+                setattr(self, k, v)
+
+        def loss_and_grads(self, noise):
+            out, self.grads = self.orc.loss_and_grads(self.imgs, self.cnt, noise)
+            self._take(out)
+
+        def run(self, noise):
+            self._take(self.orc.forward(self.imgs, self.cnt, noise))
+
+    def make_pair(imgs, cnt, params, train=True, global_step=2000, **kw):
+        orc = O.AIROracle(params={k: v.clone() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING,
+                          train=train)
+        orc.global_step = global_step
+        return orc, Stand(orc, imgs, cnt)
+
+    monkeypatch.setattr(T, "make_pair", make_pair)
+    monkeypatch.setattr(T, "cuda_noise", lambda n: n)
+    monkeypatch.setattr(T, "_cu", lambda a: torch.from_numpy(np.ascontiguousarray(a)))
+    monkeypatch.setattr(T.ab, "transformer", O.transformer)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    T.test_st_kernels_bit_exact_with_reference_graph(golden_dir)
+    T.test_train_step_against_reference_graph(golden_dir)
+    T.test_test_mode_against_reference_graph(golden_dir, "default", PU.default_fixture, 1)
+    T.test_test_mode_against_reference_graph(golden_dir, "realistic", PU.realistic_fixture, 2)
+    orig = T.ab.visualize_reconstructions
+    monkeypatch.setattr(T.ab, "visualize_reconstructions", lambda *a, **k: orig(*a, transformer=O.transformer, **k))
+    T.test_reconstruction_image_summary_bit_exact_on_device(golden_dir)
