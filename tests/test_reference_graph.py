@@ -285,3 +285,32 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
     orig = T.ab.visualize_reconstructions
     monkeypatch.setattr(T.ab, "visualize_reconstructions", lambda *a, **k: orig(*a, transformer=O.transformer, **k))
     T.test_reconstruction_image_summary_bit_exact_on_device(golden_dir)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
+def test_three_consecutive_train_steps_follow_the_graph():
+    """sess.run(model.training) three times, variables / Adam slots / beta powers / global_step carried from one run
+    of the graph to the next, fresh noise per step: the oracle's losses follow to 1e-6 and its accumulated parameter
+    movement to 2e-4 of that movement (annealed prior, clip, ApplyAdam and the beta-power updates all in the loop)."""
+    nodes = pb.load_metagraph(G.META)
+    imgs, cnt, params, _ = PU.covered_fixture(64, seed=5)
+    orc = O.AIROracle(params={k: v.clone() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING)
+    P = {k: v.numpy().copy() for k, v in params.items()}
+    state = dict(adam_m=None, adam_v=None, global_step=0, beta1_power=np.float32(0.9), beta2_power=np.float32(0.999))
+    for step in range(3):
+        nz = O.make_noise(100 + step, 3, 64)
+        nv = (out := G.run_train_step(nodes, P, imgs, cnt, nz, **state))["new_variables"]
+        P = {k: nv["air/rnn/" + k] for k in P}
+        state = dict(adam_m={k: nv[f"air/training/air/rnn/{k}/Adam"] for k in P},
+                     adam_v={k: nv[f"air/training/air/rnn/{k}/Adam_1"] for k in P},
+                     global_step=int(nv["air/global_step"]), beta1_power=nv["air/training/beta1_power"],
+                     beta2_power=nv["air/training/beta2_power"])
+        o, _ = orc.train_step(imgs, cnt, nz)
+        assert abs(float(o["loss"]) - float(out["loss"])) <= 1e-6 * abs(float(out["loss"]))
+        assert state["global_step"] == orc.global_step == step + 1
+        assert float(state["beta1_power"]) == float(orc.beta1_power)
+        assert float(state["beta2_power"]) == float(orc.beta2_power)
+        for k in P:
+            moved = np.linalg.norm(P[k] - params[k].numpy())
+            if moved > 0:
+                assert np.linalg.norm(P[k] - orc.params[k].numpy()) <= 2e-4 * moved, (step, k)
