@@ -60,6 +60,9 @@ def _common_fetches(I, scope, nodes):
            "reconstruction": I.fetch(f"{scope}/loss/reconstruction/clipped_rec"),
            "reconstruction_loss": I.fetch(f"{scope}/loss/reconstruction/Neg"),
            "loss_per_item": I.fetch(f"{scope}/add_1")}
+    # per-step stop mask ``stopping_sum_new < threshold`` (air_model.py:427-439): an in-loop tensor, one per iteration
+    trip = I.trip_count(f"{scope}/rnn/while/{scope}/rnn/while/")
+    out["stop_masks"] = np.stack([I.eval(f"{scope}/rnn/while/canvas/Less", 0, t) for t in range(trip)], 1)
     for key, node in PER_STEP.items():
         if f"{scope}/{node}" in nodes:
             out[key] = I.fetch(f"{scope}/{node}")

@@ -18,7 +18,7 @@ from tests import parity_util as PU                      # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SMALL = ("rec_scales", "rec_shifts", "rec_st_back", "rec_latents", "z_pres_probs", "z_pres_kls", "scale_kls", "shift_kls",
-         "vae_kls", "rec_num_digits", "running_loss", "stopping_sum", "reconstruction_loss", "loss_per_item")
+         "vae_kls", "stop_masks", "rec_num_digits", "running_loss", "stopping_sum", "reconstruction_loss", "loss_per_item")
 
 
 def st_inputs(B=64, seed=1):

@@ -36,6 +36,7 @@ def test_st_kernels_bit_exact_with_reference_graph(golden_dir):
 
 def _per_step(m, g, tol):
     assert np.array_equal(m.rec_num_digits.cpu().numpy(), g["rec_num_digits"])
+    assert np.array_equal(m.stop_masks.cpu().numpy(), g["stop_masks"])
     assert m.executed_steps == int(g["executed_steps"])
     for k in ("rec_scales", "rec_shifts", "rec_st_back", "z_pres_probs", "z_pres_kls", "scale_kls", "shift_kls",
               "vae_kls"):

@@ -57,6 +57,7 @@ def _check_per_step(out, g, tol):
         assert _rel(out[k].numpy().reshape(g[k].shape), g[k]) < tol, (k, _rel(out[k].numpy().reshape(g[k].shape), g[k]))
     assert _rel(out["rec_windows"].numpy()[:, :, ::8], g["rec_windows_sub"]) < tol
     assert np.array_equal(out["rec_num_digits"].numpy(), g["rec_num_digits"])
+    assert np.array_equal(out["stop_masks"].numpy(), g["stop_masks"])
     assert out["executed_steps"] == int(g["executed_steps"])
     assert float(out["accuracy"]) == pytest.approx(float(g["accuracy"]), abs=1e-7)
 
