@@ -86,3 +86,14 @@ def test_reconstruction_image_summary_bit_exact_on_device(golden_dir):
     got = got.cpu().numpy()
     assert np.array_equal(got[:4], g["image_full"])
     assert [hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in got] == list(g["sha256"])
+
+
+def test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir):
+    """Training-mode forward on realistic poses (continuous z_pres, items that stop after 1 or 2 steps) against the
+    reference graph evaluated in fp64: masks / digit counts exact, per-step outputs <= 1e-5.  The canvas-derived loss
+    and the gradients of this uncovered fixture are compared in fp64 on the CPU side only."""
+    g = _g(golden_dir, "ref_graph_train_realistic_fp64.npz")
+    imgs, cnt, params, noise = realistic_fixture(64, seed=1)
+    _, m = make_pair(imgs, cnt, params, train=True, global_step=2000)
+    m.run(cuda_noise(noise))
+    _per_step(m, g, 1e-5)

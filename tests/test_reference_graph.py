@@ -283,6 +283,7 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
     T.test_train_step_against_reference_graph(golden_dir)
     T.test_test_mode_against_reference_graph(golden_dir, "default", PU.default_fixture, 1)
     T.test_test_mode_against_reference_graph(golden_dir, "realistic", PU.realistic_fixture, 2)
+    T.test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir)
     orig = T.ab.visualize_reconstructions
     monkeypatch.setattr(T.ab, "visualize_reconstructions", lambda *a, **k: orig(*a, transformer=O.transformer, **k))
     T.test_reconstruction_image_summary_bit_exact_on_device(golden_dir)
