@@ -80,3 +80,75 @@ def test_batches_and_corruption(tmp_path):
     open(path, "wb").write(bytes(raw))
     with pytest.raises(ValueError, match="corrupt"):
         list(tfr.iter_records(path))
+
+
+def _example_classes():
+    """tf.train.Example / Features / Feature built at run time from the published schema
+    (tensorflow/core/example/{example,feature}.proto) with the protobuf library -- an encoder/decoder that shares no
+    code with tfrecords.py."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name="air_test_example.proto", package="airtest", syntax="proto3")
+    F = descriptor_pb2.FieldDescriptorProto
+
+    def msg(name, *fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = ".airtest." + tname
+        return m
+    msg("BytesList", ("value", 1, F.TYPE_BYTES, F.LABEL_REPEATED, None))
+    msg("FloatList", ("value", 1, F.TYPE_FLOAT, F.LABEL_REPEATED, None))
+    msg("Int64List", ("value", 1, F.TYPE_INT64, F.LABEL_REPEATED, None))
+    feat = msg("Feature", ("bytes_list", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "BytesList"),
+               ("float_list", 2, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "FloatList"),
+               ("int64_list", 3, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "Int64List"))
+    feat.oneof_decl.add(name="kind")
+    for f in feat.field:
+        f.oneof_index = 0
+    feats = msg("Features", ("feature", 1, F.TYPE_MESSAGE, F.LABEL_REPEATED, "Features.FeatureEntry"))
+    entry = feats.nested_type.add(name="FeatureEntry")
+    entry.options.map_entry = True
+    entry.field.add(name="key", number=1, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    entry.field.add(name="value", number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name=".airtest.Feature")
+    msg("Example", ("features", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "Features"))
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName("airtest.Example"))
+
+
+def test_example_encoding_against_the_protobuf_library():
+    """Both directions against google.protobuf: what encode_example writes parses to the same features, and what the
+    library serialises decode_example reads back -- for the exact feature set of multi_mnist.py:186-212."""
+    Example = _example_classes()
+    rng = np.random.RandomState(0)
+    image = rng.rand(2500).astype(np.float32).tobytes()
+    feats = {"height": [50], "width": [50], "digits": [2], "indices": np.array([7, 12345], np.int32).tobytes(),
+             "positions": np.array([3, 4, 20, 21], np.int32).tobytes(), "boxes": np.array([18, 20, 14, 19], np.int32).tobytes(),
+             "labels": np.array([5, 9], np.int32).tobytes(), "image": image}
+    ours = tfr.encode_example(feats)
+    ex = Example()
+    ex.ParseFromString(ours)
+    assert set(ex.features.feature) == set(feats)
+    for k, v in feats.items():
+        f = ex.features.feature[k]
+        if isinstance(v, bytes):
+            assert f.WhichOneof("kind") == "bytes_list" and list(f.bytes_list.value) == [v], k
+        else:
+            assert f.WhichOneof("kind") == "int64_list" and list(f.int64_list.value) == v, k
+    lib = Example()
+    for k, v in feats.items():
+        if isinstance(v, bytes):
+            lib.features.feature[k].bytes_list.value.append(v)
+        else:
+            lib.features.feature[k].int64_list.value.extend(v)
+    back = tfr.decode_example(lib.SerializeToString())
+    assert set(back) == set(feats)
+    for k, v in feats.items():
+        got = back[k]
+        assert (got == [v] or got == v) if isinstance(v, bytes) else list(got) == v, k
+    # negative int64 (ten-byte varint) survives both ways
+    neg = tfr.encode_example({"digits": [-3]})
+    ex = Example()
+    ex.ParseFromString(neg)
+    assert list(ex.features.feature["digits"].int64_list.value) == [-3]
