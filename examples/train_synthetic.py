@@ -1,0 +1,76 @@
+"""Train AIR on synthetic canvases through the product API and watch the digit-count accuracy (the quantity behind the
+reference README's "98 % after ~25k iterations" claim, there on multi-MNIST) -- the GPU counterpart of
+oracle/train_convergence.py, with the reference's training configuration (training.py:100-122, batch 64).
+
+    python examples/train_synthetic.py --iters 25000 --log profiles/rN_gpu_convergence.log
+
+NOT YET RUN ON A GPU: written when round 1's GPU minutes were spent; everything it calls (device_canvases, feed,
+capture, train_step, run, accuracy, reuse=True) is covered by tests/test_gpu_model.py, but the first run of this
+script itself belongs to the next round.
+"""
+import argparse
+import os
+import sys
+import time
+from importlib import import_module
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import air_b200 as ab   # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=25000)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--train-images", type=int, default=60000)
+    ap.add_argument("--val-images", type=int, default=4096)
+    ap.add_argument("--every", type=int, default=500)
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--log", default=None)
+    a = ap.parse_args()
+    data = import_module("tf-attend-infer-repeat_b200.data")
+    train, train_cnt = data.device_canvases(a.train_images, seed=0)
+    val, val_cnt = data.device_canvases(a.val_images, seed=12345)
+    ab.reset_variable_scopes()
+    m = ab.AIRModel(train[:a.batch].clone(), train_cnt[:a.batch].clone(), train=True,
+                    annealing_schedules=data.TRAINING_ANNEALING, gemm_mode=a.gemm, seed=0, **data.TRAINING_HYPER)
+    ev = ab.AIRModel(val, val_cnt, train=False, reuse=True, annealing_schedules=data.TRAINING_ANNEALING,
+                     gemm_mode=a.gemm, **data.TRAINING_HYPER)
+    m.capture()
+    log = open(a.log, "w") if a.log else None
+
+    def emit(s):
+        print(s, flush=True)
+        if log:
+            log.write(s + "\n")
+            log.flush()
+
+    emit(f"# CUDA training, batch {a.batch}, gemm {a.gemm}; columns: iteration  train_loss  train_acc  "
+         f"val_acc(test mode)  val_acc_by_count(0/1/2)  seconds")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    t0 = time.time()
+    loss_sum = torch.zeros((), device="cuda")
+    acc_sum = torch.zeros((), device="cuda")
+    for it in range(a.iters + 1):
+        if it % a.every == 0:
+            ev.run()
+            hit = (ev.rec_num_digits == val_cnt).float()
+            by = [hit[val_cnt == k].mean().item() for k in range(3)]
+            n = max(1, min(it, a.every))
+            emit(f"{it:6d}  {loss_sum.item() / n:10.3f}  {acc_sum.item() / n:.4f}  {hit.mean().item():.4f}  "
+                 f"{by[0]:.3f}/{by[1]:.3f}/{by[2]:.3f}  {time.time() - t0:7.1f}")
+            loss_sum.zero_()
+            acc_sum.zero_()
+        if it == a.iters:
+            break
+        idx = torch.randint(0, a.train_images, (a.batch,), generator=g, device="cuda")
+        m.feed(train[idx], train_cnt[idx])
+        m.train_step()
+        loss_sum += m.loss.reshape(())
+        acc_sum += m.accuracy.reshape(())
+
+
+if __name__ == "__main__":
+    main()
