@@ -121,15 +121,24 @@ def run_train_step(nodes, params, images, num_digits, noise, float_dtype=np.floa
     return run_in_big_stack(body)
 
 
-def run_test_model(nodes, params, images, num_digits, noise, float_dtype=np.float32):
-    """The ``air_1`` graph (train=False: tf.round of z_pres, air_model.py:385-386) on fed placeholders."""
+def run_test_model(nodes, params, images, num_digits, noise, float_dtype=np.float32, max_steps=None):
+    """The ``air_1`` graph (train=False: tf.round of z_pres, air_model.py:385-386) on fed placeholders.
+    ``max_steps`` overrides the one place the loop uses it, the constant of cond()'s ``step < max_steps``
+    (air_model.py:271-275), e.g. 5 for the inference configuration; the summaries (unrolled for 3 steps when the
+    graph was built) are then skipped."""
     def body():
         used = set()
-        I = Interpreter(nodes, graph_variables(params),
-                        {"pipeline/Placeholder:0": _np(images).astype(np.float32),
-                         "pipeline/Placeholder_1:0": _np(num_digits).astype(np.int32)}, _random_fn(noise, used),
-                        float_dtype)
+        feeds = {"pipeline/Placeholder:0": _np(images).astype(np.float32),
+                 "pipeline/Placeholder_1:0": _np(num_digits).astype(np.int32)}
+        if max_steps is not None:
+            feeds["air_1/rnn/while/Less/y:0"] = np.int32(max_steps)
+        I = Interpreter(nodes, graph_variables(params), feeds, _random_fn(noise, used), float_dtype)
         out = _common_fetches(I, "air_1", I.nodes)
+        if max_steps is not None:
+            out["loss"] = I.fetch("air_1/summaries/loss")
+            out["accuracy"] = I.fetch("air_1/summaries/accuracy")
+            out["executed_steps"] = I.trip_count("air_1/rnn/while/air_1/rnn/while/")
+            return out
         out["loss"] = I.fetch("air_1/summaries/loss")
         out["accuracy"] = I.fetch("air_1/summaries/accuracy")
         out["executed_steps"] = I.trip_count("air_1/rnn/while/air_1/rnn/while/")

@@ -95,6 +95,13 @@ def main():
                                 rec_st_back=out["rec_st_back"][:12], rec_num_digits=out["rec_num_digits"][:12],
                                 image_full=im[:4],
                                 sha256=np.array([hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in im]))
+    # inference configuration (BASELINE configs[4]): the same test graph with cond()'s max_steps constant fed as 5
+    imgs, cnt, params, noise = PU.realistic_fixture(64, seed=8, T=5)
+    out = G.run_test_model(nodes, params, imgs, cnt, noise, max_steps=5)
+    d = {k: out[k] for k in SMALL if k in out}
+    d.update(accuracy=out["accuracy"], executed_steps=np.int32(out["executed_steps"]),
+             rec_windows_sub=out["rec_windows"][:, :, ::8])
+    np.savez_compressed(os.path.join(HERE, "ref_graph_test_realistic_T5.npz"), **d)
     for f in sorted(os.listdir(HERE)):
         if f.startswith("ref_graph"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

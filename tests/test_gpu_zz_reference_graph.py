@@ -97,3 +97,12 @@ def test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir):
     _, m = make_pair(imgs, cnt, params, train=True, global_step=2000)
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
+
+
+def test_five_step_inference_against_reference_graph(golden_dir):
+    """configs[4]'s 5 attention steps: the reference's test graph with cond()'s max_steps constant fed as 5."""
+    g = _g(golden_dir, "ref_graph_test_realistic_T5.npz")
+    imgs, cnt, params, noise = realistic_fixture(64, seed=8, T=5)
+    _, m = make_pair(imgs, cnt, params, train=False, global_step=0, max_steps=5)
+    m.run(cuda_noise(noise))
+    _per_step(m, g, 1e-5)

@@ -136,6 +136,18 @@ def test_test_mode_graph(golden_dir, name, fixture, seed):
     assert len(np.unique(g["rec_num_digits"])) >= 3
 
 
+def test_five_step_inference_graph(golden_dir):
+    """BASELINE configs[4] runs 5 attention steps.  The reference graph uses max_steps in exactly one place inside the
+    loop, the constant of cond()'s ``step < max_steps``; fed as 5, the same serialized graph is the 5-step model."""
+    g = _g(golden_dir, "ref_graph_test_realistic_T5.npz")
+    imgs, cnt, params, noise = PU.realistic_fixture(64, seed=8, T=5)
+    out = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False, max_steps=5).forward(imgs, cnt, noise)
+    assert g["rec_scales"].shape == (64, 5, 1) and int(g["executed_steps"]) == 5
+    _check_per_step(out, g, 1e-5)
+    assert np.array_equal(out["stopping_sum"].numpy(), g["stopping_sum"])
+    assert set(np.unique(g["rec_num_digits"])) == {0, 1, 2, 3, 4, 5}
+
+
 @pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
 def test_interpreter_reproduces_committed_goldens_live(golden_dir):
     nodes = pb.load_metagraph(G.META)
@@ -270,7 +282,7 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
 
     def make_pair(imgs, cnt, params, train=True, global_step=2000, **kw):
         orc = O.AIROracle(params={k: v.clone() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING,
-                          train=train)
+                          train=train, **kw)
         orc.global_step = global_step
         return orc, Stand(orc, imgs, cnt)
 
@@ -284,6 +296,7 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
     T.test_test_mode_against_reference_graph(golden_dir, "default", PU.default_fixture, 1)
     T.test_test_mode_against_reference_graph(golden_dir, "realistic", PU.realistic_fixture, 2)
     T.test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir)
+    T.test_five_step_inference_against_reference_graph(golden_dir)
     orig = T.ab.visualize_reconstructions
     monkeypatch.setattr(T.ab, "visualize_reconstructions", lambda *a, **k: orig(*a, transformer=O.transformer, **k))
     T.test_reconstruction_image_summary_bit_exact_on_device(golden_dir)
