@@ -83,7 +83,21 @@ def scalar_summaries(I, scope):
     return out
 
 
-def run_train_step(nodes, params, images, num_digits, noise, float_dtype=np.float32, **var_kwargs):
+GRAD = "air/training/gradients/air/rnn/while/"
+# In-loop tensors around the two Spatial Transformers: forward operands (frame "f", iteration = step t) and the
+# gradients TF's autodiff graph carries in and out of them (frame "b", iteration j = step T-1-j).
+ST_TAPS = {
+    "theta": ("air/rnn/while/st_forward/stack_2", "f"), "theta_inv": ("air/rnn/while/st_backward/stack_2", "f"),
+    "window_recon": ("air/rnn/while/vae/gen_sample/Sigmoid", "f"),
+    "d_crop": (GRAD + "vae/Reshape_grad/Reshape", "b"),                     # d loss / d ST(canvas, theta)
+    "d_theta": (GRAD + "st_forward/SpatialTransformer/_transform/Reshape_grad/Reshape", "b"),
+    "d_writeback": (GRAD + "canvas/Reshape_grad/Reshape", "b"),              # d loss / d ST(window, theta_inv)
+    "d_theta_inv": (GRAD + "st_backward/SpatialTransformer/_transform/Reshape_grad/Reshape", "b"),
+    "d_window_recon": (GRAD + "st_backward/Reshape_grad/Reshape", "b"),
+}
+
+
+def run_train_step(nodes, params, images, num_digits, noise, float_dtype=np.float32, taps=None, **var_kwargs):
     """One ``sess.run([model.training, loss, accuracy, ...])`` of the reference's train graph.  Returns a dict with
     loss, accuracy, per-step outputs, raw gradients (inputs of the L2Loss ops of clip_by_global_norm), clipped
     gradients (ApplyAdam inputs), the global norm and the updated variables."""
@@ -115,6 +129,10 @@ def run_train_step(nodes, params, images, num_digits, noise, float_dtype=np.floa
         out["global_norm"] = I.fetch("air/training/global_norm/global_norm")
         out["executed_steps"] = I.trip_count("air/rnn/while/air/rnn/while/")
         out["raw_grads"], out["clipped_grads"] = raw, clipped
+        T = out["executed_steps"]
+        for key, (node, fr) in (taps or {}).items():       # [T, ...] in forward step order
+            vals = [I.eval(node, 0, t if fr == "f" else T - 1 - t) for t in range(T)]
+            out["tap:" + key] = np.stack(vals)
         out["new_variables"] = dict(I.assigned)
         out["noise_used"] = used
         return out

@@ -76,7 +76,13 @@ def main():
     out = G.run_train_step(nodes, params, imgs, cnt, noise, global_step=2000)
     np.savez_compressed(os.path.join(HERE, "ref_graph_train_covered.npz"), **pack_train(out))
 
+    # gradients TF's autodiff graph carries into and out of the two Spatial Transformers, tapped inside the gradient
+    # loop of an fp32 train step on realistic poses (step t = 1, first 16 items; the ST is per-item independent)
     imgs, cnt, params, noise = PU.realistic_fixture(64, seed=1)
+    out = G.run_train_step(nodes, params, imgs, cnt, noise, global_step=2000, taps=G.ST_TAPS)
+    np.savez_compressed(os.path.join(HERE, "ref_graph_st_grad.npz"),
+                        **{k[4:]: v[1][:16] for k, v in out.items() if k.startswith("tap:")})
+
     out = G.run_train_step(nodes, params, imgs, cnt, noise, global_step=2000, float_dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "ref_graph_train_realistic_fp64.npz"), **pack_train(out))
 

@@ -106,3 +106,4 @@ def test_five_step_inference_against_reference_graph(golden_dir):
     _, m = make_pair(imgs, cnt, params, train=False, global_step=0, max_steps=5)
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
+
