@@ -97,16 +97,17 @@ ST_TAPS = {
 }
 
 
-def run_train_step(nodes, params, images, num_digits, noise, float_dtype=np.float32, taps=None, **var_kwargs):
+def run_train_step(nodes, params, images, num_digits, noise, float_dtype=np.float32, taps=None, extra_feeds=None,
+                   **var_kwargs):
     """One ``sess.run([model.training, loss, accuracy, ...])`` of the reference's train graph.  Returns a dict with
     loss, accuracy, per-step outputs, raw gradients (inputs of the L2Loss ops of clip_by_global_norm), clipped
     gradients (ApplyAdam inputs), the global norm and the updated variables."""
     def body():
         used = set()
-        I = Interpreter(nodes, graph_variables(params, **var_kwargs),
-                        {"pipeline/shuffle_batch:0": _np(images).astype(np.float32),
-                         "pipeline/shuffle_batch:1": _np(num_digits).astype(np.int32)}, _random_fn(noise, used),
-                        float_dtype)
+        feeds = {"pipeline/shuffle_batch:0": _np(images).astype(np.float32),
+                 "pipeline/shuffle_batch:1": _np(num_digits).astype(np.int32)}
+        feeds.update(extra_feeds or {})                    # e.g. a chosen upstream gradient at an ST_TAPS tensor
+        I = Interpreter(nodes, graph_variables(params, **var_kwargs), feeds, _random_fn(noise, used), float_dtype)
         N = I.nodes
         out = {"loss": I.fetch("air/summaries/loss"), "accuracy": I.fetch("air/summaries/accuracy")}
         out.update(_common_fetches(I, "air", N))
