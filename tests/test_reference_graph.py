@@ -359,3 +359,42 @@ def test_three_consecutive_train_steps_follow_the_graph():
             moved = np.linalg.norm(P[k] - params[k].numpy())
             if moved > 0:
                 assert np.linalg.norm(P[k] - orc.params[k].numpy()) <= 2e-4 * moved, (step, k)
+
+
+def test_protobuf_decoder_on_hand_assembled_messages():
+    """oracle/tfgraph/pb.py against bytes assembled by hand from the .proto field numbers (NodeDef with data and
+    control inputs, tensor / int / shape / list attributes, negative varints, the repeat-last-value rule)."""
+    import struct
+
+    def vint(v):
+        v &= (1 << 64) - 1
+        out = b""
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            out += bytes([b | (0x80 if v else 0)])
+            if not v:
+                return out
+
+    def ld(fn, payload):
+        return vint(fn << 3 | 2) + vint(len(payload)) + payload
+
+    def vf(fn, v):
+        return vint(fn << 3) + vint(v)
+    dim = lambda n: ld(2, vf(1, n))                                                  # noqa: E731
+    tensor = vf(1, 1) + ld(2, dim(2) + dim(3)) + ld(5, struct.pack("<2f", 1.5, -2.0))   # float [2,3]: 1.5, -2, -2 ...
+    itensor = vf(1, 3) + ld(2, b"") + ld(7, vint(-7))                                # int32 scalar -7
+    content = vf(1, 9) + ld(2, dim(2)) + ld(4, struct.pack("<2q", 5, -6))            # int64 [2] in tensor_content
+    attr = lambda k, v: ld(5, ld(1, k.encode()) + ld(2, v))                          # noqa: E731
+    node = (ld(1, b"scope/n") + ld(2, b"Const") + ld(3, b"a:1") + ld(3, b"b") + ld(3, b"^c") +
+            attr("value", ld(8, tensor)) + attr("ival", ld(8, itensor)) + attr("cval", ld(8, content)) +
+            attr("i", vf(3, -3)) + attr("f", vint(4 << 3 | 5) + struct.pack("<f", 0.25)) + attr("b", vf(5, 1)) +
+            attr("s", ld(2, b"frame")) + attr("shape", ld(7, dim(-1) + dim(2500))) +
+            attr("list", ld(1, ld(3, vint(1) + vint(2) + vint(-1)))))
+    nd = pb.Node(memoryview(node))
+    assert (nd.name, nd.op, nd.inputs, nd.ctrl) == ("scope/n", "Const", [("a", 1), ("b", 0)], ["c"])
+    assert np.array_equal(nd.attr["value"], np.array([[1.5, -2, -2], [-2, -2, -2]], np.float32))
+    assert nd.attr["ival"].dtype == np.int32 and int(nd.attr["ival"]) == -7 and nd.attr["ival"].shape == ()
+    assert nd.attr["cval"].dtype == np.int64 and list(nd.attr["cval"]) == [5, -6]
+    assert nd.attr["i"] == -3 and nd.attr["f"] == 0.25 and nd.attr["b"] is True and nd.attr["s"] == b"frame"
+    assert nd.attr["shape"] == ("shape", [-1, 2500]) and nd.attr["list"] == [1, 2, -1]
