@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--every", type=int, default=500)
     ap.add_argument("--threads", type=int, default=4)
     ap.add_argument("--log", default=None)
+    ap.add_argument("--save", default=None, help="write the final parameters (float16 .npz, reference variable names)")
     a = ap.parse_args()
     torch.set_num_threads(a.threads)
     torch.manual_seed(0)
@@ -62,6 +63,10 @@ def main():
                  f"{by[0]:.3f}/{by[1]:.3f}/{by[2]:.3f}  {float(m.hyper('z_pres_prior_log_odds')):8.3f}  {time.time() - t0:7.0f}")
             run_loss = run_acc = 0.0
         if it == a.iters:
+            if a.save:
+                import numpy as np
+                np.savez(a.save, global_step=np.int32(m.global_step),
+                         **{k: v.detach().numpy().astype(np.float16) for k, v in m.params.items()})
             break
         idx = torch.randint(0, a.train_images, (a.batch,), generator=g)
         out, _ = m.train_step(train[idx], train_cnt[idx], O.make_noise(it, 3, a.batch))
