@@ -111,3 +111,22 @@ def test_five_step_inference_against_reference_graph(golden_dir):
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
 
+
+def test_trained_weights_inference_counts_digits():
+    """Inference with TRAINED weights (tests/golden/trained_synthetic_fp16.npz, see tests/test_trained_weights.py) on
+    held-out canvases: the CUDA model infers the oracle's digit counts (a 1-ulp GEMM difference may flip a rounded
+    z_pres on a borderline item, hence >= 99 %) and counts correctly; so does the tensor-core (TF32) mode."""
+    from tests.test_trained_weights import PATH, heldout, trained_params
+    if not os.path.exists(PATH):
+        pytest.skip("trained-weights fixture not generated")
+    params, step = trained_params()
+    imgs, cnt, noise = heldout()
+    orc, m = make_pair(imgs, cnt, params, train=False, global_step=step)
+    out = orc.forward(imgs, cnt, noise)
+    m.run(cuda_noise(noise))
+    digits = m.rec_num_digits.cpu()
+    assert (digits == out["rec_num_digits"]).float().mean().item() >= 0.99
+    assert (digits == cnt).float().mean().item() >= 0.93
+    _, m32 = make_pair(imgs, cnt, params, train=False, global_step=step, gemm_mode="tf32")
+    m32.run(cuda_noise(noise))
+    assert (m32.rec_num_digits.cpu() == cnt).float().mean().item() >= 0.90

@@ -327,6 +327,9 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
     T.test_test_mode_against_reference_graph(golden_dir, "realistic", PU.realistic_fixture, 2)
     T.test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir)
     T.test_five_step_inference_against_reference_graph(golden_dir)
+    from tests.test_trained_weights import PATH as trained_path
+    if os.path.exists(trained_path):
+        T.test_trained_weights_inference_counts_digits()
     orig = T.ab.visualize_reconstructions
     monkeypatch.setattr(T.ab, "visualize_reconstructions", lambda *a, **k: orig(*a, transformer=O.transformer, **k))
     T.test_reconstruction_image_summary_bit_exact_on_device(golden_dir)
