@@ -130,3 +130,22 @@ def test_trained_weights_inference_counts_digits():
     _, m32 = make_pair(imgs, cnt, params, train=False, global_step=step, gemm_mode="tf32")
     m32.run(cuda_noise(noise))
     assert (m32.rec_num_digits.cpu() == cnt).float().mean().item() >= 0.90
+
+
+def test_st_backward_kernels_against_the_graphs_autodiff(golden_dir):
+    """air_st_backward on realistic poses against the gradients the reference graph's autodiff subgraph produces for a
+    fed N(0,1) upstream gradient (tests/test_reference_graph.py::test_st_gradients_benign_upstream): d theta and
+    d theta^-1 (all six entries) <= 1e-4; dU <= 5e-4, the measured fp32 conditioning floor of that sum (two fp32
+    summation orders of the reference's own formula differ by 0.6e-4 norm-wise, 2.5e-4 on single items)."""
+    from tests.golden.make_golden_ref_graph import benign_upstream
+    g = _g(golden_dir, "ref_graph_st_grad_benign.npz")
+    d_wb, d_crop = (a[:16] for a in benign_upstream())
+    U = realistic_fixture(64, seed=1)[0][:16].reshape(16, 50, 50, 1).cuda()
+    th = _cu(g["theta"].reshape(16, 6)).requires_grad_(True)
+    ab.transformer(U, th, (28, 28)).backward(_cu(d_crop.reshape(16, 28, 28, 1)))
+    assert relnorm(th.grad.reshape(16, 2, 3), g["d_theta"]) < 1e-4
+    W = _cu(g["window_recon"].reshape(16, 28, 28, 1)).requires_grad_(True)
+    ti = _cu(g["theta_inv"].reshape(16, 6)).requires_grad_(True)
+    ab.transformer(W, ti, (50, 50)).backward(_cu(d_wb.reshape(16, 50, 50, 1)))
+    assert relnorm(ti.grad.reshape(16, 2, 3), g["d_theta_inv"]) < 1e-4
+    assert relnorm(W.grad.reshape(16, 784), g["d_window_recon"]) < 5e-4

@@ -166,6 +166,24 @@ def test_st_gradients_bit_exact_with_the_graphs_autodiff(golden_dir):
     assert _rel(tth.grad.numpy().reshape(16, 2, 3), g["d_theta"]) < 1e-5
 
 
+def test_st_gradients_benign_upstream(golden_dir):
+    """Same taps, N(0,1) upstream gradient fed into the graph: C restatement bit-exact again; torch autograd shows the
+    fp32 conditioning floor of this op (d theta 1e-6, dU ~1e-4: out-of-range pixels add cancelling terms of magnitude
+    (x1f - x)(y1f - y) to the edge pixels' dU), which is why the GPU check of dU uses 5e-4."""
+    g = _g(golden_dir, "ref_graph_st_grad_benign.npz")
+    d_wb, d_crop = (a[:16] for a in MG.benign_upstream())
+    U = PU.realistic_fixture(64, seed=1)[0][:16].numpy().reshape(16, 50, 50, 1)
+    th, ti, W = g["theta"].reshape(16, 6), g["theta_inv"].reshape(16, 6), g["window_recon"].reshape(16, 28, 28, 1)
+    _, dth = C.st_backward(U, th, d_crop.reshape(16, 28, 28, 1), need_dU=False)
+    dU, dti = C.st_backward(W, ti, d_wb.reshape(16, 50, 50, 1), need_dU=True)
+    assert np.array_equal(dth.reshape(16, 2, 3), g["d_theta"]) and np.array_equal(dti.reshape(16, 2, 3), g["d_theta_inv"])
+    assert np.array_equal(dU.reshape(16, 784), g["d_window_recon"])
+    tW, tti = torch.from_numpy(W).requires_grad_(True), torch.from_numpy(ti).requires_grad_(True)
+    O.transformer(tW, tti, (50, 50)).backward(torch.from_numpy(d_wb.reshape(16, 50, 50, 1)))
+    assert _rel(tti.grad.numpy().reshape(16, 2, 3), g["d_theta_inv"]) < 1e-5
+    assert _rel(tW.grad.numpy().reshape(16, 784), g["d_window_recon"]) < 5e-4
+
+
 def test_five_step_inference_graph(golden_dir):
     """BASELINE configs[4] runs 5 attention steps.  The reference graph uses max_steps in exactly one place inside the
     loop, the constant of cond()'s ``step < max_steps``; fed as 5, the same serialized graph is the 5-step model."""
@@ -327,6 +345,7 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
     T.test_test_mode_against_reference_graph(golden_dir, "realistic", PU.realistic_fixture, 2)
     T.test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir)
     T.test_five_step_inference_against_reference_graph(golden_dir)
+    T.test_st_backward_kernels_against_the_graphs_autodiff(golden_dir)
     from tests.test_trained_weights import PATH as trained_path
     if os.path.exists(trained_path):
         T.test_trained_weights_inference_counts_digits()
