@@ -4,6 +4,7 @@ import hashlib
 import importlib
 import json
 import os
+import types
 from collections import OrderedDict
 
 import numpy as np
@@ -127,3 +128,72 @@ def test_evaluation_summaries_host_logic():
     assert np.isnan(st["kl_3_step_all_dig"])                                         # padded step, nobody ran it
     st1 = mw.summarize_by_step(per_step, steps, tgt, 3, 2, "kl", one_more_step=True)
     assert st1["kl_1_step_all_dig"] == 2.0 and st1["kl_2_step_all_dig"] == 25.0
+
+
+class _OracleBackedModel:
+    """Stand-in with the result attributes / feed / run of AIRModel, computed by the CPU oracle (test only)."""
+
+    def __init__(self, B, params, noise_seed=12, **hyper):
+        import torch
+        from oracle import air_oracle as O
+        self.O, self.batch_size, self.device = O, B, torch.device("cpu")
+        self.orc = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False, **hyper)
+        self.noise = O.make_noise(noise_seed, self.orc.h["max_steps"], B)
+        self.images = torch.zeros(B, 2500)
+
+    def feed(self, images, targets=None):
+        self.images = images.clone()
+
+    def run(self, noise=None):
+        import torch
+        out = self.orc.forward(self.images, torch.zeros(self.batch_size, dtype=torch.int32), self.noise)
+        for k, v in out.items():
+            setattr(self, k, v)
+
+
+def test_model_wrapper_equals_the_reference_class():
+    """ModelWrapper.infer against THE REFERENCE'S OWN demo/model_wrapper.py (imported from /root/reference; plain
+    numpy, its session.run served by the same oracle outputs): same six lists, element for element, including the
+    empty arrays of images with no inferred digit and a trailing partial batch."""
+    import importlib.util
+    import numpy as np
+    import pytest
+    ref_path = "/root/reference/demo/model_wrapper.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("/root/reference not present (GPU box)")
+    import torch
+    from oracle import air_oracle as O
+    from air_b200.demo import model_wrapper as mw
+    spec = importlib.util.spec_from_file_location("ref_model_wrapper", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    B = 16
+    params = O.init_params(seed=12)
+    params["z_pres/log_odds/output/biases"] += 0.5
+    model = _OracleBackedModel(B, params)
+    images = [im.reshape(50, 50).numpy() for im in O.synthetic_canvases(B + 6, seed=12)[0]]   # 22 images: 16 + 6
+
+    class Session:                                       # what sess.run(fetches, feed_dict) does for the reference
+        def run(self, fetches, feed_dict):
+            (data,) = feed_dict.values()
+            n = len(data)
+            batch = torch.zeros(B, 2500)
+            batch[:n] = torch.from_numpy(np.stack(data))
+            model.feed(batch)
+            model.run()
+            return [getattr(model, name)[:n].numpy() for name in fetches]
+    names = types.SimpleNamespace(**{k: k for k in ("rec_num_digits", "rec_scales", "rec_shifts", "reconstruction",
+                                                    "rec_windows", "rec_latents", "reconstruction_loss")})
+    want = [[], [], [], [], [], []]
+    ref_wrapper = ref.ModelWrapper(names, Session(), "placeholder")
+    for start in (0, B):                                 # the reference has no batching: one call per batch
+        for acc, part in zip(want, ref_wrapper.infer(images[start:start + B])):
+            acc.extend(part)
+    got = mw.ModelWrapper(model).infer(images)
+    assert len(got) == 6 and all(len(g) == 22 for g in got)
+    assert got[0] == want[0] and len(set(got[0])) >= 3 and 0 in got[0]
+    for g_list, w_list in zip(got[1:], want[1:]):
+        for g, w in zip(g_list, w_list):
+            g, w = np.asarray(g), np.asarray(w)
+            assert g.shape == w.shape and g.dtype == w.dtype and np.array_equal(g, w)

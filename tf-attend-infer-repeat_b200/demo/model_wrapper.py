@@ -23,9 +23,7 @@ class ModelWrapper:
         self.window_size = window_size
 
     def infer(self, images, noise=None):
-        all_digits, all_positions = [], []
-        all_windows, all_latents = [], []
-        all_reconstructions, all_loss = [], []
+        all_digits, all_positions, all_reconstructions, all_windows, all_latents, all_loss = ([] for _ in range(6))
         m = self.model
         B = m.batch_size
         flat = np.stack([np.ravel(np.asarray(img, dtype=np.float32)) for img in images]) if len(images) else \
@@ -37,26 +35,20 @@ class ModelWrapper:
             batch[:n] = chunk
             m.feed(torch.from_numpy(batch).to(m.device))
             m.run(noise)
-            rec_digits = m.rec_num_digits[:n].cpu().numpy()
-            rec_scales = m.rec_scales[:n].cpu().numpy()
-            rec_shifts = m.rec_shifts[:n].cpu().numpy()
-            reconstructions = m.reconstruction[:n].cpu().numpy()
-            rec_windows = m.rec_windows[:n].cpu().numpy()
-            rec_latents = m.rec_latents[:n].cpu().numpy()
-            rec_loss = m.reconstruction_loss[:n].cpu().numpy()
-            for i in range(n):
-                digits = int(rec_digits[i])
-                positions, windows, latents = [], [], []
-                for j in range(digits):
-                    positions.append(np.array([rec_scales[i][j][0]] + list(rec_shifts[i][j])))
-                    windows.append(np.reshape(rec_windows[i][j], (self.window_size, self.window_size)))
-                    latents.append(rec_latents[i][j])
-                all_digits.append(digits)
-                all_positions.append(np.array(positions))
-                all_reconstructions.append(np.reshape(reconstructions[i], (self.canvas_size, self.canvas_size)))
-                all_windows.append(np.array(windows))
-                all_latents.append(np.array(latents))
-                all_loss.append(rec_loss[i])
+            fetched = {k: getattr(m, k)[:n].cpu().numpy() for k in
+                       ("rec_num_digits", "rec_scales", "rec_shifts", "reconstruction", "rec_windows", "rec_latents",
+                        "reconstruction_loss")}
+            ws, cs = self.window_size, self.canvas_size
+            pose = np.concatenate([fetched["rec_scales"], fetched["rec_shifts"]], axis=2)      # [n, T, 3] = (s, x, y)
+            for i, d in enumerate(int(v) for v in fetched["rec_num_digits"]):
+                # per image: only the first ``d`` (= inferred digit count) steps are reported, as the reference does
+                empty = np.array([])
+                all_digits.append(d)
+                all_positions.append(pose[i, :d].copy() if d else empty)
+                all_windows.append(fetched["rec_windows"][i, :d].reshape(d, ws, ws) if d else empty)
+                all_latents.append(fetched["rec_latents"][i, :d].copy() if d else empty)
+                all_reconstructions.append(fetched["reconstruction"][i].reshape(cs, cs))
+                all_loss.append(fetched["reconstruction_loss"][i])
         return all_digits, all_positions, all_reconstructions, all_windows, all_latents, all_loss
 
 
