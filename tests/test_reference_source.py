@@ -1,0 +1,110 @@
+"""The reference's checked-in SOURCE, executed (no GPU, no TensorFlow): air/transformer.py and air/concrete.py are
+imported from /root/reference with ``tensorflow`` resolved to oracle/tfgraph/tf_shim.py, a numpy stand-in for the ~30
+``tf.*`` calls they make.  This pins the functions the saved graph does not contain -- batch_transformer
+(transformer.py:178-195), concrete_binary_sample incl. hard=True (concrete.py:4-17) -- and re-pins transformer() for
+multi-channel, non-square and rotated cases.  Skipped where /root/reference does not exist (the GPU box); the GPU tests
+compare the CUDA path with the same oracle functions (tests/test_gpu_st.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import air_oracle as O
+from oracle import c_oracle as C
+from oracle.tfgraph import tf_shim as S
+
+REF = "/root/reference/air/"
+pytestmark = pytest.mark.skipif(not os.path.exists(REF + "transformer.py"), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    with S.installed():
+        return S.load_reference_module(REF + "transformer.py"), S.load_reference_module(REF + "concrete.py")
+
+
+def _thetas(rng, B):
+    th = np.zeros((B, 6), np.float32)
+    th[:, 0] = th[:, 4] = rng.uniform(0.05, 1.6, B)      # incl. windows larger than the canvas
+    th[:, 2], th[:, 5] = rng.uniform(-0.6, 0.6, B), rng.uniform(-0.6, 0.6, B)
+    th[::3] = rng.uniform(-1.1, 1.1, (len(th[::3]), 6))  # every third: shear / rotation
+    return th
+
+
+@pytest.mark.parametrize("shape,out", [((9, 50, 50, 1), (28, 28)), ((9, 28, 28, 1), (50, 50)), ((5, 20, 30, 3), (7, 9)),
+                                       ((2, 1, 1, 1), (3, 3)), ((4, 50, 50, 1), (100, 100))])
+def test_transformer_source_bit_exact(ref, shape, out):
+    rng = np.random.default_rng(sum(shape))
+    U = rng.uniform(0, 1, shape).astype(np.float32)
+    th = _thetas(rng, shape[0])
+    want = ref[0].transformer(U, th, out)
+    assert want.shape == (shape[0],) + out + (shape[3],) and want.dtype == np.float32
+    assert np.array_equal(C.st_forward(U, th, out), want)
+    assert np.array_equal(O.transformer(torch.from_numpy(U), torch.from_numpy(th), out).numpy(), want)
+    # theta as [B,2,3] is accepted (transformer.py:144 reshapes)
+    assert np.array_equal(ref[0].transformer(U, th.reshape(-1, 2, 3), out), want)
+
+
+def test_batch_transformer_source_bit_exact(ref):
+    rng = np.random.default_rng(5)
+    U = rng.uniform(0, 1, (3, 20, 30, 2)).astype(np.float32)
+    ths = rng.uniform(-1, 1, (3, 4, 6)).astype(np.float32)
+    want = ref[0].batch_transformer(U, S.tensor(ths), (7, 9))
+    assert want.shape == (12, 7, 9, 2)
+    got = O.batch_transformer(torch.from_numpy(U), torch.from_numpy(ths), (7, 9)).numpy()
+    assert np.array_equal(got, want)
+    # output row b*N + n is input b under its n-th transform
+    one = ref[0].transformer(U[1:2], ths[1, 2:3], (7, 9))
+    assert np.array_equal(want[1 * 4 + 2], one[0])
+
+
+def test_concrete_source(ref):
+    rng = np.random.default_rng(6)
+    lo = rng.normal(0, 3, 256).astype(np.float32)
+    u = rng.uniform(0, 1, 256).astype(np.float32)
+    u[:4] = [0.0, 1.0 - 2.0 ** -24, 0.5, 1e-12]           # the eps terms matter at the ends of [0,1)
+    t = np.float32(0.7)
+    with S.installed(uniform=u):
+        y = ref[1].concrete_binary_pre_sigmoid_sample(lo, t)
+        y_soft, s_soft = ref[1].concrete_binary_sample(lo, t, hard=False)
+        y_hard, s_hard = ref[1].concrete_binary_sample(lo, t, hard=True)
+    kl = ref[1].concrete_binary_kl_mc_sample(y, np.float32(-1.3), t, lo, t)
+    tl, tu = torch.from_numpy(lo), torch.from_numpy(u)
+    oy = O.concrete_binary_pre_sigmoid_sample(tl, 0.7, tu)
+    np.testing.assert_allclose(oy.numpy(), y, rtol=2e-6, atol=2e-6)          # numpy vs torch log differ by an ulp
+    okl = O.concrete_binary_kl_mc_sample(torch.from_numpy(y), -1.3, 0.7, tl, 0.7)
+    np.testing.assert_allclose(okl.numpy(), kl, rtol=1e-5, atol=1e-5)
+    oy2, os2 = O.concrete_binary_sample(tl, 0.7, tu, hard=False)
+    np.testing.assert_allclose(oy2.numpy(), y_soft, rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(os2.numpy(), s_soft, rtol=2e-6, atol=1e-7)
+    oy3, os3 = O.concrete_binary_sample(tl, 0.7, tu, hard=True)
+    safe = np.abs(y_hard / t) > 1e-4                                         # away from sigmoid == 0.5 exactly
+    assert np.array_equal(os3.numpy()[safe], s_hard[safe]) and set(np.unique(s_hard)) <= {0.0, 1.0}
+    # pre-sigmoid sample and (y, sigmoid) variant are the same draw: y_soft / t == y
+    np.testing.assert_allclose(y_soft / t, y, rtol=1e-6, atol=1e-6)
+    # the C restatement of the fused step uses the same sample and KL
+    out = C.concrete_step(lo, u, np.zeros(256, np.float32), np.zeros(256, np.float32), np.zeros(256, np.int32),
+                          -1.3, 0.7, 0.99, 1)
+    np.testing.assert_allclose(out["kl"], ref[1].concrete_binary_kl_mc_sample(y, np.float32(-1.3), t, lo, t),
+                               rtol=1e-5, atol=1e-5)
+
+
+def test_vae_source(ref):
+    """air/vae.py through the shim (contrib.layers.fully_connected = act(x @ W + b), TF softplus, injected normal
+    noise): reconstruction / mean / log-variance agree with the oracle's vae(), and the FOURTH return value of the
+    checked-in source is the recognition MEAN (vae.py:43) -- the saved graph, an older revision, recorded the sample
+    there; the oracle and the CUDA path follow the source."""
+    rng = np.random.default_rng(7)
+    params = O.init_params(seed=7)
+    vp = {k[len("vae/"):]: v.numpy() for k, v in params.items() if k.startswith("vae/")}
+    x = rng.uniform(0, 1, (16, 784)).astype(np.float32)
+    n1, n2 = rng.standard_normal((16, 50)).astype(np.float32), rng.standard_normal((16, 784)).astype(np.float32)
+    with S.installed(normal=[n1, n2], params=vp):
+        vae_mod = S.load_reference_module(REF + "vae.py")
+        rec, mean, logvar, latent = vae_mod.vae(x, 784, (512, 256), 50, (256, 512), 0.3)
+    orec, omean, ologvar, olatent = O.vae(torch.from_numpy(x), params, "vae/", 2, 2, torch.from_numpy(n1),
+                                          torch.from_numpy(n2), 0.3)
+    assert latent is mean
+    for got, want in ((orec, rec), (omean, mean), (ologvar, logvar), (olatent, mean)):
+        np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=2e-6)
