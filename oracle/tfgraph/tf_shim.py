@@ -224,3 +224,114 @@ def load_reference_module(path):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+# ---- tf.train.Example / tf.python_io.TFRecordWriter (for the reference's multi_mnist.py:186-212) -------------------
+def example_classes():
+    """tf.train.{Example, Features, Feature, BytesList, FloatList, Int64List} built at run time with the protobuf
+    library from the published schema (tensorflow/core/example/{example,feature}.proto)."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name="air_shim_example.proto", package="airshim", syntax="proto3")
+    F = descriptor_pb2.FieldDescriptorProto
+
+    def msg(name, *fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = ".airshim." + tname
+        return m
+    msg("BytesList", ("value", 1, F.TYPE_BYTES, F.LABEL_REPEATED, None))
+    msg("FloatList", ("value", 1, F.TYPE_FLOAT, F.LABEL_REPEATED, None))
+    msg("Int64List", ("value", 1, F.TYPE_INT64, F.LABEL_REPEATED, None))
+    feat = msg("Feature", ("bytes_list", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "BytesList"),
+               ("float_list", 2, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "FloatList"),
+               ("int64_list", 3, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "Int64List"))
+    feat.oneof_decl.add(name="kind")
+    for f in feat.field:
+        f.oneof_index = 0
+    feats = msg("Features", ("feature", 1, F.TYPE_MESSAGE, F.LABEL_REPEATED, "Features.FeatureEntry"))
+    entry = feats.nested_type.add(name="FeatureEntry")
+    entry.options.map_entry = True
+    entry.field.add(name="key", number=1, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    entry.field.add(name="value", number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name=".airshim.Feature")
+    msg("Example", ("features", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, "Features"))
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return types.SimpleNamespace(**{n: message_factory.GetMessageClass(pool.FindMessageTypeByName("airshim." + n))
+                                    for n in ("Example", "Features", "Feature", "BytesList", "FloatList", "Int64List")})
+
+
+def _crc32c_table():
+    tab = []
+    for i in builtins.range(256):
+        c = i
+        for _ in builtins.range(8):
+            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+        tab.append(c)
+    return tab
+
+
+_CRC = _crc32c_table()
+
+
+def masked_crc32c(data):
+    """CRC-32C (Castagnoli), then TFRecord's mask: rotate right by 15 and add 0xa282ead8 (lib/hash/crc32c.h)."""
+    c = 0xFFFFFFFF
+    for b in data:
+        c = _CRC[(c ^ b) & 0xFF] ^ (c >> 8)
+    c ^= 0xFFFFFFFF
+    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+class TFRecordWriter:
+    """tf.python_io.TFRecordWriter: u64 length, masked crc of the length, payload, masked crc of the payload."""
+
+    def __init__(self, path):
+        self.f = open(path, "wb")
+
+    def write(self, record):
+        import struct
+        head = struct.pack("<Q", len(record))
+        self.f.write(head + struct.pack("<I", masked_crc32c(head)) + record + struct.pack("<I", masked_crc32c(record)))
+
+    def close(self):
+        self.f.close()
+
+
+python_io = types.SimpleNamespace(TFRecordWriter=TFRecordWriter)
+
+
+class _Train:
+    def __getattr__(self, name):
+        return getattr(example_classes_cached(), name)
+
+
+_example_cache = []
+
+
+def example_classes_cached():
+    if not _example_cache:
+        _example_cache.append(example_classes())
+    return _example_cache[0]
+
+
+train = _Train()
+
+
+class NumpyCompat:
+    """``np`` for reference modules written against NumPy 1.x: ndarray.tostring() (removed in NumPy 2.3) is provided
+    on the arrays returned by asarray / ravel."""
+
+    class _A(np.ndarray):
+        def tostring(self):
+            return self.tobytes()
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    def asarray(self, *a, **k):
+        return np.asarray(*a, **k).view(self._A)
+
+    def ravel(self, *a, **k):
+        return np.ravel(*a, **k).view(self._A)

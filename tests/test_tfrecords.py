@@ -152,3 +152,41 @@ def test_example_encoding_against_the_protobuf_library():
     ex = Example()
     ex.ParseFromString(neg)
     assert list(ex.features.feature["digits"].int64_list.value) == [-3]
+
+
+def test_reader_against_the_references_own_writer(tmp_path):
+    """multi_mnist.py:186-212 executed: the reference's write_to_records is imported from /root/reference with
+    tf.train.* backed by the protobuf library and tf.python_io.TFRecordWriter by an independent framing
+    implementation (oracle/tfgraph/tf_shim.py).  Its file is read by tfrecords.read_test_data / iter_records, and
+    tfrecords.write_to_records produces records that decode to the same examples."""
+    import os
+    import sys
+    import types
+    if not os.path.exists("/root/reference/multi_mnist.py"):
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle.tfgraph import tf_shim as S
+    extra = {"tensorflow.examples": types.ModuleType("e"), "tensorflow.examples.tutorials": types.ModuleType("t"),
+             "tensorflow.examples.tutorials.mnist": types.ModuleType("m")}
+    extra["tensorflow.examples.tutorials.mnist"].input_data = None
+    with S.installed():
+        sys.modules.update(extra)
+        try:
+            ref = S.load_reference_module("/root/reference/multi_mnist.py")
+        finally:
+            for k in extra:
+                sys.modules.pop(k, None)
+        ref.np = S.NumpyCompat()
+        images, indices, positions, boxes, labels, digits = _dataset(n=12, seed=4)
+        ref.write_to_records(str(tmp_path / "ref"), images, indices, positions, boxes, labels, digits)
+    im, dg, ix, ps, bx, lb = tfr.read_test_data(str(tmp_path / "ref.tfrecords"))
+    assert dg == list(digits) and len(im) == 12
+    for i in range(12):
+        assert np.array_equal(np.ravel(im[i]), np.ravel(np.asarray(images[i], np.float32)))
+        d = digits[i]                                     # the reader keeps the first d (2d) entries, as the reference's does
+        assert list(ix[i]) == list(indices[i][:d]) and list(ps[i]) == list(positions[i][:2 * d])
+        assert list(bx[i]) == list(boxes[i][:2 * d]) and list(lb[i]) == list(labels[i][:d])
+    tfr.write_to_records(str(tmp_path / "ours"), images, indices, positions, boxes, labels, digits)
+    ref_recs = [tfr.decode_example(r) for r in tfr.iter_records(str(tmp_path / "ref.tfrecords"))]
+    our_recs = [tfr.decode_example(r) for r in tfr.iter_records(str(tmp_path / "ours.tfrecords"))]
+    assert ref_recs == our_recs
+    assert os.path.getsize(tmp_path / "ref.tfrecords") == os.path.getsize(tmp_path / "ours.tfrecords")
