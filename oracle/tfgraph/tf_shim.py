@@ -299,7 +299,22 @@ class TFRecordWriter:
         self.f.close()
 
 
-python_io = types.SimpleNamespace(TFRecordWriter=TFRecordWriter)
+def tf_record_iterator(path):
+    """tf.python_io.tf_record_iterator: yields the payloads, checking both masked CRCs (independent of tfrecords.py)."""
+    import struct
+    with open(path, "rb") as f:
+        while True:
+            head = f.read(8)
+            if not head:
+                return
+            (n,) = struct.unpack("<Q", head)
+            assert struct.unpack("<I", f.read(4))[0] == masked_crc32c(head), "length crc"
+            data = f.read(n)
+            assert struct.unpack("<I", f.read(4))[0] == masked_crc32c(data), "payload crc"
+            yield data
+
+
+python_io = types.SimpleNamespace(TFRecordWriter=TFRecordWriter, tf_record_iterator=tf_record_iterator)
 
 
 class _Train:
@@ -335,3 +350,7 @@ class NumpyCompat:
 
     def ravel(self, *a, **k):
         return np.ravel(*a, **k).view(self._A)
+
+    @staticmethod
+    def fromstring(data, dtype=float):                   # NumPy 1.x binary mode == frombuffer + copy
+        return np.frombuffer(data, dtype=dtype).copy()

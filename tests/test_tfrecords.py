@@ -190,3 +190,15 @@ def test_reader_against_the_references_own_writer(tmp_path):
     our_recs = [tfr.decode_example(r) for r in tfr.iter_records(str(tmp_path / "ours.tfrecords"))]
     assert ref_recs == our_recs
     assert os.path.getsize(tmp_path / "ref.tfrecords") == os.path.getsize(tmp_path / "ours.tfrecords")
+    # ... and the reference's own read_test_data (multi_mnist.py:254-296) reads OUR file like ours does, with and
+    # without the empty-image reordering
+    for shift in (False, True):
+        with S.installed():
+            want = ref.read_test_data(str(tmp_path / "ours.tfrecords"), shift_zero_digits_images=shift)
+        got = tfr.read_test_data(str(tmp_path / "ours.tfrecords"), shift_zero_digits_images=shift)
+        assert len(want) == len(got) == 6
+        for w_list, g_list in zip(want, got):
+            assert len(w_list) == len(g_list)
+            for w, g in zip(w_list, g_list):
+                assert np.array_equal(np.asarray(w), np.asarray(g))
+    assert digits.count(0) >= 2                            # the reordering has something to move
