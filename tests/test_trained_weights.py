@@ -57,3 +57,23 @@ def test_trained_weights_survive_the_tf_bundle_format(tmp_path):
     assert set(back) == set(tensors) and int(back["air/global_step"]) == 25000
     for k, v in tensors.items():
         assert np.array_equal(back[k], v), k
+
+
+@needs_weights
+@pytest.mark.skipif(not os.path.exists("/root/reference/model/air-model.meta"), reason="/root/reference not present")
+def test_reference_graph_counts_digits_with_the_trained_weights():
+    """The reference's own test-mode graph, loaded with the trained weights and run by the interpreter, infers the
+    same digit counts as the oracle on held-out canvases and is right about them (its own accuracy summary)."""
+    from oracle.tfgraph import air_graph as G
+    from oracle.tfgraph import pb
+    params, step = trained_params()
+    imgs, cnt, noise = heldout(B=64, seed=778)
+    out = G.run_test_model(pb.load_metagraph(G.META), params, imgs, cnt, noise)
+    orc = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False)
+    o = orc.forward(imgs, cnt, noise)
+    assert np.array_equal(out["rec_num_digits"], o["rec_num_digits"].numpy())
+    assert np.array_equal(out["stop_masks"], o["stop_masks"].numpy())
+    assert float(out["accuracy"]) >= 0.9 and out["summaries"]["digit_acc_all_dig"] == pytest.approx(float(out["accuracy"]))
+    for k in ("rec_scales", "rec_shifts", "rec_windows"):
+        a, b = out[k], o[k].numpy().reshape(out[k].shape)
+        assert np.linalg.norm(a - b) <= 1e-5 * np.linalg.norm(b), k
