@@ -61,7 +61,7 @@ def stack(values, axis=0):
     return np.stack([np.asarray(v) for v in values], axis)
 
 
-def transpose(x, perm):
+def transpose(x, perm=None):
     return np.transpose(x, perm)
 
 
@@ -116,7 +116,7 @@ def linspace(start, stop, num):
     return (start + step * np.arange(n, dtype=f32)).astype(f32)
 
 
-def concat(axis, values):
+def concat(values, axis):
     return np.concatenate(values, axis)
 
 
@@ -145,7 +145,8 @@ def stop_gradient(x):
 
 
 def random_uniform(shp, minval=0, maxval=1):
-    u = np.asarray(_uniform[0], f32)
+    src = _uniform[0]
+    u = np.asarray(src.pop(0) if isinstance(src, list) else src, f32)
     assert tuple(int(s) for s in shp) == u.shape
     return u
 
@@ -159,7 +160,7 @@ _normal = [None]
 def variable_scope(name, *a, **k):
     _scopes.append(name)
     try:
-        yield types.SimpleNamespace(name="/".join(_scopes))
+        yield types.SimpleNamespace(name="/".join(_scopes), reuse=bool(k.get("reuse")))
     finally:
         _scopes.pop()
 
@@ -181,33 +182,52 @@ def _softplus(x):
     return np.where(x > -thr, x, np.where(x < thr, e, np.log(e + f32(1.0)))).astype(np.float32)
 
 
-def _fully_connected(inputs, num_outputs, activation_fn=None, scope=None):
-    """tf.contrib.layers.fully_connected: activation(inputs @ weights + biases); the variables come from the
-    parameter dict given to ``installed(params=...)`` under ``<scope name>/weights|biases``."""
-    w, b = (np.asarray(_params[0][f"{scope.name}/{n}"], f32) for n in ("weights", "biases"))
+def _param(name):
+    """Variable value by its full scope path, or by the path with the model's ``<scope>/rnn/`` prefix removed (the
+    key convention of oracle.init_params / the checkpoint names minus ``air/rnn/``)."""
+    p = _params[0]
+    if name in p:
+        return np.asarray(p[name], f32)
+    parts = name.split("/")
+    return np.asarray(p["/".join(parts[2:]) if parts[1] == "rnn" else "/".join(parts[1:])], f32)
+
+
+_RELU = object()
+
+
+def _fully_connected(inputs, num_outputs, activation_fn=_RELU, scope=None):
+    """tf.contrib.layers.fully_connected: activation(inputs @ weights + biases), ReLU unless told otherwise; the
+    variables come from the parameter dict given to ``installed(params=...)``."""
+    if activation_fn is _RELU:
+        activation_fn = nn.relu
+    w, b = (_param(f"{scope.name}/{n}") for n in ("weights", "biases"))
     assert w.shape == (inputs.shape[1], num_outputs)
     y = np.matmul(inputs, w) + b
     return activation_fn(y) if activation_fn is not None else y
 
 
-layers = types.ModuleType("tensorflow.contrib.layers")
-layers.fully_connected = _fully_connected
+contrib_layers = types.ModuleType("tensorflow.contrib.layers")
+contrib_layers.fully_connected = _fully_connected
 contrib = types.ModuleType("tensorflow.contrib")
-contrib.layers = layers
+contrib.layers = contrib_layers
 
 
 nn = types.SimpleNamespace(sigmoid=lambda x: (f32(1.0) / (f32(1.0) + np.exp(-x))).astype(np.asarray(x).dtype),
-                           softplus=_softplus)
+                           softplus=_softplus, relu=lambda x: np.maximum(x, f32(0.0)), tanh=lambda x: np.tanh(x))
 
 
 @contextlib.contextmanager
-def installed(uniform=None, normal=None, params=None):
+def installed(uniform=None, normal=None, params=None, global_step=0):
     """Make ``import tensorflow`` (and ``tensorflow.contrib.layers``) resolve to this module inside the block, with
     the injected uniform noise, normal-noise sequence and variable values."""
-    names = {"tensorflow": sys.modules[__name__], "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers}
+    names = {"tensorflow": sys.modules[__name__], "tensorflow.contrib": contrib, "tensorflow.contrib.layers": contrib_layers,
+             "tensorflow.contrib.rnn": rnn}
+    _global_step[0] = global_step
+    summaries.clear()
     saved = {k: sys.modules.get(k) for k in names}
     sys.modules.update(names)
-    _uniform[0], _normal[0], _params[0] = uniform, list(normal) if normal is not None else None, params
+    _uniform[0] = list(uniform) if isinstance(uniform, (list, tuple)) else uniform
+    _normal[0], _params[0] = list(normal) if normal is not None else None, params
     try:
         yield
     finally:
@@ -354,3 +374,264 @@ class NumpyCompat:
     @staticmethod
     def fromstring(data, dtype=float):                   # NumPy 1.x binary mode == frombuffer + copy
         return np.frombuffer(data, dtype=dtype).copy()
+
+
+# ---- the rest of what air/air_model.py calls (whole-model forward, train=False) -------------------------------------
+float32, int32 = np.float32, np.int32
+_global_step = [0]
+summaries = {}                                            # tag -> value of every tf.summary.scalar / image
+sigmoid = nn.sigmoid
+
+
+def constant(v, dtype=None):
+    return np.asarray(v, dtype) if dtype else (np.int32(v) if isinstance(v, int) else np.asarray(v, f32))
+
+
+def zeros_like(x):
+    return np.zeros_like(x)
+
+
+def less(a, b):
+    return np.less(a, b)
+
+
+def greater(a, b):
+    return np.greater(a, b)
+
+
+def equal(a, b):
+    return np.equal(a, b)
+
+
+def logical_and(a, b):
+    return np.logical_and(a, b)
+
+
+def reduce_any(x):
+    return np.any(x)
+
+
+def reduce_sum(x, axis=None):
+    return np.sum(x, axis=axis)
+
+
+def reduce_mean(x, axis=None):
+    import warnings
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.mean(x, axis=axis, dtype=np.asarray(x).dtype)
+
+
+def square(x):
+    return x * x
+
+
+def minimum(a, b):
+    return np.minimum(a, b)
+
+
+def maximum(a, b):
+    return np.maximum(a, b)
+
+
+def where(c, t, e):
+    c = np.asarray(c)
+    if c.ndim == 1 and np.ndim(t) > 1:                     # vector condition selects rows
+        c = c.reshape((-1,) + (1,) * (np.ndim(t) - 1))
+    return np.where(c, t, e).astype(np.asarray(t).dtype)
+
+
+def boolean_mask(x, mask):
+    return np.asarray(x)[np.asarray(mask)]
+
+
+def pad(x, paddings):
+    return np.pad(x, [(int(a), int(b)) for a, b in paddings])
+
+
+def get_variable(shape=None, dtype=None, initializer=None, trainable=True):
+    """Only ``global_step`` is created this way (air_model.py:69); every other variable comes from a layer."""
+    return np.int32(_global_step[0])
+
+
+def constant_initializer(v):
+    return v
+
+
+def get_variable_scope():
+    return types.SimpleNamespace(name="/".join(_scopes), reuse=False)
+
+
+def trainable_variables():
+    return []
+
+
+def while_loop(cond, body, loop_vars):
+    v = list(loop_vars)
+    while bool(cond(*v)):
+        v = list(body(*v))
+    return v
+
+
+class TensorArray:
+    def __init__(self, dtype=None, size=0, dynamic_size=True):
+        self.items = []
+
+    def size(self):
+        return len(self.items)
+
+    def write(self, index, value):
+        assert index == len(self.items)
+        self.items.append(value)
+        return self
+
+    def stack(self):
+        return np.stack(self.items)
+
+
+class _LSTMCell:
+    """tf.contrib.rnn.BasicLSTMCell (TF 1.3): [x, h] @ kernel + bias -> i, j, f, o; c' = c*sigmoid(f + 1) +
+    sigmoid(i)*tanh(j); h' = tanh(c')*sigmoid(o); state = (c, h)."""
+
+    def __init__(self, num_units, reuse=None):
+        self.n = num_units
+
+    def zero_state(self, batch, dtype):
+        z = np.zeros((int(batch), self.n), dtype)
+        return (z, z.copy())
+
+    def __call__(self, inputs, state, scope=None):
+        c, h = state
+        gates = np.matmul(np.concatenate([inputs, h], 1), _param(scope.name + "/kernel")) + _param(scope.name + "/bias")
+        i, j, f, o = np.split(gates, 4, axis=1)
+        new_c = c * nn.sigmoid(f + f32(1.0)) + nn.sigmoid(i) * np.tanh(j)
+        new_h = np.tanh(new_c) * nn.sigmoid(o)
+        return new_h, (new_c, new_h)
+
+
+rnn = types.ModuleType("tensorflow.contrib.rnn")
+rnn.BasicLSTMCell = _LSTMCell
+contrib.rnn = rnn
+
+
+def _exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase=False, name=None):
+    p = f32(global_step) / f32(decay_steps)                # Cast, Cast, RealDiv (the op sequence of the saved graph)
+    if staircase:
+        p = np.floor(p)
+    return f32(learning_rate) * np.power(f32(decay_rate), p)
+
+
+def _scalar(name, value):
+    summaries[name] = float(value)
+
+
+def _image(name, tensor_, max_outputs=3):
+    summaries["image:" + name] = np.asarray(tensor_)
+
+
+summary = types.SimpleNamespace(scalar=_scalar, image=_image, histogram=lambda *a, **k: None)
+
+
+def _resize_images(images, size):
+    """tf.image.resize_images (bilinear, align_corners=False), as oracle/tfgraph/interp.py::op_ResizeBilinear."""
+    oh, ow = int(size[0]), int(size[1])
+    _, H, W, _ = images.shape
+
+    def axis(n_in, n_out):
+        src = np.arange(n_out, dtype=f32) * (f32(n_in) / f32(n_out))
+        lo = np.floor(src).astype(np.int64)
+        return lo, np.minimum(lo + 1, n_in - 1), (src - lo.astype(f32)).astype(f32)
+    y0, y1, ly = axis(H, oh)
+    x0, x1, lx = axis(W, ow)
+    lx, ly = lx[None, None, :, None], ly[None, :, None, None]
+    top = images[:, y0][:, :, x0] + (images[:, y0][:, :, x1] - images[:, y0][:, :, x0]) * lx
+    bottom = images[:, y1][:, :, x0] + (images[:, y1][:, :, x1] - images[:, y1][:, :, x0]) * lx
+    return top + (bottom - top) * ly
+
+
+def _draw_bounding_boxes(images, boxes):
+    out = np.array(images, copy=True)
+    B, H, W, _ = out.shape
+    for b in builtins.range(B):
+        for ymin, xmin, ymax, xmax in np.asarray(boxes[b]):
+            r0, r1, c0, c1 = int(ymin * (H - 1)), int(ymax * (H - 1)), int(xmin * (W - 1)), int(xmax * (W - 1))
+            out[b, r0, c0:c1 + 1] = out[b, r1, c0:c1 + 1] = 1.0          # first colour of the table, first channel
+            out[b, r0:r1 + 1, c0] = out[b, r0:r1 + 1, c1] = 1.0
+    return out
+
+
+image = types.SimpleNamespace(resize_images=_resize_images, draw_bounding_boxes=_draw_bounding_boxes)
+
+
+def _conv2d(inputs, filters, kernel_size, strides, padding, activation, reuse=None, name=None):
+    """tf.layers.conv2d, 'same', stride 1, NHWC x HWIO; variables ``<scope>/<name>/kernel|bias``."""
+    assert padding == "same" and tuple(strides) == (1, 1)
+    scope_name = "/".join(_scopes + [name])
+    w, b = _param(scope_name + "/kernel"), _param(scope_name + "/bias")
+    kh, kw = kernel_size
+    B, H, W, _ = inputs.shape
+    x = np.pad(inputs, [(0, 0), (kh // 2, kh // 2), (kw // 2, kw // 2), (0, 0)])
+    out = np.zeros((B, H, W, filters), f32)
+    for ky in builtins.range(kh):
+        for kx in builtins.range(kw):
+            out += np.matmul(x[:, ky:ky + H, kx:kx + W, :], w[ky, kx])
+    return activation(out + b)
+
+
+def _max_pooling2d(inputs, pool_size, strides, name=None):
+    assert tuple(pool_size) == (2, 2) and strides == 2
+    B, H, W, C = inputs.shape
+    x = inputs[:, :H // 2 * 2, :W // 2 * 2]
+    return x.reshape(B, H // 2, 2, W // 2, 2, C).max(axis=(2, 4))
+
+
+layers = types.SimpleNamespace(conv2d=_conv2d, max_pooling2d=_max_pooling2d)        # tf.layers
+
+
+class _TrainNS:
+    exponential_decay = staticmethod(_exponential_decay)
+
+    def __getattr__(self, name):
+        return getattr(example_classes_cached(), name)
+
+
+train = _TrainNS()
+
+
+def _wrap_module():
+    """Every function above returns plain ndarrays; the reference also calls ``.set_shape`` / ``.get_shape`` on
+    tensors and applies functions to Python floats, so: results become _Arr views, float arguments become float32."""
+    import functools
+
+    def conv(v):
+        if isinstance(v, np.ndarray) and not isinstance(v, _Arr):
+            return v.view(_Arr)
+        if isinstance(v, tuple):
+            return tuple(conv(x) for x in v)
+        return v
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(*a, **k):
+            a = [f32(x) if isinstance(x, float) else x for x in a]
+            k.pop("name", None)                          # graph-node names mean nothing here
+            return conv(fn(*a, **k))
+        return inner
+    g = globals()
+    skip = {"installed", "variable_scope", "load_reference_module", "example_classes", "example_classes_cached",
+            "masked_crc32c", "tf_record_iterator", "tensor", "get_variable_scope", "while_loop", "trainable_variables",
+            "constant_initializer"}
+    for name, fn in list(g.items()):
+        if isinstance(fn, types.FunctionType) and fn.__module__ == __name__ and not name.startswith("_") and name not in skip:
+            g[name] = wrap(fn)
+    for ns in (nn, image):
+        for name, fn in list(vars(ns).items()):
+            setattr(ns, name, wrap(fn))
+    contrib_layers.fully_connected = wrap(_fully_connected)
+    _LSTMCell.__call__ = (lambda f: lambda self, *a, **k: conv(f(self, *a, **k)))(_LSTMCell.__call__)
+    _LSTMCell.zero_state = (lambda f: lambda self, *a, **k: conv(f(self, *a, **k)))(_LSTMCell.zero_state)
+    TensorArray.stack = (lambda f: lambda self: conv(f(self)))(TensorArray.stack)
+
+
+_Arr.set_shape = lambda self, shape: None
+_wrap_module()

@@ -108,3 +108,93 @@ def test_vae_source(ref):
     assert latent is mean
     for got, want in ((orec, rec), (omean, mean), (ologvar, logvar), (olatent, mean)):
         np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=2e-6)
+
+
+def _run_source_model(imgs, cnt, params, noise, T=3, cnn=False, global_step=0, **kw):
+    """AIRModel of the checked-in air/air_model.py (train=False: the optimizer is not built), executed eagerly by the
+    shim: tf.while_loop is a Python loop, TensorArrays are lists, variables come from ``params``, the five noise
+    tensors of every step are served in call order (scale, shift, VAE latent, VAE likelihood normals; Concrete uniform)."""
+    import importlib
+    import sys
+    normal, uniform = [], []
+    for t in range(T):
+        normal += [noise[k][t].numpy() for k in ("scale", "shift", "vae_latent", "vae_like")]
+        uniform.append(noise["concrete_u"][t].numpy())
+    P = {k: v.numpy() for k, v in params.items()}
+    with S.installed(uniform=uniform, normal=normal, params=P, global_step=global_step):
+        sys.path.insert(0, "/root/reference")
+        try:
+            mod = importlib.import_module("air.air_model")
+            hyper = dict(O.DEFAULT_HYPER, **kw)
+            hyper.update(cnn=cnn, max_steps=T)
+            m = mod.AIRModel(S.tensor(imgs.numpy()), S.tensor(cnt.numpy().astype(np.int32)), train=False,
+                             annealing_schedules=O.DEFAULT_ANNEALING, **hyper)
+            return m, dict(S.summaries)
+        finally:
+            sys.path.remove("/root/reference")
+            for k in [k for k in sys.modules if k == "air" or k.startswith("air.")]:
+                del sys.modules[k]
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+PER_STEP = ("rec_scales", "rec_shifts", "rec_st_back", "rec_windows", "rec_latents", "z_pres_probs", "z_pres_kls",
+            "scale_kls", "shift_kls", "vae_kls")
+
+
+@pytest.mark.parametrize("fixture,seed,T", [("realistic", 2, 3), ("default", 1, 3), ("realistic", 8, 5)])
+def test_air_model_source_forward(fixture, seed, T):
+    """The whole forward model of the CHECKED-IN source (air_model.py:269-611, test mode) against the oracle: digit
+    counts exact, every per-step output <= 1e-5 -- including rec_latents, which at this revision is the recognition
+    mean (the saved graph is older there) -- plus the 88 scalar summaries and the image summary the source builds."""
+    import types
+    import air_b200 as ab
+    from tests import parity_util as PU
+    imgs, cnt, params, noise = getattr(PU, fixture + "_fixture")(64, seed=seed, T=T)
+    m, summ = _run_source_model(imgs, cnt, params, noise, T=T)
+    out = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False, max_steps=T).forward(imgs, cnt, noise)
+    assert np.array_equal(m.rec_num_digits, out["rec_num_digits"].numpy()) and len(np.unique(m.rec_num_digits)) >= 3
+    for k in PER_STEP:
+        got = np.asarray(getattr(m, k))
+        assert got.shape == tuple(out[k].shape) and _rel(got, out[k].numpy()) < 1e-5, (k, _rel(got, out[k].numpy()))
+    assert float(m.accuracy) == pytest.approx(float(out["accuracy"]), abs=1e-7)
+    if T != 3:
+        return                                            # the source's step summaries index max_steps columns
+    # summaries: host logic of demo/model_wrapper.py and demo/visualize.py fed with the SOURCE model's own tensors
+    stand = types.SimpleNamespace(max_digits=2, max_steps=3, **{
+        k: torch.from_numpy(np.asarray(getattr(m, k))) for k in PER_STEP + ("rec_num_digits", "reconstruction_loss")})
+    stand.loss_per_item = stand.reconstruction_loss + out["running_loss"]
+    got = ab.evaluation_summaries(stand, cnt)
+    scalars = {k: v for k, v in summ.items() if not k.startswith("image:")}
+    assert set(got) == set(scalars) and len(scalars) == 88
+    for k, v in scalars.items():
+        tol = 1e-5 if "total_loss" not in k else 1e-4     # total_loss adds the oracle's running KL sum
+        assert (np.isnan(v) and np.isnan(got[k])) or got[k] == pytest.approx(v, rel=tol, abs=1e-6), (k, got[k], v)
+    vis = ab.visualize_reconstructions(imgs[:60], torch.from_numpy(np.asarray(m.reconstruction))[:60],
+                                       torch.from_numpy(np.asarray(m.rec_st_back))[:60],
+                                       torch.from_numpy(np.asarray(m.rec_num_digits))[:60], transformer=O.transformer)
+    assert np.array_equal(vis.numpy(), summ["image:reconstruction"])
+
+
+def test_air_model_source_covered_loss_and_cnn_frontend():
+    from tests import parity_util as PU
+    imgs, cnt, params, noise = PU.covered_fixture(64, seed=3)
+    m, _ = _run_source_model(imgs, cnt, params, noise, global_step=2000)
+    orc = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False)
+    orc.global_step = 2000
+    out = orc.forward(imgs, cnt, noise)
+    assert abs(float(m.loss) - float(out["loss"])) <= 1e-6 * abs(float(out["loss"]))
+    assert _rel(np.asarray(m.reconstruction_loss), out["reconstruction_loss"].numpy()) < 1e-6
+    # cnn=True (air_model.py:510-535): the source's wiring of the front-end (three 5x5 convs, two 2x2 pools, NHWC
+    # flatten to 12*12*8) with the shim's plain-numpy conv; features and the model on top of them follow the oracle
+    imgs, cnt, params, noise = PU.covered_fixture(16, seed=4, cnn=True)
+    m, _ = _run_source_model(imgs, cnt, params, noise, cnn=True)
+    feat = O.cnn_frontend(imgs, params)
+    assert np.asarray(m.rnn_input).shape == (16, 1152) and _rel(np.asarray(m.rnn_input), feat.numpy()) < 1e-5
+    out = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False, cnn=True).forward(imgs, cnt, noise)
+    assert np.array_equal(m.rec_num_digits, out["rec_num_digits"].numpy())
+    for k in PER_STEP:
+        assert _rel(np.asarray(getattr(m, k)), out[k].numpy()) < 1e-5, k
