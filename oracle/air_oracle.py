@@ -14,7 +14,9 @@ ApplyAdam, test model) executed by the numpy graph interpreter in oracle/tfgraph
 tests/test_reference_graph.py: ST bit-exact, loss identical, 36 gradients <= 7e-7 on the
 covered fixture, fp64 agreement on realistic poses.  TensorFlow's own kernels never ran:
 the per-op arithmetic of that interpreter is itself restated.  The
-cnn=True front-end is not part of the saved graph and stays restated-only.  TF-library semantics that cannot be read from the reference tree
+checked-in SOURCE (air/*.py, whole AIRModel in test mode incl. the cnn=True branch that no
+saved graph contains) is also executed, through the numpy tf shim oracle/tfgraph/tf_shim.py,
+and compared with this file in tests/test_reference_source.py.  TF-library semantics that cannot be read from the reference tree
 (LSTM gate order, softplus thresholds, Adam epsilon placement ...) are restated from the
 published TF 1.3 behaviour and are listed in SURVEY.md section 8(c).
 

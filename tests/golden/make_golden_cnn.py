@@ -1,7 +1,8 @@
 """Golden vector of the CNN front-end restatement (oracle.cnn_frontend, air_model.py:510-535): inputs, the six
 conv tensors, the [B,1152] feature map and the parameter gradients of a fixed linear functional of it.
-PARITY UNPINNED for this part: the cnn=True front-end is not in the reference's saved graph, so this is an oracle
-regression pin (torch conv2d, cross-checked against plain-C loops), not a reference output.
+The cnn=True front-end is not in the reference's saved graph: its wiring is pinned by executing the source through the
+tf shim (tests/test_reference_source.py); this file is an oracle regression pin of the convolution arithmetic (torch
+conv2d, cross-checked against plain-C loops), not a reference output.
 
     python tests/golden/make_golden_cnn.py
 """
