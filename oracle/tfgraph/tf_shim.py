@@ -337,11 +337,6 @@ def tf_record_iterator(path):
 python_io = types.SimpleNamespace(TFRecordWriter=TFRecordWriter, tf_record_iterator=tf_record_iterator)
 
 
-class _Train:
-    def __getattr__(self, name):
-        return getattr(example_classes_cached(), name)
-
-
 _example_cache = []
 
 
@@ -349,9 +344,6 @@ def example_classes_cached():
     if not _example_cache:
         _example_cache.append(example_classes())
     return _example_cache[0]
-
-
-train = _Train()
 
 
 class NumpyCompat:
@@ -589,6 +581,7 @@ layers = types.SimpleNamespace(conv2d=_conv2d, max_pooling2d=_max_pooling2d)    
 
 
 class _TrainNS:
+    """tf.train: exponential_decay, and the Example / Features / Feature / *List message classes."""
     exponential_decay = staticmethod(_exponential_decay)
 
     def __getattr__(self, name):
