@@ -1,15 +1,19 @@
-"""A numpy stand-in for the handful of ``tf.*`` calls made by the reference's ``air/transformer.py`` and
-``air/concrete.py``, so that THEIR SOURCE runs unmodified without TensorFlow (test infrastructure).
+"""A numpy stand-in for the ``tf.*`` calls made by the reference's ``air/transformer.py``, ``air/concrete.py``,
+``air/vae.py``, ``air/air_model.py`` (forward model, train=False) and ``multi_mnist.py`` (TFRecord writer / reader), so
+that THEIR SOURCE runs unmodified without TensorFlow (test infrastructure).
 
     with tf_shim.installed(uniform=u):                    # sys.modules["tensorflow"] = this module, temporarily
         ref = tf_shim.load_reference_module("/root/reference/air/transformer.py")
     out = ref.transformer(U, theta, (28, 28))
 
-Tensors are plain float32 / int32 numpy arrays, every function is eager, one rounding per op like TF's executor
-(matmul with a float inner dimension sums separately rounded products in k order: no FMA, as oracle/tfgraph/interp.py).
-``tf.random_uniform`` returns the array given to ``installed(uniform=...)`` (noise is always injected here).
-Complements the graph interpreter: the saved graph pins what training.py built; this pins the functions of the checked-in
-source that the graph does not contain (batch_transformer, concrete_binary_sample with hard=True)."""
+Tensors are float32 / int32 numpy arrays, every function is eager, one rounding per op like TF's executor (matmul with
+a float inner dimension of the Spatial Transformer sums separately rounded products in k order: no FMA, as
+oracle/tfgraph/interp.py).  ``tf.while_loop`` is a Python loop, TensorArrays are lists, variables are looked up in the
+parameter dict given to ``installed(params=...)``, ``tf.random_uniform`` / ``tf.random_normal`` serve the injected noise
+in call order, summaries are collected in ``summaries``.  Not supported: anything that needs autodiff (train=True).
+Complements the graph interpreter: the saved graph pins what training.py built (including the gradient graph); this
+pins the checked-in revision of the source, and the parts no saved graph contains (batch_transformer,
+concrete_binary_sample with hard=True, the cnn=True front-end's wiring, the TFRecord functions)."""
 import builtins
 import contextlib
 import importlib.util
