@@ -584,9 +584,30 @@ def _max_pooling2d(inputs, pool_size, strides, name=None):
 layers = types.SimpleNamespace(conv2d=_conv2d, max_pooling2d=_max_pooling2d)        # tf.layers
 
 
+class _NoOptimizer:
+    """tf.train.AdamOptimizer stand-in for train=True FORWARD runs: there is no autodiff here, so compute_gradients
+    reports one variable without a gradient (the source skips ``None`` gradients) and apply_gradients does nothing.
+    The gradient graph, clipping and ApplyAdam are pinned by the saved graph instead (oracle/tfgraph/interp.py)."""
+
+    def __init__(self, learning_rate):
+        self.learning_rate = learning_rate
+
+    def compute_gradients(self, loss):
+        return [(None, types.SimpleNamespace(name="no_autodiff_in_the_shim"))]
+
+    def apply_gradients(self, grads_and_vars, global_step=None):
+        return None
+
+
+def clip_by_global_norm(grads, clip_norm):
+    assert all(g is None for g in grads)
+    return list(grads), None
+
+
 class _TrainNS:
     """tf.train: exponential_decay, and the Example / Features / Feature / *List message classes."""
     exponential_decay = staticmethod(_exponential_decay)
+    AdamOptimizer = _NoOptimizer
 
     def __getattr__(self, name):
         return getattr(example_classes_cached(), name)
@@ -617,7 +638,7 @@ def _wrap_module():
     g = globals()
     skip = {"installed", "variable_scope", "load_reference_module", "example_classes", "example_classes_cached",
             "masked_crc32c", "tf_record_iterator", "tensor", "get_variable_scope", "while_loop", "trainable_variables",
-            "constant_initializer"}
+            "constant_initializer", "clip_by_global_norm"}
     for name, fn in list(g.items()):
         if isinstance(fn, types.FunctionType) and fn.__module__ == __name__ and not name.startswith("_") and name not in skip:
             g[name] = wrap(fn)

@@ -110,7 +110,7 @@ def test_vae_source(ref):
         np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=2e-6)
 
 
-def _run_source_model(imgs, cnt, params, noise, T=3, cnn=False, global_step=0, **kw):
+def _run_source_model(imgs, cnt, params, noise, T=3, cnn=False, global_step=0, train=False, **kw):
     """AIRModel of the checked-in air/air_model.py (train=False: the optimizer is not built), executed eagerly by the
     shim: tf.while_loop is a Python loop, TensorArrays are lists, variables come from ``params``, the five noise
     tensors of every step are served in call order (scale, shift, VAE latent, VAE likelihood normals; Concrete uniform)."""
@@ -127,7 +127,7 @@ def _run_source_model(imgs, cnt, params, noise, T=3, cnn=False, global_step=0, *
             mod = importlib.import_module("air.air_model")
             hyper = dict(O.DEFAULT_HYPER, **kw)
             hyper.update(cnn=cnn, max_steps=T)
-            m = mod.AIRModel(S.tensor(imgs.numpy()), S.tensor(cnt.numpy().astype(np.int32)), train=False,
+            m = mod.AIRModel(S.tensor(imgs.numpy()), S.tensor(cnt.numpy().astype(np.int32)), train=train,
                              annealing_schedules=O.DEFAULT_ANNEALING, **hyper)
             return m, dict(S.summaries)
         finally:
@@ -196,5 +196,26 @@ def test_air_model_source_covered_loss_and_cnn_frontend():
     assert np.asarray(m.rnn_input).shape == (16, 1152) and _rel(np.asarray(m.rnn_input), feat.numpy()) < 1e-5
     out = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=False, cnn=True).forward(imgs, cnt, noise)
     assert np.array_equal(m.rec_num_digits, out["rec_num_digits"].numpy())
+    for k in PER_STEP:
+        assert _rel(np.asarray(getattr(m, k)), out[k].numpy()) < 1e-5, k
+
+
+def test_air_model_source_train_mode_forward(golden_dir):
+    """train=True forward of the source (continuous z_pres; the optimizer is a no-op stand-in, there is no autodiff in
+    the shim): on the covered fixture the loss equals the oracle's AND the saved graph's (5730.3291), i.e. source,
+    graph and oracle agree on the training objective; on realistic poses the per-step quantities and masks agree."""
+    from tests import parity_util as PU
+    g = np.load(os.path.join(golden_dir, "ref_graph_train_covered.npz"))
+    imgs, cnt, params, noise = PU.covered_fixture(64, seed=3)
+    m, _ = _run_source_model(imgs, cnt, params, noise, global_step=2000, train=True)
+    assert m.training is None and abs(float(m.loss) - float(g["loss"])) <= 1e-6 * float(g["loss"])
+    for k in ("rec_scales", "rec_shifts", "z_pres_kls", "scale_kls", "shift_kls", "vae_kls"):
+        assert _rel(np.asarray(getattr(m, k)).reshape(g[k].shape), g[k]) < 1e-6, k
+    imgs, cnt, params, noise = PU.realistic_fixture(64, seed=1)
+    m, _ = _run_source_model(imgs, cnt, params, noise, global_step=2000, train=True)
+    orc = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=True)
+    orc.global_step = 2000
+    out = orc.forward(imgs, cnt, noise)
+    assert np.array_equal(m.rec_num_digits, out["rec_num_digits"].numpy()) and len(np.unique(m.rec_num_digits)) >= 3
     for k in PER_STEP:
         assert _rel(np.asarray(getattr(m, k)), out[k].numpy()) < 1e-5, k
