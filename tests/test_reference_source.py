@@ -219,3 +219,30 @@ def test_air_model_source_train_mode_forward(golden_dir):
     assert np.array_equal(m.rec_num_digits, out["rec_num_digits"].numpy()) and len(np.unique(m.rec_num_digits)) >= 3
     for k in PER_STEP:
         assert _rel(np.asarray(getattr(m, k)), out[k].numpy()) < 1e-5, k
+
+
+def test_transformer_source_fuzz(ref):
+    """Property test: for random shapes (1..6 images, 1..12 x 1..12 pixels, 1..3 channels, 1..9 x 1..9 outputs) and
+    random affine maps -- tiny / huge scales, far-off shifts, exact identity, all-zero theta -- the C restatement and the
+    torch restatement reproduce the source's transformer() bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(st.integers(1, 6), st.integers(1, 12), st.integers(1, 12), st.integers(1, 3), st.integers(1, 9),
+           st.integers(1, 9), st.integers(0, 2 ** 31 - 1), st.sampled_from(["affine", "identity", "zero", "huge", "tiny"]))
+    def check(B, H, W, C_, oh, ow, seed, kind):
+        rng = np.random.default_rng(seed)
+        U = rng.uniform(-1, 1, (B, H, W, C_)).astype(np.float32)
+        th = rng.uniform(-1.5, 1.5, (B, 6)).astype(np.float32)
+        if kind == "identity":
+            th[:] = [1, 0, 0, 0, 1, 0]
+        elif kind == "zero":
+            th[:] = 0
+        elif kind == "huge":
+            th *= np.float32(1e4)
+        elif kind == "tiny":
+            th *= np.float32(1e-6)
+        want = ref[0].transformer(U, th, (oh, ow))
+        assert np.array_equal(C.st_forward(U, th, (oh, ow)), want)
+        assert np.array_equal(O.transformer(torch.from_numpy(U), torch.from_numpy(th), (oh, ow)).numpy(), want)
+    check()
