@@ -246,3 +246,24 @@ def test_transformer_source_fuzz(ref):
         assert np.array_equal(C.st_forward(U, th, (oh, ow)), want)
         assert np.array_equal(O.transformer(torch.from_numpy(U), torch.from_numpy(th), (oh, ow)).numpy(), want)
     check()
+
+
+def test_air_model_source_non_default_sizes():
+    """Other constructor sizes (40x40 canvas, 20x20 window, 128 LSTM units, narrower VAE and heads -- the shapes of
+    tests/test_gpu_model.py::test_train_parity_non_default_sizes): the source run through the shim and the oracle agree,
+    so the oracle's handling of the size hyper-parameters is the reference's."""
+    B, cs, ws = 6, 40, 20
+    kw = dict(canvas_size=cs, windows_size=ws, rnn_units=128, vae_latent_dimensions=24, vae_recognition_units=(96, 64),
+              vae_generative_units=(64, 96), scale_hidden_units=32, shift_hidden_units=32, z_pres_hidden_units=32)
+    imgs, cnt = O.synthetic_canvases(B, canvas_size=cs, seed=5, digit_size=(10, 16))
+    params = O.init_params(seed=5, **{k: v for k, v in kw.items()})
+    params["z_pres/log_odds/output/biases"] += 1.0
+    noise = O.make_noise(5, 3, B, latent=24, win=ws * ws)
+    for train in (False, True):
+        m, _ = _run_source_model(imgs, cnt, params, noise, train=train, **kw)
+        out = O.AIROracle(params=params, annealing_schedules=O.DEFAULT_ANNEALING, train=train, **kw).forward(imgs, cnt, noise)
+        assert np.array_equal(m.rec_num_digits, out["rec_num_digits"].numpy())
+        for k in PER_STEP:
+            got = np.asarray(getattr(m, k))
+            assert got.shape == tuple(out[k].shape) and _rel(got, out[k].numpy()) < 1e-5, (train, k)
+        assert np.asarray(m.reconstruction).shape == (B, cs * cs)
