@@ -110,7 +110,8 @@ def test_vae_source(ref):
         np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=2e-6)
 
 
-def _run_source_model(imgs, cnt, params, noise, T=3, cnn=False, global_step=0, train=False, **kw):
+def _run_source_model(imgs, cnt, params, noise, T=3, cnn=False, global_step=0, train=False,
+                      annealing=O.DEFAULT_ANNEALING, **kw):
     """AIRModel of the checked-in air/air_model.py (train=False: the optimizer is not built), executed eagerly by the
     shim: tf.while_loop is a Python loop, TensorArrays are lists, variables come from ``params``, the five noise
     tensors of every step are served in call order (scale, shift, VAE latent, VAE likelihood normals; Concrete uniform)."""
@@ -128,7 +129,7 @@ def _run_source_model(imgs, cnt, params, noise, T=3, cnn=False, global_step=0, t
             hyper = dict(O.DEFAULT_HYPER, **kw)
             hyper.update(cnn=cnn, max_steps=T)
             m = mod.AIRModel(S.tensor(imgs.numpy()), S.tensor(cnt.numpy().astype(np.int32)), train=train,
-                             annealing_schedules=O.DEFAULT_ANNEALING, **hyper)
+                             annealing_schedules=annealing, **hyper)
             return m, dict(S.summaries)
         finally:
             sys.path.remove("/root/reference")
@@ -267,3 +268,27 @@ def test_air_model_source_non_default_sizes():
             got = np.asarray(getattr(m, k))
             assert got.shape == tuple(out[k].shape) and _rel(got, out[k].numpy()) < 1e-5, (train, k)
         assert np.asarray(m.reconstruction).shape == (B, cs * cs)
+
+
+def test_air_model_source_other_hyper_parameters():
+    """Every scalar hyper-parameter of the constructor moved off its default (priors, temperature, threshold,
+    likelihood std, a fixed instead of an annealed z_pres prior; an annealed schedule with staircase / max): per-step
+    outputs, KL terms and the covered-fixture loss of the source and of the oracle agree."""
+    from tests import parity_util as PU
+    kw = dict(scale_prior_mean=-0.5, scale_prior_variance=0.2, shift_prior_mean=0.1, shift_prior_variance=0.5,
+              vae_prior_mean=0.2, vae_prior_variance=2.0, vae_likelihood_std=0.1, z_pres_prior_log_odds=-2.0,
+              z_pres_temperature=0.5, stopping_threshold=0.8)
+    schedules = (None, {"z_pres_prior_log_odds": {"init": 50.0, "factor": 0.5, "iters": 1000, "staircase": True,
+                                                  "max": 20.0, "min": 0.001, "log": True}})
+    for annealing in schedules:
+        for fixture, train in ((PU.covered_fixture, True), (PU.realistic_fixture, False)):
+            imgs, cnt, params, noise = fixture(32, seed=11)
+            m, _ = _run_source_model(imgs, cnt, params, noise, train=train, annealing=annealing, global_step=2500, **kw)
+            orc = O.AIROracle(params=params, annealing_schedules=annealing, train=train, **kw)
+            orc.global_step = 2500
+            out = orc.forward(imgs, cnt, noise)
+            assert np.array_equal(m.rec_num_digits, out["rec_num_digits"].numpy())
+            for k in PER_STEP:
+                assert _rel(np.asarray(getattr(m, k)), out[k].numpy()) < 1e-5, (k, train, annealing is None)
+            if fixture is PU.covered_fixture:
+                assert abs(float(m.loss) - float(out["loss"])) <= 2e-6 * abs(float(out["loss"]))
