@@ -16,7 +16,9 @@ python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_refere
 # 4. ncu launch list of the FINAL 75-kernel train step (the committed r1_train_launches_e.md predates two ST changes)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 260 --csv --log-file gpurun_out/launches_train.csv \
     python bench.py --workload train --steps 3 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
-python profiles/summarize_launches.py gpurun_out/launches_train.csv > gpurun_out/train_launches.md 2>&1 || true
+python profiles/summarize_launches.py gpurun_out/launches_train.csv "train step launch list, final schedule, TF32 mode, B=4096" \
+    "ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 260 --csv python bench.py --workload train --steps 3 --warmup 3" \
+    > gpurun_out/train_launches.md 2>&1 || true
 # 5. training through the CUDA path on synthetic canvases (counterpart of profiles/r1_oracle_convergence.log)
 timeout 600 python examples/train_synthetic.py --iters 25000 --every 1000 --log gpurun_out/gpu_convergence.log \
     > gpurun_out/gpu_convergence.out 2>&1
