@@ -420,3 +420,24 @@ def test_protobuf_decoder_on_hand_assembled_messages():
     assert nd.attr["cval"].dtype == np.int64 and list(nd.attr["cval"]) == [5, -6]
     assert nd.attr["i"] == -3 and nd.attr["f"] == 0.25 and nd.attr["b"] is True and nd.attr["s"] == b"frame"
     assert nd.attr["shape"] == ("shape", [-1, 2500]) and nd.attr["list"] == [1, 2, -1]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
+def test_fused_canvas_update_bit_exact_with_the_graph(golden_dir):
+    """ST write-back + z_pres scaling + stop-mask select + accumulation (air_model.py:363-366, 429-439) as the graph
+    wires them, fed with the committed st.npz operands (incl. stopping sums exactly AT the threshold): the C
+    restatement of the fused op (what air_st_writeback_canvas_fwd is tested against) is bit-exact."""
+    g = _g(golden_dir, "st.npz")
+    n = len(g["z"])
+    assert n <= 64
+    pad = lambda a: np.concatenate([a, np.zeros((64 - n,) + a.shape[1:], a.dtype)])     # noqa: E731  (graph batch = 64)
+    window_st = pad(g["back"].reshape(n, 50, 50))         # ST(window, theta_inv), itself bit-exact (test above)
+    nodes = pb.load_metagraph(G.META)
+    I = Interpreter(nodes, {}, {"air/rnn/while/st_backward/strided_slice:0": window_st,
+                                "air/rnn/while/z_pres/gumbel/Sigmoid:0": pad(g["z"]),
+                                "air/rnn/while/add:0": pad(g["stop"]),
+                                "air/rnn/while/Identity_4:0": pad(g["canvas"])})
+    got = I.eval("air/rnn/while/canvas/add", 0, 0)[:n]
+    assert np.array_equal(got, g["canvas_out"])
+    assert np.array_equal(got, C.canvas_update(g["canvas"], g["back"].reshape(-1, 2500), g["z"], g["stop"], 0.99))
+    assert (g["stop"] == np.float32(0.99)).any()          # 0.99 itself is NOT < 0.99: those rows stay untouched
