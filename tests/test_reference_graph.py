@@ -441,3 +441,34 @@ def test_fused_canvas_update_bit_exact_with_the_graph(golden_dir):
     assert np.array_equal(got, g["canvas_out"])
     assert np.array_equal(got, C.canvas_update(g["canvas"], g["back"].reshape(-1, 2500), g["z"], g["stop"], 0.99))
     assert (g["stop"] == np.float32(0.99)).any()          # 0.99 itself is NOT < 0.99: those rows stay untouched
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("scope,train", [("air", 1), ("air_1", 0)])
+def test_concrete_act_step_subgraph(golden_dir, scope, train):
+    """Concrete sample, its MC KL against the (annealed) prior, the z_pres KL masked by the OLD stopping sum, the new
+    stopping sum and the digit counter, evaluated inside the reference graph's loop body for fed log-odds / uniform
+    noise / loop state (train graph: continuous z; test graph: tf.round): the C restatement of the fused step (what
+    air_concrete_step_fwd is tested against) gives the same integers and masks exactly and the floats to an ulp of
+    log/exp."""
+    g = _g(golden_dir, "concrete.npz")
+    w = f"{scope}/rnn/while/"
+    nodes = pb.load_metagraph(G.META)
+    I = Interpreter(nodes, {}, {w + "z_pres/log_odds/output/strided_slice:0": g["log_odds"],
+                                w + "Identity_1:0": g["stop_prev"], w + "Identity_5:0": g["loss_prev"],
+                                w + "Identity_6:0": g["digits_prev"],
+                                f"{scope}/z_pres_prior_log_odds_log:0": np.float32(g["prior"])},
+                    random_fn=lambda node, it, shape: g["u"])
+    want = C.concrete_step(g["log_odds"], g["u"], g["stop_prev"], g["loss_prev"], g["digits_prev"], float(g["prior"]),
+                           1.0, 0.99, train)
+    z_node = "z_pres/gumbel/Round" if not train else "z_pres/gumbel/Sigmoid"
+    got = {"y": I.eval(w + "z_pres/gumbel/truediv", 0, 0), "z": I.eval(w + z_node, 0, 0),
+           "kl": I.eval(w + "loss/z_pres_kl/sub_4", 0, 0), "loss_new": I.eval(w + "loss/z_pres_kl/add_8", 0, 0),
+           "stop_new": I.eval(w + "add", 0, 0), "digits_new": I.eval(w + "add_1", 0, 0)}
+    assert np.array_equal(got["digits_new"], want["digits_new"])
+    assert np.array_equal(got["stop_new"] < np.float32(0.99), want["stop_new"] < np.float32(0.99))
+    assert np.array_equal(got["loss_new"] != g["loss_prev"], want["loss_new"] != g["loss_prev"])     # same KL mask
+    if not train:
+        assert np.array_equal(got["z"], want["z"]) and np.array_equal(got["stop_new"], want["stop_new"])
+    for k in ("y", "z", "kl", "loss_new", "stop_new"):
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-6, atol=2e-6, err_msg=k)
