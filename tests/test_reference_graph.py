@@ -472,3 +472,32 @@ def test_concrete_act_step_subgraph(golden_dir, scope, train):
         assert np.array_equal(got["z"], want["z"]) and np.array_equal(got["stop_new"], want["stop_new"])
     for k in ("y", "z", "kl", "loss_new", "stop_new"):
         np.testing.assert_allclose(got[k], want[k], rtol=2e-6, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
+def test_reconstruction_loss_and_its_gradient_tie_rules():
+    """air_model.py:580-593 and the gradient TF generated for it, with canvas values exactly at and beyond the clip
+    bounds: the loss vector, and d(mean loss)/d(canvas) -- MinimumGrad passes where canvas <= 1, MaximumGrad where the
+    clipped value >= 0, so the gradient passes AT 0.0 and AT 1.0 and is blocked outside -- equal the oracle's."""
+    rng = np.random.default_rng(9)
+    canvas = rng.uniform(-0.2, 1.2, (64, 2500)).astype(np.float32)
+    canvas.ravel()[::7] = 0.0
+    canvas.ravel()[3::11] = 1.0
+    canvas.ravel()[5::13] = np.float32(-1e-7)             # a negative rounding residue
+    x = (rng.uniform(0, 1, (64, 2500)) * (rng.uniform(0, 1, (64, 2500)) < 0.3)).astype(np.float32)
+    nodes = pb.load_metagraph(G.META)
+    I = Interpreter(nodes, {}, {"air/rnn/while/Exit_4:0": canvas, "pipeline/shuffle_batch:0": x,
+                                "air/rnn/while/Exit_5:0": np.zeros(64, np.float32)})
+    rec_loss = I.fetch("air/loss/reconstruction/Neg")
+    dcanvas = I.fetch("air/training/gradients/air/loss/reconstruction/Minimum_grad/tuple/control_dependency")
+    tc = torch.from_numpy(canvas).requires_grad_(True)
+    tx = torch.from_numpy(x)
+    r = torch.clamp(tc, 0.0, 1.0)                         # the oracle's statement of max(min(r, 1), 0)  (:582)
+    loss_vec = -torch.sum(tx * torch.log(r + O.EPS) + (1.0 - tx) * torch.log(1.0 - r + O.EPS), 1)
+    torch.mean(loss_vec).backward()
+    np.testing.assert_allclose(loss_vec.detach().numpy(), rec_loss, rtol=2e-6)
+    got, want = dcanvas, tc.grad.numpy()
+    assert np.array_equal(got != 0, want != 0)            # same pass / block pattern
+    assert (got[canvas == 0.0] != 0).all() and (got[canvas == 1.0] != 0).any()
+    assert (got[canvas < 0] == 0).all() and (got[canvas > 1] == 0).all()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-8)      # atol: the two terms of the derivative cancel
