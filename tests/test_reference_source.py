@@ -292,3 +292,47 @@ def test_air_model_source_other_hyper_parameters():
                 assert _rel(np.asarray(getattr(m, k)), out[k].numpy()) < 1e-5, (k, train, annealing is None)
             if fixture is PU.covered_fixture:
                 assert abs(float(m.loss) - float(out["loss"])) <= 2e-6 * abs(float(out["loss"]))
+
+
+def test_call_signatures_are_the_references(ref):
+    """Drop-in surface: parameter names, order and DEFAULT VALUES of the product's transformer /
+    batch_transformer / vae / concrete_* / AIRModel / ModelWrapper equal those of the reference's source, read with
+    inspect from the imported reference modules.  The product may only ADD keyword-only / trailing optional arguments."""
+    import importlib
+    import inspect
+    import sys
+    import air_b200 as ab
+    with S.installed():
+        sys.path.insert(0, "/root/reference")
+        try:
+            ref_model = importlib.import_module("air.air_model").AIRModel
+            ref_vae = importlib.import_module("air.vae").vae
+            ref_wrapper = importlib.import_module("demo.model_wrapper").ModelWrapper
+        finally:
+            sys.path.remove("/root/reference")
+            for k in [k for k in sys.modules if k.split(".")[0] in ("air", "demo")]:
+                del sys.modules[k]
+
+    def params(fn):
+        return [(p.name, p.default, p.kind) for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+
+    def same_prefix(ours, theirs, allow_extra=True, skip_defaults=()):
+        o, t = params(ours), params(theirs)
+        assert len(o) >= len(t), (ours, o, t)
+        for (on, od, ok), (tn, td, tk) in zip(o, t):
+            assert on == tn and ok == tk, (ours.__name__, on, tn)
+            if tn not in skip_defaults:
+                assert od == td or (od is inspect.Parameter.empty and td is inspect.Parameter.empty), (ours.__name__, on, od, td)
+        for name, default, kind in o[len(t):]:             # additions must be optional
+            assert allow_extra and (default is not inspect.Parameter.empty or kind == inspect.Parameter.VAR_KEYWORD), name
+
+    same_prefix(ab.transformer, ref[0].transformer)
+    same_prefix(ab.batch_transformer, ref[0].batch_transformer)
+    same_prefix(ab.AIRModel.__init__, ref_model.__init__)
+    assert [n for n, _, k in params(ab.AIRModel.__init__)[len(params(ref_model.__init__)):]
+            if k != inspect.Parameter.KEYWORD_ONLY] == []   # gemm_mode / seed / process_group are keyword-only
+    same_prefix(ab.ModelWrapper.__init__, ref_wrapper.__init__, skip_defaults=("session", "data_placeholder"))
+    assert params(ab.ModelWrapper.infer)[0][0] == params(ref_wrapper.infer)[0][0] == "images"
+    same_prefix(ab.vae, ref_vae, skip_defaults=("activation",))      # default activation: softplus in both, other objects
+    for name in ("concrete_binary_sample", "concrete_binary_pre_sigmoid_sample", "concrete_binary_kl_mc_sample"):
+        same_prefix(getattr(ab, name), getattr(ref[1], name))
