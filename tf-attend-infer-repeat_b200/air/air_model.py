@@ -103,9 +103,10 @@ class AIRModel:
                 raise NotImplementedError(f"annealing of {name!r} is not supported on device "
                                           f"(supported: {_DEVICE_ANNEALABLE})")
         # derived constants the reference also keeps on the model (air_model.py:72-74), as Python floats
-        self.scale_prior_log_variance = math.log(scale_prior_variance)
-        self.shift_prior_log_variance = math.log(shift_prior_variance)
-        self.vae_prior_log_variance = math.log(vae_prior_variance)
+        _log = lambda v: math.log(v) if v > 0 else float("-inf")
+        self.scale_prior_log_variance = _log(scale_prior_variance)
+        self.shift_prior_log_variance = _log(shift_prior_variance)
+        self.vae_prior_log_variance = _log(vae_prior_variance)
         self._prior = torch.full((1,), float(z_pres_prior_log_odds), device=self.device, dtype=torch.float32)
         self.hyper = C.Hyper(scale_prior_mean, scale_prior_variance, shift_prior_mean, shift_prior_variance,
                              vae_prior_mean, vae_prior_variance, vae_likelihood_std, z_pres_temperature,
