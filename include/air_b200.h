@@ -137,7 +137,12 @@ int air_concrete_step_bwd(const float *log_odds, const float *y, const float *z,
  * Cinit / bias / aux may be NULL; Cinit and aux use ldc; Cinit may alias C.
  * mode AIR_GEMM_FP32_EXACT: SIMT FFMA, one FMA per k in strictly increasing k order
  *   (bit-reproducible, equals oracle_gemm_seq_fma);
- * mode AIR_GEMM_TF32: tcgen05 tensor cores, TF32 inputs, FP32 accumulation in TMEM. */
+ * mode AIR_GEMM_TF32: tcgen05 tensor cores, operands cut to TF32 (top 19 bits), FP32 accumulation in TMEM
+ *   (~1e-3 relative: the throughput mode);
+ * mode AIR_GEMM_TF32X3: tcgen05 tensor cores at FP32 accuracy ("3xTF32"): every operand is split in-kernel into
+ *   hi + lo TF32 parts, three MMAs per k-step (hi*hi, lo*hi, hi*lo), FP32 accumulation; error ~1e-6 relative,
+ *   the same order as an FP32 FMA chain of that length.  This is the mode the model-level parity bars
+ *   (<= 1e-5 outputs / ELBO, <= 1e-4 gradients) are checked in at tensor-core speed. */
 #define AIR_EPI_NONE 0
 #define AIR_EPI_RELU 1
 #define AIR_EPI_SOFTPLUS 2      /* tf.nn.softplus: x>13.94->x, x<-13.94->exp(x), else log(exp(x)+1) */
@@ -146,11 +151,8 @@ int air_concrete_step_bwd(const float *log_odds, const float *y, const float *z,
 #define AIR_EPI_SIGMOID_NOISE 5 /* out = sigmoid(v + aux * epi_param): vae.py:36-41 (aux = N(0,1) noise, epi_param = likelihood std) */
 #define AIR_GEMM_FP32_EXACT 0
 #define AIR_GEMM_TF32 1
-/* AIR_GEMM_TF32 needs 16-byte aligned A / B with lda, ldb multiples of 4 (TMA).  GEMMs with few
- * output tiles and a long K (weight gradients) run split-K through a per-device workspace: give
- * the library a caller-owned buffer (floats; NULL detaches it) so nothing is allocated inside;
- * calls that share it must be stream-ordered.  M*N*32 floats of the largest such GEMM suffice. */
-int air_gemm_set_workspace(float *workspace, int64_t nfloats);
+#define AIR_GEMM_TF32X3 2
+/* The tensor-core modes need 16-byte aligned A / B with lda, ldb multiples of 4 (TMA). */
 int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
              int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue, int mode,
              air_stream_t stream);
@@ -158,6 +160,14 @@ int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const
 int air_gemm_ex(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
                 int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue,
                 float epi_param, int mode, air_stream_t stream);
+/* same, with a caller-owned scratch buffer (device, 16-byte aligned, workspace_floats floats; NULL = none).
+ * GEMMs with few output tiles and a long K (the weight gradients: reduction over the batch) then run split-K
+ * through it -- as many splits as fit, M*N floats each, summed in a fixed order by a second pass -- instead of
+ * leaving most SMs idle.  The library keeps no pointer to it after the call's kernels; calls sharing one
+ * buffer must be stream-ordered.  M*N*32 floats of the largest such GEMM allow every split the heuristic wants. */
+int air_gemm_ws(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
+                int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue,
+                float epi_param, int mode, float *workspace, int64_t workspace_floats, air_stream_t stream);
 
 /* ---- fused model-specific elementwise kernels (air/air_model.py loop body) ----------
  * Hyper-parameters that are plain Python floats in the reference constructor

@@ -12,7 +12,7 @@ from air_b200 import ops  # noqa: E402
 K = ab._cabi
 mode = K.GEMM_MODES[os.environ.get("MODE", "tf32")]
 ws = torch.empty(16 << 20, device="cuda")
-ops.set_gemm_workspace(ws)
+
 B, TB = 4096, 3 * 4096
 shapes = [  # name, M, N, K, tA, tB, cinit, bias, epi(aux)
     ("fwd xK", B, 1024, 2500, 0, 0, 0, 0, 0), ("fwd hKh+xk+b", B, 1024, 256, 0, 0, 1, 1, 0), ("fwd hid relu", B, 320, 256, 0, 0, 0, 1, 1),
@@ -36,7 +36,7 @@ for name, M, N, Kd, tA, tB, ci, bi, epi in shapes:
     Cinit = torch.randn(M, N, device="cuda") if ci else None
     bias = torch.randn(N, device="cuda") if bi else None
     aux = torch.rand(M, N, device="cuda") if epi in (3, 4) else None
-    run = lambda: ops.gemm(A, Bm, out, Cinit=Cinit, bias=bias, aux=aux, tA=bool(tA), tB=bool(tB), epi=epi, mode=mode)
+    run = lambda: ops.gemm(A, Bm, out, Cinit=Cinit, bias=bias, aux=aux, tA=bool(tA), tB=bool(tB), epi=epi, mode=mode, ws=ws)
     for _ in range(3):
         run()
     torch.cuda.synchronize()

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench_train
 
-m, imgs, cnt, data = bench_train._model(4096, "tf32", seed=0, train=True, max_steps=3, cnn=bool(int(os.environ.get("CNN", "0"))))
+m, imgs, cnt, data = bench_train._model(4096, os.environ.get("MODE", "tf32"), seed=0, train=True, max_steps=3, cnn=bool(int(os.environ.get("CNN", "0"))))
 for _ in range(5):
     m.train_step()
 torch.cuda.synchronize()

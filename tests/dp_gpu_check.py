@@ -54,7 +54,6 @@ gathered = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 same = all(torch.equal(gathered[0], g) for g in gathered)
 # the CUDA-graph path (three graphs: the first gradient bucket's all-reduce overlaps the second graph)
-m.noise = None
 m.capture()
 for _ in range(3):
     m.train_step()

@@ -269,7 +269,17 @@ def test_vae_function_reference_signature():
 # ---------------------------------------------------------------------------------------------
 # tcgen05 TF32 mode
 # ---------------------------------------------------------------------------------------------
-def _tf32_case(M, N, Kd, tA, tB, seed=0, ints=True, epi=K.EPI_NONE, use_cinit=False, use_bias=False):
+_WS = {}
+
+
+def _gemm_ws():
+    """caller-owned split-K scratch (air_gemm_ws): the library allocates nothing itself"""
+    if "ws" not in _WS:
+        _WS["ws"] = torch.empty(16 << 20, device=DEV)
+    return _WS["ws"]
+
+
+def _tf32_case(M, N, Kd, tA, tB, seed=0, ints=True, epi=K.EPI_NONE, use_cinit=False, use_bias=False, mode="tf32"):
     rng = np.random.RandomState(seed)
     if ints:   # small integers are exact in TF32 and their dot products are exact in FP32
         A = rng.randint(-2, 3, (M, Kd)).astype(np.float32)
@@ -288,7 +298,7 @@ def _tf32_case(M, N, Kd, tA, tB, seed=0, ints=True, epi=K.EPI_NONE, use_cinit=Fa
     Ci = cu(rng.randint(-3, 4, (M, N)).astype(np.float32)) if use_cinit else None
     bias = cu(rng.randint(-3, 4, N).astype(np.float32)) if use_bias else None
     out = torch.full((M, N), 7.0, device=DEV)
-    ops.gemm(Av, Bv, out, Cinit=Ci, bias=bias, tA=tA, tB=tB, epi=epi, mode=K.GEMM_MODES["tf32"])
+    ops.gemm(Av, Bv, out, Cinit=Ci, bias=bias, tA=tA, tB=tB, epi=epi, mode=K.GEMM_MODES[mode], ws=_gemm_ws())
     want = A.astype(np.float64) @ Bm.astype(np.float64)
     if use_cinit:
         want = want + Ci.cpu().numpy()
@@ -297,27 +307,65 @@ def _tf32_case(M, N, Kd, tA, tB, seed=0, ints=True, epi=K.EPI_NONE, use_cinit=Fa
     return out.cpu().numpy(), want
 
 
+TC_MODES = ["tf32", "tf32x3"]
+
+
+@pytest.mark.parametrize("mode", TC_MODES)
 @pytest.mark.parametrize("tA,tB", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,Kd", [(128, 128, 32), (128, 64, 64), (256, 256, 256), (4096, 1024, 256), (200, 100, 50),
                                     (130, 70, 36), (784, 512, 4096), (2500, 1024, 512), (64, 8, 24), (4096, 320, 256)])
-def test_gemm_tf32_exact_on_integers(M, N, Kd, tA, tB):
-    got, want = _tf32_case(M, N, Kd, tA, tB, seed=M + N + Kd)
+def test_gemm_tf32_exact_on_integers(M, N, Kd, tA, tB, mode):
+    got, want = _tf32_case(M, N, Kd, tA, tB, seed=M + N + Kd, mode=mode)
     assert np.array_equal(got, want.astype(np.float32)), np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("mode", TC_MODES)
+@pytest.mark.parametrize("tA,tB", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,Kd", [(4096, 640, 2112), (2500, 1024, 2500)])
+def test_gemm_tf32_cluster_multicast_exact_on_integers(M, N, Kd, tA, tB, mode):
+    """>= 64 k-blocks per CTA, even M-tile count, >= 148 tiles (no split-K): the 2-CTA cluster path, in which each CTA
+    loads half of the shared B tile and TMA-multicasts it to both.  Ragged M (2500 = 19.5 tiles) and ragged K included."""
+    got, want = _tf32_case(M, N, Kd, tA, tB, seed=M + N + Kd, use_cinit=True, use_bias=True, mode=mode)
+    assert np.array_equal(got, want.astype(np.float32)), np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("mode", TC_MODES)
+def test_gemm_tf32_epilogue_cinit_bias_and_splitk(mode):
+    for (M, N, Kd, tA, tB) in ((784, 512, 4096, True, False), (4096, 512, 784, False, False), (256, 1024, 4096, True, False)):
+        got, want = _tf32_case(M, N, Kd, tA, tB, seed=1, use_cinit=True, use_bias=True, epi=K.EPI_RELU, mode=mode)
+        assert np.array_equal(got, np.maximum(want, 0).astype(np.float32))
 
 
 @pytest.mark.parametrize("tA,tB", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("M,N,Kd", [(4096, 640, 2112), (2500, 1024, 2500)])
-def test_gemm_tf32_cluster_multicast_exact_on_integers(M, N, Kd, tA, tB):
-    """>= 64 k-blocks per CTA, even M-tile count, >= 148 tiles (no split-K): the 2-CTA cluster path, in which each CTA
-    loads half of the shared B tile and TMA-multicasts it to both.  Ragged M (2500 = 19.5 tiles) and ragged K included."""
-    got, want = _tf32_case(M, N, Kd, tA, tB, seed=M + N + Kd, use_cinit=True, use_bias=True)
-    assert np.array_equal(got, want.astype(np.float32)), np.abs(got - want).max()
+@pytest.mark.parametrize("M,N,Kd", [(512, 384, 776), (4096, 1024, 2500), (784, 512, 12288), (256, 320, 12288), (130, 70, 36)])
+def test_gemm_tf32x3_is_fp32_grade(M, N, Kd, tA, tB):
+    """The 3xTF32 mode on random fp32 operands, every layout, the model's long-K shapes (cluster path, split-K):
+    as close to the fp64 product as the exact-FP32 FMA chain is (within 4x of its error, and < 2e-6 norm-wise)."""
+    got, want = _tf32_case(M, N, Kd, tA, tB, seed=5, ints=False, mode="tf32x3")
+    ref32, _ = _tf32_case(M, N, Kd, tA, tB, seed=5, ints=False, mode="fp32")
+    e3, e32 = relnorm(got, want), relnorm(ref32, want)
+    assert e3 < 2e-6 and e3 < 4 * e32 + 2e-7, (e3, e32)
+    # element-wise: no entry is off by more than 2e-5 of the typical magnitude sqrt(K)
+    assert np.abs(got - want).max() < 2e-5 * np.sqrt(Kd)
 
 
-def test_gemm_tf32_epilogue_cinit_bias_and_splitk():
-    for (M, N, Kd, tA, tB) in ((784, 512, 4096, True, False), (4096, 512, 784, False, False), (256, 1024, 4096, True, False)):
-        got, want = _tf32_case(M, N, Kd, tA, tB, seed=1, use_cinit=True, use_bias=True, epi=K.EPI_RELU)
-        assert np.array_equal(got, np.maximum(want, 0).astype(np.float32))
+def test_gemm_tf32x3_wide_dynamic_range_and_specials():
+    """operands spanning 2^-40 .. 2^40 (the split must be exact per element, not per tile) and an inf / NaN entry
+    (they travel in the hi part; the lo part of a non-finite value is 0 rather than inf - inf)"""
+    rng = np.random.RandomState(7)
+    M, N, Kd = 256, 128, 512
+    A = (rng.randn(M, Kd) * np.exp2(rng.randint(-40, 41, (M, 1)))).astype(np.float32)
+    Bm = (rng.randn(Kd, N) * np.exp2(rng.randint(-40, 41, (1, N)))).astype(np.float32)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(cu(A), cu(Bm), out, mode=K.GEMM_MODES["tf32x3"])
+    want = A.astype(np.float64) @ Bm.astype(np.float64)
+    scale = np.sqrt((A.astype(np.float64) ** 2).sum(1))[:, None] * np.sqrt((Bm.astype(np.float64) ** 2).sum(0))[None, :]
+    assert (np.abs(out.cpu().numpy() - want) / scale).max() < 1e-6
+    A[3, 5] = np.inf
+    A[7, 9] = np.nan
+    ops.gemm(cu(A), cu(Bm), out, mode=K.GEMM_MODES["tf32x3"])
+    got = out.cpu().numpy()
+    assert (~np.isfinite(got[3])).all() and np.isnan(got[7]).all() and np.isfinite(np.delete(got, (3, 7), axis=0)).all()
 
 
 def test_gemm_tf32_random_accuracy():
@@ -335,7 +383,24 @@ def test_gemm_tf32_random_accuracy():
     assert relnorm(out, A.double() @ Bm.double()) < 1e-6
 
 
-def test_gemm_tf32_rejects_unaligned_leading_dimension():
+@pytest.mark.parametrize("mode", TC_MODES)
+def test_gemm_tf32_rejects_unaligned_leading_dimension(mode):
     a = torch.zeros(64, 50, device=DEV)       # ld = 50 floats = 200 bytes: not a TMA stride
     with pytest.raises(ab.AirError, match="TMA|aligned"):
-        ops.gemm(a, torch.zeros(50, 64, device=DEV), torch.zeros(64, 64, device=DEV), mode=K.GEMM_MODES["tf32"])
+        ops.gemm(a, torch.zeros(50, 64, device=DEV), torch.zeros(64, 64, device=DEV), mode=K.GEMM_MODES[mode])
+
+
+def test_gemm_split_k_needs_a_caller_workspace_and_is_deterministic():
+    """without a workspace the long-K weight-gradient shape runs unsplit; with one it splits; both are deterministic and
+    agree to FP32 rounding; a workspace too small for any split silently means 'unsplit' (never an allocation)"""
+    rng = np.random.RandomState(11)
+    A, Bm = cu(rng.randn(12288, 256).astype(np.float32)), cu(rng.randn(12288, 320).astype(np.float32))
+    outs = []
+    for ws in (None, _gemm_ws(), _gemm_ws(), torch.empty(1000, device=DEV)):
+        out = torch.empty(256, 320, device=DEV)
+        n0 = ab.launch_count()
+        ops.gemm(A, Bm, out, tA=True, mode=K.GEMM_MODES["tf32x3"], ws=ws)
+        outs.append((out, ab.launch_count() - n0))
+    assert outs[0][1] == 1 and outs[1][1] == 2 and outs[3][1] == 1
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[0][0], outs[3][0])
+    assert relnorm(outs[0][0], outs[1][0]) < 1e-6

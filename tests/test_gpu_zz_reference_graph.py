@@ -15,6 +15,9 @@ from tests.parity_util import covered_fixture, cuda_noise, default_fixture, make
 
 pytestmark = pytest.mark.gpu
 
+# both GEMM modes held to the north-star bars: the SIMT FFMA chain and the FP32-grade tensor-core mode (3xTF32)
+EXACT_MODES = ["fp32", "tf32x3"]
+
 
 def _g(golden_dir, name):
     return np.load(os.path.join(golden_dir, name))
@@ -46,12 +49,13 @@ def _per_step(m, g, tol):
     assert m.accuracy.item() == pytest.approx(float(g["accuracy"]), abs=1e-7)
 
 
-def test_train_step_against_reference_graph(golden_dir):
+@pytest.mark.parametrize("gemm_mode", EXACT_MODES)
+def test_train_step_against_reference_graph(golden_dir, gemm_mode):
     """Loss, per-step outputs, reconstruction and all 36 gradients of one training step, covered fixture (the one
-    test_gradient_parity_covered_fixture uses), exact-FP32 GEMM mode."""
+    test_gradient_parity_covered_fixture uses), in both FP32-grade GEMM modes."""
     g = _g(golden_dir, "ref_graph_train_covered.npz")
     imgs, cnt, params, noise = covered_fixture(64, seed=3)
-    _, m = make_pair(imgs, cnt, params, train=True, global_step=2000)
+    _, m = make_pair(imgs, cnt, params, train=True, global_step=2000, gemm_mode=gemm_mode)
     m.loss_and_grads(cuda_noise(noise))
     assert abs(m.loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     _per_step(m, g, 1e-5)
@@ -70,13 +74,14 @@ def test_train_step_against_reference_graph(golden_dir):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("gemm_mode", EXACT_MODES)
 @pytest.mark.parametrize("name,fixture,seed", [("default", default_fixture, 1), ("realistic", realistic_fixture, 2)])
-def test_test_mode_against_reference_graph(golden_dir, name, fixture, seed):
+def test_test_mode_against_reference_graph(golden_dir, name, fixture, seed, gemm_mode):
     """train=False model (tf.round on z_pres) on fixtures with dead steps: digit counts exact, per-step outputs
     <= 1e-5 (the canvas-derived loss is excluded on these uncovered fixtures)."""
     g = _g(golden_dir, f"ref_graph_test_{name}.npz")
     imgs, cnt, params, noise = fixture(64, seed=seed)
-    _, m = make_pair(imgs, cnt, params, train=False, global_step=0)      # the golden run used global_step 0
+    _, m = make_pair(imgs, cnt, params, train=False, global_step=0, gemm_mode=gemm_mode)  # the golden run used global_step 0
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
 
@@ -92,22 +97,24 @@ def test_reconstruction_image_summary_bit_exact_on_device(golden_dir):
     assert [hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in got] == list(g["sha256"])
 
 
-def test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir):
+@pytest.mark.parametrize("gemm_mode", EXACT_MODES)
+def test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir, gemm_mode):
     """Training-mode forward on realistic poses (continuous z_pres, items that stop after 1 or 2 steps) against the
     reference graph evaluated in fp64: masks / digit counts exact, per-step outputs <= 1e-5.  The canvas-derived loss
     and the gradients of this uncovered fixture are compared in fp64 on the CPU side only."""
     g = _g(golden_dir, "ref_graph_train_realistic_fp64.npz")
     imgs, cnt, params, noise = realistic_fixture(64, seed=1)
-    _, m = make_pair(imgs, cnt, params, train=True, global_step=2000)
+    _, m = make_pair(imgs, cnt, params, train=True, global_step=2000, gemm_mode=gemm_mode)
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
 
 
-def test_five_step_inference_against_reference_graph(golden_dir):
+@pytest.mark.parametrize("gemm_mode", EXACT_MODES)
+def test_five_step_inference_against_reference_graph(golden_dir, gemm_mode):
     """configs[4]'s 5 attention steps: the reference's test graph with cond()'s max_steps constant fed as 5."""
     g = _g(golden_dir, "ref_graph_test_realistic_T5.npz")
     imgs, cnt, params, noise = realistic_fixture(64, seed=8, T=5)
-    _, m = make_pair(imgs, cnt, params, train=False, global_step=0, max_steps=5)
+    _, m = make_pair(imgs, cnt, params, train=False, global_step=0, max_steps=5, gemm_mode=gemm_mode)
     m.run(cuda_noise(noise))
     _per_step(m, g, 1e-5)
 
@@ -130,6 +137,9 @@ def test_trained_weights_inference_counts_digits():
     _, m32 = make_pair(imgs, cnt, params, train=False, global_step=step, gemm_mode="tf32")
     m32.run(cuda_noise(noise))
     assert (m32.rec_num_digits.cpu() == cnt).float().mean().item() >= 0.90
+    _, mx3 = make_pair(imgs, cnt, params, train=False, global_step=step, gemm_mode="tf32x3")
+    mx3.run(cuda_noise(noise))
+    assert (mx3.rec_num_digits.cpu() == out["rec_num_digits"]).float().mean().item() >= 0.99
 
 
 def test_st_backward_kernels_against_the_graphs_autodiff(golden_dir):

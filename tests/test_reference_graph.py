@@ -328,7 +328,7 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
         def run(self, noise):
             self._take(self.orc.forward(self.imgs, self.cnt, noise))
 
-    def make_pair(imgs, cnt, params, train=True, global_step=2000, **kw):
+    def make_pair(imgs, cnt, params, train=True, global_step=2000, gemm_mode="fp32", **kw):
         orc = O.AIROracle(params={k: v.clone() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING,
                           train=train, **kw)
         orc.global_step = global_step
@@ -340,11 +340,11 @@ def test_gpu_reference_graph_tests_rehearsed_on_the_oracle(golden_dir, monkeypat
     monkeypatch.setattr(T.ab, "transformer", O.transformer)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     T.test_st_kernels_bit_exact_with_reference_graph(golden_dir)
-    T.test_train_step_against_reference_graph(golden_dir)
-    T.test_test_mode_against_reference_graph(golden_dir, "default", PU.default_fixture, 1)
-    T.test_test_mode_against_reference_graph(golden_dir, "realistic", PU.realistic_fixture, 2)
-    T.test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir)
-    T.test_five_step_inference_against_reference_graph(golden_dir)
+    T.test_train_step_against_reference_graph(golden_dir, "fp32")
+    T.test_test_mode_against_reference_graph(golden_dir, "default", PU.default_fixture, 1, "fp32")
+    T.test_test_mode_against_reference_graph(golden_dir, "realistic", PU.realistic_fixture, 2, "fp32")
+    T.test_train_mode_realistic_poses_against_fp64_graph_run(golden_dir, "fp32")
+    T.test_five_step_inference_against_reference_graph(golden_dir, "fp32")
     T.test_st_backward_kernels_against_the_graphs_autodiff(golden_dir)
     from tests.test_trained_weights import PATH as trained_path
     if os.path.exists(trained_path):

@@ -39,7 +39,8 @@ _SIGS = {
     "air_concrete_step_bwd": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_float, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
     "air_gemm": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 9 + [_c_f]),
     "air_gemm_ex": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 8 + [ctypes.c_float, ctypes.c_int, _c_f]),
-    "air_gemm_set_workspace": (ctypes.c_int, [_c_f, ctypes.c_int64]),
+    "air_gemm_ws": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int64] + [ctypes.c_int] * 8 +
+                    [ctypes.c_float, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
     "air_lstm_fwd": (ctypes.c_int, [_c_f] * 4 + [ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_lstm_bwd": (ctypes.c_int, [_c_f] * 8 + [ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_heads_fwd": (ctypes.c_int, [_c_f] * 14 + [ctypes.c_int64, ctypes.c_int, _c_f]),
@@ -81,7 +82,7 @@ class Hyper(ctypes.Structure):
  F_YPRE, F_Z, F_ZPROB, F_KL_Z, F_KL_SCALE, F_KL_SHIFT, F_KL_VAE, F_STOP_PREV, F_STOP_NEW) = range(19)
 NF = 20
 EPI_NONE, EPI_RELU, EPI_SOFTPLUS, EPI_MUL_DRELU, EPI_MUL_DSOFTPLUS, EPI_SIGMOID_NOISE = range(6)
-GEMM_MODES = {"fp32": 0, "tf32": 1}
+GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 _lib = None
 

@@ -36,6 +36,7 @@ from .vae import (VAEWeights, _flat2, alloc_vae_scratch, dense_dw, vae_backward_
                   vae_weight_grads)
 
 _VARIABLE_SCOPES = {}
+_GEMM_WORKSPACES = {}  # device -> float32 scratch tensor (split-K partial sums)
 
 _DEVICE_ANNEALABLE = ("z_pres_prior_log_odds", "learning_rate")
 
@@ -117,12 +118,13 @@ class AIRModel:
         self.world = dp.world_size(process_group)
 
         self._alloc()
-        if self.gemm == C.GEMM_MODES["tf32"]:
-            # torch-owned split-K workspace for the weight-gradient GEMMs (nothing is allocated inside the library)
-            AIRModel._gemm_ws = getattr(AIRModel, "_gemm_ws", None)
-            if AIRModel._gemm_ws is None or AIRModel._gemm_ws.device != self.device:
-                AIRModel._gemm_ws = torch.empty(16 << 20, device=self.device, dtype=torch.float32)
-            ops.set_gemm_workspace(AIRModel._gemm_ws)
+        # torch-owned split-K scratch for the weight-gradient GEMMs of the tensor-core modes, one per device, handed
+        # to the library with every call (the library keeps no pointer and allocates nothing)
+        self._gemm_ws = None
+        if train and self.gemm != C.GEMM_MODES["fp32"]:
+            if self.device not in _GEMM_WORKSPACES:
+                _GEMM_WORKSPACES[self.device] = torch.empty(16 << 20, device=self.device, dtype=torch.float32)
+            self._gemm_ws = _GEMM_WORKSPACES[self.device]
         self._graphs = None
         self.noise = None
         self.rec_num_digits = self.rec_scales = None
@@ -222,7 +224,9 @@ class AIRModel:
             self.target_num_digits.copy_(target_num_digits, non_blocking=True)
 
     def set_noise(self, noise):
-        """Inject the five noise tensors ([T,B,1], [T,B,2], [T,B,L], [T,B,win], [T,B])."""
+        """Inject the five noise tensors ([T,B,1], [T,B,2], [T,B,L], [T,B,win], [T,B]) for the NEXT evaluation only:
+        the run() / loss_and_grads() / train_step() that follows uses them instead of drawing, every later call
+        draws fresh noise again -- like the reference, where each session.run samples anew."""
         for k, buf in self.w["noise"].items():
             buf.copy_(noise[k].reshape(buf.shape))
         self.noise = "injected"
@@ -378,12 +382,12 @@ class AIRModel:
     def _weight_grads_rnn(self):
         w, mode, T = self.w, self.gemm, self.max_steps
         if T > 1:   # K_h sees h_{t-1}: rows t = 1..T-1 (h_{-1} = 0 contributes nothing)
-            ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode)
+            ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode, ws=self._gemm_ws)
         else:
             self.gKh.zero_()
         # the image rows of the LSTM kernel see the same input every step: one GEMM on the summed dgates
         rnn_in = w["cnn_out"][2] if self.cnn else self.input_images
-        ops.gemm(rnn_in, w["dgates_sum"], self.gKx, tA=True, mode=mode)
+        ops.gemm(rnn_in, w["dgates_sum"], self.gKx, tA=True, mode=mode, ws=self._gemm_ws)
         ops.colsum_multi(self._colsum_items_rnn, w["colsum_ws_rnn"])
         if self.cnn:
             self._cnn_backward()
@@ -394,8 +398,8 @@ class AIRModel:
         ops.reduce_rows(w["heads_ws"], T * self._heads_rows, nw + 7, nw, g["heads/out_w"])
         ops.reduce_rows(w["heads_ws"].view(-1)[nw:], T * self._heads_rows, nw + 7, 7, g["heads/out_b"])
         allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
-        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, w["vae_d"], None, mode)
-        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], None, mode)
+        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, w["vae_d"], None, mode, gemm_ws=self._gemm_ws)
+        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], None, mode, gemm_ws=self._gemm_ws)
         ops.colsum_multi(self._colsum_items, w["colsum_ws"])
 
     def _apply_gradients(self):
@@ -428,7 +432,9 @@ class AIRModel:
         """Forward pass only (what session.run of any result attribute evaluates)."""
         if noise is not None:
             self.set_noise(noise)
-        elif self.noise != "injected":
+        if self.noise == "injected":
+            self.noise = None        # one-shot: consumed by this evaluation (the buffers keep it for the backward)
+        else:
             self._draw_noise()
         self._forward()
         self._publish()
@@ -461,7 +467,11 @@ class AIRModel:
         """Capture noise + forward + backward, and clip + Adam, as CUDA graphs; subsequent train_step() calls replay
         them.  With more than one rank the backward is split after the LSTM-kernel gradients so that the (eager)
         NCCL all-reduce of that first bucket overlaps the remaining weight-gradient GEMMs."""
-        assert self.train and self.noise != "injected"
+        if not self.train:
+            raise C.AirError("capture() records a training step: the model was built with train=False")
+        if self.noise == "injected":
+            raise C.AirError("capture() would freeze the injected noise into the graph: run the pending evaluation "
+                             "first (injection is one-shot) or call capture() before set_noise()")
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -73,9 +73,10 @@ def dense_dx(x_in, W, dY, dX, mode, act_of_x=False):
     return dX
 
 
-def dense_dw(x_in, dY, gW, gb, colsum_ws, mode, accumulate=False):
-    """gW (+)= x_in^T dY, gb (+)= colsum(dY).  x_in / dY may be time-batched [T*B, .] views."""
-    ops.gemm(x_in, dY, gW, Cinit=gW if accumulate else None, tA=True, mode=mode)
+def dense_dw(x_in, dY, gW, gb, colsum_ws, mode, accumulate=False, gemm_ws=None):
+    """gW (+)= x_in^T dY, gb (+)= colsum(dY).  x_in / dY may be time-batched [T*B, .] views.
+    ``gemm_ws``: split-K scratch of the tensor-core GEMM (the reduction runs over the batch: few tiles, long K)."""
+    ops.gemm(x_in, dY, gW, Cinit=gW if accumulate else None, tA=True, mode=mode, ws=gemm_ws)
     if colsum_ws is not None:  # None: the caller sums all its bias gradients in one launch (vae_bias_items)
         ops.colsum(dY, gb, accumulate, colsum_ws)
 
@@ -111,7 +112,7 @@ def vae_backward_dx(x, w: VAEWeights, noise_latent, hyper, buf, dbuf, dloss, fie
     return dx_out
 
 
-def vae_weight_grads(x, w: VAEWeights, buf, dbuf, colsum_ws, mode, accumulate=False):
+def vae_weight_grads(x, w: VAEWeights, buf, dbuf, colsum_ws, mode, accumulate=False, gemm_ws=None):
     """All VAE parameter gradients from (time-batched) activations ``buf`` and the matching
     pre-activation gradients ``dbuf``: one long-K GEMM + one column sum per layer."""
     flat = lambda t: t.reshape(-1, t.shape[-1]) if t.is_contiguous() else t.flatten(0, -2)
@@ -119,12 +120,12 @@ def vae_weight_grads(x, w: VAEWeights, buf, dbuf, colsum_ws, mode, accumulate=Fa
     dys = list(dbuf["ddec"]) + [dbuf["dgen"]]
     grads = list(w.g_gen) + [w.g_gm]
     for a, dy, (gW, gb) in zip(acts, dys, grads):
-        dense_dw(_flat2(a), _flat2(dy), gW, gb, colsum_ws, mode, accumulate)
+        dense_dw(_flat2(a), _flat2(dy), gW, gb, colsum_ws, mode, accumulate, gemm_ws)
     acts = [x] + list(buf["enc"])
     dys = list(dbuf["denc"]) + [dbuf["dml"]]
     grads = list(w.g_rec) + [w.g_ml]
     for a, dy, (gW, gb) in zip(acts, dys, grads):
-        dense_dw(_flat2(a), _flat2(dy), gW, gb, colsum_ws, mode, accumulate)
+        dense_dw(_flat2(a), _flat2(dy), gW, gb, colsum_ws, mode, accumulate, gemm_ws)
 
 
 def vae_bias_items(w: VAEWeights, dbuf, accumulate=False):

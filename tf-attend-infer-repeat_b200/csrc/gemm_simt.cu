@@ -186,13 +186,15 @@ int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit
 }
 
 int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux, int M,
-              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s);
+              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, bool x3, float *workspace,
+              int64_t ws_floats, cudaStream_t s);
 
 }  // namespace air
 
-extern "C" int air_gemm_ex(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
+extern "C" int air_gemm_ws(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
                            const float *aux, int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
-                           int epilogue, float epi_param, int mode, air_stream_t stream) {
+                           int epilogue, float epi_param, int mode, float *workspace, int64_t workspace_floats,
+                           air_stream_t stream) {
   AIR_REQUIRE(M >= 0 && N >= 0 && K >= 0 && M < (int64_t(1) << 31), AIR_ERR_BAD_SHAPE, "air_gemm: bad shape M=%lld N=%d K=%d",
               (long long)M, N, K);
   if (M == 0 || N == 0) return AIR_OK;
@@ -204,20 +206,25 @@ extern "C" int air_gemm_ex(const float *A, const float *B, float *C, const float
   AIR_REQUIRE((epilogue != AIR_EPI_MUL_DRELU && epilogue != AIR_EPI_MUL_DSOFTPLUS && epilogue != AIR_EPI_SIGMOID_NOISE) || aux,
               AIR_ERR_NULL, "air_gemm: epilogue %d needs aux", epilogue);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  AIR_REQUIRE(mode == AIR_GEMM_FP32_EXACT || mode == AIR_GEMM_TF32, AIR_ERR_UNSUPPORTED, "air_gemm: unknown mode %d", mode);
+  AIR_REQUIRE(mode == AIR_GEMM_FP32_EXACT || mode == AIR_GEMM_TF32 || mode == AIR_GEMM_TF32X3, AIR_ERR_UNSUPPORTED,
+              "air_gemm: unknown mode %d", mode);
   if (K == 0) return air::gemm_k0(C, Cinit, bias, aux, static_cast<int>(M), N, ldc, epilogue, epi_param, s);
   if (mode == AIR_GEMM_FP32_EXACT)
     return air::gemm_fp32_exact(A, B, C, Cinit, bias, aux, static_cast<int>(M), N, K, lda, ldb, ldc, transA, transB,
                                 epilogue, epi_param, s);
-  if (mode == AIR_GEMM_TF32)
-    return air::gemm_tf32(A, B, C, Cinit, bias, aux, static_cast<int>(M), N, K, lda, ldb, ldc, transA, transB, epilogue,
-                          epi_param, s);
-  air::set_error("air_gemm: unknown mode %d", mode);
-  return AIR_ERR_UNSUPPORTED;
+  return air::gemm_tf32(A, B, C, Cinit, bias, aux, static_cast<int>(M), N, K, lda, ldb, ldc, transA, transB, epilogue,
+                        epi_param, mode == AIR_GEMM_TF32X3, workspace, workspace ? workspace_floats : 0, s);
+}
+
+extern "C" int air_gemm_ex(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
+                           const float *aux, int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                           int epilogue, float epi_param, int mode, air_stream_t stream) {
+  return air_gemm_ws(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, transA, transB, epilogue, epi_param, mode, nullptr, 0,
+                     stream);
 }
 
 extern "C" int air_gemm(const float *A, const float *B, float *C, const float *Cinit, const float *bias,
                         const float *aux, int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                         int epilogue, int mode, air_stream_t stream) {
-  return air_gemm_ex(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, transA, transB, epilogue, 0.0f, mode, stream);
+  return air_gemm_ws(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, transA, transB, epilogue, 0.0f, mode, nullptr, 0, stream);
 }

@@ -16,9 +16,21 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue: TMEM lane quarter = warp_idx % 4, two warps per quarter each taking half
 // of the tile's columns (the epilogue, not the MMA pipe, bounds the small-K GEMMs of this model).
+//
+// Mode AIR_GEMM_TF32X3 (template flag X3) is the FP32-grade tensor-core mode ("3xTF32"): every fp32
+// operand a is used as a = hi + lo with hi = the top 19 bits of a (exactly what the tensor core reads
+// from the raw fp32 tile, so the TMA-loaded tile IS the hi operand) and lo = rn_tf32(a - hi), written by
+// the eight epilogue warps -- idle during the main loop otherwise -- into a second shared-memory tile of
+// the same swizzled layout.  Three MMAs per k-step: hi*hi into the main accumulator(s), lo*hi + hi*lo
+// into a separate correction accumulator (its terms are 2^-11 smaller, so its own rounding is
+// irrelevant); the dropped lo*lo term is <= 2^-20 relative per product.  The hi*hi products are
+// accumulated in `chains` TMEM accumulators used round-robin over the k-blocks and summed in FP32 (RN)
+// by the epilogue: the tensor core's accumulate step rounds toward zero, so shorter chains mean less of
+// that bias (measured in tests/diag_tc_rounding.py).
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <stdlib.h>
 
 #include "air_common.cuh"
@@ -103,6 +115,19 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t *r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// lo part of the 3xTF32 split: a - trunc_tf32(a) is exact in fp32 (<= 13 significant bits); rounding it to
+// TF32 here (RN) keeps the tensor core's own truncation of the operand from biasing it
+__device__ __forceinline__ float tf32_lo(float a) {
+  const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  float lo = __fsub_rn(a, hi);
+  if ((__float_as_uint(a) & 0x7F800000u) == 0x7F800000u) lo = 0.0f;  // inf / NaN travel in the hi part only
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+  return __uint_as_float(r);
+}
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout).
 // layout_type 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B: the only layout the
@@ -135,24 +160,33 @@ struct TcParams {
   float epi_param;
   int kb_per_split, num_kb, splits;
   int stages;  // TMA->MMA ring depth (<= kMaxStages)
-  int mma_repeat;  // diagnostics only (AIR_TC_MMA_REPEAT): re-issue each k-block's MMAs (results are then wrong)
+  int chains;  // X3: number of hi*hi accumulators used round-robin over the k-blocks (1..kMaxChains)
 };
+
+constexpr int kMaxChains = 3;
+constexpr int kSplitWarps = 8;  // the epilogue warps write the lo tiles during the main loop (X3)
+
+__host__ __device__ constexpr uint32_t tmem_cols_for(int BN, bool x3) {
+  const int want = x3 ? (kMaxChains + 1) * BN : BN;
+  return want <= 32 ? 32u : want <= 64 ? 64u : want <= 128 ? 128u : want <= 256 ? 256u : 512u;
+}
 
 // CL: launched as clusters of two CTAs that are neighbours along M (same N tile).  They need the same B tile:
 // each loads half of it and multicasts it to both, which halves the L2 -> SM traffic of that operand (the kernel
 // is L2 -> SM bandwidth bound with fp32 operands, profiles/r1_gemm_tf32_big_ncu_full.md).  A stage is refilled only
 // after BOTH CTAs' MMAs have read it: the empty barriers count two arrivals, one multicast commit from each CTA.
-template <int BN, bool A_MN, bool B_MN, bool CL>
+template <int BN, bool A_MN, bool B_MN, bool CL, bool X3>
 __global__ void __launch_bounds__(kTcThreads)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
   constexpr uint32_t kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4;
-  constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32
+  constexpr uint32_t kRawBytes = kABytes + kBBytes;              // what TMA delivers per stage (= the hi operands)
+  constexpr uint32_t kStageBytes = X3 ? 2 * kRawBytes : kRawBytes;  // X3: + the lo tiles, same layout
+  constexpr uint32_t kTmemCols = tmem_cols_for(BN, X3);
   const int kStages = p.stages;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned tiles (SWIZZLE_128B atoms)
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], split_bar[kMaxStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,6 +195,7 @@ __global__ void __launch_bounds__(kTcThreads)
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
   const int nkb = kb_end - kb_begin;
+  const int chains = X3 ? min(p.chains, nkb) : 1;  // every chain used below has received at least one k-block
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mapA);
@@ -168,6 +203,7 @@ __global__ void __launch_bounds__(kTcThreads)
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CL ? 2 : 1);
+      mbar_init(&split_bar[s], kSplitWarps);
     }
     mbar_init(&tmem_full_bar, 1);
     fence_mbar_init();
@@ -182,43 +218,69 @@ __global__ void __launch_bounds__(kTcThreads)
   pdl_sync();  // PDL: barriers, TMEM and descriptors were set up while the previous grid drained
 
   // ================= TMA producers =================
-  // Every stage is loaded as 4 + 4 quarter boxes issued by four threads: lane 0 of warp 0 and of the
-  // (otherwise idle until the accumulator is complete) epilogue warps 2..4.  Measured neutral against a
-  // single issuing thread: TMA issue is not the limit -- machine-wide the kernel is bound by L2 -> SM operand
-  // bandwidth (profiles/r1_gemm_tf32_big_ncu_full.md).
-  if (warp == 0 || (warp >= 2 && warp <= 4)) {
+  // Every stage is loaded as 4 + 4 quarter boxes.  Plain TF32: issued by four threads, lane 0 of warp 0 and of the
+  // (otherwise idle until the accumulator is complete) epilogue warps 2..4 -- measured neutral against a single
+  // issuing thread (TMA issue is not the limit).  X3: the epilogue warps are busy splitting, warp 0 issues all eight.
+  if (warp == 0 || (!X3 && warp >= 2 && warp <= 4)) {
     if (lane == 0) {
-      const int pi = warp == 0 ? 0 : warp - 1;  // producer index 0..3
+      const int pi_begin = X3 ? 0 : (warp == 0 ? 0 : warp - 1), pi_end = X3 ? 4 : pi_begin + 1;
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait_spin(&empty_bar[s], ph ^ 1);
         unsigned char *sa = tiles + s * kStageBytes, *sb = sa + kABytes;
-        if (pi == 0) mbar_expect_tx(&full_bar[s], kStageBytes);
+        if (warp == 0) mbar_expect_tx(&full_bar[s], kRawBytes);
         const int k0 = (kb_begin + i) * kBK;
-        if (!A_MN) {  // box {32 k, 32 m}: rows [32 pi, 32 pi + 32)
-          tma_load_2d(sa + pi * (32 * 128), &mapA, &full_bar[s], k0, m0 + pi * 32);
-        } else {      // box {32 m, 32 k}: 32-wide chunk pi
-          tma_load_2d(sa + pi * (kBK * 128), &mapA, &full_bar[s], m0 + pi * 32, k0);
-        }
-        unsigned char *bdst;
-        int bc0, bc1;
-        if (!B_MN) {  // box {32 k, BN/4 n}
-          bdst = sb + pi * (BN / 4 * 128); bc0 = k0; bc1 = n0 + pi * (BN / 4);
-        } else if (BN == 128) {  // box {32 n, 32 k}: chunk pi
-          bdst = sb + pi * (kBK * 128); bc0 = n0 + pi * 32; bc1 = k0;
-        } else {      // BN == 64: box {32 n, 16 k}: chunk pi/2, k-half pi%2
-          bdst = sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128); bc0 = n0 + (pi >> 1) * 32; bc1 = k0 + (pi & 1) * 16;
-        }
-        if (!CL) {
-          tma_load_2d(bdst, &mapB, &full_bar[s], bc0, bc1);
-        } else if (static_cast<uint32_t>(pi >> 1) == crank) {  // this CTA's half of the shared B tile, to both CTAs
-          tma_load_2d_mc(bdst, &mapB, &full_bar[s], bc0, bc1, static_cast<uint16_t>(3));
+        for (int pi = pi_begin; pi < pi_end; ++pi) {
+          if (!A_MN) {  // box {32 k, 32 m}: rows [32 pi, 32 pi + 32)
+            tma_load_2d(sa + pi * (32 * 128), &mapA, &full_bar[s], k0, m0 + pi * 32);
+          } else {      // box {32 m, 32 k}: 32-wide chunk pi
+            tma_load_2d(sa + pi * (kBK * 128), &mapA, &full_bar[s], m0 + pi * 32, k0);
+          }
+          unsigned char *bdst;
+          int bc0, bc1;
+          if (!B_MN) {  // box {32 k, BN/4 n}
+            bdst = sb + pi * (BN / 4 * 128); bc0 = k0; bc1 = n0 + pi * (BN / 4);
+          } else if (BN == 128) {  // box {32 n, 32 k}: chunk pi
+            bdst = sb + pi * (kBK * 128); bc0 = n0 + pi * 32; bc1 = k0;
+          } else {      // BN == 64: box {32 n, 16 k}: chunk pi/2, k-half pi%2
+            bdst = sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128); bc0 = n0 + (pi >> 1) * 32; bc1 = k0 + (pi & 1) * 16;
+          }
+          if (!CL) {
+            tma_load_2d(bdst, &mapB, &full_bar[s], bc0, bc1);
+          } else if (static_cast<uint32_t>(pi >> 1) == crank) {  // this CTA's half of the shared B tile, to both CTAs
+            tma_load_2d_mc(bdst, &mapB, &full_bar[s], bc0, bc1, static_cast<uint16_t>(3));
+          }
         }
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
+  }
+  if (X3 && warp >= 2) {
+    // ================= 3xTF32 splitter: lo = rn_tf32(a - trunc_tf32(a)) for both raw tiles of every stage =========
+    // The lo tile has the raw tile's (swizzled) layout, so this is elementwise on float4s.  A stage's lo tile is
+    // rewritten only after full_bar[s] of the NEXT ring pass, i.e. after the MMAs that read it have completed.
+    constexpr int kVec = kRawBytes / 16, kThreads = kSplitWarps * 32;
+    static_assert(kVec % kThreads == 0, "split loop assumes a whole number of float4 per thread");
+    const int tid = threadIdx.x - 64;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&full_bar[s], ph);
+      const float4 *raw = reinterpret_cast<const float4 *>(tiles + s * kStageBytes);
+      float4 *lo = reinterpret_cast<float4 *>(tiles + s * kStageBytes + kRawBytes);
+      float4 v[kVec / kThreads];
+#pragma unroll
+      for (int j = 0; j < kVec / kThreads; ++j) v[j] = raw[j * kThreads + tid];
+#pragma unroll
+      for (int j = 0; j < kVec / kThreads; ++j)
+        lo[j * kThreads + tid] = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[s]);
+      if (++s == kStages) { s = 0; ph ^= 1; }
+    }
   }
   if (warp == 0) {
   } else if (warp == 1) {
@@ -231,18 +293,32 @@ __global__ void __launch_bounds__(kTcThreads)
       constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_adv = A_MN ? 1024 : 32;
       constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_adv = B_MN ? 1024 : 32;
       constexpr uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
-      int s = 0;
+      const uint32_t tmem_corr = tmem_acc + kMaxChains * BN;  // X3: lo*hi + hi*lo
+      int s = 0, chain = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait_spin(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + s * kStageBytes), sb = sa + kABytes;
-        for (int rep = 0; rep < p.mma_repeat; ++rep) {
+        const uint32_t tmem_main = tmem_acc + (X3 ? chain * BN : 0);
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lt);
+          const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lt);
+          umma_tf32(tmem_main, da, db, idesc, (i >= chains || k != 0) ? 1u : 0u);  // chain c is first used by k-block c
+        }
+        if (X3) {
+          if (++chain == chains) chain = 0;
+          mbar_wait_spin(&split_bar[s], ph);  // the hi*hi MMAs above run while the lo tiles are being written
+          tc_fence_after();
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lt);
             const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_acc, da, db, idesc, (i | k | rep) != 0 ? 1u : 0u);
+            const uint64_t dal = make_smem_desc(sa + kRawBytes + k * a_adv, a_lbo, a_sbo, a_lt);
+            const uint64_t dbl = make_smem_desc(sb + kRawBytes + k * b_adv, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_corr, dal, db, idesc, (i | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_corr, da, dbl, idesc, 1u);
           }
         }
         if (CL) umma_commit_mc(&empty_bar[s], static_cast<uint16_t>(3));
@@ -251,7 +327,8 @@ __global__ void __launch_bounds__(kTcThreads)
       }
       umma_commit(&tmem_full_bar);  // accumulator complete
     }
-  } else if (warp >= 2) {
+  }
+  if (warp >= 2) {
     // ================= epilogue: TMEM -> registers -> global (8 warps) =================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // which half of the tile's columns
@@ -291,6 +368,19 @@ __global__ void __launch_bounds__(kTcThreads)
         }
       }
       tmem_ld_wait();
+      if (X3) {  // product = ((chain_0 + chain_1) + ...) + correction, FP32 round-to-nearest, fixed order
+        uint32_t r2[16];
+        for (int c = 1; c < chains; ++c) {
+          tmem_ld_x16(tbase + c * BN + c0, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+        }
+        tmem_ld_x16(tbase + kMaxChains * BN + c0, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+      }
       if (!row_ok) continue;
       if (fast) {
         float v[16];
@@ -406,38 +496,21 @@ static int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1
   return AIR_OK;
 }
 
-// split-K workspace, one per device: either provided by the caller (air_gemm_set_workspace, the
-// normal case: torch owns the memory and nothing is allocated during graph capture) or grown
-// on demand.  GEMMs that use it must be stream-ordered with each other.
-static float *g_ws[16] = {nullptr};
-static size_t g_ws_bytes[16] = {0};
-static bool g_ws_external[16] = {false};
-
-int set_gemm_workspace(float *ws, size_t bytes) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return AIR_ERR_CUDA;
-  dev &= 15;
-  if (g_ws[dev] && !g_ws_external[dev]) cudaFree(g_ws[dev]);
-  g_ws[dev] = ws;
-  g_ws_bytes[dev] = ws ? bytes : 0;
-  g_ws_external[dev] = ws != nullptr;
-  return AIR_OK;
-}
-
-static float *splitk_workspace(size_t bytes) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 15;
-  if (g_ws_bytes[dev] < bytes) {
-    if (g_ws_external[dev]) return nullptr;  // caller's buffer is too small: fail loudly
-    if (g_ws[dev]) cudaFree(g_ws[dev]);
-    g_ws[dev] = nullptr;
-    g_ws_bytes[dev] = 0;
-    size_t want = std::max(bytes, static_cast<size_t>(64) << 20);
-    if (cudaMalloc(&g_ws[dev], want) != cudaSuccess) return nullptr;
-    g_ws_bytes[dev] = want;
+// Tuning / diagnostics knobs, read ONCE when the library is first used (never on the launch path):
+//   AIR_TC_STAGES   ring depth override            AIR_TC_BN       force 64- or 128-wide tiles
+//   AIR_TC_CLUSTER  0 = never, 2 = always pair CTAs AIR_TC_CHAINS   hi*hi accumulator chains of the X3 mode (1..3)
+struct TcEnv {
+  int stages = 0, bn = 0, cluster = 1, chains = 2;
+  TcEnv() {
+    if (const char *e = getenv("AIR_TC_STAGES")) stages = std::max(1, atoi(e));
+    if (const char *e = getenv("AIR_TC_BN")) bn = atoi(e);
+    if (const char *e = getenv("AIR_TC_CLUSTER")) cluster = atoi(e);
+    if (const char *e = getenv("AIR_TC_CHAINS")) chains = std::max(1, std::min(atoi(e), kMaxChains));
   }
-  return g_ws[dev];
+};
+static const TcEnv &tc_env() {
+  static const TcEnv env;
+  return env;
 }
 
 template <typename... KArgs, typename... Args>
@@ -460,30 +533,33 @@ static cudaError_t launch_cluster_pdl(void (*kern)(KArgs...), dim3 grid, dim3 bl
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool CL>
+template <int BN, bool A_MN, bool B_MN, bool CL, bool X3>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, cudaStream_t s) {
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL>;
-  const size_t stage_bytes = static_cast<size_t>(kBM + BN) * kBK * 4;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL, X3>;
+  const size_t stage_bytes = static_cast<size_t>(kBM + BN) * kBK * 4 * (X3 ? 2 : 1);
+  const int max_stages = static_cast<int>(std::min<size_t>(kMaxStages, 200 * 1024 / stage_bytes));
   // Keep as many operand bytes in flight per SM as shared memory allows: a deep ring when the grid gives each SM
   // one CTA, half of it when two CTAs will share an SM.  (tests/diag_gemm_single_cta.py: one CTA per SM with
-  // operands streaming from HBM runs 1.5 / 2.3 / 2.35 k-blocks per us with 2 / 4 / 6 stages.)
+  // operands streaming from HBM runs 1.5 / 2.3 / 2.35 k-blocks per us with 2 / 4 / 6 stages.)  X3 stages are twice
+  // as large (raw + lo tiles) and its CTAs own all 512 TMEM columns: always one CTA per SM, the deepest ring that fits.
   const int64_t ctas = static_cast<int64_t>((p.N + BN - 1) / BN) * ((p.M + kBM - 1) / kBM) * p.splits;
-  const size_t budget = (ctas <= sm_count() ? 200 : 100) * 1024;
+  const size_t budget = (X3 || ctas <= sm_count() ? 200 : 100) * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
-  stages = std::max(2, std::min({stages, kMaxStages, std::max(p.kb_per_split, 2)}));
-  if (const char *e = getenv("AIR_TC_STAGES")) stages = std::max(1, std::min(atoi(e), static_cast<int>(200 * 1024 / stage_bytes)));
+  stages = std::max(2, std::min({stages, max_stages, std::max(p.kb_per_split, 2)}));
+  if (tc_env().stages) stages = std::min(tc_env().stages, max_stages);
   p.stages = stages;
-  p.mma_repeat = 1;
-  if (const char *e = getenv("AIR_TC_MMA_REPEAT")) p.mma_repeat = std::max(1, atoi(e));
+  p.chains = tc_env().chains;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
-  const size_t smem_max = static_cast<size_t>(kMaxStages) * stage_bytes + 1024 > 225 * 1024
-                              ? static_cast<size_t>(200 * 1024 / stage_bytes) * stage_bytes + 1024
-                              : static_cast<size_t>(kMaxStages) * stage_bytes + 1024;
-  static bool configured = false;
-  if (!configured) {
+  const size_t smem_max = static_cast<size_t>(max_stages) * stage_bytes + 1024;
+  // the opt-in shared-memory limit is a per-device function attribute: set it once per (instantiation, device)
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = uint64_t(1) << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(gemm_tf32): %s", cudaGetErrorString(e));
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_release);
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, p.splits);
   if (CL) {
@@ -493,14 +569,17 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, c
     AIR_LAUNCH(kern, grid, kTcThreads, smem, s, ma, mb, p);
   }
   count_launch();
-  return check_launch("gemm_tf32");
+  return check_launch(X3 ? "gemm_tf32x3" : "gemm_tf32");
 }
 
 int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
                     int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s);
 
+// x3: the FP32-grade 3xTF32 mode.  workspace (nullable) / ws_floats: caller-owned split-K scratch; without one (or with
+// one that is too small for a useful split) the GEMM runs unsplit -- nothing is ever allocated or cached here.
 int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux, int M,
-              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s) {
+              int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, bool x3, float *workspace,
+              int64_t ws_floats, cudaStream_t s) {
   if (K == 0)  // no products at all: C = epi(Cinit + bias); nothing for the tensor cores to do
     return gemm_fp32_exact(A, B, C, Cinit, bias, aux, M, N, K, lda, ldb, ldc, tA, tB, epi, epi_param, s);
   AIR_REQUIRE(aligned16(A) && aligned16(B) && (lda % 4 == 0) && (ldb % 4 == 0), AIR_ERR_BAD_ALIGN,
@@ -520,9 +599,11 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   p.C = C; p.Cinit = Cinit; p.bias = bias; p.aux = aux;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epi; p.epi_param = epi_param;
   p.num_kb = (K + kBK - 1) / kBK;
-  const bool can_split = (N % 4 == 0);
+  const bool can_split = (N % 4 == 0) && workspace != nullptr && aligned16(workspace);
+  const int64_t ws_splits = can_split ? ws_floats / (static_cast<int64_t>(M) * N) : 1;
   auto want_splits = [&](int64_t tiles) {
     int sp = static_cast<int>(std::min<int64_t>((2 * sms + tiles - 1) / tiles, p.num_kb / 8));
+    sp = static_cast<int>(std::min<int64_t>(sp, ws_splits));
     return std::max(1, std::min(sp, 32));
   };
   int BN, splits = 1;
@@ -535,17 +616,11 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
     BN = 64;   // twice the CTAs of the wide tiling
     if (tiles64 < sms && can_split && p.num_kb >= 64) splits = want_splits(tiles64);
   }
-  if (const char *e = getenv("AIR_TC_BN")) BN = (atoi(e) == 64 || N <= 64) ? 64 : 128;  // tuning / diagnostics override
+  if (tc_env().bn) BN = (tc_env().bn == 64 || N <= 64) ? 64 : 128;  // tuning / diagnostics override
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   p.splits = splits;
-  float *ws = nullptr;
-  if (splits > 1) {
-    ws = splitk_workspace(sizeof(float) * static_cast<size_t>(splits) * M * N);
-    AIR_REQUIRE(ws != nullptr, AIR_ERR_CUDA, "air_gemm(TF32): split-K workspace too small / not allocatable (%lld floats needed)",
-                (long long)splits * M * N);
-    p.C = ws;
-  }
+  if (splits > 1) p.C = workspace;
 
   CUtensorMap ma, mb;
   int rc;
@@ -560,19 +635,21 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   // mainloop is long: measured (profiles/r1_gemm_cluster_multicast.md) +6.5 % / +9 % on the two biggest GEMMs
   // (K = 2500, 4096), neutral at ~77 k-blocks per CTA, and 3-5 % slower on the short-K GEMMs, where the two
   // cluster barriers and the gang launch cost more than the operand traffic saves.  AIR_TC_CLUSTER=0/2 forces off/on.
-  static const int cl_env = [] { const char *e = getenv("AIR_TC_CLUSTER"); return e ? atoi(e) : 1; }();
+  const int cl_env = tc_env().cluster;
   const bool cl = cl_env != 0 && (mt % 2 == 0) && (cl_env == 2 || p.kb_per_split >= 64);
-#define AIR_TC_DISPATCH(BNv, CLv)                                                                                \
-  (a_mn ? (b_mn ? launch_tc<BNv, true, true, CLv>(ma, mb, p, s) : launch_tc<BNv, true, false, CLv>(ma, mb, p, s)) \
-        : (b_mn ? launch_tc<BNv, false, true, CLv>(ma, mb, p, s) : launch_tc<BNv, false, false, CLv>(ma, mb, p, s)))
+#define AIR_TC_DISPATCH2(BNv, CLv, X3v)                                                                                 \
+  (a_mn ? (b_mn ? launch_tc<BNv, true, true, CLv, X3v>(ma, mb, p, s) : launch_tc<BNv, true, false, CLv, X3v>(ma, mb, p, s)) \
+        : (b_mn ? launch_tc<BNv, false, true, CLv, X3v>(ma, mb, p, s) : launch_tc<BNv, false, false, CLv, X3v>(ma, mb, p, s)))
+#define AIR_TC_DISPATCH(BNv, CLv) (x3 ? AIR_TC_DISPATCH2(BNv, CLv, true) : AIR_TC_DISPATCH2(BNv, CLv, false))
   if (cl) rc = (BN == 128) ? AIR_TC_DISPATCH(128, true) : AIR_TC_DISPATCH(64, true);
   else rc = (BN == 128) ? AIR_TC_DISPATCH(128, false) : AIR_TC_DISPATCH(64, false);
 #undef AIR_TC_DISPATCH
+#undef AIR_TC_DISPATCH2
   if (rc) return rc;
   if (splits > 1) {
     const int64_t total = static_cast<int64_t>(M) * N / 4;
     const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
-    AIR_LAUNCH(splitk_reduce_kernel, blocks, 256, 0, s, ws, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param);
+    AIR_LAUNCH(splitk_reduce_kernel, blocks, 256, 0, s, workspace, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param);
     count_launch();
     rc = check_launch("splitk_reduce");
   }
@@ -580,7 +657,3 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
 }
 
 }  // namespace air
-
-extern "C" int air_gemm_set_workspace(float *workspace, int64_t nfloats) {
-  return air::set_gemm_workspace(workspace, workspace ? sizeof(float) * static_cast<size_t>(nfloats) : 0);
-}

@@ -81,21 +81,32 @@ def summarize_by_step(tensor, steps, target_digits, max_steps, max_digits, name,
     return out
 
 
-def evaluation_summaries(model, target_num_digits=None):
-    """The numeric summaries the reference logs for its test model (air_model.py:613-625)."""
+def evaluation_summaries(model, target_num_digits=None, reference_trip_count=True):
+    """The numeric summaries the reference logs for its test model (air_model.py:613-625).
+
+    The reference's while_loop leaves as soon as the WHOLE batch has stopped (air_model.py:271-275) and
+    _summarize_by_step zero-pads the steps that never ran (air_model.py:188); this model always runs max_steps
+    iterations, so with ``reference_trip_count`` the columns at and beyond ``model.executed_steps`` are zeroed first
+    (one host sync) -- that is what the reference would have logged for a batch that stops early."""
     t = model.target_num_digits if target_num_digits is None else target_num_digits
     t = t.cpu()
     d = model.rec_num_digits.cpu()
     md, ms = model.max_digits, model.max_steps
+    n_exec = model.executed_steps if reference_trip_count else ms
+
+    def per_step(x):
+        x = x.cpu().clone()
+        x[:, n_exec:] = 0
+        return x
     out = {}
     out.update(summarize_by_digit_count(d, t, md, "steps"))
     out.update(summarize_by_digit_count(model.reconstruction_loss.cpu(), t, md, "rec_loss"))
     out.update(summarize_by_digit_count((t == d).float(), t, md, "digit_acc"))
     out.update(summarize_by_digit_count(model.loss_per_item.cpu(), t, md, "total_loss"))
-    out.update(summarize_by_step(model.rec_scales[:, :, 0].cpu(), d, t, ms, md, "scale"))
-    out.update(summarize_by_step(model.z_pres_probs.cpu(), d, t, ms, md, "z_pres_prob", all_steps=True))
-    out.update(summarize_by_step(model.z_pres_kls.cpu(), d, t, ms, md, "z_pres_kl", one_more_step=True))
-    out.update(summarize_by_step(model.scale_kls.cpu(), d, t, ms, md, "scale_kl"))
-    out.update(summarize_by_step(model.shift_kls.cpu(), d, t, ms, md, "shift_kl"))
-    out.update(summarize_by_step(model.vae_kls.cpu(), d, t, ms, md, "vae_kl"))
+    out.update(summarize_by_step(per_step(model.rec_scales[:, :, 0]), d, t, ms, md, "scale"))
+    out.update(summarize_by_step(per_step(model.z_pres_probs), d, t, ms, md, "z_pres_prob", all_steps=True))
+    out.update(summarize_by_step(per_step(model.z_pres_kls), d, t, ms, md, "z_pres_kl", one_more_step=True))
+    out.update(summarize_by_step(per_step(model.scale_kls), d, t, ms, md, "scale_kl"))
+    out.update(summarize_by_step(per_step(model.shift_kls), d, t, ms, md, "shift_kl"))
+    out.update(summarize_by_step(per_step(model.vae_kls), d, t, ms, md, "vae_kl"))
     return out

@@ -25,8 +25,9 @@ def _p2(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.EPI_NONE, mode=0, epi_param=0.0):
-    """out[M,N] = epi((Cinit + op(A) op(B)) + bias); see include/air_b200.h (air_gemm)."""
+def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.EPI_NONE, mode=0, epi_param=0.0, ws=None):
+    """out[M,N] = epi((Cinit + op(A) op(B)) + bias); see include/air_b200.h (air_gemm_ws).
+    ``ws``: optional float32 CUDA scratch tensor on the operands' device: lets long-K / few-tile GEMMs run split-K."""
     M, N = out.shape
     K = A.shape[0] if tA else A.shape[1]
     kb = B.shape[1] if tB else B.shape[0]
@@ -36,8 +37,11 @@ def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.E
     for t in (Cinit, aux):
         if t is not None and (_ld(t) != ldc or t.shape != out.shape):
             raise C.AirError("Cinit / aux must have the layout of out")
-    check(lib().air_gemm_ex(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), _p2(aux), M, N, K, _ld(A), _ld(B), ldc,
-                            int(tA), int(tB), epi, float(epi_param), mode, stream()), "air_gemm")
+    if ws is not None and ws.device != out.device:
+        raise C.AirError("the GEMM workspace must live on the device of the operands")
+    check(lib().air_gemm_ws(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), _p2(aux), M, N, K, _ld(A), _ld(B), ldc,
+                            int(tA), int(tB), epi, float(epi_param), mode, ptr(ws), 0 if ws is None else ws.numel(),
+                            stream()), "air_gemm")
     return out
 
 
@@ -143,11 +147,6 @@ def anneal(state, schedule, out):
                            int(bool(schedule.get("staircase", False))), float(schedule.get("min", nan)),
                            float(schedule.get("max", nan)), int(bool(schedule.get("log", False))), ptr(out), stream()),
           "air_anneal")
-
-
-def set_gemm_workspace(ws):
-    """Attach a caller-owned split-K workspace (float32 CUDA tensor) to the TF32 GEMM; None detaches."""
-    check(lib().air_gemm_set_workspace(ptr(ws), 0 if ws is None else ws.numel()), "air_gemm_set_workspace")
 
 
 def st_forward(U, theta, out, H, W, Cc, oh, ow):
