@@ -284,13 +284,40 @@ int air_anneal(const float *state, float init, float factor, float iters, int st
                int take_log, float *out, air_stream_t stream);
 
 /* ---- synthetic input canvases, generated on the device -------------------------------
- * Stand-in for multi_mnist.py:82-183 (needs the MNIST download): 0..max_digits stroke-like blobs (14-24 x 10-24
- * pixels) per canvas, uniform placement with pixel-overlap rejection (generate_multi_image, :141-160, 20 attempts),
- * background exactly 0.0, values in (0, 1]; counts[b] = number of digits drawn for that image's target label.
+ * Stand-in for the data set of multi_mnist.py (needs the MNIST download) with generate_multi_image's placement
+ * semantics (multi_mnist.py:82-183, use_pixel_overlap, gap = margin = 0): 0..max_digits "digits" per canvas -- here
+ * stroke-like blobs (14-24 x 10-24 pixel frames, values in (0, 1], background exactly 0.0) cropped to their non-empty
+ * bounding box like crop_non_empty (:36-43) -- each placed at a uniform position, x drawn before y (:143-144); the
+ * first always fits, later ones are re-drawn up to 100 times (:141) until no pixel overlaps the canvas (pixels_overlap,
+ * :61-65); a digit that cannot be placed restarts the whole canvas with fresh digits (:95-171), so counts[b] always
+ * equals the number of digits drawn.  positions [B, max_digits, 2] = (x, y) and boxes [B, max_digits, 2] = (w, h) of
+ * the placed digits (:165-166), zero padded; both nullable.
  * Counter-based RNG: image first_index + b depends only on (seed, first_index + b), so ranks generate their own
- * shards of one global data set.  images [B, canvas_size^2], counts [B].  Bit-exact vs oracle/synth_oracle.py. */
+ * shards of one global data set.  images [B, canvas_size^2], counts [B].  Bit-exact vs oracle/synth_oracle.py, which
+ * is pinned to the reference's own generate_multi_image (tests/test_reference_source.py). */
 int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int64_t B, int canvas_size,
                        int max_digits, air_stream_t stream);
+int air_synth_canvases_ex(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int32_t *positions,
+                          int32_t *boxes, int64_t B, int canvas_size, int max_digits, air_stream_t stream);
+
+/* ---- host-side input path: the reference's multi-MNIST TFRecord files -----------------------------------------
+ * multi_mnist.py:186-212 writes tf.train.Example records (features height, width, digits: int64; indices, positions,
+ * boxes, labels: int32 bytes; image: canvas^2 float32 bytes); training reads them with TFRecordReader +
+ * parse_single_example + shuffle_batch on 4 threads (multi_mnist.py:228-251, training.py:28, 76-81).  These three
+ * entry points take HOST pointers (no CUDA); tfrecords.py builds the batched reader on them.
+ *
+ * air_tfrecord_index: one pass over the bytes of a .tfrecords file (e.g. a memory map): checks the framing
+ *   (u64 length, masked CRC-32C of the length, payload, masked CRC-32C of the payload; CRCs only if verify_crc), parses
+ *   each Example and stores the byte offset / length of its `image` payload and its `digits` value.  Returns the number
+ *   of records (with all three output pointers NULL: only counts, for sizing) or a negative AIR_ERR_* code.
+ * air_shuffle_order: the order in which a shuffle queue with min_after_dequeue = buffer, fed with record indices
+ *   0..n-1 `epochs` times, emits them (order[n * epochs]); deterministic in seed.
+ * air_gather_rows: dst[i, :] = src[offsets[i] : offsets[i] + row_bytes], i < n, on up to n_threads host threads
+ *   (dst is typically a pinned batch buffer). */
+int64_t air_tfrecord_index(const uint8_t *buf, uint64_t nbytes, int verify_crc, int64_t max_records, uint64_t *image_off,
+                           uint32_t *image_len, int32_t *digits);
+int air_shuffle_order(int64_t n, int64_t buffer, int epochs, uint64_t seed, int64_t *order);
+int air_gather_rows(const uint8_t *src, const uint64_t *offsets, int64_t n, uint64_t row_bytes, uint8_t *dst, int n_threads);
 
 /* ---- CNN front-end of AIRModel(cnn=True): air_model.py:510-535 -------------------------
  * tf.layers.conv2d(filters=8, kernel_size=5, padding="same", activation=relu) optionally followed by

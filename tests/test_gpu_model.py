@@ -184,7 +184,6 @@ def test_cuda_graph_capture_trains():
     assert m.global_step >= 30 and np.isfinite(m.loss.item()) and m.loss.item() < first
 
 
-@pytest.mark.parametrize("gemm_mode", EXACT_MODES)
 def test_injected_noise_is_one_shot():
     """The reference samples anew on every session.run; injection therefore covers exactly one evaluation."""
     B = 16

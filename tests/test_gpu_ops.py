@@ -192,9 +192,21 @@ def test_colsum_multi_and_reduce_rows():
 def test_device_canvas_generator_bit_exact_and_shardable():
     from air_b200 import data
     from oracle import synth_oracle as S
-    im, cnt = data.device_canvases(193, seed=11, first_index=5)
-    want_im, want_cnt = S.synth_canvases(193, seed=11, first_index=5)
+    im, cnt, pos, box = data.device_canvases(193, seed=11, first_index=5, with_boxes=True)
+    want_im, want_cnt, want_pos, want_box = S.synth_canvases(193, seed=11, first_index=5, with_boxes=True)
     assert np.array_equal(cnt.cpu().numpy(), want_cnt) and np.array_equal(im.cpu().numpy(), want_im)   # bit-exact
+    assert np.array_equal(pos.cpu().numpy().reshape(193, -1), want_pos) and np.array_equal(box.cpu().numpy().reshape(193, -1), want_box)
+    # the generator's invariants (multi_mnist.py:141-166): boxes inside the canvas, label == boxes written, the ink of a
+    # canvas is exactly the union of its boxes' ink (no pixel overlap), nothing outside the boxes
+    P, Bx, I = pos.cpu().numpy(), box.cpu().numpy(), im.cpu().numpy().reshape(193, 50, 50)
+    for b in range(193):
+        k = int(cnt[b])
+        assert (Bx[b, :k] > 0).all() and (Bx[b, k:] == 0).all()
+        mask = np.zeros((50, 50), bool)
+        for (x, y), (w, h) in zip(P[b, :k], Bx[b, :k]):
+            assert 0 <= x and x + w <= 50 and 0 <= y and y + h <= 50
+            mask[y:y + h, x:x + w] = True
+        assert not I[b][~mask].any()
     # image i of a seed does not depend on the batch it is generated in (data-parallel shards)
     a, ca = data.device_canvases(64, seed=11, first_index=5)
     b, cb = data.device_canvases(129, seed=11, first_index=69)

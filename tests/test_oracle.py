@@ -322,3 +322,39 @@ def test_cnn_c_restatement_agrees_with_torch_restatement(golden_dir):
     ones = C.conv5x5_relu_pool(np.ones((1, 4, 4, 1), np.float32), np.ones((5, 5, 1, 1), np.float32),
                                np.zeros(1, np.float32), False)[0, :, :, 0]
     assert np.array_equal(ones, np.outer([3, 4, 4, 3], [3, 4, 4, 3]).astype(np.float32))
+
+
+def test_synth_oracle_equals_the_references_generate_multi_image(golden_dir):
+    """tests/golden/ref_multi_mnist_gen.npz holds what the reference's OWN generate_multi_image (multi_mnist.py:82-183)
+    returned for the blobs and placement draws of images 5..100 of seed 11 (make_golden_multi_mnist.py): canvases bit
+    for bit, digit counts, positions (x, y) and boxes (w, h).  The restated generator must reproduce them exactly --
+    and the device generator is bit-exact with the restatement (tests/test_gpu_ops.py)."""
+    from oracle import synth_oracle as S
+    g = np.load(os.path.join(golden_dir, "ref_multi_mnist_gen.npz"))
+    n = len(g["counts"])
+    im, cnt, pos, box = S.synth_canvases(n, seed=int(g["seed"]), first_index=int(g["first_index"]), with_boxes=True)
+    assert np.array_equal(cnt, g["counts"]) and np.array_equal(im, g["canvases"])
+    assert np.array_equal(pos, g["positions"]) and np.array_equal(box, g["boxes"])
+    assert set(np.unique(cnt)) == {0, 1, 2} and (box[cnt == 2] > 0).all()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/multi_mnist.py"), reason="/root/reference not present (GPU box)")
+def test_references_generator_replayed_live_including_a_canvas_restart():
+    """The same replay, live, on other images -- and on a crowded 36x36 canvas with up to three digits, where placements
+    fail after 100 attempts and the reference starts the canvas over (multi_mnist.py:95-171): same restarts, same
+    result."""
+    from oracle import synth_oracle as S
+    from tests.golden import make_golden_multi_mnist as G
+    ref = G.load_reference()
+    for img in (1000, 1001, 1002, 1003, 1004, 1005):
+        canvas, count, _, pos, box = G.reference_canvas(ref, 3, img)
+        c2, k2, p2, b2 = S.one_canvas(3, img)
+        assert count == k2 and np.array_equal(canvas, c2) and list(pos) == list(p2[:2 * k2]) and list(box) == list(b2[:2 * k2])
+    restarted = 0
+    for img in range(40):
+        trace = {}
+        c2, k2, p2, b2 = S.one_canvas(7, img, cs=36, max_digits=3, trace=trace)
+        restarted += len(trace["blobs"]) > k2
+        canvas, count, _, pos, box = G.reference_canvas(ref, 7, img, cs=36, max_digits=3)
+        assert count == k2 and np.array_equal(canvas, c2) and list(pos) == list(p2[:2 * k2]) and list(box) == list(b2[:2 * k2])
+    assert restarted > 0, "the crowded configuration should exercise the restart path"

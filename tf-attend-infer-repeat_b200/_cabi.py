@@ -64,6 +64,13 @@ _SIGS = {
     "air_reduce_rows": (ctypes.c_int, [_c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_f, ctypes.c_int, _c_f]),
     "air_synth_canvases": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, _c_f, _c_f, ctypes.c_int64, ctypes.c_int,
                                           ctypes.c_int, _c_f]),
+    "air_synth_canvases_ex": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, _c_f, _c_f, _c_f, _c_f, ctypes.c_int64,
+                                             ctypes.c_int, ctypes.c_int, _c_f]),
+    "air_tfrecord_index": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
+    "air_shuffle_order": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]),
+    "air_gather_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p,
+                                       ctypes.c_int]),
     "air_conv5x5_fwd": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),
     "air_conv5x5_bwd_workspace": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "air_conv5x5_bwd": (ctypes.c_int, [_c_f] * 8 + [ctypes.c_int, _c_f, ctypes.c_int64] + [ctypes.c_int] * 5 + [_c_f]),

@@ -27,149 +27,9 @@
 // accumulated in `chains` TMEM accumulators used round-robin over the k-blocks and summed in FP32 (RN)
 // by the epilogue: the tensor core's accumulate step rounds toward zero, so shorter chains mean less of
 // that bias (measured in tests/diag_tc_rounding.py).
-#include <cuda.h>
-
-#include <algorithm>
-#include <atomic>
-#include <stdlib.h>
-
-#include "air_common.cuh"
-#include "epilogue.cuh"
+#include "tc_common.cuh"
 
 namespace air {
-
-constexpr int kBM = 128;      // UMMA M (cta_group::1)
-constexpr int kBK = 32;       // 32 tf32 = 128 bytes = one swizzle row
-constexpr int kMaxStages = 8;  // ring depth is chosen per launch: deep when one CTA owns the SM, shallow when two share it
-constexpr int kTcThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
-
-// ---- PTX wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// same load, delivered to the same shared-memory offsets (tile and mbarrier) of every CTA of the cluster in cta_mask
-__device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                               uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
-      "[%2], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// the same arrival, on the mbarrier at this offset in every CTA of cta_mask (frees a stage that both CTAs fill)
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t *r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// lo part of the 3xTF32 split: a - trunc_tf32(a) is exact in fp32 (<= 13 significant bits); rounding it to
-// TF32 here (RN) keeps the tensor core's own truncation of the operand from biasing it
-__device__ __forceinline__ float tf32_lo(float a) {
-  const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-  float lo = __fsub_rn(a, hi);
-  if ((__float_as_uint(a) & 0x7F800000u) == 0x7F800000u) lo = 0.0f;  // inf / NaN travel in the hi part only
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
-  return __uint_as_float(r);
-}
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout).
-// layout_type 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B: the only layout the
-// tensor core accepts for MN-major 32-bit (TF32) operands -- 32-byte swizzle granules, 4-row atoms.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);       // start address      [0,14)
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset [16,30)
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset  [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(layout_type) << 61;
-  return d;
-}
-
-// cute::UMMA::InstrDescriptor for kind::tf32, FP32 accumulate
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4)                                   // c_format = F32
-         | (2u << 7) | (2u << 10)                    // a_format = b_format = TF32
-         | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16)
-         | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
-
-struct TcParams {
-  float *C;             // output (or split-K workspace [splits][M][N] when splits > 1)
-  const float *Cinit;
-  const float *bias;
-  const float *aux;
-  int M, N, K, ldc, epi;
-  float epi_param;
-  int kb_per_split, num_kb, splits;
-  int stages;  // TMA->MMA ring depth (<= kMaxStages)
-  int chains;  // X3: number of hi*hi accumulators used round-robin over the k-blocks (1..kMaxChains)
-};
-
-constexpr int kMaxChains = 3;
-constexpr int kSplitWarps = 8;  // the epilogue warps write the lo tiles during the main loop (X3)
-
-__host__ __device__ constexpr uint32_t tmem_cols_for(int BN, bool x3) {
-  const int want = x3 ? (kMaxChains + 1) * BN : BN;
-  return want <= 32 ? 32u : want <= 64 ? 64u : want <= 128 ? 128u : want <= 256 ? 256u : 512u;
-}
 
 // CL: launched as clusters of two CTAs that are neighbours along M (same N tile).  They need the same B tile:
 // each loads half of it and multicasts it to both, which halves the L2 -> SM traffic of that operand (the kernel
@@ -330,87 +190,9 @@ __global__ void __launch_bounds__(kTcThreads)
   }
   if (warp >= 2) {
     // ================= epilogue: TMEM -> registers -> global (8 warps) =================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns
-    const int row = m0 + q * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    float *Cout = p.C;
-    int ldo = p.ldc;
-    const bool partial = p.splits > 1;
-    if (partial) {
-      Cout = p.C + static_cast<int64_t>(split) * p.M * p.N;
-      ldo = p.N;
-    }
-    const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) &&
-                        (partial || ((p.ldc % 4 == 0) && (!p.Cinit || (reinterpret_cast<uintptr_t>(p.Cinit) & 15) == 0) &&
-                                     (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) &&
-                                     (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
-    const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-    const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_x16(tbase + c0, r);
-      const int nb = n0 + c0;
-      const bool row_ok = row < p.M && nb < p.N;
-      const bool fast = vec_ok && row_ok && nb + 16 <= p.N;
-      float ci[16], ax[16], bi[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { ci[j] = 0.0f; ax[j] = 0.0f; bi[j] = 0.0f; }
-      const int64_t o = static_cast<int64_t>(row) * p.ldc + nb;
-      if (fast && !partial) {  // epilogue inputs are fetched while the TMEM load is in flight
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          if (p.Cinit) *reinterpret_cast<float4 *>(ci + 4 * j4) = *reinterpret_cast<const float4 *>(p.Cinit + o + 4 * j4);
-          if (p.aux) *reinterpret_cast<float4 *>(ax + 4 * j4) = *reinterpret_cast<const float4 *>(p.aux + o + 4 * j4);
-          if (p.bias) *reinterpret_cast<float4 *>(bi + 4 * j4) = __ldg(reinterpret_cast<const float4 *>(p.bias + nb) + j4);
-        }
-      }
-      tmem_ld_wait();
-      if (X3) {  // product = ((chain_0 + chain_1) + ...) + correction, FP32 round-to-nearest, fixed order
-        uint32_t r2[16];
-        for (int c = 1; c < chains; ++c) {
-          tmem_ld_x16(tbase + c * BN + c0, r2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
-        }
-        tmem_ld_x16(tbase + kMaxChains * BN + c0, r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
-      }
-      if (!row_ok) continue;
-      if (fast) {
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        if (!partial) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = (v[j] + ci[j]) + bi[j];
-          apply_epilogue16(v, ax, p.epi, p.epi_param);
-        }
-        float4 *dst = reinterpret_cast<float4 *>(Cout + static_cast<int64_t>(row) * ldo + nb);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = nb + j;
-          if (n < p.N) {
-            float v = __uint_as_float(r[j]);
-            if (!partial) {
-              const int64_t oo = static_cast<int64_t>(row) * p.ldc + n;
-              if (p.Cinit) v += p.Cinit[oo];
-              if (p.bias) v += __ldg(p.bias + n);
-              v = apply_epilogue(v, p.epi, p.aux ? p.aux[oo] : 0.0f, p.epi_param);
-            }
-            Cout[static_cast<int64_t>(row) * ldo + n] = v;
-          }
-        }
-      }
-    }
+    tc_epilogue<BN, X3>(p, tmem_acc, m0, n0, split, warp, lane, chains, kMaxChains * BN);
     tc_fence_before();
   }
   __syncthreads();
@@ -460,77 +242,24 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
+static int launch_splitk_reduce(const float *ws, int splits, float *C, const float *Cinit, const float *bias, const float *aux,
+                                int M, int N, int ldc, int epi, float epi_param, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(M) * N / 4;
+  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
+  AIR_LAUNCH(splitk_reduce_kernel, blocks, 256, 0, s, ws, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param);
+  count_launch();
+  return check_launch("splitk_reduce");
 }
 
-// 2-D fp32 tensor map: dim0 = contiguous dimension (extent d0), dim1 has stride ld elements (extent d1)
-static int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1, int64_t ld, int box0, int box1,
-                     bool mn_major) {
-  EncodeTiledFn enc = get_encode();
-  AIR_REQUIRE(enc != nullptr, AIR_ERR_CUDA, "air_gemm(TF32): cuTensorMapEncodeTiled is unavailable");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  AIR_REQUIRE(r == CUDA_SUCCESS, AIR_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (d0=%lld d1=%lld ld=%lld)", (int)r,
-              (long long)d0, (long long)d1, (long long)ld);
-  return AIR_OK;
-}
+int gemm_tf32_pair(const float *A, const float *B, TcParams p, int lda, int ldb, bool a_mn, bool b_mn, int BNP, bool x3,
+                   cudaStream_t s);  // gemm_tc2.cu
 
-// Tuning / diagnostics knobs, read ONCE when the library is first used (never on the launch path):
-//   AIR_TC_STAGES   ring depth override            AIR_TC_BN       force 64- or 128-wide tiles
-//   AIR_TC_CLUSTER  0 = never, 2 = always pair CTAs AIR_TC_CHAINS   hi*hi accumulator chains of the X3 mode (1..3)
-struct TcEnv {
-  int stages = 0, bn = 0, cluster = 1, chains = 2;
-  TcEnv() {
-    if (const char *e = getenv("AIR_TC_STAGES")) stages = std::max(1, atoi(e));
-    if (const char *e = getenv("AIR_TC_BN")) bn = atoi(e);
-    if (const char *e = getenv("AIR_TC_CLUSTER")) cluster = atoi(e);
-    if (const char *e = getenv("AIR_TC_CHAINS")) chains = std::max(1, std::min(atoi(e), kMaxChains));
-  }
-};
-static const TcEnv &tc_env() {
-  static const TcEnv env;
-  return env;
-}
-
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_cluster_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, dim3 cluster,
-                                      Args &&...args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster.x;
-  attr[0].val.clusterDim.y = cluster.y;
-  attr[0].val.clusterDim.z = cluster.z;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+// Width of the CTA-pair tile (0 = use the one-CTA kernel).
+static int pair_width(int M, int N, int num_kb, bool x3, int sms) {
+  const int env = tc_env().pair;
+  if (env == 0 || M <= kBM || N < 64) return 0;
+  if (env == 128 || env == 256) return N > 128 ? env : 128;
+  return 0;  // automatic choice: filled in from the per-shape measurements (profiles/r2_gemm_pair_shapes.md)
 }
 
 template <int BN, bool A_MN, bool B_MN, bool CL, bool X3>
@@ -549,6 +278,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, c
   if (tc_env().stages) stages = std::min(tc_env().stages, max_stages);
   p.stages = stages;
   p.chains = tc_env().chains;
+  p.flags = tc_env().flags;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
   const size_t smem_max = static_cast<size_t>(max_stages) * stage_bytes + 1024;
   // the opt-in shared-memory limit is a per-device function attribute: set it once per (instantiation, device)
@@ -606,6 +336,21 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
     sp = static_cast<int>(std::min<int64_t>(sp, ws_splits));
     return std::max(1, std::min(sp, 32));
   };
+  // CTA pairs (gemm_tc2.cu, 256 x 128|256 tiles): half the L2 -> SM operand bytes per FLOP.  AIR_TC_PAIR: 0 = never,
+  // 128 / 256 = force that pair width wherever a pair fits; default = automatic (see pair_width()).
+  const int BNP = pair_width(M, N, p.num_kb, x3, sms);
+  if (BNP) {
+    const int64_t ctas = 2 * static_cast<int64_t>((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BNP - 1) / BNP);
+    int splits = 1;
+    if (ctas < sms && can_split && p.num_kb >= 64) splits = want_splits(ctas);
+    p.kb_per_split = (p.num_kb + splits - 1) / splits;
+    splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = splits;
+    if (splits > 1) p.C = workspace;
+    int rc = gemm_tf32_pair(A, B, p, lda, ldb, a_mn, b_mn, BNP, x3, s);
+    if (rc) return rc;
+    return splits > 1 ? launch_splitk_reduce(workspace, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param, s) : AIR_OK;
+  }
   int BN, splits = 1;
   if (N > 64 && tiles128 >= sms) {
     BN = 128;  // at least one wide CTA per SM (most SMs get two)
@@ -646,14 +391,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
 #undef AIR_TC_DISPATCH
 #undef AIR_TC_DISPATCH2
   if (rc) return rc;
-  if (splits > 1) {
-    const int64_t total = static_cast<int64_t>(M) * N / 4;
-    const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
-    AIR_LAUNCH(splitk_reduce_kernel, blocks, 256, 0, s, workspace, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param);
-    count_launch();
-    rc = check_launch("splitk_reduce");
-  }
-  return rc;
+  return splits > 1 ? launch_splitk_reduce(workspace, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param, s) : AIR_OK;
 }
 
 }  // namespace air

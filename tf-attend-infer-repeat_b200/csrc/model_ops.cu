@@ -668,31 +668,51 @@ __device__ __forceinline__ uint64_t synth_rnd(uint64_t seed, uint64_t image, uin
   return z ^ (z >> 31);
 }
 
+// Placement semantics of multi_mnist.py:82-183 (generate_multi_image with use_pixel_overlap, gap = margin = 0):
+// every digit image is cropped to its non-empty bounding box (crop_non_empty, :36-43), placed at a uniform position
+// x in [0, cs - w], y in [0, cs - h] (x drawn before y, :143-144); the first digit always fits, later ones are
+// re-drawn up to 100 times until no pixel overlaps what is already on the canvas (pixels_overlap, :61-65); if a
+// digit cannot be placed the WHOLE canvas is started over with fresh digits (:95-171), so the label always equals the
+// number of digits drawn.  positions = [x, y] and boxes = [w, h] per placed digit (:165-166).
+constexpr int kSynthAttempts = 100;  // multi_mnist.py:141
+constexpr int kSynthRestarts = 64;   // the reference retries forever; a canvas that fails 64 times stays empty (label 0)
+
 __global__ void __launch_bounds__(256)
-    synth_canvases_k(uint64_t seed, int64_t first, float *__restrict__ images, int32_t *__restrict__ counts, int cs,
-                     int max_digits) {
+    synth_canvases_k(uint64_t seed, int64_t first, float *__restrict__ images, int32_t *__restrict__ counts,
+                     int32_t *__restrict__ positions, int32_t *__restrict__ boxes, int cs, int max_digits) {
   extern __shared__ float sC[];  // [cs*cs]
+  __shared__ int bb[4];          // y0, y1, x0, x1 of the blob's non-empty pixels
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
   const uint64_t img = static_cast<uint64_t>(first + b);
-  for (int p = tid; p < cs * cs; p += 256) sC[p] = 0.0f;
-  const int count = static_cast<int>((synth_rnd(seed, img, 0) >> 33) % static_cast<uint64_t>(max_digits + 1));
+  int count = static_cast<int>((synth_rnd(seed, img, 0) >> 33) % static_cast<uint64_t>(max_digits + 1));
   uint32_t draw = 1;
+  bool ready = count == 0;
+  for (int p = tid; p < cs * cs; p += 256) sC[p] = 0.0f;
+  for (int p = tid; p < 2 * max_digits; p += 256) {
+    if (positions) positions[b * 2 * max_digits + p] = 0;
+    if (boxes) boxes[b * 2 * max_digits + p] = 0;
+  }
   __syncthreads();
-  for (int k = 0; k < count; ++k) {
-    for (int attempt = 0; attempt < 20; ++attempt) {
+  for (int restart = 0; restart < kSynthRestarts && !ready; ++restart) {
+    if (restart) {
+      for (int p = tid; p < cs * cs; p += 256) sC[p] = 0.0f;
+      __syncthreads();
+    }
+    bool failed = false;
+    for (int k = 0; k < count && !failed; ++k) {
+      // ---- the "digit": a stroke-like blob in an hh x ww frame (MNIST itself is not available offline)
       const int hh = 14 + static_cast<int>((synth_rnd(seed, img, draw + 0) >> 33) % 11u);
       const int ww = 10 + static_cast<int>((synth_rnd(seed, img, draw + 1) >> 33) % 15u);
       const float bar_on = static_cast<float>((synth_rnd(seed, img, draw + 2) >> 33) & 1u);
       const float u = static_cast<float>(synth_rnd(seed, img, draw + 3) >> 40) * 5.9604644775390625e-08f;  // 2^-24
       const float bar_off = -2.0f + 4.0f * u;
-      const int top = static_cast<int>((synth_rnd(seed, img, draw + 4) >> 33) % static_cast<uint64_t>(cs - hh + 1));
-      const int left = static_cast<int>((synth_rnd(seed, img, draw + 5) >> 33) % static_cast<uint64_t>(cs - ww + 1));
-      draw += 6;
+      draw += 4;
       const float cy = static_cast<float>(hh - 1) / 2.0f, cx = static_cast<float>(ww - 1) / 2.0f;
       const float ry = fmaxf(static_cast<float>(hh) / 2.0f - 1.5f, 2.0f), rx = fmaxf(static_cast<float>(ww) / 2.0f - 1.5f, 2.0f);
+      if (tid == 0) { bb[0] = hh; bb[1] = -1; bb[2] = ww; bb[3] = -1; }
+      __syncthreads();
       float v[3];  // hh * ww <= 24 * 24 = 576 <= 3 * 256
-      int clash = 0;
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const int p = tid + 256 * q;
@@ -706,21 +726,59 @@ __global__ void __launch_bounds__(256)
           float val = fmaxf(ring, bar);
           if (val < 0.15f) val = 0.0f;
           v[q] = val;
-          if (val > 0.0f && sC[(top + y) * cs + left + x] > 0.0f) clash = 1;
-        }
-      }
-      if (__syncthreads_or(clash)) continue;  // overlap rejection (uniform decision)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int p = tid + 256 * q;
-        if (p < hh * ww) {
-          const int y = p / ww, x = p - y * ww;
-          float *c = &sC[(top + y) * cs + left + x];
-          *c = fmaxf(*c, v[q]);
+          if (val > 0.0f) {  // crop_non_empty: integer min / max are order independent
+            atomicMin(&bb[0], y); atomicMax(&bb[1], y); atomicMin(&bb[2], x); atomicMax(&bb[3], x);
+          }
         }
       }
       __syncthreads();
-      break;
+      const int y0 = bb[0], x0 = bb[2], h = bb[1] - bb[0] + 1, w = bb[3] - bb[2] + 1;
+      // ---- position: x then y, up to 100 draws
+      bool found = false;
+      int px = 0, py = 0;
+      for (int attempt = 0; attempt < kSynthAttempts && !found; ++attempt) {
+        px = static_cast<int>((synth_rnd(seed, img, draw + 0) >> 33) % static_cast<uint64_t>(cs - w + 1));
+        py = static_cast<int>((synth_rnd(seed, img, draw + 1) >> 33) % static_cast<uint64_t>(cs - h + 1));
+        draw += 2;
+        int clash = 0;
+        if (k > 0) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int p = tid + 256 * q;
+            if (p < hh * ww && v[q] > 0.0f) {
+              const int y = p / ww, x = p - y * ww;
+              if (sC[(py + y - y0) * cs + px + x - x0] > 0.0f) clash = 1;
+            }
+          }
+        }
+        found = !__syncthreads_or(clash);
+      }
+      if (!found) {
+        failed = true;  // uniform: start the canvas over
+        break;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int p = tid + 256 * q;
+        if (p < hh * ww && v[q] > 0.0f) {
+          const int y = p / ww, x = p - y * ww;
+          sC[(py + y - y0) * cs + px + x - x0] += v[q];  // canvas[y:y+h, x:x+w] += image (no overlap: 0 + v)
+        }
+      }
+      if (tid == 0) {
+        if (positions) { positions[(b * max_digits + k) * 2] = px; positions[(b * max_digits + k) * 2 + 1] = py; }
+        if (boxes) { boxes[(b * max_digits + k) * 2] = w; boxes[(b * max_digits + k) * 2 + 1] = h; }
+      }
+      __syncthreads();
+    }
+    ready = !failed;
+  }
+  if (!ready) {  // never observed; keeps label == digits drawn even then
+    count = 0;
+    for (int p = tid; p < cs * cs; p += 256) sC[p] = 0.0f;
+    for (int p = tid; p < 2 * max_digits; p += 256) {
+      if (positions) positions[b * 2 * max_digits + p] = 0;
+      if (boxes) boxes[b * 2 * max_digits + p] = 0;
     }
   }
   __syncthreads();
@@ -927,16 +985,21 @@ extern "C" int air_colsum_multi(const air_colsum_item_t *items, int n_items, flo
   return check_launch("colsum_multi");
 }
 
-extern "C" int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int64_t B,
-                                  int canvas_size, int max_digits, air_stream_t stream) {
+extern "C" int air_synth_canvases_ex(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int32_t *positions,
+                                     int32_t *boxes, int64_t B, int canvas_size, int max_digits, air_stream_t stream) {
   AIR_REQUIRE(B >= 0 && canvas_size >= 24 && canvas_size <= 104 && max_digits >= 0 && first_index >= 0, AIR_ERR_BAD_SHAPE,
               "synth_canvases: bad arguments (24 <= canvas_size <= 104)");
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(images && counts, AIR_ERR_NULL, "synth_canvases: null pointer");
   AIR_LAUNCH(synth_canvases_k, static_cast<unsigned>(B), 256, static_cast<size_t>(canvas_size) * canvas_size * 4, ST(stream), seed,
-             first_index, images, counts, canvas_size, max_digits);
+             first_index, images, counts, positions, boxes, canvas_size, max_digits);
   count_launch();
   return check_launch("synth_canvases");
+}
+
+extern "C" int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int64_t B,
+                                  int canvas_size, int max_digits, air_stream_t stream) {
+  return air_synth_canvases_ex(seed, first_index, images, counts, nullptr, nullptr, B, canvas_size, max_digits, stream);
 }
 
 extern "C" int air_reduce_rows(const float *partials, int R, int stride, int n, float *out, int accumulate, air_stream_t stream) {

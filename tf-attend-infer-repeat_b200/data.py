@@ -37,7 +37,7 @@ def synthetic_canvases(B, canvas_size=50, max_digits=2, seed=0, n_templates=256)
     return torch.from_numpy(imgs.reshape(B, -1)), torch.from_numpy(counts)
 
 
-def device_canvases(B, seed=0, first_index=0, canvas_size=50, max_digits=2, device="cuda", out=None):
+def device_canvases(B, seed=0, first_index=0, canvas_size=50, max_digits=2, device="cuda", out=None, with_boxes=False):
     """Multi-digit canvases generated ON the GPU (air_synth_canvases): -> (images [B, cs*cs] fp32, counts [B] int32).
     Image ``first_index + b`` depends only on (seed, first_index + b): data-parallel ranks call this with their own
     ``first_index`` and together hold one global, reproducible data set.  ``out=(images, counts)`` refills buffers
@@ -45,6 +45,11 @@ def device_canvases(B, seed=0, first_index=0, canvas_size=50, max_digits=2, devi
     from . import ops
     if out is None:
         out = (torch.empty(B, canvas_size * canvas_size, device=device), torch.empty(B, device=device, dtype=torch.int32))
+    if with_boxes:   # + the generator's bookkeeping (multi_mnist.py:165-166): positions (x, y), boxes (w, h)
+        pos = torch.empty(B, max_digits, 2, device=out[0].device, dtype=torch.int32)
+        box = torch.empty_like(pos)
+        ops.synth_canvases(out[0], out[1], seed, first_index, canvas_size, max_digits, positions=pos, boxes=box)
+        return out[0], out[1], pos, box
     return ops.synth_canvases(out[0], out[1], seed, first_index, canvas_size, max_digits)
 
 

@@ -92,7 +92,8 @@ def evaluation_summaries(model, target_num_digits=None, reference_trip_count=Tru
     t = t.cpu()
     d = model.rec_num_digits.cpu()
     md, ms = model.max_digits, model.max_steps
-    n_exec = model.executed_steps if reference_trip_count else ms
+    # (stand-ins that already carry the reference's dynamic time dimension have no executed_steps: nothing to trim)
+    n_exec = getattr(model, "executed_steps", ms) if reference_trip_count else ms
 
     def per_step(x):
         x = x.cpu().clone()

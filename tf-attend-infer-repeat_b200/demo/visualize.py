@@ -36,19 +36,18 @@ def resize_bilinear(images, size):
 
 
 def draw_colored_bounding_boxes(images, boxes, steps):
-    """air_model.py:130-158.  images [N,H,W,1], boxes [N,>=3,H,W] in {0,1}, steps [N] int: frame s is added to colour
-    channel s and subtracted from the other two, for the images that executed more than s steps."""
-    channels = [images, images, images]
-    one, zero = torch.ones_like(images), torch.zeros_like(images)
+    """air_model.py:130-158.  images [N,H,W,1], boxes [N,>=3,H,W], steps [N] int -> [N,H,W,3].
+    The frame of step s is added to colour channel s (saturating at 1) and subtracted from the other two (saturating
+    at 0), for the images that executed more than s steps.  All three channels are carried in one [N,H,W,3] tensor:
+    per step, a +1 / -1 / -1 pattern along the channel axis says which saturation applies -- the same two roundings
+    per element as the reference's nine tf.where updates, hence bit-identical."""
+    rgb = images.expand(-1, -1, -1, 3)
+    plus = torch.eye(3, dtype=torch.bool, device=images.device)           # plus[s, c]: channel c gains frame s
     for s in range(3):
-        step_box = boxes[:, s, :, :].unsqueeze(3)
-        live = (steps > s).reshape(-1, 1, 1, 1)
-        for c in range(3):
-            if s == c:
-                channels[c] = torch.where(live, torch.minimum(channels[c] + step_box, one), channels[c])
-            else:
-                channels[c] = torch.where(live, torch.maximum(channels[c] - step_box, zero), channels[c])
-    return torch.cat(channels, dim=3)
+        frame = boxes[:, s, :, :, None]                                   # [N,H,W,1], broadcast over the channels
+        updated = torch.where(plus[s], (rgb + frame).clamp_max(1.0), (rgb - frame).clamp_min(0.0))
+        rgb = torch.where((steps > s).view(-1, 1, 1, 1), updated, rgb)
+    return rgb
 
 
 def visualize_reconstructions(original, reconstruction, st_back, steps, max_steps=3, canvas_size=50, windows_size=28,

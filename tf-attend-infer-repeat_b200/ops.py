@@ -219,11 +219,15 @@ def conv5x5_bwd(x, w, out, argmax, dout, din, dw, db, accumulate, workspace, H, 
           "air_conv5x5_bwd")
 
 
-def synth_canvases(images, counts, seed=0, first_index=0, canvas_size=50, max_digits=2):
-    """Fill images [B, canvas_size**2] / counts [B] int32 with device-generated multi-digit canvases."""
-    if counts.dtype != torch.int32:
-        raise C.AirError("counts must be int32")
-    check(lib().air_synth_canvases(int(seed), int(first_index), ptr(images), ptr(counts), images.shape[0], canvas_size,
-                                   max_digits, stream()), "air_synth_canvases")
+def synth_canvases(images, counts, seed=0, first_index=0, canvas_size=50, max_digits=2, positions=None, boxes=None):
+    """Fill images [B, canvas_size**2] / counts [B] int32 with device-generated multi-digit canvases; optionally the
+    (x, y) positions and (w, h) boxes of the placed digits, int32 [B, max_digits, 2] each (multi_mnist.py:165-166)."""
+    for t in (counts, positions, boxes):
+        if t is not None and t.dtype != torch.int32:
+            raise C.AirError("counts / positions / boxes must be int32")
+    for t in (positions, boxes):
+        if t is not None and t.numel() != images.shape[0] * 2 * max_digits:
+            raise C.AirError("positions / boxes must hold [B, max_digits, 2] entries")
+    check(lib().air_synth_canvases_ex(int(seed), int(first_index), ptr(images), ptr(counts), ptr(positions), ptr(boxes),
+                                      images.shape[0], canvas_size, max_digits, stream()), "air_synth_canvases")
     return images, counts
-

@@ -157,55 +157,95 @@ def read_test_data(filename, shift_zero_digits_images=False):
         boxes_list.append(np.frombuffer(ex["boxes"], dtype=np.int32)[:d * 2].copy())
         labels_list.append(np.frombuffer(ex["labels"], dtype=np.int32)[:d].copy())
     if shift_zero_digits_images:
-        empty = [i for i in range(len(digits_list)) if digits_list[i] == 0]
-        non_empty = [i for i in range(len(digits_list)) if digits_list[i] > 0]
-        images_list, digits_list = np.array(images_list), np.array(digits_list)
-        images_list = np.concatenate([np.array([images_list[empty[0]]]), images_list[non_empty], images_list[empty[1:]]])
-        digits_list = np.concatenate([np.array([digits_list[empty[0]]]), digits_list[non_empty], digits_list[empty[1:]]])
+        # one stable permutation does the reference's three-way concatenation (multi_mnist.py:284-294): rank 0 for the
+        # first empty canvas, rank 1 for every canvas with digits, rank 2 for the remaining empty ones
+        digits_arr = np.asarray(digits_list)
+        rank = np.where(digits_arr > 0, 1, 2)
+        rank[np.flatnonzero(digits_arr == 0)[0]] = 0    # (IndexError without an empty canvas, as in the reference)
+        order = np.argsort(rank, kind="stable")
+        images_list, digits_list = np.asarray(images_list)[order], digits_arr[order]
     return images_list, digits_list, indices_list, positions_list, boxes_list, labels_list
+
+
+class TFRecordFile:
+    """A memory-mapped multi-MNIST TFRecord file with an index built ONCE by the native scanner
+    (air_tfrecord_index: framing + CRCs + tf.train.Example parse): ``digits`` [n] int32 and the byte offset of every
+    record's ``image`` payload.  Batches are then plain multi-threaded gathers out of the page cache
+    (air_gather_rows) -- no per-record Python work, unlike the reference's 4 reader threads + shuffle queue
+    (multi_mnist.py:228-251, training.py:76-81)."""
+
+    def __init__(self, path, canvas_size=50, verify_crc=True):
+        import ctypes
+        import mmap
+        from . import _cabi as C
+        self._C, self._ct = C, ctypes
+        self.path, self.row_bytes = path, canvas_size * canvas_size * 4
+        self._f = open(path, "rb")
+        size = self._f.seek(0, 2)
+        self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ) if size else None
+        self._buf = np.frombuffer(self._mm, dtype=np.uint8) if size else np.zeros(0, np.uint8)
+        lib, base = C.lib(), self._buf.ctypes.data
+        n = int(lib.air_tfrecord_index(base, size, int(verify_crc), 0, None, None, None))
+        if n < 0:
+            raise ValueError(f"{path}: {lib.air_last_error().decode()}")
+        self.offsets, lens = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        self.digits = np.zeros(n, np.int32)
+        if n:
+            got = int(lib.air_tfrecord_index(base, size, 0, n, self.offsets.ctypes.data, lens.ctypes.data, self.digits.ctypes.data))
+            if got != n:
+                raise ValueError(f"{path}: {lib.air_last_error().decode()}")
+            if not (lens == self.row_bytes).all():
+                raise ValueError(f"{path}: record image has {int(lens[lens != self.row_bytes][0]) // 4} pixels, "
+                                 f"expected {canvas_size}^2")
+
+    def __len__(self):
+        return len(self.digits)
+
+    def gather(self, idx, out=None, threads=None):
+        """images [len(idx), canvas^2] float32 of the records ``idx`` (int array) into ``out`` (a CPU tensor, ideally
+        pinned) -> (images, digits int32 tensor)."""
+        import os
+        import torch
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        n = len(idx)
+        if out is None:
+            out = torch.empty(n, self.row_bytes // 4)
+        if out.shape[0] < n or out.shape[1] * 4 != self.row_bytes or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("gather: bad output buffer")
+        offs = np.ascontiguousarray(self.offsets[idx])
+        self._C.check(self._C.lib().air_gather_rows(self._buf.ctypes.data, offs.ctypes.data, n, self.row_bytes, out.data_ptr(),
+                                                    threads or os.cpu_count() or 1), "air_gather_rows")
+        return out[:n], torch.from_numpy(self.digits[idx])
+
+    def shuffle_order(self, shuffle_buffer=10000, seed=0, epochs=1):
+        """Record indices in the order a shuffle queue with min_after_dequeue = shuffle_buffer emits them."""
+        order = np.zeros(len(self) * epochs, np.int64)
+        self._C.check(self._C.lib().air_shuffle_order(len(self), int(shuffle_buffer), int(epochs), int(seed), order.ctypes.data),
+                      "air_shuffle_order")
+        return order
+
+    def batches(self, batch_size, shuffle_buffer=10000, seed=0, epochs=1, pin_memory=True, ring=3):
+        """(images [batch, canvas^2] float32, digits [batch] int32) batches in shuffle-queue order; incomplete
+        trailing batches are dropped, as shuffle_batch does.  Pinned buffers are reused round-robin (``ring`` of them):
+        a batch stays valid until ``ring - 1`` further batches have been drawn."""
+        import torch
+        order = self.shuffle_order(shuffle_buffer, seed, epochs)
+        pin = pin_memory and torch.cuda.is_available()
+        bufs = [torch.empty(batch_size, self.row_bytes // 4, pin_memory=pin) for _ in range(max(ring, 1))]
+        for k in range(len(order) // batch_size):
+            imgs, digs = self.gather(order[k * batch_size:(k + 1) * batch_size], out=bufs[k % len(bufs)])
+            yield imgs, (digs.pin_memory() if pin else digs)
 
 
 def read_and_decode(filename, batch_size, canvas_size, shuffle_buffer=10000, seed=0, epochs=1, pin_memory=True):
     """Batches of (images [batch, canvas*canvas] float32, digits [batch] int32) like multi_mnist.py:228-251
-    (TFRecordReader + shuffle_batch with min_after_dequeue=10000), as pinned torch tensors ready for
-    ``AIRModel.feed``.  Incomplete trailing batches are dropped, as shuffle_batch does."""
-    import torch
-    rng = np.random.RandomState(seed)
-    buf_img, buf_dig = [], []
-
-    def emit():
-        idx = rng.randint(len(buf_img))
-        buf_img[idx], buf_img[-1] = buf_img[-1], buf_img[idx]
-        buf_dig[idx], buf_dig[-1] = buf_dig[-1], buf_dig[idx]
-        return buf_img.pop(), buf_dig.pop()
-
-    out_i, out_d = [], []
-
-    def flush():
-        imgs, digs = torch.from_numpy(np.stack(out_i)), torch.from_numpy(np.asarray(out_d, dtype=np.int32))
-        out_i.clear()
-        out_d.clear()
-        if pin_memory and torch.cuda.is_available():
-            imgs, digs = imgs.pin_memory(), digs.pin_memory()
-        return imgs, digs
-
-    for _ in range(epochs):
-        for rec in iter_records(filename):
-            ex = decode_example(rec)
-            img = np.frombuffer(ex["image"], dtype=np.float32)
-            if img.size != canvas_size * canvas_size:
-                raise ValueError(f"record image has {img.size} pixels, expected {canvas_size}^2")
-            buf_img.append(img.copy())
-            buf_dig.append(int(ex["digits"][0]))
-            if len(buf_img) > shuffle_buffer:
-                i, d = emit()
-                out_i.append(i)
-                out_d.append(d)
-                if len(out_i) == batch_size:
-                    yield flush()
-    while buf_img:
-        i, d = emit()
-        out_i.append(i)
-        out_d.append(d)
-        if len(out_i) == batch_size:
-            yield flush()
+    (TFRecordReader + shuffle_batch with min_after_dequeue=10000), ready for ``AIRModel.feed``.  Each batch owns its
+    memory (use TFRecordFile.batches for the zero-allocation ring of pinned buffers)."""
+    f = TFRecordFile(filename, canvas_size)
+    for imgs, digs in f.batches(batch_size, shuffle_buffer, seed, epochs, pin_memory=False, ring=1):
+        imgs, digs = imgs.clone(), digs.clone()
+        if pin_memory:
+            import torch
+            if torch.cuda.is_available():
+                imgs, digs = imgs.pin_memory(), digs.pin_memory()
+        yield imgs, digs
