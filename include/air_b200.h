@@ -140,9 +140,12 @@ int air_concrete_step_bwd(const float *log_odds, const float *y, const float *z,
  * mode AIR_GEMM_TF32: tcgen05 tensor cores, operands cut to TF32 (top 19 bits), FP32 accumulation in TMEM
  *   (~1e-3 relative: the throughput mode);
  * mode AIR_GEMM_TF32X3: tcgen05 tensor cores at FP32 accuracy ("3xTF32"): every operand is split in-kernel into
- *   hi + lo TF32 parts, three MMAs per k-step (hi*hi, lo*hi, hi*lo), FP32 accumulation; error ~1e-6 relative,
+ *   hi + lo TF32 parts, three MMAs per k-step (hi*hi, lo*hi, hi*lo), FP32 accumulation; error 1-3e-6 norm-wise,
  *   the same order as an FP32 FMA chain of that length.  This is the mode the model-level parity bars
- *   (<= 1e-5 outputs / ELBO, <= 1e-4 gradients) are checked in at tensor-core speed. */
+ *   (<= 1e-5 outputs / ELBO, <= 1e-4 gradients) are checked in at tensor-core speed.  What remains over FP32 is the
+ *   tensor core's accumulate step, which rounds toward zero (~0.5 ulp of bias per 8-deep MMA): the kernels keep the
+ *   hi*hi accumulation chains short (three round-robin TMEM accumulators, or K split through the caller's workspace
+ *   -- air_gemm_ws -- and summed in FP32 round-to-nearest); a K > ~8192 GEMM WITHOUT a workspace is ~1e-5. */
 #define AIR_EPI_NONE 0
 #define AIR_EPI_RELU 1
 #define AIR_EPI_SOFTPLUS 2      /* tf.nn.softplus: x>13.94->x, x<-13.94->exp(x), else log(exp(x)+1) */

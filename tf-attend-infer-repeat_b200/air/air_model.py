@@ -117,14 +117,15 @@ class AIRModel:
         self.pg = process_group
         self.world = dp.world_size(process_group)
 
-        self._alloc()
         # torch-owned split-K scratch for the weight-gradient GEMMs of the tensor-core modes, one per device, handed
         # to the library with every call (the library keeps no pointer and allocates nothing)
         self._gemm_ws = None
-        if train and self.gemm != C.GEMM_MODES["fp32"]:
+        if self.gemm != C.GEMM_MODES["fp32"]:
             if self.device not in _GEMM_WORKSPACES:
                 _GEMM_WORKSPACES[self.device] = torch.empty(16 << 20, device=self.device, dtype=torch.float32)
             self._gemm_ws = _GEMM_WORKSPACES[self.device]
+            self.gemm = ops.GemmMode(self.gemm, self._gemm_ws)   # every GEMM of the model may split K through it
+        self._alloc()
         self._graphs = None
         self.noise = None
         self.rec_num_digits = self.rec_scales = None

@@ -254,12 +254,20 @@ static int launch_splitk_reduce(const float *ws, int splits, float *C, const flo
 int gemm_tf32_pair(const float *A, const float *B, TcParams p, int lda, int ldb, bool a_mn, bool b_mn, int BNP, bool x3,
                    cudaStream_t s);  // gemm_tc2.cu
 
-// Width of the CTA-pair tile (0 = use the one-CTA kernel).
-static int pair_width(int M, int N, int num_kb, bool x3, int sms) {
+// Width of the CTA-pair tile (0 = use the one-CTA kernel).  From the per-shape measurements of the model's 26 GEMMs
+// (profiles/r2_gemm_shapes.md): in plain TF32 the pair kernel wins where the main loop is long and the grid is wide
+// (the image projection and its weight gradient: 34 vs 48 us, 54 vs 69 us); the short-K GEMMs are bound by per-CTA
+// fixed costs and prefer two co-resident one-CTA tiles.  In the 3xTF32 mode every k-block costs three MMAs and two
+// extra shared-memory passes, so halving the operand traffic pays almost everywhere (-35 % over the step).
+constexpr int kX3MaxChainKb = 26;  // longest hi*hi accumulation chain (k-blocks) of the 256-wide X3 pair tile, see below
+static int pair_width(int M, int N, int num_kb, bool x3) {
   const int env = tc_env().pair;
-  if (env == 0 || M <= kBM || N < 64) return 0;
+  if (env == 0 || M <= kBM || N < 128) return 0;
   if (env == 128 || env == 256) return N > 128 ? env : 128;
-  return 0;  // automatic choice: filled in from the per-shape measurements (profiles/r2_gemm_pair_shapes.md)
+  if (!x3) return (num_kb >= 64 && N >= 512 && M >= 512) ? 256 : 0;
+  if (num_kb <= 4) return 0;
+  if (num_kb >= 64) return N > 128 ? 256 : 128;
+  return N >= 768 ? 256 : 128;
 }
 
 template <int BN, bool A_MN, bool B_MN, bool CL, bool X3>
@@ -338,11 +346,20 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   };
   // CTA pairs (gemm_tc2.cu, 256 x 128|256 tiles): half the L2 -> SM operand bytes per FLOP.  AIR_TC_PAIR: 0 = never,
   // 128 / 256 = force that pair width wherever a pair fits; default = automatic (see pair_width()).
-  const int BNP = pair_width(M, N, p.num_kb, x3, sms);
+  int BNP = pair_width(M, N, p.num_kb, x3);
   if (BNP) {
-    const int64_t ctas = 2 * static_cast<int64_t>((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BNP - 1) / BNP);
+    int64_t ctas = 2 * static_cast<int64_t>((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BNP - 1) / BNP);
     int splits = 1;
-    if (ctas < sms && can_split && p.num_kb >= 64) splits = want_splits(ctas);
+    if (2 * ctas <= sms && can_split && p.num_kb >= 64) splits = want_splits(ctas);  // (a nearly full wave stays unsplit)
+    if (x3 && BNP == 256 && (p.num_kb + splits - 1) / splits > kX3MaxChainKb) {
+      // The 256-wide X3 tile has TMEM columns for ONE hi*hi accumulator (256 + 256 correction = 512), and the tensor
+      // core's accumulate step rounds toward zero: a chain of n k-blocks is biased by ~2 n ulp.  Keep chains short by
+      // splitting K (the partial sums are added in FP32 round-to-nearest by the second pass), or use the 128-wide
+      // tile with its three round-robin accumulators when there is no workspace for that.
+      const int need = (p.num_kb + kX3MaxChainKb - 1) / kX3MaxChainKb;
+      if (can_split && need <= ws_splits && need <= 32) splits = std::max(splits, need);
+      else { BNP = 128; ctas *= 2; splits = 1; if (2 * ctas <= sms && can_split && p.num_kb >= 64) splits = want_splits(ctas); }
+    }
     p.kb_per_split = (p.num_kb + splits - 1) / splits;
     splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
     p.splits = splits;

@@ -276,7 +276,7 @@ inline int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1
 //   AIR_TC_CHAINS   hi*hi accumulator chains of the X3 mode (1..3)
 //   AIR_TC_PAIR     0 = never use the cta_group::2 kernel, 128 / 256 = force that pair-tile width, 1 = automatic
 struct TcEnv {
-  int stages = 0, bn = 0, cluster = 1, chains = 2, pair = 1, flags = 0;
+  int stages = 0, bn = 0, cluster = 1, chains = 3, pair = 1, flags = 0;
   TcEnv() {
     if (const char *e = getenv("AIR_TC_STAGES")) stages = std::max(1, atoi(e));
     if (const char *e = getenv("AIR_TC_BN")) bn = atoi(e);

@@ -25,6 +25,16 @@ def _p2(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+class GemmMode(int):
+    """An air_gemm mode (AIR_GEMM_*) that carries the caller's split-K scratch tensor: ``GemmMode(mode, ws)`` can be
+    passed wherever a plain mode integer is accepted and makes every gemm() call hand ``ws`` to the library."""
+
+    def __new__(cls, mode, ws=None):
+        self = super().__new__(cls, int(mode))
+        self.ws = ws
+        return self
+
+
 def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.EPI_NONE, mode=0, epi_param=0.0, ws=None):
     """out[M,N] = epi((Cinit + op(A) op(B)) + bias); see include/air_b200.h (air_gemm_ws).
     ``ws``: optional float32 CUDA scratch tensor on the operands' device: lets long-K / few-tile GEMMs run split-K."""
@@ -37,10 +47,12 @@ def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.E
     for t in (Cinit, aux):
         if t is not None and (_ld(t) != ldc or t.shape != out.shape):
             raise C.AirError("Cinit / aux must have the layout of out")
+    if ws is None:
+        ws = getattr(mode, "ws", None)
     if ws is not None and ws.device != out.device:
         raise C.AirError("the GEMM workspace must live on the device of the operands")
     check(lib().air_gemm_ws(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), _p2(aux), M, N, K, _ld(A), _ld(B), ldc,
-                            int(tA), int(tB), epi, float(epi_param), mode, ptr(ws), 0 if ws is None else ws.numel(),
+                            int(tA), int(tB), epi, float(epi_param), int(mode), ptr(ws), 0 if ws is None else ws.numel(),
                             stream()), "air_gemm")
     return out
 
