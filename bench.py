@@ -319,6 +319,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=["train", "st", "infer"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 4096 train, 65536 st)")
+    ap.add_argument("--global-batch", type=int, default=None, dest="global_batch",
+                    help="train: fixed GLOBAL batch sharded over the ranks (configs[3]: 32768); default is a fixed per-GPU batch")
     ap.add_argument("--gemm", default=None, help="GEMM mode for the train workload")
     ap.add_argument("--cnn", action="store_true", help="train/infer with the CNN front-end (AIRModel(cnn=True)); not the headline config")
     args = ap.parse_args()
@@ -358,6 +360,17 @@ def main():
                 line["st_microbench"] = st_summary(peaks)
             except Exception as e:  # never lose the train line over the side measurement
                 line["st_microbench"] = {"error": str(e)[:200]}
+            try:  # configs[4] (inference, B = 65536, 5 steps) in compact form (full line: --workload infer)
+                import copy
+                import torch
+                torch.cuda.empty_cache()
+                a2 = copy.copy(args)
+                a2.workload, a2.batch, a2.steps = "infer", None, 20
+                inf = bench_train.run(a2, rank, world, peaks)
+                line["inference_c5"] = {k: inf[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "kernels_per_step")}
+                line["inference_c5"]["config"] = {k: inf["config"][k] for k in ("workload", "batch_per_gpu", "gemm_mode", "cuda_graph")}
+            except Exception as e:
+                line["inference_c5"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -16,6 +16,9 @@ def _model(B, gemm_mode, seed, train=True, max_steps=3, cnn=False):
     from importlib import import_module
     data = import_module("tf-attend-infer-repeat_b200.data")
     imgs, cnt = data.synthetic_canvases(B, seed=seed)
+    # like the reference's MNIST-derived data set, the canvases hold the 256 values k * fl(1/255) (see air_expand_u8):
+    # the same batch exists as uint8 (what the end-to-end path ships over PCIe) and as fp32 (device-resident runs)
+    imgs = torch.round(imgs * 255.0).to(torch.uint8).float() * torch.tensor(1.0 / 255.0, dtype=torch.float32)
     hyper = dict(data.TRAINING_HYPER)
     hyper["max_steps"] = max_steps
     hyper["cnn"] = bool(cnn)   # air_model.py:510-535 front-end (the reference's own scripts all run cnn=False)
@@ -88,6 +91,50 @@ def parity_block(mode, B=4096, T=3, seed=7):
     return res
 
 
+def dp_check(m, rank, world, mode, T=3):
+    """Evidence that the data-parallel step is the single-process step: (a) after the timed steps every rank holds
+    bit-identical parameters (checksums over the raw bits, all-gathered); (b) on a global batch of 64 sharded over the
+    ranks, the all-reduced gradient equals the gradient a single-GPU model computes on the whole batch (same weights,
+    canvases, injected noise), up to fp32 summation order."""
+    import torch.distributed as dist
+    import air_b200 as ab
+    bits = m.store.flat.view(torch.int32).to(torch.int64)
+    cs = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=bits.device)).sum(),
+                      torch.tensor(int(m.global_step), device=bits.device)])
+    allcs = [torch.empty_like(cs) for _ in range(world)]
+    dist.all_gather(allcs, cs)
+    identical = all(torch.equal(allcs[0], c) for c in allcs)
+    Bg = 64
+    g = torch.Generator(device="cuda").manual_seed(123)
+    L, win = 50, 784
+    noise = dict(scale=torch.randn(T, Bg, 1, device="cuda", generator=g), shift=torch.randn(T, Bg, 2, device="cuda", generator=g),
+                 vae_latent=torch.randn(T, Bg, L, device="cuda", generator=g), vae_like=torch.randn(T, Bg, win, device="cuda", generator=g),
+                 concrete_u=torch.rand(T, Bg, device="cuda", generator=g))
+    from importlib import import_module
+    data = import_module("tf-attend-infer-repeat_b200.data")
+    imgs, cnt = data.synthetic_canvases(Bg, seed=99)
+    hyper = dict(data.TRAINING_HYPER)
+
+    def build(images, counts, scope, pg):
+        mm = ab.AIRModel(images.cuda(), counts.cuda(), train=True, annealing_schedules=data.TRAINING_ANNEALING, gemm_mode=mode,
+                         seed=0, scope=scope, process_group=pg, **hyper)
+        mm.feed(_covered(mm, images).cuda())
+        mm.store.global_step = 2000
+        return mm
+    per = Bg // world
+    sl = slice(rank * per, (rank + 1) * per)
+    m_dp = build(imgs[sl], cnt[sl], "dpcheck_shard", None)
+    m_dp.loss_and_grads({k: v[:, sl].contiguous() for k, v in noise.items()})
+    m_ref = build(imgs, cnt, "dpcheck_full", "local")
+    m_ref.loss_and_grads(noise)
+    err = float((m_dp.store.grad.double() - m_ref.store.grad.double()).norm() / m_ref.store.grad.double().norm())
+    worst = torch.tensor([err], device="cuda", dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    return {"replicas_bit_identical_after_timed_steps": bool(identical), "global_step": int(m.global_step),
+            "reduced_grad_vs_single_gpu_rel_err": float(worst.item()), "fixture": f"global batch {Bg} = {per} rows per rank, covered poses, injected noise",
+            "gemm_mode": mode}
+
+
 def gemm_roofline(B, mode, peaks, steps=20):
     """The dominant kernel of the step: the [B,2500]x[2500,1024] LSTM input projection GEMM
     (and its twin dK = x^T dgates), timed alone with CUDA events."""
@@ -119,17 +166,18 @@ def gemm_roofline(B, mode, peaks, steps=20):
 def run(args, rank, world, peaks):
     import air_b200 as ab
     B = args.batch or 4096
+    if getattr(args, "global_batch", None):     # configs[3] as written: a fixed global batch sharded over the ranks
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world
     mode = args.gemm or os.environ.get("AIR_GEMM", "tf32")
     infer = args.workload == "infer"
     T = 5 if infer else 3
     if infer and not args.batch:
         B = 65536
     m, imgs, cnt, data = _model(B, mode, seed=rank, train=not infer, max_steps=T, cnn=getattr(args, "cnn", False))
-    if infer:
-        step = lambda: m.run()
-    else:
-        m.capture()
-        step = m.train_step
+    m.capture()   # one CUDA graph per step: noise + forward (+ backward + bucketed all-reduce + clip + Adam)
+    step = m.run if infer else m.train_step
     n0 = ab.launch_count()
     for _ in range(args.warmup):
         step()
@@ -153,8 +201,10 @@ def run(args, rank, world, peaks):
     # input pipeline: batch k+1 is staged on a copy stream while step k computes, and the loss of step k is
     # consumed one step later (async D2H into pinned memory), so PCIe overlaps the kernels.
     n_host = 4
-    host_batches = [(imgs.clone().pin_memory(), cnt.clone().pin_memory()) for _ in range(n_host)]
-    stage = [(torch.empty_like(imgs, device="cuda"), torch.empty_like(cnt, device="cuda")) for _ in range(2)]
+    imgs_u8 = torch.round(imgs * 255.0).to(torch.uint8)     # exact: the canvases are k * fl(1/255)
+    assert torch.equal(imgs_u8.float() * torch.tensor(1.0 / 255.0, dtype=torch.float32), imgs)
+    host_batches = [(imgs_u8.clone().pin_memory(), cnt.clone().pin_memory()) for _ in range(n_host)]
+    stage = [(torch.empty_like(imgs_u8, device="cuda"), torch.empty_like(cnt, device="cuda")) for _ in range(2)]
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     staged_ev = [torch.cuda.Event() for _ in range(2)]
@@ -181,7 +231,7 @@ def run(args, rank, world, peaks):
             if k + 1 < n:
                 prefetch(k + 1)
             main.wait_event(staged_ev[slot])
-            m.feed(stage[slot][0], stage[slot][1])             # device-to-device into the model's input buffers
+            m.feed(stage[slot][0], stage[slot][1])             # uint8 -> fp32 expansion into the model's input buffers
             consumed_ev[slot].record(main)
             step()
             loss_host[slot].copy_(result_of().reshape(1), non_blocking=True)
@@ -205,12 +255,9 @@ def run(args, rank, world, peaks):
     # kernels per step: count one eager step (graph replays do not pass through the launch counter)
     probe, _, _, _ = (m, None, None, None)
     c0 = ab.launch_count()
-    if infer:
-        m.run()
-    else:
-        g, m._graphs = m._graphs, None
-        m.train_step()
-        m._graphs = g
+    g, m._graphs = m._graphs, None
+    step()
+    m._graphs = g
     per_step = ab.launch_count() - c0
     torch.cuda.synchronize()
 
@@ -225,12 +272,14 @@ def run(args, rank, world, peaks):
                                 "AIRModel default inference (train=False), T=5"),
                    "cnn_frontend": bool(getattr(args, "cnn", False)),
                    "batch_per_gpu": B, "global_batch": B * world, "gemm_mode": mode, "parallelism": f"dp{world}",
-                   "noise": "drawn on device inside the timed step", "cuda_graph": not infer,
+                   "noise": "drawn on device inside the timed step", "cuda_graph": True,
                    "l2": f"per-step working set ~{B * 61e3 / 1e6:.0f} MB of activations + 16 MB weights > 126 MB L2"},
         "step_tflops_canonical": round(value * flops_img / 1e12, 2),
         "e2e": {"value": round(B * world / (e2e_ms * 1e-3), 1), "unit": "images/s",
-                "h2d_bytes_per_step": int(imgs_h.numel() * 4 + cnt_h.numel() * 4), "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": int(imgs_h.numel() * imgs_h.element_size() + cnt_h.numel() * 4), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms, 4), "last_result": last,
+                "input_format": "uint8 canvases: the data set's values are k * fl(1/255) like the reference's MNIST-derived "
+                                "canvases; AIRModel.feed expands them bit for bit on the device (air_expand_u8)",
                 "pipeline": "H2D of batch k+1 on a copy stream overlaps step k; loss of step k read back asynchronously"},
         "gpu_launches": int(per_step * args.steps),
         "kernels_per_step": int(per_step),
@@ -241,6 +290,32 @@ def run(args, rank, world, peaks):
         line["roofline"] = gemm_roofline(B, mode, peaks)
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(seconds=12.0)
+    if world > 1 and not infer:
+        line["dp_check"] = dp_check(m, rank, world, mode, T)
+        line["allreduce"] = {"buckets_floats": [b - a for a, b in zip(m._buckets[:-1], m._buckets[1:])],
+                             "note": "NCCL all-reduces captured inside the step's CUDA graph on forked branches, one per gradient "
+                                     "bucket in production order; only the last (the 17 KB arena of biases) is not behind a GEMM"}
+        if world in (2, 4) and not getattr(args, "global_batch", None) and not args.batch:
+            # configs[3] as written: global batch 32768 sharded over this many GPUs (at 8 GPUs that is the line itself)
+            del m
+            torch.cuda.empty_cache()
+            Bc = 32768 // world
+            m4, _, _, _ = _model(Bc, mode, seed=rank, train=True, max_steps=T)
+            m4.capture()
+            for _ in range(3):
+                m4.train_step()
+            barrier(world)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                m4.train_step()
+            e1.record()
+            barrier(world)
+            ms4 = max_over_ranks(e0.elapsed_time(e1), world) / 10
+            line["c4_global_batch_32768"] = {"batch_per_gpu": Bc, "ms_per_step": round(ms4, 4), "value": round(32768 / (ms4 * 1e-3), 1),
+                                             "unit": "images/s", "steps": 10}
+            del m4
+            m = None
     if world == 1 and not infer:
         # parity figures of the mode that was timed, and the FP32-grade modes beside it on the same workload
         del m

@@ -303,6 +303,12 @@ int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_
 int air_synth_canvases_ex(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int32_t *positions,
                           int32_t *boxes, int64_t B, int canvas_size, int max_digits, air_stream_t stream);
 
+/* uint8 canvases -> fp32 on the device: dst[i] = fl(float(src[i]) * fl(1/255)), the scaling of the MNIST loader behind
+ * multi_mnist.py (tensorflow's input_data: numpy.multiply(images.astype(float32), 1.0 / 255.0)).  The reference's
+ * default data set (digits pasted without overlap, no rescaling / rotation) only holds those 256 values, so its
+ * canvases can cross PCIe as bytes -- a quarter of the fp32 traffic -- and be expanded bit for bit next to the model. */
+int air_expand_u8(const uint8_t *src, float *dst, int64_t n, air_stream_t stream);
+
 /* ---- host-side input path: the reference's multi-MNIST TFRecord files -----------------------------------------
  * multi_mnist.py:186-212 writes tf.train.Example records (features height, width, digits: int64; indices, positions,
  * boxes, labels: int32 bytes; image: canvas^2 float32 bytes); training reads them with TFRecordReader +

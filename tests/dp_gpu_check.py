@@ -37,8 +37,7 @@ ok = True
 if rank == 0:
     # single-GPU reference on the full batch (no process group -> world 1)
     ref = ab.AIRModel(imgs.cuda(), cnt.cuda(), train=True, annealing_schedules=O.DEFAULT_ANNEALING, scope="ref",
-                      process_group=None, **hyper)
-    ref.world = 1
+                      process_group="local", **hyper)
     ref.store.load_named({k: v.cuda() for k, v in params.items()})
     ref.store.global_step = 2000
     ref.set_noise({k: v.cuda() for k, v in noise.items()})
@@ -53,7 +52,7 @@ flat = m.store.flat.clone()
 gathered = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 same = all(torch.equal(gathered[0], g) for g in gathered)
-# the CUDA-graph path (three graphs: the first gradient bucket's all-reduce overlaps the second graph)
+# the CUDA-graph path: ONE graph per step with the five bucketed NCCL all-reduces captured on forked branches
 m.capture()
 for _ in range(3):
     m.train_step()

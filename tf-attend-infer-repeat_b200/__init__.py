@@ -12,7 +12,7 @@ from .air.transformer import transformer, batch_transformer, writeback_canvas
 from .air.vae import vae
 from .air.air_model import AIRModel, reset_variable_scopes
 from .air.params import ParamStore
-from . import checkpoint, dp, ops, tfrecords
+from . import checkpoint, data, dp, ops, tfrecords
 from .demo.model_wrapper import ModelWrapper, evaluation_summaries
 from .demo.visualize import visualize_reconstructions, draw_colored_bounding_boxes
 from .air.concrete import (concrete_binary_sample, concrete_binary_pre_sigmoid_sample,

@@ -66,6 +66,7 @@ _SIGS = {
                                           ctypes.c_int, _c_f]),
     "air_synth_canvases_ex": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, _c_f, _c_f, _c_f, _c_f, ctypes.c_int64,
                                              ctypes.c_int, ctypes.c_int, _c_f]),
+    "air_expand_u8": (ctypes.c_int, [_c_f, _c_f, ctypes.c_int64, _c_f]),
     "air_tfrecord_index": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_void_p]),
     "air_shuffle_order": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]),

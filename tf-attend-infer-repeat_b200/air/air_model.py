@@ -113,9 +113,10 @@ class AIRModel:
                              vae_prior_mean, vae_prior_variance, vae_likelihood_std, z_pres_temperature,
                              stopping_threshold, 1 if train else 0)
 
-        # ---- data parallelism: one process per GPU, gradients all-reduced over NCCL
-        self.pg = process_group
-        self.world = dp.world_size(process_group)
+        # ---- data parallelism: one process per GPU, gradients all-reduced over NCCL.  process_group="local" builds a
+        #      single-GPU model inside a distributed job (e.g. a global-batch reference on rank 0).
+        self.pg = None if process_group == "local" else process_group
+        self.world = 1 if process_group == "local" else dp.world_size(process_group)
 
         # torch-owned split-K scratch for the weight-gradient GEMMs of the tensor-core modes, one per device, handed
         # to the library with every call (the library keeps no pointer and allocates nothing)
@@ -207,20 +208,24 @@ class AIRModel:
         self.vw = VAEWeights(p, g, len(self.vae_recognition_units), len(self.vae_generative_units))
         if self.train:
             # every bias gradient of the step = column sums of a time-batched dY buffer: one launch pair for all
-            pairs = vae_bias_items(self.vw, w["vae_d"]) + [(_flat2(w["dhh"]), g["heads/hidden_b"], False)]
-            pairs_rnn = [(w["dgates_sum"], g["rnn/bias"], False)]
-            self._colsum_items, self._colsum_items_rnn = ops.colsum_items(pairs), ops.colsum_items(pairs_rnn)
-            self._colsum_keep = (pairs, pairs_rnn)  # the ctypes arrays hold raw pointers: keep the views alive
+            pairs = vae_bias_items(self.vw, w["vae_d"]) + [(_flat2(w["dhh"]), g["heads/hidden_b"], False),
+                                                           (w["dgates_sum"], g["rnn/bias"], False)]
+            self._colsum_items = ops.colsum_items(pairs)
+            self._colsum_keep = pairs  # the ctypes array holds raw pointers: keep the views alive
             w["colsum_ws"] = torch.zeros(ops.colsum_multi_workspace(self._colsum_items), device=dev)
-            w["colsum_ws_rnn"] = torch.zeros(ops.colsum_multi_workspace(self._colsum_items_rnn), device=dev)
-            # gradient buckets for the data-parallel all-reduce: A = [cnn,] rnn (70 % of the bytes, produced first),
-            # B = heads + vae.  The flat buffer is laid out in that order.
-            self._bucket_split = self.store.offsets["heads/hidden_w"]
+            # gradient buckets of the data-parallel all-reduce, contiguous in the flat buffer and in production order
+            # (params.py): kernel image rows | kernel h rows + cnn | head hidden weights | vae weights | arena
+            self._buckets = self.store.bucket_bounds()
+            self._pending = []
 
     # ------------------------------------------------------------------------------------------
     def feed(self, input_images, target_num_digits=None):
-        """Refill the input buffers in place (the feed_dict of the reference)."""
-        self.input_images.copy_(input_images, non_blocking=True)
+        """Refill the input buffers in place (the feed_dict of the reference).  uint8 canvases (CUDA) are expanded on the
+        device to k * fl(1/255), the values the reference's MNIST-derived data set holds (air_expand_u8)."""
+        if input_images.dtype == torch.uint8:
+            ops.expand_u8(input_images.contiguous(), self.input_images)
+        else:
+            self.input_images.copy_(input_images, non_blocking=True)
         if target_num_digits is not None:
             self.target_num_digits.copy_(target_num_digits, non_blocking=True)
 
@@ -330,8 +335,7 @@ class AIRModel:
     # ------------------------------------------------------------------------------------------
     def _backward(self):
         self._backward_loop()
-        self._weight_grads_rnn()
-        self._weight_grads_rest()
+        self._weight_grads()
 
     def _backward_loop(self):
         w, hp, mode = self.w, self.hyper, self.gemm
@@ -377,31 +381,35 @@ class AIRModel:
                 self._debug[t] = {k: w[k][t].clone() for k in ("dwin", "dtheta", "dtheta_inv", "dz")}
                 self._debug[t]["dh"] = w["dh"].clone()
 
-    # ---- weight gradients, once per train step, over the time-batched buffers.  The LSTM kernel (and the CNN
-    #      front-end) come first: they are 70 % of the gradient bytes and the first bucket of the data-parallel
-    #      all-reduce, which then overlaps the remaining weight-gradient GEMMs (train_step).
-    def _weight_grads_rnn(self):
-        w, mode, T = self.w, self.gemm, self.max_steps
+    # ---- weight gradients, once per train step, over the time-batched buffers, in the order of the flat buffer; each
+    #      finished bucket is handed to the all-reduce at once (data parallel) and travels while the next GEMMs run.
+    def _weight_grads(self):
+        w, g, mode, T = self.w, self.store.g, self.gemm, self.max_steps
+        # the image rows of the LSTM kernel see the same input every step: one GEMM on the summed dgates (64 % of all
+        # gradient bytes: first out)
+        rnn_in = w["cnn_out"][2] if self.cnn else self.input_images
+        ops.gemm(rnn_in, w["dgates_sum"], self.gKx, tA=True, mode=mode)
+        self._reduce_bucket(0)
         if T > 1:   # K_h sees h_{t-1}: rows t = 1..T-1 (h_{-1} = 0 contributes nothing)
-            ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode, ws=self._gemm_ws)
+            ops.gemm(_flat2(w["h"][:T - 1]), _flat2(w["dgates"][1:]), self.gKh, tA=True, mode=mode)
         else:
             self.gKh.zero_()
-        # the image rows of the LSTM kernel see the same input every step: one GEMM on the summed dgates
-        rnn_in = w["cnn_out"][2] if self.cnn else self.input_images
-        ops.gemm(rnn_in, w["dgates_sum"], self.gKx, tA=True, mode=mode, ws=self._gemm_ws)
-        ops.colsum_multi(self._colsum_items_rnn, w["colsum_ws_rnn"])
         if self.cnn:
             self._cnn_backward()
-
-    def _weight_grads_rest(self):
-        w, g, mode, T = self.w, self.store.g, self.gemm, self.max_steps
+        self._reduce_bucket(1)
+        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], None, mode)
+        self._reduce_bucket(2)
+        allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
+        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, w["vae_d"], None, mode)
+        self._reduce_bucket(3)
+        # the arena: head outputs and every bias gradient (one column-sum launch pair), 17 KB -- the only message
+        # that is not hidden behind a GEMM
         nw = 7 * self.scale_hidden_units
         ops.reduce_rows(w["heads_ws"], T * self._heads_rows, nw + 7, nw, g["heads/out_w"])
         ops.reduce_rows(w["heads_ws"].view(-1)[nw:], T * self._heads_rows, nw + 7, 7, g["heads/out_b"])
-        allbuf = dict(enc=w["enc"], ml=w["ml"], zs=w["zs"], dec=w["dec"], recon=w["recon"])
-        vae_weight_grads(_flat2(w["win"]), self.vw, allbuf, w["vae_d"], None, mode, gemm_ws=self._gemm_ws)
-        dense_dw(_flat2(w["h"]), _flat2(w["dhh"]), g["heads/hidden_w"], g["heads/hidden_b"], None, mode, gemm_ws=self._gemm_ws)
         ops.colsum_multi(self._colsum_items, w["colsum_ws"])
+        self._reduce_bucket(4)
+        self._reduce_wait()
 
     def _apply_gradients(self):
         """air_model.py:673, 692: clip by global norm, Adam, global_step += 1."""
@@ -409,22 +417,20 @@ class AIRModel:
         ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, self.gradient_clipping_norm, 0.9, 0.999, 1e-8,
                       1.0, self.w["adam_ws"])
 
-    def _allreduce(self):
-        dp.allreduce_flat(self.store.grad, self.pg)  # SUM; the per-item loss weight already carries 1/world
+    def _reduce_bucket(self, i):
+        """SUM all-reduce of gradient bucket i on the communicator's stream, ordered after the kernels queued so far
+        (the per-item loss weight already carries 1/world).  Capturable: inside capture() the collective becomes a
+        node of the step's CUDA graph on a forked branch."""
+        if self.world > 1:
+            lo, hi = self._buckets[i], self._buckets[i + 1]
+            if hi > lo:
+                self._pending.append(dp.allreduce_async(self.store.grad[lo:hi], self.pg))
 
-    def _reduce_overlapped(self, first, second):
-        """first(); all-reduce(bucket A) on the communicator's stream while second() runs; all-reduce(bucket B);
-        the current stream then waits for both.  With one rank: just first(); second()."""
-        first()
-        if self.world == 1:
-            second()
-            return
-        grad, k = self.store.grad, self._bucket_split
-        wa = dp.allreduce_async(grad[:k], self.pg)
-        second()
-        wb = dp.allreduce_async(grad[k:], self.pg)
-        wa.wait()
-        wb.wait()
+    def _reduce_wait(self):
+        """The current stream (not the host) waits for every pending bucket."""
+        for work in self._pending:
+            work.wait()
+        self._pending = []
 
     # ------------------------------------------------------------------------------------------
     # public API
@@ -435,6 +441,9 @@ class AIRModel:
             self.set_noise(noise)
         if self.noise == "injected":
             self.noise = None        # one-shot: consumed by this evaluation (the buffers keep it for the backward)
+        elif self._graphs is not None and not self.train:
+            self._graphs.replay()    # captured inference step: fresh noise + forward in one graph replay
+            return self
         else:
             self._draw_noise()
         self._forward()
@@ -448,7 +457,7 @@ class AIRModel:
         if not self.train:
             raise C.AirError("model was built with train=False")
         self.run(noise)
-        self._reduce_overlapped(lambda: (self._backward_loop(), self._weight_grads_rnn()), self._weight_grads_rest)
+        self._backward()
         return self.loss, self.store.named_grads()
 
     def train_step(self, noise=None):
@@ -456,42 +465,36 @@ class AIRModel:
         if not self.train:
             raise C.AirError("model was built with train=False")
         if self._graphs is not None and noise is None:
-            g_a, g_b, g_opt = self._graphs
-            self._reduce_overlapped(g_a.replay, g_b.replay if g_b is not None else (lambda: None))
-            g_opt.replay()
+            self._graphs.replay()
             return self
         self.loss_and_grads(noise)
         self._apply_gradients()
         return self
 
     def capture(self, warmup=3):
-        """Capture noise + forward + backward, and clip + Adam, as CUDA graphs; subsequent train_step() calls replay
-        them.  With more than one rank the backward is split after the LSTM-kernel gradients so that the (eager)
-        NCCL all-reduce of that first bucket overlaps the remaining weight-gradient GEMMs."""
-        if not self.train:
-            raise C.AirError("capture() records a training step: the model was built with train=False")
+        """Capture one whole optimisation step -- noise, forward, backward, the bucketed NCCL all-reduces (data
+        parallel: forked branches of the graph that overlap the remaining weight-gradient GEMMs), clip + Adam -- as
+        ONE CUDA graph; subsequent train_step() calls are a single replay with no host work in between.  A model built
+        with train=False captures its inference step (noise + forward); run() then replays it."""
         if self.noise == "injected":
             raise C.AirError("capture() would freeze the injected noise into the graph: run the pending evaluation "
                              "first (injection is one-shot) or call capture() before set_noise()")
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._draw_noise(); self._forward(); self._backward()
+            for _ in range(warmup):   # (also creates the NCCL communicator before anything is captured)
+                self._draw_noise(); self._forward()
+                if self.train:
+                    self._backward()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g_a, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        g_b = torch.cuda.CUDAGraph() if self.world > 1 else None
-        with torch.cuda.graph(g_a):
-            self._draw_noise(); self._forward(); self._backward_loop(); self._weight_grads_rnn()
-            if g_b is None:
-                self._weight_grads_rest()
-        if g_b is not None:  # data parallel: the first gradient bucket is all-reduced while this graph runs
-            with torch.cuda.graph(g_b, pool=g_a.pool()):
-                self._weight_grads_rest()
-        with torch.cuda.graph(g_opt, pool=g_a.pool()):
-            self._apply_gradients()
-        self._graphs = (g_a, g_b, g_opt)
+        g = torch.cuda.CUDAGraph()
+        # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
+        with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
+            self._draw_noise(); self._forward()
+            if self.train:
+                self._backward(); self._apply_gradients()
+        self._graphs = g
         self._publish()
         return self
 

@@ -92,11 +92,22 @@ class ParamStore:
         fused["vae/gen_mean/weights"] = (prev, win)
         fused["vae/gen_mean/biases"] = (win,)
         self.fused_shapes = fused
+        # Order in the flat buffer = the order in which the backward PRODUCES the gradients, so that the data-parallel
+        # all-reduce can run as contiguous buckets that leave while the remaining weight-gradient GEMMs still run
+        # (AIRModel._reduce_bucket): LSTM kernel (image rows first, 64 % of all bytes) | CNN front-end | head hidden
+        # weights | VAE weights, decoder first (the order of vae_weight_grads) | an arena with everything that is
+        # produced last by the batched reductions -- head outputs and ALL biases, 6 K floats: the only exposed message.
+        vae_w = [f"vae/generative_{i + 1}/weights" for i in range(len(gen_units))] + ["vae/gen_mean/weights"] + \
+                [f"vae/recognition_{i + 1}/weights" for i in range(len(rec_units))] + ["vae/rec_ml/weights"]
+        order = ["rnn/kernel"] + [k for k in fused if k.startswith("cnn/")] + ["heads/hidden_w"] + vae_w
+        arena = [k for k in fused if k not in order]
+        self.bucket_names = dict(rnn=["rnn/kernel"], cnn=[k for k in fused if k.startswith("cnn/")], heads=["heads/hidden_w"],
+                                 vae=vae_w, arena=arena)
         self.offsets = OrderedDict()
         off = 0
-        for k, shp in fused.items():
+        for k in order + arena:
             self.offsets[k] = off
-            off += (int(math.prod(shp)) + 3) & ~3  # 16-byte aligned tensors
+            off += (int(math.prod(fused[k])) + 3) & ~3  # 16-byte aligned tensors
         self.n = off
         self.n_params = sum(int(math.prod(s)) for s in fused.values())
         self.flat = torch.zeros(self.n, device=self.device, dtype=torch.float32)
@@ -112,8 +123,17 @@ class ParamStore:
 
     # ---- views -------------------------------------------------------------------------
     def _views(self, flat):
-        return OrderedDict((k, flat[o:o + int(math.prod(self.fused_shapes[k]))].view(self.fused_shapes[k]))
-                           for k, o in self.offsets.items())
+        return OrderedDict((k, flat[self.offsets[k]:self.offsets[k] + int(math.prod(shp))].view(shp))
+                           for k, shp in self.fused_shapes.items())
+
+    def bucket_bounds(self):
+        """Flat-buffer boundaries of the gradient buckets, in production order:
+        [0, kernel image rows | kernel h rows + cnn | head hidden weights | vae weights | arena, n]."""
+        in_rows = self.dims["in_dim"] * 4 * self.dims["R"]
+        b = [0, in_rows, self.offsets["heads/hidden_w"], self.offsets[self.bucket_names["vae"][0]],
+             self.offsets[self.bucket_names["arena"][0]], self.n]
+        assert b == sorted(b) and in_rows % 4 == 0
+        return b
 
     def _named(self, v):
         d, HU, L = OrderedDict(), self.dims["HU"], self.dims["L"]

@@ -786,6 +786,26 @@ __global__ void __launch_bounds__(256)
   if (tid == 0) counts[b] = count;
 }
 
+// uint8 canvases -> fp32, bit for bit what the MNIST loader behind multi_mnist.py produces: tensorflow's
+// input_data.read_data_sets scales pixels with numpy.multiply(images.astype(float32), 1.0 / 255.0), i.e. in fp32
+// fl(float(k) * fl(1/255)).  16 pixels per thread: one 128-bit load, four 128-bit stores.
+__global__ void __launch_bounds__(256) expand_u8_k(const uint8_t *__restrict__ src, float *__restrict__ dst, int64_t n) {
+  pdl_sync();
+  const float inv = 1.0f / 255.0f;  // 0x3b808081, the fp32 constant numpy uses
+  const int64_t nvec = n >> 4;
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < nvec; v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src) + v);
+    const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+    float4 *o = reinterpret_cast<float4 *>(dst) + 4 * v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = make_float4(__fmul_rn(static_cast<float>(wds[j] & 0xffu), inv), __fmul_rn(static_cast<float>((wds[j] >> 8) & 0xffu), inv),
+                         __fmul_rn(static_cast<float>((wds[j] >> 16) & 0xffu), inv), __fmul_rn(static_cast<float>(wds[j] >> 24), inv));
+  }
+  if (blockIdx.x == 0)  // tail
+    for (int64_t i = (nvec << 4) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __fmul_rn(static_cast<float>(src[i]), inv);
+}
+
 }  // namespace air
 
 // ---- C ABI --------------------------------------------------------------------------------
@@ -1000,6 +1020,16 @@ extern "C" int air_synth_canvases_ex(uint64_t seed, int64_t first_index, float *
 extern "C" int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int64_t B,
                                   int canvas_size, int max_digits, air_stream_t stream) {
   return air_synth_canvases_ex(seed, first_index, images, counts, nullptr, nullptr, B, canvas_size, max_digits, stream);
+}
+
+extern "C" int air_expand_u8(const uint8_t *src, float *dst, int64_t n, air_stream_t stream) {
+  AIR_REQUIRE(n >= 0, AIR_ERR_BAD_SHAPE, "expand_u8: n < 0");
+  if (n == 0) return AIR_OK;
+  AIR_REQUIRE(src && dst, AIR_ERR_NULL, "expand_u8: null pointer");
+  AIR_REQUIRE(aligned16(src) && aligned16(dst), AIR_ERR_BAD_ALIGN, "expand_u8: 16-byte aligned buffers required");
+  AIR_LAUNCH(expand_u8_k, grid_for(std::max<int64_t>(n >> 4, 1), 256), 256, 0, ST(stream), src, dst, n);
+  count_launch();
+  return check_launch("expand_u8");
 }
 
 extern "C" int air_reduce_rows(const float *partials, int R, int stride, int n, float *out, int accumulate, air_stream_t stream) {

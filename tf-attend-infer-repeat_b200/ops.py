@@ -231,6 +231,14 @@ def conv5x5_bwd(x, w, out, argmax, dout, din, dw, db, accumulate, workspace, H, 
           "air_conv5x5_bwd")
 
 
+def expand_u8(src, dst):
+    """dst (float32) = float(src) * fl(1/255) for a uint8 CUDA tensor of the same number of elements (air_expand_u8)."""
+    if src.dtype != torch.uint8 or dst.dtype != torch.float32 or src.numel() != dst.numel():
+        raise C.AirError("expand_u8: uint8 source and float32 destination of equal size required")
+    check(lib().air_expand_u8(ptr(src), ptr(dst), src.numel(), stream()), "air_expand_u8")
+    return dst
+
+
 def synth_canvases(images, counts, seed=0, first_index=0, canvas_size=50, max_digits=2, positions=None, boxes=None):
     """Fill images [B, canvas_size**2] / counts [B] int32 with device-generated multi-digit canvases; optionally the
     (x, y) positions and (w, h) boxes of the placed digits, int32 [B, max_digits, 2] each (multi_mnist.py:165-166)."""
