@@ -136,6 +136,17 @@ def barrier(world):
 # ------------------------------------------------------------------------------------------
 ST_BYTES = {"crop_fwd": 13160, "crop_bwd": 13184, "writeback_canvas_fwd": 23168, "writeback_canvas_bwd": 16332,
             "writeback_canvas_bwd_full_dtheta": 16332}
+# What a STOPPED image (stopping_sum >= threshold, 30 % of the microbench batch) moves in the fused kernels: the forward
+# still copies its canvas row (10,000 in + 10,000 out + the two scalars it tests); the backward only writes zeros
+# (3,136 dwindow + 24 dtheta + 4 dz) and reads the 4-byte stopping sum -- no window, no dCanvas row.
+ST_BYTES_STOPPED = {"writeback_canvas_fwd": 20008, "writeback_canvas_bwd": 3168, "writeback_canvas_bwd_full_dtheta": 3168}
+
+
+def st_moved_bytes(name, B, live_frac):
+    """bytes one launch really has to move given the batch's live fraction (== SURVEY's figure for the unmasked kernels)"""
+    dead = ST_BYTES_STOPPED.get(name)
+    per = ST_BYTES[name] if dead is None else live_frac * ST_BYTES[name] + (1.0 - live_frac) * dead
+    return B * per
 
 
 def st_inputs(B, dev, seed=1):
@@ -222,6 +233,7 @@ def run_st(args, rank, world, peaks):
     dev = torch.device("cuda")
     d = st_inputs(B, dev)
     ks = st_kernels(d, B)
+    live_frac = float((d["stop"] < 0.99).float().mean().item())
     res = {}
     n0 = ab.launch_count()
     barrier(world)
@@ -231,7 +243,9 @@ def run_st(args, rank, world, peaks):
         for name, fn in ks.items():
             ms = max_over_ranks(time_launches(fn, args.steps, args.warmup), world)
             gbs = B * ST_BYTES[name] / (ms * 1e-3) / 1e9
+            moved = st_moved_bytes(name, B, live_frac) / (ms * 1e-3) / 1e9
             res[name] = {"ms": round(ms, 5), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+                         "GBps_moved": round(moved, 1), "frac_of_hbm_peak_moved": round(moved / peaks["hbm_gbs"], 4),
                          "bytes_per_image": ST_BYTES[name],
                          "ncu_dram_bytes": (round(ST_NCU_TRAFFIC_B65536[name] * B / 65536)
                                             if name in ST_NCU_TRAFFIC_B65536 else None)}
@@ -279,15 +293,19 @@ def st_summary(peaks, B=65536, steps=20, warmup=5):
     import torch
     d = st_inputs(B, torch.device("cuda"))
     ks = st_kernels(d, B)
+    live_frac = float((d["stop"] < 0.99).float().mean().item())
     out = {}
     for name, fn in ks.items():
         ms = time_launches(fn, steps, warmup)
         gbs = B * ST_BYTES[name] / (ms * 1e-3) / 1e9
-        out[name] = {"ms": round(ms, 5), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)}
+        moved = st_moved_bytes(name, B, live_frac) / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 5), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+                     "GBps_moved": round(moved, 1), "frac_of_hbm_peak_moved": round(moved / peaks["hbm_gbs"], 4)}
     del d, ks
     torch.cuda.empty_cache()
-    return {"batch": B, "steps": steps, "unit": "GB/s of algorithmic bytes (SURVEY 8d)", "hbm_peak_GBps": peaks["hbm_gbs"],
-            "kernels": out}
+    return {"batch": B, "steps": steps, "unit": "GB/s of algorithmic bytes (SURVEY 8d); *_moved: bytes the launch really has to "
+            "move, stopped images (stop >= thr) counted at what they touch", "live_fraction": round(live_frac, 4),
+            "hbm_peak_GBps": peaks["hbm_gbs"], "kernels": out}
 
 
 def cpu_baseline_st(B=4096):
@@ -308,6 +326,31 @@ def cpu_baseline_st(B=4096):
     dt = (time.time() - t0) / reps
     return {"value": round(B * ST_BYTES["crop_fwd"] / dt / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "port",
             "sample": f"oracle/st_oracle.c crop fwd, batch {B}, {reps} reps (~5 s)"}
+
+
+def shutdown_distributed(timeout_s=20.0):
+    """Leave a multi-rank run cleanly.  The step's CUDA graph holds captured NCCL kernels, and ncclCommDestroy waits for
+    every graph that references the communicator: drop the graphs first (gc), then destroy the process group -- on a
+    helper thread with a deadline, so that a teardown that still blocks cannot hang the job (the result line is already
+    out); the process then exits through os._exit."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier()
+    try:
+        import air_b200 as ab
+        ab.reset_variable_scopes()
+    except Exception:
+        pass
+    gc.collect()
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------
@@ -374,9 +417,7 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+        shutdown_distributed()
     return 0
 
 

@@ -316,6 +316,8 @@ def run(args, rank, world, peaks):
                                              "unit": "images/s", "steps": 10}
             del m4
             m = None
+        if m is not None:
+            m._graphs = None   # (graphs with captured NCCL kernels must be gone before the process group is destroyed)
     if world == 1 and not infer:
         # parity figures of the mode that was timed, and the FP32-grade modes beside it on the same workload
         del m

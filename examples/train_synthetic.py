@@ -2,11 +2,10 @@
 reference README's "98 % after ~25k iterations" claim, there on multi-MNIST) -- the GPU counterpart of
 oracle/train_convergence.py, with the reference's training configuration (training.py:100-122, batch 64).
 
-    python examples/train_synthetic.py --iters 25000 --log profiles/rN_gpu_convergence.log
+    python examples/train_synthetic.py --iters 25000 --gemm tf32x3 --log profiles/r2_gpu_convergence_tf32x3.log
 
-NOT YET RUN ON A GPU: written when round 1's GPU minutes were spent; everything it calls (device_canvases, feed,
-capture, train_step, run, accuracy, reuse=True) is covered by tests/test_gpu_model.py, but the first run of this
-script itself belongs to the next round.
+Logs of round 2's runs (3xTF32 and plain TF32 GEMM modes) are in profiles/r2_gpu_convergence_*.log, next to the CPU
+oracle's profiles/r1_oracle_convergence.log.
 """
 import argparse
 import os
@@ -27,7 +26,7 @@ def main():
     ap.add_argument("--train-images", type=int, default=60000)
     ap.add_argument("--val-images", type=int, default=4096)
     ap.add_argument("--every", type=int, default=500)
-    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--log", default=None)
     a = ap.parse_args()
     data = import_module("tf-attend-infer-repeat_b200.data")

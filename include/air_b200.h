@@ -152,6 +152,10 @@ int air_concrete_step_bwd(const float *log_odds, const float *y, const float *z,
 #define AIR_EPI_MUL_DRELU 3     /* out = v * (aux > 0)            (ReLU backward, aux = ReLU output) */
 #define AIR_EPI_MUL_DSOFTPLUS 4 /* out = v * (1 - exp(-aux))      (softplus backward, aux = softplus output) */
 #define AIR_EPI_SIGMOID_NOISE 5 /* out = sigmoid(v + aux * epi_param): vae.py:36-41 (aux = N(0,1) noise, epi_param = likelihood std) */
+#define AIR_EPI_SIGMOID_RNG 6   /* the same with the noise GENERATED in the epilogue: aux points at the device RNG state
+                                 * (air_rng_state_t, cast to const float *); element (m, n) gets the N(0,1) sample
+                                 * m * N + n of stream AIR_RNG_LIKE for the state's current step counter.  No noise
+                                 * tensor is written or read (38 MB per train step at B = 4096). */
 #define AIR_GEMM_FP32_EXACT 0
 #define AIR_GEMM_TF32 1
 #define AIR_GEMM_TF32X3 2
@@ -171,6 +175,30 @@ int air_gemm_ex(const float *A, const float *B, float *C, const float *Cinit, co
 int air_gemm_ws(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
                 int64_t M, int N, int K, int lda, int ldb, int ldc, int transA, int transB, int epilogue,
                 float epi_param, int mode, float *workspace, int64_t workspace_floats, air_stream_t stream);
+
+/* ---- sampling noise generated on the device, where it is consumed -------------------------------------------------
+ * The reference samples with tf.random_normal / tf.random_uniform inside the graph (air_model.py:123-128, vae.py:23, 37,
+ * concrete.py:23).  Every compute entry point takes its noise as an input (parity runs inject it); for production
+ * steps the noise is a pure function of (seed, step counter, stream, element index): Philox4x32-10 + a Box-Muller
+ * transform built from correctly rounded fp32 operations only, restated bit for bit in oracle/rng_oracle.py.
+ * State: 4 x uint64 on the DEVICE, caller-owned: [0] seed, [1] step counter, [2] scratch (zero-initialised), [3] unused.
+ *
+ * air_noise_fill: advances the step counter by one and fills the step's small noise tensors from the new counter:
+ *   scale [T*B] and shift [T*B*2] and vae_latent [T*B*L] ~ N(0,1), concrete_u [T*B] ~ U[0,1) (each nullable).  The big
+ *   one -- the VAE likelihood noise [T*B, window^2] -- is never materialised: AIR_EPI_SIGMOID_RNG generates it in the GEMM
+ *   epilogue from the same state.  One launch; graph-capturable (the counter lives on the device).
+ * air_rng_normals: out[i] = N(0,1) sample i of `stream` at the state's CURRENT counter (no advance): test / inspection
+ *   helper, e.g. to reproduce the samples an AIR_EPI_SIGMOID_RNG epilogue used. */
+typedef struct air_rng_state { uint64_t seed, counter, scratch, unused; } air_rng_state_t;
+#define AIR_RNG_SCALE 1
+#define AIR_RNG_SHIFT 2
+#define AIR_RNG_LATENT 3
+#define AIR_RNG_CONCRETE 4
+#define AIR_RNG_LIKE 5
+int air_noise_fill(air_rng_state_t *state, float *scale, float *shift, float *vae_latent, float *concrete_u, int64_t TB,
+                   int L, air_stream_t stream);
+int air_rng_normals(const air_rng_state_t *state, int rng_stream, float *out, int64_t n, air_stream_t stream);
+int air_rng_uniforms(const air_rng_state_t *state, int rng_stream, float *out, int64_t n, air_stream_t stream);
 
 /* ---- fused model-specific elementwise kernels (air/air_model.py loop body) ----------
  * Hyper-parameters that are plain Python floats in the reference constructor
@@ -302,6 +330,11 @@ int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_
                        int max_digits, air_stream_t stream);
 int air_synth_canvases_ex(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int32_t *positions,
                           int32_t *boxes, int64_t B, int canvas_size, int max_digits, air_stream_t stream);
+
+/* Zero up to 8 device buffers (16-byte aligned, sizes multiples of 16 bytes) with ONE launch: the accumulators a step
+ * starts from (stopping sums, running loss, digit counts of air_model.py:550-553; the summed gate gradients).  `buffers`
+ * and `nbytes` are HOST arrays. */
+int air_zero_buffers(void *const *buffers, const int64_t *nbytes, int n, air_stream_t stream);
 
 /* uint8 canvases -> fp32 on the device: dst[i] = fl(float(src[i]) * fl(1/255)), the scaling of the MNIST loader behind
  * multi_mnist.py (tensorflow's input_data: numpy.multiply(images.astype(float32), 1.0 / 255.0)).  The reference's

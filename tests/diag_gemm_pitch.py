@@ -2,7 +2,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import air_b200 as ab
 from air_b200 import ops
-ws = torch.empty(16 << 20, device="cuda"); 
+ws = torch.zeros(16 << 20, device="cuda"); 
 def t(run):
     for _ in range(3): run()
     torch.cuda.synchronize()

@@ -11,7 +11,7 @@ from air_b200 import ops  # noqa: E402
 
 K = ab._cabi
 mode = K.GEMM_MODES[os.environ.get("MODE", "tf32")]
-ws = torch.empty(16 << 20, device="cuda")
+ws = torch.zeros(16 << 20, device="cuda")
 
 B, TB = 4096, 3 * 4096
 shapes = [  # name, M, N, K, tA, tB, cinit, bias, epi(aux)

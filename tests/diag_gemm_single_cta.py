@@ -7,7 +7,7 @@ def child():
     import torch
     import air_b200 as ab
     from air_b200 import ops
-    ws = torch.empty(16 << 20, device="cuda"); 
+    ws = torch.zeros(16 << 20, device="cuda"); 
     for (M, N, K) in [(128, 128, 8192), (128, 64, 8192), (128, 128, 32768), (256, 128, 8192), (128 * 148, 128, 8192), (128 * 148, 128, 2048)]:
         A = torch.randn(M, K, device="cuda"); Bm = torch.randn(K, N, device="cuda"); out = torch.empty(M, N, device="cuda")
         run = lambda: ops.gemm(A, Bm, out, mode=1)

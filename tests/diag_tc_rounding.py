@@ -61,7 +61,7 @@ def part2():
 
 def part3():
     rng = np.random.RandomState(1)
-    ws = torch.empty(16 << 20, device="cuda")
+    ws = torch.zeros(16 << 20, device="cuda")
     print("AIR_TC_CHAINS =", os.environ.get("AIR_TC_CHAINS", "(default)"))
     for (M, N, Kd, tA, what) in ((4096, 1024, 2500, False, "xK fwd"), (1024, 512, 784, False, "enc1"), (784, 512, 12288, True, "dW long K"),
                                  (2500, 1024, 4096, True, "dKx")):

@@ -67,5 +67,16 @@ if rank == 0:
     ok &= same and same_graph
     print("DP CHECK", "OK" if ok else "FAILED")
 dist.barrier()
-dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+# the step's CUDA graph holds captured NCCL kernels; ncclCommDestroy waits for such graphs: drop them first, and do
+# not let a blocking teardown hang the job
+import gc      # noqa: E402
+import threading  # noqa: E402
+m._graphs = None
+del m
+gc.collect()
+torch.cuda.synchronize()
+t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+t.start()
+t.join(20.0)
+sys.stdout.flush()
+os._exit(0 if ok else 1)

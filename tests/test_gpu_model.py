@@ -218,17 +218,78 @@ def test_inference_config_five_steps(gemm_mode):
     assert relnorm(m.rec_windows, out["rec_windows"]) < 1e-5
 
 
-def test_constructor_rejects_out_of_scope_options():
+def test_constructor_surface_and_variable_scopes():
     x, t = torch.zeros(2, 2500, device="cuda"), torch.zeros(2, dtype=torch.int32, device="cuda")
     ab.reset_variable_scopes()
     m = ab.AIRModel(x, t)                                   # the reference's literal defaults: cnn=True, 8 filters
     assert m.cnn and m.Kx.shape == (12 * 12 * 8, 1024)
     with pytest.raises(NotImplementedError):
-        ab.AIRModel(x, t, cnn_filters=16)                   # conv kernels are built for the reference's 8 filters
-    with pytest.raises(NotImplementedError):
-        ab.AIRModel(x, t, cnn=False, scale_hidden_units=32)  # the fused heads kernel needs equal hidden sizes
+        ab.AIRModel(x, t, cnn_filters=16, scope="f16")      # conv kernels are built for the reference's 8 filters
     with pytest.raises(ab.AirError):
-        ab.AIRModel(x.cpu(), t.cpu(), cnn=False)
+        ab.AIRModel(x.cpu(), t.cpu(), cnn=False, scope="cpu")
+    # tf.variable_scope semantics (air_model.py:68): an existing scope needs reuse=True, and reuse checks the shapes
+    with pytest.raises(ValueError, match="already exists"):
+        ab.AIRModel(x, t)
+    with pytest.raises(ValueError, match="other shapes"):
+        ab.AIRModel(x, t, cnn=False, reuse=True)
+    with pytest.raises(ValueError, match="does not exist"):
+        ab.AIRModel(x, t, reuse=True, scope="nope")
+    assert ab.AIRModel(x, t, reuse=True).store is m.store
+    with pytest.raises(ValueError, match="cannot be annealed"):
+        ab.AIRModel(x, t, scope="s2", annealing_schedules={"max_steps": {"init": 3, "factor": 0.5, "iters": 10}})
+
+
+@pytest.mark.parametrize("gemm_mode", EXACT_MODES)
+def test_train_parity_unequal_head_sizes(gemm_mode):
+    """scale / shift / z_pres heads of 48 / 64 / 16 hidden units (air_model.py:288-316, 372-376 take them separately):
+    the fused head blocks are zero-padded to the widest, which leaves the arithmetic of the real units unchanged; padded
+    weights receive zero gradients and stay zero through Adam."""
+    kw = dict(scale_hidden_units=48, shift_hidden_units=64, z_pres_hidden_units=16)
+    imgs, cnt, _, noise = covered_fixture(16, seed=6)
+    params = _covered_params(**kw)
+    orc, m = make_pair(imgs, cnt, params, train=True, gemm_mode=gemm_mode, **kw)
+    assert m.store.named_views()["scale/mean/hidden/weights"].shape == (256, 48)
+    assert m.store.named_views()["z_pres/log_odds/output/weights"].shape == (16, 1)
+    out, grads = orc.loss_and_grads(imgs, cnt, noise)
+    m.loss_and_grads(cuda_noise(noise))
+    assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"])
+    assert abs(m.loss.item() - out["loss"].item()) / abs(out["loss"].item()) < 1e-5
+    for k, g in m.store.named_grads().items():
+        assert relnorm(g, grads[k]) < 1e-4, (k, relnorm(g, grads[k]))
+    pad_w = m.store.p["heads/hidden_w"][:, 4 * 64 + 16:]                  # padding of the z_pres block
+    m._apply_gradients()
+    assert not pad_w.any() and not m.store.g["heads/hidden_w"][:, 48:64].any() and not m.store.g["heads/out_w"][:2, 48:].any()
+
+
+def test_host_annealed_hyper_parameters():
+    """air_model.py:76-82 anneals ANY attribute.  The ones that are kernel launch arguments are annealed on the host:
+    z_pres_temperature and vae_likelihood_std follow exponential_decay(global_step) step by step and the model equals
+    an oracle built with that step's values; capture() refuses to freeze them."""
+    from importlib import import_module
+    annealed_value = import_module("tf-attend-infer-repeat_b200.air.air_model").annealed_value
+    sched = {"z_pres_temperature": {"init": 2.0, "factor": 0.5, "iters": 1000, "min": 0.6},
+             "vae_likelihood_std": {"init": 0.5, "factor": 0.1, "iters": 4000, "staircase": True}}
+    imgs, cnt, params, noise = covered_fixture(8, seed=7)
+    ab.reset_variable_scopes()
+    m = ab.AIRModel(imgs.cuda(), cnt.cuda(), train=True, annealing_schedules=dict(O.DEFAULT_ANNEALING, **sched),
+                    **O.DEFAULT_HYPER)
+    m.store.load_named({k: v.cuda() for k, v in params.items()})
+    for step in (0, 1500, 4100):
+        m.store.global_step = step
+        want = {k: annealed_value(v, step) for k, v in sched.items()}
+        assert want["z_pres_temperature"] == pytest.approx(max(2.0 * 0.5 ** (step / 1000), 0.6), rel=1e-6)
+        assert want["vae_likelihood_std"] == pytest.approx(0.5 * 0.1 ** (step // 4000), rel=1e-6)
+        orc = O.AIROracle(params={k: v.clone() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING, train=True,
+                          **want)
+        orc.global_step = step
+        out = orc.forward(imgs, cnt, noise)
+        m.run(cuda_noise(noise))
+        assert m.z_pres_temperature == want["z_pres_temperature"] and m.vae_likelihood_std == want["vae_likelihood_std"]
+        assert abs(m.loss.item() - out["loss"].item()) <= 1e-5 * abs(out["loss"].item())
+        assert relnorm(m.rec_windows, out["rec_windows"]) < 1e-5 and relnorm(m.z_pres_kls, out["z_pres_kls"]) < 1e-5
+    m.train_step()                                               # eager steps work; graphs would freeze the values
+    with pytest.raises(ab.AirError, match="host-annealed"):
+        m.capture()
 
 
 def test_tf32_mode_close_to_oracle_and_trains():

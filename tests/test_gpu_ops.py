@@ -287,7 +287,7 @@ _WS = {}
 def _gemm_ws():
     """caller-owned split-K scratch (air_gemm_ws): the library allocates nothing itself"""
     if "ws" not in _WS:
-        _WS["ws"] = torch.empty(16 << 20, device=DEV)
+        _WS["ws"] = torch.zeros(16 << 20, device=DEV)   # zero once: its tail holds the split-K tickets
     return _WS["ws"]
 
 
@@ -404,8 +404,9 @@ def test_gemm_tf32_rejects_unaligned_leading_dimension(mode):
 
 
 def test_gemm_split_k_needs_a_caller_workspace_and_is_deterministic():
-    """without a workspace the long-K weight-gradient shape runs unsplit; with one it splits; both are deterministic; a
-    workspace too small for any split silently means 'unsplit' (never an allocation).  The split result is the more
+    """without a workspace the long-K weight-gradient shape runs unsplit; with one it splits (a second pass sums the
+    partials in split order); both are deterministic; a workspace too small for any split silently means 'unsplit'
+    (never an allocation).  The split result is the more
     accurate one: the tensor core's accumulate step rounds toward zero, so an unsplit K = 12288 chain (3 x 128
     k-blocks) carries ~1e-5 of bias, the 32 short chains of the split run ~1e-6 (include/air_b200.h, AIR_GEMM_TF32X3)."""
     rng = np.random.RandomState(11)
@@ -416,8 +417,58 @@ def test_gemm_split_k_needs_a_caller_workspace_and_is_deterministic():
         n0 = ab.launch_count()
         ops.gemm(A, Bm, out, tA=True, mode=K.GEMM_MODES["tf32x3"], ws=ws)
         outs.append((out, ab.launch_count() - n0))
-    assert outs[0][1] == 1 and outs[1][1] == 2 and outs[3][1] == 1
-    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[0][0], outs[3][0])
+    assert [n for _, n in outs] == [1, 2, 2, 1]
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[0][0], outs[3][0]) and not torch.equal(outs[0][0], outs[1][0])
     want = A.double().t() @ Bm.double()
     e_unsplit, e_split = relnorm(outs[0][0], want), relnorm(outs[1][0], want)
     assert e_split < 2e-6 and e_unsplit < 2e-5 and e_split < e_unsplit, (e_split, e_unsplit)
+
+
+# ---------------------------------------------------------------------------------------------
+# counter-based noise generated in the kernels (csrc/rng.cuh) vs its host restatement (oracle/rng_oracle.py)
+# ---------------------------------------------------------------------------------------------
+def test_device_noise_generator_equals_host_restatement_bit_for_bit():
+    from oracle import rng_oracle as R
+    seed, L, TB = 0x1234567890ABCDEF & 0x7FFFFFFFFFFFFFFF, 50, 3 * 37
+    st = ops.rng_state(seed, DEV, counter=41)
+    # samples of a stream at the current counter, odd lengths included
+    for stream, n in ((K.RNG_SHIFT, 4099), (K.RNG_LATENT, 777), (K.RNG_SCALE, 5)):
+        assert np.array_equal(ops.rng_normals(st, stream, n).cpu().numpy(), R.normals(seed, 41, stream, n))
+    # the likelihood stream (generated inside the gen_mean GEMM epilogue) uses the SFU form of the transform: same
+    # Philox words, samples equal to the host formula to ~1e-5 (hardware lg2 / rsqrt / sin / cos approximations)
+    like = ops.rng_normals(st, K.RNG_LIKE, 100_003).cpu().numpy()
+    assert np.abs(like - R.normals(seed, 41, K.RNG_LIKE, 100_003)).max() < 3e-5
+    assert np.array_equal(ops.rng_uniforms(st, K.RNG_CONCRETE, 1001).cpu().numpy(), R.uniforms(seed, 41, K.RNG_CONCRETE, 1001))
+    # one fill = one step: the counter advances first, then every tensor is that counter's stream
+    sc, sh, la, cu_ = (torch.empty(TB, device=DEV), torch.empty(TB, 2, device=DEV), torch.empty(TB, L, device=DEV),
+                       torch.empty(TB, device=DEV))
+    for step in (42, 43):
+        ops.noise_fill(st, sc, sh, la, cu_, TB, L)
+        assert st.cpu().tolist() == [seed, step, 0, 0]
+        assert np.array_equal(sc.cpu().numpy(), R.normals(seed, step, K.RNG_SCALE, TB))
+        assert np.array_equal(sh.cpu().numpy().ravel(), R.normals(seed, step, K.RNG_SHIFT, 2 * TB))
+        assert np.array_equal(la.cpu().numpy().ravel(), R.normals(seed, step, K.RNG_LATENT, TB * L))
+        assert np.array_equal(cu_.cpu().numpy(), R.uniforms(seed, step, K.RNG_CONCRETE, TB))
+    # moments of a large draw (the transform is an exact Box-Muller up to fp32 rounding)
+    z = ops.rng_normals(st, K.RNG_LIKE, 4_000_000).double()
+    assert abs(z.mean()) < 2e-3 and abs(z.std() - 1) < 2e-3 and abs((z ** 4).mean() - 3) < 2e-2 and z.abs().max() < 6
+    u = ops.rng_uniforms(st, K.RNG_CONCRETE, 1_000_000)
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 2e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("M,N,Kd", [(300, 784, 512), (64, 50, 36), (256, 128, 0)])
+def test_gemm_epilogue_generates_the_likelihood_noise(mode, M, N, Kd):
+    """AIR_EPI_SIGMOID_RNG == AIR_EPI_SIGMOID_NOISE fed with the samples of stream RNG_LIKE (element m * N + n), in every
+    GEMM path (tensor-core fast path, ragged tiles, SIMT, the K = 0 kernel): no noise tensor needed."""
+    rng = np.random.RandomState(M + N)
+    # (operands as views of padded buffers: TMA leading dimensions, and a K = 0 view keeps a unit inner stride)
+    A = cu(rng.randn(M, (Kd + 3) // 4 * 4 + 4).astype(np.float32))[:, :Kd]
+    Bm = cu(rng.randn(Kd + 1, (N + 3) // 4 * 4).astype(np.float32))[:Kd, :N]
+    bias = cu(rng.randn(N).astype(np.float32))
+    st = ops.rng_state(99, DEV, counter=7)
+    noise = ops.rng_normals(st, K.RNG_LIKE, M * N).reshape(M, N)
+    got, want = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    ops.gemm(A, Bm, got, bias=bias, aux=st, epi=K.EPI_SIGMOID_RNG, epi_param=0.3, mode=K.GEMM_MODES[mode], ws=_gemm_ws())
+    ops.gemm(A, Bm, want, bias=bias, aux=noise, epi=K.EPI_SIGMOID_NOISE, epi_param=0.3, mode=K.GEMM_MODES[mode], ws=_gemm_ws())
+    assert torch.equal(got, want)

@@ -358,3 +358,26 @@ def test_references_generator_replayed_live_including_a_canvas_restart():
         canvas, count, _, pos, box = G.reference_canvas(ref, 7, img, cs=36, max_digits=3)
         assert count == k2 and np.array_equal(canvas, c2) and list(pos) == list(p2[:2 * k2]) and list(box) == list(b2[:2 * k2])
     assert restarted > 0, "the crowded configuration should exercise the restart path"
+
+
+def test_rng_oracle_philox_known_answers_and_moments():
+    """oracle/rng_oracle.py (the host restatement of csrc/rng.cuh): Philox4x32-10 against the known-answer vectors of
+    the Random123 distribution (kat_vectors: zero, all-ones and pi-digits counter / key), and the Box-Muller transform's
+    moments / independence of the two samples of a pair."""
+    from oracle import rng_oracle as R
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(v) for v in R.philox4x32(*ctr, *key)) == want
+    z = R.normals(5, 11, R.STREAM_LATENT, 2_000_000).astype(np.float64)
+    assert abs(z.mean()) < 3e-3 and abs(z.std() - 1) < 3e-3 and abs((z ** 3).mean()) < 1e-2 and abs((z ** 4).mean() - 3) < 3e-2
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 5e-3
+    u = R.uniforms(5, 11, R.STREAM_CONCRETE, 1_000_000)
+    assert u.dtype == np.float32 and 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 2e-3
+    # streams, counters and seeds decorrelate; the same arguments reproduce
+    a = R.normals(5, 11, R.STREAM_LIKE, 1000)
+    assert np.array_equal(a, R.normals(5, 11, R.STREAM_LIKE, 1000))
+    for other in (R.normals(5, 12, R.STREAM_LIKE, 1000), R.normals(6, 11, R.STREAM_LIKE, 1000), R.normals(5, 11, R.STREAM_SCALE, 1000)):
+        assert abs(np.corrcoef(a, other)[0, 1]) < 0.15
+    assert np.array_equal(R.normals(5, 11, R.STREAM_LIKE, 1000)[:997], R.normals(5, 11, R.STREAM_LIKE, 997))

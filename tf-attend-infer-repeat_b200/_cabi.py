@@ -66,6 +66,10 @@ _SIGS = {
                                           ctypes.c_int, _c_f]),
     "air_synth_canvases_ex": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, _c_f, _c_f, _c_f, _c_f, ctypes.c_int64,
                                              ctypes.c_int, ctypes.c_int, _c_f]),
+    "air_noise_fill": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_int64, ctypes.c_int, _c_f]),
+    "air_rng_normals": (ctypes.c_int, [_c_f, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
+    "air_rng_uniforms": (ctypes.c_int, [_c_f, ctypes.c_int, _c_f, ctypes.c_int64, _c_f]),
+    "air_zero_buffers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_f]),
     "air_expand_u8": (ctypes.c_int, [_c_f, _c_f, ctypes.c_int64, _c_f]),
     "air_tfrecord_index": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_void_p]),
@@ -89,7 +93,8 @@ class Hyper(ctypes.Structure):
 (F_SCALE_MEAN, F_SCALE_LV, F_SHIFT_MEAN_X, F_SHIFT_MEAN_Y, F_SHIFT_LV_X, F_SHIFT_LV_Y, F_LOG_ODDS, F_S, F_X, F_Y,
  F_YPRE, F_Z, F_ZPROB, F_KL_Z, F_KL_SCALE, F_KL_SHIFT, F_KL_VAE, F_STOP_PREV, F_STOP_NEW) = range(19)
 NF = 20
-EPI_NONE, EPI_RELU, EPI_SOFTPLUS, EPI_MUL_DRELU, EPI_MUL_DSOFTPLUS, EPI_SIGMOID_NOISE = range(6)
+EPI_NONE, EPI_RELU, EPI_SOFTPLUS, EPI_MUL_DRELU, EPI_MUL_DSOFTPLUS, EPI_SIGMOID_NOISE, EPI_SIGMOID_RNG = range(7)
+RNG_SCALE, RNG_SHIFT, RNG_LATENT, RNG_CONCRETE, RNG_LIKE = 1, 2, 3, 4, 5
 GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 _lib = None

@@ -39,6 +39,28 @@ _VARIABLE_SCOPES = {}
 _GEMM_WORKSPACES = {}  # device -> float32 scratch tensor (split-K partial sums)
 
 _DEVICE_ANNEALABLE = ("z_pres_prior_log_odds", "learning_rate")
+# float hyper-parameters that reach the kernels as launch arguments: annealed on the host, step by step (eager steps)
+_HOST_ANNEALABLE = ("scale_prior_mean", "scale_prior_variance", "shift_prior_mean", "shift_prior_variance", "vae_prior_mean",
+                    "vae_prior_variance", "vae_likelihood_std", "z_pres_temperature", "stopping_threshold",
+                    "gradient_clipping_norm")
+
+
+def annealed_value(schedule, step, eps=10e-10):
+    """air_model.py:94-121 in fp32, as TensorFlow evaluates it: exponential_decay(init, step, iters, factor[, staircase]),
+    then max(., min), min(., max), log(. + eps)."""
+    import numpy as np
+    f = np.float32
+    p = f(step) / f(schedule["iters"])
+    if schedule.get("staircase", False):
+        p = np.floor(p)
+    v = f(schedule["init"]) * np.power(f(schedule["factor"]), p, dtype=np.float32)
+    if "min" in schedule:
+        v = np.maximum(v, f(schedule["min"]))
+    if "max" in schedule:
+        v = np.minimum(v, f(schedule["max"]))
+    if schedule.get("log", False):
+        v = np.log(v + f(eps), dtype=np.float32)
+    return float(v)
 
 
 def reset_variable_scopes():
@@ -62,8 +84,6 @@ class AIRModel:
             raise ValueError("the reference's CNN front-end hard-codes 50x50 canvases (air_model.py:512, 533)")
         if cnn and cnn_filters != 8:
             raise NotImplementedError("the conv kernels are built for the reference's cnn_filters=8")
-        if not (scale_hidden_units == shift_hidden_units == z_pres_hidden_units):
-            raise NotImplementedError("the fused heads kernel needs equal scale/shift/z_pres hidden sizes")
         if not input_images.is_cuda:
             raise C.AirError("AIRModel needs CUDA tensors (no CPU fallback)")
         C.lib()  # fail loudly if the extension is missing
@@ -85,14 +105,25 @@ class AIRModel:
 
         # ---- variables: shared by scope, like tf.variable_scope(scope, reuse=reuse) (air_model.py:68)
         key = (scope, self.device)
+        hu = scale_hidden_units if scale_hidden_units == shift_hidden_units == z_pres_hidden_units else \
+            (scale_hidden_units, shift_hidden_units, z_pres_hidden_units)   # unequal: zero-padded to the widest
+        want = dict(in_dim=self.rnn_input_dim, win=windows_size * windows_size, R=rnn_units, HU_spec=hu,
+                    L=vae_latent_dimensions, rec_units=self.vae_recognition_units, gen_units=self.vae_generative_units,
+                    cnn_filters=cnn_filters if cnn else None)
         if reuse:
             if key not in _VARIABLE_SCOPES:
                 raise ValueError(f"variable scope {scope!r} does not exist (reuse=True)")
             self.store = _VARIABLE_SCOPES[key]
+            diff = {k: (self.store.dims[k], v) for k, v in want.items() if self.store.dims[k] != v}
+            if diff:   # TF: "Trying to share variable ..., but specified shape ... and found shape ..."
+                raise ValueError(f"variable scope {scope!r} holds variables of other shapes (existing, requested): {diff}")
         else:
-            self.store = ParamStore(self.device, self.rnn_input_dim, windows_size * windows_size, rnn_units,
-                                    scale_hidden_units, vae_latent_dimensions, self.vae_recognition_units,
-                                    self.vae_generative_units, seed=seed, cnn_filters=cnn_filters if cnn else None)
+            if key in _VARIABLE_SCOPES:   # TF: "Variable air/global_step already exists, disallowed. Did you mean to set reuse=True"
+                raise ValueError(f"variable scope {scope!r} already exists on {self.device}: pass reuse=True to share its "
+                                 "variables, another scope= for independent ones, or call reset_variable_scopes()")
+            self.store = ParamStore(self.device, want["in_dim"], want["win"], rnn_units, hu, vae_latent_dimensions,
+                                    self.vae_recognition_units, self.vae_generative_units, seed=seed,
+                                    cnn_filters=want["cnn_filters"])
             _VARIABLE_SCOPES[key] = self.store
         if train:
             self.store.state[4] = float(learning_rate if not self._annealed("learning_rate") else 0.0)
@@ -100,9 +131,10 @@ class AIRModel:
         # ---- annealed hyper-parameters (air_model.py:76-82): evaluated on device from global_step
         self.annealing_schedules = annealing_schedules or {}
         for name in self.annealing_schedules:
-            if name not in _DEVICE_ANNEALABLE:
-                raise NotImplementedError(f"annealing of {name!r} is not supported on device "
-                                          f"(supported: {_DEVICE_ANNEALABLE})")
+            if name not in _DEVICE_ANNEALABLE + _HOST_ANNEALABLE:
+                raise ValueError(f"{name!r} cannot be annealed: it is not a float hyper-parameter of the loop "
+                                 f"(annealable: {_DEVICE_ANNEALABLE + _HOST_ANNEALABLE})")
+        self._host_annealed = [n for n in self.annealing_schedules if n in _HOST_ANNEALABLE]
         # derived constants the reference also keeps on the model (air_model.py:72-74), as Python floats
         _log = lambda v: math.log(v) if v > 0 else float("-inf")
         self.scale_prior_log_variance = _log(scale_prior_variance)
@@ -123,7 +155,8 @@ class AIRModel:
         self._gemm_ws = None
         if self.gemm != C.GEMM_MODES["fp32"]:
             if self.device not in _GEMM_WORKSPACES:
-                _GEMM_WORKSPACES[self.device] = torch.empty(16 << 20, device=self.device, dtype=torch.float32)
+                # (zeros: the last 64 KB hold the split-K tickets, which every GEMM leaves at zero again)
+                _GEMM_WORKSPACES[self.device] = torch.zeros(16 << 20, device=self.device, dtype=torch.float32)
             self._gemm_ws = _GEMM_WORKSPACES[self.device]
             self.gemm = ops.GemmMode(self.gemm, self._gemm_ws)   # every GEMM of the model may split K through it
         self._alloc()
@@ -143,7 +176,7 @@ class AIRModel:
 
     def _alloc(self):
         B, T, dev = self.batch_size, self.max_steps, self.device
-        R, HU, L = self.rnn_units, self.scale_hidden_units, self.vae_latent_dimensions
+        R, HU, L = self.rnn_units, self.store.dims["HU"], self.vae_latent_dimensions
         win, cs2 = self.windows_size ** 2, self.canvas_size ** 2
         z = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         w = self.w = {}
@@ -160,13 +193,16 @@ class AIRModel:
         w["dec"] = [z(T, B, u) for u in self.vae_generative_units]
         w["recon"] = z(T, B, win)
         w["gen"] = z(B, win)
-        w["stop"], w["loss"], w["rec_loss"], w["loss_item"] = z(B), z(B), z(B), z(B)
-        w["digits"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        Bp = (B + 3) // 4 * 4   # (padded to 16 bytes: the three accumulators are zeroed together by one launch)
+        self._acc_base = [z(Bp), z(Bp), torch.zeros(Bp, device=dev, dtype=torch.int32)]
+        w["stop"], w["loss"], w["digits"] = (t[:B] for t in self._acc_base)
+        w["rec_loss"], w["loss_item"] = z(B), z(B)
+        self._zero_fwd = ops.zero_items(self._acc_base)
         w["canvas"], w["reconstruction"] = z(B, cs2), z(B, cs2)
         w["out2"] = torch.zeros(2, device=dev)
         # the four Gaussian noise tensors are views of one buffer: one normal_ launch per step (sizes padded to
         # 16 bytes so that every view stays aligned for the vectorised consumers)
-        sizes = dict(scale=T * B, shift=T * B * 2, vae_latent=T * B * L, vae_like=T * B * win)
+        sizes = dict(scale=T * B, shift=T * B * 2, vae_latent=T * B * L)
         offs, tot = {}, 0
         for k, nelem in sizes.items():
             offs[k] = tot
@@ -174,7 +210,9 @@ class AIRModel:
         w["noise_flat"] = z(tot)
         nv = lambda k, *shape: w["noise_flat"][offs[k]:offs[k] + sizes[k]].view(*shape)
         w["noise"] = dict(scale=nv("scale", T, B, 1), shift=nv("shift", T, B, 2), vae_latent=nv("vae_latent", T, B, L),
-                          vae_like=nv("vae_like", T, B, win), concrete_u=z(T, B))
+                          vae_like=None, concrete_u=z(T, B))
+        w["rng_state"] = ops.rng_state(self.seed + 0x9E3779B97F4A7C15 * (1 + dp.rank(self.pg) if self.world > 1 else 1), dev)
+        self._like_noise = w["rng_state"]
         if self.train:
             w["dcanvas"] = z(B, cs2)
             # the VAE / ST backward of all T steps runs before the (sequential) LSTM backward: per-step buffers
@@ -185,6 +223,7 @@ class AIRModel:
             # per train step over the time-batched [T*B, .] buffers (one long-K GEMM per layer)
             w["dhh"] = z(T, B, 5 * HU)
             w["dgates"], w["dgates_sum"] = z(T, B, 4 * R), z(B, 4 * R)
+            self._zero_bwd = ops.zero_items([w["dgates_sum"]])
             w["vae_d"] = alloc_vae_scratch(B, win, self.vae_recognition_units, L, self.vae_generative_units, dev,
                                            lead=(T,))
             # per-CTA partial sums of d(heads/out_w|b) for every step; summed once per train step
@@ -233,16 +272,35 @@ class AIRModel:
         """Inject the five noise tensors ([T,B,1], [T,B,2], [T,B,L], [T,B,win], [T,B]) for the NEXT evaluation only:
         the run() / loss_and_grads() / train_step() that follows uses them instead of drawing, every later call
         draws fresh noise again -- like the reference, where each session.run samples anew."""
+        if self.w["noise"]["vae_like"] is None:   # (only injected noise needs the likelihood-noise tensor)
+            T, B = self.max_steps, self.batch_size
+            self.w["noise"]["vae_like"] = torch.empty(T, B, self.windows_size ** 2, device=self.device)
         for k, buf in self.w["noise"].items():
             buf.copy_(noise[k].reshape(buf.shape))
+        self._like_noise = _flat2(self.w["noise"]["vae_like"])
         self.noise = "injected"
 
     def _draw_noise(self):
-        self.w["noise_flat"].normal_()
-        self.w["noise"]["concrete_u"].uniform_()
+        """Fresh noise for one evaluation: one launch fills the small tensors from the counter-based generator and
+        advances the device step counter; the VAE likelihood noise ([T*B, window^2], 38 MB at B = 4096) is generated
+        inside the gen_mean GEMM epilogue from the same counter and never exists in memory."""
+        n = self.w["noise"]
+        ops.noise_fill(self.w["rng_state"], n["scale"], n["shift"], n["vae_latent"], n["concrete_u"],
+                       self.max_steps * self.batch_size, self.vae_latent_dimensions)
+        self._like_noise = self.w["rng_state"]
 
     def _update_scalars(self):
         st = self.store.state
+        if self._host_annealed:
+            # any other float hyper-parameter (air_model.py:76-82 anneals ANY attribute): these are launch arguments,
+            # so the schedule is evaluated on the host from global_step (one device read) before the step's launches
+            step = self.store.global_step
+            for name in self._host_annealed:
+                setattr(self, name, annealed_value(self.annealing_schedules[name], step))
+            self.hyper = C.Hyper(self.scale_prior_mean, self.scale_prior_variance, self.shift_prior_mean,
+                                 self.shift_prior_variance, self.vae_prior_mean, self.vae_prior_variance,
+                                 self.vae_likelihood_std, self.z_pres_temperature, self.stopping_threshold,
+                                 1 if self.train else 0)
         if self._annealed("z_pres_prior_log_odds"):
             ops.anneal(st, self.annealing_schedules["z_pres_prior_log_odds"], self._prior)
         if self.train and self._annealed("learning_rate"):
@@ -252,14 +310,14 @@ class AIRModel:
     # forward: air_model.py:278-508 (loop body) + :580-611 (loss / accuracy)
     # ------------------------------------------------------------------------------------------
     def _forward(self):
+        self._update_scalars()   # annealed hyper-parameters of this step (device scalars / the host struct)
         w, hp, mode = self.w, self.hyper, self.gemm
         B, T = self.batch_size, self.max_steps
         x = self.input_images
         p = self.store.p
         cs, wsz = self.canvas_size, self.windows_size
         n = w["noise"]
-        w["stop"].zero_(); w["loss"].zero_(); w["digits"].zero_()  # (the canvas starts at zero: first write-back)
-        self._update_scalars()
+        ops.zero_many(self._zero_fwd)  # stopping sums, running loss, digit counts (the canvas starts at zero: first write-back)
         # step-invariant image projection x @ K[:in_dim] (bias added per step, after the h part)
         ops.gemm(self._rnn_input(), self.Kx, w["xk"], mode=mode)
         # ---- (1) the recurrent chain: LSTM -> heads (pose, z_pres, stop) -> attention crop, step by step.  Nothing
@@ -289,7 +347,7 @@ class AIRModel:
                 ops.vae_latent_fwd(w["ml"][t], n["vae_latent"][t], hp, w["zs"][t], w["fields"][t], w["loss"])
         allbuf = dict(enc=[_flat2(e) for e in w["enc"]], ml=_flat2(w["ml"]), zs=_flat2(w["zs"]),
                       dec=[_flat2(d) for d in w["dec"]], recon=_flat2(w["recon"]))
-        vae_forward(_flat2(w["win"]), self.vw, None, _flat2(n["vae_like"]), self.vae_likelihood_std, hp, allbuf,
+        vae_forward(_flat2(w["win"]), self.vw, None, self._like_noise, self.vae_likelihood_std, hp, allbuf,
                     w["gen"], None, w["loss"], mode, latent_fn=latent_steps)
         # ---- (3) write-back + canvas accumulation in step order (air_model.py:351-366, 429-439)
         #      -- all T of them in one pass over the canvas (the running canvas stays in registers; starts from zero)
@@ -345,7 +403,7 @@ class AIRModel:
         cs, wsz = self.canvas_size, self.windows_size
         n = w["noise"]
         dscale = 1.0 / (B * self.world)
-        w["dgates_sum"].zero_()
+        ops.zero_many(self._zero_bwd)  # the summed gate gradients the LSTM backward accumulates into
         vd = w["vae_d"]
         # ---- (1) write-back backward of every step (the canvas is a plain sum: all steps see the same dcanvas)
         #      -- one launch for all T steps
@@ -404,7 +462,7 @@ class AIRModel:
         self._reduce_bucket(3)
         # the arena: head outputs and every bias gradient (one column-sum launch pair), 17 KB -- the only message
         # that is not hidden behind a GEMM
-        nw = 7 * self.scale_hidden_units
+        nw = 7 * self.store.dims["HU"]
         ops.reduce_rows(w["heads_ws"], T * self._heads_rows, nw + 7, nw, g["heads/out_w"])
         ops.reduce_rows(w["heads_ws"].view(-1)[nw:], T * self._heads_rows, nw + 7, 7, g["heads/out_b"])
         ops.colsum_multi(self._colsum_items, w["colsum_ws"])
@@ -479,6 +537,10 @@ class AIRModel:
         if self.noise == "injected":
             raise C.AirError("capture() would freeze the injected noise into the graph: run the pending evaluation "
                              "first (injection is one-shot) or call capture() before set_noise()")
+        if self._host_annealed:
+            raise C.AirError(f"capture() would freeze the host-annealed hyper-parameters {self._host_annealed} into the "
+                             "graph (they are kernel launch arguments): train eagerly, or anneal only "
+                             f"{_DEVICE_ANNEALABLE}, which are evaluated on the device")
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -21,6 +21,14 @@ HEADS = (("scale", "mean"), ("scale", "log_variance"), ("shift", "mean"), ("shif
 HEAD_OUT_ROWS = ((0, 0, 1), (1, 1, 1), (2, 2, 2), (3, 4, 2), (4, 6, 1))
 
 
+def head_sizes(HU):
+    """hidden units of the five head layers (HEADS order) from an int or a (scale, shift, z_pres) triple."""
+    if isinstance(HU, int):
+        return (HU,) * 5
+    hs, hf, hz = (int(v) for v in HU)
+    return (hs, hs, hf, hf, hz)
+
+
 def reference_shapes(in_dim, win, R, HU, L, rec_units, gen_units, cnn_filters=None):
     """name -> shape exactly as in model/air-model.index (minus the 'air/rnn/' prefix),
     ordered [cnn,] rnn, scale, shift, z_pres, vae (the order only matters for the init RNG stream).
@@ -35,11 +43,11 @@ def reference_shapes(in_dim, win, R, HU, L, rec_units, gen_units, cnn_filters=No
             prev = cnn_filters
     s["rnn/kernel"] = (in_dim + R, 4 * R)
     s["rnn/bias"] = (4 * R,)
-    for head, stat in HEADS:
+    for (head, stat), hu in zip(HEADS, head_sizes(HU)):
         out = 2 if head == "shift" else 1
-        s[f"{head}/{stat}/hidden/weights"] = (R, HU)
-        s[f"{head}/{stat}/hidden/biases"] = (HU,)
-        s[f"{head}/{stat}/output/weights"] = (HU, out)
+        s[f"{head}/{stat}/hidden/weights"] = (R, hu)
+        s[f"{head}/{stat}/hidden/biases"] = (hu,)
+        s[f"{head}/{stat}/output/weights"] = (hu, out)
         s[f"{head}/{stat}/output/biases"] = (out,)
     prev = win
     for i, u in enumerate(rec_units):
@@ -62,8 +70,14 @@ def reference_shapes(in_dim, win, R, HU, L, rec_units, gen_units, cnn_filters=No
 class ParamStore:
     def __init__(self, device, in_dim, win, R, HU, L, rec_units, gen_units, seed=0, cnn_filters=None):
         self.device = torch.device(device)
-        self.dims = dict(in_dim=in_dim, win=win, R=R, HU=HU, L=L, rec_units=tuple(rec_units), gen_units=tuple(gen_units),
-                         cnn_filters=cnn_filters)
+        # Unequal scale / shift / z_pres hidden sizes (air_model.py:288-316, 372-376 allow them): every head block of the
+        # fused [R, 5*HU] hidden layer and [7, HU] output matrix is padded to the widest head with zeros.  A padded unit
+        # is relu(0 . h + 0) = 0, meets a zero output weight and receives a zero gradient (so it stays zero under Adam):
+        # the arithmetic of the real units is unchanged, bit for bit; named_views() expose the reference-shaped slices.
+        self.head_units = head_sizes(HU)
+        HU_spec, HU = HU, max(self.head_units)
+        self.dims = dict(in_dim=in_dim, win=win, R=R, HU=HU, HU_spec=HU_spec, L=L, rec_units=tuple(rec_units),
+                         gen_units=tuple(gen_units), cnn_filters=cnn_filters)
         fused = OrderedDict()
         if cnn_filters:
             prev = 1
@@ -141,10 +155,10 @@ class ParamStore:
             if k.startswith("cnn/"):
                 d[k] = v[k]
         d["rnn/kernel"], d["rnn/bias"] = v["rnn/kernel"], v["rnn/bias"]
-        for (head, stat), (blk, row, nout) in zip(HEADS, HEAD_OUT_ROWS):
-            d[f"{head}/{stat}/hidden/weights"] = v["heads/hidden_w"][:, blk * HU:(blk + 1) * HU]
-            d[f"{head}/{stat}/hidden/biases"] = v["heads/hidden_b"][blk * HU:(blk + 1) * HU]
-            d[f"{head}/{stat}/output/weights"] = v["heads/out_w"][row:row + nout].t()
+        for (head, stat), (blk, row, nout), hu in zip(HEADS, HEAD_OUT_ROWS, self.head_units):
+            d[f"{head}/{stat}/hidden/weights"] = v["heads/hidden_w"][:, blk * HU:blk * HU + hu]
+            d[f"{head}/{stat}/hidden/biases"] = v["heads/hidden_b"][blk * HU:blk * HU + hu]
+            d[f"{head}/{stat}/output/weights"] = v["heads/out_w"][row:row + nout, :hu].t()
             d[f"{head}/{stat}/output/biases"] = v["heads/out_b"][row:row + nout]
         for k in v:
             if k.startswith("vae/") and not k.startswith("vae/rec_ml/"):
@@ -172,7 +186,7 @@ class ParamStore:
         g = torch.Generator().manual_seed(seed)
         d = self.dims
         named = self.named_views()
-        for name, shape in reference_shapes(d["in_dim"], d["win"], d["R"], d["HU"], d["L"], d["rec_units"],
+        for name, shape in reference_shapes(d["in_dim"], d["win"], d["R"], d["HU_spec"], d["L"], d["rec_units"],
                                             d["gen_units"], d["cnn_filters"]).items():
             if len(shape) >= 2:  # conv kernels [kh,kw,in,out]: fan_in = kh*kw*in, fan_out = kh*kw*out (TF glorot)
                 rf = math.prod(shape[:-2])

@@ -60,9 +60,11 @@ def vae_forward(x, w: VAEWeights, noise_latent, noise_like, likelihood_std, hype
     for (W, b), out in zip(w.gen, buf["dec"]):
         ops.gemm(a, W, out, bias=b, epi=C.EPI_SOFTPLUS, mode=mode)
         a = out
-    # gen_mean layer with the noisy-sigmoid output fused into the GEMM epilogue (vae.py:33-41)
-    ops.gemm(a, w.gm[0], buf["recon"], bias=w.gm[1], aux=noise_like, epi=C.EPI_SIGMOID_NOISE, epi_param=likelihood_std,
-             mode=mode)
+    # gen_mean layer with the noisy-sigmoid output fused into the GEMM epilogue (vae.py:33-41); noise_like is either
+    # the [rows, win] noise tensor (injected) or the int64 device RNG state: the samples are then generated in the epilogue
+    rng = noise_like.dtype == torch.int64
+    ops.gemm(a, w.gm[0], buf["recon"], bias=w.gm[1], aux=noise_like, epi=C.EPI_SIGMOID_RNG if rng else C.EPI_SIGMOID_NOISE,
+             epi_param=likelihood_std, mode=mode)
     return buf["recon"]
 
 

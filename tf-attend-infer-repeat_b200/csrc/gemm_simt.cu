@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256)
       const int64_t o = static_cast<int64_t>(m) * ldc + n;
       float v = acc[i][j];
       if (bias) v = add_rn(v, __ldg(bias + n));
-      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f, epi_param);
+      C[o] = apply_epilogue(v, epi, epi_aux_value(aux, epi, o, static_cast<int64_t>(m) * N + n), epi_param);
     }
   }
 }
@@ -150,14 +150,20 @@ __global__ void __launch_bounds__(256)
         const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n));
         v.x = add_rn(v.x, bv.x); v.y = add_rn(v.y, bv.y); v.z = add_rn(v.z, bv.z); v.w = add_rn(v.w, bv.w);
       }
-      const float4 ax = aux ? *reinterpret_cast<const float4 *>(aux + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 ax = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (epi == AIR_EPI_SIGMOID_RNG) {  // N % 4 == 0 here: element m * N + n starts a Philox block
+        const unsigned long long *st = reinterpret_cast<const unsigned long long *>(aux);
+        ax = rng_normal4(st[0], st[1], kRngLike, static_cast<unsigned long long>(m * N + n) >> 2);
+      } else if (aux) {
+        ax = *reinterpret_cast<const float4 *>(aux + o);
+      }
       v.x = apply_epilogue(v.x, epi, ax.x, epi_param); v.y = apply_epilogue(v.y, epi, ax.y, epi_param);
       v.z = apply_epilogue(v.z, epi, ax.z, epi_param); v.w = apply_epilogue(v.w, epi, ax.w, epi_param);
       *reinterpret_cast<float4 *>(C + o) = v;
     } else {
       float v = Cinit ? Cinit[o] : 0.0f;
       if (bias) v = add_rn(v, __ldg(bias + n));
-      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f, epi_param);
+      C[o] = apply_epilogue(v, epi, epi_aux_value(aux, epi, o, static_cast<int64_t>(m) * N + n), epi_param);
     }
   }
 }
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(256)
 int gemm_k0(float *C, const float *Cinit, const float *bias, const float *aux, int M, int N, int ldc, int epi,
             float epi_param, cudaStream_t s) {
   const bool vec = N % 4 == 0 && ldc % 4 == 0 && aligned16(C) && (!Cinit || aligned16(Cinit)) && (!bias || aligned16(bias)) &&
-                   (!aux || aligned16(aux));
+                   (!aux || epi == AIR_EPI_SIGMOID_RNG || aligned16(aux));
   const int64_t work = static_cast<int64_t>(M) * (vec ? N / 4 : N);
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, static_cast<int64_t>(sm_count()) * 8)));
   if (vec)
@@ -201,10 +207,13 @@ extern "C" int air_gemm_ws(const float *A, const float *B, float *C, const float
   AIR_REQUIRE(((A && B) || K == 0) && C, AIR_ERR_NULL, "air_gemm: null pointer");  // K == 0: C = epi(Cinit + bias)
   AIR_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, AIR_ERR_BAD_SHAPE,
               "air_gemm: leading dimension too small (lda=%d ldb=%d ldc=%d)", lda, ldb, ldc);
-  AIR_REQUIRE(epilogue >= AIR_EPI_NONE && epilogue <= AIR_EPI_SIGMOID_NOISE, AIR_ERR_BAD_SHAPE, "air_gemm: bad epilogue %d",
+  AIR_REQUIRE(epilogue >= AIR_EPI_NONE && epilogue <= AIR_EPI_SIGMOID_RNG, AIR_ERR_BAD_SHAPE, "air_gemm: bad epilogue %d",
               epilogue);
-  AIR_REQUIRE((epilogue != AIR_EPI_MUL_DRELU && epilogue != AIR_EPI_MUL_DSOFTPLUS && epilogue != AIR_EPI_SIGMOID_NOISE) || aux,
+  AIR_REQUIRE((epilogue != AIR_EPI_MUL_DRELU && epilogue != AIR_EPI_MUL_DSOFTPLUS && epilogue != AIR_EPI_SIGMOID_NOISE &&
+               epilogue != AIR_EPI_SIGMOID_RNG) || aux,
               AIR_ERR_NULL, "air_gemm: epilogue %d needs aux", epilogue);
+  AIR_REQUIRE(epilogue != AIR_EPI_SIGMOID_RNG || (reinterpret_cast<uintptr_t>(aux) & 7) == 0, AIR_ERR_BAD_ALIGN,
+              "air_gemm: AIR_EPI_SIGMOID_RNG takes the 8-byte aligned device RNG state as aux");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   AIR_REQUIRE(mode == AIR_GEMM_FP32_EXACT || mode == AIR_GEMM_TF32 || mode == AIR_GEMM_TF32X3, AIR_ERR_UNSUPPORTED,
               "air_gemm: unknown mode %d", mode);

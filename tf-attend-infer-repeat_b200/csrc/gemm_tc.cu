@@ -97,19 +97,24 @@ __global__ void __launch_bounds__(kTcThreads)
           } else {      // box {32 m, 32 k}: 32-wide chunk pi
             tma_load_2d(sa + pi * (kBK * 128), &mapA, &full_bar[s], m0 + pi * 32, k0);
           }
-          unsigned char *bdst;
-          int bc0, bc1;
-          if (!B_MN) {  // box {32 k, BN/4 n}
-            bdst = sb + pi * (BN / 4 * 128); bc0 = k0; bc1 = n0 + pi * (BN / 4);
-          } else if (BN == 128) {  // box {32 n, 32 k}: chunk pi
-            bdst = sb + pi * (kBK * 128); bc0 = n0 + pi * 32; bc1 = k0;
-          } else {      // BN == 64: box {32 n, 16 k}: chunk pi/2, k-half pi%2
-            bdst = sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128); bc0 = n0 + (pi >> 1) * 32; bc1 = k0 + (pi & 1) * 16;
-          }
-          if (!CL) {
-            tma_load_2d(bdst, &mapB, &full_bar[s], bc0, bc1);
-          } else if (static_cast<uint32_t>(pi >> 1) == crank) {  // this CTA's half of the shared B tile, to both CTAs
-            tma_load_2d_mc(bdst, &mapB, &full_bar[s], bc0, bc1, static_cast<uint16_t>(3));
+          // B: producer pi loads a quarter of the tile (one box; two 32-wide chunks of the 256-wide MN-major tile)
+#pragma unroll
+          for (int part = 0; part < ((B_MN && BN == 256) ? 2 : 1); ++part) {
+            unsigned char *bdst;
+            int bc0, bc1;
+            if (!B_MN) {  // box {32 k, BN/4 n}
+              bdst = sb + pi * (BN / 4 * 128); bc0 = k0; bc1 = n0 + pi * (BN / 4);
+            } else if (BN >= 128) {  // box {32 n, 32 k}: chunk pi (and pi + 4)
+              const int c = pi + 4 * part;
+              bdst = sb + c * (kBK * 128); bc0 = n0 + c * 32; bc1 = k0;
+            } else {      // BN == 64: box {32 n, 16 k}: chunk pi/2, k-half pi%2
+              bdst = sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128); bc0 = n0 + (pi >> 1) * 32; bc1 = k0 + (pi & 1) * 16;
+            }
+            if (!CL) {
+              tma_load_2d(bdst, &mapB, &full_bar[s], bc0, bc1);
+            } else if (static_cast<uint32_t>(pi >> 1) == crank) {  // this CTA's half of the shared B tile, to both CTAs
+              tma_load_2d_mc(bdst, &mapB, &full_bar[s], bc0, bc1, static_cast<uint16_t>(3));
+            }
           }
         }
         if (++s == kStages) { s = 0; ph ^= 1; }
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(256)
       float v = vals[j];
       if (Cinit) v += Cinit[o];
       if (bias) v += __ldg(bias + n + j);
-      C[o] = apply_epilogue(v, epi, aux ? aux[o] : 0.0f, epi_param);
+      C[o] = apply_epilogue(v, epi, epi_aux_value(aux, epi, o, e + j), epi_param);
     }
   }
 }
@@ -253,6 +258,15 @@ static int launch_splitk_reduce(const float *ws, int splits, float *C, const flo
 
 int gemm_tf32_pair(const float *A, const float *B, TcParams p, int lda, int ldb, bool a_mn, bool b_mn, int BNP, bool x3,
                    cudaStream_t s);  // gemm_tc2.cu
+
+// 128 x 256 tiles of the one-CTA kernel (plain TF32; AIR_TC_BN=256 forces them).  Measured per shape
+// (profiles/r2_gemm_shapes.md): they win on the long-K split-K weight gradients that the pair kernel does not take
+// (dW g2 / r2 / Kh: 18 / 18 / 23 us against 27 / 27 / 30 with 128-wide tiles) and lose on the short-K GEMMs, where
+// fewer, fatter CTAs leave SMs idle.
+static bool use_bn256(int M, int N, int num_kb, int splits, int sms) {
+  (void)M; (void)splits; (void)sms;
+  return num_kb >= 64 && N >= 256;
+}
 
 // Width of the CTA-pair tile (0 = use the one-CTA kernel).  From the per-shape measurements of the model's 26 GEMMs
 // (profiles/r2_gemm_shapes.md): in plain TF32 the pair kernel wins where the main loop is long and the grid is wide
@@ -334,9 +348,13 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   const int mt = (M + kBM - 1) / kBM;
   const int64_t tiles128 = static_cast<int64_t>(mt) * ((N + 127) / 128), tiles64 = static_cast<int64_t>(mt) * ((N + 63) / 64);
   TcParams p;
-  p.C = C; p.Cinit = Cinit; p.bias = bias; p.aux = aux;
+  p.C = C; p.Cout = C; p.Cinit = Cinit; p.bias = bias; p.aux = aux;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epi = epi; p.epi_param = epi_param;
   p.num_kb = (K + kBK - 1) / kBK;
+  // Split-K needs the caller's workspace for the partial tiles [splits][M][N]; a second, machine-wide pass adds them in
+  // increasing split order.  (Letting the last CTA of each tile do that sum inside the GEMM kernel -- one launch less --
+  // was measured 3-4x SLOWER on the weight-gradient shapes: one CTA per tile reads 2 MB of partials at L2 latency while
+  // the other SMs idle; profiles/r2_gemm_shapes.md.)
   const bool can_split = (N % 4 == 0) && workspace != nullptr && aligned16(workspace);
   const int64_t ws_splits = can_split ? ws_floats / (static_cast<int64_t>(M) * N) : 1;
   auto want_splits = [&](int64_t tiles) {
@@ -378,7 +396,10 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
     BN = 64;   // twice the CTAs of the wide tiling
     if (tiles64 < sms && can_split && p.num_kb >= 64) splits = want_splits(tiles64);
   }
-  if (tc_env().bn) BN = (tc_env().bn == 64 || N <= 64) ? 64 : 128;  // tuning / diagnostics override
+  // 128 x 256 tiles (plain TF32 only: the X3 accumulators would not fit TMEM): one MMA reads A 4 KB + B 8 KB for twice
+  // the FLOPs of the 128-wide one -- 96 instead of 128 bytes of shared-memory operand reads per tensor-core clock
+  if (!x3 && BN == 128 && use_bn256(M, N, p.num_kb, splits, sms)) BN = 256;
+  if (tc_env().bn) BN = (tc_env().bn == 64 || N <= 64) ? 64 : (tc_env().bn == 256 && !x3 && N > 128) ? 256 : 128;  // diagnostics override
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   p.splits = splits;
@@ -390,7 +411,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   else       rc = make_tmap(&ma, A, M, K, lda, 32, kBK, true);        // [K,M] M contiguous: box {32 m, 32 k}
   if (rc) return rc;
   if (!b_mn) rc = make_tmap(&mb, B, K, N, ldb, kBK, BN / 4, false);              // [N,K] K contiguous: box {32 k, BN/4 n}
-  else       rc = make_tmap(&mb, B, N, K, ldb, 32, BN == 128 ? kBK : 16, true);  // [K,N] N contiguous: box {32 n, 32|16 k}
+  else       rc = make_tmap(&mb, B, N, K, ldb, 32, BN >= 128 ? kBK : 16, true);  // [K,N] N contiguous: box {32 n, 32|16 k}
   if (rc) return rc;
 
   // Pairs of M-neighbour CTAs share their B tile through TMA multicast when the M-tile count is even and the
@@ -403,7 +424,8 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   (a_mn ? (b_mn ? launch_tc<BNv, true, true, CLv, X3v>(ma, mb, p, s) : launch_tc<BNv, true, false, CLv, X3v>(ma, mb, p, s)) \
         : (b_mn ? launch_tc<BNv, false, true, CLv, X3v>(ma, mb, p, s) : launch_tc<BNv, false, false, CLv, X3v>(ma, mb, p, s)))
 #define AIR_TC_DISPATCH(BNv, CLv) (x3 ? AIR_TC_DISPATCH2(BNv, CLv, true) : AIR_TC_DISPATCH2(BNv, CLv, false))
-  if (cl) rc = (BN == 128) ? AIR_TC_DISPATCH(128, true) : AIR_TC_DISPATCH(64, true);
+  if (BN == 256) rc = cl ? AIR_TC_DISPATCH2(256, true, false) : AIR_TC_DISPATCH2(256, false, false);
+  else if (cl) rc = (BN == 128) ? AIR_TC_DISPATCH(128, true) : AIR_TC_DISPATCH(64, true);
   else rc = (BN == 128) ? AIR_TC_DISPATCH(128, false) : AIR_TC_DISPATCH(64, false);
 #undef AIR_TC_DISPATCH
 #undef AIR_TC_DISPATCH2

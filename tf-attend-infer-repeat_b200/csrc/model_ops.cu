@@ -786,6 +786,78 @@ __global__ void __launch_bounds__(256)
   if (tid == 0) counts[b] = count;
 }
 
+// ---- counter-based noise (rng.cuh) -------------------------------------------------------------------------------------
+// One launch fills the four small noise tensors of a step.  Work item = one Philox block (4 samples) of one stream;
+// the streams are laid end to end.  The step counter is advanced here: every CTA reads the old value c and samples
+// with c + 1; the last CTA to finish (ticket) publishes c + 1, so the kernels that follow in the stream -- the
+// AIR_EPI_SIGMOID_RNG epilogue -- see the counter this step was sampled with.
+__global__ void __launch_bounds__(256)
+    noise_fill_k(unsigned long long *state, float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ latent,
+                 float *__restrict__ conc, int64_t TB, int L) {
+  pdl_sync();
+  const unsigned long long seed = state[0], ctr = *reinterpret_cast<volatile unsigned long long *>(state + 1) + 1ull;
+  const int64_t n[4] = {scale ? TB : 0, shift ? 2 * TB : 0, latent ? TB * L : 0, conc ? TB : 0};
+  float *const out[4] = {scale, shift, latent, conc};
+  const uint32_t stream[4] = {kRngScale, kRngShift, kRngLatent, kRngConcrete};
+  int64_t nb[4], total = 0;
+  for (int q = 0; q < 4; ++q) { nb[q] = (n[q] + 3) >> 2; total += nb[q]; }
+  for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; w < total; w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int q = 0;
+    int64_t blk = w;
+    while (blk >= nb[q]) { blk -= nb[q]; ++q; }
+    float4 v;
+    if (q == 3) {
+      const uint4 r = rng_block(seed, ctr, stream[q], static_cast<unsigned long long>(blk));
+      v = make_float4(rng_uniform(r.x), rng_uniform(r.y), rng_uniform(r.z), rng_uniform(r.w));
+    } else {
+      v = rng_normal4(seed, ctr, stream[q], static_cast<unsigned long long>(blk));
+    }
+    float *o = out[q] + 4 * blk;
+    if (4 * blk + 4 <= n[q] && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+      *reinterpret_cast<float4 *>(o) = v;
+    } else {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      for (int l = 0; l < 4 && 4 * blk + l < n[q]; ++l) o[l] = vv[l];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(state + 2, 1ull);
+    if (t == gridDim.x - 1) {
+      state[2] = 0;
+      state[1] = ctr;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rng_samples_k(const unsigned long long *state, uint32_t stream, int uniform, float *out, int64_t n) {
+  pdl_sync();
+  const unsigned long long seed = state[0], ctr = state[1];
+  for (int64_t blk = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; 4 * blk < n; blk += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float vv[4];
+    if (uniform) {
+      const uint4 r = rng_block(seed, ctr, stream, static_cast<unsigned long long>(blk));
+      vv[0] = rng_uniform(r.x); vv[1] = rng_uniform(r.y); vv[2] = rng_uniform(r.z); vv[3] = rng_uniform(r.w);
+    } else {
+      const float4 v = rng_normal4(seed, ctr, stream, static_cast<unsigned long long>(blk));
+      vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
+    }
+    for (int l = 0; l < 4 && 4 * blk + l < n; ++l) out[4 * blk + l] = vv[l];
+  }
+}
+
+// several small buffers zeroed by ONE launch (the accumulators a step starts from), 16 bytes per thread and iteration
+struct ZeroBatch { void *ptr[8]; int64_t n16[8]; int n; };
+__global__ void __launch_bounds__(256) zero_many_k(ZeroBatch zb) {
+  pdl_sync();
+  for (int q = 0; q < zb.n; ++q) {
+    uint4 *p = reinterpret_cast<uint4 *>(zb.ptr[q]);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < zb.n16[q]; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      p[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // uint8 canvases -> fp32, bit for bit what the MNIST loader behind multi_mnist.py produces: tensorflow's
 // input_data.read_data_sets scales pixels with numpy.multiply(images.astype(float32), 1.0 / 255.0), i.e. in fp32
 // fl(float(k) * fl(1/255)).  16 pixels per thread: one 128-bit load, four 128-bit stores.
@@ -1020,6 +1092,55 @@ extern "C" int air_synth_canvases_ex(uint64_t seed, int64_t first_index, float *
 extern "C" int air_synth_canvases(uint64_t seed, int64_t first_index, float *images, int32_t *counts, int64_t B,
                                   int canvas_size, int max_digits, air_stream_t stream) {
   return air_synth_canvases_ex(seed, first_index, images, counts, nullptr, nullptr, B, canvas_size, max_digits, stream);
+}
+
+extern "C" int air_noise_fill(air_rng_state_t *state, float *scale, float *shift, float *vae_latent, float *concrete_u,
+                              int64_t TB, int L, air_stream_t stream) {
+  AIR_REQUIRE(TB >= 0 && L >= 0, AIR_ERR_BAD_SHAPE, "noise_fill: bad shape");
+  AIR_REQUIRE(state, AIR_ERR_NULL, "noise_fill: null RNG state");
+  const int64_t blocks = ((scale ? TB : 0) + 3) / 4 + ((shift ? 2 * TB : 0) + 3) / 4 + ((vae_latent ? TB * L : 0) + 3) / 4 +
+                         ((concrete_u ? TB : 0) + 3) / 4;
+  AIR_LAUNCH(noise_fill_k, grid_for(std::max<int64_t>(blocks, 1), 256), 256, 0, ST(stream),
+             reinterpret_cast<unsigned long long *>(state), scale, shift, vae_latent, concrete_u, TB, L);
+  count_launch();
+  return check_launch("noise_fill");
+}
+
+static int rng_samples(const air_rng_state_t *state, int rng_stream, int uniform, float *out, int64_t n, air_stream_t stream) {
+  AIR_REQUIRE(n >= 0 && rng_stream > 0, AIR_ERR_BAD_SHAPE, "rng_samples: bad arguments");
+  if (n == 0) return AIR_OK;
+  AIR_REQUIRE(state && out, AIR_ERR_NULL, "rng_samples: null pointer");
+  AIR_LAUNCH(rng_samples_k, grid_for((n + 3) / 4, 256), 256, 0, ST(stream), reinterpret_cast<const unsigned long long *>(state),
+             static_cast<uint32_t>(rng_stream), uniform, out, n);
+  count_launch();
+  return check_launch("rng_samples");
+}
+
+extern "C" int air_rng_normals(const air_rng_state_t *state, int rng_stream, float *out, int64_t n, air_stream_t stream) {
+  return rng_samples(state, rng_stream, 0, out, n, stream);
+}
+
+extern "C" int air_rng_uniforms(const air_rng_state_t *state, int rng_stream, float *out, int64_t n, air_stream_t stream) {
+  return rng_samples(state, rng_stream, 1, out, n, stream);
+}
+
+extern "C" int air_zero_buffers(void *const *buffers, const int64_t *nbytes, int n, air_stream_t stream) {
+  AIR_REQUIRE(n >= 0 && n <= 8, AIR_ERR_BAD_SHAPE, "zero_buffers: at most 8 buffers per call");
+  if (n == 0) return AIR_OK;
+  AIR_REQUIRE(buffers && nbytes, AIR_ERR_NULL, "zero_buffers: null pointer");
+  ZeroBatch zb;
+  zb.n = n;
+  int64_t most = 0;
+  for (int q = 0; q < n; ++q) {
+    AIR_REQUIRE(buffers[q] && aligned16(buffers[q]) && nbytes[q] >= 0 && nbytes[q] % 16 == 0, AIR_ERR_BAD_ALIGN,
+                "zero_buffers: buffers must be 16-byte aligned with sizes that are multiples of 16 bytes");
+    zb.ptr[q] = buffers[q];
+    zb.n16[q] = nbytes[q] / 16;
+    most = std::max(most, zb.n16[q]);
+  }
+  AIR_LAUNCH(zero_many_k, grid_for(std::max<int64_t>(most, 1), 256), 256, 0, ST(stream), zb);
+  count_launch();
+  return check_launch("zero_buffers");
 }
 
 extern "C" int air_expand_u8(const uint8_t *src, float *dst, int64_t n, air_stream_t stream) {

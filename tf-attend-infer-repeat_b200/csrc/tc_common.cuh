@@ -136,6 +136,7 @@ struct TcParams {
   int stages;  // TMA->MMA ring depth (<= kMaxStages)
   int chains;  // X3: number of hi*hi accumulators used round-robin over the k-blocks (1..kMaxChains)
   int flags;   // experiment switches (AIR_TC_FLAGS), 0 in production
+  float *Cout;             // the real output (C above is the split-K workspace when splits > 1)
 };
 
 constexpr int kMaxChains = 3;
@@ -146,92 +147,114 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int BN, bool x3) {
   return want <= 32 ? 32u : want <= 64 ? 64u : want <= 128 ? 128u : want <= 256 ? 256u : 512u;
 }
 
-
 // Epilogue of one 128-row output tile, run by the eight epilogue warps (warps 2..9): TMEM lane quarter = warp % 4, two
 // warps per quarter each taking half of the tile's BN columns.  X3: the accumulator is the FP32 (RN) sum of `chains`
 // hi*hi accumulators (columns c * BN) and the correction accumulator (column corr_col), in that fixed order.
+// Split-K (p.splits > 1): the raw partial tile goes to the workspace slice of this split (p.C); splitk_reduce_kernel
+// adds the slices in increasing split order and applies Cinit / bias / epilogue.
 template <int BN, bool X3>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t tmem_acc, int m0, int n0, int split, int warp, int lane,
                                             int chains, int corr_col) {
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns
-    const int row = m0 + q * 32 + lane;
-    float *Cout = p.C;
-    int ldo = p.ldc;
-    const bool partial = p.splits > 1;
-    if (partial) {
-      Cout = p.C + static_cast<int64_t>(split) * p.M * p.N;
-      ldo = p.N;
-    }
-    const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) &&
-                        (partial || ((p.ldc % 4 == 0) && (!p.Cinit || (reinterpret_cast<uintptr_t>(p.Cinit) & 15) == 0) &&
-                                     (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) &&
-                                     (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)));
-    const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-    const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_x16(tbase + c0, r);
-      const int nb = n0 + c0;
-      const bool row_ok = row < p.M && nb < p.N;
-      const bool fast = vec_ok && row_ok && nb + 16 <= p.N;
-      float ci[16], ax[16], bi[16];
+  const int q = warp & 3;            // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;  // which half of the tile's columns
+  const int row = m0 + q * 32 + lane;
+  const bool partial = p.splits > 1;
+  const int64_t slice = static_cast<int64_t>(p.M) * p.N;
+  float *Cpart = p.C + static_cast<int64_t>(split) * slice;  // (partial only: p.C is the workspace)
+  const bool vec_part = (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  const bool vec_out = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.Cout) & 15) == 0) &&
+                       (!p.Cinit || (reinterpret_cast<uintptr_t>(p.Cinit) & 15) == 0) &&
+                       (!p.aux || p.epi == AIR_EPI_SIGMOID_RNG || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) &&
+                       (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
+  const bool rng = p.epi == AIR_EPI_SIGMOID_RNG;  // aux = device RNG state, the noise is generated here
+  const unsigned long long *rng_st = reinterpret_cast<const unsigned long long *>(p.aux);
+
+  // v[16] = product terms of (row, nb .. nb + 15)  ->  C = epi((Cinit + v) + bias)
+  auto finalize = [&](float (&v)[16], int nb, bool fast, const float (&ci)[16], float (&ax)[16], const float (&bi)[16]) {
+    if (fast) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { ci[j] = 0.0f; ax[j] = 0.0f; bi[j] = 0.0f; }
-      const int64_t o = static_cast<int64_t>(row) * p.ldc + nb;
-      if (fast && !partial) {  // epilogue inputs are fetched while the TMEM load is in flight
+      for (int j = 0; j < 16; ++j) v[j] = (v[j] + ci[j]) + bi[j];
+      if (rng) {  // 16 consecutive elements of row `row`: four Philox blocks when the row starts on a block boundary
+        const unsigned long long idx = static_cast<unsigned long long>(row) * p.N + nb, seed = rng_st[0], ctr = rng_st[1];
+        if ((idx & 3) == 0) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          if (p.Cinit) *reinterpret_cast<float4 *>(ci + 4 * j4) = *reinterpret_cast<const float4 *>(p.Cinit + o + 4 * j4);
-          if (p.aux) *reinterpret_cast<float4 *>(ax + 4 * j4) = *reinterpret_cast<const float4 *>(p.aux + o + 4 * j4);
-          if (p.bias) *reinterpret_cast<float4 *>(bi + 4 * j4) = __ldg(reinterpret_cast<const float4 *>(p.bias + nb) + j4);
+          for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<float4 *>(ax + 4 * j4) = rng_normal4(seed, ctr, kRngLike, (idx >> 2) + j4);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ax[j] = rng_normal_elem(seed, ctr, kRngLike, idx + j);
         }
       }
-      tmem_ld_wait();
-      if (X3) {  // product = ((chain_0 + chain_1) + ...) + correction, FP32 round-to-nearest, fixed order
-        uint32_t r2[16];
-        for (int c = 1; c < chains; ++c) {
-          tmem_ld_x16(tbase + c * BN + c0, r2);
-          tmem_ld_wait();
+      apply_epilogue16(v, ax, p.epi, p.epi_param);
+      float4 *dst = reinterpret_cast<float4 *>(p.Cout + static_cast<int64_t>(row) * p.ldc + nb);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+      for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = nb + j;
+        if (n < p.N) {
+          const int64_t oo = static_cast<int64_t>(row) * p.ldc + n;
+          float x = v[j];
+          if (p.Cinit) x += p.Cinit[oo];
+          if (p.bias) x += __ldg(p.bias + n);
+          p.Cout[oo] = apply_epilogue(x, p.epi, epi_aux_value(p.aux, p.epi, oo, static_cast<int64_t>(row) * p.N + n), p.epi_param);
         }
-        tmem_ld_x16(tbase + corr_col + c0, r2);
+      }
+    }
+  };
+  auto fetch_inputs = [&](int nb, float (&ci)[16], float (&ax)[16], float (&bi)[16]) {
+    const int64_t o = static_cast<int64_t>(row) * p.ldc + nb;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      if (p.Cinit) *reinterpret_cast<float4 *>(ci + 4 * j4) = *reinterpret_cast<const float4 *>(p.Cinit + o + 4 * j4);
+      if (p.aux && !rng) *reinterpret_cast<float4 *>(ax + 4 * j4) = *reinterpret_cast<const float4 *>(p.aux + o + 4 * j4);
+      if (p.bias) *reinterpret_cast<float4 *>(bi + 4 * j4) = __ldg(reinterpret_cast<const float4 *>(p.bias + nb) + j4);
+    }
+  };
+
+#pragma unroll 1
+  for (int c0 = cbeg; c0 < cend; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld_x16(tbase + c0, r);
+    const int nb = n0 + c0;
+    const bool row_ok = row < p.M && nb < p.N;
+    const bool fast = (partial ? vec_part : vec_out) && row_ok && nb + 16 <= p.N;
+    float ci[16], ax[16], bi[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { ci[j] = 0.0f; ax[j] = 0.0f; bi[j] = 0.0f; }
+    if (fast && !partial) fetch_inputs(nb, ci, ax, bi);  // epilogue inputs are fetched while the TMEM load is in flight
+    tmem_ld_wait();
+    if (X3) {  // product = ((chain_0 + chain_1) + ...) + correction, FP32 round-to-nearest, fixed order
+      uint32_t r2[16];
+      for (int c = 1; c < chains; ++c) {
+        tmem_ld_x16(tbase + c * BN + c0, r2);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
       }
-      if (!row_ok) continue;
-      if (fast) {
-        float v[16];
+      tmem_ld_x16(tbase + corr_col + c0, r2);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        if (!partial) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = (v[j] + ci[j]) + bi[j];
-          apply_epilogue16(v, ax, p.epi, p.epi_param);
-        }
-        float4 *dst = reinterpret_cast<float4 *>(Cout + static_cast<int64_t>(row) * ldo + nb);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = nb + j;
-          if (n < p.N) {
-            float v = __uint_as_float(r[j]);
-            if (!partial) {
-              const int64_t oo = static_cast<int64_t>(row) * p.ldc + n;
-              if (p.Cinit) v += p.Cinit[oo];
-              if (p.bias) v += __ldg(p.bias + n);
-              v = apply_epilogue(v, p.epi, p.aux ? p.aux[oo] : 0.0f, p.epi_param);
-            }
-            Cout[static_cast<int64_t>(row) * ldo + n] = v;
-          }
-        }
-      }
+      for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
     }
+    if (!row_ok) continue;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    if (!partial) {
+      finalize(v, nb, fast, ci, ax, bi);
+    } else if (fast) {
+      float4 *dst = reinterpret_cast<float4 *>(Cpart + static_cast<int64_t>(row) * p.N + nb);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (nb + j < p.N) Cpart[static_cast<int64_t>(row) * p.N + nb + j] = v[j];
+    }
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------

@@ -37,21 +37,28 @@ class GemmMode(int):
 
 def gemm(A, B, out, Cinit=None, bias=None, aux=None, tA=False, tB=False, epi=C.EPI_NONE, mode=0, epi_param=0.0, ws=None):
     """out[M,N] = epi((Cinit + op(A) op(B)) + bias); see include/air_b200.h (air_gemm_ws).
-    ``ws``: optional float32 CUDA scratch tensor on the operands' device: lets long-K / few-tile GEMMs run split-K."""
+    ``ws``: optional float32 CUDA scratch tensor on the operands' device: lets long-K / few-tile GEMMs run split-K.
+    ``aux``: the [M, N] second operand of an epilogue, or -- EPI_SIGMOID_RNG -- the int64 device RNG state (rng_state())."""
     M, N = out.shape
     K = A.shape[0] if tA else A.shape[1]
     kb = B.shape[1] if tB else B.shape[0]
     if kb != K or (A.shape[1] if tA else A.shape[0]) != M or (B.shape[0] if tB else B.shape[1]) != N:
         raise C.AirError(f"gemm shape mismatch: A{tuple(A.shape)} tA={tA} B{tuple(B.shape)} tB={tB} out{tuple(out.shape)}")
     ldc = _ld(out)
-    for t in (Cinit, aux):
+    if epi == C.EPI_SIGMOID_RNG:
+        if aux is None or aux.dtype != torch.int64 or aux.numel() != 4 or not aux.is_cuda:
+            raise C.AirError("EPI_SIGMOID_RNG takes the device RNG state (ops.rng_state) as aux")
+        aux_p = ptr(aux)
+    else:
+        aux_p = _p2(aux)
+    for t in (Cinit, None if epi == C.EPI_SIGMOID_RNG else aux):
         if t is not None and (_ld(t) != ldc or t.shape != out.shape):
             raise C.AirError("Cinit / aux must have the layout of out")
     if ws is None:
         ws = getattr(mode, "ws", None)
     if ws is not None and ws.device != out.device:
         raise C.AirError("the GEMM workspace must live on the device of the operands")
-    check(lib().air_gemm_ws(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), _p2(aux), M, N, K, _ld(A), _ld(B), ldc,
+    check(lib().air_gemm_ws(_p2(A), _p2(B), _p2(out), _p2(Cinit), ptr(bias), aux_p, M, N, K, _ld(A), _ld(B), ldc,
                             int(tA), int(tB), epi, float(epi_param), int(mode), ptr(ws), 0 if ws is None else ws.numel(),
                             stream()), "air_gemm")
     return out
@@ -229,6 +236,51 @@ def conv5x5_bwd(x, w, out, argmax, dout, din, dw, db, accumulate, workspace, H, 
     check(lib().air_conv5x5_bwd(ptr(x), ptr(w), ptr(out), ptr(argmax), ptr(dout), ptr(din), ptr(dw), ptr(db),
                                 int(accumulate), ptr(workspace), x.shape[0], H, W, cin, cout, int(pool), stream()),
           "air_conv5x5_bwd")
+
+
+def rng_state(seed, device, counter=0):
+    """Device RNG state of include/air_b200.h (air_rng_state_t): int64 [4] = seed, step counter, scratch, unused."""
+    return torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(counter), 0, 0], dtype=torch.int64, device=device)
+
+
+def noise_fill(state, scale, shift, vae_latent, concrete_u, TB, L):
+    """Advance the step counter and fill the small noise tensors of a step (TB = T * B rows): scale [TB], shift [TB, 2],
+    vae_latent [TB, L] ~ N(0,1), concrete_u [TB] ~ U[0,1); any of them may be None."""
+    for t, n in ((scale, TB), (shift, 2 * TB), (vae_latent, TB * L), (concrete_u, TB)):
+        if t is not None and (t.numel() != n or t.dtype != torch.float32):
+            raise C.AirError("noise_fill: tensor sizes must be T*B, 2*T*B, T*B*L, T*B (float32)")
+    check(lib().air_noise_fill(ptr(state), ptr(scale), ptr(shift), ptr(vae_latent), ptr(concrete_u), TB, L, stream()), "air_noise_fill")
+
+
+def rng_normals(state, rng_stream, n):
+    out = torch.empty(n, device=state.device)
+    check(lib().air_rng_normals(ptr(state), rng_stream, ptr(out), n, stream()), "air_rng_normals")
+    return out
+
+
+def rng_uniforms(state, rng_stream, n):
+    out = torch.empty(n, device=state.device)
+    check(lib().air_rng_uniforms(ptr(state), rng_stream, ptr(out), n, stream()), "air_rng_uniforms")
+    return out
+
+
+def zero_items(tensors):
+    """-> opaque handle for zero_many(): the (pointer, byte count) arrays of up to 8 contiguous CUDA tensors whose
+    storage is 16-byte aligned and a multiple of 16 bytes long (keep the tensors alive as long as the handle)."""
+    n = len(tensors)
+    ptrs, sizes = (ctypes.c_void_p * n)(), (ctypes.c_int64 * n)()
+    for i, t in enumerate(tensors):
+        nb = t.numel() * t.element_size()
+        if not (t.is_cuda and t.is_contiguous()) or nb % 16 or t.data_ptr() % 16:
+            raise C.AirError("zero_many: contiguous CUDA tensors, 16-byte aligned, sizes multiples of 16 bytes")
+        ptrs[i], sizes[i] = t.data_ptr(), nb
+    return ptrs, sizes, n
+
+
+def zero_many(handle):
+    """Zero all tensors of a zero_items() handle with one launch."""
+    ptrs, sizes, n = handle
+    check(lib().air_zero_buffers(ptrs, sizes, n, stream()), "air_zero_buffers")
 
 
 def expand_u8(src, dst):
