@@ -202,6 +202,57 @@ def st_kernels(d, B):
             "writeback_canvas_bwd_full_dtheta": wb_bwd(0)}
 
 
+# the launches the MODEL makes: all T = 3 loop steps of an op in one launch, rows [T, B, ...] against the one shared
+# canvas / dCanvas (air_st_*_steps).  Algorithmic bytes per IMAGE (T steps): the shared operand once, the per-step ones T x.
+ST_STEPS_T = 3
+ST_STEPS_BYTES = {"crop_fwd_steps": 10000 + ST_STEPS_T * (24 + 3136),                    # canvas once, T x (theta, window out)
+                  "crop_bwd_steps": 10000 + ST_STEPS_T * (3136 + 24 + 24),               # canvas once, T x (dwindow, theta, dtheta)
+                  "compose_steps": ST_STEPS_T * (3136 + 24 + 8) + 10000,                 # T x (window, theta_inv, z, stop), canvas out
+                  "writeback_canvas_bwd_steps": 10000 + ST_STEPS_T * (3136 + 24 + 8 + 3136 + 24 + 4)}   # dcanvas once, T x (in, out)
+
+
+def st_steps_kernels(B, dev, seed=2):
+    """name -> zero-arg launcher for the batched-over-T launches of the model at per-step batch B."""
+    import torch
+    from air_b200 import ops
+    T = ST_STEPS_T
+    ds = [st_inputs(B, dev, seed + t) for t in range(T)]
+    U = ds[0]["U"]
+    th, thi = torch.stack([d["th"] for d in ds]), torch.stack([d["thi"] for d in ds])
+    win = torch.stack([d["win"] for d in ds])
+    fields = torch.zeros(T, 2, B, device=dev)
+    for t, d in enumerate(ds):
+        fields[t, 0], fields[t, 1] = d["z"], d["stop"]
+    dwin, dcanvas = torch.stack([d["dwin"] for d in ds]), ds[0]["dcanvas"]
+    out_win, dth = torch.empty(T, B, 784, device=dev), torch.empty(T, B, 6, device=dev)
+    canvas = torch.empty(B, 2500, device=dev)
+    dgen, dthi, dz = torch.empty(T, B, 784, device=dev), torch.empty(T, B, 6, device=dev), torch.empty(T, B, device=dev)
+    live = float((fields[:, 1] < 0.99).float().mean().item())
+    ks = {"crop_fwd_steps": lambda: ops.st_forward_steps(U, th, out_win, 50, 50, 1, 28, 28),
+          "crop_bwd_steps": lambda: ops.st_backward_steps(U, th, dwin, dth, 50, 50, 1, 28, 28),
+          "compose_steps": lambda: ops.writeback_canvas_fwd_steps(win, thi, fields[0, 0], fields[0, 1], 2 * B, 0.99, None, canvas,
+                                                                  28, 28, 50, 50),
+          "writeback_canvas_bwd_steps": lambda: ops.writeback_canvas_bwd_steps(win, thi, fields[0, 0], fields[0, 1], 2 * B, 0.99, dcanvas,
+                                                                               dgen, dthi, dz, 28, 28, 50, 50, window_is_sigmoid=True,
+                                                                               axis_aligned_theta=True)}
+    return ks, live
+
+
+def st_steps_summary(peaks, B, steps=20, warmup=5):
+    import torch
+    ks, live = st_steps_kernels(B, torch.device("cuda"))
+    out = {}
+    for name, fn in ks.items():
+        ms = time_launches(fn, steps, warmup)
+        gbs = B * ST_STEPS_BYTES[name] / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 5), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+                     "bytes_per_image": ST_STEPS_BYTES[name]}
+    del ks
+    torch.cuda.empty_cache()
+    return {"T": ST_STEPS_T, "batch": B, "live_fraction": round(live, 4), "kernels": out,
+            "note": "algorithmic bytes as if every step were live; stopped steps (30 %) move less in compose / bwd"}
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 65536, from the `ncu --set full` captures
 # summarised under profiles/ (r1_crop_fwd_ncu_full.md was taken at B = 16384 x4 images per CTA: 840.7 MB per
 # 65536 images; r1_st_bwd_k1/k2_ncu_full.md).  The fused backward reads LESS than the algorithmic figure because
@@ -276,6 +327,7 @@ def run_st(args, rank, world, peaks):
                      "algorithmic_bytes": B * ST_BYTES["crop_fwd"], "peak_source": peaks["source"],
                      "kernel": "st_fwd_staged<50,50,28,28,4,false>"},
         "kernels": res,
+        "model_launches": {f"B{b}": st_steps_summary(peaks, b, max(5, args.steps // 3), 3) for b in (4096, B)},
         "e2e": {"value": round(B * ST_BYTES["crop_fwd"] / (e2e_ms * 1e-3) / 1e9 * world, 2), "unit": "GB/s",
                 "h2d_bytes_per_step": int(U_h.numel() * 4 + th_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
                 "ms_per_step": round(e2e_ms, 4)},

@@ -78,16 +78,22 @@ def cuda_noise(noise):
 
 
 def smoke_model():
-    """One tiny train step of the full model on cuda:0, checked against the oracle."""
-    imgs, cnt, params, noise = covered_fixture(8, seed=0)
-    orc, m = make_pair(imgs, cnt, params, train=True)
-    out, grads = orc.loss_and_grads(imgs, cnt, noise)
-    m.loss_and_grads(cuda_noise(noise))
-    assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"]), "digit counts differ from the oracle"
-    rel = abs(m.loss.item() - out["loss"].item()) / abs(out["loss"].item())
-    assert rel < 1e-5, f"loss differs from the oracle by {rel:.2e}"
-    worst = max(relnorm(g, grads[k]) for k, g in m.store.named_grads().items())
-    assert worst < 1e-4, f"gradient differs from the oracle by {worst:.2e}"
-    m._apply_gradients()
-    torch.cuda.synchronize()
-    print(f"smoke model OK: loss rel err {rel:.2e}, worst grad rel err {worst:.2e}")
+    """One tiny train step of the full model on cuda:0 in each GEMM mode, checked against the oracle: the two FP32-grade
+    modes (SIMT FFMA, 3xTF32 on tcgen05) at the parity bars, plain TF32 (the throughput mode, also tcgen05) at its own."""
+    imgs, cnt, params, noise = covered_fixture(256, seed=0)    # 256 rows: the CTA-pair tensor-core kernels engage too
+    orc = None
+    for mode, loss_bar, grad_bar in (("fp32", 1e-5, 1e-4), ("tf32x3", 1e-5, 1e-4), ("tf32", 5e-3, 5e-2)):
+        orc, m = make_pair(imgs, cnt, params, train=True, gemm_mode=mode)
+        if mode == "fp32":
+            out, grads = orc.loss_and_grads(imgs, cnt, noise)
+        m.loss_and_grads(cuda_noise(noise))
+        if mode != "tf32":
+            assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"]), f"{mode}: digit counts differ from the oracle"
+        rel = abs(m.loss.item() - out["loss"].item()) / abs(out["loss"].item())
+        assert rel < loss_bar, f"{mode}: loss differs from the oracle by {rel:.2e}"
+        worst = max(relnorm(g, grads[k]) for k, g in m.store.named_grads().items())
+        assert worst < grad_bar, f"{mode}: gradient differs from the oracle by {worst:.2e}"
+        m._apply_gradients()
+        m.train_step()          # one step with noise generated on the device (counter-based RNG, in-epilogue likelihood noise)
+        torch.cuda.synchronize()
+        print(f"smoke model OK [{mode}]: loss rel err {rel:.2e}, worst grad rel err {worst:.2e}")
