@@ -135,11 +135,12 @@ def barrier(world):
 # ST microbench (BASELINE.json configs[1]); algorithmic bytes per image from SURVEY.md 8(d)
 # ------------------------------------------------------------------------------------------
 ST_BYTES = {"crop_fwd": 13160, "crop_bwd": 13184, "writeback_canvas_fwd": 23168, "writeback_canvas_bwd": 16332,
-            "writeback_canvas_bwd_full_dtheta": 16332}
+            "writeback_canvas_bwd_analytic": 16332, "writeback_canvas_bwd_full_dtheta": 16332}
 # What a STOPPED image (stopping_sum >= threshold, 30 % of the microbench batch) moves in the fused kernels: the forward
 # still copies its canvas row (10,000 in + 10,000 out + the two scalars it tests); the backward only writes zeros
 # (3,136 dwindow + 24 dtheta + 4 dz) and reads the 4-byte stopping sum -- no window, no dCanvas row.
-ST_BYTES_STOPPED = {"writeback_canvas_fwd": 20008, "writeback_canvas_bwd": 3168, "writeback_canvas_bwd_full_dtheta": 3168}
+ST_BYTES_STOPPED = {"writeback_canvas_fwd": 20008, "writeback_canvas_bwd": 3168, "writeback_canvas_bwd_analytic": 3168,
+                    "writeback_canvas_bwd_full_dtheta": 3168}
 
 
 def st_moved_bytes(name, B, live_frac):
@@ -196,10 +197,12 @@ def st_kernels(d, B):
                                                   p(dwin), p(dth), p(dz), flags, B, 28, 28, 50, 50, c.stream()), "wb_bwd")
         return f
 
-    # writeback_canvas_bwd is the call the model makes (AIR_WB_SIGMOID_WINDOW | AIR_WB_AXIS_ALIGNED_THETA: SigmoidGrad
-    # fused, only the four dtheta_inv entries the model consumes); *_full_dtheta is the general fused kernel (flags 0)
-    return {"crop_fwd": crop_fwd, "crop_bwd": crop_bwd, "writeback_canvas_fwd": wb_fwd, "writeback_canvas_bwd": wb_bwd(3),
-            "writeback_canvas_bwd_full_dtheta": wb_bwd(0)}
+    # writeback_canvas_bwd is the call the model makes: AIR_WB_SIGMOID_WINDOW | AIR_WB_AXIS_ALIGNED_THETA |
+    # AIR_WB_REFERENCE_ROUNDING (st_wb_bwd_ref: every canvas pixel, the un-cancelled corner terms of the reference's fp32
+    # autodiff); *_analytic is the same call without the last flag (st_wb_bwd_axis: in-range rectangle only, the fp64-like
+    # gradient the reference does NOT train on); *_full_dtheta is the general fused kernel (flags 0)
+    return {"crop_fwd": crop_fwd, "crop_bwd": crop_bwd, "writeback_canvas_fwd": wb_fwd, "writeback_canvas_bwd": wb_bwd(7),
+            "writeback_canvas_bwd_analytic": wb_bwd(3), "writeback_canvas_bwd_full_dtheta": wb_bwd(0)}
 
 
 # the launches the MODEL makes: all T = 3 loop steps of an op in one launch, rows [T, B, ...] against the one shared
@@ -208,7 +211,8 @@ ST_STEPS_T = 3
 ST_STEPS_BYTES = {"crop_fwd_steps": 10000 + ST_STEPS_T * (24 + 3136),                    # canvas once, T x (theta, window out)
                   "crop_bwd_steps": 10000 + ST_STEPS_T * (3136 + 24 + 24),               # canvas once, T x (dwindow, theta, dtheta)
                   "compose_steps": ST_STEPS_T * (3136 + 24 + 8) + 10000,                 # T x (window, theta_inv, z, stop), canvas out
-                  "writeback_canvas_bwd_steps": 10000 + ST_STEPS_T * (3136 + 24 + 8 + 3136 + 24 + 4)}   # dcanvas once, T x (in, out)
+                  "writeback_canvas_bwd_steps": 10000 + ST_STEPS_T * (3136 + 24 + 8 + 3136 + 24 + 4),   # dcanvas once, T x (in, out)
+                  "writeback_canvas_bwd_analytic_steps": 10000 + ST_STEPS_T * (3136 + 24 + 8 + 3136 + 24 + 4)}
 
 
 def st_steps_kernels(B, dev, seed=2):
@@ -234,7 +238,10 @@ def st_steps_kernels(B, dev, seed=2):
                                                                   28, 28, 50, 50),
           "writeback_canvas_bwd_steps": lambda: ops.writeback_canvas_bwd_steps(win, thi, fields[0, 0], fields[0, 1], 2 * B, 0.99, dcanvas,
                                                                                dgen, dthi, dz, 28, 28, 50, 50, window_is_sigmoid=True,
-                                                                               axis_aligned_theta=True)}
+                                                                               axis_aligned_theta=True, reference_rounding=True),
+          "writeback_canvas_bwd_analytic_steps": lambda: ops.writeback_canvas_bwd_steps(
+              win, thi, fields[0, 0], fields[0, 1], 2 * B, 0.99, dcanvas, dgen, dthi, dz, 28, 28, 50, 50, window_is_sigmoid=True,
+              axis_aligned_theta=True)}
     return ks, live
 
 
@@ -259,7 +266,7 @@ def st_steps_summary(peaks, B, steps=20, warmup=5):
 # stopped images (30 % of the synthetic batch) never fetch their dCanvas rows.
 ST_NCU_TRAFFIC_B65536 = {"crop_fwd": 4 * (656.946e6 + 183.790e6), "crop_bwd": 862.487e6 + 5.773e6,
                          "writeback_canvas_fwd": 863.045e6 + 615.292e6,          # profiles/r1_wb_fwd_ncu_full.md
-                         "writeback_canvas_bwd": 606.693e6 + 187.272e6,          # profiles/r1_st_wb_bwd_axis_ncu_full.md
+                         "writeback_canvas_bwd_analytic": 606.693e6 + 187.272e6,  # profiles/r1_st_wb_bwd_axis_ncu_full.md
                          "writeback_canvas_bwd_full_dtheta": 606.910e6 + 186.340e6}
 
 

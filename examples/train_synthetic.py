@@ -28,13 +28,24 @@ def main():
     ap.add_argument("--every", type=int, default=500)
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--log", default=None)
+    ap.add_argument("--seed", type=int, default=0, help="initialisation, sampling noise and batch order")
+    ap.add_argument("--data", default="device", choices=["device", "oracle"],
+                    help="device: air_synth_canvases (generate_multi_image placement); oracle: the CPU generator "
+                         "oracle/train_convergence.py trains on (test infrastructure, used here only to repeat that run)")
+    ap.add_argument("--clean-gradient", action="store_true", help="reference_rounding=False (the fp64-like gradient)")
     a = ap.parse_args()
     data = import_module("tf-attend-infer-repeat_b200.data")
-    train, train_cnt = data.device_canvases(a.train_images, seed=0)
-    val, val_cnt = data.device_canvases(a.val_images, seed=12345)
+    if a.data == "oracle":
+        from oracle import air_oracle as O
+        train, train_cnt = (t.cuda() for t in O.synthetic_canvases(a.train_images, seed=0))
+        val, val_cnt = (t.cuda() for t in O.synthetic_canvases(a.val_images, seed=12345))
+    else:
+        train, train_cnt = data.device_canvases(a.train_images, seed=0)
+        val, val_cnt = data.device_canvases(a.val_images, seed=12345)
     ab.reset_variable_scopes()
     m = ab.AIRModel(train[:a.batch].clone(), train_cnt[:a.batch].clone(), train=True,
-                    annealing_schedules=data.TRAINING_ANNEALING, gemm_mode=a.gemm, seed=0, **data.TRAINING_HYPER)
+                    annealing_schedules=data.TRAINING_ANNEALING, gemm_mode=a.gemm, seed=a.seed, reference_rounding=not a.clean_gradient,
+                    **data.TRAINING_HYPER)
     ev = ab.AIRModel(val, val_cnt, train=False, reuse=True, annealing_schedules=data.TRAINING_ANNEALING,
                      gemm_mode=a.gemm, **data.TRAINING_HYPER)
     m.capture()
@@ -48,7 +59,7 @@ def main():
 
     emit(f"# CUDA training, batch {a.batch}, gemm {a.gemm}; columns: iteration  train_loss  train_acc  "
          f"val_acc(test mode)  val_acc_by_count(0/1/2)  seconds")
-    g = torch.Generator(device="cuda").manual_seed(1)
+    g = torch.Generator(device="cuda").manual_seed(1 + a.seed)
     t0 = time.time()
     loss_sum = torch.zeros((), device="cuda")
     acc_sum = torch.zeros((), device="cuda")

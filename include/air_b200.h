@@ -101,9 +101,20 @@ int air_st_writeback_canvas_fwd_steps(const float *windows, const float *theta_i
  *   AIR_WB_AXIS_ALIGNED_THETA  the caller builds theta_inv = [[1/s,0,-x/s],[0,1/s,-y/s]] (air_model.py:351-360) and
  *                              consumes only dtheta_inv[0], [2], [4], [5]; the gradients w.r.t. the structural zeros
  *                              ([1], [3]) are written as 0 for axis-aligned rows.  Enables the warp-specialised
- *                              kernel (28x28 window, 50x50 canvas); rows with shear/rotation still get all six. */
+ *                              kernel (28x28 window, 50x50 canvas); rows with shear/rotation still get all six.
+ *   AIR_WB_REFERENCE_ROUNDING  sum what the reference's fp32 autodiff sums (gradient subgraph of transformer.py:84-116 in
+ *                              model/air-model.meta): a canvas pixel outside the window meets one clipped border pixel
+ *                              twice, with the weights (v - i) and (i - v); the reference multiplies the upstream
+ *                              gradient into each corner term separately and the ~1e10 products of a lit, not yet
+ *                              reconstructed pixel (BCE gradient -x / (0 + 1e-9)) cancel only to rounding error.  The
+ *                              reference's training depends on these residues; without the flag
+ *                              such pixels are skipped as the exact zeros they are on paper (the fp64 gradient).  Per
+ *                              pixel the arithmetic is the graph's own (dz, dtheta_inv: all six entries); the order in
+ *                              which dwindow accumulates over pixels (unspecified in the reference: UnsortedSegmentSum)
+ *                              is fixed and deterministic.  28x28 windows on 50x50 canvases, dz required. */
 #define AIR_WB_SIGMOID_WINDOW 1
 #define AIR_WB_AXIS_ALIGNED_THETA 2
+#define AIR_WB_REFERENCE_ROUNDING 4
 int air_st_writeback_canvas_bwd(const float *window, const float *theta_inv, const float *z, const float *stop_new,
                                 float thr, const float *dcanvas, float *dwindow, float *dtheta_inv, float *dz,
                                 int flags, int64_t B, int wh, int ww, int ch, int cw, air_stream_t stream);

@@ -29,13 +29,14 @@ def main():
     ap.add_argument("--every", type=int, default=500)
     ap.add_argument("--threads", type=int, default=4)
     ap.add_argument("--log", default=None)
+    ap.add_argument("--seed", type=int, default=0, help="initialisation, sampling noise and batch order (0 = the committed run)")
     ap.add_argument("--save", default=None, help="write the final parameters (float16 .npz, reference variable names)")
     a = ap.parse_args()
     torch.set_num_threads(a.threads)
     torch.manual_seed(0)
     train, train_cnt = O.synthetic_canvases(a.train_images, seed=0)
     val, val_cnt = O.synthetic_canvases(a.val_images, seed=12345)
-    m = O.AIROracle(annealing_schedules=O.DEFAULT_ANNEALING, train=True, seed=0)
+    m = O.AIROracle(annealing_schedules=O.DEFAULT_ANNEALING, train=True, seed=a.seed)
     log = open(a.log, "w") if a.log else None
 
     def emit(s):
@@ -47,7 +48,7 @@ def main():
     emit(f"# oracle training, batch {a.batch}, {a.train_images} synthetic train canvases, {a.val_images} held out, "
          f"{a.threads} threads; columns: iteration  train_loss  train_acc  val_acc(test mode)  val_acc_by_count(0/1/2)  "
          f"z_pres_prior_log_odds  seconds")
-    g = torch.Generator().manual_seed(1)
+    g = torch.Generator().manual_seed(1 + a.seed)
     t0 = time.time()
     run_loss = run_acc = 0.0
     for it in range(a.iters + 1):
@@ -69,7 +70,7 @@ def main():
                          **{k: v.detach().numpy().astype(np.float16) for k, v in m.params.items()})
             break
         idx = torch.randint(0, a.train_images, (a.batch,), generator=g)
-        out, _ = m.train_step(train[idx], train_cnt[idx], O.make_noise(it, 3, a.batch))
+        out, _ = m.train_step(train[idx], train_cnt[idx], O.make_noise(it + 1_000_003 * a.seed, 3, a.batch))
         run_loss += float(out["loss"])
         run_acc += float(out["accuracy"])
 

@@ -57,7 +57,7 @@ def default_fixture(B, seed=0, T=3):
     return imgs, cnt, O.init_params(seed=seed), O.make_noise(seed, T, B)
 
 
-def make_pair(imgs, cnt, params, train=True, global_step=2000, gemm_mode="fp32", **hyper):
+def make_pair(imgs, cnt, params, train=True, global_step=2000, gemm_mode="fp32", reference_rounding=True, **hyper):
     """(oracle, cuda model) with identical parameters / hyper-parameters / global step."""
     import air_b200 as ab
     h = dict(O.DEFAULT_HYPER)
@@ -67,7 +67,7 @@ def make_pair(imgs, cnt, params, train=True, global_step=2000, gemm_mode="fp32",
     orc.global_step = global_step
     ab.reset_variable_scopes()
     m = ab.AIRModel(imgs.cuda(), cnt.cuda(), train=train, annealing_schedules=O.DEFAULT_ANNEALING, gemm_mode=gemm_mode,
-                    **{k: v for k, v in h.items()})
+                    reference_rounding=reference_rounding, **{k: v for k, v in h.items()})
     m.store.load_named({k: v.cuda() for k, v in params.items()})
     m.store.global_step = global_step
     return orc, m

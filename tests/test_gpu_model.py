@@ -112,14 +112,20 @@ def test_backward_schedule_realistic_poses_smooth_canvas_gradient(gemm_mode):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("reference_rounding", [False, True])
 @pytest.mark.parametrize("gemm_mode", EXACT_MODES)
-def test_gradient_adversarial_fixture_vs_fp64_truth(gemm_mode):
-    """Default init: uncovered lit pixels amplify rounding residues by up to 1e9, so fp32
-    implementations legitimately differ.  Check the CUDA gradient is as close to the fp64
-    truth (same op sequence in double) as the fp32 oracle is, within a factor."""
+def test_gradient_adversarial_fixture_vs_fp64_truth(gemm_mode, reference_rounding):
+    """Default init: uncovered lit pixels amplify the rounding residues of the out-of-window bilinear weights by up to
+    1e9, so the reference's fp32 gradient is dominated by them (the fp32 oracle is O(100) x |g64| away from the same op
+    sequence in double) and every summation order lands somewhere else.
+      reference_rounding=False: the analytic write-back backward drops those terms -- the CUDA gradient is at least as
+        close to the fp64 truth as the fp32 oracle is (within a factor);
+      reference_rounding=True (the default, what the reference trains on): the residues are there -- the CUDA gradient is
+        noise-dominated like the oracle's, and its distance from fp64 stays within the range the summation order spans
+        (torch's order in the oracle vs the graph's gradient-list order here: up to ~500 x, profiles/r2_reference_rounding.md)."""
     B = 32
     imgs, cnt, params, noise = default_fixture(B, seed=4)
-    orc, m = make_pair(imgs, cnt, params, train=True, gemm_mode=gemm_mode)
+    orc, m = make_pair(imgs, cnt, params, train=True, gemm_mode=gemm_mode, reference_rounding=reference_rounding)
     _, g32 = orc.loss_and_grads(imgs, cnt, noise)
     o64 = O.AIROracle(params={k: v.double() for k, v in params.items()}, annealing_schedules=O.DEFAULT_ANNEALING,
                       train=True, dtype=torch.float64)
@@ -129,8 +135,13 @@ def test_gradient_adversarial_fixture_vs_fp64_truth(gemm_mode):
     tot = lambda gd: torch.cat([gd[k].detach().cpu().double().reshape(-1) for k in g64])
     e_gpu = relnorm(tot(m.store.named_grads()), tot(g64))
     e_orc = relnorm(tot(g32), tot(g64))
-    print(f"adversarial fixture: |g_gpu-g64|/|g64| = {e_gpu:.3e}, |g_oracle32-g64|/|g64| = {e_orc:.3e}")
-    assert e_gpu < max(10 * e_orc, 1e-3)
+    print(f"adversarial fixture (reference_rounding={reference_rounding}): |g_gpu-g64|/|g64| = {e_gpu:.3e}, "
+          f"|g_oracle32-g64|/|g64| = {e_orc:.3e}")
+    assert e_orc > 1.0          # the reference arithmetic itself is residue-dominated on this fixture
+    if reference_rounding:
+        assert 1.0 < e_gpu < 1e4 * e_orc
+    else:
+        assert e_gpu < max(10 * e_orc, 1e-3) and e_gpu < 1.0
 
 
 @pytest.mark.parametrize("gemm_mode", EXACT_MODES)

@@ -22,6 +22,12 @@ Differences from the reference, by design:
     otherwise it is drawn with torch's CUDA generator into persistent buffers.
   * the image part of the LSTM input projection (x @ K[:2500]) is step-invariant
     (air_model.py:535: rnn_input is the raw image every step) and is computed once.
+
+``reference_rounding`` (default True): the write-back backward accumulates the gradient terms of canvas pixels OUTSIDE
+the attention window the way the reference's fp32 autodiff does -- four ~1e10 corner products per lit, not yet
+reconstructed pixel that cancel only to rounding error -- instead of dropping them as the exact zeros they are on paper.
+The reference's training depends on those residues (with the exactly-cancelled gradient the model never leaves loss
+~1900); False selects the analytic kernel (st_wb_bwd_axis), whose gradient is the fp64 one.
 """
 from __future__ import annotations
 
@@ -79,7 +85,7 @@ class AIRModel:
                  z_pres_prior_log_odds=-2.0, z_pres_temperature=1.0, stopping_threshold=0.99,
                  learning_rate=1e-3, gradient_clipping_norm=100.0, cnn=True, cnn_filters=8,
                  num_summary_images=60, train=False, reuse=False, scope="air",
-                 annealing_schedules=None, *, gemm_mode="fp32", seed=0, process_group=None):
+                 annealing_schedules=None, *, gemm_mode="fp32", seed=0, process_group=None, reference_rounding=True):
         if cnn and canvas_size != 50:
             raise ValueError("the reference's CNN front-end hard-codes 50x50 canvases (air_model.py:512, 533)")
         if cnn and cnn_filters != 8:
@@ -411,7 +417,8 @@ class AIRModel:
         ops.writeback_canvas_bwd_steps(w["recon"], w["theta_inv"], f0[C.F_Z], f0[C.F_STOP_NEW], C.NF * B,
                                        self.stopping_threshold, w["dcanvas"], vd["dgen"], w["dtheta_inv"], w["dz"],
                                        wsz, wsz, cs, cs, window_is_sigmoid=True,  # SigmoidGrad fused into the store
-                                       axis_aligned_theta=True)  # heads_bwd reads dtheta_inv[0,2,4,5] only
+                                       axis_aligned_theta=True,  # heads_bwd reads dtheta_inv[0,2,4,5] only
+                                       reference_rounding=self.reference_rounding)
         # ---- (2) VAE backward of all steps as one evaluation on T*B rows, then the crop backward per step
         def latent_bwd_steps():
             for t in range(T):

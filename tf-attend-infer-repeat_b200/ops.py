@@ -196,9 +196,9 @@ def st_backward_steps(U, theta, dout, dtheta, H, W, C_, oh, ow):
 
 
 def writeback_canvas_bwd_steps(windows, theta_inv, z0, stop0, step_stride, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw,
-                               window_is_sigmoid=False, axis_aligned_theta=False):
+                               window_is_sigmoid=False, axis_aligned_theta=False, reference_rounding=False):
     T, B = windows.shape[0], windows.shape[1]
-    flags = (1 if window_is_sigmoid else 0) | (2 if axis_aligned_theta else 0)
+    flags = (1 if window_is_sigmoid else 0) | (2 if axis_aligned_theta else 0) | (4 if reference_rounding else 0)
     check(lib().air_st_writeback_canvas_bwd_steps(ptr(windows), ptr(theta_inv), ptr(z0), ptr(stop0), int(step_stride), float(thr),
                                                   ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), flags, B, T, wh, ww, ch, cw,
                                                   stream()), "air_st_writeback_canvas_bwd_steps")
@@ -214,9 +214,10 @@ def writeback_canvas_fwd_steps(windows, theta_inv, z0, stop0, step_stride, thr, 
 
 
 def writeback_canvas_bwd(window, theta_inv, z, stop_new, thr, dcanvas, dwindow, dtheta_inv, dz, wh, ww, ch, cw,
-                         window_is_sigmoid=False, axis_aligned_theta=False):
-    """flags of include/air_b200.h: AIR_WB_SIGMOID_WINDOW = 1, AIR_WB_AXIS_ALIGNED_THETA = 2 (dtheta_inv[1], [3] := 0)."""
-    flags = (1 if window_is_sigmoid else 0) | (2 if axis_aligned_theta else 0)
+                         window_is_sigmoid=False, axis_aligned_theta=False, reference_rounding=False):
+    """flags of include/air_b200.h: AIR_WB_SIGMOID_WINDOW = 1, AIR_WB_AXIS_ALIGNED_THETA = 2 (dtheta_inv[1], [3] := 0),
+    AIR_WB_REFERENCE_ROUNDING = 4 (out-of-window pixels contribute their un-cancelled fp32 corner terms)."""
+    flags = (1 if window_is_sigmoid else 0) | (2 if axis_aligned_theta else 0) | (4 if reference_rounding else 0)
     check(lib().air_st_writeback_canvas_bwd(ptr(window), ptr(theta_inv), ptr(z), ptr(stop_new), float(thr),
                                             ptr(dcanvas), ptr(dwindow), ptr(dtheta_inv), ptr(dz), flags,
                                             window.shape[0], wh, ww, ch, cw, stream()), "air_st_writeback_canvas_bwd")
