@@ -153,6 +153,16 @@ def test_spiky_upstream_gradient_per_pixel_terms_are_the_graphs():
     resid = np.abs(dw.astype(np.float64) - cw)[L]
     assert (resid <= 512 * 2.0 ** -24 * terms[L] + 1e-4 * np.abs(cw[L]) + 1e-6).all()
     assert resid[:, ~inner].max() > 10.0                            # residues of the reference's magnitude are present
+    # ... the magnitude the reference graph's own accumulation order leaves (oracle_st_backward is bit-exact with the
+    # graph's UnsortedSegmentSum order): same order of magnitude, image by image in the median
+    up = (d * z[:, None, None]).astype(F)
+    oU, _ = C.st_backward(win.reshape(B, 28, 28, 1), thi.reshape(B, 2, 3), up.reshape(B, 50, 50, 1))
+    o_res = np.abs(oU.reshape(B, 28, 28).astype(np.float64) - cw)[L][:, ~inner]
+    ours, theirs = np.sqrt((resid[:, ~inner] ** 2).mean(1)), np.sqrt((o_res ** 2).mean(1))
+    ok = theirs > 1.0
+    ratio = np.median(ours[ok] / theirs[ok])
+    print("border residue rms, ours / graph order: median ratio", ratio, " (ours", np.median(ours[ok]), ", graph order", np.median(theirs[ok]), ")")
+    assert ok.sum() > 20 and 0.03 < ratio < 30.0
 
 
 def test_rotated_theta_takes_the_per_pixel_path():

@@ -1333,6 +1333,7 @@ __global__ void __launch_bounds__(kRefThreads, 8)
         if (ra >= rb) return;
         int icur = second ? sRow[ra].i1 : sRow[ra].i0;
         float s = t[icur];
+#pragma unroll 2
         for (int r = ra; r < rb; ++r) {
           const Ent re = sRow[r];
           const int ii = second ? re.i1 : re.i0;
