@@ -150,16 +150,18 @@ def gemm_roofline(B, mode, peaks, steps=20):
     kern = "gemm_simt<128,128,16,8,8> (fp32 FFMA, exact mode)" if mode == "fp32" else "gemm_tf32 (tcgen05)"
     return {"bound": "tensor", "achieved": round(tf, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
             "frac": round(tf / peak, 4),
-            # dram__bytes_read + write of one launch at B = 4096 from the ncu --set full capture in
-            # profiles/r1_gemm_tf32_big_ncu_full.md (C stays in L2 within one launch); scaled with B
-            "traffic": round(52.29e6 * B / 4096) if mode == "tf32" else None,
+            # traffic: NOT measured in this run -- dram__bytes_read + write of one launch at B = 4096 from the ncu --set full
+            # captures under profiles/ (C stays in L2 within one launch), scaled with B; null for other batches' kernels
+            "traffic": (round((51.28e6 + 1.94e6) * B / 4096) if mode == "tf32" else round((51.41e6 + 3.21e6) * B / 4096)
+                        if mode == "tf32x3" else None),
+            "traffic_source": "profiles/r2_gemm_pair_ncu_full.md (ncu capture of round 2, not this run)" if mode != "fp32" else None,
             "algorithmic_bytes": int(4 * (B * 2500 + 2500 * 1024 + B * 1024)),
-            "tensor_pipe_util_ncu": 0.349 if mode == "tf32" else None,
+            "tensor_pipe_active_ncu_r2_capture": 0.503 if mode == "tf32" else 0.442 if mode == "tf32x3" else None,
             "peak_source": peaks["source"], "kernel": kern,
             "shape": f"[{B},2500]x[2500,1024]", "ms": round(ms, 4),
-            "note": "peak = measured cuBLAS bf16 burst" + (" / 2 (TF32 dense estimate; ncu's UTCHMMA-TF32 path reports 34.9 % "
-                                                           "of its own peak at 365 TFLOP/s, i.e. the pipe peak is ~1.05 PFLOP/s "
-                                                           "and this frac is optimistic by ~1.3x)" if mode == "tf32" else
+            "note": "peak = measured cuBLAS bf16 burst" + (" / 2 (TF32 dense estimate; ncu of the CTA-pair kernel: tensor pipe active "
+                                                           "50 % of elapsed cycles at 512 TFLOP/s under the profiler, "
+                                                           "profiles/r2_gemm_pair_ncu_full.md)" if mode == "tf32" else
                                                            "; exact-fp32 SIMT mode cannot approach a tensor-core peak")}
 
 

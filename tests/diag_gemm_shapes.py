@@ -26,6 +26,11 @@ shapes = [  # name, M, N, K, tA, tB, cinit, bias, epi(aux)
     ("dW hid", 256, 320, TB, 1, 0, 0, 0, 0), ("dW Kh", 256, 1024, 2 * B, 1, 0, 0, 0, 0), ("dW Kx", 2500, 1024, B, 1, 0, 0, 0, 0),
 ]
 mult = {"fwd xK": 1, "dW Kx": 1}
+if os.environ.get("M_FULL", "0") != "0":   # the VAE GEMMs as the model runs them: once per step on T*B rows
+    vae = ("r1", "r2", "ml", "g1", "g2", "gm")
+    shapes = [(n, TB if (n.split()[1] in vae and not n.startswith("dW")) else M, N, Kd, tA, tB, ci, bi, epi)
+              for n, M, N, Kd, tA, tB, ci, bi, epi in shapes]
+    mult.update({n: 1 for n, *_ in shapes if n.split()[1] in vae})
 tot = 0.0
 print(f"{'gemm':18s} {'M':>6s} {'N':>5s} {'K':>6s}   us     TFLOP/s  x/step  us/step")
 for name, M, N, Kd, tA, tB, ci, bi, epi in shapes:

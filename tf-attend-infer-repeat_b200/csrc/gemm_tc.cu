@@ -208,6 +208,149 @@ __global__ void __launch_bounds__(kTcThreads)
   if (CL) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
 }
 
+// =========================================================================================
+// Persistent variant (plain TF32, no cluster): one CTA per SM (or two) walks tiles t = blockIdx.x, + gridDim.x, ... with
+//   * ONE operand ring that keeps running across tiles: the producer is already fetching the next tile's k-blocks while
+//     the last MMAs of the current tile execute, so only the first tile of a CTA pays the TMA round trip;
+//   * TWO accumulator stages in TMEM (2 x BN columns): the epilogue warps drain tile i (tcgen05.ld, Cinit / bias /
+//     activation, global stores) while the tensor core already accumulates tile i + 1 into the other stage
+//     (tmem_full / tmem_empty mbarriers, one phase bit per stage);
+//   * barrier init, TMEM allocation, descriptor prefetch and the PDL wait once per CTA instead of once per tile.
+// The short-K GEMMs of this model (K = 256 ... 784: 8 - 25 k-blocks per tile) spend as long in the epilogue as in the
+// main loop; this overlaps the two.  Tile order: n fastest (the CTAs of a wave share their A rows through L2).
+// =========================================================================================
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads)
+    gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p,
+                             int tiles_n, int tiles_mn, int tiles_total) {
+  constexpr uint32_t kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4, kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = tmem_cols_for(2 * BN, false);
+  const int kStages = p.stages;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], kTcThreads / 32 - 2);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+  pdl_sync();  // PDL: barriers, TMEM and descriptors were set up while the previous grid drained
+
+  // tile t -> (split, m tile, n tile), its k-block range
+  auto tile_coords = [&](int t, int &m0, int &n0, int &split, int &kb_begin, int &nkb) {
+    split = t / tiles_mn;
+    const int r = t - split * tiles_mn;
+    const int mt = r / tiles_n;
+    m0 = mt * kBM;
+    n0 = (r - mt * tiles_n) * BN;
+    kb_begin = split * p.kb_per_split;
+    nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (one thread) =================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+        int m0, n0, split, kb_begin, nkb;
+        tile_coords(t, m0, n0, split, kb_begin, nkb);
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait_spin(&empty_bar[s], ph ^ 1);
+          unsigned char *sa = tiles + s * kStageBytes, *sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[s], kStageBytes);
+          const int k0 = (kb_begin + i) * kBK;
+#pragma unroll
+          for (int pi = 0; pi < 4; ++pi) {
+            if (!A_MN) tma_load_2d(sa + pi * (32 * 128), &mapA, &full_bar[s], k0, m0 + pi * 32);      // box {32 k, 32 m}
+            else       tma_load_2d(sa + pi * (kBK * 128), &mapA, &full_bar[s], m0 + pi * 32, k0);     // box {32 m, 32 k}
+            if (!B_MN) {            // box {32 k, BN/4 n}
+              tma_load_2d(sb + pi * (BN / 4 * 128), &mapB, &full_bar[s], k0, n0 + pi * (BN / 4));
+            } else if (BN >= 128) {  // box {32 n, 32 k}: chunk pi
+              tma_load_2d(sb + pi * (kBK * 128), &mapB, &full_bar[s], n0 + pi * 32, k0);
+            } else {                // BN == 64: box {32 n, 16 k}: chunk pi/2, k-half pi%2
+              tma_load_2d(sb + (pi >> 1) * (kBK * 128) + (pi & 1) * (16 * 128), &mapB, &full_bar[s], n0 + (pi >> 1) * 32,
+                          k0 + (pi & 1) * 16);
+            }
+          }
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_adv = A_MN ? 1024 : 32;
+      constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_adv = B_MN ? 1024 : 32;
+      constexpr uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+        int m0, n0, split, kb_begin, nkb;
+        tile_coords(t, m0, n0, split, kb_begin, nkb);
+        mbar_wait_spin(&tmem_empty_bar[acc], acc_ph ^ 1);  // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_acc + acc * BN;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait_spin(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + s * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lt);
+            const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_d, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator of this tile complete
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue: TMEM -> registers -> global (8 warps), one tile behind the MMAs =================
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+      int m0, n0, split, kb_begin, nkb;
+      tile_coords(t, m0, n0, split, kb_begin, nkb);
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      tc_epilogue<BN, false>(p, tmem_acc + acc * BN, m0, n0, split, warp, lane, 1, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, kTmemCols);
+  }
+}
+
 // second pass of split-K: C = epi((Cinit + sum_s partial[s]) + bias), s in increasing order.
 // float4 per thread, splits loop unrolled 4x so the partial loads are in flight together.
 __global__ void __launch_bounds__(256)
@@ -324,6 +467,37 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, c
   return check_launch(X3 ? "gemm_tf32x3" : "gemm_tf32");
 }
 
+// Persistent launch: ctas_per_sm resident CTAs per SM (1: the whole shared memory as one deep ring; 2: two shallower
+// rings whose prologues / epilogues interleave), never more CTAs than tiles.
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc_persist(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, int ctas_per_sm, cudaStream_t s) {
+  auto kern = gemm_tf32_persist_kernel<BN, A_MN, B_MN>;
+  const size_t stage_bytes = static_cast<size_t>(kBM + BN) * kBK * 4;
+  const int max_stages = static_cast<int>(std::min<size_t>(kMaxStages, 200 * 1024 / stage_bytes));
+  const int tiles_n = (p.N + BN - 1) / BN, tiles_mn = tiles_n * ((p.M + kBM - 1) / kBM), total = tiles_mn * p.splits;
+  const size_t budget = (ctas_per_sm == 1 ? 200 : 100) * 1024;
+  int stages = std::max(2, std::min(static_cast<int>(budget / stage_bytes), max_stages));
+  if (tc_env().stages) stages = std::min(tc_env().stages, max_stages);
+  p.stages = stages;
+  p.chains = 1;
+  p.flags = tc_env().flags;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
+  const size_t smem_max = static_cast<size_t>(max_stages) * stage_bytes + 1024;
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = uint64_t(1) << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max));
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(gemm_tf32_persist): %s", cudaGetErrorString(e));
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  const int grid = std::min(total, sm_count() * ctas_per_sm);
+  AIR_LAUNCH(kern, grid, kTcThreads, smem, s, ma, mb, p, tiles_n, tiles_mn, total);
+  count_launch();
+  return check_launch("gemm_tf32_persist");
+}
+
 int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
                     int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s);
 
@@ -420,6 +594,29 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   // cluster barriers and the gang launch cost more than the operand traffic saves.  AIR_TC_CLUSTER=0/2 forces off/on.
   const int cl_env = tc_env().cluster;
   const bool cl = cl_env != 0 && (mt % 2 == 0) && (cl_env == 2 || p.kb_per_split >= 64);
+  // Persistent kernel (two TMEM accumulator stages: the epilogue of tile i overlaps the main loop of tile i + 1) for
+  // the plain-TF32 GEMMs whose tiles outnumber the resident CTAs.  AIR_TC_PERSIST: 0 = never, 1 / 2 = that many CTAs
+  // per SM wherever it applies, default = automatic.
+  if (!x3 && !cl && BN <= 128 && tc_env().persist != 0) {
+    const int64_t total = (BN == 128 ? tiles128 : tiles64) * splits;
+    const int per_sm = tc_env().persist > 0 ? std::min(tc_env().persist, 2) : 1;
+    // Automatic choice, from the per-shape measurements at the model's sizes (profiles/r2_gemm_shapes.md, M = 12288):
+    // one persistent CTA per SM wins where every CTA gets 2+ wide tiles AND the epilogue is heavy -- the dX GEMMs with
+    // a K-major weight operand (dX gm 49 -> 41 us, dX r2 30 -> 26, dX r1 39 -> 37) and the 784-wide gen_mean layer
+    // (43 -> 39); it loses 5-25 % on the 256-wide layers and on fwd r1 / g2 (the non-persistent kernel keeps two CTAs per
+    // SM there, whose prologues and epilogues already interleave).
+    const bool auto_on = BN == 128 && splits == 1 && total >= 2 * static_cast<int64_t>(sms) && p.num_kb >= 8 &&
+                         ((!b_mn && N >= 512) || N >= 768);
+    if (tc_env().persist > 0 || auto_on) {
+#define AIR_TC_PERSIST_DISPATCH(BNv)                                                                                             \
+  (a_mn ? (b_mn ? launch_tc_persist<BNv, true, true>(ma, mb, p, per_sm, s) : launch_tc_persist<BNv, true, false>(ma, mb, p, per_sm, s)) \
+        : (b_mn ? launch_tc_persist<BNv, false, true>(ma, mb, p, per_sm, s) : launch_tc_persist<BNv, false, false>(ma, mb, p, per_sm, s)))
+      rc = BN == 128 ? AIR_TC_PERSIST_DISPATCH(128) : AIR_TC_PERSIST_DISPATCH(64);
+#undef AIR_TC_PERSIST_DISPATCH
+      if (rc) return rc;
+      return splits > 1 ? launch_splitk_reduce(workspace, splits, C, Cinit, bias, aux, M, N, ldc, epi, epi_param, s) : AIR_OK;
+    }
+  }
 #define AIR_TC_DISPATCH2(BNv, CLv, X3v)                                                                                 \
   (a_mn ? (b_mn ? launch_tc<BNv, true, true, CLv, X3v>(ma, mb, p, s) : launch_tc<BNv, true, false, CLv, X3v>(ma, mb, p, s)) \
         : (b_mn ? launch_tc<BNv, false, true, CLv, X3v>(ma, mb, p, s) : launch_tc<BNv, false, false, CLv, X3v>(ma, mb, p, s)))

@@ -298,14 +298,16 @@ inline int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1
 //   AIR_TC_CLUSTER  0 = never, 2 = always multicast pairs (one-CTA kernel)
 //   AIR_TC_CHAINS   hi*hi accumulator chains of the X3 mode (1..3)
 //   AIR_TC_PAIR     0 = never use the cta_group::2 kernel, 128 / 256 = force that pair-tile width, 1 = automatic
+//   AIR_TC_PERSIST  0 = never use the persistent one-CTA kernel, 1 / 2 = use it everywhere with that many CTAs per SM
 struct TcEnv {
-  int stages = 0, bn = 0, cluster = 1, chains = 3, pair = 1, flags = 0;
+  int stages = 0, bn = 0, cluster = 1, chains = 3, pair = 1, flags = 0, persist = -1;
   TcEnv() {
     if (const char *e = getenv("AIR_TC_STAGES")) stages = std::max(1, atoi(e));
     if (const char *e = getenv("AIR_TC_BN")) bn = atoi(e);
     if (const char *e = getenv("AIR_TC_CLUSTER")) cluster = atoi(e);
     if (const char *e = getenv("AIR_TC_PAIR")) pair = atoi(e);
     if (const char *e = getenv("AIR_TC_FLAGS")) flags = atoi(e);
+    if (const char *e = getenv("AIR_TC_PERSIST")) persist = atoi(e);
     if (const char *e = getenv("AIR_TC_CHAINS")) chains = std::max(1, std::min(atoi(e), kMaxChains));
   }
 };
