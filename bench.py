@@ -473,7 +473,11 @@ def main():
     ap.add_argument("--no-convergence", action="store_true", dest="no_convergence",
                     help="skip the 25k-iteration training runs that ride along on the single-GPU train line (~40 s)")
     ap.add_argument("--cnn", action="store_true", help="train/infer with the CNN front-end (AIRModel(cnn=True)); not the headline config")
+    ap.add_argument("--convergence-only", action="store_true", dest="convergence_only", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.convergence_only:
+        print(json.dumps(training_convergence()), flush=True)
+        return 0
     args.warmup = max(args.warmup, 3)
     peaks = measured_peaks()
 
@@ -523,7 +527,15 @@ def main():
                 line["inference_c5"] = {"error": str(e)[:200]}
             if not args.no_convergence:
                 try:  # does the step being timed LEARN?  (the reference's configs[0] schedule, batch 64, 25k iterations: ~18 s per seed)
-                    line["training_convergence"] = training_convergence()
+                    # in a fresh process: the run is independent of whatever the measurements above left behind (graphs,
+                    # allocator pools), and a failure there cannot take the bench line with it
+                    import subprocess
+                    import torch
+                    torch.cuda.empty_cache()
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--convergence-only"], capture_output=True, text=True,
+                                       timeout=300)
+                    sys.stderr.write(r.stderr[-2000:])
+                    line["training_convergence"] = json.loads(r.stdout.strip().splitlines()[-1])
                 except Exception as e:
                     line["training_convergence"] = {"error": str(e)[:200]}
     if rank == 0:

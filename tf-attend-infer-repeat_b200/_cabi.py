@@ -139,10 +139,19 @@ def declared_symbols():
     return list(_SIGS.keys())
 
 
+_DEBUG_CAPTURE = os.environ.get("AIR_DEBUG_CAPTURE", "0") != "0"
+
+
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = lib().air_last_error().decode("utf-8", "replace")
         raise AirError(f"{what} failed with code {code}: {msg}")
+    if _DEBUG_CAPTURE:   # diagnostics: name the first call after which the stream's capture has been invalidated
+        import torch
+        try:
+            torch.cuda.is_current_stream_capturing()
+        except Exception as e:
+            raise AirError(f"stream capture is invalid after {what}: {e}") from None
 
 
 def ptr(t):

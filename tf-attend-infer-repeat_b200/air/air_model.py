@@ -558,8 +558,9 @@ class AIRModel:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
-        with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
+        # thread_local: other host threads (NCCL's watchdog, a data-feeding thread, a clock sampler) may touch the CUDA API
+        # while this thread captures; only this thread's calls belong to the graph
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._draw_noise(); self._forward()
             if self.train:
                 self._backward(); self._apply_gradients()

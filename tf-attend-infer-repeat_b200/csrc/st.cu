@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(kFwdThreads)
             const int r = q / OW, c = q - r * OW;
             if (sepi) {
               const Ent ce = sCol[i * OW + c], re = sRow[i * OH + r];
-              // clipped on both axes: the four products cancel to exactly +0 (same bits as the full formula)
-              v = (ce.i0 == ce.i1 && re.i0 == re.i1) ? 0.0f : bilerp(sU + i * HW, ce, re);
+              // clipped ROW: both corner rows are the same source row with weights w and -w, so in the order of the
+              // add_n (:116) the first two products cancel to +0 and then the last two do: exactly +0, the same bits as
+              // the full formula.  (A clipped COLUMN alone leaves the residue ((A + B) - A) - B, which is computed.)
+              v = (re.i0 == re.i1) ? 0.0f : bilerp(sU + i * HW, ce, re);
             } else {
               Ent ce, re;
               float xt, yt;
@@ -312,8 +314,8 @@ __global__ void __launch_bounds__(kFwdThreads)
             const int r = q / OW, c = q - r * OW;
             if (sepi) {
               const Ent ce = sCol[slot * OW + c], re = sRow[slot * OH + r];
-              // clipped on both axes: the four products cancel to exactly +0 (same bits as the full formula)
-              v = (ce.i0 == ce.i1 && re.i0 == re.i1) ? 0.0f : bilerp(sU + slot * HW, ce, re);
+              // clipped ROW: exactly +0, the same bits as the full formula (see st_fwd_staged)
+              v = (re.i0 == re.i1) ? 0.0f : bilerp(sU + slot * HW, ce, re);
             } else {
               Ent ce, re;
               float xt, yt;
