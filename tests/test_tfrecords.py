@@ -271,9 +271,9 @@ def test_indexed_reader_reads_the_references_own_file(tmp_path):
 
 
 def test_indexed_reader_throughput(tmp_path):
-    """The batched reader is a memory-bandwidth job, not a per-record Python loop: >= 0.5 M images/s even on this
-    container's few cores (the pure-Python decoder it replaces: ~20 k images/s); the figure on the GPU box's host is
-    recorded in profiles/ (tests/diag_loader.py)."""
+    """The batched reader is a memory-bandwidth job, not a per-record Python loop.  Measured against the per-record
+    decoder it replaces ON THE SAME MACHINE STATE (so the bar holds on a loaded container): >= 10 x; on an idle
+    8-core container it does 1.0-1.3 M images/s against ~20 k (profiles/r2_loader.txt has the GPU box's figure)."""
     import time
     images, indices, positions, boxes, labels, digits = _dataset(n=64, seed=3)
     tfr.write_to_records(str(tmp_path / "c"), images * 64, indices * 64, positions * 64, boxes * 64, labels * 64, digits * 64)
@@ -285,5 +285,13 @@ def test_indexed_reader_throughput(tmp_path):
     for im, dg in it:
         n += len(dg)
     rate = n / (time.perf_counter() - t0)
-    print(f"TFRecordFile.batches: {rate / 1e6:.2f} M images/s")
-    assert rate > 0.5e6
+    t0, m = time.perf_counter(), 0
+    for rec in tfr.iter_records(str(tmp_path / "c.tfrecords")):
+        ex = tfr.decode_example(rec)
+        np.frombuffer(ex["image"], np.float32).copy()
+        m += 1
+        if m == 1024:
+            break
+    per_record = m / (time.perf_counter() - t0)
+    print(f"TFRecordFile.batches: {rate / 1e6:.2f} M images/s; per-record Python decoder: {per_record / 1e3:.1f} k images/s")
+    assert rate > 10 * per_record

@@ -532,7 +532,7 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   const bool can_split = (N % 4 == 0) && workspace != nullptr && aligned16(workspace);
   const int64_t ws_splits = can_split ? ws_floats / (static_cast<int64_t>(M) * N) : 1;
   auto want_splits = [&](int64_t tiles) {
-    int sp = static_cast<int>(std::min<int64_t>((2 * sms + tiles - 1) / tiles, p.num_kb / 8));
+    int sp = static_cast<int>(std::min<int64_t>((tc_env().split_waves * sms + tiles - 1) / tiles, p.num_kb / 8));
     sp = static_cast<int>(std::min<int64_t>(sp, ws_splits));
     return std::max(1, std::min(sp, 32));
   };
