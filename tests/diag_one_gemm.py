@@ -1,10 +1,30 @@
-import os, sys, torch
+"""Diagnostic: ONE GEMM shape of the train step, a few launches (for ncu captures).
+SHAPE="name" (a row of tests/diag_gemm_shapes.py, default "dX gm dsp") MODE=tf32|tf32x3 M_ROWS=12288"""
+import os
+import sys
+
+import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import air_b200 as ab
-from air_b200 import ops
-M, N, Kd = 4096, 512, 256
-A = torch.randn(M, Kd, device="cuda"); W = torch.randn(Kd, N, device="cuda"); b = torch.randn(N, device="cuda")
+import air_b200 as ab  # noqa: E402
+from air_b200 import ops  # noqa: E402
+
+SHAPES = {  # name: N, K, tA, tB, cinit, bias, epi
+    "fwd r1 softplus": (512, 784, 0, 0, 0, 1, 2), "fwd gm": (784, 512, 0, 0, 0, 1, 0), "dX gm dsp": (512, 784, 0, 1, 0, 0, 4),
+    "dX r1": (784, 512, 0, 1, 0, 0, 0), "fwd r2 softplus": (256, 512, 0, 0, 0, 1, 2), "fwd hKh": (1024, 256, 0, 0, 1, 1, 0),
+}
+name = os.environ.get("SHAPE", "dX gm dsp")
+N, Kd, tA, tB, ci, bi, epi = SHAPES[name]
+M = int(os.environ.get("M_ROWS", "12288"))
+mode = ab._cabi.GEMM_MODES[os.environ.get("MODE", "tf32")]
+ws = torch.zeros(16 << 20, device="cuda")
+A = torch.randn(M, Kd, device="cuda")
+Bm = torch.randn((N, Kd) if tB else (Kd, N), device="cuda")
 out = torch.empty(M, N, device="cuda")
+Cinit = torch.randn(M, N, device="cuda") if ci else None
+bias = torch.randn(N, device="cuda") if bi else None
+aux = torch.rand(M, N, device="cuda") if epi in (3, 4) else None
 for _ in range(6):
-    ops.gemm(A, W, out, bias=b, epi=2, mode=1)
+    ops.gemm(A, Bm, out, Cinit=Cinit, bias=bias, aux=aux, tA=bool(tA), tB=bool(tB), epi=epi, mode=mode, ws=ws)
 torch.cuda.synchronize()
+print(name, M, N, Kd, "done")
