@@ -351,6 +351,150 @@ __global__ void __launch_bounds__(kTcThreads)
   }
 }
 
+// =========================================================================================
+// Persistent kernel on 2 x 2 CLUSTERS with TMA multicast (plain TF32, 128 x 128 tiles).
+// The short-K GEMMs of this model are bound by L2 -> SM operand traffic: with fp32 operands a 128 x 128 tile moves
+// 32 KB per k-block for 1 MFLOP (profiles/r2_gemm_short_k_ncu_full.md: 340 MB through the fabric at ~7 TB/s while DRAM
+// supplies 65 MB, tensor pipe 20 %).  Here four CTAs own a 256 x 256 block of the output as 2 x 2 tiles of 128 x 128:
+// the two CTAs of a block ROW need the same A rows -- each loads half of that A tile and multicasts it to both; the two
+// CTAs of a block COLUMN need the same B columns -- likewise.  Every SM then receives its full 32 KB per k-block but only
+// 16 KB of it cross the fabric on its behalf: half the L2 -> SM bytes per FLOP of the one-CTA kernel, the traffic of a
+// 256 x 256 tile with the scheduling granularity of 128 x 128 ones.  A stage may be refilled once the three CTAs its
+// loads write to (self, row peer, column peer) have consumed it: the empty barriers count three multicast commits.
+// Persistence and the two TMEM accumulator stages are those of gemm_tf32_persist_kernel; the cluster walks block
+// g = cluster id, + number of clusters, ...; tiles outside the matrix (odd tile counts) load zeros and store nothing.
+// =========================================================================================
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads)
+    gemm_tf32_cluster4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p,
+                              int blocks_n, int blocks_total) {
+  constexpr int BN = 128;
+  constexpr uint32_t kABytes = kBM * kBK * 4, kBBytes = BN * kBK * 4, kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = tmem_cols_for(2 * BN, false);
+  const int kStages = p.stages;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // 0..3: (block row, block column) = (crank >> 1, crank & 1)
+  const int rm = static_cast<int>(crank >> 1), rn = static_cast<int>(crank & 1);
+  const uint16_t mask_a = static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 1u)));   // the CTAs that share my A rows
+  const uint16_t mask_b = static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2u)));   // ... my B columns
+  const uint16_t mask_done = static_cast<uint16_t>(mask_a | mask_b);                     // whom my loads write to
+  const int cluster_id = blockIdx.x >> 2, n_clusters = gridDim.x >> 2;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 3);  // self + row peer + column peer
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], kTcThreads / 32 - 2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+  cluster_sync_all();  // every CTA's barriers exist before anything is multicast to them
+  pdl_sync();          // PDL: barriers, TMEM and descriptors were set up while the previous grid drained
+
+  auto block_coords = [&](int g, int &m0, int &n0) {
+    const int gm = g / blocks_n, gn = g - gm * blocks_n;
+    m0 = (2 * gm + rm) * kBM;
+    n0 = (2 * gn + rn) * BN;
+  };
+  const int nkb = p.num_kb;
+
+  if (warp == 0) {
+    // ================= TMA producer (one thread): my half of my A tile -> row pair, my half of my B tile -> column pair
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int g = cluster_id; g < blocks_total; g += n_clusters) {
+        int m0, n0;
+        block_coords(g, m0, n0);
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait_spin(&empty_bar[s], ph ^ 1);
+          unsigned char *sa = tiles + s * kStageBytes, *sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[s], kStageBytes);  // both halves of both tiles land here (two of them from the peers)
+          const int k0 = i * kBK;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int pa = 2 * rn + h;  // quarter boxes of the A tile this CTA fetches (its row peer fetches the others)
+            if (!A_MN) tma_load_2d_mc(sa + pa * (32 * 128), &mapA, &full_bar[s], k0, m0 + pa * 32, mask_a);
+            else       tma_load_2d_mc(sa + pa * (kBK * 128), &mapA, &full_bar[s], m0 + pa * 32, k0, mask_a);
+            const int pb = 2 * rm + h;  // ... of the B tile (its column peer fetches the others)
+            if (!B_MN) tma_load_2d_mc(sb + pb * (BN / 4 * 128), &mapB, &full_bar[s], k0, n0 + pb * (BN / 4), mask_b);
+            else       tma_load_2d_mc(sb + pb * (kBK * 128), &mapB, &full_bar[s], n0 + pb * 32, k0, mask_b);
+          }
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_adv = A_MN ? 1024 : 32;
+      constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_adv = B_MN ? 1024 : 32;
+      constexpr uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      for (int g = cluster_id; g < blocks_total; g += n_clusters) {
+        mbar_wait_spin(&tmem_empty_bar[acc], acc_ph ^ 1);  // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_acc + acc * BN;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait_spin(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + s * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lt);
+            const uint64_t db = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_d, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_mc(&empty_bar[s], mask_done);  // this stage of mine is free for me and for the peers that write into it
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator of this tile complete
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (8 warps), one tile behind the MMAs =================
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int g = cluster_id; g < blocks_total; g += n_clusters) {
+      int m0, n0;
+      block_coords(g, m0, n0);
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      if (m0 < p.M && n0 < p.N) tc_epilogue<BN, false>(p, tmem_acc + acc * BN, m0, n0, 0, warp, lane, 1, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, kTmemCols);
+  }
+  cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory or signal its barriers
+}
+
 // second pass of split-K: C = epi((Cinit + sum_s partial[s]) + bias), s in increasing order.
 // float4 per thread, splits loop unrolled 4x so the partial loads are in flight together.
 __global__ void __launch_bounds__(256)
@@ -498,6 +642,55 @@ static int launch_tc_persist(const CUtensorMap &ma, const CUtensorMap &mb, TcPar
   return check_launch("gemm_tf32_persist");
 }
 
+// 2 x 2 cluster launch: as many clusters as the device can keep resident (one CTA per SM: the whole shared memory as one
+// six-stage ring), never more than there are 256 x 256 blocks.
+template <bool A_MN, bool B_MN>
+static int launch_tc_cluster4(const CUtensorMap &ma, const CUtensorMap &mb, TcParams p, cudaStream_t s) {
+  auto kern = gemm_tf32_cluster4_kernel<A_MN, B_MN>;
+  constexpr int BN = 128;
+  const size_t stage_bytes = static_cast<size_t>(kBM + BN) * kBK * 4;
+  const int max_stages = static_cast<int>(std::min<size_t>(kMaxStages, 200 * 1024 / stage_bytes));
+  int stages = max_stages;
+  if (tc_env().stages) stages = std::min(tc_env().stages, max_stages);
+  p.stages = std::max(2, stages);
+  p.chains = 1;
+  p.flags = tc_env().flags;
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
+  const size_t smem_max = static_cast<size_t>(max_stages) * stage_bytes + 1024;
+  const int blocks_n = ((p.N + BN - 1) / BN + 1) / 2, blocks_m = ((p.M + kBM - 1) / kBM + 1) / 2, total = blocks_n * blocks_m;
+  static std::atomic<uint64_t> configured{0};
+  static int max_clusters[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = uint64_t(1) << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max));
+    AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(gemm_tf32_cluster4): %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem_max;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    AIR_REQUIRE(e == cudaSuccess && n > 0, AIR_ERR_CUDA, "cudaOccupancyMaxActiveClusters(gemm_tf32_cluster4): %s (%d)",
+                cudaGetErrorString(e), n);
+    max_clusters[dev & 63] = n;
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  const int clusters = std::min(total, max_clusters[dev & 63]);
+  cudaError_t e = launch_cluster_pdl(kern, dim3(4 * clusters), dim3(kTcThreads), smem, s, dim3(4, 1, 1), ma, mb, p, blocks_n, total);
+  AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "gemm_tf32_cluster4 launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return check_launch("gemm_tf32_cluster4");
+}
+
 int gemm_fp32_exact(const float *A, const float *B, float *C, const float *Cinit, const float *bias, const float *aux,
                     int M, int N, int K, int lda, int ldb, int ldc, int tA, int tB, int epi, float epi_param, cudaStream_t s);
 
@@ -597,6 +790,17 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
   // Persistent kernel (two TMEM accumulator stages: the epilogue of tile i overlaps the main loop of tile i + 1) for
   // the plain-TF32 GEMMs whose tiles outnumber the resident CTAs.  AIR_TC_PERSIST: 0 = never, 1 / 2 = that many CTAs
   // per SM wherever it applies, default = automatic.
+  // 2 x 2 multicast clusters (AIR_TC_CLUSTER4: 0 = never, 1 = wherever it applies; default = automatic)
+  if (!x3 && !cl && BN == 128 && splits == 1 && tc_env().cluster4 != 0) {
+    const int64_t blocks4 = static_cast<int64_t>((mt + 1) / 2) * (((N + 127) / 128 + 1) / 2);
+    const bool auto_on = false;
+    if (tc_env().cluster4 > 0 || auto_on) {
+      (void)blocks4;
+      rc = a_mn ? (b_mn ? launch_tc_cluster4<true, true>(ma, mb, p, s) : launch_tc_cluster4<true, false>(ma, mb, p, s))
+                : (b_mn ? launch_tc_cluster4<false, true>(ma, mb, p, s) : launch_tc_cluster4<false, false>(ma, mb, p, s));
+      return rc;
+    }
+  }
   if (!x3 && !cl && BN <= 128 && tc_env().persist != 0) {
     const int64_t total = (BN == 128 ? tiles128 : tiles64) * splits;
     const int per_sm = tc_env().persist > 0 ? std::min(tc_env().persist, 2) : 1;

@@ -300,7 +300,7 @@ inline int make_tmap(CUtensorMap *map, const float *base, int64_t d0, int64_t d1
 //   AIR_TC_PAIR     0 = never use the cta_group::2 kernel, 128 / 256 = force that pair-tile width, 1 = automatic
 //   AIR_TC_PERSIST  0 = never use the persistent one-CTA kernel, 1 / 2 = use it everywhere with that many CTAs per SM
 struct TcEnv {
-  int stages = 0, bn = 0, cluster = 1, chains = 3, pair = 1, flags = 0, persist = -1, split_waves = 2;
+  int stages = 0, bn = 0, cluster = 1, chains = 3, pair = 1, flags = 0, persist = -1, split_waves = 2, cluster4 = -1;
   TcEnv() {
     if (const char *e = getenv("AIR_TC_STAGES")) stages = std::max(1, atoi(e));
     if (const char *e = getenv("AIR_TC_BN")) bn = atoi(e);
@@ -308,6 +308,7 @@ struct TcEnv {
     if (const char *e = getenv("AIR_TC_PAIR")) pair = atoi(e);
     if (const char *e = getenv("AIR_TC_FLAGS")) flags = atoi(e);
     if (const char *e = getenv("AIR_TC_PERSIST")) persist = atoi(e);
+    if (const char *e = getenv("AIR_TC_CLUSTER4")) cluster4 = atoi(e);
     if (const char *e = getenv("AIR_TC_SPLIT_WAVES")) split_waves = std::max(1, atoi(e));
     if (const char *e = getenv("AIR_TC_CHAINS")) chains = std::max(1, std::min(atoi(e), kMaxChains));
   }
