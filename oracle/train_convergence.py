@@ -20,6 +20,32 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import air_oracle as O   # noqa: E402
 
 
+def _use_graph_order():
+    """transformer.py:56-117 with the four gathers expressed as ONE gather of the concatenated index list: autograd then
+    accumulates their gradients as one list in the order a | b | c | d -- the order of the reference graph's
+    gradients/concat -> UnsortedSegmentSum (TensorFlow's CPU kernel is sequential).  Forward values are bit-identical."""
+    def interpolate(im, x, y, out_size):
+        num_batch, height, width, channels = im.shape
+        dtype = im.dtype
+        oh, ow = out_size
+        x = (x + 1.0) * (torch.tensor(float(width), dtype=dtype) - 1.001) / 2.0
+        y = (y + 1.0) * (torch.tensor(float(height), dtype=dtype) - 1.001) / 2.0
+        x0 = torch.floor(x).to(torch.int64); x1 = x0 + 1
+        y0 = torch.floor(y).to(torch.int64); y1 = y0 + 1
+        x0, x1 = torch.clamp(x0, 0, width - 1), torch.clamp(x1, 0, width - 1)
+        y0, y1 = torch.clamp(y0, 0, height - 1), torch.clamp(y1, 0, height - 1)
+        base = (torch.arange(num_batch, dtype=torch.int64) * (width * height)).repeat_interleave(oh * ow)
+        idx = torch.cat([base + y0 * width + x0, base + y1 * width + x0, base + y0 * width + x1, base + y1 * width + x1])
+        vals = im.reshape(-1, channels)[idx]
+        n = x.numel()
+        Ia, Ib, Ic, Id = vals[:n], vals[n:2 * n], vals[2 * n:3 * n], vals[3 * n:]
+        x0_f, x1_f, y0_f, y1_f = x0.to(dtype), x1.to(dtype), y0.to(dtype), y1.to(dtype)
+        wa = ((x1_f - x) * (y1_f - y)).unsqueeze(1); wb = ((x1_f - x) * (y - y0_f)).unsqueeze(1)
+        wc = ((x - x0_f) * (y1_f - y)).unsqueeze(1); wd = ((x - x0_f) * (y - y0_f)).unsqueeze(1)
+        return ((wa * Ia + wb * Ib) + wc * Ic) + wd * Id
+    O._interpolate = interpolate
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=25000)
@@ -30,10 +56,15 @@ def main():
     ap.add_argument("--threads", type=int, default=4)
     ap.add_argument("--log", default=None)
     ap.add_argument("--seed", type=int, default=0, help="initialisation, sampling noise and batch order (0 = the committed run)")
+    ap.add_argument("--order", default="torch", choices=["torch", "graph"],
+                    help="accumulation order of the gather gradients in _interpolate: torch = four buffers (autograd's own), "
+                         "graph = ONE list a|b|c|d as the reference graph's gradients/concat -> UnsortedSegmentSum does")
     ap.add_argument("--save", default=None, help="write the final parameters (float16 .npz, reference variable names)")
     a = ap.parse_args()
     torch.set_num_threads(a.threads)
     torch.manual_seed(0)
+    if a.order == "graph":
+        _use_graph_order()
     train, train_cnt = O.synthetic_canvases(a.train_images, seed=0)
     val, val_cnt = O.synthetic_canvases(a.val_images, seed=12345)
     m = O.AIROracle(annealing_schedules=O.DEFAULT_ANNEALING, train=True, seed=a.seed)
