@@ -33,6 +33,8 @@ def main():
                     help="device: air_synth_canvases (generate_multi_image placement); oracle: the CPU generator "
                          "oracle/train_convergence.py trains on (test infrastructure, used here only to repeat that run)")
     ap.add_argument("--clean-gradient", action="store_true", help="reference_rounding=False (the fp64-like gradient)")
+    ap.add_argument("--skip-nonfinite", action="store_true",
+                    help="skip optimisation steps with a non-finite gradient norm (the reference would go NaN for good)")
     a = ap.parse_args()
     data = import_module("tf-attend-infer-repeat_b200.data")
     if a.data == "oracle":
@@ -45,6 +47,7 @@ def main():
     ab.reset_variable_scopes()
     m = ab.AIRModel(train[:a.batch].clone(), train_cnt[:a.batch].clone(), train=True,
                     annealing_schedules=data.TRAINING_ANNEALING, gemm_mode=a.gemm, seed=a.seed, reference_rounding=not a.clean_gradient,
+                    skip_nonfinite_updates=a.skip_nonfinite,
                     **data.TRAINING_HYPER)
     ev = ab.AIRModel(val, val_cnt, train=False, reuse=True, annealing_schedules=data.TRAINING_ANNEALING,
                      gemm_mode=a.gemm, **data.TRAINING_HYPER)

@@ -318,6 +318,14 @@ int air_reduce_rows(const float *partials, int R, int stride, int n, float *out,
 int64_t air_adam_workspace(int64_t n);
 int air_adam_step(float *params, const float *grads, float *m, float *v, float *state, float clip_norm, float beta1,
                   float beta2, float epsilon, float grad_scale, float *workspace, int64_t n, air_stream_t stream);
+/* The same with flags.  AIR_ADAM_SKIP_NONFINITE: when the global gradient norm is not finite the step is a no-op
+ * (parameters, Adam slots, beta powers and global_step untouched; state[3] = the norm, state[5] += 1 counts the skip).
+ * The reference has no such guard: there an overflowed gradient (a window that collapsed to ~1e-14 of the canvas makes
+ * the un-cancelled corner products of air/transformer.py:108-116 exceed fp32) turns every variable into NaN for good. */
+#define AIR_ADAM_SKIP_NONFINITE 1
+int air_adam_step_ex(float *params, const float *grads, float *m, float *v, float *state, float clip_norm, float beta1,
+                     float beta2, float epsilon, float grad_scale, float *workspace, int64_t n, int flags,
+                     air_stream_t stream);
 
 /* air_model.py:94-121: value = init * factor^(step/iters) [floor if staircase], clamped to
  * [min,max] (NaN = no bound), optional log(value + 1e-9); step read from adam state[2].

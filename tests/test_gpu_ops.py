@@ -243,6 +243,32 @@ def test_adam_step_matches_tf_semantics():
     np.testing.assert_allclose(st.state[:2].cpu().numpy(), [0.9 ** 4, 0.999 ** 4], rtol=1e-6)
 
 
+def test_adam_step_skips_a_non_finite_gradient_only_when_asked():
+    """AIR_ADAM_SKIP_NONFINITE: an overflowed gradient (inf - inf in the un-cancelled corner products of a collapsed window)
+    leaves parameters, Adam slots, beta powers and global_step untouched and is counted; without the flag the step does
+    what the reference's clip_by_global_norm + ApplyAdam do -- NaN everywhere."""
+    st = ab.ParamStore(DEV, 2500, 784, 256, 64, 50, (512, 256), (256, 512), seed=2)
+    st.state[4] = 1e-4
+    ws = torch.zeros(int(K.lib().air_adam_workspace(st.n)), device=DEV)
+    st.grad.normal_()
+    ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, 1.0, 0.9, 0.999, 1e-8, 1.0, ws, skip_nonfinite=True)
+    before = (st.flat.clone(), st.adam_m.clone(), st.adam_v.clone(), st.state.clone())
+    assert st.global_step == 1 and st.state[5].item() == 0
+    for bad in (float("inf"), float("nan")):
+        st.grad.normal_()
+        st.grad[12345] = bad
+        ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, 1.0, 0.9, 0.999, 1e-8, 1.0, ws, skip_nonfinite=True)
+        assert torch.equal(st.flat, before[0]) and torch.equal(st.adam_m, before[1]) and torch.equal(st.adam_v, before[2])
+        assert torch.equal(st.state[:3], before[3][:3]) and not torch.isfinite(st.state[3])
+    assert st.state[5].item() == 2 and st.global_step == 1
+    st.grad.normal_()   # a finite gradient afterwards: business as usual
+    ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, 1.0, 0.9, 0.999, 1e-8, 1.0, ws, skip_nonfinite=True)
+    assert st.global_step == 2 and torch.isfinite(st.flat).all() and not torch.equal(st.flat, before[0])
+    st.grad[7] = float("nan")
+    ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, 1.0, 0.9, 0.999, 1e-8, 1.0, ws)
+    assert not torch.isfinite(st.flat).any() and st.global_step == 3   # the reference's behaviour: the NaN norm reaches every variable
+
+
 def test_anneal_kernel():
     st = torch.zeros(8, device=DEV)
     out = torch.zeros(1, device=DEV)

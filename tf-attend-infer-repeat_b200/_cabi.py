@@ -57,6 +57,7 @@ _SIGS = {
     "air_colsum": (ctypes.c_int, [_c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_adam_workspace": (ctypes.c_int64, [ctypes.c_int64]),
     "air_adam_step": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float] * 5 + [_c_f, ctypes.c_int64, _c_f]),
+    "air_adam_step_ex": (ctypes.c_int, [_c_f] * 5 + [ctypes.c_float] * 5 + [_c_f, ctypes.c_int64, ctypes.c_int, _c_f]),
     "air_anneal": (ctypes.c_int, [_c_f] + [ctypes.c_float] * 3 + [ctypes.c_int] + [ctypes.c_float] * 2 +
                    [ctypes.c_int, _c_f, _c_f]),
     "air_colsum_multi_workspace": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),

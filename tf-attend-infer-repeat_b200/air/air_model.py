@@ -28,6 +28,11 @@ the attention window the way the reference's fp32 autodiff does -- four ~1e10 co
 reconstructed pixel that cancel only to rounding error -- instead of dropping them as the exact zeros they are on paper.
 The reference's training depends on those residues (with the exactly-cancelled gradient the model never leaves loss
 ~1900); False selects the analytic kernel (st_wb_bwd_axis), whose gradient is the fp64 one.
+
+``skip_nonfinite_updates`` (default False = the reference): with True an optimisation step whose global gradient norm is
+not finite changes nothing (``skipped_updates`` counts them).  The un-cancelled corner products overflow fp32 when a
+sampled window collapses to ~1e-14 of the canvas (seen once in twelve 25k-iteration runs); the reference, and the default
+here, then write NaN into every variable for good.
 """
 from __future__ import annotations
 
@@ -85,7 +90,8 @@ class AIRModel:
                  z_pres_prior_log_odds=-2.0, z_pres_temperature=1.0, stopping_threshold=0.99,
                  learning_rate=1e-3, gradient_clipping_norm=100.0, cnn=True, cnn_filters=8,
                  num_summary_images=60, train=False, reuse=False, scope="air",
-                 annealing_schedules=None, *, gemm_mode="fp32", seed=0, process_group=None, reference_rounding=True):
+                 annealing_schedules=None, *, gemm_mode="fp32", seed=0, process_group=None, reference_rounding=True,
+                 skip_nonfinite_updates=False):
         if cnn and canvas_size != 50:
             raise ValueError("the reference's CNN front-end hard-codes 50x50 canvases (air_model.py:512, 533)")
         if cnn and cnn_filters != 8:
@@ -179,6 +185,11 @@ class AIRModel:
     @property
     def global_step(self):
         return self.store.global_step
+
+    @property
+    def skipped_updates(self):
+        """optimisation steps skipped because of a non-finite gradient norm (skip_nonfinite_updates=True)"""
+        return int(self.store.state[5].item())
 
     def _alloc(self):
         B, T, dev = self.batch_size, self.max_steps, self.device
@@ -480,7 +491,7 @@ class AIRModel:
         """air_model.py:673, 692: clip by global norm, Adam, global_step += 1."""
         st = self.store
         ops.adam_step(st.flat, st.grad, st.adam_m, st.adam_v, st.state, self.gradient_clipping_norm, 0.9, 0.999, 1e-8,
-                      1.0, self.w["adam_ws"])
+                      1.0, self.w["adam_ws"], skip_nonfinite=self.skip_nonfinite_updates)
 
     def _reduce_bucket(self, i):
         """SUM all-reduce of gradient bucket i on the communicator's stream, ordered after the kernels queued so far

@@ -585,7 +585,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     adam_apply_k(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  const float *__restrict__ state, const float *__restrict__ partials, int n_partials, float clip,
-                 float beta1, float beta2, float eps, float gs, float *__restrict__ norm_out, int64_t n, int vec4) {
+                 float beta1, float beta2, float eps, float gs, float *__restrict__ norm_out, int64_t n, int vec4,
+                 int skip_nonfinite) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
   __shared__ float red[8];
   __shared__ float s_scale;
@@ -601,10 +602,14 @@ __global__ void __launch_bounds__(256)
     const float norm = sqrtf((t / 2.0f) * 2.0f);  // sqrt(2 * sum(l2_loss))
     float sc = 1.0f;
     if (clip > 0.0f) sc = clip * fminf(1.0f / norm, 1.0f / clip);  // tf.clip_by_global_norm
+    // AIR_ADAM_SKIP_NONFINITE: a non-finite global norm (an overflowed gradient) turns the whole step into a no-op
+    // instead of writing NaN into every parameter the way clip_by_global_norm + ApplyAdam do
+    if (skip_nonfinite && !(norm <= 3.0e38f)) sc = -1.0f;
     s_scale = sc;
     if (blockIdx.x == 0) *norm_out = norm;
   }
   __syncthreads();
+  if (s_scale < 0.0f) return;  // (every CTA reads the same partials: uniform across the grid)
   const float sc = s_scale * gs;
   const float b1p = state[0], b2p = state[1], lr = state[4];
   const float alpha = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
@@ -635,8 +640,13 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void adam_advance_k(float *state, float beta1, float beta2, const float *norm_in) {
+__global__ void adam_advance_k(float *state, float beta1, float beta2, const float *norm_in, int skip_nonfinite) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
+  state[3] = *norm_in;
+  if (skip_nonfinite && !(*norm_in <= 3.0e38f)) {  // skipped step: optimizer state untouched, the skip is counted
+    state[5] += 1.0f;
+    return;
+  }
   state[0] *= beta1;
   state[1] *= beta2;
   state[2] += 1.0f;
@@ -1163,14 +1173,20 @@ extern "C" int64_t air_adam_workspace(int64_t n) { return kAdamPartials + 8 + 0 
 extern "C" int air_adam_step(float *params, const float *grads, float *m, float *v, float *state, float clip_norm,
                              float beta1, float beta2, float epsilon, float grad_scale, float *workspace, int64_t n,
                              air_stream_t stream) {
+  return air_adam_step_ex(params, grads, m, v, state, clip_norm, beta1, beta2, epsilon, grad_scale, workspace, n, 0, stream);
+}
+
+extern "C" int air_adam_step_ex(float *params, const float *grads, float *m, float *v, float *state, float clip_norm,
+                                float beta1, float beta2, float epsilon, float grad_scale, float *workspace, int64_t n,
+                                int flags, air_stream_t stream) {
   AIR_REQUIRE(n > 0, AIR_ERR_BAD_SHAPE, "adam_step: n <= 0");
   AIR_REQUIRE(params && grads && m && v && state && workspace, AIR_ERR_NULL, "adam_step: null pointer");
   const int np = static_cast<int>(std::min<int64_t>(kAdamPartials, (n + 1023) / 1024));
   AIR_LAUNCH(sumsq_partial_k, np, 256, 0, ST(stream), grads, grad_scale, workspace, n);
   AIR_LAUNCH(adam_apply_k, grid_for(n, 256, 4), 256, 0, ST(stream), params, grads, m, v, state, workspace, np, clip_norm, beta1,
                                                             beta2, epsilon, grad_scale, workspace + kAdamPartials, n,
-             (aligned16(params) && aligned16(grads) && aligned16(m) && aligned16(v)) ? 1 : 0);
-  AIR_LAUNCH(adam_advance_k, 1, 1, 0, ST(stream), state, beta1, beta2, workspace + kAdamPartials);
+             (aligned16(params) && aligned16(grads) && aligned16(m) && aligned16(v)) ? 1 : 0, flags & AIR_ADAM_SKIP_NONFINITE);
+  AIR_LAUNCH(adam_advance_k, 1, 1, 0, ST(stream), state, beta1, beta2, workspace + kAdamPartials, flags & AIR_ADAM_SKIP_NONFINITE);
   count_launch(3);
   return check_launch("adam_step");
 }

@@ -155,9 +155,12 @@ def reduce_rows(partials, R, stride, n, out, accumulate=False):
     check(lib().air_reduce_rows(ptr(partials), R, stride, n, ptr(out), int(accumulate), stream()), "air_reduce_rows")
 
 
-def adam_step(params, grads, m, v, state, clip_norm, beta1, beta2, eps, grad_scale, workspace):
-    check(lib().air_adam_step(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(state), float(clip_norm or 0.0), beta1,
-                              beta2, eps, float(grad_scale), ptr(workspace), params.numel(), stream()), "air_adam_step")
+def adam_step(params, grads, m, v, state, clip_norm, beta1, beta2, eps, grad_scale, workspace, skip_nonfinite=False):
+    """skip_nonfinite: AIR_ADAM_SKIP_NONFINITE -- a step whose global gradient norm is not finite changes nothing
+    (state[5] counts such steps); the reference would write NaN into every variable."""
+    check(lib().air_adam_step_ex(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(state), float(clip_norm or 0.0), beta1,
+                                 beta2, eps, float(grad_scale), ptr(workspace), params.numel(), 1 if skip_nonfinite else 0,
+                                 stream()), "air_adam_step")
 
 
 def anneal(state, schedule, out):
