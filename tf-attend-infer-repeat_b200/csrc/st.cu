@@ -1279,6 +1279,9 @@ __global__ void __launch_bounds__(kRefThreads, 8)
     if (rok) qa[ja * QS] = sa, qc[jc * QS] = sc;
   } else {
     // ---- per-pixel pass over the in-range rows (all columns): dz and dtheta_inv; lane = canvas column
+    //      (dealing a share of the rows to warps 0 and 1 after their contraction was measured SLOWER, twice: 0.54 -> 0.60 /
+    //      0.87 ms at B = 65536 -- the first contraction is a latency-bound chain, and lengthening those warps' path costs
+    //      more than the idle slots it fills)
     int lo = 1 << 30, hi = -1;
     for (int k = lane; k < OH; k += 32) {
       const int2 e = *reinterpret_cast<const int2 *>(sRow + k);
@@ -1348,6 +1351,7 @@ __global__ void __launch_bounds__(kRefThreads, 8)
         }
         t[icur] = s;
       };
+      // (four inlined copies: one loop over the four blocks with run-time selects was measured 5 % slower)
       block(qa, false, ra0, rb0);
       block(qa, true, ra1, rb1);
       block(qc, false, ra0, rb0);
