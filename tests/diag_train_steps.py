@@ -8,7 +8,10 @@ import torch  # noqa: E402
 import bench_train  # noqa: E402
 
 m, imgs, cnt, data = bench_train._model(4096, os.environ.get("MODE", "tf32"), seed=0, train=True, max_steps=3)
+import air_b200 as ab  # noqa: E402
 for _ in range(int(os.environ.get("STEPS", "3"))):
+    n0 = ab.launch_count()
     m.train_step()
+    per_step = ab.launch_count() - n0
 torch.cuda.synchronize()
-print("loss", float(m.loss))
+print("loss", float(m.loss), "kernels_per_step", per_step)

@@ -806,11 +806,14 @@ int gemm_tf32(const float *A, const float *B, float *C, const float *Cinit, cons
     const int per_sm = tc_env().persist > 0 ? std::min(tc_env().persist, 2) : 1;
     // Automatic choice, from the per-shape measurements at the model's sizes (profiles/r2_gemm_shapes.md, M = 12288):
     // one persistent CTA per SM wins where every CTA gets 2+ wide tiles AND the epilogue is heavy -- the dX GEMMs with
-    // a K-major weight operand (dX gm 49 -> 41 us, dX r2 30 -> 26, dX r1 39 -> 37) and the 784-wide gen_mean layer
-    // (43 -> 39); it loses 5-25 % on the 256-wide layers and on fwd r1 / g2 (the non-persistent kernel keeps two CTAs per
+    // a K-major weight operand (dX gm 49 -> 41 us, dX r2 30 -> 26, dX r1 39 -> 37);
+    // it loses 5-25 % on the 256-wide layers and on fwd r1 / g2 (the non-persistent kernel keeps two CTAs per
     // SM there, whose prologues and epilogues already interleave).
-    const bool auto_on = BN == 128 && splits == 1 && total >= 2 * static_cast<int64_t>(sms) && p.num_kb >= 8 &&
-                         ((!b_mn && N >= 512) || N >= 768);
+    // (not the gen_mean layer with its in-epilogue noise generator, AIR_EPI_SIGMOID_RNG: eight epilogue warps per SM
+    // instead of sixteen doubled that GEMM in the real step, 40 -> 79 us, although the same shape with a plain epilogue
+    // gained 4 us in the per-shape table)
+    const bool auto_on = BN == 128 && splits == 1 && total >= 2 * static_cast<int64_t>(sms) && p.num_kb >= 8 && !b_mn &&
+                         N >= 512 && epi != AIR_EPI_SIGMOID_RNG;
     if (tc_env().persist > 0 || auto_on) {
 #define AIR_TC_PERSIST_DISPATCH(BNv)                                                                                             \
   (a_mn ? (b_mn ? launch_tc_persist<BNv, true, true>(ma, mb, p, per_sm, s) : launch_tc_persist<BNv, true, false>(ma, mb, p, per_sm, s)) \

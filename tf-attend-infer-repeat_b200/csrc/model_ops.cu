@@ -601,7 +601,10 @@ __global__ void __launch_bounds__(256)
     for (int k = 0; k < 8; ++k) t += red[k];
     const float norm = sqrtf((t / 2.0f) * 2.0f);  // sqrt(2 * sum(l2_loss))
     float sc = 1.0f;
-    if (clip > 0.0f) sc = clip * fminf(1.0f / norm, 1.0f / clip);  // tf.clip_by_global_norm
+    if (clip > 0.0f) {  // tf.clip_by_global_norm; tf.minimum PROPAGATES a NaN norm (fminf would drop it): every gradient NaN
+      const float inv = 1.0f / norm;
+      sc = clip * ((inv < 1.0f / clip || inv != inv) ? inv : 1.0f / clip);
+    }
     // AIR_ADAM_SKIP_NONFINITE: a non-finite global norm (an overflowed gradient) turns the whole step into a no-op
     // instead of writing NaN into every parameter the way clip_by_global_norm + ApplyAdam do
     if (skip_nonfinite && !(norm <= 3.0e38f)) sc = -1.0f;
