@@ -1179,10 +1179,31 @@ __global__ void __launch_bounds__(kAxisThreads, 11)
 //     unspecified); here it is fixed and separable: per canvas row the wx1 terms of all columns in column order and then
 //     the wx0 terms continue the same accumulators (Q = G Wx), then the same along the rows (dwindow = Wy^T Q).
 // Deterministic (no atomics), one CTA per (image, step):
-//   warps 0-1 : Q, lane = canvas row;   warps 2-3 : the per-pixel pass (dz, dtheta_inv), lane = canvas column;
-//   barrier;  warp 0 : Wy^T Q, lane = window column;  barrier;  all : scaled 128-bit stores of dwindow.
+//   warp 0 : Qa / Qc, lane = two canvas rows (packed fp32x2);   warps 1-3 : the per-pixel pass (dz, dtheta_inv), lane =
+//   canvas column;   barrier;   every warp : its 7 window rows of Wy^T Q, lane = window column;   barrier;   all : 128-bit
+//   stores of dwindow.
 // theta_inv with a rotation / shear / negative scale: per-pixel shared-memory atomics with the same per-pixel formulas.
 // =========================================================================================
+// packed fp32x2 arithmetic (sm_100a: FMUL2 / FFMA2 on 64-bit register pairs)
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &a, float &b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 constexpr int kRefThreads = 128;
 constexpr int kRefQS = 51;  // row stride of the transposed Q buffer [W][51] (odd: conflict-free for both passes)
 
@@ -1300,44 +1321,49 @@ __global__ void __launch_bounds__(kRefThreads, 8)
 
   __syncthreads();  // tables visible
   mbar_wait(&bar, 0);
-  if (warp < 2) {
-    // ---- first contraction, along the columns; lane = canvas row (ALL rows: a clipped row's sums feed the cancelling
-    //      blocks of the second contraction).  The wx1 terms (corners a, b) and the wx0 terms (corners c, d) are kept
-    //      apart -- they must not meet before the end:
+  if (warp == 0) {
+    // ---- first contraction, along the columns; lane = TWO canvas rows (lane and lane + OH / 2: ALL rows -- a clipped
+    //      row's sums feed the cancelling blocks of the second contraction), packed fp32x2 arithmetic (FFMA2): one warp
+    //      does what took two, the other three share the per-pixel pass.  The wx1 terms (corners a, b) and the wx0 terms
+    //      (corners c, d) are kept apart -- they must not meet before the end:
     //          Qa[r][j] = sum_{c: j0(c) = j} wx1[c] g[r][c],   Qc[r][j] = sum_{c: j1(c) = j} wx0[c] g[r][c]   (c ascending)
-    const int r = warp * 32 + lane;
-    const bool rok = r < OH;
-    const float *grow = sG + (rok ? r : OH - 1) * OW;
-    float *qa = sQ + r, *qc = sQ + W * QS + r;  // Q[r][j] at [j * QS + r]; only dereferenced under rok
+    static_assert(OH % 2 == 0 && OH / 2 <= 32, "two canvas rows per lane");
+    constexpr int HR = OH / 2;
+    const bool rok = lane < HR;
+    const int r0 = rok ? lane : HR - 1;
+    const float *gA = sG + r0 * OW, *gB = gA + HR * OW;
+    float *qaA = sQ + r0, *qaB = qaA + HR, *qcA = qaA + W * QS, *qcB = qcA + HR;  // Q[r][j] at [j * QS + r]; stores under rok
     if (rok) {
 #pragma unroll 4
-      for (int j = 0; j < W; ++j) qa[j * QS] = 0.0f, qc[j * QS] = 0.0f;
+      for (int j = 0; j < W; ++j) qaA[j * QS] = 0.0f, qaB[j * QS] = 0.0f, qcA[j * QS] = 0.0f, qcB[j * QS] = 0.0f;
     }
+    const uint64_t z2 = pack_f32x2(zval, zval);
     int ja = sCol[0].i0, jc = sCol[0].i1;
-    float sa = 0.0f, sc = 0.0f;
+    uint64_t sa = 0, sc = 0;  // (+0.0, +0.0)
 #pragma unroll 2
     for (int c = 0; c < OW; ++c) {
       const Ent ce = sCol[c];
-      const float g = mul_rn(grow[c], zval);
+      const uint64_t g2 = mul_f32x2(pack_f32x2(gA[c], gB[c]), z2);
       if (ce.i0 != ja) {  // warp-uniform: depends on the column only
-        if (rok) qa[ja * QS] = sa;
-        sa = 0.0f;
+        if (rok) unpack_f32x2(sa, qaA[ja * QS], qaB[ja * QS]);
+        sa = 0;
         ja = ce.i0;
       }
       if (ce.i1 != jc) {
-        if (rok) qc[jc * QS] = sc;
-        sc = 0.0f;
+        if (rok) unpack_f32x2(sc, qcA[jc * QS], qcB[jc * QS]);
+        sc = 0;
         jc = ce.i1;
       }
-      sa = add_rn(sa, mul_rn(ce.w1, g));
-      sc = add_rn(sc, mul_rn(ce.w0, g));
+      sa = fma_f32x2(pack_f32x2(ce.w1, ce.w1), g2, sa);
+      sc = fma_f32x2(pack_f32x2(ce.w0, ce.w0), g2, sc);
     }
-    if (rok) qa[ja * QS] = sa, qc[jc * QS] = sc;
+    if (rok) {
+      unpack_f32x2(sa, qaA[ja * QS], qaB[ja * QS]);
+      unpack_f32x2(sc, qcA[jc * QS], qcB[jc * QS]);
+    }
   } else {
-    // ---- per-pixel pass over the in-range rows (all columns): dz and dtheta_inv; lane = canvas column
-    //      (dealing a share of the rows to warps 0 and 1 after their contraction was measured SLOWER, twice: 0.54 -> 0.60 /
-    //      0.87 ms at B = 65536 -- the first contraction is a latency-bound chain, and lengthening those warps' path costs
-    //      more than the idle slots it fills)
+    // ---- per-pixel pass over the in-range rows (all columns): dz and dtheta_inv; lane = canvas column, warps 1-3
+    //      (dealing a share of these rows to the contraction warp as well was measured SLOWER, twice)
     int lo = 1 << 30, hi = -1;
     for (int k = lane; k < OH; k += 32) {
       const int2 e = *reinterpret_cast<const int2 *>(sRow + k);
@@ -1350,7 +1376,7 @@ __global__ void __launch_bounds__(kRefThreads, 8)
       const int c = cok ? cb + lane : OW - 1;  // surplus lanes redo the last column with a zero upstream gradient
       const Ent ce = sCol[c];
       const float xt = sGrid[c];
-      for (int r = lo + (warp - 2); r <= hi; r += 2) {
+      for (int r = lo + (warp - 1); r <= hi; r += 3) {
         float wa, wb, wc, wd, g;
         pixel(ce, sRow[r], xt, sGrid[OW + r], cok ? sG[r * OW + c] : 0.0f, wa, wb, wc, wd, g);
       }
@@ -1417,8 +1443,8 @@ __global__ void __launch_bounds__(kRefThreads, 8)
       const float sx = 0.5f * wf, sy = 0.5f * hf;
       float *d = dtheta + b * 6;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) d[k] = (sPart[2][k] + sPart[3][k]) * (k < 3 ? sx : sy);
-      dz[b] = sPart[2][6] + sPart[3][6];
+      for (int k = 0; k < 6; ++k) d[k] = ((sPart[1][k] + sPart[2][k]) + sPart[3][k]) * (k < 3 ? sx : sy);
+      dz[b] = (sPart[1][6] + sPart[2][6]) + sPart[3][6];
     }
   }
   __syncthreads();
