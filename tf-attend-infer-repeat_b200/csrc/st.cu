@@ -1433,7 +1433,8 @@ __global__ void __launch_bounds__(kRefThreads, 8)
         }
         t[icur] = s;
       };
-      // (four inlined copies: one loop over the four blocks with run-time selects was measured 5 % slower)
+      // (four inlined copies: one loop over the four blocks with run-time selects was measured 5 % slower; two window
+      // columns per lane in packed fp32x2 arithmetic -- what the first contraction does with rows -- 7 % slower: 14 lanes)
       block(qa, false, ra0, rb0);
       block(qa, true, ra1, rb1);
       block(qc, false, ra0, rb0);
