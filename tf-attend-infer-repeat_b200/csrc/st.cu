@@ -1224,7 +1224,9 @@ __global__ void __launch_bounds__(kRefThreads, 8)
   Ent *sCol = reinterpret_cast<Ent *>(sQ + 2 * W * QS);    // [OW]
   Ent *sRow = sCol + OW;                                   // [OH]
   float *sGrid = reinterpret_cast<float *>(sRow + OH);     // [OW + OH] normalised grid x_t | y_t
+  float *sT4 = sGrid + ((OW + OH + 3) & ~3);               // [HW] fourth corner tile (sep4 launches only)
   static_assert((HW * 4) % 16 == 0 && (OHW * 4) % 16 == 0 && (W * QS * 4) % 16 == 0, "16-byte aligned carve-up");
+  static_assert(3 * HW <= OHW, "three corner tiles fit into the dead dcanvas tile");
   __shared__ uint64_t bar;
   __shared__ float sTh[8];
   __shared__ float sPart[kRefThreads / 32][8];
@@ -1263,6 +1265,7 @@ __global__ void __launch_bounds__(kRefThreads, 8)
   }
   // separable scans need an axis-aligned theta whose source index grows with the output index
   const bool regular = !(sig & 2) && th1 == 0.0f && th3 == 0.0f && th0 > 0.0f && th4 > 0.0f && th0 < 1.0e30f && th4 < 1.0e30f;
+  const bool sep4 = (sig & 4) != 0;  // experiment: one accumulator per corner (a, b, c, d), summed at the end (autograd's order)
   sig &= 1;
   const float wf = sub_rn(static_cast<float>(W), 1.001f), hf = sub_rn(static_cast<float>(H), 1.001f);
   float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum dx*xt, dx*yt, dx, dy*xt, dy*yt, dy, dcanvas*sample
@@ -1412,11 +1415,14 @@ __global__ void __launch_bounds__(kRefThreads, 8)
     range(false, ra0, rb0);
     range(true, ra1, rb1);
     if (lane < W) {
-      float *t = tile + lane;
+      float *tA = tile + lane, *tB = sep4 ? tA + HW : tA, *tC = sep4 ? tA + 2 * HW : tA, *tD = sep4 ? sT4 + lane : tA;
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) t[ilo + i * W] = 0.0f;
+      for (int i = 0; i < RPW; ++i) {
+        tA[ilo + i * W] = 0.0f;
+        if (sep4) tB[ilo + i * W] = 0.0f, tC[ilo + i * W] = 0.0f, tD[ilo + i * W] = 0.0f;
+      }
       const float *qa = sQ + lane * QS, *qc = qa + W * QS;
-      auto block = [&](const float *q, bool second, int ra, int rb) {
+      auto block = [&](const float *q, bool second, int ra, int rb, float *t) {
         if (ra >= rb) return;
         int icur = second ? sRow[ra].i1 : sRow[ra].i0;
         float s = t[icur];
@@ -1435,10 +1441,10 @@ __global__ void __launch_bounds__(kRefThreads, 8)
       };
       // (four inlined copies: one loop over the four blocks with run-time selects was measured 5 % slower; two window
       // columns per lane in packed fp32x2 arithmetic -- what the first contraction does with rows -- 7 % slower: 14 lanes)
-      block(qa, false, ra0, rb0);
-      block(qa, true, ra1, rb1);
-      block(qc, false, ra0, rb0);
-      block(qc, true, ra1, rb1);
+      block(qa, false, ra0, rb0, tA);
+      block(qa, true, ra1, rb1, tB);
+      block(qc, false, ra0, rb0, tC);
+      block(qc, true, ra1, rb1, tD);
     }
     if (tid == 32) {
       const float sx = 0.5f * wf, sy = 0.5f * hf;
@@ -1452,6 +1458,12 @@ __global__ void __launch_bounds__(kRefThreads, 8)
   float4 *dst = reinterpret_cast<float4 *>(dUb);
   for (int k = tid; k < (HW >> 2); k += kRefThreads) {
     float4 v = *reinterpret_cast<const float4 *>(tile + 4 * k);
+    if (sep4) {  // ((d + c) + b) + a: the order in which autograd adds the four gather gradients of the oracle
+      const float4 b4 = *reinterpret_cast<const float4 *>(tile + HW + 4 * k), c4 = *reinterpret_cast<const float4 *>(tile + 2 * HW + 4 * k);
+      const float4 d4 = *reinterpret_cast<const float4 *>(sT4 + 4 * k);
+      v.x = add_rn(add_rn(add_rn(d4.x, c4.x), b4.x), v.x); v.y = add_rn(add_rn(add_rn(d4.y, c4.y), b4.y), v.y);
+      v.z = add_rn(add_rn(add_rn(d4.z, c4.z), b4.z), v.z); v.w = add_rn(add_rn(add_rn(d4.w, c4.w), b4.w), v.w);
+    }
     if (sig) {  // SigmoidGrad of the window fused into the store: d/d(pre-sigmoid) = d/dw * w (1 - w)
       const float4 u = *reinterpret_cast<const float4 *>(sU + 4 * k);
       v.x *= u.x * (1.0f - u.x); v.y *= u.y * (1.0f - u.y); v.z *= u.z * (1.0f - u.z); v.w *= u.w * (1.0f - u.w);
@@ -1640,8 +1652,9 @@ template <int H_, int W_, int OH_, int OW_>
 static int launch_wb_bwd_ref(const float *U, const float *theta, const float *dcanvas, const float *z, const float *stop,
                              float thr, float *dU, float *dtheta, float *dz, int sig, int64_t B, cudaStream_t s) {
   auto kern = st_wb_bwd_ref<H_, W_, OH_, OW_>;
-  constexpr size_t smem = (static_cast<size_t>(H_) * W_ + OH_ * OW_ + 2 * W_ * kRefQS + OW_ + OH_) * 4 + (OW_ + OH_) * sizeof(Ent);
-  static_assert(smem <= 48 * 1024, "no opt-in needed");
+  constexpr size_t smem0 = (static_cast<size_t>(H_) * W_ + OH_ * OW_ + 2 * W_ * kRefQS + ((OW_ + OH_ + 3) & ~3)) * 4 + (OW_ + OH_) * sizeof(Ent);
+  static_assert(smem0 + H_ * W_ * 4 <= 48 * 1024, "no opt-in needed");
+  const size_t smem = smem0 + ((sig & 4) ? H_ * W_ * 4 : 0);  // the fourth corner tile of the sep4 experiment
   static bool once = false;
   if (!once) {  // the largest shared-memory carve-out: 8+ CTAs of 21 KB per SM
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1672,7 +1685,7 @@ static int st_backward_impl(const float *U, const float *theta, const float *dou
       if (H == 28 && W == 28 && OH == 50 && OW == 50 && (flags & AIR_WB_REFERENCE_ROUNDING) && dU && dz && aligned16(dU))
         {
           static const int atomics = [] { const char *e = getenv("AIR_WB_REF_ATOMICS"); return e ? atoi(e) : 0; }();  // experiment
-          return launch_wb_bwd_ref<28, 28, 50, 50>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig | (atomics ? 2 : 0), B, s);
+          return launch_wb_bwd_ref<28, 28, 50, 50>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig | (atomics == 1 ? 2 : atomics == 4 ? 4 : 0), B, s);
         }
       if (flags & AIR_WB_REFERENCE_ROUNDING)  // other sizes / no dz: the per-pixel path of the generic staged kernel
         return launch_bwd_staged<0, 0, 0, 0, true>(U, theta, dout, z, stop, thr, dU, dtheta, dz, sig | 2, B, H, W, OH, OW, s);
