@@ -22,34 +22,38 @@ def _torch_layer(x_nhwc, w_hwio, b, pool):
     return t.permute(0, 2, 3, 1)
 
 
+@pytest.mark.parametrize("F_", [8, 4, 16])
 @pytest.mark.parametrize("cin,H,W,pool", LAYERS)
 @pytest.mark.parametrize("B", [1, 37])
-def test_conv_layer_forward_backward(cin, H, W, pool, B):
+def test_conv_layer_forward_backward(cin, H, W, pool, B, F_):
+    """F_ = cnn_filters (air_model.py:21, default 8): output channels of every layer, input channels of conv2 / conv3."""
+    if cin > 1:
+        cin = F_
     g = torch.Generator().manual_seed(100 + cin + H + B)
     x = torch.rand(B, H, W, cin, generator=g) * (torch.rand(B, H, W, cin, generator=g) > 0.6)   # sparse, like a canvas
-    w = (torch.rand(5, 5, cin, 8, generator=g) - 0.45) * 0.5
-    b = (torch.rand(8, generator=g) - 0.5) * 0.2
+    w = (torch.rand(5, 5, cin, F_, generator=g) - 0.45) * 0.5
+    b = (torch.rand(F_, generator=g) - 0.5) * 0.2
     xt, wt, bt = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     want = _torch_layer(xt, wt, bt, pool)
     PH, PW = (H // 2, W // 2) if pool else (H, W)
-    out = torch.empty(B, PH, PW, 8, device=DEV)
-    arg = torch.empty(B, PH, PW, 8, device=DEV, dtype=torch.uint8) if pool else None
+    out = torch.empty(B, PH, PW, F_, device=DEV)
+    arg = torch.empty(B, PH, PW, F_, device=DEV, dtype=torch.uint8) if pool else None
     xg, wg, bg = x.to(DEV), w.to(DEV), b.to(DEV)
-    ops.conv5x5_fwd(xg, wg, bg, out, arg, H, W, cin, 8, pool)
+    ops.conv5x5_fwd(xg, wg, bg, out, arg, H, W, cin, F_, pool)
     np.testing.assert_allclose(out.cpu().numpy(), want.detach().numpy(), rtol=2e-5, atol=2e-6)
     assert (want > 0).float().mean() > 0.2                      # the test exercises live units
-    dout = torch.randn(B, PH, PW, 8, generator=g)
+    dout = torch.randn(B, PH, PW, F_, generator=g)
     want.backward(dout)
-    dw, db = torch.full((5, 5, cin, 8), 7.0, device=DEV), torch.full((8,), 7.0, device=DEV)
+    dw, db = torch.full((5, 5, cin, F_), 7.0, device=DEV), torch.full((F_,), 7.0, device=DEV)
     din = torch.empty(B, H, W, cin, device=DEV) if cin > 1 else None
-    ws = torch.zeros(ops.conv5x5_bwd_workspace(B, cin, 8), device=DEV)
-    ops.conv5x5_bwd(xg, wg, out, arg, dout.to(DEV), din, dw, db, False, ws, H, W, cin, 8, pool)
+    ws = torch.zeros(ops.conv5x5_bwd_workspace(B, cin, F_), device=DEV)
+    ops.conv5x5_bwd(xg, wg, out, arg, dout.to(DEV), din, dw, db, False, ws, H, W, cin, F_, pool)
     assert relnorm(dw, wt.grad) < 1e-5 and relnorm(db, bt.grad) < 1e-5
     if din is not None:
         assert relnorm(din, xt.grad) < 1e-5
     # accumulate == 1 adds to the existing gradient; the run is bit-reproducible
     dw2, db2 = dw.clone(), db.clone()
-    ops.conv5x5_bwd(xg, wg, out, arg, dout.to(DEV), din, dw2, db2, True, ws, H, W, cin, 8, pool)
+    ops.conv5x5_bwd(xg, wg, out, arg, dout.to(DEV), din, dw2, db2, True, ws, H, W, cin, F_, pool)
     assert torch.equal(dw2, dw + dw) and torch.equal(db2, db + db)
 
 
@@ -60,10 +64,16 @@ def test_conv_unsupported_shape_fails_loudly():
                         None, 10, 10, 3, 8, False)
 
 
-def test_model_cnn_forward_and_gradients_vs_oracle():
+@pytest.mark.parametrize("filters", [8, 4, 16])
+def test_model_cnn_forward_and_gradients_vs_oracle(filters):
     imgs, cnt, params, noise = covered_fixture(8, seed=2, cnn=True)
-    orc, m = make_pair(imgs, cnt, params, train=True, cnn=True)
-    assert m.Kx.shape == (1152, 1024)
+    if filters != 8:   # (the fixture's parameter dict is built for the default 8 filters: re-draw the front-end and the LSTM input rows)
+        fresh = O.init_params(seed=2, cnn=True, cnn_filters=filters)
+        for k in fresh:
+            if k.startswith("cnn/") or k == "rnn/kernel":
+                params[k] = fresh[k]
+    orc, m = make_pair(imgs, cnt, params, train=True, cnn=True, cnn_filters=filters)
+    assert m.Kx.shape == (144 * filters, 1024)
     out, grads = orc.loss_and_grads(imgs, cnt, noise)
     m.loss_and_grads(cuda_noise(noise))
     assert torch.equal(m.rec_num_digits.cpu(), out["rec_num_digits"])

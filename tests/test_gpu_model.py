@@ -234,8 +234,10 @@ def test_constructor_surface_and_variable_scopes():
     ab.reset_variable_scopes()
     m = ab.AIRModel(x, t)                                   # the reference's literal defaults: cnn=True, 8 filters
     assert m.cnn and m.Kx.shape == (12 * 12 * 8, 1024)
+    m16 = ab.AIRModel(x, t, cnn_filters=16, scope="f16")    # the conv kernels are built for 4, 8 and 16 filters
+    assert m16.Kx.shape == (12 * 12 * 16, 1024)
     with pytest.raises(NotImplementedError):
-        ab.AIRModel(x, t, cnn_filters=16, scope="f16")      # conv kernels are built for the reference's 8 filters
+        ab.AIRModel(x, t, cnn_filters=12, scope="f12")
     with pytest.raises(ab.AirError):
         ab.AIRModel(x.cpu(), t.cpu(), cnn=False, scope="cpu")
     # tf.variable_scope semantics (air_model.py:68): an existing scope needs reuse=True, and reuse checks the shapes

@@ -94,8 +94,8 @@ class AIRModel:
                  skip_nonfinite_updates=False):
         if cnn and canvas_size != 50:
             raise ValueError("the reference's CNN front-end hard-codes 50x50 canvases (air_model.py:512, 533)")
-        if cnn and cnn_filters != 8:
-            raise NotImplementedError("the conv kernels are built for the reference's cnn_filters=8")
+        if cnn and cnn_filters not in (4, 8, 16):
+            raise NotImplementedError("the conv kernels are built for cnn_filters in (4, 8, 16); the reference's default is 8")
         if not input_images.is_cuda:
             raise C.AirError("AIRModel needs CUDA tensors (no CPU fallback)")
         C.lib()  # fail loudly if the extension is missing

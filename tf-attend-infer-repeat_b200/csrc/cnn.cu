@@ -18,7 +18,6 @@
 
 namespace air {
 
-constexpr int kCout = 8;
 
 // model_ops.cu: out[e] (+)= sum_r partials[r * stride + e], fixed order (deterministic)
 int reduce_rows_launch(const float *partials, int R, int stride, int n, float *out, int accumulate, cudaStream_t s);
@@ -33,53 +32,56 @@ __device__ __forceinline__ void load_padded(const float *__restrict__ src, float
   }
 }
 
-template <int CIN, int H, int W, bool POOL, int THREADS>
+template <int CIN, int COUT, int H, int W, bool POOL, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     conv5x5_fwd_k(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
                   float *__restrict__ out, uint8_t *__restrict__ arg, int64_t B) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
-  constexpr int IW = W + 4, IH = H + 4, PH = POOL ? H / 2 : H, PW = POOL ? W / 2 : W, NP = POOL ? 4 : 1;
+  static_assert(COUT % 4 == 0, "output channels travel as float4 / packed argmax bytes");
+  constexpr int IW = W + 4, IH = H + 4, PH = POOL ? H / 2 : H, PW = POOL ? W / 2 : W, NP = POOL ? 4 : 1, CV = COUT / 4;
   extern __shared__ __align__(16) float smem[];
   float *sIn = smem;                                   // [IH][IW][CIN] zero-padded input tile
-  float *sW = sIn + ((IH * IW * CIN + 3) & ~3);        // [25*CIN][8]  (HWIO, as stored)
-  float *sB = sW + 25 * CIN * kCout;                   // [8]
+  float *sW = sIn + ((IH * IW * CIN + 3) & ~3);        // [25*CIN][COUT]  (HWIO, as stored)
+  float *sB = sW + 25 * CIN * COUT;                    // [COUT]
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
   load_padded<CIN, H, W>(in + b * H * W * CIN, sIn, tid, THREADS);
-  for (int e = tid; e < 25 * CIN * kCout; e += THREADS) sW[e] = __ldg(w + e);
-  if (tid < kCout) sB[tid] = __ldg(bias + tid);
+  for (int e = tid; e < 25 * CIN * COUT; e += THREADS) sW[e] = __ldg(w + e);
+  if (tid < COUT) sB[tid] = __ldg(bias + tid);
   __syncthreads();
   for (int item = tid; item < PH * PW; item += THREADS) {
     const int py = item / PW, px = item - py * PW;
     const int y0 = POOL ? 2 * py : py, x0 = POOL ? 2 * px : px;
-    float acc[NP][kCout];
+    float acc[NP][COUT];
 #pragma unroll
     for (int p = 0; p < NP; ++p)
 #pragma unroll
-      for (int co = 0; co < kCout; ++co) acc[p][co] = sB[co];
+      for (int co = 0; co < COUT; ++co) acc[p][co] = sB[co];
 #pragma unroll 1
     for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-          const float4 wa = *reinterpret_cast<const float4 *>(sW + ((ky * 5 + kx) * CIN + ci) * kCout);
-          const float4 wb = *reinterpret_cast<const float4 *>(sW + ((ky * 5 + kx) * CIN + ci) * kCout + 4);
+          float v[NP];
 #pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            const float v = sIn[((y0 + (p >> 1) + ky) * IW + (x0 + (p & 1) + kx)) * CIN + ci];
-            acc[p][0] = fmaf(v, wa.x, acc[p][0]); acc[p][1] = fmaf(v, wa.y, acc[p][1]);
-            acc[p][2] = fmaf(v, wa.z, acc[p][2]); acc[p][3] = fmaf(v, wa.w, acc[p][3]);
-            acc[p][4] = fmaf(v, wb.x, acc[p][4]); acc[p][5] = fmaf(v, wb.y, acc[p][5]);
-            acc[p][6] = fmaf(v, wb.z, acc[p][6]); acc[p][7] = fmaf(v, wb.w, acc[p][7]);
+          for (int p = 0; p < NP; ++p) v[p] = sIn[((y0 + (p >> 1) + ky) * IW + (x0 + (p & 1) + kx)) * CIN + ci];
+#pragma unroll
+          for (int q = 0; q < CV; ++q) {
+            const float4 wq = *reinterpret_cast<const float4 *>(sW + ((ky * 5 + kx) * CIN + ci) * COUT + 4 * q);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              acc[p][4 * q + 0] = fmaf(v[p], wq.x, acc[p][4 * q + 0]); acc[p][4 * q + 1] = fmaf(v[p], wq.y, acc[p][4 * q + 1]);
+              acc[p][4 * q + 2] = fmaf(v[p], wq.z, acc[p][4 * q + 2]); acc[p][4 * q + 3] = fmaf(v[p], wq.w, acc[p][4 * q + 3]);
+            }
           }
         }
       }
     }
-    float r[kCout];
-    uint8_t a[kCout];
+    float r[COUT];
+    uint8_t a[COUT];
 #pragma unroll
-    for (int co = 0; co < kCout; ++co) {
+    for (int co = 0; co < COUT; ++co) {
       float m = fmaxf(acc[0][co], 0.0f);  // ReLU, then max-pool (first maximum wins)
       int am = 0;
 #pragma unroll
@@ -90,113 +92,116 @@ __global__ void __launch_bounds__(THREADS)
       r[co] = m;
       a[co] = static_cast<uint8_t>(am);
     }
-    float *o = out + (b * PH * PW + item) * kCout;
-    *reinterpret_cast<float4 *>(o) = make_float4(r[0], r[1], r[2], r[3]);
-    *reinterpret_cast<float4 *>(o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    float *o = out + (b * PH * PW + item) * COUT;
+#pragma unroll
+    for (int q = 0; q < CV; ++q) *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     if (POOL) {
-      uint2 pk;
-      pk.x = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
-      pk.y = a[4] | (a[5] << 8) | (a[6] << 16) | (a[7] << 24);
-      *reinterpret_cast<uint2 *>(arg + (b * PH * PW + item) * kCout) = pk;
+      uint32_t *ao = reinterpret_cast<uint32_t *>(arg + (b * PH * PW + item) * COUT);
+#pragma unroll
+      for (int q = 0; q < CV; ++q) ao[q] = a[4 * q] | (a[4 * q + 1] << 8) | (a[4 * q + 2] << 16) | (a[4 * q + 3] << 24);
     }
   }
 }
 
-template <int CIN, int H, int W, bool POOL>
+template <int CIN, int COUT, int H, int W, bool POOL>
 constexpr size_t conv_fwd_smem() {
-  return (static_cast<size_t>(((H + 4) * (W + 4) * CIN + 3) & ~3) + 25 * CIN * kCout + kCout) * sizeof(float);
+  return (static_cast<size_t>(((H + 4) * (W + 4) * CIN + 3) & ~3) + 25 * CIN * COUT + COUT) * sizeof(float);
 }
 
-template <int CIN, int H, int W, bool POOL, bool NEED_DX>
+template <int CIN, int COUT, int H, int W, bool POOL, bool NEED_DX>
 constexpr size_t conv_bwd_smem() {
   constexpr size_t pin = ((H + 4) * (W + 4) * CIN + 3) & ~3;
-  constexpr size_t pd = NEED_DX ? (H + 4) * (W + 4) * kCout : 0;
-  constexpr size_t pg = (POOL ? (H / 2) * (W / 2) : H * W) * kCout;
-  constexpr size_t pw = NEED_DX ? 25 * CIN * kCout : 0;
+  constexpr size_t pd = NEED_DX ? (H + 4) * (W + 4) * COUT : 0;
+  constexpr size_t pg = (POOL ? (H / 2) * (W / 2) : H * W) * COUT;
+  constexpr size_t pw = NEED_DX ? 25 * CIN * COUT : 0;
   return (pin + pd + pg + pw) * sizeof(float) + (POOL ? pg : 0);
 }
 
 // GS threads form a group that owns the 25*CIN weight taps + 8 biases; the THREADS / GS groups of a CTA split the
 // output pixels among themselves and write one partial row each (fixed assignment -> deterministic).
-template <int CIN, int H, int W, bool POOL, bool NEED_DX, int THREADS, int GS>
+template <int CIN, int COUT, int H, int W, bool POOL, bool NEED_DX, int THREADS, int GS>
 __global__ void __launch_bounds__(THREADS)
     conv5x5_bwd_k(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ out,
                   const uint8_t *__restrict__ arg, const float *__restrict__ dout, float *__restrict__ din,
                   float *__restrict__ partials, int64_t B) {
   pdl_sync();  // PDL: no global access before the previous grid has completed
-  static_assert(25 * CIN + kCout <= GS && THREADS % GS == 0, "one thread per weight tap + one per bias in every group");
-  constexpr int NG = THREADS / GS;
+  static_assert(25 * CIN + COUT <= GS && THREADS % GS == 0, "one thread per weight tap + one per bias in every group");
+  static_assert(COUT % 4 == 0, "output channels travel as float4");
+  constexpr int NG = THREADS / GS, CV = COUT / 4;
   constexpr int IW = W + 4, IH = H + 4, PH = POOL ? H / 2 : H, PW = POOL ? W / 2 : W, NPIX = PH * PW;
   extern __shared__ __align__(16) float smem[];
-  float *sIn = smem;                                              // [IH][IW][CIN] zero-padded layer input
-  float *sD = sIn + ((IH * IW * CIN + 3) & ~3);                   // [IH][IW][8]   zero-padded dense d(conv)  (NEED_DX)
-  float *sG = sD + (NEED_DX ? IH * IW * kCout : 0);               // [NPIX][8]     d(out) * (out > 0)
-  float *sW = sG + NPIX * kCout;                                  // [25*CIN][8]   (NEED_DX)
-  uint8_t *sA = reinterpret_cast<uint8_t *>(sW + (NEED_DX ? 25 * CIN * kCout : 0));  // [NPIX][8] argmax (POOL)
+  float *sIn = smem;                                              // [IH][IW][CIN]  zero-padded layer input
+  float *sD = sIn + ((IH * IW * CIN + 3) & ~3);                   // [IH][IW][COUT] zero-padded dense d(conv)  (NEED_DX)
+  float *sG = sD + (NEED_DX ? IH * IW * COUT : 0);                // [NPIX][COUT]   d(out) * (out > 0)
+  float *sW = sG + NPIX * COUT;                                   // [25*CIN][COUT] (NEED_DX)
+  uint8_t *sA = reinterpret_cast<uint8_t *>(sW + (NEED_DX ? 25 * CIN * COUT : 0));  // [NPIX][COUT] argmax (POOL)
   const int tid = threadIdx.x;
   if (NEED_DX)
-    for (int e = tid; e < 25 * CIN * kCout; e += THREADS) sW[e] = __ldg(w + e);
-  // this thread's weight tap (ky, kx, ci) and its 8 gradient accumulators, or a bias accumulator
+    for (int e = tid; e < 25 * CIN * COUT; e += THREADS) sW[e] = __ldg(w + e);
+  // this thread's weight tap (ky, kx, ci) and its COUT gradient accumulators, or a bias accumulator
   const int group = tid / GS, lt = tid - group * GS;
-  const bool tap = lt < 25 * CIN, isb = lt >= 25 * CIN && lt < 25 * CIN + kCout;
+  const bool tap = lt < 25 * CIN, isb = lt >= 25 * CIN && lt < 25 * CIN + COUT;
   const int ci = lt % CIN, kk = lt / CIN, ky = kk / 5, kx = kk - ky * 5;
-  float gw[kCout] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gw[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) gw[co] = 0.0f;
   float gb = 0.0f;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();  // the previous image's tiles are no longer read
     load_padded<CIN, H, W>(in + b * H * W * CIN, sIn, tid, THREADS);
-    for (int e = tid; e < NPIX * kCout; e += THREADS) {
-      const int64_t o = b * NPIX * kCout + e;
+    for (int e = tid; e < NPIX * COUT; e += THREADS) {
+      const int64_t o = b * NPIX * COUT + e;
       sG[e] = out[o] > 0.0f ? dout[o] : 0.0f;  // ReluGrad
       if (POOL) sA[e] = arg[o];
     }
     if (NEED_DX)
-      for (int e = tid; e < IH * IW * kCout; e += THREADS) sD[e] = 0.0f;
+      for (int e = tid; e < IH * IW * COUT; e += THREADS) sD[e] = 0.0f;
     __syncthreads();
     if (NEED_DX) {  // un-pool: scatter the pooled gradients to their argmax positions (distinct targets)
-      for (int e = tid; e < NPIX * kCout; e += THREADS) {
-        const int pp = e / kCout, co = e - pp * kCout;
+      for (int e = tid; e < NPIX * COUT; e += THREADS) {
+        const int pp = e / COUT, co = e - pp * COUT;
         const int py = pp / PW, px = pp - py * PW;
         const int a = POOL ? sA[e] : 0;
         const int y = POOL ? 2 * py + (a >> 1) : py, x = POOL ? 2 * px + (a & 1) : px;
-        sD[((y + 2) * IW + (x + 2)) * kCout + co] = sG[e];
+        sD[((y + 2) * IW + (x + 2)) * COUT + co] = sG[e];
       }
       __syncthreads();
     }
     if (tap && NEED_DX) {
       // dW[ky][kx][ci][:] += sum over conv pixels of in[y+ky-2][x+kx-2][ci] * d(conv)[y][x][:], from the dense
-      // (un-pooled) tile that the dX pass needs anyway: one input load + two broadcast 128-bit loads per 8 FMAs
+      // (un-pooled) tile that the dX pass needs anyway: one input load + COUT/4 broadcast 128-bit loads per COUT FMAs
       constexpr int CH = POOL ? 2 * PH : H, CW = POOL ? 2 * PW : W;  // conv pixels that can carry a gradient
       for (int q = group; q < CH * CW; q += NG) {
         const int y = q / CW, x = q - y * CW;
-        const float *dp = sD + ((y + 2) * IW + (x + 2)) * kCout;
-        const float4 ga = *reinterpret_cast<const float4 *>(dp), gq = *reinterpret_cast<const float4 *>(dp + 4);
+        const float *dp = sD + ((y + 2) * IW + (x + 2)) * COUT;
         const float v = sIn[((y + ky) * IW + (x + kx)) * CIN + ci];
-        gw[0] = fmaf(v, ga.x, gw[0]); gw[1] = fmaf(v, ga.y, gw[1]); gw[2] = fmaf(v, ga.z, gw[2]); gw[3] = fmaf(v, ga.w, gw[3]);
-        gw[4] = fmaf(v, gq.x, gw[4]); gw[5] = fmaf(v, gq.y, gw[5]); gw[6] = fmaf(v, gq.z, gw[6]); gw[7] = fmaf(v, gq.w, gw[7]);
+#pragma unroll
+        for (int u = 0; u < CV; ++u) {
+          const float4 g4 = *reinterpret_cast<const float4 *>(dp + 4 * u);
+          gw[4 * u + 0] = fmaf(v, g4.x, gw[4 * u + 0]); gw[4 * u + 1] = fmaf(v, g4.y, gw[4 * u + 1]);
+          gw[4 * u + 2] = fmaf(v, g4.z, gw[4 * u + 2]); gw[4 * u + 3] = fmaf(v, g4.w, gw[4 * u + 3]);
+        }
       }
     } else if (tap) {  // (first layer: no dense tile) the same sum over the pooled elements and their argmax positions
       for (int pp = group; pp < NPIX; pp += NG) {
         const int py = pp / PW, px = pp - py * PW;
-        const float4 ga = *reinterpret_cast<const float4 *>(sG + pp * kCout), gq = *reinterpret_cast<const float4 *>(sG + pp * kCout + 4);
-        const float g[kCout] = {ga.x, ga.y, ga.z, ga.w, gq.x, gq.y, gq.z, gq.w};
-        if (POOL) {
-          const uint2 pk = *reinterpret_cast<const uint2 *>(sA + pp * kCout);
 #pragma unroll
-          for (int co = 0; co < kCout; ++co) {
-            const unsigned a = ((co < 4 ? pk.x : pk.y) >> (8 * (co & 3))) & 3u;
-            const float v = sIn[((2 * py + (a >> 1) + ky) * IW + (2 * px + (a & 1) + kx)) * CIN + ci];
-            gw[co] = fmaf(v, g[co], gw[co]);
+        for (int u = 0; u < CV; ++u) {
+          const float4 g4 = *reinterpret_cast<const float4 *>(sG + pp * COUT + 4 * u);
+          const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+          const uint32_t pk = POOL ? *reinterpret_cast<const uint32_t *>(sA + pp * COUT + 4 * u) : 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned a = (pk >> (8 * j)) & 3u;
+            const float v = POOL ? sIn[((2 * py + (a >> 1) + ky) * IW + (2 * px + (a & 1) + kx)) * CIN + ci]
+                                 : sIn[((py + ky) * IW + (px + kx)) * CIN + ci];
+            gw[4 * u + j] = fmaf(v, g[j], gw[4 * u + j]);
           }
-        } else {
-          const float v = sIn[((py + ky) * IW + (px + kx)) * CIN + ci];
-#pragma unroll
-          for (int co = 0; co < kCout; ++co) gw[co] = fmaf(v, g[co], gw[co]);
         }
       }
     } else if (isb) {
       const int co = lt - 25 * CIN;
-      for (int pp = group; pp < NPIX; pp += NG) gb += sG[pp * kCout + co];
+      for (int pp = group; pp < NPIX; pp += NG) gb += sG[pp * COUT + co];
     }
     if (NEED_DX) {  // d(in)[y][x][ci] = sum_{ky,kx,co} d(conv)[y+2-ky][x+2-kx][co] * W[ky][kx][ci][co]
       for (int p = tid; p < H * W; p += THREADS) {
@@ -207,16 +212,17 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll 1
         for (int t = 0; t < 25; ++t) {
           const int ty = t / 5, tx = t - ty * 5;
-          const float *dp = sD + ((y + 4 - ty) * IW + (x + 4 - tx)) * kCout;
-          const float4 da = *reinterpret_cast<const float4 *>(dp), db = *reinterpret_cast<const float4 *>(dp + 4);
+          const float *dp = sD + ((y + 4 - ty) * IW + (x + 4 - tx)) * COUT;
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) {
-            const float4 wa = *reinterpret_cast<const float4 *>(sW + (t * CIN + c) * kCout);
-            const float4 wb = *reinterpret_cast<const float4 *>(sW + (t * CIN + c) * kCout + 4);
-            float s = acc[c];
-            s = fmaf(da.x, wa.x, s); s = fmaf(da.y, wa.y, s); s = fmaf(da.z, wa.z, s); s = fmaf(da.w, wa.w, s);
-            s = fmaf(db.x, wb.x, s); s = fmaf(db.y, wb.y, s); s = fmaf(db.z, wb.z, s); s = fmaf(db.w, wb.w, s);
-            acc[c] = s;
+          for (int u = 0; u < CV; ++u) {
+            const float4 d4 = *reinterpret_cast<const float4 *>(dp + 4 * u);
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+              const float4 w4 = *reinterpret_cast<const float4 *>(sW + (t * CIN + c) * COUT + 4 * u);
+              float sacc = acc[c];
+              sacc = fmaf(d4.x, w4.x, sacc); sacc = fmaf(d4.y, w4.y, sacc); sacc = fmaf(d4.z, w4.z, sacc); sacc = fmaf(d4.w, w4.w, sacc);
+              acc[c] = sacc;
+            }
           }
         }
         float *o = din + (b * H * W + p) * CIN;
@@ -225,22 +231,22 @@ __global__ void __launch_bounds__(THREADS)
       }
     }
   }
-  float *part = partials + (static_cast<int64_t>(blockIdx.x) * NG + group) * (25 * CIN * kCout + kCout);
+  float *part = partials + (static_cast<int64_t>(blockIdx.x) * NG + group) * (25 * CIN * COUT + COUT);
   if (tap) {
 #pragma unroll
-    for (int co = 0; co < kCout; ++co) part[lt * kCout + co] = gw[co];  // HWIO order: ((ky*5+kx)*CIN+ci)*8+co
+    for (int co = 0; co < COUT; ++co) part[lt * COUT + co] = gw[co];  // HWIO order: ((ky*5+kx)*CIN+ci)*COUT+co
   } else if (isb) {
-    part[25 * CIN * kCout + (lt - 25 * CIN)] = gb;
+    part[25 * CIN * COUT + (lt - 25 * CIN)] = gb;
   }
 }
 
 static int conv_bwd_ctas(int64_t B) { return static_cast<int>(std::min<int64_t>(B, static_cast<int64_t>(sm_count()) * 4)); }
 
-template <int CIN, int H, int W, bool POOL, int THREADS>
+template <int CIN, int COUT, int H, int W, bool POOL, int THREADS>
 static int launch_conv_fwd(const float *in, const float *w, const float *bias, float *out, uint8_t *arg, int64_t B,
                            cudaStream_t s) {
-  auto kern = conv5x5_fwd_k<CIN, H, W, POOL, THREADS>;
-  constexpr size_t smem = conv_fwd_smem<CIN, H, W, POOL>();
+  auto kern = conv5x5_fwd_k<CIN, COUT, H, W, POOL, THREADS>;
+  constexpr size_t smem = conv_fwd_smem<CIN, COUT, H, W, POOL>();
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(conv5x5_fwd): %s", cudaGetErrorString(e));
@@ -250,11 +256,12 @@ static int launch_conv_fwd(const float *in, const float *w, const float *bias, f
   return check_launch("conv5x5_fwd");
 }
 
-template <int CIN, int H, int W, bool POOL, bool NEED_DX, int THREADS, int GS>
+template <int CIN, int COUT, int H, int W, bool POOL, bool NEED_DX, int THREADS, int GS>
 static int launch_conv_bwd(const float *in, const float *w, const float *out, const uint8_t *arg, const float *dout,
                            float *din, float *dw, float *db, int accumulate, float *workspace, int64_t B, cudaStream_t s) {
-  auto kern = conv5x5_bwd_k<CIN, H, W, POOL, NEED_DX, THREADS, GS>;
-  constexpr size_t smem = conv_bwd_smem<CIN, H, W, POOL, NEED_DX>();
+  auto kern = conv5x5_bwd_k<CIN, COUT, H, W, POOL, NEED_DX, THREADS, GS>;
+  constexpr size_t smem = conv_bwd_smem<CIN, COUT, H, W, POOL, NEED_DX>();
+  static_assert(smem <= 220 * 1024, "the layer's tiles must fit the shared memory of one SM");
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     AIR_REQUIRE(e == cudaSuccess, AIR_ERR_CUDA, "cudaFuncSetAttribute(conv5x5_bwd): %s", cudaGetErrorString(e));
@@ -272,12 +279,35 @@ static int launch_conv_bwd(const float *in, const float *w, const float *out, co
   count_launch();
   int rc = check_launch("conv5x5_bwd");
   if (rc) return rc;
-  const int nw = 25 * CIN * kCout;
-  rc = reduce_rows_launch(workspace, R, nw + kCout, nw, dw, accumulate, s);
+  const int nw = 25 * CIN * COUT;
+  rc = reduce_rows_launch(workspace, R, nw + COUT, nw, dw, accumulate, s);
   if (rc) return rc;
-  rc = reduce_rows_launch(workspace + nw, R, nw + kCout, kCout, db, accumulate, s);
+  rc = reduce_rows_launch(workspace + nw, R, nw + COUT, COUT, db, accumulate, s);
   if (rc) return rc;
   return check_launch("conv5x5_bwd reduce");
+}
+
+// the three layers of air_model.py:510-535 for F = cnn_filters output channels (conv2 / conv3 have F input channels)
+template <int F, int T2, int GS2>
+static int conv_fwd_dispatch(const float *in, const float *w, const float *bias, float *out, uint8_t *argmax, int64_t B, int H,
+                             int W, int cin, int pool, cudaStream_t s) {
+  if (cin == 1 && H == 50 && W == 50 && pool) return launch_conv_fwd<1, F, 50, 50, true, 256>(in, w, bias, out, argmax, B, s);
+  if (cin == F && H == 25 && W == 25 && pool) return launch_conv_fwd<F, F, 25, 25, true, 160>(in, w, bias, out, argmax, B, s);
+  if (cin == F && H == 12 && W == 12 && !pool) return launch_conv_fwd<F, F, 12, 12, false, 160>(in, w, bias, out, argmax, B, s);
+  return AIR_ERR_UNSUPPORTED;
+}
+
+template <int F, int T2, int GS2>
+static int conv_bwd_dispatch(const float *in, const float *w, const float *out, const uint8_t *argmax, const float *dout,
+                             float *din, float *dw, float *db, int accumulate, float *workspace, int64_t B, int H, int W, int cin,
+                             int pool, cudaStream_t s) {
+  if (cin == 1 && H == 50 && W == 50 && pool && !din)
+    return launch_conv_bwd<1, F, 50, 50, true, false, 256, 64>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, s);
+  if (cin == F && H == 25 && W == 25 && pool && din)
+    return launch_conv_bwd<F, F, 25, 25, true, true, T2, GS2>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, s);
+  if (cin == F && H == 12 && W == 12 && !pool && din)
+    return launch_conv_bwd<F, F, 12, 12, false, true, T2, GS2>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, s);
+  return AIR_ERR_UNSUPPORTED;
 }
 
 }  // namespace air
@@ -292,11 +322,14 @@ extern "C" int air_conv5x5_fwd(const float *in, const float *w, const float *bia
   AIR_REQUIRE(aligned16(out) && (!pool || (reinterpret_cast<uintptr_t>(argmax) & 7u) == 0), AIR_ERR_UNSUPPORTED,
               "conv5x5_fwd: out must be 16-byte and argmax 8-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cout == 8 && cin == 1 && H == 50 && W == 50 && pool) return launch_conv_fwd<1, 50, 50, true, 256>(in, w, bias, out, argmax, B, s);
-  if (cout == 8 && cin == 8 && H == 25 && W == 25 && pool) return launch_conv_fwd<8, 25, 25, true, 160>(in, w, bias, out, argmax, B, s);
-  if (cout == 8 && cin == 8 && H == 12 && W == 12 && !pool) return launch_conv_fwd<8, 12, 12, false, 160>(in, w, bias, out, argmax, B, s);
-  set_error("conv5x5_fwd: only the three layers of air_model.py:510-535 are built (cin=%d cout=%d %dx%d pool=%d)", cin, cout, H, W, pool);
-  return AIR_ERR_UNSUPPORTED;
+  int rc = AIR_ERR_UNSUPPORTED;
+  if (cout == 8) rc = conv_fwd_dispatch<8, 256, 256>(in, w, bias, out, argmax, B, H, W, cin, pool, s);
+  else if (cout == 4) rc = conv_fwd_dispatch<4, 256, 128>(in, w, bias, out, argmax, B, H, W, cin, pool, s);
+  else if (cout == 16) rc = conv_fwd_dispatch<16, 512, 512>(in, w, bias, out, argmax, B, H, W, cin, pool, s);
+  if (rc == AIR_ERR_UNSUPPORTED)
+    set_error("conv5x5_fwd: only the three layers of air_model.py:510-535 are built, for 4, 8 or 16 filters "
+              "(cin=%d cout=%d %dx%d pool=%d)", cin, cout, H, W, pool);
+  return rc;
 }
 
 extern "C" int64_t air_conv5x5_bwd_workspace(int64_t B, int cin, int cout) {
@@ -310,13 +343,12 @@ extern "C" int air_conv5x5_bwd(const float *in, const float *w, const float *out
   if (B == 0) return AIR_OK;
   AIR_REQUIRE(in && w && out && dout && dw && db && workspace && (!pool || argmax), AIR_ERR_NULL, "conv5x5_bwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cout == 8 && cin == 1 && H == 50 && W == 50 && pool && !din)
-    return launch_conv_bwd<1, 50, 50, true, false, 256, 64>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, s);
-  if (cout == 8 && cin == 8 && H == 25 && W == 25 && pool && din)
-    return launch_conv_bwd<8, 25, 25, true, true, 256, 256>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, s);
-  if (cout == 8 && cin == 8 && H == 12 && W == 12 && !pool && din)
-    return launch_conv_bwd<8, 12, 12, false, true, 256, 256>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, s);
-  set_error("conv5x5_bwd: only the three layers of air_model.py:510-535 are built (cin=%d cout=%d %dx%d pool=%d din=%d)", cin,
-            cout, H, W, pool, din != nullptr);
-  return AIR_ERR_UNSUPPORTED;
+  int rc = AIR_ERR_UNSUPPORTED;
+  if (cout == 8) rc = conv_bwd_dispatch<8, 256, 256>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, H, W, cin, pool, s);
+  else if (cout == 4) rc = conv_bwd_dispatch<4, 256, 128>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, H, W, cin, pool, s);
+  else if (cout == 16) rc = conv_bwd_dispatch<16, 512, 512>(in, w, out, argmax, dout, din, dw, db, accumulate, workspace, B, H, W, cin, pool, s);
+  if (rc == AIR_ERR_UNSUPPORTED)
+    set_error("conv5x5_bwd: only the three layers of air_model.py:510-535 are built, for 4, 8 or 16 filters "
+              "(cin=%d cout=%d %dx%d pool=%d din=%d)", cin, cout, H, W, pool, din != nullptr);
+  return rc;
 }
