@@ -2,10 +2,13 @@
 reference README's "98 % after ~25k iterations" claim, there on multi-MNIST) -- the GPU counterpart of
 oracle/train_convergence.py, with the reference's training configuration (training.py:100-122, batch 64).
 
-    python examples/train_synthetic.py --iters 25000 --gemm tf32x3 --log profiles/r2_gpu_convergence_tf32x3.log
+    python examples/train_synthetic.py --iters 25000 --gemm tf32x3 --seed 3 --log run.log     # 25k iterations: ~18 s on a B200
 
-Logs of round 2's runs (3xTF32 and plain TF32 GEMM modes) are in profiles/r2_gpu_convergence_*.log, next to the CPU
-oracle's profiles/r1_oracle_convergence.log.
+The model is built with reference_rounding=True (default): the write-back backward sums the un-cancelled fp32 corner
+terms the reference's training depends on (--clean-gradient shows what happens without them: loss ~1900 for ever).
+Whether a run settles on the right digit COUNT is a seed lottery in the reference's arithmetic (5 of 12 seeds reach
+>= 95 %, the CPU oracle 2 of 3); logs of round 2's runs: profiles/r2_reference_rounding/gpu_training_*.log, next to the CPU
+oracle's profiles/r1_oracle_convergence.log; the story: profiles/r2_reference_rounding.md.
 """
 import argparse
 import os
