@@ -526,6 +526,10 @@ def main():
             except Exception as e:
                 line["inference_c5"] = {"error": str(e)[:200]}
             if not args.no_convergence:
+                if os.environ.get("AIR_BENCH_CONV_INPROC", "0") != "0":   # diagnostics: the same runs inside this process
+                    line["training_convergence"] = training_convergence(iters=int(os.environ.get("AIR_BENCH_CONV_ITERS", "25000")))
+                    print(json.dumps(line), flush=True)
+                    return 0
                 try:  # does the step being timed LEARN?  (the reference's configs[0] schedule, batch 64, 25k iterations: ~18 s per seed)
                     # in a fresh process: the run is independent of whatever the measurements above left behind (graphs,
                     # allocator pools), and a failure there cannot take the bench line with it

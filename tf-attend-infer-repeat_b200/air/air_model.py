@@ -570,11 +570,23 @@ class AIRModel:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         # thread_local: other host threads (NCCL's watchdog, a data-feeding thread, a clock sampler) may touch the CUDA API
-        # while this thread captures; only this thread's calls belong to the graph
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            self._draw_noise(); self._forward()
-            if self.train:
-                self._backward(); self._apply_gradients()
+        # while this thread captures; only this thread's calls belong to the graph.
+        # The garbage collector stays off while capturing: a collection that happens to run inside the capture can free
+        # pinned host buffers or multi-stream tensors of models dropped earlier (AIRModel holds reference cycles), and the
+        # allocators then record / query events on other streams -- calls that invalidate the capture ("operation not
+        # permitted when stream is capturing"; seen in bench.py after the train / inference measurements).
+        import gc
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._draw_noise(); self._forward()
+                if self.train:
+                    self._backward(); self._apply_gradients()
+        finally:
+            if gc_was_on:
+                gc.enable()
         self._graphs = g
         self._publish()
         return self
