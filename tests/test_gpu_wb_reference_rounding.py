@@ -215,6 +215,8 @@ def test_training_needs_the_reference_rounding():
         m = ab.AIRModel(train[:64].clone(), cnt[:64].clone(), train=True, annealing_schedules=data.TRAINING_ANNEALING,
                         gemm_mode="tf32x3", seed=0, reference_rounding=ref, **data.TRAINING_HYPER)
         m.capture()
+        import gc
+        assert gc.isenabled()     # (capture() keeps the collector off only while the graph is being recorded)
         g = torch.Generator(device=DEV).manual_seed(1)
         tot = torch.zeros((), device=DEV)
         for it in range(6000):
