@@ -111,7 +111,11 @@ int air_st_writeback_canvas_fwd_steps(const float *windows, const float *theta_i
  *                              such pixels are skipped as the exact zeros they are on paper (the fp64 gradient).  Per
  *                              pixel the arithmetic is the graph's own (dz, dtheta_inv: all six entries); the order in
  *                              which dwindow accumulates over pixels (unspecified in the reference: UnsortedSegmentSum)
- *                              is fixed and deterministic.  28x28 windows on 50x50 canvases, dz required. */
+ *                              is fixed and deterministic for 28x28 windows on 50x50 canvases with an axis-aligned
+ *                              theta_inv of positive scale (the model's case; dz and a 16-byte aligned dwindow
+ *                              required for that kernel); any other size or theta takes the same per-pixel
+ *                              arithmetic with shared-memory atomics for dwindow (order not fixed, like the
+ *                              reference on a GPU). */
 #define AIR_WB_SIGMOID_WINDOW 1
 #define AIR_WB_AXIS_ALIGNED_THETA 2
 #define AIR_WB_REFERENCE_ROUNDING 4
