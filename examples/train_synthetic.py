@@ -7,7 +7,7 @@ oracle/train_convergence.py, with the reference's training configuration (traini
 The model is built with reference_rounding=True (default): the write-back backward sums the un-cancelled fp32 corner
 terms the reference's training depends on (--clean-gradient shows what happens without them: loss ~1900 for ever).
 Whether a run settles on the right digit COUNT is a seed lottery in the reference's arithmetic (5 of 12 seeds reach
->= 95 %, the CPU oracle 2 of 3); logs of round 2's runs: profiles/r2_reference_rounding/gpu_training_*.log, next to the CPU
+>= 95 %, the CPU oracle 2 of 5); logs of round 2's runs: profiles/r2_reference_rounding/gpu_training_*.log, next to the CPU
 oracle's profiles/r1_oracle_convergence.log; the story: profiles/r2_reference_rounding.md.
 """
 import argparse
